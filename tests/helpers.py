@@ -1,0 +1,38 @@
+"""Shared helpers for the test-suite (oracle access, fixture weights, golden vectors)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from tcvom_b200 import synthetic  # noqa: E402
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def key_table():
+    with open(os.path.join(GOLDEN, "vmn_gca_keys.json")) as f:
+        return json.load(f)
+
+
+_SD = {}
+
+
+def fixture_sd():
+    """The calibrated fixture checkpoint (584 keys, CPU fp32)."""
+    if "sd" not in _SD:
+        shapes = {k: tuple(s) for k, s in key_table()["state_dict"]}
+        _SD["sd"] = synthetic.fixture_state_dict(shapes, 0)
+    return _SD["sd"]
+
+
+def op_inputs(tag, shape, seed=11):
+    return synthetic._rng(tag, seed).standard_normal(size=shape).astype(np.float32)
