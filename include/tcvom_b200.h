@@ -1,0 +1,162 @@
+/* tcvom_b200 -- C ABI of the B200 (sm_100a) kernels behind TCVOM's GCA+TAM hot path.
+ *
+ * Every entry point takes plain device pointers, explicit dimensions and a CUDA stream
+ * (pass torch.cuda.current_stream().cuda_stream); returns 0 on success or a negative
+ * error code (never throws, never exits); tcv_last_error() returns the message for the
+ * calling thread.  The library owns no device memory: all workspaces are passed in.
+ *
+ * Data layout ("split-bf16 NHWC"): an activation tensor [N,H,W,C] is stored as two bf16
+ * planes, hi at `base` and lo at `base + N*H*W*C` (elements), value = float(hi)+float(lo).
+ * Boundary tensors that the reference exposes (images, trimaps, alpha, TAM logits) are
+ * fp32 in the reference's own layouts.
+ *
+ * Reference interfaces replaced (reference checkout, commit f5fa07a):
+ *   tcv_preprocess_eval   models/model.py:360-387   EvalModel.preprocess
+ *   tcv_postprocess_eval  models/model.py:413-424   EvalModel.forward tail (where/compositing)
+ *   tcv_sn_fold_pack      models/GCA/ops.py:38-45   SpectralNorm._noupdate_u_v (W_bar / u^T W v)
+ *   tcv_conv2d            nn.Conv2d / nn.ConvTranspose2d + BatchNorm2d + ReLU/LeakyReLU/+residual
+ *                         call sites: GCA/encoders/resnet_enc.py:33-49,129-145,
+ *                         res_gca_enc.py:20-33,47-55,57-90, GCA/decoders/resnet_dec.py:43-59,
+ *                         VMN/VMN_GCA.py:26-49, VMN/VMN_model.py:13-15
+ *   tcv_avgpool2          nn.AvgPool2d(2,2)          resnet_enc.py:112
+ *   tcv_gca_*             models/GCA/ops.py:106-229  GuidedCxtAtten.forward
+ *   tcv_tam_attend        models/VMN/VMN_model.py:18-68  FeatureAggregationModule.forward
+ *   tcv_nchw_to_split / tcv_split_to_nchw   layout adapters for the operator seams
+ */
+#ifndef TCVOM_B200_H
+#define TCVOM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* tcv_stream_t; /* cudaStream_t */
+
+#define TCV_OK 0
+#define TCV_ERR_INVALID (-1)
+#define TCV_ERR_CUDA (-2)
+#define TCV_ERR_UNSUPPORTED (-3)
+
+#define TCV_ACT_NONE 0
+#define TCV_ACT_RELU 1
+#define TCV_ACT_LEAKY02 2
+#define TCV_ACT_TANH01 3 /* (tanh(x)+1)/2 -- VMN_GCA.py:47 */
+
+#define TCV_PAD_ZERO 0
+#define TCV_PAD_REFLECT 1
+
+#define TCV_MAX_TAPS 16
+
+int tcv_version(void);
+const char* tcv_last_error(void);
+/* number of kernels launched by this library since load (for bench.py's gpu_launches) */
+long long tcv_launch_count(void);
+
+/* Generic gather-form convolution with fused epilogue.
+ *   out[n, gy*oy_mul+oy_off, gx*ox_mul+ox_off, co] = epi( sum_t sum_ci
+ *        in[n, gy*stride+dy[t], gx*stride+dx[t], ci] * w[wtap[t]][ci][co] )
+ *   epi(a) : t = a*s1[co]+b1[co]; t += res1[n, oy>>res1_shift, ox>>res1_shift, co];
+ *            t = act(t); t = t*s2[co]+b2[co]; t += res2[n,oy,ox,co]
+ * An ordinary conv has gh=oh, gw=ow, oy_mul=1; one phase of the 4x4/stride-2 transposed conv
+ * has gh=ih, gw=iw, oy_mul=2, oy_off=phase and 4 taps.  Null s1/b1/s2/b2/res* are skipped. */
+typedef struct {
+  const void* x;      /* split-bf16 NHWC [n, ih, iw, cin]                                  */
+  long long x_plane;  /* elements between the hi and lo plane of x (0: n*ih*iw*cin)          */
+  long long x_img_stride; /* elements between consecutive images of x (0: ih*iw*cin)         */
+  int n, ih, iw, cin; /* cin multiple of 8                                                   */
+  const float* w;     /* fp32 [wtaps][cin][cout] (wtaps >= max(wtap)+1)                      */
+  int ntaps;
+  int dy[TCV_MAX_TAPS], dx[TCV_MAX_TAPS];
+  int wtap[TCV_MAX_TAPS]; /* weight slice used by tap t (identity for an ordinary conv)      */
+  int stride;
+  int pad_mode;
+  void* y;            /* split-bf16 NHWC [n, oh, ow, cout] (may be null if y_f32 is given)   */
+  float* y_f32;       /* optional fp32 NHWC copy of the output                               */
+  int oh, ow, cout;
+  int gh, gw;
+  int oy_mul, oy_off, ox_mul, ox_off;
+  const float* s1;
+  const float* b1;
+  const void* res1;   /* split-bf16 NHWC [n, oh>>res1_shift, ow>>res1_shift, cout]           */
+  long long res1_plane; /* elements between hi and lo plane of res1 (0: contiguous default)  */
+  int res1_shift;
+  int act;
+  const float* s2;
+  const float* b2;
+  const void* res2;   /* split-bf16 NHWC [n, oh, ow, cout]                                   */
+  long long res2_plane; /* elements between hi and lo plane of res2 (0: contiguous default)  */
+} tcv_conv_desc;
+
+int tcv_conv2d(const tcv_conv_desc* d, tcv_stream_t stream);
+
+/* sigma = u^T W v  (W viewed [rows, cols], rows = w_bar.shape[0]); then packs W/sigma into the
+ * kernel layout fp32 [ntaps][cin_pad][cout].  `transposed` != 0: w_bar is [cin,cout,kh,kw]
+ * (ConvTranspose2d), else [cout,cin,kh,kw].  u == NULL: plain conv weight (sigma = 1).
+ * Tap order in the packed tensor is (kh, kw) raster.  sigma_out (1 float, device) optional. */
+int tcv_sn_fold_pack(const float* w_bar, const float* u, const float* v, int cout, int cin, int kh,
+                     int kw, int transposed, int cin_pad, float* packed, float* sigma_out,
+                     tcv_stream_t stream);
+
+/* scale = gamma / sqrt(var+eps), shift = beta - mean*scale (eval BatchNorm2d as an affine) */
+int tcv_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                int c, float* scale, float* shift, tcv_stream_t stream);
+
+/* EvalModel.preprocess.  imgs fp32 [F,3,H,W] BGR 0..255, tris fp32 [F,1,H,W].
+ * x8: split-bf16 NHWC [F,H,W,8] = (normalised RGB, one-hot{bg,unknown,fg}, 0, 0);
+ * trimask: fp32 [F,H,W] (0/1).  dilate <= 0: no dilation; else max-pool radius; tmp = 2*F*H*W bytes. */
+int tcv_preprocess_eval(const float* imgs, const float* tris, int frames, int h, int w, int dilate,
+                        void* x8, float* trimask, uint8_t* tmp, tcv_stream_t stream);
+
+/* alpha[f] = trimask ? pred : tri/255 for inner frames, 0 for the first/last frame of each
+ * sample.  pred fp32 [B,H,W] (centre frames only when S==3: index b*(S-2)+(s-1)). */
+int tcv_postprocess_eval(const float* pred, const float* tris, const float* trimask, int batch,
+                         int frames, int h, int w, float* alphas, tcv_stream_t stream);
+
+int tcv_avgpool2(const void* x, int n, int h, int w, int c, void* y, tcv_stream_t stream);
+
+/* unknown[n, y, x] = x8[n, y*8, x*8, channel 4]  (res_gca_enc.py:71) ; fp32 [n, h/8, w/8] */
+int tcv_unknown_os8(const void* x8, int n, int h, int w, float* unknown, tcv_stream_t stream);
+
+/* ---- guided contextual attention (GCA/ops.py:106-229), per image, P = (h/2)*(w/2) patches,
+ * h,w = OS8 feature size, P_pad = P rounded up to 64.
+ *  prep:    g split-bf16 [n,h/2,w/2,64] (guidance_conv output at stride 2), unknown fp32 [n,h,w]
+ *           -> Q fp32 [n,P,576], Kn fp32 [n,P,576] (= Q/max(|Q|,1e-4) * per-key scale),
+ *              mm fp32 [n,P] ; scales fp32 [n,2] = (unknown_scale, known_scale)
+ *  values:  feat split-bf16 [n,h,w,128] -> Vt fp32 [n,2048,P_pad]  (row = (ty*4+tx)*128+c)
+ *  softmax: S fp32 [n,P,P_pad] in place: P = softmax_p(S - 1e4*[q==p]*mm[p]), pad cols = 0
+ *  fold:    O fp32 [n,P,2048] -> Y split-bf16 [n,h,w,128] = fold(O; k4,s2,p1)/4            */
+int tcv_gca_prep(const void* g, const float* unknown, int n, int h, int w, float* Q, float* Kn,
+                 float* mm, float* scales, tcv_stream_t stream);
+int tcv_gca_values(const void* feat, int n, int h, int w, float* Vt, tcv_stream_t stream);
+int tcv_gca_softmax(float* S, const float* mm, int n, int P, int P_pad, tcv_stream_t stream);
+int tcv_gca_fold(const float* O, int n, int h, int w, void* Y, tcv_stream_t stream);
+
+/* C[b] = A[b] * B[b]^T, fp32 row-major, A [M,K] lda, B [N,K] ldb, C [M,N] ldc, K % 8 == 0,
+ * batch strides in elements. */
+int tcv_gemm_tn_f32(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb,
+                    int ldc, long long strideA, long long strideB, long long strideC, int batch,
+                    tcv_stream_t stream);
+
+/* ---- temporal attention module core (VMN_model.py:27-68) after the q/k/v convolutions.
+ * q, v, kb, kf: split-bf16 NHWC [B,H,W,C] (contiguous); mask fp32 full resolution
+ * [mh,mw] per sample with per-sample stride mask_stride (elements), sampled at
+ * (y*mh/H, x*mw/W) (nearest, VMN_model.py:22).
+ * out split-bf16 [B,H,W,C] = v + m*(agg_b+agg_f); attb/attf fp32 [B,win*win,H*W] raw scaled
+ * logits zeroed outside the mask; small_mask uint8 [B,H,W]. */
+int tcv_tam_attend(const void* q, const void* v, const void* kb, const void* kf, const float* mask,
+                   long long mask_stride, int mh, int mw, int batch, int h, int w, int c, int window,
+                   void* out, float* attb, float* attf, uint8_t* small_mask, tcv_stream_t stream);
+
+/* layout adapters for the operator-level seams (fp32 NCHW <-> split-bf16 NHWC, c_pad >= c);
+ * plane = elements between the hi and lo plane of the split tensor (0: n*h*w*c_pad) */
+int tcv_nchw_to_split(const float* x, int n, int c, int h, int w, int c_pad, void* y, long long y_plane,
+                      tcv_stream_t stream);
+int tcv_split_to_nchw(const void* x, int n, int c, int h, int w, int c_pad, long long x_plane, float* y,
+                      tcv_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,99 @@
+"""ctypes binding of ``libtcvom_b200.so`` (the C ABI declared in ``include/tcvom_b200.h``).
+
+The library is built in-tree by ``tcvom_b200/csrc/build.sh`` (or ``__graft_entry__.build()``).
+Loading is lazy and does NOT touch CUDA, so that ``pred_test.py``-style ``fork`` after import
+stays legal.  There is no fallback: if the library is missing or a call fails, a
+``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtcvom_b200.so")
+
+ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_TANH01 = 0, 1, 2, 3
+PAD_ZERO, PAD_REFLECT = 0, 1
+MAX_TAPS = 16
+
+c_void_p, c_int, c_ll, c_float = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+
+
+class ConvDesc(C.Structure):
+    """Mirror of ``tcv_conv_desc``."""
+    _fields_ = [
+        ("x", c_void_p), ("x_plane", c_ll), ("x_img_stride", c_ll),
+        ("n", c_int), ("ih", c_int), ("iw", c_int), ("cin", c_int),
+        ("w", c_void_p), ("ntaps", c_int), ("dy", c_int * MAX_TAPS), ("dx", c_int * MAX_TAPS),
+        ("wtap", c_int * MAX_TAPS),
+        ("stride", c_int), ("pad_mode", c_int),
+        ("y", c_void_p), ("y_f32", c_void_p),
+        ("oh", c_int), ("ow", c_int), ("cout", c_int), ("gh", c_int), ("gw", c_int),
+        ("oy_mul", c_int), ("oy_off", c_int), ("ox_mul", c_int), ("ox_off", c_int),
+        ("s1", c_void_p), ("b1", c_void_p), ("res1", c_void_p), ("res1_plane", c_ll),
+        ("res1_shift", c_int), ("act", c_int),
+        ("s2", c_void_p), ("b2", c_void_p), ("res2", c_void_p), ("res2_plane", c_ll),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/tcvom_b200.h declares
+SIGNATURES = {
+    "tcv_version": (c_int, []),
+    "tcv_last_error": (C.c_char_p, []),
+    "tcv_launch_count": (c_ll, []),
+    "tcv_conv2d": (c_int, [C.POINTER(ConvDesc), c_void_p]),
+    "tcv_sn_fold_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_void_p, c_void_p, c_void_p]),
+    "tcv_bn_fold": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_void_p]),
+    "tcv_preprocess_eval": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                    c_void_p, c_void_p]),
+    "tcv_postprocess_eval": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                     c_void_p]),
+    "tcv_avgpool2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_unknown_os8": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_gca_prep": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_void_p]),
+    "tcv_gca_values": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_gca_softmax": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "tcv_gca_fold": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_gemm_tn_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                c_ll, c_ll, c_ll, c_int, c_void_p]),
+    "tcv_tam_attend": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int,
+                               c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tcv_nchw_to_split": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
+    "tcv_split_to_nchw": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_void_p, c_void_p]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib() -> C.CDLL:
+    """Loads the shared library once (thread-safe: nn.DataParallel calls from worker threads)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"tcvom_b200: native library not built ({LIB_PATH}); run "
+                        "`python -c 'import __graft_entry__ as g; g.build()'` or tcvom_b200/csrc/build.sh. "
+                        "There is no CPU/PyTorch fallback.")
+                L = C.CDLL(LIB_PATH)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(L, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = L
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().tcv_last_error().decode(errors="replace")
+        raise RuntimeError(f"tcvom_b200.{what} failed (rc={rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().tcv_launch_count())

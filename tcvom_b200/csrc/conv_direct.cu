@@ -1,0 +1,168 @@
+// CUDA-core gather-form convolution with fused epilogue (fp32 accumulate on split-bf16 NHWC).
+//
+// This is the general-shape path: small channel counts (3/6/16 -> N), the Cout=1 alpha head,
+// reflect padding, stride-2 and the 4 phases of the 4x4/stride-2 transposed conv.  These
+// layers are HBM-bound, so the kernel is organised around coalesced
+// NHWC access: one thread owns one output pixel and COT consecutive output channels, reads
+// its input pixels as 16-byte vectors (8 channels per plane) and receives the weights as
+// warp-wide shared-memory broadcasts.
+//
+// Replaces nn.Conv2d / nn.ConvTranspose2d + BatchNorm2d + activation + residual call sites,
+// see include/tcvom_b200.h (tcv_conv2d).
+#include "common.cuh"
+
+namespace tcv {
+
+constexpr int CIC = 32;  // input channels staged per weight chunk
+
+template <int COT>
+__global__ void __launch_bounds__(256) conv_direct_kernel(const tcv_conv_desc d) {
+  extern __shared__ float wsm[];  // [ntaps][CIC][COT]
+  const int cic = d.cin < CIC ? d.cin : CIC;
+  const int pix = blockIdx.x * 256 + threadIdx.x;
+  const int co0 = blockIdx.y * COT;
+  const int n = blockIdx.z;
+  const bool valid = pix < d.gh * d.gw;
+  const int gy = valid ? pix / d.gw : 0;
+  const int gx = valid ? pix - gy * d.gw : 0;
+  const long long xplane = d.x_plane;
+  const __nv_bfloat16* xin = reinterpret_cast<const __nv_bfloat16*>(d.x) + (long long)n * d.x_img_stride;
+
+  float acc[COT];
+#pragma unroll
+  for (int j = 0; j < COT; ++j) acc[j] = 0.f;
+
+  for (int ci0 = 0; ci0 < d.cin; ci0 += cic) {
+    __syncthreads();
+    const int chunk = d.ntaps * cic * COT;
+    for (int i = threadIdx.x; i < chunk; i += 256) {
+      const int j = i % COT;
+      const int c = (i / COT) % cic;
+      const int t = i / (COT * cic);
+      wsm[i] = d.w[((long long)d.wtap[t] * d.cin + ci0 + c) * d.cout + co0 + j];
+    }
+    __syncthreads();
+    if (!valid) continue;
+    for (int t = 0; t < d.ntaps; ++t) {
+      int iy = gy * d.stride + d.dy[t];
+      int ix = gx * d.stride + d.dx[t];
+      if (d.pad_mode == TCV_PAD_REFLECT) {
+        iy = reflect(iy, d.ih);
+        ix = reflect(ix, d.iw);
+      } else if (iy < 0 || iy >= d.ih || ix < 0 || ix >= d.iw) {
+        continue;
+      }
+      const __nv_bfloat16* p = xin + ((long long)iy * d.iw + ix) * d.cin + ci0;
+      const float* wt = wsm + t * cic * COT;
+      for (int c8 = 0; c8 < cic; c8 += 8) {
+        float f[8];
+        load8(p + c8, xplane, f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float xv = f[k];
+          const float* wp = wt + (c8 + k) * COT;
+          if (COT >= 4) {
+#pragma unroll
+            for (int j = 0; j < COT / 4; ++j) {
+              const float4 w4 = reinterpret_cast<const float4*>(wp)[j];
+              acc[4 * j + 0] = fmaf(xv, w4.x, acc[4 * j + 0]);
+              acc[4 * j + 1] = fmaf(xv, w4.y, acc[4 * j + 1]);
+              acc[4 * j + 2] = fmaf(xv, w4.z, acc[4 * j + 2]);
+              acc[4 * j + 3] = fmaf(xv, w4.w, acc[4 * j + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < COT; ++j) acc[j] = fmaf(xv, wp[j], acc[j]);
+          }
+        }
+      }
+    }
+  }
+  if (!valid) return;
+
+  // ---- fused epilogue
+  const int oy = gy * d.oy_mul + d.oy_off;
+  const int ox = gx * d.ox_mul + d.ox_off;
+  const long long oplane = (long long)d.n * d.oh * d.ow * d.cout;
+  const long long obase = (((long long)n * d.oh + oy) * d.ow + ox) * d.cout + co0;
+  if (d.s1) {
+#pragma unroll
+    for (int j = 0; j < COT; ++j) acc[j] = acc[j] * d.s1[co0 + j];
+  }
+  if (d.b1) {
+#pragma unroll
+    for (int j = 0; j < COT; ++j) acc[j] += d.b1[co0 + j];
+  }
+  if (d.res1) {
+    const int rh = d.oh >> d.res1_shift, rw = d.ow >> d.res1_shift;
+    const long long rplane = d.res1_plane;
+    const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(d.res1) +
+                             (((long long)n * rh + (oy >> d.res1_shift)) * rw + (ox >> d.res1_shift)) * d.cout + co0;
+    if (COT >= 8) {
+#pragma unroll
+      for (int j = 0; j < COT; j += 8) {
+        float f[8];
+        load8(r + j, rplane, f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[j + k] += f[k];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < COT; ++j) acc[j] += load1(r + j, rplane);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < COT; ++j) acc[j] = apply_act(acc[j], d.act);
+  if (d.s2) {
+#pragma unroll
+    for (int j = 0; j < COT; ++j) acc[j] = acc[j] * d.s2[co0 + j] + d.b2[co0 + j];
+  }
+  if (d.res2) {
+    const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(d.res2) + obase;
+    if (COT >= 8) {
+#pragma unroll
+      for (int j = 0; j < COT; j += 8) {
+        float f[8];
+        load8(r + j, d.res2_plane, f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[j + k] += f[k];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < COT; ++j) acc[j] += load1(r + j, d.res2_plane);
+    }
+  }
+  if (d.y) {
+    __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(d.y) + obase;
+    if (COT >= 8) {
+#pragma unroll
+      for (int j = 0; j < COT; j += 8) store8(y + j, oplane, acc + j);
+    } else {
+#pragma unroll
+      for (int j = 0; j < COT; ++j) store1(y + j, oplane, acc[j]);
+    }
+  }
+  if (d.y_f32) {
+    float* y = d.y_f32 + obase;
+#pragma unroll
+    for (int j = 0; j < COT; ++j) y[j] = acc[j];
+  }
+}
+
+template <int COT>
+static int launch_conv(const tcv_conv_desc& d, cudaStream_t st) {
+  const int cic = d.cin < CIC ? d.cin : CIC;
+  const size_t smem = (size_t)d.ntaps * cic * COT * sizeof(float);
+  dim3 grid((d.gh * d.gw + 255) / 256, d.cout / COT, d.n);
+  conv_direct_kernel<COT><<<grid, 256, smem, st>>>(d);
+  return launched("conv_direct_kernel");
+}
+
+int conv2d_direct(const tcv_conv_desc& d, cudaStream_t st) {
+  if (d.cout % 32 == 0) return launch_conv<32>(d, st);
+  if (d.cout % 16 == 0) return launch_conv<16>(d, st);
+  if (d.cout % 8 == 0) return launch_conv<8>(d, st);
+  return launch_conv<1>(d, st);
+}
+
+}  // namespace tcv

@@ -1,0 +1,233 @@
+// Guided contextual attention (models/GCA/ops.py:106-229) -- operand preparation, masked
+// softmax and overlap-add fold.  The two GEMMs (scores = Q.Kn^T, aggregation = P.Vt^T) run in
+// gemm_f32.cu (exact path) or gemm_tc.cu (tcgen05 path).
+//
+//   hh = h/2, ww = w/2 (OS16 grid), P = hh*ww patches, D = 9*64 = 576, DV = 16*128 = 2048.
+//   Q[p][(kh*3+kw)*64 + c]  = g_reflect[py+kh-1][px+kw-1][c]                    (ops.py:125-130)
+//   Kn[p]                   = Q[p] / max(|Q[p]|, 1e-4) * (mm[p] ? s_u : s_k)    (ops.py:174-175,186)
+//   mm[p]                   = any(unknown_os16 in the reflect 3x3 window of p)   (ops.py:148-156)
+//   Vt[(ty*4+tx)*128+c][p]  = feat_reflect[2py+ty-1][2px+tx-1][c]               (ops.py:112-118)
+// The (kh,kw,c) ordering of the 576/2048 axes differs from the reference's (c,kh,kw); inner
+// products and the fold are invariant to that permutation as long as both sides agree.
+#include "common.cuh"
+
+namespace tcv {
+
+constexpr int GC = 64;     // guidance channels after guidance_conv
+constexpr int FC = 128;    // alpha-feature channels
+constexpr int QD = 9 * GC; // 576
+constexpr int VD = 16 * FC;// 2048
+
+// scales[n] = (clamp(sqrt(um/(1-um)),0.1,10), clamp(sqrt((1-um)/um),0.1,10)), um = mean(unknown[::2,::2])
+__global__ void gca_scales_kernel(const float* __restrict__ unknown, int h, int w, float* __restrict__ scales) {
+  __shared__ float part[32];
+  const int n = blockIdx.x;
+  const int hh = h / 2, ww = w / 2;
+  const float* u = unknown + (long long)n * h * w;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < hh * ww; i += blockDim.x) {
+    const int y = i / ww, x = i - y * ww;
+    s += u[(2 * y) * w + 2 * x];
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) {
+      const float um = t / (float)(hh * ww);
+      const float km = 1.0f - um;
+      scales[2 * n + 0] = fminf(fmaxf(sqrtf(um / km), 0.1f), 10.f);
+      scales[2 * n + 1] = fminf(fmaxf(sqrtf(km / um), 0.1f), 10.f);
+    }
+  }
+}
+
+// one warp per patch
+__global__ void gca_prep_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ unknown, int n,
+                                int h, int w, const float* __restrict__ scales, float* __restrict__ Q,
+                                float* __restrict__ Kn, float* __restrict__ mm) {
+  const int hh = h / 2, ww = w / 2, P = hh * ww;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n * P) return;
+  const int img = warp / P, p = warp - img * P;
+  const int py = p / ww, px = p - py * ww;
+  const long long gplane = (long long)n * P * GC;
+  const __nv_bfloat16* gi = g + (long long)img * P * GC;
+  const float* u = unknown + (long long)img * h * w;
+
+  float q[18];  // 576 / 32 : lane owns 2 channels (2*lane, 2*lane+1) of each of the 9 taps
+  float ss = 0.f;
+  float usum = 0.f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int yy = reflect(py + t / 3 - 1, hh), xx = reflect(px + t % 3 - 1, ww);
+    const __nv_bfloat16* src = gi + ((long long)yy * ww + xx) * GC + 2 * lane;
+    const uint32_t a = *reinterpret_cast<const uint32_t*>(src);
+    const uint32_t b = *reinterpret_cast<const uint32_t*>(src + gplane);
+    q[2 * t] = __uint_as_float(a << 16) + __uint_as_float(b << 16);
+    q[2 * t + 1] = __uint_as_float(a & 0xffff0000u) + __uint_as_float(b & 0xffff0000u);
+    ss += q[2 * t] * q[2 * t] + q[2 * t + 1] * q[2 * t + 1];
+    usum += u[(2 * yy) * w + 2 * xx];
+  }
+  ss = warp_sum(ss);
+  const float m = usum > 0.f ? 1.f : 0.f;
+  const float scale = m > 0.f ? scales[2 * img] : scales[2 * img + 1];
+  const float inv = scale / fmaxf(sqrtf(ss), 1e-4f);
+  float* qo = Q + ((long long)img * P + p) * QD;
+  float* ko = Kn + ((long long)img * P + p) * QD;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    *reinterpret_cast<float2*>(qo + t * GC + 2 * lane) = make_float2(q[2 * t], q[2 * t + 1]);
+    *reinterpret_cast<float2*>(ko + t * GC + 2 * lane) = make_float2(q[2 * t] * inv, q[2 * t + 1] * inv);
+  }
+  if (lane == 0) mm[(long long)img * P + p] = m;
+}
+
+__global__ void gca_values_kernel(const __nv_bfloat16* __restrict__ feat, int n, int h, int w, int P_pad,
+                                  float* __restrict__ Vt) {
+  const int hh = h / 2, ww = w / 2, P = hh * ww;
+  const long long total = (long long)n * VD * P_pad;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int p = (int)(i % P_pad);
+  const int row = (int)((i / P_pad) % VD);
+  const int img = (int)(i / ((long long)P_pad * VD));
+  float v = 0.f;
+  if (p < P) {
+    const int c = row % FC, t = row / FC;
+    const int py = p / ww, px = p - py * ww;
+    const int yy = reflect(2 * py + t / 4 - 1, h), xx = reflect(2 * px + t % 4 - 1, w);
+    v = load1(feat + (((long long)img * h + yy) * w + xx) * FC + c, (long long)n * h * w * FC);
+  }
+  Vt[i] = v;
+}
+
+// one CTA per (row q, image): in-place masked softmax over keys
+__global__ void __launch_bounds__(256) gca_softmax_kernel(float* __restrict__ S, const float* __restrict__ mm, int P,
+                                                          int P_pad) {
+  __shared__ float red[32];
+  __shared__ float bcast;
+  const int q = blockIdx.x, img = blockIdx.y;
+  float* row = S + ((long long)img * P + q) * P_pad;
+  const float diag = -1e4f * mm[(long long)img * P + q];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float mx = -INFINITY;
+  for (int p = threadIdx.x; p < P; p += 256) {
+    float s = row[p];
+    if (p == q) s += diag;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (warp == 0) {
+    float t = lane < 8 ? red[lane] : -INFINITY;
+    t = warp_max(t);
+    if (lane == 0) bcast = t;
+  }
+  __syncthreads();
+  mx = bcast;
+  float sum = 0.f;
+  for (int p = threadIdx.x; p < P; p += 256) {
+    float s = row[p];
+    if (p == q) s += diag;
+    const float e = expf(s - mx);
+    row[p] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncthreads();
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  if (warp == 0) {
+    float t = lane < 8 ? red[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) bcast = t;
+  }
+  __syncthreads();
+  const float inv = 1.0f / bcast;
+  for (int p = threadIdx.x; p < P_pad; p += 256) row[p] = p < P ? row[p] * inv : 0.f;
+}
+
+// Y[y][x][c] = 1/4 * sum over (ty,tx) with (y+1-ty), (x+1-tx) even and in range of O[q][(ty*4+tx)*128+c]
+__global__ void gca_fold_kernel(const float* __restrict__ O, int n, int h, int w, __nv_bfloat16* __restrict__ Y) {
+  const int hh = h / 2, ww = w / 2, P = hh * ww;
+  const long long total = (long long)n * h * w * (FC / 4);
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % (FC / 4)) * 4;
+  long long t = i / (FC / 4);
+  const int x = (int)(t % w);
+  t /= w;
+  const int y = (int)(t % h);
+  const int img = (int)(t / h);
+  float acc[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int ty = ((y + 1) & 1) + 2 * a;
+    const int qy = (y + 1 - ty) / 2;
+    if (y + 1 - ty < 0 || qy >= hh) continue;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int tx = ((x + 1) & 1) + 2 * b;
+      const int qx = (x + 1 - tx) / 2;
+      if (x + 1 - tx < 0 || qx >= ww) continue;
+      const float4 o = *reinterpret_cast<const float4*>(O + ((long long)img * P + qy * ww + qx) * VD +
+                                                        (ty * 4 + tx) * FC + c);
+      acc[0] += o.x; acc[1] += o.y; acc[2] += o.z; acc[3] += o.w;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc[k] *= 0.25f;
+  store4(Y + (((long long)img * h + y) * w + x) * FC + c, (long long)n * h * w * FC, acc);
+}
+
+}  // namespace tcv
+
+using namespace tcv;
+
+extern "C" {
+
+int tcv_gca_prep(const void* g, const float* unknown, int n, int h, int w, float* Q, float* Kn, float* mm,
+                 float* scales, tcv_stream_t stream) {
+  TCV_REQUIRE(g && unknown && Q && Kn && mm && scales, "gca_prep: null pointer");
+  TCV_REQUIRE(n > 0 && h >= 4 && w >= 4 && h % 2 == 0 && w % 2 == 0, "gca_prep: h,w must be even and >= 4");
+  gca_scales_kernel<<<n, 256, 0, S(stream)>>>(unknown, h, w, scales);
+  int rc = launched("gca_scales_kernel");
+  if (rc) return rc;
+  const long long warps = (long long)n * (h / 2) * (w / 2);
+  gca_prep_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, S(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(g), unknown, n, h, w, scales, Q, Kn, mm);
+  return launched("gca_prep_kernel");
+}
+
+int tcv_gca_values(const void* feat, int n, int h, int w, float* Vt, tcv_stream_t stream) {
+  TCV_REQUIRE(feat && Vt, "gca_values: null pointer");
+  TCV_REQUIRE(h % 2 == 0 && w % 2 == 0 && h >= 4 && w >= 4, "gca_values: h,w must be even and >= 4");
+  const int P = (h / 2) * (w / 2), P_pad = (P + 63) / 64 * 64;
+  const long long total = (long long)n * VD * P_pad;
+  gca_values_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(feat), n, h, w, P_pad, Vt);
+  return launched("gca_values_kernel");
+}
+
+int tcv_gca_softmax(float* Sm, const float* mm, int n, int P, int P_pad, tcv_stream_t stream) {
+  TCV_REQUIRE(Sm && mm, "gca_softmax: null pointer");
+  TCV_REQUIRE(P > 0 && P_pad >= P, "gca_softmax: bad P");
+  dim3 grid(P, n);
+  gca_softmax_kernel<<<grid, 256, 0, S(stream)>>>(Sm, mm, P, P_pad);
+  return launched("gca_softmax_kernel");
+}
+
+int tcv_gca_fold(const float* O, int n, int h, int w, void* Y, tcv_stream_t stream) {
+  TCV_REQUIRE(O && Y, "gca_fold: null pointer");
+  const long long total = (long long)n * h * w * (FC / 4);
+  gca_fold_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(O, n, h, w,
+                                                                         reinterpret_cast<__nv_bfloat16*>(Y));
+  return launched("gca_fold_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,387 @@
+"""Host-side engine for the ``vmn_gca`` frame-window forward: weight folding/packing cache,
+static per-shape execution plans, and the kernel program (what runs, in which order, on which
+buffers).  All arithmetic is done by the sm_100a kernels behind the C ABI; torch is used for
+device memory, streams and (optionally) CUDA-graph capture only.
+
+Program restated from (reference checkout):
+  per-frame part   VMN_model.py:93-98 -> res_gca_enc.py:57-90, VMN_GCA.py:27-34
+  per-centre part  VMN_model.py:107-110 -> VMN_GCA.py:35-49
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import ACT_LEAKY02, ACT_NONE, ACT_RELU, ACT_TANH01, PAD_REFLECT, PAD_ZERO, ConvDesc
+from .modules import DEC_LAYERS, ENC_LAYERS
+
+BN_EPS = 1e-5
+
+
+class Act:
+    """split-bf16 NHWC activation: ``buf[0]`` = hi plane, ``buf[1]`` = lo plane."""
+    __slots__ = ("buf", "n", "h", "w", "c", "ptr", "plane")
+
+    def __init__(self, buf, n, h, w, c, ptr, plane):
+        self.buf, self.n, self.h, self.w, self.c, self.ptr, self.plane = buf, n, h, w, c, ptr, plane
+
+    @staticmethod
+    def empty(n, h, w, c, device) -> "Act":
+        buf = torch.empty((2, n, h, w, c), dtype=torch.bfloat16, device=device)
+        return Act(buf, n, h, w, c, buf.data_ptr(), n * h * w * c)
+
+    def slice(self, n0: int, n1: int) -> "Act":
+        return Act(self.buf, n1 - n0, self.h, self.w, self.c, self.ptr + 2 * n0 * self.h * self.w * self.c,
+                   self.plane)
+
+    @property
+    def img_elems(self) -> int:
+        return self.h * self.w * self.c
+
+    def float(self) -> torch.Tensor:
+        """[n,h,w,c] fp32 view of the full parent tensor (debug / tests)."""
+        return self.buf[0].float() + self.buf[1].float()
+
+
+class Plan:
+    """A recorded, replayable list of C-ABI calls on static buffers for one input shape."""
+
+    def __init__(self):
+        self.calls: List[Tuple] = []
+        self.keep: List = []
+        self.io: Dict[str, torch.Tensor] = {}
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.n_launch = 0
+
+    def replay(self, stream_ptr: int) -> None:
+        for fn, args, what in self.calls:
+            rc = fn(*args, stream_ptr)
+            if rc != 0:
+                _cabi.check(rc, what)
+
+
+def _k(prefix: str, name: str) -> str:
+    return f"{prefix}.{name}" if prefix else name
+
+
+class GcaVmnEngine:
+    """Owns derived device state for one ``VMN`` module on one device."""
+
+    def __init__(self, window: int):
+        self.net = None
+        self.window = window
+        self.device: Optional[torch.device] = None
+        self.w: Dict[str, dict] = {}
+        self.aff: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self.bias: Dict[str, torch.Tensor] = {}
+        self._fingerprint = None
+        self._tensors = None
+        self.plans: Dict[Tuple, Plan] = {}
+        self._rec: Optional[Plan] = None
+        self.use_graphs = True
+
+    # ------------------------------------------------------------------ weights
+    def _named(self) -> Dict[str, torch.Tensor]:
+        d = dict(self.net.named_parameters())
+        d.update(dict(self.net.named_buffers()))
+        return d
+
+    def _current_fingerprint(self):
+        if self._tensors is None:
+            self._tensors = list(self._named().values())
+        return (tuple(t._version for t in self._tensors), self._tensors[0].data_ptr())
+
+    def refresh_weights(self, net: torch.nn.Module, force=False) -> None:
+        """(Re)derives folded/packed weights when parameters changed (load_state_dict, optimizer step,
+        device move, a fresh DataParallel replica).  Packed buffers are updated in place so
+        recorded plans stay valid."""
+        if net is not self.net:
+            self.net = net
+            self._tensors = None
+        named = self._named()
+        dev = next(iter(named.values())).device
+        if dev.type != "cuda":
+            raise RuntimeError("tcvom_b200: the module must live on a CUDA device (no CPU fallback)")
+        if self.device is not None and dev != self.device:
+            self.w.clear(); self.aff.clear(); self.bias.clear(); self.plans.clear()
+            self._tensors = None
+        self.device = dev
+        fp = self._current_fingerprint()
+        if not force and fp == self._fingerprint:
+            return
+        L = _cabi.lib()
+        st = torch.cuda.current_stream(dev).cuda_stream
+        sig = getattr(self, "_sigma_ws", None)
+        if sig is None or sig.device != dev:
+            sig = self._sigma_ws = torch.empty(256, dtype=torch.float32, device=dev)
+        i_sig = 0
+        for name, t in named.items():
+            if t.dtype.is_floating_point and (t.dtype != torch.float32 or not t.is_contiguous()):
+                raise RuntimeError(f"tcvom_b200: parameter {name} must be contiguous fp32")
+        for name, t in named.items():
+            if name.endswith(".module.weight_bar"):
+                p = name[: -len(".module.weight_bar")]
+                u, v = named[p + ".module.weight_u"], named[p + ".module.weight_v"]
+                self._pack(L, st, p, t, u, v, sig[i_sig:i_sig + 1], transposed=(t.shape[2] == 4))
+                i_sig += 1
+            elif name.endswith(".weight") and t.dim() == 4:
+                p = name[: -len(".weight")]
+                self._pack(L, st, p, t, None, None, None, transposed=False)
+                b = named.get(p + ".bias")
+                if b is not None:
+                    self.bias[p] = b
+            elif name.endswith(".running_var"):
+                p = name[: -len(".running_var")]
+                c = t.numel()
+                if p not in self.aff:
+                    self.aff[p] = (torch.empty(c, dtype=torch.float32, device=dev),
+                                   torch.empty(c, dtype=torch.float32, device=dev))
+                s, b = self.aff[p]
+                _cabi.check(L.tcv_bn_fold(named[p + ".weight"].data_ptr(), named[p + ".bias"].data_ptr(),
+                                          named[p + ".running_mean"].data_ptr(), t.data_ptr(), BN_EPS, c,
+                                          s.data_ptr(), b.data_ptr(), st), "bn_fold")
+        self._fingerprint = fp
+
+    def _pack(self, L, st, p, wbar, u, v, sig, transposed):
+        if transposed:
+            cin, cout, kh, kw = wbar.shape
+        else:
+            cout, cin, kh, kw = wbar.shape
+        cin_pad = (cin + 7) // 8 * 8
+        ent = self.w.get(p)
+        if ent is None:
+            ent = self.w[p] = dict(w=torch.empty((kh * kw, cin_pad, cout), dtype=torch.float32, device=wbar.device),
+                                   cout=cout, cin=cin_pad, k=kh, transposed=transposed)
+        _cabi.check(L.tcv_sn_fold_pack(wbar.data_ptr(), u.data_ptr() if u is not None else None,
+                                       v.data_ptr() if v is not None else None, cout, cin, kh, kw,
+                                       1 if transposed else 0, cin_pad, ent["w"].data_ptr(),
+                                       sig.data_ptr() if sig is not None else None, st), "sn_fold_pack")
+
+    # ------------------------------------------------------------------ call recording
+    def _call(self, fn_name: str, *args):
+        fn = getattr(_cabi.lib(), fn_name)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _cabi.check(fn(*args, st), fn_name)
+        if self._rec is not None:
+            self._rec.calls.append((fn, args, fn_name))
+
+    def _keep(self, *objs):
+        if self._rec is not None:
+            self._rec.keep.extend(objs)
+
+    def _empty(self, shape, dtype=torch.float32):
+        t = torch.empty(shape, dtype=dtype, device=self.device)
+        self._keep(t)
+        return t
+
+    def _act(self, n, h, w, c) -> Act:
+        a = Act.empty(n, h, w, c, self.device)
+        self._keep(a.buf)
+        return a
+
+    # ------------------------------------------------------------------ operators
+    def conv(self, x: Act, wkey: str, *, stride=1, pad=PAD_ZERO, bn: Optional[str] = None, bias=False,
+             act=ACT_NONE, res1: Optional[Act] = None, res1_shift=0, bn2: Optional[str] = None,
+             res2: Optional[Act] = None, f32_out: Optional[torch.Tensor] = None, f32_ptr: int = 0,
+             want_split=True) -> Optional[Act]:
+        ent = self.w[wkey]
+        cout, k = ent["cout"], ent["k"]
+        assert ent["cin"] == x.c, (wkey, ent["cin"], x.c)
+        assert not ent["transposed"]
+        if k == 3:
+            taps = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+            oh, ow = (x.h + 2 - 3) // stride + 1, (x.w + 2 - 3) // stride + 1
+        else:
+            taps = [(0, 0)]
+            oh, ow = (x.h - 1) // stride + 1, (x.w - 1) // stride + 1
+        y = self._act(x.n, oh, ow, cout) if want_split else None
+        d = self._desc(x, ent["w"].data_ptr(), taps, stride, pad, y, oh, ow, cout, oh, ow, 1, 0, 1, 0, wkey, bn, bias,
+                       act, res1, res1_shift, bn2, res2, f32_ptr if f32_ptr else
+                       (f32_out.data_ptr() if f32_out is not None else 0))
+        self._call("tcv_conv2d", C.byref(d))
+        return y
+
+    def deconv4x4s2(self, x: Act, wkey: str, *, bn: str, act, res2: Optional[Act] = None) -> Act:
+        """ConvTranspose2d(k=4, s=2, p=1) as 4 sub-pixel phases of 2x2 taps each."""
+        ent = self.w[wkey]
+        assert ent["transposed"] and ent["cin"] == x.c
+        cout = ent["cout"]
+        oh, ow = 2 * x.h, 2 * x.w
+        y = self._act(x.n, oh, ow, cout)
+        for py in range(2):
+            for px in range(2):
+                # oy = 2*iy - 1 + ky: phase py uses kernel rows (ky, input row offset dy)
+                kys = [(1, 0), (3, -1)] if py == 0 else [(0, 1), (2, 0)]
+                kxs = [(1, 0), (3, -1)] if px == 0 else [(0, 1), (2, 0)]
+                taps = [(dy, dx) for ky, dy in kys for kx, dx in kxs]
+                wtap = [ky * 4 + kx for ky, dy in kys for kx, dx in kxs]
+                d = self._desc(x, ent["w"].data_ptr(), taps, 1, PAD_ZERO, y, oh, ow, cout, x.h, x.w, 2, py, 2, px,
+                               wkey, bn, False, act, None, 0, None, res2, 0, wtap=wtap)
+                self._call("tcv_conv2d", C.byref(d))
+        return y
+
+    def _desc(self, x: Act, wptr, taps, stride, pad, y: Optional[Act], oh, ow, cout, gh, gw, oy_mul, oy_off, ox_mul,
+              ox_off, wkey, bn, bias, act, res1, res1_shift, bn2, res2, f32_ptr, wtap=None) -> ConvDesc:
+        d = ConvDesc()
+        d.x, d.x_plane, d.x_img_stride = x.ptr, x.plane, x.img_elems
+        d.n, d.ih, d.iw, d.cin = x.n, x.h, x.w, x.c
+        d.w, d.ntaps = wptr, len(taps)
+        for i, (dy, dx) in enumerate(taps):
+            d.dy[i], d.dx[i] = dy, dx
+            d.wtap[i] = wtap[i] if wtap is not None else i
+        d.stride, d.pad_mode = stride, pad
+        d.y = y.ptr if y is not None else None
+        d.y_f32 = f32_ptr or None
+        d.oh, d.ow, d.cout, d.gh, d.gw = oh, ow, cout, gh, gw
+        d.oy_mul, d.oy_off, d.ox_mul, d.ox_off = oy_mul, oy_off, ox_mul, ox_off
+        if bn is not None:
+            s, b = self.aff[bn]
+            d.s1, d.b1 = s.data_ptr(), b.data_ptr()
+        elif bias:
+            d.b1 = self.bias[wkey].data_ptr()
+        if res1 is not None:
+            assert res1.c == cout and res1.n == x.n and res1.h == oh >> res1_shift and res1.w == ow >> res1_shift, wkey
+            d.res1, d.res1_plane, d.res1_shift = res1.ptr, res1.plane, res1_shift
+        d.act = act
+        if bn2 is not None:
+            s, b = self.aff[bn2]
+            d.s2, d.b2 = s.data_ptr(), b.data_ptr()
+        if res2 is not None:
+            assert res2.c == cout and res2.n == x.n and res2.h == oh and res2.w == ow, wkey
+            d.res2, d.res2_plane = res2.ptr, res2.plane
+        self._keep(d)
+        return d
+
+    def avgpool2(self, x: Act) -> Act:
+        y = self._act(x.n, x.h // 2, x.w // 2, x.c)
+        assert x.plane == x.n * x.img_elems
+        self._call("tcv_avgpool2", x.ptr, x.n, x.h, x.w, x.c, y.ptr)
+        return y
+
+    def gca(self, p: str, im_fea: Act, feat: Act, unknown: torch.Tensor) -> Act:
+        """GuidedCxtAtten.forward (GCA/ops.py:106-229)."""
+        n, h, w = feat.n, feat.h, feat.w
+        assert feat.c == 128 and im_fea.c == 128 and (im_fea.h, im_fea.w) == (h, w)
+        assert h % 2 == 0 and w % 2 == 0
+        g = self.conv(im_fea, _k(p, "guidance_conv"), stride=2, bias=True)       # 1x1, then [::2, ::2]
+        P = (h // 2) * (w // 2)
+        P_pad = (P + 63) // 64 * 64
+        Q = self._empty((n, P, 576))
+        Kn = self._empty((n, P, 576))
+        mm = self._empty((n, P))
+        scales = self._empty((n, 2))
+        self._call("tcv_gca_prep", g.ptr, unknown.data_ptr(), n, h, w, Q.data_ptr(), Kn.data_ptr(), mm.data_ptr(),
+                   scales.data_ptr())
+        Vt = self._empty((n, 2048, P_pad))
+        self._call("tcv_gca_values", feat.ptr, n, h, w, Vt.data_ptr())
+        Sm = self._empty((n, P, P_pad))
+        self._call("tcv_gemm_tn_f32", Q.data_ptr(), Kn.data_ptr(), Sm.data_ptr(), P, P, 576, 576, 576, P_pad,
+                   P * 576, P * 576, P * P_pad, n)
+        self._call("tcv_gca_softmax", Sm.data_ptr(), mm.data_ptr(), n, P, P_pad)
+        O = self._empty((n, P, 2048))
+        self._call("tcv_gemm_tn_f32", Sm.data_ptr(), Vt.data_ptr(), O.data_ptr(), P, 2048, P_pad, P_pad, P_pad, 2048,
+                   P * P_pad, 2048 * P_pad, P * 2048, n)
+        Y = self._act(n, h, w, 128)
+        self._call("tcv_gca_fold", O.data_ptr(), n, h, w, Y.ptr)
+        self.last_gca_scales = scales
+        return self.conv(Y, _k(p, "W.0"), bn=_k(p, "W.1"), res1=feat)
+
+    def tam(self, p: str, x: Act, xb: Act, xf: Act, mask_ptr: int, mask_stride: int, mh: int, mw: int,
+            attb_ptr: int, attf_ptr: int, sm_ptr: int) -> Act:
+        """FeatureAggregationModule.forward (VMN_model.py:18-68)."""
+        q = self.conv(x, _k(p, "query_conv"), bias=True)
+        v = self.conv(x, _k(p, "value_conv"), bias=True)
+        kb = self.conv(xb, _k(p, "key_conv"), bias=True)
+        kf = self.conv(xf, _k(p, "key_conv"), bias=True)
+        out = self._act(x.n, x.h, x.w, x.c)
+        self._call("tcv_tam_attend", q.ptr, v.ptr, kb.ptr, kf.ptr, mask_ptr, mask_stride, mh, mw, x.n, x.h, x.w, x.c,
+                   self.window, out.ptr, attb_ptr, attf_ptr, sm_ptr)
+        return out
+
+    # ------------------------------------------------------------------ network program
+    def _enc_block(self, x: Act, p: str, stride: int) -> Act:
+        o = self.conv(x, p + ".conv1", stride=stride, bn=p + ".bn1", act=ACT_RELU)
+        idt = x
+        if stride != 1:
+            idt = self.conv(self.avgpool2(x), p + ".downsample.1", bn=p + ".downsample.2")
+        return self.conv(o, p + ".conv2", bn=p + ".bn2", res1=idt, act=ACT_RELU)
+
+    def _shortcut(self, x: Act, p: str) -> Act:
+        o = self.conv(x, p + ".0", act=ACT_RELU, bn2=p + ".2")
+        return self.conv(o, p + ".3", act=ACT_RELU, bn2=p + ".5")
+
+    def _dec_layer(self, x: Act, p: str, blocks: int, res2: Optional[Act]) -> Act:
+        for i in range(blocks):
+            bp = f"{p}.{i}"
+            last = res2 if i == blocks - 1 else None
+            if i == 0:
+                o = self.deconv4x4s2(x, bp + ".conv1", bn=bp + ".bn1", act=ACT_LEAKY02)
+                idt = self.conv(x, bp + ".upsample.1", bn=bp + ".upsample.2")    # 1x1 at low res; nearest-up commutes
+                x = self.conv(o, bp + ".conv2", bn=bp + ".bn2", res1=idt, res1_shift=1, act=ACT_LEAKY02, res2=last)
+            else:
+                o = self.conv(x, bp + ".conv1", bn=bp + ".bn1", act=ACT_LEAKY02)
+                x = self.conv(o, bp + ".conv2", bn=bp + ".bn2", res1=x, act=ACT_LEAKY02, res2=last)
+        return x
+
+    def per_frame(self, x8: Act) -> dict:
+        """encoder + decoder head for all frames at once (VMN_model.py:93-98)."""
+        e = "encoder"
+        c1 = self.conv(x8, e + ".conv1", stride=2, bn=e + ".bn1", act=ACT_RELU)
+        x1 = self.conv(c1, e + ".conv2", bn=e + ".bn2", act=ACT_RELU)
+        c3 = self.conv(x1, e + ".conv3", stride=2, bn=e + ".bn3", act=ACT_RELU)
+        g = x8
+        for ci, bi in ((1, 3), (5, 7), (9, 11)):                                # guidance head (res_gca_enc.py:20-33)
+            g = self.conv(g, f"{e}.guidance_head.{ci}", stride=2, pad=PAD_REFLECT, act=ACT_RELU,
+                          bn2=f"{e}.guidance_head.{bi}")
+        im_fea = g
+        unknown = self._empty((x8.n, x8.h // 8, x8.w // 8))
+        self._call("tcv_unknown_os8", x8.ptr, x8.n, x8.h, x8.w, unknown.data_ptr())
+        feats = []
+        cur = c3
+        for name, planes, blocks, stride in ENC_LAYERS:
+            if name == "layer3":
+                cur = self.gca(e + ".gca", im_fea, cur, unknown)
+                feats[-1] = cur
+            for i in range(blocks):
+                cur = self._enc_block(cur, f"{e}.{name}.{i}", stride if i == 0 else 1)
+            feats.append(cur)
+        x2, x3, x4, emb = feats
+        fea = [self._shortcut(t, f"{e}.shortcut.{i}") for i, t in enumerate((x8, x1, x2, x3, x4))]
+        d = self._dec_layer(emb, "decoder.layer1", DEC_LAYERS[0][2], fea[4])
+        d = self._dec_layer(d, "decoder.layer2", DEC_LAYERS[1][2], fea[3])
+        feat = self.gca("decoder.gca", im_fea, d, unknown)
+        return dict(fea=fea, feat=feat, im_fea=im_fea, unknown=unknown)
+
+    def tail(self, pf: dict, n0: int, ncen: int, mask_ptr: int, mask_stride: int, H: int, W: int, pred_ptr: int,
+             attb_ptr: int, attf_ptr: int, sm_ptr: int) -> None:
+        """decoder tail for `ncen` consecutive centre frames starting at image n0+1 (VMN_GCA.py:35-49)."""
+        feat: Act = pf["feat"]
+        x = feat.slice(n0 + 1, n0 + 1 + ncen)
+        xb = feat.slice(n0, n0 + ncen)
+        xf = feat.slice(n0 + 2, n0 + 2 + ncen)
+        fea = [f.slice(n0 + 1, n0 + 1 + ncen) for f in pf["fea"]]
+        t = self.tam("decoder.fam", x, xb, xf, mask_ptr, mask_stride, H, W, attb_ptr, attf_ptr, sm_ptr)
+        t = self._dec_layer(t, "decoder.layer3", DEC_LAYERS[2][2], fea[2])
+        t = self._dec_layer(t, "decoder.layer4", DEC_LAYERS[3][2], fea[1])
+        t = self.deconv4x4s2(t, "decoder.conv1", bn="decoder.bn1", act=ACT_LEAKY02, res2=fea[0])
+        self.conv(t, "decoder.conv2", bias=True, act=ACT_TANH01, f32_ptr=pred_ptr, want_split=False)
+
+    def window_program(self, x8: Act, trimask: torch.Tensor, B: int, S: int, H: int, W: int) -> dict:
+        """Runs (and records) the whole VMN forward on preprocessed input.  trimask fp32 [B*S,H,W]."""
+        dev = self.device
+        ncen = S - 2
+        N8 = (H // 8) * (W // 8)
+        w2 = self.window * self.window
+        pred = self._empty((B, ncen, 1, H, W))
+        attb = self._empty((B, ncen, w2, N8))
+        attf = self._empty((B, ncen, w2, N8))
+        sm = self._empty((B, ncen, 1, H // 8, W // 8), torch.uint8)
+        pf = self.per_frame(x8)
+        for b in range(B):
+            n0 = b * S
+            self.tail(pf, n0, ncen, trimask.data_ptr() + 4 * (n0 + 1) * H * W, H * W, H, W,
+                      pred[b].data_ptr(), attb[b].data_ptr(), attf[b].data_ptr(), sm[b].data_ptr())
+        return dict(pred=pred, attb=attb, attf=attf, small_mask=sm, feat=pf["feat"], pf=pf)

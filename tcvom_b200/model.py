@@ -1,0 +1,326 @@
+"""Host-side mirror of the reference's operator surface for the GCA+TAM path.
+
+Same names, argument meaning and error behaviour as the reference (checkout f5fa07a):
+
+  get_VMN_models(arch, agg_window, agg_reduction=1, freeze_backbone=False)   models/VMN/__init__.py:11-29
+  VMN.forward(images, masks, extras=None)                                   models/VMN/VMN_model.py:83-113
+  FeatureAggregationModule(input_chn, reduction, window).forward(x,b,f,mask) models/VMN/VMN_model.py:9-68
+  GuidedCxtAtten(out_channels, guidance_channels, rate=2).forward(f, alpha, unknown)  models/GCA/ops.py:83-229
+  EvalModel(model, dilate_kernel=None, eps=0, agg_window=...).forward(imgs, tris)      models/model.py:359-424
+
+All compute goes through the C ABI (include/tcvom_b200.h).  There is no PyTorch/CPU fallback:
+tensors must be on a CUDA device and the native library must be built, otherwise a
+RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import threading
+from typing import List, Optional, Sequence
+
+import torch
+from torch import nn
+
+from . import _cabi
+from .engine import Act, GcaVmnEngine, Plan
+from .modules import GCADecoderParams, GCAEncoderParams, GuidedCxtAttenParams, TAMParams
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"tcvom_b200: {what} must be a CUDA tensor (there is no CPU fallback)")
+
+
+_ENGINE_LOCK = threading.Lock()
+
+
+def _engine_for(module: nn.Module, window: int) -> GcaVmnEngine:
+    """One engine per (module, device).  nn.DataParallel replicas share the module __dict__ (and so
+    this table) but run one thread per device, so a per-device engine is never used concurrently."""
+    dev = next(module.parameters()).device
+    if dev.type != "cuda":
+        raise RuntimeError("tcvom_b200: the module must live on a CUDA device (no CPU fallback)")
+    with _ENGINE_LOCK:
+        table = module.__dict__.get("_engines")
+        if table is None:
+            table = module.__dict__["_engines"] = {}
+        eng = table.get(dev.index)
+        if eng is None:
+            eng = table[dev.index] = GcaVmnEngine(window)
+    eng.refresh_weights(module)
+    return eng
+
+
+class _OpEngineMixin:
+    """Gives a standalone operator module (TAM / GCA) its own small engine over its parameters."""
+
+    def _op_engine(self, window=1) -> GcaVmnEngine:
+        return _engine_for(self, window)
+
+
+class FeatureAggregationModule(TAMParams, _OpEngineMixin):
+    """Temporal Attention Module (VMN_model.py:9-68) as a drop-in operator: NCHW fp32 in/out."""
+
+    def forward(self, x, b, f, mask):
+        for t, nme in ((x, "x"), (b, "b"), (f, "f"), (mask, "mask")):
+            _require_cuda(t, nme)
+        B, Cc, H, W = x.shape
+        assert b.shape == x.shape and f.shape == x.shape          # VMN_model.py:26
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("tcvom_b200: TAM backward kernels are not built yet (inference only)")
+        eng = self._op_engine(self.window)
+        L = _cabi.lib()
+        st = _stream(x.device)
+        acts = []
+        for t in (x, b, f):
+            a = Act.empty(B, H, W, Cc, x.device)
+            _cabi.check(L.tcv_nchw_to_split(t.contiguous().float().data_ptr(), B, Cc, H, W, Cc, a.ptr, 0, st), "nchw_to_split")
+            acts.append(a)
+        w2 = self.window * self.window
+        attb = torch.empty((B, w2, H * W), dtype=torch.float32, device=x.device)
+        attf = torch.empty_like(attb)
+        sm = torch.empty((B, 1, H, W), dtype=torch.uint8, device=x.device)
+        m = mask.contiguous().float()
+        mh, mw = m.shape[-2:]
+        out = eng.tam("", acts[0], acts[1], acts[2], m.data_ptr(), mh * mw, mh, mw, attb.data_ptr(),
+                      attf.data_ptr(), sm.data_ptr())
+        y = torch.empty((B, Cc, H, W), dtype=torch.float32, device=x.device)
+        _cabi.check(L.tcv_split_to_nchw(out.ptr, B, Cc, H, W, Cc, 0, y.data_ptr(), st), "split_to_nchw")
+        return y, attb, attf, sm.bool()
+
+
+class GuidedCxtAtten(GuidedCxtAttenParams, _OpEngineMixin):
+    """Guided contextual attention (GCA/ops.py:83-229) as a drop-in operator: NCHW fp32 in/out.
+    Returns (y, (offsets, softmax_scale)); ``offsets`` (an argmax visualisation the VMN path
+    drops, VMN_GCA.py:33) is not computed and returned as None."""
+
+    def forward(self, f, alpha, unknown=None, ksize=3, stride=1, fuse_k=3, softmax_scale=1., training=True):
+        _require_cuda(f, "f"); _require_cuda(alpha, "alpha")
+        if unknown is None:
+            raise NotImplementedError("tcvom_b200: GuidedCxtAtten without an unknown map is not on the VMN path")
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("tcvom_b200: GCA backward kernels are not built yet (inference only)")
+        B, Cc, H, W = alpha.shape
+        assert unknown.shape[2] == H and unknown.shape[3] == W, "mask should have same size as f at dim 2,3"
+        eng = self._op_engine()
+        L = _cabi.lib()
+        st = _stream(f.device)
+        a_f = Act.empty(B, H, W, f.shape[1], f.device)
+        a_al = Act.empty(B, H, W, Cc, f.device)
+        _cabi.check(L.tcv_nchw_to_split(f.contiguous().float().data_ptr(), B, f.shape[1], H, W, f.shape[1], a_f.ptr, 0, st), "nchw_to_split")
+        _cabi.check(L.tcv_nchw_to_split(alpha.contiguous().float().data_ptr(), B, Cc, H, W, Cc, a_al.ptr, 0, st), "nchw_to_split")
+        unk = unknown.contiguous().float().reshape(B, H, W)
+        out = eng.gca("", a_f, a_al, unk)
+        y = torch.empty((B, Cc, H, W), dtype=torch.float32, device=f.device)
+        _cabi.check(L.tcv_split_to_nchw(out.ptr, B, Cc, H, W, Cc, 0, y.data_ptr(), st), "split_to_nchw")
+        return y, (None, eng.last_gca_scales.clone())
+
+
+class _GCADecoder(GCADecoderParams):
+    def __init__(self, reduction, window, freeze_backbone=False):
+        super().__init__(reduction, window, freeze_backbone)
+
+    def train(self, mode=True):
+        super().train(mode)
+        if self.freeze_backbone:                                  # VMN_GCA.py:18-24
+            print('Set GCA decoder feature extraction part in eval() mode.')
+            self.layer1.eval(); self.layer2.eval(); self.gca.eval()
+        return self
+
+
+class VMN(nn.Module):
+    """Video matting network (VMN_model.py:70-113) with the GCA base net, native forward."""
+
+    def __init__(self, encoder, decoder, freeze_backbone=False):
+        super().__init__()
+        self.encoder = encoder
+        self.decoder = decoder
+        self.freeze_backbone = freeze_backbone
+
+    def train(self, mode=True):
+        super().train(mode)
+        if self.freeze_backbone:
+            print('Set VMN encoder to eval() mode.')
+            self.encoder.eval()
+        return self
+
+    # -- engine plumbing -------------------------------------------------------------
+    def engine(self) -> GcaVmnEngine:
+        """Engine for this module on its current device, with weights refreshed."""
+        return _engine_for(self, self.decoder.fam.window)
+
+    def __deepcopy__(self, memo):
+        # engines hold device pointers; never copy them with the module (DataParallel.replicate,
+        # copy.deepcopy): the copy derives its own state lazily.
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        import copy
+        for k, v in self.__dict__.items():
+            if k == "_engines":
+                continue
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
+
+    def _check_mode(self):
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError(
+                "tcvom_b200: the training path (backward kernels, train-mode BatchNorm/SpectralNorm) is not "
+                "built yet; call .eval() / torch.no_grad() for inference.  No PyTorch fallback is provided.")
+        if self.training:
+            raise NotImplementedError(
+                "tcvom_b200: train-mode forward (batch-statistics BatchNorm, SpectralNorm power iteration) is "
+                "not built yet; call .eval().")
+
+    def forward(self, images: List[torch.Tensor], masks: Sequence[torch.Tensor], extras=None):
+        """images: list of S tensors [B,1,6,H,W] (normalised RGB + one-hot trimap); masks: S tensors
+        [B,1,1,H,W].  Returns (preds, attb, attf, small_mask) exactly like VMN_model.py:113."""
+        if extras is not None:
+            raise NotImplementedError("tcvom_b200: `extras` is only used by the FBA base network")
+        self._check_mode()
+        S = len(images)
+        for i in range(S):
+            images[i] = images[i].squeeze(1)                        # VMN_model.py:94 (in-place list update)
+        x0 = images[0]
+        _require_cuda(x0, "images")
+        B, Cin, H, W = x0.shape
+        assert Cin == 6, "vmn_gca takes 3 image + 3 trimap channels"
+        if H % 32 or W % 32:
+            raise ValueError("tcvom_b200: H and W must be multiples of 32 (pred_test.py pads to 32)")
+        eng = self.engine()
+        L = _cabi.lib()
+        st = _stream(x0.device)
+        x8 = Act.empty(B * S, H, W, 8, x0.device)
+        trimask = torch.empty((B * S, H, W), dtype=torch.float32, device=x0.device)
+        for i in range(S):
+            xi = images[i].contiguous().float()
+            mi = masks[i].reshape(B, H, W).float()
+            for b in range(B):
+                n = b * S + i
+                _cabi.check(L.tcv_nchw_to_split(xi[b].data_ptr(), 1, 6, H, W, 8, x8.slice(n, n + 1).ptr, x8.plane,
+                                                st), "nchw_to_split")
+                trimask[n].copy_(mi[b])
+        out = eng.window_program(x8, trimask, B, S, H, W)
+        preds: List[Optional[torch.Tensor]] = [None] * S
+        attb: List[Optional[torch.Tensor]] = [None] * S
+        attf: List[Optional[torch.Tensor]] = [None] * S
+        small: List[Optional[torch.Tensor]] = [None] * S
+        for i in range(1, S - 1):
+            preds[i] = out["pred"][:, i - 1]
+            attb[i] = out["attb"][:, i - 1]
+            attf[i] = out["attf"][:, i - 1]
+            small[i] = out["small_mask"][:, i - 1].bool()
+        preds[0] = torch.zeros_like(preds[1])
+        preds[-1] = torch.zeros_like(preds[-2])
+        return preds, attb, attf, small
+
+
+def get_VMN_models(arch, agg_window, agg_reduction=1, freeze_backbone=False, **kwargs):
+    """Plugin seam of the reference (models/VMN/__init__.py:11-29)."""
+    if arch != 'vmn_gca':
+        if arch in ('vmn_dim', 'vmn_fba', 'vmn_index'):
+            raise NotImplementedError(f"tcvom_b200: base network '{arch}' is outside the built hot path (vmn_gca)")
+        raise ValueError
+    if agg_reduction != 1:
+        raise NotImplementedError("tcvom_b200: agg_reduction != 1 is not supported")
+    e = GCAEncoderParams()
+    d = _GCADecoder(agg_reduction, int(agg_window), freeze_backbone=freeze_backbone)
+    d.fam = FeatureAggregationModule(128, agg_reduction, int(agg_window))
+    d.gca = GuidedCxtAtten(128, 128)
+    e.gca = GuidedCxtAtten(128, 128)
+    return VMN(encoder=e, decoder=d, freeze_backbone=freeze_backbone)
+
+
+class EvalModel(nn.Module):
+    """Inference wrapper (models/model.py:359-424): raw BGR frames + trimaps -> alpha mattes.
+
+    forward(imgs [B,S,3,H,W] BGR 0..255, tris [B,S,1,H,W] in {0,128,255}) -> alphas [B,S,1,H,W]
+    (first and last frame of each sample are zeros, model.py:419-421)."""
+
+    def __init__(self, model, dilate_kernel=None, eps=0, **kwargs):
+        super().__init__()
+        if not model.startswith('vmn'):
+            raise NotImplementedError("tcvom_b200: only the VMN (video) architectures are on the built path")
+        self.DILATION_KERNEL = dilate_kernel
+        self.EPS = eps
+        self.IMG_SCALE = 1. / 255
+        self.register_buffer('IMG_MEAN', torch.tensor([0.485, 0.456, 0.406]).reshape([1, 1, 3, 1, 1]).float())
+        self.register_buffer('IMG_STD', torch.tensor([0.229, 0.224, 0.225]).reshape([1, 1, 3, 1, 1]).float())
+        self.model_name = model
+        self.NET = get_VMN_models(arch=model, **kwargs)
+        self.window = kwargs['agg_window']
+        self.method = model[model.rfind('_') + 1:]
+        self.TRIMAP_CHANNEL = 3
+
+    # -- plan handling ---------------------------------------------------------------
+    def _plan(self, B, S, H, W, dev) -> Plan:
+        eng = self.NET.engine()
+        dil = -1 if self.DILATION_KERNEL is None else int(self.DILATION_KERNEL)
+        self.__dict__["_eng"] = eng
+        key = ("eval", B, S, H, W, dil)
+        plan = eng.plans.get(key)
+        if plan is not None:
+            return plan
+        plan = Plan()
+        eng._rec = plan
+        try:
+            imgs = eng._empty((B, S, 3, H, W))
+            tris = eng._empty((B, S, 1, H, W))
+            x8 = eng._act(B * S, H, W, 8)
+            trimask = eng._empty((B * S, H, W))
+            tmp = eng._empty((2 * B * S * H * W,), torch.uint8)
+            alphas = eng._empty((B, S, 1, H, W))
+            # inputs must hold valid data while recording runs the kernels once
+            imgs.zero_(); tris.zero_()
+            n0 = _cabi.launch_count()
+            eng._call("tcv_preprocess_eval", imgs.data_ptr(), tris.data_ptr(), B * S, H, W, dil, x8.ptr,
+                      trimask.data_ptr(), tmp.data_ptr())
+            out = eng.window_program(x8, trimask, B, S, H, W)
+            eng._call("tcv_postprocess_eval", out["pred"].data_ptr(), tris.data_ptr(), trimask.data_ptr(), B, S, H, W,
+                      alphas.data_ptr())
+            plan.n_launch = _cabi.launch_count() - n0
+            plan.io = dict(imgs=imgs, tris=tris, alphas=alphas, trimask=trimask, **{k: out[k] for k in
+                                                                                   ("pred", "attb", "attf", "small_mask")})
+            plan.io["feat"] = out["feat"].buf
+        finally:
+            eng._rec = None
+        eng.plans[key] = plan
+        return plan
+
+    def run_plan(self, plan: Plan) -> None:
+        """Replays the recorded kernel sequence on the current stream (CUDA graph when enabled)."""
+        eng = self._eng
+        dev = eng.device
+        if eng.use_graphs:
+            if plan.graph is None:
+                st = torch.cuda.Stream(dev)
+                st.wait_stream(torch.cuda.current_stream(dev))
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.stream(st):
+                    plan.replay(st.cuda_stream)                     # warm-up outside capture
+                    st.synchronize()
+                    with torch.cuda.graph(g, stream=st):
+                        plan.replay(torch.cuda.current_stream(dev).cuda_stream)
+                torch.cuda.current_stream(dev).wait_stream(st)
+                plan.graph = g
+            plan.graph.replay()
+        else:
+            plan.replay(torch.cuda.current_stream(dev).cuda_stream)
+
+    def forward(self, imgs, tris):
+        _require_cuda(imgs, "imgs")
+        if self.method == 'fba':
+            raise NotImplementedError
+        self.NET._check_mode()
+        B, S, Cc, H, W = imgs.shape
+        assert Cc == 3 and S >= 3
+        if H % 32 or W % 32:
+            raise ValueError("tcvom_b200: H and W must be multiples of 32 (pred_test.py pads to 32)")
+        plan = self._plan(B, S, H, W, imgs.device)
+        plan.io["imgs"].copy_(imgs, non_blocking=True)
+        plan.io["tris"].copy_(tris, non_blocking=True)
+        self.run_plan(plan)
+        return plan.io["alphas"].clone()

@@ -1,0 +1,138 @@
+"""GPU parity tests: the sm_100a path (through the C ABI) against the golden vectors produced by
+the unmodified reference and against the CPU oracle on the same seeded inputs.
+
+Tolerance: north_star states 1e-3 max abs on the alpha matte (fp32 reference)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import fixture_sd, golden, op_inputs
+from oracle import vmn_gca_oracle as O
+
+pytestmark = pytest.mark.gpu
+ALPHA_TOL = 1e-3
+CASES = ["ring64", "ring96x128", "allunk64", "nounk64", "dil64x96", "batch2_64"]
+
+
+def _model(dilate=None):
+    import tcvom_b200
+    m = tcvom_b200.EvalModel(model="vmn_gca", agg_window=7, dilate_kernel=dilate)
+    m.NET.load_state_dict(fixture_sd(), strict=True)
+    return m.cuda().eval()
+
+
+def _prefixed(prefix):
+    return {k[len(prefix):]: v for k, v in fixture_sd().items() if k.startswith(prefix)}
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_eval_forward_matches_reference_golden(case):
+    g = golden(f"eval_{case}.npz")
+    dil = int(g["dilate"])
+    m = _model(None if dil < 0 else dil)
+    imgs = torch.from_numpy(g["imgs"]).float().cuda()
+    tris = torch.from_numpy(g["tris"]).float().cuda()
+    with torch.no_grad():
+        alphas = m(imgs, tris)
+    plan = list(m.NET.engine().plans.values())[0]
+    assert np.array_equal(plan.io["trimask"].reshape(g["trimask"].shape).cpu().numpy().astype(np.uint8), g["trimask"])
+    err = np.abs(alphas.cpu().numpy() - g["alphas"]).max()
+    print(case, "alpha max abs err", err)
+    assert err < ALPHA_TOL
+    pred = plan.io["pred"][:, 0].cpu().numpy()
+    assert np.abs(pred - g["pred1"]).max() < ALPHA_TOL
+    assert np.array_equal(plan.io["small_mask"][:, 0].bool().cpu().numpy(), g["small_mask1"])
+    for mine, ref in ((plan.io["attb"][:, 0], g["attb1"]), (plan.io["attf"][:, 0], g["attf1"])):
+        assert np.abs(mine.cpu().numpy() - ref).max() <= 2e-3 * max(1.0, np.abs(ref).max())
+
+
+def test_eval_forward_second_call_and_graph_replay():
+    g = golden("eval_ring64.npz")
+    m = _model()
+    imgs = torch.from_numpy(g["imgs"]).float().cuda()
+    tris = torch.from_numpy(g["tris"]).float().cuda()
+    with torch.no_grad():
+        a1 = m(imgs, tris).clone()
+        a2 = m(imgs, tris).clone()         # CUDA-graph replay of the recorded plan
+        a3 = m(imgs.flip(-1).contiguous(), tris.flip(-1).contiguous())
+        a4 = m(imgs, tris)
+    assert torch.equal(a1, a2) and torch.equal(a1, a4)
+    assert not torch.equal(a1, a3)
+    assert np.abs(a1.cpu().numpy() - g["alphas"]).max() < ALPHA_TOL
+
+
+def test_vmn_seam_matches_oracle():
+    """Plugin seam models.VMN.get_VMN_models(...).forward(images, masks)."""
+    import tcvom_b200
+    g = golden("eval_batch2_64.npz")
+    sd = fixture_sd()
+    imgs = torch.from_numpy(g["imgs"]).float()
+    tris = torch.from_numpy(g["tris"]).float()
+    x6, trimask = O.eval_preprocess(imgs, tris)
+    S = imgs.shape[1]
+    ref_preds, ref_attb, ref_attf, ref_small, _ = O.vmn_forward(
+        sd, [x6[:, i] for i in range(S)], [trimask[:, i] for i in range(S)], 7)
+    net = tcvom_b200.get_VMN_models("vmn_gca", agg_window=7)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    images = list(x6.cuda().split(1, dim=1))
+    masks = trimask.cuda().split(1, dim=1)
+    with torch.no_grad():
+        preds, attb, attf, small = net(images, masks)
+    assert preds[0].abs().max() == 0 and preds[-1].abs().max() == 0 and attb[0] is None
+    assert (preds[1].cpu() - ref_preds[1]).abs().max() < ALPHA_TOL
+    assert torch.equal(small[1].cpu(), ref_small[1])
+    assert (attb[1].cpu() - ref_attb[1]).abs().max() <= 2e-3 * max(1.0, float(ref_attb[1].abs().max()))
+
+
+def test_tam_operator_matches_reference_golden():
+    import tcvom_b200
+    g = golden("op_tam.npz")
+    fam = tcvom_b200.FeatureAggregationModule(128, 1, 7)
+    fam.load_state_dict(_prefixed("decoder.fam."), strict=True)
+    fam = fam.cuda().eval()
+    x = torch.from_numpy(op_inputs("tam_x", (2, 128, 12, 16))).cuda()
+    b = torch.from_numpy(op_inputs("tam_b", (2, 128, 12, 16))).cuda()
+    f = torch.from_numpy(op_inputs("tam_f", (2, 128, 12, 16))).cuda()
+    mask = torch.from_numpy((op_inputs("tam_m", (2, 1, 96, 128)) > 0.5).astype(np.float32)).cuda()
+    with torch.no_grad():
+        feat, attb, attf, sm = fam(x, b, f, mask)
+    assert np.array_equal(sm.cpu().numpy(), g["small_mask"])
+    # inputs are rounded to split-bf16 (16 mantissa bits) at the seam: tolerance is relative
+    for mine, ref in ((feat, g["feat"]), (attb, g["attb"]), (attf, g["attf"])):
+        assert np.abs(mine.cpu().numpy() - ref).max() <= 1e-3 * max(1.0, np.abs(ref).max())
+
+
+def test_gca_operator_matches_reference_golden():
+    import tcvom_b200
+    g = golden("op_gca.npz")
+    gca = tcvom_b200.GuidedCxtAtten(128, 128)
+    gca.load_state_dict(_prefixed("decoder.gca."), strict=True)
+    gca = gca.cuda().eval()
+    f = torch.from_numpy(op_inputs("gca_f", (2, 128, 16, 24))).cuda()
+    al = torch.from_numpy(op_inputs("gca_alpha", (2, 128, 16, 24))).cuda()
+    unk = torch.from_numpy((op_inputs("gca_unk", (2, 1, 16, 24)) > 0.3).astype(np.float32)).cuda()
+    with torch.no_grad():
+        y, (offsets, scale) = gca(f, al, unk)
+    assert np.abs(scale.cpu().numpy() - g["scale"]).max() < 1e-5
+    assert np.abs(y.cpu().numpy() - g["y"]).max() <= 1e-3 * max(1.0, np.abs(g["y"]).max())
+
+
+def test_eval_forward_256_matches_oracle():
+    """BASELINE config 1 shape (256x256 window) against the CPU oracle on the same seeded input."""
+    from tcvom_b200 import synthetic
+    imgs, tris = synthetic.make_window(256, 256, seed=7)
+    ti, tt = torch.from_numpy(imgs).float(), torch.from_numpy(tris).float()
+    ref = O.eval_forward(fixture_sd(), ti, tt)
+    m = _model()
+    with torch.no_grad():
+        out = m(ti.cuda(), tt.cuda())
+    err = (out.cpu() - ref).abs().max().item()
+    print("256x256 alpha max abs err", err)
+    assert err < ALPHA_TOL
+
+
+def test_no_fallback_on_cpu_tensor():
+    m = _model()
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 3, 64, 64), torch.zeros(1, 3, 1, 64, 64))
