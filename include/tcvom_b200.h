@@ -67,6 +67,9 @@ typedef struct {
   long long x_img_stride; /* elements between consecutive images of x (0: ih*iw*cin)         */
   int n, ih, iw, cin; /* cin multiple of 8                                                   */
   const float* w;     /* fp32 [wtaps][cin][cout] (wtaps >= max(wtap)+1)                      */
+  const void* w_tc;   /* optional bf16 hi/lo [2][w_tc_taps][cout][cin] copy of w (tcv_pack_weight_tc);
+                         when present and the shape qualifies, the tcgen05 implicit-GEMM path runs */
+  int w_tc_taps;
   int ntaps;
   int dy[TCV_MAX_TAPS], dx[TCV_MAX_TAPS];
   int wtap[TCV_MAX_TAPS]; /* weight slice used by tap t (identity for an ordinary conv)      */
@@ -90,6 +93,9 @@ typedef struct {
 } tcv_conv_desc;
 
 int tcv_conv2d(const tcv_conv_desc* d, tcv_stream_t stream);
+/* which kernel tcv_conv2d dispatches this descriptor to: 1 = tcgen05 implicit GEMM, 0 = CUDA-core
+ * gather conv (reporting helper for bench.py; no launch) */
+int tcv_conv2d_path(const tcv_conv_desc* d);
 
 /* sigma = u^T W v  (W viewed [rows, cols], rows = w_bar.shape[0]); then packs W/sigma into the
  * kernel layout fp32 [ntaps][cin_pad][cout].  `transposed` != 0: w_bar is [cin,cout,kh,kw]
@@ -98,6 +104,10 @@ int tcv_conv2d(const tcv_conv_desc* d, tcv_stream_t stream);
 int tcv_sn_fold_pack(const float* w_bar, const float* u, const float* v, int cout, int cin, int kh,
                      int kw, int transposed, int cin_pad, float* packed, float* sigma_out,
                      tcv_stream_t stream);
+
+/* bf16 hi/lo re-layout of a packed fp32 weight for the tcgen05 path:
+ * packed fp32 [taps][cin][cout] -> w_tc bf16 [2][taps][cout][cin] (plane 0 = hi, plane 1 = lo) */
+int tcv_pack_weight_tc(const float* packed, int taps, int cin, int cout, void* w_tc, tcv_stream_t stream);
 
 /* scale = gamma / sqrt(var+eps), shift = beta - mean*scale (eval BatchNorm2d as an affine) */
 int tcv_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
@@ -122,15 +132,18 @@ int tcv_unknown_os8(const void* x8, int n, int h, int w, float* unknown, tcv_str
 /* ---- guided contextual attention (GCA/ops.py:106-229), per image, P = (h/2)*(w/2) patches,
  * h,w = OS8 feature size, P_pad = P rounded up to 64.
  *  prep:    g split-bf16 [n,h/2,w/2,64] (guidance_conv output at stride 2), unknown fp32 [n,h,w]
- *           -> Q fp32 [n,P,576], Kn fp32 [n,P,576] (= Q/max(|Q|,1e-4) * per-key scale),
+ *           -> Q [n,P,576], Kn [n,P,576] (= Q/max(|Q|,1e-4) * per-key scale): fp32 when
+ *              bf16_split == 0, else split-bf16 planes [2][n][P][576];
  *              mm fp32 [n,P] ; scales fp32 [n,2] = (unknown_scale, known_scale)
- *  values:  feat split-bf16 [n,h,w,128] -> Vt fp32 [n,2048,P_pad]  (row = (ty*4+tx)*128+c)
- *  softmax: S fp32 [n,P,P_pad] in place: P = softmax_p(S - 1e4*[q==p]*mm[p]), pad cols = 0
+ *  values:  feat split-bf16 [n,h,w,128] -> Vt [n,2048,P_pad] (row = (ty*4+tx)*128+c), fp32 or
+ *           (bf16 != 0) plain bf16
+ *  softmax: S fp32 [n,P,P_pad]: P = softmax_p(S - 1e4*[q==p]*mm[p]), pad cols = 0; written in
+ *           place (P_bf16 == NULL) or as bf16 [n,P,P_pad] into P_bf16
  *  fold:    O fp32 [n,P,2048] -> Y split-bf16 [n,h,w,128] = fold(O; k4,s2,p1)/4            */
-int tcv_gca_prep(const void* g, const float* unknown, int n, int h, int w, float* Q, float* Kn,
-                 float* mm, float* scales, tcv_stream_t stream);
-int tcv_gca_values(const void* feat, int n, int h, int w, float* Vt, tcv_stream_t stream);
-int tcv_gca_softmax(float* S, const float* mm, int n, int P, int P_pad, tcv_stream_t stream);
+int tcv_gca_prep(const void* g, const float* unknown, int n, int h, int w, void* Q, void* Kn,
+                 float* mm, float* scales, int bf16_split, tcv_stream_t stream);
+int tcv_gca_values(const void* feat, int n, int h, int w, void* Vt, int bf16, tcv_stream_t stream);
+int tcv_gca_softmax(float* S, const float* mm, int n, int P, int P_pad, void* P_bf16, tcv_stream_t stream);
 int tcv_gca_fold(const float* O, int n, int h, int w, void* Y, tcv_stream_t stream);
 
 /* C[b] = A[b] * B[b]^T, fp32 row-major, A [M,K] lda, B [N,K] ldb, C [M,N] ldc, K % 8 == 0,
@@ -138,6 +151,13 @@ int tcv_gca_fold(const float* O, int n, int h, int w, void* Y, tcv_stream_t stre
 int tcv_gemm_tn_f32(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb,
                     int ldc, long long strideA, long long strideB, long long strideC, int batch,
                     tcv_stream_t stream);
+
+/* C[b] = A[b] * B[b]^T on the tensor cores (tcgen05, fp32 accumulate in TMEM).  A bf16 [batch][M][K]
+ * (nsplit == 3: hi plane at A, lo plane a_plane elements later; products Ahi.Bhi+Ahi.Blo+Alo.Bhi),
+ * B bf16 [batch][N][K] likewise; C fp32 or (out_bf16) bf16 [batch][M][ldc].  K % 64 == 0. */
+int tcv_gemm_tn_tc(const void* A, long long a_plane, const void* B, long long b_plane, void* C, int M, int N,
+                   int K, long long ldc, long long c_batch_stride, int batch, int nsplit, int out_bf16,
+                   tcv_stream_t stream);
 
 /* ---- temporal attention module core (VMN_model.py:27-68) after the q/k/v convolutions.
  * q, v, kb, kf: split-bf16 NHWC [B,H,W,C] (contiguous); mask fp32 full resolution

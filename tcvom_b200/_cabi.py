@@ -25,7 +25,7 @@ class ConvDesc(C.Structure):
     _fields_ = [
         ("x", c_void_p), ("x_plane", c_ll), ("x_img_stride", c_ll),
         ("n", c_int), ("ih", c_int), ("iw", c_int), ("cin", c_int),
-        ("w", c_void_p), ("ntaps", c_int), ("dy", c_int * MAX_TAPS), ("dx", c_int * MAX_TAPS),
+        ("w", c_void_p), ("w_tc", c_void_p), ("w_tc_taps", c_int), ("ntaps", c_int), ("dy", c_int * MAX_TAPS), ("dx", c_int * MAX_TAPS),
         ("wtap", c_int * MAX_TAPS),
         ("stride", c_int), ("pad_mode", c_int),
         ("y", c_void_p), ("y_f32", c_void_p),
@@ -43,6 +43,7 @@ SIGNATURES = {
     "tcv_last_error": (C.c_char_p, []),
     "tcv_launch_count": (c_ll, []),
     "tcv_conv2d": (c_int, [C.POINTER(ConvDesc), c_void_p]),
+    "tcv_conv2d_path": (c_int, [C.POINTER(ConvDesc)]),
     "tcv_sn_fold_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p]),
     "tcv_bn_fold": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_void_p]),
@@ -53,9 +54,12 @@ SIGNATURES = {
     "tcv_avgpool2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_unknown_os8": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_gca_prep": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                             c_void_p]),
-    "tcv_gca_values": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "tcv_gca_softmax": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+                             c_int, c_void_p]),
+    "tcv_gca_values": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "tcv_gca_softmax": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_pack_weight_tc": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_gemm_tn_tc": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_ll, c_ll, c_int,
+                               c_int, c_int, c_void_p]),
     "tcv_gca_fold": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_gemm_tn_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_ll, c_ll, c_ll, c_int, c_void_p]),

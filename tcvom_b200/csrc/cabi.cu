@@ -38,6 +38,14 @@ int tcv_version(void) { return 100; }
 const char* tcv_last_error(void) { return g_err; }
 long long tcv_launch_count(void) { return g_launches.load(); }
 
+int tcv_conv2d_path(const tcv_conv_desc* dp) {
+  if (!dp) return -1;
+  tcv_conv_desc d = *dp;
+  if (d.x_plane == 0) d.x_plane = (long long)d.n * d.ih * d.iw * d.cin;
+  if (d.x_img_stride == 0) d.x_img_stride = (long long)d.ih * d.iw * d.cin;
+  return conv2d_tc_supported(d) ? 1 : 0;
+}
+
 int tcv_conv2d(const tcv_conv_desc* dp, tcv_stream_t stream) {
   TCV_REQUIRE(dp, "conv2d: null descriptor");
   tcv_conv_desc d = *dp;

@@ -166,6 +166,17 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, const float* __r
   packed[i] = val;
 }
 
+__global__ void pack_weight_tc_kernel(const float* __restrict__ packed, int taps, int cin, int cout,
+                                      __nv_bfloat16* __restrict__ wtc) {
+  const long long total = (long long)taps * cout * cin;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ci = (int)(i % cin);
+  const int co = (int)((i / cin) % cout);
+  const int t = (int)(i / ((long long)cin * cout));
+  store1(wtc + i, total, packed[((long long)t * cin + ci) * cout + co]);
+}
+
 __global__ void bn_fold_kernel(const float* g, const float* b, const float* m, const float* v, float eps, int c,
                                float* scale, float* shift) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -274,6 +285,14 @@ int tcv_sn_fold_pack(const float* w_bar, const float* u, const float* v, int cou
   pack_weight_kernel<<<blocks(total), 256, 0, S(stream)>>>(w_bar, u ? sigma_out : nullptr, cout, cin, kh, kw,
                                                            transposed, cin_pad, packed);
   return launched("pack_weight_kernel");
+}
+
+int tcv_pack_weight_tc(const float* packed, int taps, int cin, int cout, void* w_tc, tcv_stream_t stream) {
+  TCV_REQUIRE(packed && w_tc && taps > 0 && cin > 0 && cout > 0, "pack_weight_tc: bad arguments");
+  const long long total = (long long)taps * cin * cout;
+  pack_weight_tc_kernel<<<blocks(total), 256, 0, S(stream)>>>(packed, taps, cin, cout,
+                                                              reinterpret_cast<__nv_bfloat16*>(w_tc));
+  return launched("pack_weight_tc_kernel");
 }
 
 int tcv_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps, int c,

@@ -45,9 +45,10 @@ __global__ void gca_scales_kernel(const float* __restrict__ unknown, int h, int 
 }
 
 // one warp per patch
+template <bool SPLIT>
 __global__ void gca_prep_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ unknown, int n,
-                                int h, int w, const float* __restrict__ scales, float* __restrict__ Q,
-                                float* __restrict__ Kn, float* __restrict__ mm) {
+                                int h, int w, const float* __restrict__ scales, void* __restrict__ Qv,
+                                void* __restrict__ Knv, float* __restrict__ mm) {
   const int hh = h / 2, ww = w / 2, P = hh * ww;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -76,18 +77,38 @@ __global__ void gca_prep_kernel(const __nv_bfloat16* __restrict__ g, const float
   const float m = usum > 0.f ? 1.f : 0.f;
   const float scale = m > 0.f ? scales[2 * img] : scales[2 * img + 1];
   const float inv = scale / fmaxf(sqrtf(ss), 1e-4f);
-  float* qo = Q + ((long long)img * P + p) * QD;
-  float* ko = Kn + ((long long)img * P + p) * QD;
+  const long long off = ((long long)img * P + p) * QD;
+  if (SPLIT) {
+    __nv_bfloat16* qo = reinterpret_cast<__nv_bfloat16*>(Qv) + off;
+    __nv_bfloat16* ko = reinterpret_cast<__nv_bfloat16*>(Knv) + off;
+    const long long plane = (long long)n * P * QD;
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    *reinterpret_cast<float2*>(qo + t * GC + 2 * lane) = make_float2(q[2 * t], q[2 * t + 1]);
-    *reinterpret_cast<float2*>(ko + t * GC + 2 * lane) = make_float2(q[2 * t] * inv, q[2 * t + 1] * inv);
+    for (int t = 0; t < 9; ++t) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(q[2 * t], h0, l0);
+      split_bf16(q[2 * t + 1], h1, l1);
+      *reinterpret_cast<uint32_t*>(qo + t * GC + 2 * lane) = pack2(h0, h1);
+      *reinterpret_cast<uint32_t*>(qo + plane + t * GC + 2 * lane) = pack2(l0, l1);
+      split_bf16(q[2 * t] * inv, h0, l0);
+      split_bf16(q[2 * t + 1] * inv, h1, l1);
+      *reinterpret_cast<uint32_t*>(ko + t * GC + 2 * lane) = pack2(h0, h1);
+      *reinterpret_cast<uint32_t*>(ko + plane + t * GC + 2 * lane) = pack2(l0, l1);
+    }
+  } else {
+    float* qo = reinterpret_cast<float*>(Qv) + off;
+    float* ko = reinterpret_cast<float*>(Knv) + off;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      *reinterpret_cast<float2*>(qo + t * GC + 2 * lane) = make_float2(q[2 * t], q[2 * t + 1]);
+      *reinterpret_cast<float2*>(ko + t * GC + 2 * lane) = make_float2(q[2 * t] * inv, q[2 * t + 1] * inv);
+    }
   }
   if (lane == 0) mm[(long long)img * P + p] = m;
 }
 
+template <bool BF16>
 __global__ void gca_values_kernel(const __nv_bfloat16* __restrict__ feat, int n, int h, int w, int P_pad,
-                                  float* __restrict__ Vt) {
+                                  void* __restrict__ Vt) {
   const int hh = h / 2, ww = w / 2, P = hh * ww;
   const long long total = (long long)n * VD * P_pad;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -102,12 +123,13 @@ __global__ void gca_values_kernel(const __nv_bfloat16* __restrict__ feat, int n,
     const int yy = reflect(2 * py + t / 4 - 1, h), xx = reflect(2 * px + t % 4 - 1, w);
     v = load1(feat + (((long long)img * h + yy) * w + xx) * FC + c, (long long)n * h * w * FC);
   }
-  Vt[i] = v;
+  if (BF16) reinterpret_cast<__nv_bfloat16*>(Vt)[i] = __float2bfloat16_rn(v);
+  else reinterpret_cast<float*>(Vt)[i] = v;
 }
 
 // one CTA per (row q, image): in-place masked softmax over keys
 __global__ void __launch_bounds__(256) gca_softmax_kernel(float* __restrict__ S, const float* __restrict__ mm, int P,
-                                                          int P_pad) {
+                                                          int P_pad, __nv_bfloat16* __restrict__ Pb) {
   __shared__ float red[32];
   __shared__ float bcast;
   const int q = blockIdx.x, img = blockIdx.y;
@@ -149,7 +171,12 @@ __global__ void __launch_bounds__(256) gca_softmax_kernel(float* __restrict__ S,
   }
   __syncthreads();
   const float inv = 1.0f / bcast;
-  for (int p = threadIdx.x; p < P_pad; p += 256) row[p] = p < P ? row[p] * inv : 0.f;
+  if (Pb) {
+    __nv_bfloat16* orow = Pb + ((long long)img * P + q) * P_pad;
+    for (int p = threadIdx.x; p < P_pad; p += 256) orow[p] = __float2bfloat16_rn(p < P ? row[p] * inv : 0.f);
+  } else {
+    for (int p = threadIdx.x; p < P_pad; p += 256) row[p] = p < P ? row[p] * inv : 0.f;
+  }
 }
 
 // Y[y][x][c] = 1/4 * sum over (ty,tx) with (y+1-ty), (x+1-tx) even and in range of O[q][(ty*4+tx)*128+c]
@@ -191,34 +218,42 @@ using namespace tcv;
 
 extern "C" {
 
-int tcv_gca_prep(const void* g, const float* unknown, int n, int h, int w, float* Q, float* Kn, float* mm,
-                 float* scales, tcv_stream_t stream) {
+int tcv_gca_prep(const void* g, const float* unknown, int n, int h, int w, void* Q, void* Kn, float* mm,
+                 float* scales, int bf16_split, tcv_stream_t stream) {
   TCV_REQUIRE(g && unknown && Q && Kn && mm && scales, "gca_prep: null pointer");
   TCV_REQUIRE(n > 0 && h >= 4 && w >= 4 && h % 2 == 0 && w % 2 == 0, "gca_prep: h,w must be even and >= 4");
   gca_scales_kernel<<<n, 256, 0, S(stream)>>>(unknown, h, w, scales);
   int rc = launched("gca_scales_kernel");
   if (rc) return rc;
   const long long warps = (long long)n * (h / 2) * (w / 2);
-  gca_prep_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, S(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(g), unknown, n, h, w, scales, Q, Kn, mm);
+  const unsigned grid = (unsigned)((warps * 32 + 255) / 256);
+  if (bf16_split)
+    gca_prep_kernel<true><<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(g), unknown, n, h, w,
+                                                       scales, Q, Kn, mm);
+  else
+    gca_prep_kernel<false><<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(g), unknown, n, h, w,
+                                                        scales, Q, Kn, mm);
   return launched("gca_prep_kernel");
 }
 
-int tcv_gca_values(const void* feat, int n, int h, int w, float* Vt, tcv_stream_t stream) {
+int tcv_gca_values(const void* feat, int n, int h, int w, void* Vt, int bf16, tcv_stream_t stream) {
   TCV_REQUIRE(feat && Vt, "gca_values: null pointer");
   TCV_REQUIRE(h % 2 == 0 && w % 2 == 0 && h >= 4 && w >= 4, "gca_values: h,w must be even and >= 4");
   const int P = (h / 2) * (w / 2), P_pad = (P + 63) / 64 * 64;
   const long long total = (long long)n * VD * P_pad;
-  gca_values_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(feat), n, h, w, P_pad, Vt);
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (bf16)
+    gca_values_kernel<true><<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(feat), n, h, w, P_pad, Vt);
+  else
+    gca_values_kernel<false><<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(feat), n, h, w, P_pad, Vt);
   return launched("gca_values_kernel");
 }
 
-int tcv_gca_softmax(float* Sm, const float* mm, int n, int P, int P_pad, tcv_stream_t stream) {
+int tcv_gca_softmax(float* Sm, const float* mm, int n, int P, int P_pad, void* P_bf16, tcv_stream_t stream) {
   TCV_REQUIRE(Sm && mm, "gca_softmax: null pointer");
   TCV_REQUIRE(P > 0 && P_pad >= P, "gca_softmax: bad P");
   dim3 grid(P, n);
-  gca_softmax_kernel<<<grid, 256, 0, S(stream)>>>(Sm, mm, P, P_pad);
+  gca_softmax_kernel<<<grid, 256, 0, S(stream)>>>(Sm, mm, P, P_pad, reinterpret_cast<__nv_bfloat16*>(P_bf16));
   return launched("gca_softmax_kernel");
 }
 

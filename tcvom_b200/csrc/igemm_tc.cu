@@ -1,0 +1,515 @@
+// tcgen05 implicit-GEMM kernel for sm_100a: one kernel template serves
+//   * the 3x3 / 1x1 / (4 phases of the) 4x4-stride-2-transposed convolutions  (EPI_CONV)
+//   * the two guided-contextual-attention GEMMs  scores = Q.Kn^T, O = P.Vt^T  (EPI_F32 / EPI_BF16)
+//
+// Structure (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0      TMA producer   cp.async.bulk.tensor (4-D NHWC activation boxes, 3-D weight boxes)
+//                              -> 64B/128B-swizzled K-major shared-memory tiles, mbarrier ring
+//   warp 1      MMA issuer     one elected thread issues tcgen05.mma (M=128, N=BN, K=16, bf16 ->
+//                              fp32 accumulators in TMEM); tcgen05.commit frees smem stages
+//   warps 2..5  epilogue       tcgen05.ld (32 lanes x 32 columns per warp) -> fused affine /
+//                              residual / activation -> split-bf16 NHWC (or fp32 / bf16 GEMM output)
+//
+// Precision ("bf16x3"): activations and weights are stored as bf16 hi/lo pairs; with NSPLIT==3 each
+// K step issues Ahi.Bhi + Ahi.Blo + Alo.Bhi, which keeps ~16 mantissa bits per operand (measured
+// 2e-5 max-abs on the alpha matte vs 1.6e-2 for plain bf16).  NSPLIT==1 is
+// plain bf16 (used for P.V where the operands are probabilities / averaged values).
+//
+// The A operand of a convolution is never materialised (no im2col): for filter tap (dy,dx) the
+// producer loads the box {BK channels, TW, TH, 1} at (c0, w0+dx, h0+dy, n); out-of-image
+// coordinates are zero-filled by TMA, which implements the zero padding.
+#include <cuda.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace tcv {
+
+enum { EPI_CONV = 0, EPI_F32 = 1, EPI_BF16 = 2 };
+
+struct TcParams {
+  int gh, gw, tiles_x, TH, TW;
+  int ntaps, kc_iters;
+  int dy[TCV_MAX_TAPS], dx[TCV_MAX_TAPS], wtap[TCV_MAX_TAPS];
+  int b_batched;  // GEMM mode: third weight-map coordinate = blockIdx.z instead of the tap index
+  // conv epilogue
+  int n_imgs, oh, ow, cout, oy_mul, oy_off, ox_mul, ox_off;
+  __nv_bfloat16* y;
+  float* y_f32;
+  const float *s1, *b1, *s2, *b2;
+  const __nv_bfloat16 *res1, *res2;
+  long long res1_plane, res2_plane;
+  int res1_shift, act;
+  // GEMM epilogue: C[batch][M][ldc]
+  void* c;
+  long long ldc, c_batch_stride;
+  int M, N;
+};
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU box -- trap after ~2 s instead.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("tcvom_b200: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+             threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout): rows of BK bf16
+// (64 B -> SWIZZLE_64B, 128 B -> SWIZZLE_128B), 8-row groups SBO apart.
+template <int BK>
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+  constexpr uint64_t row_bytes = BK * 2;
+  constexpr uint64_t sbo = (8 * row_bytes) >> 4;
+  constexpr uint64_t layout = row_bytes == 128 ? 2 : 4;  // SWIZZLE_128B : SWIZZLE_64B
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
+template <int BN>
+__device__ __forceinline__ uint32_t instr_desc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+template <int BN, int BK, int NSPLIT>
+struct TcCfg {
+  static constexpr int A_BYTES = 128 * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int PLANES = NSPLIT == 3 ? 2 : 1;
+  static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
+  // two CTAs per SM when the tile is small enough (their mainloop/epilogue phases overlap)
+  static constexpr int BUDGET = BN <= 128 ? 100 * 1024 : 200 * 1024;
+  static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, int BK, int NSPLIT, int EPI>
+__global__ void __launch_bounds__(192) igemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi,
+                                                       const __grid_constant__ CUtensorMap mapA_lo,
+                                                       const __grid_constant__ CUtensorMap mapB_hi,
+                                                       const __grid_constant__ CUtensorMap mapB_lo,
+                                                       const __grid_constant__ TcParams p) {
+  using Cfg = TcCfg<BN, BK, NSPLIT>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;  // full[STAGES], empty[STAGES], accum, tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = accum_bar + 8u;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
+  const int h0 = tile_y * p.TH, w0 = tile_x * p.TW;
+  const int n0 = blockIdx.y * BN;
+  const int img = blockIdx.z;
+  const int total_iters = p.ntaps * p.kc_iters;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB_hi) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int it = 0;
+      for (int t = 0; t < p.ntaps; ++t) {
+        const int cw = w0 + p.dx[t], ch = h0 + p.dy[t];
+        const int bz = p.b_batched ? img : p.wtap[t];
+        for (int kc = 0; kc < p.kc_iters; ++kc, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
+          mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+          tma_load_4d(st, &mapA_hi, full_bar(s), kc * BK, cw, ch, img);
+          tma_load_3d(st + Cfg::PLANES * Cfg::A_BYTES, &mapB_hi, full_bar(s), kc * BK, n0, bz);
+          if (NSPLIT == 3) {
+            tma_load_4d(st + Cfg::A_BYTES, &mapA_lo, full_bar(s), kc * BK, cw, ch, img);
+            tma_load_3d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapB_lo, full_bar(s), kc * BK, n0, bz);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc<BN>();
+      for (int it = 0; it < total_iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
+        const uint32_t a_hi = st, a_lo = st + Cfg::A_BYTES;
+        const uint32_t b_hi = st + Cfg::PLANES * Cfg::A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < BK / 16; ++ks) {
+          const uint64_t ah = smem_desc<BK>(a_hi + ks * 32), bh = smem_desc<BK>(b_hi + ks * 32);
+          tc_mma(tmem_d, ah, bh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          if (NSPLIT == 3) {
+            const uint64_t al = smem_desc<BK>(a_lo + ks * 32), bl = smem_desc<BK>(b_lo + ks * 32);
+            tc_mma(tmem_d, ah, bl, idesc, 1u);
+            tc_mma(tmem_d, al, bh, idesc, 1u);
+          }
+        }
+        tc_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+      }
+      tc_commit(accum_bar);       // accumulator complete
+    }
+  } else {
+    // ================================ epilogue (warps 2..5) ================================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;            // accumulator row = tile pixel
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
+    if (EPI == EPI_CONV) {
+      const int ty = r / p.TW, tx = r - ty * p.TW;
+      const int gy = h0 + ty, gx = w0 + tx;
+      const bool valid = gy < p.gh && gx < p.gw;
+      const int oy = gy * p.oy_mul + p.oy_off, ox = gx * p.ox_mul + p.ox_off;
+      const long long oplane = (long long)p.n_imgs * p.oh * p.ow * p.cout;
+      const long long obase = (((long long)img * p.oh + oy) * p.ow + ox) * p.cout + n0;
+      const int rh = p.oh >> p.res1_shift, rw = p.ow >> p.res1_shift;
+      const long long r1base = (((long long)img * rh + (oy >> p.res1_shift)) * rw + (ox >> p.res1_shift)) * p.cout + n0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tc_ld32(taddr + c0, v);
+        if (!valid) continue;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.s1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] *= __ldg(p.s1 + n0 + c0 + j);
+        }
+        if (p.b1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += __ldg(p.b1 + n0 + c0 + j);
+        }
+        if (p.res1) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float g[8];
+            load8(p.res1 + r1base + c0 + j, p.res1_plane, g);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[j + k] += g[k];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+        if (p.s2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = f[j] * __ldg(p.s2 + n0 + c0 + j) + __ldg(p.b2 + n0 + c0 + j);
+        }
+        if (p.res2) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float g[8];
+            load8(p.res2 + obase + c0 + j, p.res2_plane, g);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[j + k] += g[k];
+          }
+        }
+        if (p.y) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) store8(p.y + obase + c0 + j, oplane, f + j);
+        }
+        if (p.y_f32) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(p.y_f32 + obase + c0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        }
+      }
+    } else {
+      const int m = w0 + r;  // GEMM mode: TH == 1, tile rows are consecutive M indices
+      const bool valid = m < p.M;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tc_ld32(taddr + c0, v);
+        if (!valid) continue;
+        const int nb = n0 + c0;
+        if (nb >= p.N) continue;
+        if (EPI == EPI_F32) {
+          float* c = reinterpret_cast<float*>(p.c) + (long long)img * p.c_batch_stride + (long long)m * p.ldc + nb;
+          if (nb + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<uint4*>(c + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            for (int j = 0; j < 32 && nb + j < p.N; ++j) c[j] = __uint_as_float(v[j]);
+          }
+        } else {
+          __nv_bfloat16* c =
+              reinterpret_cast<__nv_bfloat16*>(p.c) + (long long)img * p.c_batch_stride + (long long)m * p.ldc + nb;
+          for (int j = 0; j < 32 && nb + j < p.N; ++j) c[j] = __float2bfloat16_rn(__uint_as_float(v[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+// bf16 tensor map, dims innermost-first; strides[i] = byte stride of dim i+1
+static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                    const cuuint32_t* box, int bk) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(TCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(TCV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return TCV_OK;
+}
+
+static void pick_tile(int gh, int gw, int* TH, int* TW) {
+  long long best = -1;
+  for (int tw = 128; tw >= 4; tw >>= 1) {
+    const int th = 128 / tw;
+    const long long cover = (long long)((gh + th - 1) / th) * th * ((gw + tw - 1) / tw) * tw;
+    if (best < 0 || cover < best) {
+      best = cover;
+      *TH = th;
+      *TW = tw;
+    }
+  }
+}
+
+struct TcOperands {
+  const __nv_bfloat16* a;   // activation / A matrix, hi plane
+  long long a_plane;        // elements hi->lo
+  int n, h, w, c;           // NHWC dims of A
+  long long a_img_stride;   // elements
+  const __nv_bfloat16* b;   // weights / B matrix [bz][rows][c], hi plane
+  long long b_plane;
+  int b_rows, b_z;
+};
+
+template <int BN, int BK, int NSPLIT, int EPI>
+static int launch_tc(const TcOperands& o, TcParams& p, cudaStream_t st) {
+  using Cfg = TcCfg<BN, BK, NSPLIT>;
+  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)o.c, (cuuint64_t)o.w, (cuuint64_t)o.h, (cuuint64_t)o.n};
+    cuuint64_t str[3] = {(cuuint64_t)o.c * 2, (cuuint64_t)o.w * o.c * 2, (cuuint64_t)o.a_img_stride * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+    int rc = make_map(&mA_hi, o.a, 4, dims, str, box, BK);
+    if (rc) return rc;
+    rc = make_map(&mA_lo, NSPLIT == 3 ? o.a + o.a_plane : o.a, 4, dims, str, box, BK);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)o.c, (cuuint64_t)o.b_rows, (cuuint64_t)o.b_z};
+    cuuint64_t str[2] = {(cuuint64_t)o.c * 2, (cuuint64_t)o.b_rows * o.c * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
+    int rc = make_map(&mB_hi, o.b, 3, dims, str, box, BK);
+    if (rc) return rc;
+    rc = make_map(&mB_lo, NSPLIT == 3 ? o.b + o.b_plane : o.b, 3, dims, str, box, BK);
+    if (rc) return rc;
+  }
+  auto kern = igemm_tc_kernel<BN, BK, NSPLIT, EPI>;
+  TCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));  // per device
+  p.tiles_x = (p.gw + p.TW - 1) / p.TW;
+  const int tiles_y = (p.gh + p.TH - 1) / p.TH;
+  const int nrows = EPI == EPI_CONV ? p.cout : p.N;
+  dim3 grid(p.tiles_x * tiles_y, (nrows + BN - 1) / BN, o.n);
+  kern<<<grid, 192, Cfg::SMEM, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, p);
+  return launched("igemm_tc_kernel");
+}
+
+// ---- convolution entry -----------------------------------------------------------------------
+// The packed tensor-core weights live next to the fp32 packed weights: tcv_conv_desc.w points at
+// fp32 [taps][cin][cout]; the bf16 hi/lo [taps][cout][cin] copy is passed through w_tc (see cabi).
+int conv2d_tc_supported(const tcv_conv_desc& d) {
+  if (!d.w_tc) return 0;
+  if (d.stride != 1 || d.pad_mode != TCV_PAD_ZERO) return 0;
+  if (d.cin % 32 != 0 || d.cout % 32 != 0) return 0;
+  if (d.x_img_stride != (long long)d.ih * d.iw * d.cin) return 0;
+  if (!d.y && d.y_f32 == nullptr) return 0;
+  return 1;
+}
+
+template <int BN>
+static int conv_tc_bn(const tcv_conv_desc& d, cudaStream_t st) {
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.gh = d.gh; p.gw = d.gw;
+  pick_tile(d.gh, d.gw, &p.TH, &p.TW);
+  p.ntaps = d.ntaps;
+  p.kc_iters = d.cin / 32;
+  for (int t = 0; t < d.ntaps; ++t) { p.dy[t] = d.dy[t]; p.dx[t] = d.dx[t]; p.wtap[t] = d.wtap[t]; }
+  p.b_batched = 0;
+  p.n_imgs = d.n; p.oh = d.oh; p.ow = d.ow; p.cout = d.cout;
+  p.oy_mul = d.oy_mul; p.oy_off = d.oy_off; p.ox_mul = d.ox_mul; p.ox_off = d.ox_off;
+  p.y = reinterpret_cast<__nv_bfloat16*>(d.y);
+  p.y_f32 = d.y_f32;
+  p.s1 = d.s1; p.b1 = d.b1; p.s2 = d.s2; p.b2 = d.b2;
+  p.res1 = reinterpret_cast<const __nv_bfloat16*>(d.res1);
+  p.res2 = reinterpret_cast<const __nv_bfloat16*>(d.res2);
+  p.res1_plane = d.res1_plane; p.res2_plane = d.res2_plane; p.res1_shift = d.res1_shift; p.act = d.act;
+  TcOperands o;
+  o.a = reinterpret_cast<const __nv_bfloat16*>(d.x);
+  o.a_plane = d.x_plane;
+  o.n = d.n; o.h = d.ih; o.w = d.iw; o.c = d.cin; o.a_img_stride = d.x_img_stride;
+  o.b = reinterpret_cast<const __nv_bfloat16*>(d.w_tc);
+  o.b_rows = d.cout;
+  o.b_z = d.w_tc_taps;
+  o.b_plane = (long long)d.w_tc_taps * d.cout * d.cin;
+  return launch_tc<BN, 32, 3, EPI_CONV>(o, p, st);
+}
+
+int conv2d_tc(const tcv_conv_desc& d, cudaStream_t st) {
+  if (d.cout % 128 == 0) return conv_tc_bn<128>(d, st);
+  if (d.cout % 64 == 0) return conv_tc_bn<64>(d, st);
+  return conv_tc_bn<32>(d, st);
+}
+
+}  // namespace tcv
+
+using namespace tcv;
+
+// C[b] = A[b] * B[b]^T on tensor cores.  A: bf16 [batch][M][K] (hi plane; lo plane a_plane elements
+// later when nsplit == 3), B: bf16 [batch][N][K]; C: fp32 (out_bf16 == 0) or bf16 [batch][M][ldc].
+// K % 64 == 0.
+extern "C" int tcv_gemm_tn_tc(const void* A, long long a_plane, const void* B, long long b_plane, void* C, int M,
+                              int N, int K, long long ldc, long long c_batch_stride, int batch, int nsplit,
+                              int out_bf16, tcv_stream_t stream) {
+  TCV_REQUIRE(A && B && C, "gemm_tn_tc: null pointer");
+  TCV_REQUIRE(M > 0 && N > 0 && K > 0 && K % 64 == 0, "gemm_tn_tc: K must be a positive multiple of 64");
+  const int bk = nsplit == 3 ? 32 : 64;
+  TCV_REQUIRE(nsplit == 1 || nsplit == 3, "gemm_tn_tc: nsplit must be 1 or 3");
+  TCV_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0,
+              "gemm_tn_tc: pointers must be 16-byte aligned");
+  TCV_REQUIRE(out_bf16 || ldc % 4 == 0, "gemm_tn_tc: ldc must be a multiple of 4 for fp32 output");
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.gh = 1; p.gw = M; p.TH = 1; p.TW = 128;
+  p.ntaps = 1; p.kc_iters = K / bk;
+  p.b_batched = 1;
+  p.c = C; p.ldc = ldc; p.c_batch_stride = c_batch_stride; p.M = M; p.N = N;
+  TcOperands o;
+  o.a = reinterpret_cast<const __nv_bfloat16*>(A);
+  o.a_plane = a_plane;
+  o.n = batch; o.h = 1; o.w = M; o.c = K; o.a_img_stride = (long long)M * K;
+  o.b = reinterpret_cast<const __nv_bfloat16*>(B);
+  o.b_plane = b_plane;
+  o.b_rows = N; o.b_z = batch;
+  cudaStream_t st = S(stream);
+  if (nsplit == 3) {
+    if (out_bf16) return launch_tc<128, 32, 3, EPI_BF16>(o, p, st);
+    return launch_tc<128, 32, 3, EPI_F32>(o, p, st);
+  }
+  if (out_bf16) return launch_tc<256, 64, 1, EPI_BF16>(o, p, st);
+  return launch_tc<256, 64, 1, EPI_F32>(o, p, st);
+}

@@ -10,6 +10,7 @@ Program restated from (reference checkout):
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -51,6 +52,7 @@ class Plan:
 
     def __init__(self):
         self.calls: List[Tuple] = []
+        self.meta: List[dict] = []
         self.keep: List = []
         self.io: Dict[str, torch.Tensor] = {}
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -61,6 +63,22 @@ class Plan:
             rc = fn(*args, stream_ptr)
             if rc != 0:
                 _cabi.check(rc, what)
+
+    def replay_timed(self, device) -> List[float]:
+        """Eager replay on the current stream with a CUDA-event pair around every call; returns
+        milliseconds per call (same order as ``calls`` / ``meta``).  Measurement helper for bench.py."""
+        st = torch.cuda.current_stream(device)
+        evs = []
+        for fn, args, what in self.calls:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            rc = fn(*args, st.cuda_stream)
+            e1.record(st)
+            if rc != 0:
+                _cabi.check(rc, what)
+            evs.append((e0, e1))
+        st.synchronize()
+        return [a.elapsed_time(b) for a, b in evs]
 
 
 def _k(prefix: str, name: str) -> str:
@@ -81,7 +99,10 @@ class GcaVmnEngine:
         self._tensors = None
         self.plans: Dict[Tuple, Plan] = {}
         self._rec: Optional[Plan] = None
-        self.use_graphs = True
+        self.use_graphs = os.environ.get("TCV_GRAPHS", "1") == "1"
+        # tcgen05 paths (default on); the CUDA-core fp32 paths stay available as the exact cross-check
+        self.use_tc_conv = os.environ.get("TCV_TC_CONV", "1") == "1"
+        self.use_tc_attn = os.environ.get("TCV_TC_ATTN", "1") == "1"
 
     # ------------------------------------------------------------------ weights
     def _named(self) -> Dict[str, torch.Tensor]:
@@ -154,19 +175,28 @@ class GcaVmnEngine:
         ent = self.w.get(p)
         if ent is None:
             ent = self.w[p] = dict(w=torch.empty((kh * kw, cin_pad, cout), dtype=torch.float32, device=wbar.device),
-                                   cout=cout, cin=cin_pad, k=kh, transposed=transposed)
+                                   cout=cout, cin=cin_pad, cin_real=cin, k=kh, transposed=transposed)
         _cabi.check(L.tcv_sn_fold_pack(wbar.data_ptr(), u.data_ptr() if u is not None else None,
                                        v.data_ptr() if v is not None else None, cout, cin, kh, kw,
                                        1 if transposed else 0, cin_pad, ent["w"].data_ptr(),
                                        sig.data_ptr() if sig is not None else None, st), "sn_fold_pack")
+        if cin_pad % 32 == 0 and cout % 32 == 0:
+            if "w_tc" not in ent:
+                ent["w_tc"] = torch.empty((2, kh * kw, cout, cin_pad), dtype=torch.bfloat16, device=wbar.device)
+            _cabi.check(L.tcv_pack_weight_tc(ent["w"].data_ptr(), kh * kw, cin_pad, cout, ent["w_tc"].data_ptr(), st),
+                        "pack_weight_tc")
 
     # ------------------------------------------------------------------ call recording
-    def _call(self, fn_name: str, *args):
+    def _call(self, fn_name: str, *args, meta: Optional[dict] = None):
         fn = getattr(_cabi.lib(), fn_name)
         st = torch.cuda.current_stream(self.device).cuda_stream
         _cabi.check(fn(*args, st), fn_name)
         if self._rec is not None:
             self._rec.calls.append((fn, args, fn_name))
+            m = dict(kind=fn_name, flops=0, bytes=0)
+            if meta:
+                m.update(meta)
+            self._rec.meta.append(m)
 
     def _keep(self, *objs):
         if self._rec is not None:
@@ -201,7 +231,7 @@ class GcaVmnEngine:
         d = self._desc(x, ent["w"].data_ptr(), taps, stride, pad, y, oh, ow, cout, oh, ow, 1, 0, 1, 0, wkey, bn, bias,
                        act, res1, res1_shift, bn2, res2, f32_ptr if f32_ptr else
                        (f32_out.data_ptr() if f32_out is not None else 0))
-        self._call("tcv_conv2d", C.byref(d))
+        self._call("tcv_conv2d", C.byref(d), meta=self._conv_meta(d, wkey, x, k, stride))
         return y
 
     def deconv4x4s2(self, x: Act, wkey: str, *, bn: str, act, res2: Optional[Act] = None) -> Act:
@@ -220,8 +250,24 @@ class GcaVmnEngine:
                 wtap = [ky * 4 + kx for ky, dy in kys for kx, dx in kxs]
                 d = self._desc(x, ent["w"].data_ptr(), taps, 1, PAD_ZERO, y, oh, ow, cout, x.h, x.w, 2, py, 2, px,
                                wkey, bn, False, act, None, 0, None, res2, 0, wtap=wtap)
-                self._call("tcv_conv2d", C.byref(d))
+                self._call("tcv_conv2d", C.byref(d), meta=self._conv_meta(d, wkey, x, 4, 2))
         return y
+
+    def _conv_meta(self, d: ConvDesc, wkey: str, x: Act, k: int, stride: int) -> dict:
+        """Algorithmic work of one conv launch: 2*MACs over the real (unpadded) channels; bytes = every
+        input/output/residual element moved once in split-bf16 (4 B/element) + the weights once."""
+        cin_real = self.w[wkey].get("cin_real", d.cin)
+        px = d.n * d.gh * d.gw
+        flops = 2 * px * d.ntaps * cin_real * d.cout
+        in_px = d.n * d.ih * d.iw if d.oy_mul == 1 else px
+        nbytes = 4 * (in_px * d.cin + px * d.cout) + 4 * d.ntaps * d.cin * d.cout
+        if d.res1:
+            nbytes += 4 * (px >> (2 * d.res1_shift)) * d.cout
+        if d.res2:
+            nbytes += 4 * px * d.cout
+        path = "tc" if _cabi.lib().tcv_conv2d_path(C.byref(d)) == 1 else "direct"
+        return dict(kind=f"conv_{path}", layer=wkey, flops=flops, bytes=nbytes,
+                    shape=f"{d.cin}->{d.cout} k{k} s{stride} @{d.gh}x{d.gw} n{d.n}")
 
     def _desc(self, x: Act, wptr, taps, stride, pad, y: Optional[Act], oh, ow, cout, gh, gw, oy_mul, oy_off, ox_mul,
               ox_off, wkey, bn, bias, act, res1, res1_shift, bn2, res2, f32_ptr, wtap=None) -> ConvDesc:
@@ -229,6 +275,9 @@ class GcaVmnEngine:
         d.x, d.x_plane, d.x_img_stride = x.ptr, x.plane, x.img_elems
         d.n, d.ih, d.iw, d.cin = x.n, x.h, x.w, x.c
         d.w, d.ntaps = wptr, len(taps)
+        ent = self.w[wkey]
+        if self.use_tc_conv and "w_tc" in ent:
+            d.w_tc, d.w_tc_taps = ent["w_tc"].data_ptr(), ent["k"] * ent["k"]
         for i, (dy, dx) in enumerate(taps):
             d.dy[i], d.dx[i] = dy, dx
             d.wtap[i] = wtap[i] if wtap is not None else i
@@ -269,21 +318,45 @@ class GcaVmnEngine:
         g = self.conv(im_fea, _k(p, "guidance_conv"), stride=2, bias=True)       # 1x1, then [::2, ::2]
         P = (h // 2) * (w // 2)
         P_pad = (P + 63) // 64 * 64
-        Q = self._empty((n, P, 576))
-        Kn = self._empty((n, P, 576))
         mm = self._empty((n, P))
         scales = self._empty((n, 2))
-        self._call("tcv_gca_prep", g.ptr, unknown.data_ptr(), n, h, w, Q.data_ptr(), Kn.data_ptr(), mm.data_ptr(),
-                   scales.data_ptr())
-        Vt = self._empty((n, 2048, P_pad))
-        self._call("tcv_gca_values", feat.ptr, n, h, w, Vt.data_ptr())
-        Sm = self._empty((n, P, P_pad))
-        self._call("tcv_gemm_tn_f32", Q.data_ptr(), Kn.data_ptr(), Sm.data_ptr(), P, P, 576, 576, 576, P_pad,
-                   P * 576, P * 576, P * P_pad, n)
-        self._call("tcv_gca_softmax", Sm.data_ptr(), mm.data_ptr(), n, P, P_pad)
         O = self._empty((n, P, 2048))
-        self._call("tcv_gemm_tn_f32", Sm.data_ptr(), Vt.data_ptr(), O.data_ptr(), P, 2048, P_pad, P_pad, P_pad, 2048,
-                   P * P_pad, 2048 * P_pad, P * 2048, n)
+        if self.use_tc_attn:
+            # tcgen05 path: scores in bf16x3 (fp32-accurate logits), probabilities and values in bf16
+            Q = self._empty((2, n, P, 576), torch.bfloat16)
+            Kn = self._empty((2, n, P, 576), torch.bfloat16)
+            self._call("tcv_gca_prep", g.ptr, unknown.data_ptr(), n, h, w, Q.data_ptr(), Kn.data_ptr(),
+                       mm.data_ptr(), scales.data_ptr(), 1)
+            Vt = self._empty((n, 2048, P_pad), torch.bfloat16)
+            self._call("tcv_gca_values", feat.ptr, n, h, w, Vt.data_ptr(), 1)
+            Sm = self._empty((n, P, P_pad))
+            self._call("tcv_gemm_tn_tc", Q.data_ptr(), n * P * 576, Kn.data_ptr(), n * P * 576, Sm.data_ptr(), P, P,
+                       576, P_pad, P * P_pad, n, 3, 0,
+                       meta=dict(kind="gca_scores_gemm_tc", flops=2 * n * P * P * 576,
+                                 bytes=n * (2 * 4 * P * 576 + 4 * P * P)))
+            Pb = self._empty((n, P, P_pad), torch.bfloat16)
+            self._call("tcv_gca_softmax", Sm.data_ptr(), mm.data_ptr(), n, P, P_pad, Pb.data_ptr(),
+                       meta=dict(kind="tcv_gca_softmax", bytes=n * P * P * 10))
+            self._call("tcv_gemm_tn_tc", Pb.data_ptr(), 0, Vt.data_ptr(), 0, O.data_ptr(), P, 2048, P_pad, 2048,
+                       P * 2048, n, 1, 0,
+                       meta=dict(kind="gca_pv_gemm_tc", flops=2 * n * P * P * 2048,
+                                 bytes=n * (2 * P * P + 2 * 2048 * P + 4 * P * 2048)))
+        else:
+            Q = self._empty((n, P, 576))
+            Kn = self._empty((n, P, 576))
+            self._call("tcv_gca_prep", g.ptr, unknown.data_ptr(), n, h, w, Q.data_ptr(), Kn.data_ptr(),
+                       mm.data_ptr(), scales.data_ptr(), 0)
+            Vt = self._empty((n, 2048, P_pad))
+            self._call("tcv_gca_values", feat.ptr, n, h, w, Vt.data_ptr(), 0)
+            Sm = self._empty((n, P, P_pad))
+            self._call("tcv_gemm_tn_f32", Q.data_ptr(), Kn.data_ptr(), Sm.data_ptr(), P, P, 576, 576, 576, P_pad,
+                       P * 576, P * 576, P * P_pad, n,
+                       meta=dict(kind="gca_scores_gemm", flops=2 * n * P * P * 576, bytes=4 * n * (2 * P * 576 + P * P)))
+            self._call("tcv_gca_softmax", Sm.data_ptr(), mm.data_ptr(), n, P, P_pad, None)
+            self._call("tcv_gemm_tn_f32", Sm.data_ptr(), Vt.data_ptr(), O.data_ptr(), P, 2048, P_pad, P_pad, P_pad, 2048,
+                       P * P_pad, 2048 * P_pad, P * 2048, n,
+                       meta=dict(kind="gca_pv_gemm", flops=2 * n * P * P * 2048,
+                                 bytes=4 * n * (P * P + 2048 * P + P * 2048)))
         Y = self._act(n, h, w, 128)
         self._call("tcv_gca_fold", O.data_ptr(), n, h, w, Y.ptr)
         self.last_gca_scales = scales

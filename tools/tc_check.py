@@ -1,0 +1,139 @@
+"""Standalone checks of the tcgen05 kernels against fp32/fp64 references (each case in its own
+process so a trapped kernel cannot poison the others).  python tools/tc_check.py [case ...]"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def split(x):
+    import torch
+    hi = x.bfloat16()
+    lo = (x - hi.float()).bfloat16()
+    return torch.stack([hi, lo]).contiguous()
+
+
+def case_gemm(nsplit, M, N, K, batch, out_bf16=0):
+    import torch
+    from tcvom_b200 import _cabi
+    L = _cabi.lib()
+    torch.manual_seed(0)
+    dev = "cuda"
+    A = torch.randn(batch, M, K, device=dev)
+    B = torch.randn(batch, N, K, device=dev)
+    ldc = (N + 63) // 64 * 64
+    Cm = torch.full((batch, M, ldc), 7.0, device=dev, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    st = torch.cuda.current_stream().cuda_stream
+    if nsplit == 3:
+        As, Bs = split(A), split(B)
+        ref = torch.matmul(A.double(), B.double().transpose(1, 2))
+        rc = L.tcv_gemm_tn_tc(As.data_ptr(), batch * M * K, Bs.data_ptr(), batch * N * K, Cm.data_ptr(), M, N, K, ldc,
+                              M * ldc, batch, 3, out_bf16, st)
+    else:
+        Ab, Bb = A.bfloat16(), B.bfloat16()
+        ref = torch.matmul(Ab.double(), Bb.double().transpose(1, 2))
+        rc = L.tcv_gemm_tn_tc(Ab.data_ptr(), 0, Bb.data_ptr(), 0, Cm.data_ptr(), M, N, K, ldc, M * ldc, batch, 1,
+                              out_bf16, st)
+    _cabi.check(rc, "gemm_tn_tc")
+    torch.cuda.synchronize()
+    got = Cm[:, :, :N].double()
+    err = (got - ref).abs().max().item()
+    rel = err / ref.abs().max().item()
+    pad_ok = bool((Cm[:, :, N:].float() == 7.0).all()) if ldc > N else True
+    print(f"gemm nsplit={nsplit} M={M} N={N} K={K} b={batch} bf16out={out_bf16}: max abs err {err:.3e} rel {rel:.3e} pad_untouched={pad_ok}")
+    tol = 2e-2 if out_bf16 else (1e-4 if nsplit == 3 else 1e-5)
+    assert rel < tol and pad_ok
+
+
+def case_conv(cin, cout, h, w, n, kind):
+    import torch
+    from tcvom_b200 import _cabi
+    from tcvom_b200._cabi import ConvDesc
+    L = _cabi.lib()
+    torch.manual_seed(1)
+    dev = "cuda"
+    st = torch.cuda.current_stream().cuda_stream
+    x = split(torch.randn(n, h, w, cin, device=dev))
+    if kind == "3x3":
+        taps = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]; wt = list(range(9)); ntw = 9
+        oh, ow, gh, gw, mul, offs = h, w, h, w, 1, (0, 0)
+    elif kind == "1x1":
+        taps = [(0, 0)]; wt = [0]; ntw = 1
+        oh, ow, gh, gw, mul, offs = h, w, h, w, 1, (0, 0)
+    else:  # one phase (py=1, px=0) of the 4x4 stride-2 transposed conv
+        kys = [(0, 1), (2, 0)]; kxs = [(1, 0), (3, -1)]
+        taps = [(dy, dx) for ky, dy in kys for kx, dx in kxs]
+        wt = [ky * 4 + kx for ky, dy in kys for kx, dx in kxs]; ntw = 16
+        oh, ow, gh, gw, mul, offs = 2 * h, 2 * w, h, w, 2, (1, 0)
+    wf = (torch.randn(ntw, cin, cout, device=dev) / (cin * len(taps)) ** 0.5).contiguous()
+    wtc = torch.empty((2, ntw, cout, cin), dtype=torch.bfloat16, device=dev)
+    _cabi.check(L.tcv_pack_weight_tc(wf.data_ptr(), ntw, cin, cout, wtc.data_ptr(), st), "pack")
+    s1 = torch.rand(cout, device=dev) + 0.5; b1 = torch.randn(cout, device=dev)
+    s2 = torch.rand(cout, device=dev) + 0.5; b2 = torch.randn(cout, device=dev)
+    res1 = split(torch.randn(n, oh // 2, ow // 2, cout, device=dev))
+    res2 = split(torch.randn(n, oh, ow, cout, device=dev))
+    outs = []
+    for use_tc in (0, 1):
+        y = torch.zeros((2, n, oh, ow, cout), dtype=torch.bfloat16, device=dev)
+        yf = torch.zeros((n, oh, ow, cout), dtype=torch.float32, device=dev)
+        d = ConvDesc()
+        d.x = x.data_ptr(); d.n, d.ih, d.iw, d.cin = n, h, w, cin
+        d.w = wf.data_ptr(); d.ntaps = len(taps)
+        if use_tc:
+            d.w_tc = wtc.data_ptr(); d.w_tc_taps = ntw
+        for i, (dy, dx) in enumerate(taps):
+            d.dy[i], d.dx[i], d.wtap[i] = dy, dx, wt[i]
+        d.stride, d.pad_mode = 1, 0
+        d.y = y.data_ptr(); d.y_f32 = yf.data_ptr()
+        d.oh, d.ow, d.cout, d.gh, d.gw = oh, ow, cout, gh, gw
+        d.oy_mul, d.oy_off, d.ox_mul, d.ox_off = mul, offs[0], mul, offs[1]
+        d.s1, d.b1 = s1.data_ptr(), b1.data_ptr()
+        d.res1, d.res1_shift = res1.data_ptr(), 1
+        d.act = 2
+        d.s2, d.b2 = s2.data_ptr(), b2.data_ptr()
+        d.res2 = res2.data_ptr()
+        assert L.tcv_conv2d_path(C.byref(d)) == use_tc, "dispatch did not pick the expected path"
+        _cabi.check(L.tcv_conv2d(C.byref(d), st), "conv2d")
+        torch.cuda.synchronize()
+        outs.append((y[0].float() + y[1].float(), yf.clone()))
+    err = (outs[0][1] - outs[1][1]).abs().max().item()
+    errs = (outs[0][0] - outs[1][0]).abs().max().item()
+    mag = outs[0][1].abs().max().item()
+    print(f"conv {kind} {cin}->{cout} {h}x{w} n={n}: tc vs direct max abs err f32 {err:.3e} split {errs:.3e} (max |y| {mag:.2f})")
+    assert err < 2e-4 * max(1.0, mag) and errs < 2e-4 * max(1.0, mag)
+
+
+CASES = {
+    "gemm1_small": lambda: case_gemm(1, 128, 256, 64, 1),
+    "gemm1": lambda: case_gemm(1, 300, 520, 192, 2),
+    "gemm1_bf16out": lambda: case_gemm(1, 300, 520, 192, 2, 1),
+    "gemm3_small": lambda: case_gemm(3, 128, 128, 64, 1),
+    "gemm3": lambda: case_gemm(3, 1000, 1000, 576, 2),
+    "conv3x3_64_128": lambda: case_conv(64, 128, 20, 28, 2, "3x3"),
+    "conv3x3_32_32": lambda: case_conv(32, 32, 16, 48, 1, "3x3"),
+    "conv3x3_256_256": lambda: case_conv(256, 256, 10, 12, 3, "3x3"),
+    "conv1x1_128_64": lambda: case_conv(128, 64, 16, 16, 2, "1x1"),
+    "deconv_64_64": lambda: case_conv(64, 64, 9, 14, 2, "deconv"),
+}
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(CASES)
+    if len(names) == 1 and os.environ.get("TC_CHECK_CHILD") == "1":
+        CASES[names[0]]()
+        sys.exit(0)
+    bad = 0
+    for nme in names:
+        env = dict(os.environ, TC_CHECK_CHILD="1")
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), nme], env=env, capture_output=True,
+                               text=True, timeout=120)
+            out = (r.stdout + r.stderr).strip().splitlines()
+            print(f"[{nme}] rc={r.returncode} :: " + " | ".join(out[-4:]), flush=True)
+            bad += r.returncode != 0
+        except subprocess.TimeoutExpired:
+            print(f"[{nme}] TIMEOUT", flush=True)
+            bad += 1
+    sys.exit(1 if bad else 0)
