@@ -252,7 +252,7 @@ def run_native(args, rank, world, local_rank):
             total = sum(k["ms"] for k in kinds.values())
             top_name, top = max(kinds.items(), key=lambda kv: kv[1]["ms"])
             pk = peaks()
-            tensor_kinds = ("gca_scores_gemm", "gca_pv_gemm", "conv_tc")
+            tensor_kinds = ("gca_scores_gemm", "gca_pv_gemm", "conv_tc", "gca_scores_gemm_tc", "gca_pv_gemm_tc")
             if top_name in tensor_kinds:
                 ach = top["flops"] / (top["ms"] * 1e-3) / 1e12
                 roof = dict(bound="tensor", achieved=ach, peak=pk["tf_sustained"], unit="TFLOP/s",
@@ -263,6 +263,10 @@ def run_native(args, rank, world, local_rank):
             roof.update(kernel=top_name, launches_per_step=top["n"], avg_launch_ms=top["ms"] / top["n"],
                         share_of_step=top["ms"] / total, peak_source=pk["source"],
                         breakdown_ms={k: round(v["ms"], 3) for k, v in sorted(kinds.items(), key=lambda kv: -kv[1]["ms"])})
+            if args.dump_calls:
+                with open(args.dump_calls, "w") as f:
+                    for m, t in sorted(zip(plan.meta, acc), key=lambda mt: -mt[1]):
+                        f.write(json.dumps(dict(ms=round(t, 4), **{k: v for k, v in m.items()})) + "\n")
             whole = GFLOP_PER_WINDOW / (ms / args.steps * 1e-3) / 1e3
             roof["whole_step_tflops"] = whole
             roof["whole_step_frac_of_tensor_peak"] = whole / pk["tf_sustained"]
@@ -310,6 +314,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-calls", default=None, help="write the per-launch timing table (JSON lines) here")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

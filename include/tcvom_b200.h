@@ -135,15 +135,16 @@ int tcv_unknown_os8(const void* x8, int n, int h, int w, float* unknown, tcv_str
  *           -> Q [n,P,576], Kn [n,P,576] (= Q/max(|Q|,1e-4) * per-key scale): fp32 when
  *              bf16_split == 0, else split-bf16 planes [2][n][P][576];
  *              mm fp32 [n,P] ; scales fp32 [n,2] = (unknown_scale, known_scale)
- *  values:  feat split-bf16 [n,h,w,128] -> Vt [n,2048,P_pad] (row = (ty*4+tx)*128+c), fp32 or
- *           (bf16 != 0) plain bf16
- *  softmax: S fp32 [n,P,P_pad]: P = softmax_p(S - 1e4*[q==p]*mm[p]), pad cols = 0; written in
- *           place (P_bf16 == NULL) or as bf16 [n,P,P_pad] into P_bf16
+ *  values:  feat split-bf16 [n,h,w,128] -> Vt [n,2048,P_pad] (row = (ty*4+tx)*128+c);
+ *           mode 0 fp32, 1 bf16, 2 split-bf16 planes [2][n][2048][P_pad], 3 fp16
+ *  softmax: S fp32 [n,P,P_pad]: P = softmax_p(S - 1e4*[q==p]*mm[p]), pad cols = 0; mode 0 writes
+ *           fp32 in place, modes 1/2/3 write bf16 / split-bf16 planes / fp16 [n,P,P_pad] into P_out
  *  fold:    O fp32 [n,P,2048] -> Y split-bf16 [n,h,w,128] = fold(O; k4,s2,p1)/4            */
 int tcv_gca_prep(const void* g, const float* unknown, int n, int h, int w, void* Q, void* Kn,
                  float* mm, float* scales, int bf16_split, tcv_stream_t stream);
-int tcv_gca_values(const void* feat, int n, int h, int w, void* Vt, int bf16, tcv_stream_t stream);
-int tcv_gca_softmax(float* S, const float* mm, int n, int P, int P_pad, void* P_bf16, tcv_stream_t stream);
+int tcv_gca_values(const void* feat, int n, int h, int w, void* Vt, int mode, tcv_stream_t stream);
+int tcv_gca_softmax(float* S, const float* mm, int n, int P, int P_pad, void* P_out, int mode,
+                    tcv_stream_t stream);
 int tcv_gca_fold(const float* O, int n, int h, int w, void* Y, tcv_stream_t stream);
 
 /* C[b] = A[b] * B[b]^T, fp32 row-major, A [M,K] lda, B [N,K] ldb, C [M,N] ldc, K % 8 == 0,
@@ -154,10 +155,11 @@ int tcv_gemm_tn_f32(const float* A, const float* B, float* C, int M, int N, int 
 
 /* C[b] = A[b] * B[b]^T on the tensor cores (tcgen05, fp32 accumulate in TMEM).  A bf16 [batch][M][K]
  * (nsplit == 3: hi plane at A, lo plane a_plane elements later; products Ahi.Bhi+Ahi.Blo+Alo.Bhi),
- * B bf16 [batch][N][K] likewise; C fp32 or (out_bf16) bf16 [batch][M][ldc].  K % 64 == 0. */
+ * B bf16 [batch][N][K] likewise; C fp32 or (out_bf16) bf16 [batch][M][ldc].  K % 64 == 0.
+ * in_fp16 != 0 (nsplit == 1 only): A and B hold IEEE half instead of bf16. */
 int tcv_gemm_tn_tc(const void* A, long long a_plane, const void* B, long long b_plane, void* C, int M, int N,
                    int K, long long ldc, long long c_batch_stride, int batch, int nsplit, int out_bf16,
-                   tcv_stream_t stream);
+                   int in_fp16, tcv_stream_t stream);
 
 /* ---- temporal attention module core (VMN_model.py:27-68) after the q/k/v convolutions.
  * q, v, kb, kf: split-bf16 NHWC [B,H,W,C] (contiguous); mask fp32 full resolution

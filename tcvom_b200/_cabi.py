@@ -56,10 +56,10 @@ SIGNATURES = {
     "tcv_gca_prep": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_int, c_void_p]),
     "tcv_gca_values": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
-    "tcv_gca_softmax": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_gca_softmax": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "tcv_pack_weight_tc": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_gemm_tn_tc": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_ll, c_ll, c_int,
-                               c_int, c_int, c_void_p]),
+                               c_int, c_int, c_int, c_void_p]),
     "tcv_gca_fold": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_gemm_tn_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_ll, c_ll, c_ll, c_int, c_void_p]),

@@ -9,6 +9,8 @@
 //   Vt[(ty*4+tx)*128+c][p]  = feat_reflect[2py+ty-1][2px+tx-1][c]               (ops.py:112-118)
 // The (kh,kw,c) ordering of the 576/2048 axes differs from the reference's (c,kh,kw); inner
 // products and the fold are invariant to that permutation as long as both sides agree.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace tcv {
@@ -106,7 +108,17 @@ __global__ void gca_prep_kernel(const __nv_bfloat16* __restrict__ g, const float
   if (lane == 0) mm[(long long)img * P + p] = m;
 }
 
-template <bool BF16>
+// store one value in the GEMM operand format `MODE`: 0 fp32, 1 bf16, 2 split-bf16 (lo plane `plane`
+// elements later), 3 fp16
+template <int MODE>
+__device__ __forceinline__ void store_operand(void* base, long long i, long long plane, float v) {
+  if (MODE == 0) reinterpret_cast<float*>(base)[i] = v;
+  else if (MODE == 1) reinterpret_cast<__nv_bfloat16*>(base)[i] = __float2bfloat16_rn(v);
+  else if (MODE == 2) store1(reinterpret_cast<__nv_bfloat16*>(base) + i, plane, v);
+  else reinterpret_cast<__half*>(base)[i] = __float2half_rn(v);
+}
+
+template <int MODE>
 __global__ void gca_values_kernel(const __nv_bfloat16* __restrict__ feat, int n, int h, int w, int P_pad,
                                   void* __restrict__ Vt) {
   const int hh = h / 2, ww = w / 2, P = hh * ww;
@@ -123,13 +135,13 @@ __global__ void gca_values_kernel(const __nv_bfloat16* __restrict__ feat, int n,
     const int yy = reflect(2 * py + t / 4 - 1, h), xx = reflect(2 * px + t % 4 - 1, w);
     v = load1(feat + (((long long)img * h + yy) * w + xx) * FC + c, (long long)n * h * w * FC);
   }
-  if (BF16) reinterpret_cast<__nv_bfloat16*>(Vt)[i] = __float2bfloat16_rn(v);
-  else reinterpret_cast<float*>(Vt)[i] = v;
+  store_operand<MODE>(Vt, i, total, v);
 }
 
 // one CTA per (row q, image): in-place masked softmax over keys
+template <int MODE>
 __global__ void __launch_bounds__(256) gca_softmax_kernel(float* __restrict__ S, const float* __restrict__ mm, int P,
-                                                          int P_pad, __nv_bfloat16* __restrict__ Pb) {
+                                                          int P_pad, void* __restrict__ Pb, long long plane) {
   __shared__ float red[32];
   __shared__ float bcast;
   const int q = blockIdx.x, img = blockIdx.y;
@@ -171,9 +183,9 @@ __global__ void __launch_bounds__(256) gca_softmax_kernel(float* __restrict__ S,
   }
   __syncthreads();
   const float inv = 1.0f / bcast;
-  if (Pb) {
-    __nv_bfloat16* orow = Pb + ((long long)img * P + q) * P_pad;
-    for (int p = threadIdx.x; p < P_pad; p += 256) orow[p] = __float2bfloat16_rn(p < P ? row[p] * inv : 0.f);
+  if (MODE != 0) {
+    const long long o = ((long long)img * P + q) * P_pad;
+    for (int p = threadIdx.x; p < P_pad; p += 256) store_operand<MODE>(Pb, o + p, plane, p < P ? row[p] * inv : 0.f);
   } else {
     for (int p = threadIdx.x; p < P_pad; p += 256) row[p] = p < P ? row[p] * inv : 0.f;
   }
@@ -236,24 +248,36 @@ int tcv_gca_prep(const void* g, const float* unknown, int n, int h, int w, void*
   return launched("gca_prep_kernel");
 }
 
-int tcv_gca_values(const void* feat, int n, int h, int w, void* Vt, int bf16, tcv_stream_t stream) {
+int tcv_gca_values(const void* feat, int n, int h, int w, void* Vt, int mode, tcv_stream_t stream) {
   TCV_REQUIRE(feat && Vt, "gca_values: null pointer");
   TCV_REQUIRE(h % 2 == 0 && w % 2 == 0 && h >= 4 && w >= 4, "gca_values: h,w must be even and >= 4");
   const int P = (h / 2) * (w / 2), P_pad = (P + 63) / 64 * 64;
   const long long total = (long long)n * VD * P_pad;
   const unsigned grid = (unsigned)((total + 255) / 256);
-  if (bf16)
-    gca_values_kernel<true><<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(feat), n, h, w, P_pad, Vt);
-  else
-    gca_values_kernel<false><<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(feat), n, h, w, P_pad, Vt);
+  TCV_REQUIRE(mode >= 0 && mode <= 3, "gca_values: mode must be 0..3");
+  auto F = reinterpret_cast<const __nv_bfloat16*>(feat);
+  switch (mode) {
+    case 0: gca_values_kernel<0><<<grid, 256, 0, S(stream)>>>(F, n, h, w, P_pad, Vt); break;
+    case 1: gca_values_kernel<1><<<grid, 256, 0, S(stream)>>>(F, n, h, w, P_pad, Vt); break;
+    case 2: gca_values_kernel<2><<<grid, 256, 0, S(stream)>>>(F, n, h, w, P_pad, Vt); break;
+    default: gca_values_kernel<3><<<grid, 256, 0, S(stream)>>>(F, n, h, w, P_pad, Vt); break;
+  }
   return launched("gca_values_kernel");
 }
 
-int tcv_gca_softmax(float* Sm, const float* mm, int n, int P, int P_pad, void* P_bf16, tcv_stream_t stream) {
+int tcv_gca_softmax(float* Sm, const float* mm, int n, int P, int P_pad, void* P_out, int mode,
+                    tcv_stream_t stream) {
   TCV_REQUIRE(Sm && mm, "gca_softmax: null pointer");
   TCV_REQUIRE(P > 0 && P_pad >= P, "gca_softmax: bad P");
   dim3 grid(P, n);
-  gca_softmax_kernel<<<grid, 256, 0, S(stream)>>>(Sm, mm, P, P_pad, reinterpret_cast<__nv_bfloat16*>(P_bf16));
+  TCV_REQUIRE(mode >= 0 && mode <= 3 && (mode == 0 || P_out), "gca_softmax: bad mode / missing output");
+  const long long plane = (long long)n * P * P_pad;
+  switch (mode) {
+    case 0: gca_softmax_kernel<0><<<grid, 256, 0, S(stream)>>>(Sm, mm, P, P_pad, nullptr, plane); break;
+    case 1: gca_softmax_kernel<1><<<grid, 256, 0, S(stream)>>>(Sm, mm, P, P_pad, P_out, plane); break;
+    case 2: gca_softmax_kernel<2><<<grid, 256, 0, S(stream)>>>(Sm, mm, P, P_pad, P_out, plane); break;
+    default: gca_softmax_kernel<3><<<grid, 256, 0, S(stream)>>>(Sm, mm, P, P_pad, P_out, plane); break;
+  }
   return launched("gca_softmax_kernel");
 }
 

@@ -33,6 +33,7 @@ struct TcParams {
   int gh, gw, tiles_x, TH, TW;
   int ntaps, kc_iters;
   int dy[TCV_MAX_TAPS], dx[TCV_MAX_TAPS], wtap[TCV_MAX_TAPS];
+  uint32_t idesc;  // tcgen05 instruction descriptor (operand format bf16 or fp16)
   int b_batched;  // GEMM mode: third weight-map coordinate = blockIdx.z instead of the tap index
   // conv epilogue
   int n_imgs, oh, ow, cout, oy_mul, oy_off, ox_mul, ox_off;
@@ -130,10 +131,10 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
   return (uint64_t)((addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
-template <int BN>
-__device__ __forceinline__ uint32_t instr_desc() {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32, A=B=bf16 (format 1) or fp16 (format 0), both K-major, M=128, N=bn
+static inline uint32_t instr_desc(int bn, bool fp16) {
+  const uint32_t fmt = fp16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
 template <int BN, int BK, int NSPLIT>
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(192) igemm_tc_kernel(const __grid_constant__ C
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     if (lane == 0) {
-      const uint32_t idesc = instr_desc<BN>();
+      const uint32_t idesc = p.idesc;
       for (int it = 0; it < total_iters; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -362,11 +363,11 @@ static EncodeTiledFn get_encode() {
 
 // bf16 tensor map, dims innermost-first; strides[i] = byte stride of dim i+1
 static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                    const cuuint32_t* box, int bk) {
+                    const cuuint32_t* box, int bk, bool fp16 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(TCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(m, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(TCV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -394,6 +395,7 @@ struct TcOperands {
   const __nv_bfloat16* b;   // weights / B matrix [bz][rows][c], hi plane
   long long b_plane;
   int b_rows, b_z;
+  bool fp16;                // operands are IEEE half instead of bf16 (NSPLIT == 1 GEMMs only)
 };
 
 template <int BN, int BK, int NSPLIT, int EPI>
@@ -404,7 +406,7 @@ static int launch_tc(const TcOperands& o, TcParams& p, cudaStream_t st) {
     cuuint64_t dims[4] = {(cuuint64_t)o.c, (cuuint64_t)o.w, (cuuint64_t)o.h, (cuuint64_t)o.n};
     cuuint64_t str[3] = {(cuuint64_t)o.c * 2, (cuuint64_t)o.w * o.c * 2, (cuuint64_t)o.a_img_stride * 2};
     cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
-    int rc = make_map(&mA_hi, o.a, 4, dims, str, box, BK);
+    int rc = make_map(&mA_hi, o.a, 4, dims, str, box, BK, o.fp16);
     if (rc) return rc;
     rc = make_map(&mA_lo, NSPLIT == 3 ? o.a + o.a_plane : o.a, 4, dims, str, box, BK);
     if (rc) return rc;
@@ -413,11 +415,12 @@ static int launch_tc(const TcOperands& o, TcParams& p, cudaStream_t st) {
     cuuint64_t dims[3] = {(cuuint64_t)o.c, (cuuint64_t)o.b_rows, (cuuint64_t)o.b_z};
     cuuint64_t str[2] = {(cuuint64_t)o.c * 2, (cuuint64_t)o.b_rows * o.c * 2};
     cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
-    int rc = make_map(&mB_hi, o.b, 3, dims, str, box, BK);
+    int rc = make_map(&mB_hi, o.b, 3, dims, str, box, BK, o.fp16);
     if (rc) return rc;
     rc = make_map(&mB_lo, NSPLIT == 3 ? o.b + o.b_plane : o.b, 3, dims, str, box, BK);
     if (rc) return rc;
   }
+  p.idesc = instr_desc(BN, o.fp16);
   auto kern = igemm_tc_kernel<BN, BK, NSPLIT, EPI>;
   TCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));  // per device
   p.tiles_x = (p.gw + p.TW - 1) / p.TW;
@@ -465,6 +468,7 @@ static int conv_tc_bn(const tcv_conv_desc& d, cudaStream_t st) {
   o.b = reinterpret_cast<const __nv_bfloat16*>(d.w_tc);
   o.b_rows = d.cout;
   o.b_z = d.w_tc_taps;
+  o.fp16 = false;
   o.b_plane = (long long)d.w_tc_taps * d.cout * d.cin;
   return launch_tc<BN, 32, 3, EPI_CONV>(o, p, st);
 }
@@ -481,14 +485,15 @@ using namespace tcv;
 
 // C[b] = A[b] * B[b]^T on tensor cores.  A: bf16 [batch][M][K] (hi plane; lo plane a_plane elements
 // later when nsplit == 3), B: bf16 [batch][N][K]; C: fp32 (out_bf16 == 0) or bf16 [batch][M][ldc].
-// K % 64 == 0.
+// K % 64 == 0.  in_fp16: operands are IEEE half (nsplit == 1 only).
 extern "C" int tcv_gemm_tn_tc(const void* A, long long a_plane, const void* B, long long b_plane, void* C, int M,
                               int N, int K, long long ldc, long long c_batch_stride, int batch, int nsplit,
-                              int out_bf16, tcv_stream_t stream) {
+                              int out_bf16, int in_fp16, tcv_stream_t stream) {
   TCV_REQUIRE(A && B && C, "gemm_tn_tc: null pointer");
   TCV_REQUIRE(M > 0 && N > 0 && K > 0 && K % 64 == 0, "gemm_tn_tc: K must be a positive multiple of 64");
   const int bk = nsplit == 3 ? 32 : 64;
   TCV_REQUIRE(nsplit == 1 || nsplit == 3, "gemm_tn_tc: nsplit must be 1 or 3");
+  TCV_REQUIRE(!in_fp16 || nsplit == 1, "gemm_tn_tc: fp16 operands only with nsplit == 1");
   TCV_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0,
               "gemm_tn_tc: pointers must be 16-byte aligned");
   TCV_REQUIRE(out_bf16 || ldc % 4 == 0, "gemm_tn_tc: ldc must be a multiple of 4 for fp32 output");
@@ -505,6 +510,7 @@ extern "C" int tcv_gemm_tn_tc(const void* A, long long a_plane, const void* B, l
   o.b = reinterpret_cast<const __nv_bfloat16*>(B);
   o.b_plane = b_plane;
   o.b_rows = N; o.b_z = batch;
+  o.fp16 = in_fp16 != 0;
   cudaStream_t st = S(stream);
   if (nsplit == 3) {
     if (out_bf16) return launch_tc<128, 32, 3, EPI_BF16>(o, p, st);

@@ -136,3 +136,23 @@ def test_no_fallback_on_cpu_tensor():
     m = _model()
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 3, 3, 64, 64), torch.zeros(1, 3, 1, 64, 64))
+
+
+def test_eval_forward_1080p_matches_oracle():
+    """BASELINE configs[1] at its full size (1088x1920 window): direct comparison with the CPU oracle
+    (a few seconds of host time), plus size-independent properties of the output."""
+    from tcvom_b200 import synthetic
+    imgs, tris = synthetic.make_window(1088, 1920, seed=7)
+    ti, tt = torch.from_numpy(imgs).float(), torch.from_numpy(tris).float()
+    m = _model()
+    with torch.no_grad():
+        out = m(ti.cuda(), tt.cuda()).cpu()
+    # properties: end frames are zero; known-region pixels reproduce the trimap exactly
+    assert out[:, 0].abs().max() == 0 and out[:, 2].abs().max() == 0
+    known = (tt[:, 1] == 0) | (tt[:, 1] == 255)
+    assert torch.equal(out[:, 1][known], (tt[:, 1] * (1.0 / 255))[known])
+    assert out.min() >= 0 and out.max() <= 1
+    ref = O.eval_forward(fixture_sd(), ti, tt)
+    err = (out - ref).abs().max().item()
+    print("1088x1920 alpha max abs err", err)
+    assert err < ALPHA_TOL

@@ -31,12 +31,12 @@ def case_gemm(nsplit, M, N, K, batch, out_bf16=0):
         As, Bs = split(A), split(B)
         ref = torch.matmul(A.double(), B.double().transpose(1, 2))
         rc = L.tcv_gemm_tn_tc(As.data_ptr(), batch * M * K, Bs.data_ptr(), batch * N * K, Cm.data_ptr(), M, N, K, ldc,
-                              M * ldc, batch, 3, out_bf16, st)
+                              M * ldc, batch, 3, out_bf16, 0, st)
     else:
         Ab, Bb = A.bfloat16(), B.bfloat16()
         ref = torch.matmul(Ab.double(), Bb.double().transpose(1, 2))
         rc = L.tcv_gemm_tn_tc(Ab.data_ptr(), 0, Bb.data_ptr(), 0, Cm.data_ptr(), M, N, K, ldc, M * ldc, batch, 1,
-                              out_bf16, st)
+                              out_bf16, 0, st)
     _cabi.check(rc, "gemm_tn_tc")
     torch.cuda.synchronize()
     got = Cm[:, :, :N].double()
