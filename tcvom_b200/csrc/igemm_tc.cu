@@ -32,6 +32,7 @@ enum { EPI_CONV = 0, EPI_F32 = 1, EPI_BF16 = 2 };
 struct TcParams {
   int gh, gw, tiles_x, TH, TW;
   int ntaps, kc_iters;
+  int stride;  // input pixels per output pixel (TMA traversal stride)
   int dy[TCV_MAX_TAPS], dx[TCV_MAX_TAPS], wtap[TCV_MAX_TAPS];
   uint32_t idesc;  // tcgen05 instruction descriptor (operand format bf16 or fp16)
   int b_batched;  // GEMM mode: third weight-map coordinate = blockIdx.z instead of the tap index
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(192) igemm_tc_kernel(const __grid_constant__ C
     if (lane == 0) {
       int it = 0;
       for (int t = 0; t < p.ntaps; ++t) {
-        const int cw = w0 + p.dx[t], ch = h0 + p.dy[t];
+        const int cw = w0 * p.stride + p.dx[t], ch = h0 * p.stride + p.dy[t];
         const int bz = p.b_batched ? img : p.wtap[t];
         for (int kc = 0; kc < p.kc_iters; ++kc, ++it) {
           const int s = it % STAGES;
@@ -363,10 +364,11 @@ static EncodeTiledFn get_encode() {
 
 // bf16 tensor map, dims innermost-first; strides[i] = byte stride of dim i+1
 static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                    const cuuint32_t* box, int bk, bool fp16 = false) {
+                    const cuuint32_t* box, int bk, bool fp16 = false, int trav = 1) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(TCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  // traversal stride on the two spatial dims (W, H) of a 4-D activation map: every `trav`-th pixel
+  cuuint32_t estr[5] = {1, (cuuint32_t)trav, (cuuint32_t)trav, 1, 1};
   CUresult r = enc(m, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -374,9 +376,10 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
   return TCV_OK;
 }
 
-static void pick_tile(int gh, int gw, int* TH, int* TW) {
+static void pick_tile(int gh, int gw, int stride, int* TH, int* TW) {
   long long best = -1;
   for (int tw = 128; tw >= 4; tw >>= 1) {
+    if (tw * stride > 256 || (128 / tw) * stride > 256) continue;  // TMA box dimension limit
     const int th = 128 / tw;
     const long long cover = (long long)((gh + th - 1) / th) * th * ((gw + tw - 1) / tw) * tw;
     if (best < 0 || cover < best) {
@@ -405,10 +408,11 @@ static int launch_tc(const TcOperands& o, TcParams& p, cudaStream_t st) {
   {
     cuuint64_t dims[4] = {(cuuint64_t)o.c, (cuuint64_t)o.w, (cuuint64_t)o.h, (cuuint64_t)o.n};
     cuuint64_t str[3] = {(cuuint64_t)o.c * 2, (cuuint64_t)o.w * o.c * 2, (cuuint64_t)o.a_img_stride * 2};
-    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
-    int rc = make_map(&mA_hi, o.a, 4, dims, str, box, BK, o.fp16);
+    // with a traversal stride s the box spans s*T input pixels and delivers T of them
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(p.TW * p.stride), (cuuint32_t)(p.TH * p.stride), 1};
+    int rc = make_map(&mA_hi, o.a, 4, dims, str, box, BK, o.fp16, p.stride);
     if (rc) return rc;
-    rc = make_map(&mA_lo, NSPLIT == 3 ? o.a + o.a_plane : o.a, 4, dims, str, box, BK);
+    rc = make_map(&mA_lo, NSPLIT == 3 ? o.a + o.a_plane : o.a, 4, dims, str, box, BK, o.fp16, p.stride);
     if (rc) return rc;
   }
   {
@@ -436,7 +440,7 @@ static int launch_tc(const TcOperands& o, TcParams& p, cudaStream_t st) {
 // fp32 [taps][cin][cout]; the bf16 hi/lo [taps][cout][cin] copy is passed through w_tc (see cabi).
 int conv2d_tc_supported(const tcv_conv_desc& d) {
   if (!d.w_tc) return 0;
-  if (d.stride != 1 || d.pad_mode != TCV_PAD_ZERO) return 0;
+  if ((d.stride != 1 && d.stride != 2) || d.pad_mode != TCV_PAD_ZERO) return 0;
   if (d.cin % 32 != 0 || d.cout % 32 != 0) return 0;
   if (d.x_img_stride != (long long)d.ih * d.iw * d.cin) return 0;
   if (!d.y && d.y_f32 == nullptr) return 0;
@@ -448,8 +452,9 @@ static int conv_tc_bn(const tcv_conv_desc& d, cudaStream_t st) {
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.gh = d.gh; p.gw = d.gw;
-  pick_tile(d.gh, d.gw, &p.TH, &p.TW);
+  pick_tile(d.gh, d.gw, d.stride, &p.TH, &p.TW);
   p.ntaps = d.ntaps;
+  p.stride = d.stride;
   p.kc_iters = d.cin / 32;
   for (int t = 0; t < d.ntaps; ++t) { p.dy[t] = d.dy[t]; p.dx[t] = d.dx[t]; p.wtap[t] = d.wtap[t]; }
   p.b_batched = 0;
@@ -500,7 +505,7 @@ extern "C" int tcv_gemm_tn_tc(const void* A, long long a_plane, const void* B, l
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.gh = 1; p.gw = M; p.TH = 1; p.TW = 128;
-  p.ntaps = 1; p.kc_iters = K / bk;
+  p.ntaps = 1; p.kc_iters = K / bk; p.stride = 1;
   p.b_batched = 1;
   p.c = C; p.ldc = ldc; p.c_batch_stride = c_batch_stride; p.M = M; p.N = N;
   TcOperands o;

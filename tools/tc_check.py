@@ -60,6 +60,10 @@ def case_conv(cin, cout, h, w, n, kind):
     if kind == "3x3":
         taps = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]; wt = list(range(9)); ntw = 9
         oh, ow, gh, gw, mul, offs = h, w, h, w, 1, (0, 0)
+    elif kind == "3x3s2":
+        taps = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]; wt = list(range(9)); ntw = 9
+        oh, ow = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+        gh, gw, mul, offs = oh, ow, 1, (0, 0)
     elif kind == "1x1":
         taps = [(0, 0)]; wt = [0]; ntw = 1
         oh, ow, gh, gw, mul, offs = h, w, h, w, 1, (0, 0)
@@ -86,7 +90,7 @@ def case_conv(cin, cout, h, w, n, kind):
             d.w_tc = wtc.data_ptr(); d.w_tc_taps = ntw
         for i, (dy, dx) in enumerate(taps):
             d.dy[i], d.dx[i], d.wtap[i] = dy, dx, wt[i]
-        d.stride, d.pad_mode = 1, 0
+        d.stride, d.pad_mode = (2 if kind == "3x3s2" else 1), 0
         d.y = y.data_ptr(); d.y_f32 = yf.data_ptr()
         d.oh, d.ow, d.cout, d.gh, d.gw = oh, ow, cout, gh, gw
         d.oy_mul, d.oy_off, d.ox_mul, d.ox_off = mul, offs[0], mul, offs[1]
@@ -115,6 +119,8 @@ CASES = {
     "conv3x3_64_128": lambda: case_conv(64, 128, 20, 28, 2, "3x3"),
     "conv3x3_32_32": lambda: case_conv(32, 32, 16, 48, 1, "3x3"),
     "conv3x3_256_256": lambda: case_conv(256, 256, 10, 12, 3, "3x3"),
+    "conv3x3s2_64_128": lambda: case_conv(64, 128, 40, 56, 2, "3x3s2"),
+    "conv3x3s2_32_64": lambda: case_conv(32, 64, 36, 52, 1, "3x3s2"),
     "conv1x1_128_64": lambda: case_conv(128, 64, 16, 16, 2, "1x1"),
     "deconv_64_64": lambda: case_conv(64, 64, 9, 14, 2, "deconv"),
 }
