@@ -93,9 +93,12 @@ typedef struct {
 } tcv_conv_desc;
 
 int tcv_conv2d(const tcv_conv_desc* d, tcv_stream_t stream);
-/* which kernel tcv_conv2d dispatches this descriptor to: 1 = tcgen05 implicit GEMM, 0 = CUDA-core
- * gather conv (reporting helper for bench.py; no launch) */
+/* which kernel tcv_conv2d dispatches this descriptor to: 2 = persistent shared-halo tcgen05 conv,
+ * 1 = tcgen05 implicit GEMM (one tap per K block), 0 = CUDA-core gather conv (no launch) */
 int tcv_conv2d_path(const tcv_conv_desc* d);
+/* selects the highest tensor-core conv kernel generation tcv_conv2d may use (1 or 2; default 2);
+ * returns the previous value.  For A/B measurements and tests. */
+int tcv_set_conv_tc_version(int v);
 
 /* sigma = u^T W v  (W viewed [rows, cols], rows = w_bar.shape[0]); then packs W/sigma into the
  * kernel layout fp32 [ntaps][cin_pad][cout].  `transposed` != 0: w_bar is [cin,cout,kh,kw]

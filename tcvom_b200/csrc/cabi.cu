@@ -27,6 +27,9 @@ int launched(const char* what) {
 int conv2d_direct(const tcv_conv_desc& d, cudaStream_t st);
 int conv2d_tc_supported(const tcv_conv_desc& d);
 int conv2d_tc(const tcv_conv_desc& d, cudaStream_t st);
+int conv2d_tc2_supported(const tcv_conv_desc& d);
+int conv2d_tc2(const tcv_conv_desc& d, cudaStream_t st);
+std::atomic<int> g_conv_tc_version{2};
 
 }  // namespace tcv
 
@@ -43,7 +46,13 @@ int tcv_conv2d_path(const tcv_conv_desc* dp) {
   tcv_conv_desc d = *dp;
   if (d.x_plane == 0) d.x_plane = (long long)d.n * d.ih * d.iw * d.cin;
   if (d.x_img_stride == 0) d.x_img_stride = (long long)d.ih * d.iw * d.cin;
+  if (g_conv_tc_version.load() >= 2 && conv2d_tc2_supported(d)) return 2;
   return conv2d_tc_supported(d) ? 1 : 0;
+}
+
+int tcv_set_conv_tc_version(int v) {
+  const int old = g_conv_tc_version.exchange(v);
+  return old;
 }
 
 int tcv_conv2d(const tcv_conv_desc* dp, tcv_stream_t stream) {
@@ -72,6 +81,7 @@ int tcv_conv2d(const tcv_conv_desc* dp, tcv_stream_t stream) {
   if (d.res1 && d.res1_plane == 0)
     d.res1_plane = (long long)d.n * (d.oh >> d.res1_shift) * (d.ow >> d.res1_shift) * d.cout;
   if (d.res2 && d.res2_plane == 0) d.res2_plane = (long long)d.n * d.oh * d.ow * d.cout;
+  if (g_conv_tc_version.load() >= 2 && conv2d_tc2_supported(d)) return conv2d_tc2(d, S(stream));
   if (conv2d_tc_supported(d)) return conv2d_tc(d, S(stream));
   return conv2d_direct(d, S(stream));
 }

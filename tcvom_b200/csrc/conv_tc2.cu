@@ -1,0 +1,382 @@
+// Persistent tcgen05 convolution kernel with shared-halo activation tiles ("v2").
+//
+// Why: the first implicit-GEMM kernel (igemm_tc.cu) reloads the 128-pixel A tile once per filter
+// tap (9x for a 3x3) and the weight tile once per 128 pixels; at 1080p every conv layer was bound
+// by L2->SM bandwidth, not by the tensor pipe (measured: 128->128 3x3 @136x240 ran at the time the
+// 1.18 MB/tile of TMA traffic takes at ~6 TB/s).  This kernel cuts that traffic ~2.2-2.7x:
+//
+//   * one CTA owns a 2*TH x TW pixel super-tile = two M=128 accumulators that share every weight
+//     tile (weights are fetched once per 256 output pixels);
+//   * for each horizontal tap offset dx the producer loads ONE activation box of (2*TH + halo)
+//     rows x TW pixels x 32 channels; the vertical taps dy are then just 1024-byte-aligned row
+//     offsets into that box (TW % 8 == 0 keeps every offset on a 64B-swizzle atom boundary), so a
+//     3x3 needs 3 boxes of 18 rows instead of 9 boxes of 8 rows per accumulator;
+//   * persistent CTAs (grid = #SMs) with a double-buffered TMEM accumulator: the 8 epilogue warps
+//     drain super-tile k while TMA/MMA already work on super-tile k+1.
+//
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
+// warps 2..5 epilogue of accumulator 0, warps 6..9 epilogue of accumulator 1.
+// Precision: bf16x3 (Ahi.Bhi + Ahi.Blo + Alo.Bhi), fp32 accumulation in TMEM.
+#include "tc_common.cuh"
+
+namespace tcv {
+
+constexpr int V2_BK = 32;
+constexpr int V2_MAXG = 3;   // distinct dx values
+constexpr int V2_MAXDY = 3;  // taps per dx group
+constexpr int V2_A_SLOTS = 3;
+constexpr int V2_A_SLOT_BYTES = 2 * 20480;  // hi + lo planes, up to 320 rows x 64 B each
+
+struct V2Params {
+  int gh, gw, TH, TW, tiles_x, tiles_y, n_tiles_n, n_imgs, total_work;
+  int kc_iters;
+  int ngroups, group_dx[V2_MAXG], ndy[V2_MAXG], dy[V2_MAXG][V2_MAXDY], wtap[V2_MAXG][V2_MAXDY];
+  int dy_min, box_rows;
+  uint32_t idesc;
+  // epilogue (same contract as tcv_conv_desc)
+  int oh, ow, cout, oy_mul, oy_off, ox_mul, ox_off;
+  __nv_bfloat16* y;
+  float* y_f32;
+  const float *s1, *b1, *s2, *b2;
+  const __nv_bfloat16 *res1, *res2;
+  long long res1_plane, res2_plane;
+  int res1_shift, act;
+};
+
+template <int BN>
+struct V2Cfg {
+  static constexpr int B_SLOT_BYTES = 2 * BN * V2_BK * 2;  // hi + lo
+  static constexpr int B_SLOTS = BN >= 128 ? 5 : 6;
+  static constexpr int A_BYTES = V2_A_SLOTS * V2_A_SLOT_BYTES;
+  static constexpr int SMEM = A_BYTES + B_SLOTS * B_SLOT_BYTES + 1024 + 512;
+  static constexpr int TMEM_COLS = 4 * BN < 32 ? 32 : 4 * BN;  // 2 buffers x 2 accumulators
+};
+
+template <int BN>
+__global__ void __launch_bounds__(320, 1) conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi,
+                                                          const __grid_constant__ CUtensorMap mapA_lo,
+                                                          const __grid_constant__ CUtensorMap mapB_hi,
+                                                          const __grid_constant__ CUtensorMap mapB_lo,
+                                                          const __grid_constant__ V2Params p) {
+  using Cfg = V2Cfg<BN>;
+  constexpr int SB = Cfg::B_SLOTS;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_base = smem_base + Cfg::A_BYTES;
+  const uint32_t bar_base = b_base + SB * Cfg::B_SLOT_BYTES;
+  auto fullA = [&](int s) { return bar_base + 8u * s; };
+  auto emptyA = [&](int s) { return bar_base + 8u * (V2_A_SLOTS + s); };
+  auto fullB = [&](int s) { return bar_base + 8u * (2 * V2_A_SLOTS + s); };
+  auto emptyB = [&](int s) { return bar_base + 8u * (2 * V2_A_SLOTS + SB + s); };
+  auto accFull = [&](int a) { return bar_base + 8u * (2 * V2_A_SLOTS + 2 * SB + a); };
+  auto accEmpty = [&](int a) { return bar_base + 8u * (2 * V2_A_SLOTS + 2 * SB + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * V2_A_SLOTS + 2 * SB + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < V2_A_SLOTS; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(accFull(a), 1); mbar_init(accEmpty(a), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB_lo) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int a_plane_bytes = p.box_rows * p.TW * (V2_BK * 2);   // one plane of an A box
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  auto decode = [&](int work, int& img, int& h0, int& w0, int& n0) {
+    const int nt = work % p.n_tiles_n;
+    int r = work / p.n_tiles_n;
+    const int t = r % tiles_per_img;
+    img = r / tiles_per_img;
+    const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+    h0 = ty * 2 * p.TH;
+    w0 = tx * p.TW;
+    n0 = nt * BN;
+  };
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int ia = 0, ib = 0;
+      for (int work = blockIdx.x; work < p.total_work; work += gridDim.x) {
+        int img, h0, w0, n0;
+        decode(work, img, h0, w0, n0);
+        for (int kc = 0; kc < p.kc_iters; ++kc) {
+          for (int g = 0; g < p.ngroups; ++g, ++ia) {
+            const int sa = ia % V2_A_SLOTS;
+            mbar_wait(emptyA(sa), ((uint32_t)(ia / V2_A_SLOTS) & 1u) ^ 1u);
+            const uint32_t adst = smem_base + sa * V2_A_SLOT_BYTES;
+            mbar_expect_tx(fullA(sa), 2 * a_plane_bytes);
+            tma_load_4d(adst, &mapA_hi, fullA(sa), kc * V2_BK, w0 + p.group_dx[g], h0 + p.dy_min, img);
+            tma_load_4d(adst + a_plane_bytes, &mapA_lo, fullA(sa), kc * V2_BK, w0 + p.group_dx[g], h0 + p.dy_min, img);
+            for (int j = 0; j < p.ndy[g]; ++j, ++ib) {
+              const int sb = ib % SB;
+              mbar_wait(emptyB(sb), ((uint32_t)(ib / SB) & 1u) ^ 1u);
+              const uint32_t bdst = b_base + sb * Cfg::B_SLOT_BYTES;
+              mbar_expect_tx(fullB(sb), Cfg::B_SLOT_BYTES);
+              tma_load_3d(bdst, &mapB_hi, fullB(sb), kc * V2_BK, n0, p.wtap[g][j]);
+              tma_load_3d(bdst + Cfg::B_SLOT_BYTES / 2, &mapB_lo, fullB(sb), kc * V2_BK, n0, p.wtap[g][j]);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      int ia = 0, ib = 0, iw = 0;
+      for (int work = blockIdx.x; work < p.total_work; work += gridDim.x, ++iw) {
+        const int buf = iw & 1;
+        mbar_wait(accEmpty(buf), ((uint32_t)(iw >> 1) & 1u) ^ 1u);   // epilogue has drained this buffer
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + (uint32_t)(buf * 2 * BN);
+        bool first = true;
+        for (int kc = 0; kc < p.kc_iters; ++kc) {
+          for (int g = 0; g < p.ngroups; ++g, ++ia) {
+            const int sa = ia % V2_A_SLOTS;
+            mbar_wait(fullA(sa), (uint32_t)(ia / V2_A_SLOTS) & 1u);
+            tc_fence_after();
+            const uint32_t a_hi = smem_base + sa * V2_A_SLOT_BYTES, a_lo = a_hi + a_plane_bytes;
+            for (int j = 0; j < p.ndy[g]; ++j, ++ib) {
+              const int sb = ib % SB;
+              mbar_wait(fullB(sb), (uint32_t)(ib / SB) & 1u);
+              tc_fence_after();
+              const uint32_t b_hi = b_base + sb * Cfg::B_SLOT_BYTES, b_lo = b_hi + Cfg::B_SLOT_BYTES / 2;
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                // rows of accumulator i for vertical tap dy start (i*TH + dy - dy_min) image rows into the box
+                const uint32_t roff = (uint32_t)((i * p.TH + p.dy[g][j] - p.dy_min) * p.TW) * (V2_BK * 2);
+#pragma unroll
+                for (int ks = 0; ks < V2_BK / 16; ++ks) {
+                  const uint64_t ah = smem_desc<V2_BK>(a_hi + roff + ks * 32), al = smem_desc<V2_BK>(a_lo + roff + ks * 32);
+                  const uint64_t bh = smem_desc<V2_BK>(b_hi + ks * 32), bl = smem_desc<V2_BK>(b_lo + ks * 32);
+                  const uint32_t d = acc0 + (uint32_t)(i * BN);
+                  tc_mma(d, ah, bh, p.idesc, (first && ks == 0) ? 0u : 1u);
+                  tc_mma(d, ah, bl, p.idesc, 1u);
+                  tc_mma(d, al, bh, p.idesc, 1u);
+                }
+              }
+              first = false;
+              tc_commit(emptyB(sb));
+            }
+            tc_commit(emptyA(sa));
+          }
+        }
+        tc_commit(accFull(buf));
+      }
+    }
+  } else {
+    // ================================ epilogue (warps 2..9) ================================
+    const int e = warp - 2;            // 0..7
+    const int i = e >> 2;              // accumulator (upper / lower tile of the super-tile)
+    const int q = warp & 3;            // TMEM lane quarter accessible to this warp
+    const int r = q * 32 + lane;
+    int iw = 0;
+    for (int work = blockIdx.x; work < p.total_work; work += gridDim.x, ++iw) {
+      int img, h0, w0, n0;
+      decode(work, img, h0, w0, n0);
+      const int buf = iw & 1;
+      mbar_wait(accFull(buf), (uint32_t)(iw >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN + i * BN);
+      const int ty = r / p.TW, tx = r - ty * p.TW;
+      const int gy = h0 + i * p.TH + ty, gx = w0 + tx;
+      const bool valid = gy < p.gh && gx < p.gw;
+      const int oy = gy * p.oy_mul + p.oy_off, ox = gx * p.ox_mul + p.ox_off;
+      const long long oplane = (long long)p.n_imgs * p.oh * p.ow * p.cout;
+      const long long obase = (((long long)img * p.oh + oy) * p.ow + ox) * p.cout + n0;
+      const int rh = p.oh >> p.res1_shift, rw = p.ow >> p.res1_shift;
+      const long long r1base = (((long long)img * rh + (oy >> p.res1_shift)) * rw + (ox >> p.res1_shift)) * p.cout + n0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tc_ld32(taddr + c0, v);
+        if (c0 + 32 >= BN) {
+          // all TMEM reads of this warp are complete: hand the buffer back to the MMA warp early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(accEmpty(buf));
+        }
+        if (!valid) continue;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.s1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] *= __ldg(p.s1 + n0 + c0 + j);
+        }
+        if (p.b1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += __ldg(p.b1 + n0 + c0 + j);
+        }
+        if (p.res1) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float g8[8];
+            load8(p.res1 + r1base + c0 + j, p.res1_plane, g8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[j + k] += g8[k];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+        if (p.s2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = f[j] * __ldg(p.s2 + n0 + c0 + j) + __ldg(p.b2 + n0 + c0 + j);
+        }
+        if (p.res2) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float g8[8];
+            load8(p.res2 + obase + c0 + j, p.res2_plane, g8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[j + k] += g8[k];
+          }
+        }
+        if (p.y) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) store8(p.y + obase + c0 + j, oplane, f + j);
+        }
+        if (p.y_f32) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(p.y_f32 + obase + c0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+static bool build_groups(const tcv_conv_desc& d, V2Params& p) {
+  p.ngroups = 0;
+  int dymin = 1 << 30, dymax = -(1 << 30);
+  for (int t = 0; t < d.ntaps; ++t) {
+    int g = -1;
+    for (int k = 0; k < p.ngroups; ++k)
+      if (p.group_dx[k] == d.dx[t]) g = k;
+    if (g < 0) {
+      if (p.ngroups == V2_MAXG) return false;
+      g = p.ngroups++;
+      p.group_dx[g] = d.dx[t];
+      p.ndy[g] = 0;
+    }
+    if (p.ndy[g] == V2_MAXDY) return false;
+    p.dy[g][p.ndy[g]] = d.dy[t];
+    p.wtap[g][p.ndy[g]] = d.wtap[t];
+    p.ndy[g]++;
+    dymin = d.dy[t] < dymin ? d.dy[t] : dymin;
+    dymax = d.dy[t] > dymax ? d.dy[t] : dymax;
+  }
+  p.dy_min = dymin;
+  p.box_rows = dymax - dymin;  // halo rows; 2*TH added once the tile is chosen
+  return true;
+}
+
+static void pick_tile2(int gh, int gw, int halo, int* TH, int* TW) {
+  long long best = -1;
+  const int cand[3][2] = {{8, 16}, {4, 32}, {16, 8}};
+  for (auto& c : cand) {
+    const int th = c[0], tw = c[1];
+    if ((2 * th + halo) * tw * V2_BK * 2 > V2_A_SLOT_BYTES / 2) continue;
+    const long long cover = (long long)((gh + 2 * th - 1) / (2 * th)) * 2 * th * ((gw + tw - 1) / tw) * tw;
+    // prefer less wasted work; among equals the first candidate (8x16: smallest halo overhead)
+    if (best < 0 || cover < best) { best = cover; *TH = th; *TW = tw; }
+  }
+}
+
+int conv2d_tc2_supported(const tcv_conv_desc& d) {
+  if (!d.w_tc) return 0;
+  if (d.stride != 1 || d.pad_mode != TCV_PAD_ZERO) return 0;
+  if (d.cin % 32 != 0 || d.cout % 32 != 0) return 0;
+  if (d.x_img_stride != (long long)d.ih * d.iw * d.cin) return 0;
+  V2Params p;
+  return build_groups(d, p) ? 1 : 0;
+}
+
+template <int BN>
+static int conv_tc2_bn(const tcv_conv_desc& d, cudaStream_t st) {
+  using Cfg = V2Cfg<BN>;
+  V2Params p;
+  memset(&p, 0, sizeof(p));
+  if (!build_groups(d, p)) return fail(TCV_ERR_UNSUPPORTED, "conv_tc2: tap pattern not supported");
+  const int halo = p.box_rows;
+  pick_tile2(d.gh, d.gw, halo, &p.TH, &p.TW);
+  p.box_rows = 2 * p.TH + halo;
+  p.gh = d.gh; p.gw = d.gw;
+  p.tiles_x = (d.gw + p.TW - 1) / p.TW;
+  p.tiles_y = (d.gh + 2 * p.TH - 1) / (2 * p.TH);
+  p.n_tiles_n = d.cout / BN;
+  p.n_imgs = d.n;
+  p.total_work = p.tiles_x * p.tiles_y * p.n_tiles_n * d.n;
+  p.kc_iters = d.cin / V2_BK;
+  p.idesc = instr_desc(BN, false);
+  p.oh = d.oh; p.ow = d.ow; p.cout = d.cout;
+  p.oy_mul = d.oy_mul; p.oy_off = d.oy_off; p.ox_mul = d.ox_mul; p.ox_off = d.ox_off;
+  p.y = reinterpret_cast<__nv_bfloat16*>(d.y);
+  p.y_f32 = d.y_f32;
+  p.s1 = d.s1; p.b1 = d.b1; p.s2 = d.s2; p.b2 = d.b2;
+  p.res1 = reinterpret_cast<const __nv_bfloat16*>(d.res1);
+  p.res2 = reinterpret_cast<const __nv_bfloat16*>(d.res2);
+  p.res1_plane = d.res1_plane; p.res2_plane = d.res2_plane; p.res1_shift = d.res1_shift; p.act = d.act;
+
+  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+  const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(d.x);
+  const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(d.w_tc);
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)d.iw, (cuuint64_t)d.ih, (cuuint64_t)d.n};
+    cuuint64_t str[3] = {(cuuint64_t)d.cin * 2, (cuuint64_t)d.iw * d.cin * 2, (cuuint64_t)d.x_img_stride * 2};
+    cuuint32_t box[4] = {(cuuint32_t)V2_BK, (cuuint32_t)p.TW, (cuuint32_t)p.box_rows, 1};
+    int rc = make_map(&mA_hi, a, 4, dims, str, box, V2_BK);
+    if (rc) return rc;
+    rc = make_map(&mA_lo, a + d.x_plane, 4, dims, str, box, V2_BK);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)d.cin, (cuuint64_t)d.cout, (cuuint64_t)d.w_tc_taps};
+    cuuint64_t str[2] = {(cuuint64_t)d.cin * 2, (cuuint64_t)d.cout * d.cin * 2};
+    cuuint32_t box[3] = {(cuuint32_t)V2_BK, (cuuint32_t)BN, 1};
+    int rc = make_map(&mB_hi, b, 3, dims, str, box, V2_BK);
+    if (rc) return rc;
+    rc = make_map(&mB_lo, b + (long long)d.w_tc_taps * d.cout * d.cin, 3, dims, str, box, V2_BK);
+    if (rc) return rc;
+  }
+  auto kern = conv_tc2_kernel<BN>;
+  TCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  int dev = 0, sms = 0;
+  TCV_CUDA(cudaGetDevice(&dev));
+  TCV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = p.total_work < sms ? p.total_work : sms;
+  kern<<<grid, 320, Cfg::SMEM, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, p);
+  return launched("conv_tc2_kernel");
+}
+
+int conv2d_tc2(const tcv_conv_desc& d, cudaStream_t st) {
+  if (d.cout % 128 == 0) return conv_tc2_bn<128>(d, st);
+  if (d.cout % 64 == 0) return conv_tc2_bn<64>(d, st);
+  return conv_tc2_bn<32>(d, st);
+}
+
+}  // namespace tcv

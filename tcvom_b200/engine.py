@@ -103,6 +103,8 @@ class GcaVmnEngine:
         # tcgen05 paths (default on); the CUDA-core fp32 paths stay available as the exact cross-check
         self.use_tc_conv = os.environ.get("TCV_TC_CONV", "1") == "1"
         self.use_tc_attn = os.environ.get("TCV_TC_ATTN", "1") == "1"
+        if "TCV_CONV_TC_VERSION" in os.environ:
+            _cabi.lib().tcv_set_conv_tc_version(int(os.environ["TCV_CONV_TC_VERSION"]))
         # operand format of the P.V aggregation GEMM: "bf16x3" (3 MMAs/step; measured 3.7e-4 max-abs alpha
         # error at 384x512), "fp16" (1 MMA; 1.3e-3, over the 1e-3 bar), "bf16" (1 MMA; 8.8e-3)
         self.pv_mode = os.environ.get("TCV_PV_MODE", "bf16x3")
@@ -268,7 +270,7 @@ class GcaVmnEngine:
             nbytes += 4 * (px >> (2 * d.res1_shift)) * d.cout
         if d.res2:
             nbytes += 4 * px * d.cout
-        path = "tc" if _cabi.lib().tcv_conv2d_path(C.byref(d)) == 1 else "direct"
+        path = {0: "direct", 1: "tc", 2: "tc2"}[_cabi.lib().tcv_conv2d_path(C.byref(d))]
         return dict(kind=f"conv_{path}", layer=wkey, flops=flops, bytes=nbytes,
                     shape=f"{d.cin}->{d.cout} k{k} s{stride} @{d.gh}x{d.gw} n{d.n}")
 

@@ -99,14 +99,15 @@ def case_conv(cin, cout, h, w, n, kind):
         d.act = 2
         d.s2, d.b2 = s2.data_ptr(), b2.data_ptr()
         d.res2 = res2.data_ptr()
-        assert L.tcv_conv2d_path(C.byref(d)) == use_tc, "dispatch did not pick the expected path"
+        path = L.tcv_conv2d_path(C.byref(d))
+        assert (path > 0) == bool(use_tc), "dispatch did not pick the expected path"
         _cabi.check(L.tcv_conv2d(C.byref(d), st), "conv2d")
         torch.cuda.synchronize()
         outs.append((y[0].float() + y[1].float(), yf.clone()))
     err = (outs[0][1] - outs[1][1]).abs().max().item()
     errs = (outs[0][0] - outs[1][0]).abs().max().item()
     mag = outs[0][1].abs().max().item()
-    print(f"conv {kind} {cin}->{cout} {h}x{w} n={n}: tc vs direct max abs err f32 {err:.3e} split {errs:.3e} (max |y| {mag:.2f})")
+    print(f"conv {kind} {cin}->{cout} {h}x{w} n={n} path={path}: tc vs direct max abs err f32 {err:.3e} split {errs:.3e} (max |y| {mag:.2f})")
     assert err < 2e-4 * max(1.0, mag) and errs < 2e-4 * max(1.0, mag)
 
 
@@ -119,6 +120,9 @@ CASES = {
     "conv3x3_64_128": lambda: case_conv(64, 128, 20, 28, 2, "3x3"),
     "conv3x3_32_32": lambda: case_conv(32, 32, 16, 48, 1, "3x3"),
     "conv3x3_256_256": lambda: case_conv(256, 256, 10, 12, 3, "3x3"),
+    "conv3x3_128_128_big": lambda: case_conv(128, 128, 136, 240, 3, "3x3"),
+    "conv3x3_32_32_big": lambda: case_conv(32, 32, 272, 480, 2, "3x3"),
+    "conv3x3_512_512": lambda: case_conv(512, 512, 34, 60, 3, "3x3"),
     "conv3x3s2_64_128": lambda: case_conv(64, 128, 40, 56, 2, "3x3s2"),
     "conv3x3s2_32_64": lambda: case_conv(32, 64, 36, 52, 1, "3x3s2"),
     "conv1x1_128_64": lambda: case_conv(128, 64, 16, 16, 2, "1x1"),
