@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc2_kernel(const __grid_constant_
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    {
       int ia = 0, ib = 0;
       for (int work = blockIdx.x; work < p.total_work; work += gridDim.x) {
         int img, h0, w0, n0;
@@ -122,16 +122,22 @@ __global__ void __launch_bounds__(320, 1) conv_tc2_kernel(const __grid_constant_
             const int sa = ia % V2_A_SLOTS;
             mbar_wait(emptyA(sa), ((uint32_t)(ia / V2_A_SLOTS) & 1u) ^ 1u);
             const uint32_t adst = smem_base + sa * V2_A_SLOT_BYTES;
-            mbar_expect_tx(fullA(sa), 2 * a_plane_bytes);
-            tma_load_4d(adst, &mapA_hi, fullA(sa), kc * V2_BK, w0 + p.group_dx[g], h0 + p.dy_min, img);
-            tma_load_4d(adst + a_plane_bytes, &mapA_lo, fullA(sa), kc * V2_BK, w0 + p.group_dx[g], h0 + p.dy_min, img);
+            if (elect_one()) {
+              mbar_expect_tx(fullA(sa), 2 * a_plane_bytes);
+              tma_load_4d(adst, &mapA_hi, fullA(sa), kc * V2_BK, w0 + p.group_dx[g], h0 + p.dy_min, img);
+              tma_load_4d(adst + a_plane_bytes, &mapA_lo, fullA(sa), kc * V2_BK, w0 + p.group_dx[g], h0 + p.dy_min, img);
+            }
+            __syncwarp();
             for (int j = 0; j < p.ndy[g]; ++j, ++ib) {
               const int sb = ib % SB;
               mbar_wait(emptyB(sb), ((uint32_t)(ib / SB) & 1u) ^ 1u);
               const uint32_t bdst = b_base + sb * Cfg::B_SLOT_BYTES;
-              mbar_expect_tx(fullB(sb), Cfg::B_SLOT_BYTES);
-              tma_load_3d(bdst, &mapB_hi, fullB(sb), kc * V2_BK, n0, p.wtap[g][j]);
-              tma_load_3d(bdst + Cfg::B_SLOT_BYTES / 2, &mapB_lo, fullB(sb), kc * V2_BK, n0, p.wtap[g][j]);
+              if (elect_one()) {
+                mbar_expect_tx(fullB(sb), Cfg::B_SLOT_BYTES);
+                tma_load_3d(bdst, &mapB_hi, fullB(sb), kc * V2_BK, n0, p.wtap[g][j]);
+                tma_load_3d(bdst + Cfg::B_SLOT_BYTES / 2, &mapB_lo, fullB(sb), kc * V2_BK, n0, p.wtap[g][j]);
+              }
+              __syncwarp();
             }
           }
         }
@@ -139,7 +145,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc2_kernel(const __grid_constant_
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    {
       int ia = 0, ib = 0, iw = 0;
       for (int work = blockIdx.x; work < p.total_work; work += gridDim.x, ++iw) {
         const int buf = iw & 1;
@@ -158,6 +164,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc2_kernel(const __grid_constant_
               mbar_wait(fullB(sb), (uint32_t)(ib / SB) & 1u);
               tc_fence_after();
               const uint32_t b_hi = b_base + sb * Cfg::B_SLOT_BYTES, b_lo = b_hi + Cfg::B_SLOT_BYTES / 2;
+              if (elect_one()) {
 #pragma unroll
               for (int i = 0; i < 2; ++i) {
                 // rows of accumulator i for vertical tap dy start (i*TH + dy - dy_min) image rows into the box
@@ -172,13 +179,17 @@ __global__ void __launch_bounds__(320, 1) conv_tc2_kernel(const __grid_constant_
                   tc_mma(d, al, bh, p.idesc, 1u);
                 }
               }
-              first = false;
               tc_commit(emptyB(sb));
+              if (j == p.ndy[g] - 1) {
+                tc_commit(emptyA(sa));
+                if (kc == p.kc_iters - 1 && g == p.ngroups - 1) tc_commit(accFull(buf));
+              }
+              }
+              __syncwarp();
+              first = false;
             }
-            tc_commit(emptyA(sa));
           }
         }
-        tc_commit(accFull(buf));
       }
     }
   } else {

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(192) igemm_tc_kernel(const __grid_constant__ C
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    {
       int it = 0;
       for (int t = 0; t < p.ntaps; ++t) {
         const int cw = w0 * p.stride + p.dx[t], ch = h0 * p.stride + p.dy[t];
@@ -115,19 +115,22 @@ __global__ void __launch_bounds__(192) igemm_tc_kernel(const __grid_constant__ C
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
-          mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
-          tma_load_4d(st, &mapA_hi, full_bar(s), kc * BK, cw, ch, img);
-          tma_load_3d(st + Cfg::PLANES * Cfg::A_BYTES, &mapB_hi, full_bar(s), kc * BK, n0, bz);
-          if (NSPLIT == 3) {
-            tma_load_4d(st + Cfg::A_BYTES, &mapA_lo, full_bar(s), kc * BK, cw, ch, img);
-            tma_load_3d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapB_lo, full_bar(s), kc * BK, n0, bz);
+          if (elect_one()) {
+            mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+            tma_load_4d(st, &mapA_hi, full_bar(s), kc * BK, cw, ch, img);
+            tma_load_3d(st + Cfg::PLANES * Cfg::A_BYTES, &mapB_hi, full_bar(s), kc * BK, n0, bz);
+            if (NSPLIT == 3) {
+              tma_load_4d(st + Cfg::A_BYTES, &mapA_lo, full_bar(s), kc * BK, cw, ch, img);
+              tma_load_3d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapB_lo, full_bar(s), kc * BK, n0, bz);
+            }
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    {
       const uint32_t idesc = p.idesc;
       for (int it = 0; it < total_iters; ++it) {
         const int s = it % STAGES;
@@ -137,6 +140,7 @@ __global__ void __launch_bounds__(192) igemm_tc_kernel(const __grid_constant__ C
         const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
         const uint32_t a_hi = st, a_lo = st + Cfg::A_BYTES;
         const uint32_t b_hi = st + Cfg::PLANES * Cfg::A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
+        if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < BK / 16; ++ks) {
           const uint64_t ah = smem_desc<BK>(a_hi + ks * 32), bh = smem_desc<BK>(b_hi + ks * 32);
@@ -148,8 +152,10 @@ __global__ void __launch_bounds__(192) igemm_tc_kernel(const __grid_constant__ C
           }
         }
         tc_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+        if (it == total_iters - 1) tc_commit(accum_bar);  // accumulator complete
+        }
+        __syncwarp();
       }
-      tc_commit(accum_bar);       // accumulator complete
     }
   } else {
     // ================================ epilogue (warps 2..5) ================================

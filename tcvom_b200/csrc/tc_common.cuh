@@ -98,6 +98,20 @@ static inline uint32_t instr_desc(int bn, bool fp16) {
 }
 
 
+// One lane of a fully converged warp.  Issuing TMA / tcgen05 instructions under this predicate (with
+// all loop control kept warp-uniform) lets ptxas emit them directly; under a plain `lane == 0` branch
+// it wraps every UTCHMMA / UTMALDG in a vote-and-elect serialisation loop (measured: ~16 extra
+// instructions per MMA, which made the single issuing thread the bottleneck).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
