@@ -99,6 +99,9 @@ int tcv_conv2d_path(const tcv_conv_desc* d);
 /* selects the highest tensor-core conv kernel generation tcv_conv2d may use (1 or 2; default 2);
  * returns the previous value.  For A/B measurements and tests. */
 int tcv_set_conv_tc_version(int v);
+/* measurement switches for kernel bring-up (bit 0: skip MMAs, 1: skip epilogue memory ops, 2/3: load
+ * activations / weights only once).  Results are WRONG when non-zero; default 0.  Returns the old value. */
+int tcv_set_debug_flags(int flags);
 
 /* sigma = u^T W v  (W viewed [rows, cols], rows = w_bar.shape[0]); then packs W/sigma into the
  * kernel layout fp32 [ntaps][cin_pad][cout].  `transposed` != 0: w_bar is [cin,cout,kh,kw]

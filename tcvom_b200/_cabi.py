@@ -45,6 +45,7 @@ SIGNATURES = {
     "tcv_conv2d": (c_int, [C.POINTER(ConvDesc), c_void_p]),
     "tcv_conv2d_path": (c_int, [C.POINTER(ConvDesc)]),
     "tcv_set_conv_tc_version": (c_int, [c_int]),
+    "tcv_set_debug_flags": (c_int, [c_int]),
     "tcv_sn_fold_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p]),
     "tcv_bn_fold": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_void_p]),

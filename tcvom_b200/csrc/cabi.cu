@@ -30,6 +30,7 @@ int conv2d_tc(const tcv_conv_desc& d, cudaStream_t st);
 int conv2d_tc2_supported(const tcv_conv_desc& d);
 int conv2d_tc2(const tcv_conv_desc& d, cudaStream_t st);
 std::atomic<int> g_conv_tc_version{2};
+std::atomic<int> g_debug_flags{0};
 
 }  // namespace tcv
 
@@ -49,6 +50,8 @@ int tcv_conv2d_path(const tcv_conv_desc* dp) {
   if (g_conv_tc_version.load() >= 2 && conv2d_tc2_supported(d)) return 2;
   return conv2d_tc_supported(d) ? 1 : 0;
 }
+
+int tcv_set_debug_flags(int flags) { return g_debug_flags.exchange(flags); }
 
 int tcv_set_conv_tc_version(int v) {
   const int old = g_conv_tc_version.exchange(v);

@@ -21,10 +21,11 @@
 
 namespace tcv {
 
+extern std::atomic<int> g_debug_flags;
+
 constexpr int V2_BK = 32;
 constexpr int V2_MAXG = 3;   // distinct dx values
 constexpr int V2_MAXDY = 3;  // taps per dx group
-constexpr int V2_A_SLOTS = 3;
 constexpr int V2_A_SLOT_BYTES = 2 * 20480;  // hi + lo planes, up to 320 rows x 64 B each
 
 struct V2Params {
@@ -32,6 +33,8 @@ struct V2Params {
   int kc_iters;
   int ngroups, group_dx[V2_MAXG], ndy[V2_MAXG], dy[V2_MAXG][V2_MAXDY], wtap[V2_MAXG][V2_MAXDY];
   int dy_min, box_rows;
+  int dbg;         // measurement switches (tcv_set_debug_flags): 1 no MMA, 2 no epilogue memory ops, 4 A loaded once, 8 B loaded once
+  int b_resident;  // all weight tiles of a work item fit the B ring: load them once, never recycle
   uint32_t idesc;
   // epilogue (same contract as tcv_conv_desc)
   int oh, ow, cout, oy_mul, oy_off, ox_mul, ox_off;
@@ -46,8 +49,11 @@ struct V2Params {
 template <int BN>
 struct V2Cfg {
   static constexpr int B_SLOT_BYTES = 2 * BN * V2_BK * 2;  // hi + lo
-  static constexpr int B_SLOTS = BN >= 128 ? 5 : 6;
-  static constexpr int A_BYTES = V2_A_SLOTS * V2_A_SLOT_BYTES;
+  // narrow layers are latency-bound on the activation stream: give them a deeper A ring, and enough
+  // B slots to keep all 9 taps of a 32-channel layer resident (weights are then loaded once per CTA)
+  static constexpr int B_SLOTS = BN >= 128 ? 5 : (BN >= 64 ? 6 : 9);
+  static constexpr int A_SLOTS = BN >= 128 ? 3 : (BN >= 64 ? 4 : 4);
+  static constexpr int A_BYTES = A_SLOTS * V2_A_SLOT_BYTES;
   static constexpr int SMEM = A_BYTES + B_SLOTS * B_SLOT_BYTES + 1024 + 512;
   static constexpr int TMEM_COLS = 4 * BN < 32 ? 32 : 4 * BN;  // 2 buffers x 2 accumulators
 };
@@ -60,6 +66,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc2_kernel(const __grid_constant_
                                                           const __grid_constant__ V2Params p) {
   using Cfg = V2Cfg<BN>;
   constexpr int SB = Cfg::B_SLOTS;
+  constexpr int V2_A_SLOTS = Cfg::A_SLOTS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_base = smem_base + Cfg::A_BYTES;
@@ -117,25 +124,35 @@ __global__ void __launch_bounds__(320, 1) conv_tc2_kernel(const __grid_constant_
       for (int work = blockIdx.x; work < p.total_work; work += gridDim.x) {
         int img, h0, w0, n0;
         decode(work, img, h0, w0, n0);
+        const bool load_b = !p.b_resident || work == (int)blockIdx.x;   // resident weights: first item only
         for (int kc = 0; kc < p.kc_iters; ++kc) {
           for (int g = 0; g < p.ngroups; ++g, ++ia) {
             const int sa = ia % V2_A_SLOTS;
             mbar_wait(emptyA(sa), ((uint32_t)(ia / V2_A_SLOTS) & 1u) ^ 1u);
             const uint32_t adst = smem_base + sa * V2_A_SLOT_BYTES;
             if (elect_one()) {
-              mbar_expect_tx(fullA(sa), 2 * a_plane_bytes);
-              tma_load_4d(adst, &mapA_hi, fullA(sa), kc * V2_BK, w0 + p.group_dx[g], h0 + p.dy_min, img);
-              tma_load_4d(adst + a_plane_bytes, &mapA_lo, fullA(sa), kc * V2_BK, w0 + p.group_dx[g], h0 + p.dy_min, img);
+              if ((p.dbg & 4) && ia >= V2_A_SLOTS) {
+                mbar_arrive(fullA(sa));
+              } else {
+                mbar_expect_tx(fullA(sa), 2 * a_plane_bytes);
+                tma_load_4d(adst, &mapA_hi, fullA(sa), kc * V2_BK, w0 + p.group_dx[g], h0 + p.dy_min, img);
+                tma_load_4d(adst + a_plane_bytes, &mapA_lo, fullA(sa), kc * V2_BK, w0 + p.group_dx[g], h0 + p.dy_min, img);
+              }
             }
             __syncwarp();
+            if (!load_b) continue;
             for (int j = 0; j < p.ndy[g]; ++j, ++ib) {
-              const int sb = ib % SB;
+              const int sb = ib % SB;   // resident mode: ib < SB, slot == stage index within the work item
               mbar_wait(emptyB(sb), ((uint32_t)(ib / SB) & 1u) ^ 1u);
               const uint32_t bdst = b_base + sb * Cfg::B_SLOT_BYTES;
               if (elect_one()) {
-                mbar_expect_tx(fullB(sb), Cfg::B_SLOT_BYTES);
-                tma_load_3d(bdst, &mapB_hi, fullB(sb), kc * V2_BK, n0, p.wtap[g][j]);
-                tma_load_3d(bdst + Cfg::B_SLOT_BYTES / 2, &mapB_lo, fullB(sb), kc * V2_BK, n0, p.wtap[g][j]);
+                if ((p.dbg & 8) && ib >= SB) {
+                  mbar_arrive(fullB(sb));
+                } else {
+                  mbar_expect_tx(fullB(sb), Cfg::B_SLOT_BYTES);
+                  tma_load_3d(bdst, &mapB_hi, fullB(sb), kc * V2_BK, n0, p.wtap[g][j]);
+                  tma_load_3d(bdst + Cfg::B_SLOT_BYTES / 2, &mapB_lo, fullB(sb), kc * V2_BK, n0, p.wtap[g][j]);
+                }
               }
               __syncwarp();
             }
@@ -153,37 +170,43 @@ __global__ void __launch_bounds__(320, 1) conv_tc2_kernel(const __grid_constant_
         tc_fence_after();
         const uint32_t acc0 = tmem_base + (uint32_t)(buf * 2 * BN);
         bool first = true;
+        int il = 0;   // weight stage index within this work item
         for (int kc = 0; kc < p.kc_iters; ++kc) {
           for (int g = 0; g < p.ngroups; ++g, ++ia) {
             const int sa = ia % V2_A_SLOTS;
             mbar_wait(fullA(sa), (uint32_t)(ia / V2_A_SLOTS) & 1u);
             tc_fence_after();
             const uint32_t a_hi = smem_base + sa * V2_A_SLOT_BYTES, a_lo = a_hi + a_plane_bytes;
-            for (int j = 0; j < p.ndy[g]; ++j, ++ib) {
-              const int sb = ib % SB;
-              mbar_wait(fullB(sb), (uint32_t)(ib / SB) & 1u);
+            for (int j = 0; j < p.ndy[g]; ++j, ++ib, ++il) {
+              const int sb = p.b_resident ? il : ib % SB;
+              mbar_wait(fullB(sb), p.b_resident ? 0u : ((uint32_t)(ib / SB) & 1u));
               tc_fence_after();
               const uint32_t b_hi = b_base + sb * Cfg::B_SLOT_BYTES, b_lo = b_hi + Cfg::B_SLOT_BYTES / 2;
               if (elect_one()) {
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
                 // rows of accumulator i for vertical tap dy start (i*TH + dy - dy_min) image rows into the box
-                const uint32_t roff = (uint32_t)((i * p.TH + p.dy[g][j] - p.dy_min) * p.TW) * (V2_BK * 2);
+                const uint32_t roff0 = (uint32_t)((p.dy[g][j] - p.dy_min) * p.TW) * (V2_BK * 2);
+                const uint32_t roff1 = roff0 + (uint32_t)(p.TH * p.TW) * (V2_BK * 2);
+                const uint32_t d0 = acc0, d1 = acc0 + (uint32_t)BN;
+                // consecutive MMAs alternate between the two accumulators: dependent (same-accumulator)
+                // MMAs issued back to back do not pipeline as well as independent ones
 #pragma unroll
-                for (int ks = 0; ks < V2_BK / 16; ++ks) {
-                  const uint64_t ah = smem_desc<V2_BK>(a_hi + roff + ks * 32), al = smem_desc<V2_BK>(a_lo + roff + ks * 32);
+                for (int ks = 0; ks < ((p.dbg & 1) ? 0 : V2_BK / 16); ++ks) {
+                  const uint64_t ah0 = smem_desc<V2_BK>(a_hi + roff0 + ks * 32), al0 = smem_desc<V2_BK>(a_lo + roff0 + ks * 32);
+                  const uint64_t ah1 = smem_desc<V2_BK>(a_hi + roff1 + ks * 32), al1 = smem_desc<V2_BK>(a_lo + roff1 + ks * 32);
                   const uint64_t bh = smem_desc<V2_BK>(b_hi + ks * 32), bl = smem_desc<V2_BK>(b_lo + ks * 32);
-                  const uint32_t d = acc0 + (uint32_t)(i * BN);
-                  tc_mma(d, ah, bh, p.idesc, (first && ks == 0) ? 0u : 1u);
-                  tc_mma(d, ah, bl, p.idesc, 1u);
-                  tc_mma(d, al, bh, p.idesc, 1u);
+                  const uint32_t acc = (first && ks == 0) ? 0u : 1u;
+                  tc_mma(d0, ah0, bh, p.idesc, acc);
+                  tc_mma(d1, ah1, bh, p.idesc, acc);
+                  tc_mma(d0, ah0, bl, p.idesc, 1u);
+                  tc_mma(d1, ah1, bl, p.idesc, 1u);
+                  tc_mma(d0, al0, bh, p.idesc, 1u);
+                  tc_mma(d1, al1, bh, p.idesc, 1u);
                 }
-              }
-              tc_commit(emptyB(sb));
-              if (j == p.ndy[g] - 1) {
-                tc_commit(emptyA(sa));
-                if (kc == p.kc_iters - 1 && g == p.ngroups - 1) tc_commit(accFull(buf));
-              }
+                if (!p.b_resident) tc_commit(emptyB(sb));
+                if (j == p.ndy[g] - 1) {
+                  tc_commit(emptyA(sa));
+                  if (kc == p.kc_iters - 1 && g == p.ngroups - 1) tc_commit(accFull(buf));
+                }
               }
               __syncwarp();
               first = false;
@@ -224,7 +247,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc2_kernel(const __grid_constant_
           __syncwarp();
           if (lane == 0) mbar_arrive(accEmpty(buf));
         }
-        if (!valid) continue;
+        if (!valid || (p.dbg & 2)) continue;
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -343,6 +366,8 @@ static int conv_tc2_bn(const tcv_conv_desc& d, cudaStream_t st) {
   p.n_imgs = d.n;
   p.total_work = p.tiles_x * p.tiles_y * p.n_tiles_n * d.n;
   p.kc_iters = d.cin / V2_BK;
+  p.dbg = g_debug_flags.load();
+  p.b_resident = (p.n_tiles_n == 1 && d.ntaps * p.kc_iters <= Cfg::B_SLOTS) ? 1 : 0;
   p.idesc = instr_desc(BN, false);
   p.oh = d.oh; p.ow = d.ow; p.cout = d.cout;
   p.oy_mul = d.oy_mul; p.oy_off = d.oy_off; p.ox_mul = d.ox_mul; p.ox_off = d.ox_off;
