@@ -183,17 +183,14 @@ def run_native(args, rank, world, local_rank):
     tris_h = torch.from_numpy(tris_np).float().pin_memory()
     out_h = torch.empty((1, S, 1, H, W), dtype=torch.float32).pin_memory()
 
+    from tcvom_b200 import dp
+
     def barrier():
-        if world > 1:
-            dist.barrier()
+        dp.barrier()
         torch.cuda.synchronize(dev)
 
     def max_over_ranks(ms):
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return ms
+        return dp.max_over_ranks(ms, dev)
 
     with torch.no_grad():
         # ---- record the plan, fill the resident input buffers
@@ -265,14 +262,17 @@ def run_native(args, rank, world, local_rank):
                         breakdown_ms={k: round(v["ms"], 3) for k, v in sorted(kinds.items(), key=lambda kv: -kv[1]["ms"])})
             if args.dump_calls:
                 with open(args.dump_calls, "w") as f:
-                    for m, t in sorted(zip(plan.meta, acc), key=lambda mt: -mt[1]):
-                        f.write(json.dumps(dict(ms=round(t, 4), **{k: v for k, v in m.items()})) + "\n")
+                    for i, (m, t) in sorted(enumerate(zip(plan.meta, acc)), key=lambda imt: -imt[1][1]):
+                        f.write(json.dumps(dict(idx=i, ms=round(t, 4), **{k: v for k, v in m.items()})) + "\n")
             whole = GFLOP_PER_WINDOW / (ms / args.steps * 1e-3) / 1e3
             roof["whole_step_tflops"] = whole
             roof["whole_step_frac_of_tensor_peak"] = whole / pk["tf_sustained"]
             tr = os.path.join(ROOT, "profiles", "traffic.json")
             if os.path.exists(tr):
-                roof["traffic"] = json.load(open(tr)).get(top_name)
+                t = json.load(open(tr)).get(top_name)
+                if t:
+                    roof["traffic"] = t["dram_bytes_per_launch"]       # ncu dram__bytes_read+write, per launch
+                    roof["algorithmic_bytes_per_launch"] = top["bytes"] / top["n"]
 
     if rank != 0:
         if world > 1:

@@ -6,3 +6,50 @@ Public surface mirrors the reference's operator/plugin interface for this path:
 from .model import EvalModel, FeatureAggregationModule, GuidedCxtAtten, VMN, get_VMN_models  # noqa: F401
 
 __version__ = "0.1.0"
+
+
+def install(native_wrapper: bool = True):
+    """Hooks this package into an importable reference checkout (``models`` on ``sys.path``).
+
+    * ``models.VMN.get_VMN_models('vmn_gca', ...)`` -> :func:`tcvom_b200.get_VMN_models`
+      (the plugin seam ``models/model.py:39-44`` calls at construction time); other archs are
+      forwarded to the reference untouched;
+    * with ``native_wrapper`` also ``models.model.EvalModel`` -> :class:`tcvom_b200.EvalModel`
+      when it is built for ``vmn_gca`` (fused preprocess / postprocess kernels, CUDA-graph replay).
+
+    Call it before the reference script imports ``models.model``."""
+    import importlib
+    import sys
+    import types
+    for m in ("matplotlib", "matplotlib.pyplot"):          # models/Index/hldecoder.py:36 imports it at module import
+        try:
+            importlib.import_module(m)
+        except ImportError:
+            sys.modules.setdefault(m, types.ModuleType(m))
+    ref_vmn = importlib.import_module("models.VMN")
+    ref_model = importlib.import_module("models.model")
+    if getattr(ref_vmn.get_VMN_models, "_tcvom_b200", False):
+        return
+    orig_factory = ref_vmn.get_VMN_models
+
+    def factory(arch, *args, **kwargs):
+        if arch == "vmn_gca":
+            return get_VMN_models(arch, *args, **kwargs)
+        return orig_factory(arch, *args, **kwargs)
+
+    factory._tcvom_b200 = True
+    factory._reference = orig_factory
+    ref_vmn.get_VMN_models = factory
+    if native_wrapper:
+        orig_eval = ref_model.EvalModel
+
+        class _EvalModelDispatch:
+            """EvalModel('vmn_gca', ...) -> native wrapper; anything else -> reference class."""
+
+            def __new__(cls, model, *args, **kwargs):
+                if model == "vmn_gca":
+                    return EvalModel(model, *args, **kwargs)
+                return orig_eval(model, *args, **kwargs)
+
+        _EvalModelDispatch._reference = orig_eval
+        ref_model.EvalModel = _EvalModelDispatch

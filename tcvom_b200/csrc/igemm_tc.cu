@@ -76,10 +76,13 @@ __global__ void __launch_bounds__(192) igemm_tc_kernel(const __grid_constant__ C
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
+  // GEMM mode rasterises N-tiles fastest: consecutive CTAs then share one A row panel (the 4 MB
+  // probability panel of P.V stays in L2 while the 16 value tiles stream past it; with M fastest the
+  // whole 268 MB P matrix was re-read from HBM once per N-tile -- ncu: 4.2 GB dram reads per launch)
+  const int tile = p.b_batched ? blockIdx.y : blockIdx.x;
   const int tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
   const int h0 = tile_y * p.TH, w0 = tile_x * p.TW;
-  const int n0 = blockIdx.y * BN;
+  const int n0 = (p.b_batched ? blockIdx.x : blockIdx.y) * BN;
   const int img = blockIdx.z;
   const int total_iters = p.ntaps * p.kc_iters;
 
@@ -313,6 +316,7 @@ static int launch_tc(const TcOperands& o, TcParams& p, cudaStream_t st) {
   const int tiles_y = (p.gh + p.TH - 1) / p.TH;
   const int nrows = EPI == EPI_CONV ? p.cout : p.N;
   dim3 grid(p.tiles_x * tiles_y, (nrows + BN - 1) / BN, o.n);
+  if (p.b_batched) grid = dim3((nrows + BN - 1) / BN, p.tiles_x * tiles_y, o.n);
   kern<<<grid, 192, Cfg::SMEM, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, p);
   return launched("igemm_tc_kernel");
 }
