@@ -18,6 +18,8 @@
  *                         call sites: GCA/encoders/resnet_enc.py:33-49,129-145,
  *                         res_gca_enc.py:20-33,47-55,57-90, GCA/decoders/resnet_dec.py:43-59,
  *                         VMN/VMN_GCA.py:26-49, VMN/VMN_model.py:13-15
+ *   tcv_preprocess_train  models/model.py:54-92     FullModel.preprocess + make_trimap
+ *   tcv_losses_vmd        models/model.py:94-127,285-345  L_im / L_af / L_tc forward (+ utils/loss_func.py:9-22)
  *   tcv_avgpool2          nn.AvgPool2d(2,2)          resnet_enc.py:112
  *   tcv_gca_*             models/GCA/ops.py:106-229  GuidedCxtAtten.forward
  *   tcv_tam_attend        models/VMN/VMN_model.py:18-68  FeatureAggregationModule.forward
@@ -130,6 +132,25 @@ int tcv_preprocess_eval(const float* imgs, const float* tris, int frames, int h,
 int tcv_postprocess_eval(const float* pred, const float* tris, const float* trimask, int batch,
                          int frames, int h, int w, float* alphas, tcv_stream_t stream);
 
+/* FullModel.preprocess + make_trimap (models/model.py:54-92, TRIMAP_CHANNEL == 3).
+ * a fp32 [B,S,1,H,W], fg/bg fp32 [B,S,3,H,W] (BGR 0..255); radii int32 [B] (device): max-pool dilation
+ * radius per sample (model.py:62 draws it per sample on the host when DILATION_KERNEL is None).
+ * Outputs: x8 split-bf16 NHWC [B*S,H,W,8]; trimask/gts/tris_vis fp32 [B,S,1,H,W]; fgs/bgs/imgs fp32
+ * [B,S,3,H,W] (RGB, /255).  tmp = 2*B*S*H*W bytes. */
+int tcv_preprocess_train(const float* a, const float* fg, const float* bg, int batch, int frames_per_sample, int h,
+                         int w, float eps, const int* radii, void* x8, float* trimask, float* gts, float* fgs,
+                         float* bgs, float* imgs, float* tris_vis, uint8_t* tmp, tcv_stream_t stream);
+
+/* Forward of the FullModel_VMD losses (models/model.py:94-127 L_im, :285-323 L_af, :326-345 L_tc) and
+ * the visualisation tensors.  pred fp32 [B,S-2,1,H,W] (inner frames); attb/attf fp32 [B,S-2,w*w,H*W/64],
+ * small_mask uint8 [B,S-2,H*W/64] (NULL for the plain FullModel: L_af = 0).  Outputs alphas fp32
+ * [B,S,1,H,W], comps fp32 [B,S,3,H,W] (clamped, zero end frames), losses fp32 [5] =
+ * (L_alpha, L_comp=0, L_grad=0, L_dt, L_att).  Workspaces: gt8 fp32 [B,S,H/8,W/8], acc double [6*S]. */
+int tcv_losses_vmd(const float* pred, const float* trimask, const float* gts, const float* fgs, const float* bgs,
+                   const float* attb, const float* attf, const uint8_t* small_mask, int batch, int frames_per_sample,
+                   int h, int w, int window, float att_thres, float label_smooth, float att_multiplier,
+                   float* alphas, float* comps, float* gt8, double* acc, float* losses, tcv_stream_t stream);
+
 int tcv_avgpool2(const void* x, int n, int h, int w, int c, void* y, tcv_stream_t stream);
 
 /* unknown[n, y, x] = x8[n, y*8, x*8, channel 4]  (res_gca_enc.py:71) ; fp32 [n, h/8, w/8] */
@@ -139,7 +160,7 @@ int tcv_unknown_os8(const void* x8, int n, int h, int w, float* unknown, tcv_str
  * h,w = OS8 feature size, P_pad = P rounded up to 64.
  *  prep:    g split-bf16 [n,h/2,w/2,64] (guidance_conv output at stride 2), unknown fp32 [n,h,w]
  *           -> Q [n,P,576], Kn [n,P,576] (= Q/max(|Q|,1e-4) * per-key scale): fp32 when
- *              bf16_split == 0, else split-bf16 planes [2][n][P][576];
+ *              bf16_split == 0, else bf16 planes [bf16_split][n][P][576] (2: hi/lo, 3: hi/mid/lo);
  *              mm fp32 [n,P] ; scales fp32 [n,2] = (unknown_scale, known_scale)
  *  values:  feat split-bf16 [n,h,w,128] -> Vt [n,2048,P_pad] (row = (ty*4+tx)*128+c);
  *           mode 0 fp32, 1 bf16, 2 split-bf16 planes [2][n][2048][P_pad], 3 fp16
@@ -160,7 +181,8 @@ int tcv_gemm_tn_f32(const float* A, const float* B, float* C, int M, int N, int 
                     tcv_stream_t stream);
 
 /* C[b] = A[b] * B[b]^T on the tensor cores (tcgen05, fp32 accumulate in TMEM).  A bf16 [batch][M][K]
- * (nsplit == 3: hi plane at A, lo plane a_plane elements later; products Ahi.Bhi+Ahi.Blo+Alo.Bhi),
+ * (nsplit == 3: hi plane at A, lo plane a_plane elements later; products Ahi.Bhi+Ahi.Blo+Alo.Bhi;
+ * nsplit == 6: three planes hi/mid/lo, products hh+hm+mh+hl+lh+mm, ~24 mantissa bits per operand),
  * B bf16 [batch][N][K] likewise; C fp32 or (out_bf16) bf16 [batch][M][ldc].  K % 64 == 0.
  * in_fp16 != 0 (nsplit == 1 only): A and B hold IEEE half instead of bf16. */
 int tcv_gemm_tn_tc(const void* A, long long a_plane, const void* B, long long b_plane, void* C, int M, int N,

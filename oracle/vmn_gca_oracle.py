@@ -293,3 +293,94 @@ def eval_forward(sd: SD, imgs, tris, dilate_kernel=None, window=7, return_aux=Fa
     if return_aux:
         return out, dict(preds=preds, attb=attb, attf=attf, small_mask=small, feats=feats)
     return out
+
+
+# --------------------------------------------------------------------------- FullModel_VMD (eval-mode forward)
+def l1_mask(x, y, mask, epsilon=1.001e-5):
+    """utils/loss_func.py:9-22 (normalize=True, mask given)."""
+    res = torch.abs(x - y) * mask
+    b, c, h, w = y.shape
+    safe = torch.sum((mask > epsilon).float()).clamp(epsilon, b * c * h * w + 1)
+    return torch.sum(res) / safe
+
+
+def train_preprocess(a, fg, bg, radii, eps=0.0):
+    """FullModel.preprocess + make_trimap, TRIMAP_CHANNEL == 3 -- models/model.py:54-92.
+    a [B,S,1,H,W], fg/bg [B,S,3,H,W] (BGR 0..255); radii: dilation radius per sample (the reference draws
+    torch.randint(0, 26) per sample when DILATION_KERNEL is None, model.py:62)."""
+    mean = torch.tensor(IMG_MEAN).reshape(1, 1, 3, 1, 1)
+    std = torch.tensor(IMG_STD).reshape(1, 1, 3, 1, 1)
+    gts = a * (1.0 / 255)
+    fgs = fg.flip([2]) * (1.0 / 255)
+    bgs = bg.flip([2]) * (1.0 / 255)
+    imgs = fgs * gts + bgs * (1.0 - gts)
+    alpha = torch.where(gts < eps, torch.zeros_like(gts), gts)
+    alpha = torch.where(alpha > 1 - eps, torch.ones_like(alpha), alpha)
+    raw = ((alpha > 0) & (alpha < 1.0)).float()
+    tm = []
+    for i in range(a.shape[0]):
+        r = int(radii[i])
+        tm.append(F.max_pool2d(raw[i], kernel_size=2 * r + 1, stride=1, padding=r))
+    trimask = torch.stack(tm)
+    cls = torch.where(trimask > 0.5, torch.ones_like(alpha), 2 * alpha).long()
+    onehot = F.one_hot(cls.squeeze(2), 3).permute(0, 1, 4, 2, 3).float()
+    norm = (imgs - mean) / std
+    return dict(imgs=imgs, fgs=fgs, bgs=bgs, gts=gts, tris=onehot, trimask=trimask, x6=torch.cat([norm, onehot], 2))
+
+
+def full_vmd_forward(sd: SD, a, fg, bg, radii, window=7, att_thres=0.3, label_smooth=0.2, eps=0.0):
+    """FullModel_VMD.forward for vmn_gca with the network in eval mode -- models/model.py:258-357
+    (single_image_loss :94-127, L_att :285-323, _dtSSD :326-345).  Returns the reference's 12-list."""
+    with torch.no_grad():
+        pp = train_preprocess(a, fg, bg, radii, eps)
+        B, S = a.shape[:2]
+        frames = [pp["x6"][:, i] for i in range(S)]
+        masks = [pp["trimask"][:, i] for i in range(S)]
+        preds, attb, attf, small, _ = vmn_forward(sd, frames, masks, window)
+        gts, trimask = pp["gts"], pp["trimask"]
+        alphas: List[Optional[torch.Tensor]] = [None] * S
+        comps: List[Optional[torch.Tensor]] = [None] * S
+        L_alpha = []
+        for c in range(1, S - 1):
+            m = trimask[:, c].float()
+            refine = torch.where(m.bool(), preds[c], gts[:, c])
+            alphas[c] = refine
+            comps[c] = pp["fgs"][:, c] * refine + pp["bgs"][:, c] * (1.0 - refine)
+            L_alpha.append(l1_mask(refine, gts[:, c], m))
+        L_alpha = sum(L_alpha) / float(len(L_alpha))
+        zero = torch.zeros_like(L_alpha)
+        for i in (0, S - 1):
+            alphas[i] = torch.zeros_like(alphas[1])
+            comps[i] = torch.zeros_like(comps[1])
+        alphas_t = torch.stack(alphas, 1).clamp(0, 1)
+        comps_t = torch.stack(comps, 1).clamp(0, 1)
+        # attention-map loss
+        H8, W8 = a.shape[-2] // 8, a.shape[-1] // 8
+        L_att = []
+        bce = torch.nn.BCEWithLogitsLoss(reduction="mean")
+        for c in range(1, S - 1):
+            bgt = F.avg_pool2d(gts[:, c - 1], 8, 8)
+            fgt = F.avg_pool2d(gts[:, c + 1], 8, 8)
+            cgt = F.avg_pool2d(gts[:, c], 8, 8)
+            m = small[c].reshape(B, -1)
+            if m.float().sum() == 0:
+                L_att.append(torch.zeros_like(L_alpha))
+                continue
+            bb = attb[c].reshape(B, -1, H8 * W8).permute(1, 0, 2)[:, m]
+            ff = attf[c].reshape(B, -1, H8 * W8).permute(1, 0, 2)[:, m]
+            bu = F.unfold(bgt, window, padding=window // 2).reshape(B, -1, H8 * W8).permute(1, 0, 2)[:, m]
+            fu = F.unfold(fgt, window, padding=window // 2).reshape(B, -1, H8 * W8).permute(1, 0, 2)[:, m]
+            cg = cgt.reshape(B, 1, H8 * W8).permute(1, 0, 2)[:, m]
+            tb = (torch.abs(cg - bu) < att_thres).float() * (1 - label_smooth)
+            tf = (torch.abs(cg - fu) < att_thres).float() * (1 - label_smooth)
+            L_att.append((bce(bb, tb) + bce(ff, tf)) / 2.0)
+        L_att = sum(L_att) / float(len(L_att))
+        if S >= 5:
+            L_dt = []
+            for c in range(1, S - 2):
+                L_dt.append(l1_mask(alphas_t[:, c] - alphas_t[:, c + 1], gts[:, c] - gts[:, c + 1], trimask[:, c]))
+            L_dt = sum(L_dt) / float(len(L_dt))
+        else:
+            L_dt = torch.zeros_like(L_att)
+        tris_vis = torch.where(trimask.bool(), torch.ones_like(gts) * 128 * (1.0 / 255), gts)
+    return [L_alpha, zero, zero.clone(), L_dt, L_att, pp["imgs"], tris_vis, alphas_t, comps_t, gts, pp["fgs"], pp["bgs"]]

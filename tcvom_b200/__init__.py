@@ -3,7 +3,8 @@
 Public surface mirrors the reference's operator/plugin interface for this path:
 ``get_VMN_models``, ``VMN``, ``FeatureAggregationModule``, ``GuidedCxtAtten``, ``EvalModel``.
 """
-from .model import EvalModel, FeatureAggregationModule, GuidedCxtAtten, VMN, get_VMN_models  # noqa: F401
+from .model import (EvalModel, FeatureAggregationModule, FullModel, FullModel_VMD, GuidedCxtAtten, VMN,  # noqa: F401
+                    get_VMN_models)
 
 __version__ = "0.1.0"
 
@@ -53,3 +54,16 @@ def install(native_wrapper: bool = True):
 
         _EvalModelDispatch._reference = orig_eval
         ref_model.EvalModel = _EvalModelDispatch
+        orig_vmd = ref_model.FullModel_VMD
+
+        class _VMDDispatch:
+            """FullModel_VMD('vmn_gca', ...) -> native wrapper (inference use, pred_vmn.py); else reference."""
+            ARCH_DICT = orig_vmd.ARCH_DICT
+
+            def __new__(cls, model, *args, **kwargs):
+                if model == "vmn_gca":
+                    return FullModel_VMD(model, *args, **kwargs)
+                return orig_vmd(model, *args, **kwargs)
+
+        _VMDDispatch._reference = orig_vmd
+        ref_model.FullModel_VMD = _VMDDispatch

@@ -53,6 +53,10 @@ SIGNATURES = {
                                     c_void_p, c_void_p]),
     "tcv_postprocess_eval": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                      c_void_p]),
+    "tcv_preprocess_train": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p]),
+    "tcv_losses_vmd": (c_int, [c_void_p] * 8 + [c_int] * 5 + [c_float] * 3 + [c_void_p] * 6),
     "tcv_avgpool2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_unknown_os8": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_gca_prep": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -226,64 +226,99 @@ __global__ void __launch_bounds__(320, 1) conv_tc2_kernel(const __grid_constant_
       int img, h0, w0, n0;
       decode(work, img, h0, w0, n0);
       const int buf = iw & 1;
-      mbar_wait(accFull(buf), (uint32_t)(iw >> 1) & 1u);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN + i * BN);
       const int ty = r / p.TW, tx = r - ty * p.TW;
       const int gy = h0 + i * p.TH + ty, gx = w0 + tx;
-      const bool valid = gy < p.gh && gx < p.gw;
+      const bool valid = gy < p.gh && gx < p.gw && !(p.dbg & 2);
       const int oy = gy * p.oy_mul + p.oy_off, ox = gx * p.ox_mul + p.ox_off;
       const long long oplane = (long long)p.n_imgs * p.oh * p.ow * p.cout;
       const long long obase = (((long long)img * p.oh + oy) * p.ow + ox) * p.cout + n0;
       const int rh = p.oh >> p.res1_shift, rw = p.ow >> p.res1_shift;
       const long long r1base = (((long long)img * rh + (oy >> p.res1_shift)) * rw + (ox >> p.res1_shift)) * p.cout + n0;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      const bool has1 = valid && p.res1 != nullptr && !(p.dbg & 32), has2 = valid && p.res2 != nullptr && !(p.dbg & 32);
+
+      // Residual operands are fetched one 32-channel chunk AHEAD of the accumulator chunk that consumes
+      // them, and the first chunk is requested before this warp even waits for the MMAs to finish: the
+      // epilogue is latency-bound on these scattered 16-byte loads, not on bandwidth.
+      uint4 ra[2][8], rb[2][8];   // [double buffer][4 x hi, 4 x lo] for res1 / res2
+      auto fetch = [&](int c0, int slot) {
+        if (has1) {
+          const uint4* h = reinterpret_cast<const uint4*>(p.res1 + r1base + c0);
+          const uint4* l = reinterpret_cast<const uint4*>(p.res1 + r1base + c0 + p.res1_plane);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { ra[slot][k] = __ldg(h + k); ra[slot][4 + k] = __ldg(l + k); }
+        }
+        if (has2) {
+          const uint4* h = reinterpret_cast<const uint4*>(p.res2 + obase + c0);
+          const uint4* l = reinterpret_cast<const uint4*>(p.res2 + obase + c0 + p.res2_plane);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { rb[slot][k] = __ldg(h + k); rb[slot][4 + k] = __ldg(l + k); }
+        }
+      };
+      auto add_res = [&](const uint4* rr, float* f) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t hw[4] = {rr[k].x, rr[k].y, rr[k].z, rr[k].w};
+          const uint32_t lw[4] = {rr[4 + k].x, rr[4 + k].y, rr[4 + k].z, rr[4 + k].w};
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            f[8 * k + 2 * m] += __uint_as_float(hw[m] << 16) + __uint_as_float(lw[m] << 16);
+            f[8 * k + 2 * m + 1] += __uint_as_float(hw[m] & 0xffff0000u) + __uint_as_float(lw[m] & 0xffff0000u);
+          }
+        }
+      };
+      fetch(0, 0);
+      mbar_wait(accFull(buf), (uint32_t)(iw >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int ci = 0; ci < BN / 32; ++ci) {
+        const int c0 = ci * 32;
+        const int slot = ci & 1;
         uint32_t v[32];
         tc_ld32(taddr + c0, v);
-        if (c0 + 32 >= BN) {
+        if (ci == BN / 32 - 1) {
           // all TMEM reads of this warp are complete: hand the buffer back to the MMA warp early
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(accEmpty(buf));
+        } else {
+          fetch(c0 + 32, slot ^ 1);
         }
-        if (!valid || (p.dbg & 2)) continue;
+        if (!valid) continue;
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
         if (p.s1) {
+          const float4* sv = reinterpret_cast<const float4*>(p.s1 + n0 + c0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] *= __ldg(p.s1 + n0 + c0 + j);
-        }
-        if (p.b1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] += __ldg(p.b1 + n0 + c0 + j);
-        }
-        if (p.res1) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float g8[8];
-            load8(p.res1 + r1base + c0 + j, p.res1_plane, g8);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) f[j + k] += g8[k];
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = __ldg(sv + j);
+            f[4 * j] *= t.x; f[4 * j + 1] *= t.y; f[4 * j + 2] *= t.z; f[4 * j + 3] *= t.w;
           }
         }
+        if (p.b1) {
+          const float4* sv = reinterpret_cast<const float4*>(p.b1 + n0 + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = __ldg(sv + j);
+            f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+          }
+        }
+        if (has1) add_res(ra[slot], f);
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
         if (p.s2) {
+          const float4* sv = reinterpret_cast<const float4*>(p.s2 + n0 + c0);
+          const float4* bv = reinterpret_cast<const float4*>(p.b2 + n0 + c0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = f[j] * __ldg(p.s2 + n0 + c0 + j) + __ldg(p.b2 + n0 + c0 + j);
-        }
-        if (p.res2) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float g8[8];
-            load8(p.res2 + obase + c0 + j, p.res2_plane, g8);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) f[j + k] += g8[k];
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = __ldg(sv + j), u = __ldg(bv + j);
+            f[4 * j] = f[4 * j] * t.x + u.x; f[4 * j + 1] = f[4 * j + 1] * t.y + u.y;
+            f[4 * j + 2] = f[4 * j + 2] * t.z + u.z; f[4 * j + 3] = f[4 * j + 3] * t.w + u.w;
           }
         }
-        if (p.y) {
+        if (has2) add_res(rb[slot], f);
+        if (p.y && !((p.dbg & 16) && f[0] != 12345.678f)) {
 #pragma unroll
           for (int j = 0; j < 32; j += 8) store8(p.y + obase + c0 + j, oplane, f + j);
         }

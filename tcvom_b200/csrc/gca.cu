@@ -47,7 +47,7 @@ __global__ void gca_scales_kernel(const float* __restrict__ unknown, int h, int 
 }
 
 // one warp per patch
-template <bool SPLIT>
+template <int SPLIT>   // 0: fp32, 2: bf16 hi/lo planes, 3: bf16 hi/mid/lo planes
 __global__ void gca_prep_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ unknown, int n,
                                 int h, int w, const float* __restrict__ scales, void* __restrict__ Qv,
                                 void* __restrict__ Knv, float* __restrict__ mm) {
@@ -84,17 +84,19 @@ __global__ void gca_prep_kernel(const __nv_bfloat16* __restrict__ g, const float
     __nv_bfloat16* qo = reinterpret_cast<__nv_bfloat16*>(Qv) + off;
     __nv_bfloat16* ko = reinterpret_cast<__nv_bfloat16*>(Knv) + off;
     const long long plane = (long long)n * P * QD;
+    auto put = [&](__nv_bfloat16* dst, float x0, float x1) {
+#pragma unroll
+      for (int pl = 0; pl < SPLIT; ++pl) {
+        const __nv_bfloat16 b0 = __float2bfloat16_rn(x0), b1 = __float2bfloat16_rn(x1);
+        *reinterpret_cast<uint32_t*>(dst + pl * plane) = pack2(b0, b1);
+        x0 -= __bfloat162float(b0);
+        x1 -= __bfloat162float(b1);
+      }
+    };
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(q[2 * t], h0, l0);
-      split_bf16(q[2 * t + 1], h1, l1);
-      *reinterpret_cast<uint32_t*>(qo + t * GC + 2 * lane) = pack2(h0, h1);
-      *reinterpret_cast<uint32_t*>(qo + plane + t * GC + 2 * lane) = pack2(l0, l1);
-      split_bf16(q[2 * t] * inv, h0, l0);
-      split_bf16(q[2 * t + 1] * inv, h1, l1);
-      *reinterpret_cast<uint32_t*>(ko + t * GC + 2 * lane) = pack2(h0, h1);
-      *reinterpret_cast<uint32_t*>(ko + plane + t * GC + 2 * lane) = pack2(l0, l1);
+      put(qo + t * GC + 2 * lane, q[2 * t], q[2 * t + 1]);
+      put(ko + t * GC + 2 * lane, q[2 * t] * inv, q[2 * t + 1] * inv);
     }
   } else {
     float* qo = reinterpret_cast<float*>(Qv) + off;
@@ -239,12 +241,14 @@ int tcv_gca_prep(const void* g, const float* unknown, int n, int h, int w, void*
   if (rc) return rc;
   const long long warps = (long long)n * (h / 2) * (w / 2);
   const unsigned grid = (unsigned)((warps * 32 + 255) / 256);
-  if (bf16_split)
-    gca_prep_kernel<true><<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(g), unknown, n, h, w,
-                                                       scales, Q, Kn, mm);
+  auto G = reinterpret_cast<const __nv_bfloat16*>(g);
+  TCV_REQUIRE(bf16_split == 0 || bf16_split == 2 || bf16_split == 3 || bf16_split == 1, "gca_prep: planes must be 0, 2 or 3");
+  if (bf16_split == 3)
+    gca_prep_kernel<3><<<grid, 256, 0, S(stream)>>>(G, unknown, n, h, w, scales, Q, Kn, mm);
+  else if (bf16_split)
+    gca_prep_kernel<2><<<grid, 256, 0, S(stream)>>>(G, unknown, n, h, w, scales, Q, Kn, mm);
   else
-    gca_prep_kernel<false><<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(g), unknown, n, h, w,
-                                                        scales, Q, Kn, mm);
+    gca_prep_kernel<0><<<grid, 256, 0, S(stream)>>>(G, unknown, n, h, w, scales, Q, Kn, mm);
   return launched("gca_prep_kernel");
 }
 

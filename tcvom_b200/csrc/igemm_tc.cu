@@ -49,7 +49,7 @@ template <int BN, int BK, int NSPLIT>
 struct TcCfg {
   static constexpr int A_BYTES = 128 * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int PLANES = NSPLIT == 3 ? 2 : 1;
+  static constexpr int PLANES = NSPLIT == 6 ? 3 : (NSPLIT == 3 ? 2 : 1);
   static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
   // two CTAs per SM when the tile is small enough (their mainloop/epilogue phases overlap)
   static constexpr int BUDGET = BN <= 128 ? 100 * 1024 : 200 * 1024;
@@ -61,8 +61,10 @@ struct TcCfg {
 template <int BN, int BK, int NSPLIT, int EPI>
 __global__ void __launch_bounds__(192) igemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi,
                                                        const __grid_constant__ CUtensorMap mapA_lo,
+                                                       const __grid_constant__ CUtensorMap mapA_p2,
                                                        const __grid_constant__ CUtensorMap mapB_hi,
                                                        const __grid_constant__ CUtensorMap mapB_lo,
+                                                       const __grid_constant__ CUtensorMap mapB_p2,
                                                        const __grid_constant__ TcParams p) {
   using Cfg = TcCfg<BN, BK, NSPLIT>;
   constexpr int STAGES = Cfg::STAGES;
@@ -122,9 +124,13 @@ __global__ void __launch_bounds__(192) igemm_tc_kernel(const __grid_constant__ C
             mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
             tma_load_4d(st, &mapA_hi, full_bar(s), kc * BK, cw, ch, img);
             tma_load_3d(st + Cfg::PLANES * Cfg::A_BYTES, &mapB_hi, full_bar(s), kc * BK, n0, bz);
-            if (NSPLIT == 3) {
+            if (NSPLIT >= 3) {
               tma_load_4d(st + Cfg::A_BYTES, &mapA_lo, full_bar(s), kc * BK, cw, ch, img);
-              tma_load_3d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapB_lo, full_bar(s), kc * BK, n0, bz);
+              tma_load_3d(st + Cfg::PLANES * Cfg::A_BYTES + Cfg::B_BYTES, &mapB_lo, full_bar(s), kc * BK, n0, bz);
+            }
+            if (NSPLIT == 6) {
+              tma_load_4d(st + 2 * Cfg::A_BYTES, &mapA_p2, full_bar(s), kc * BK, cw, ch, img);
+              tma_load_3d(st + 3 * Cfg::A_BYTES + 2 * Cfg::B_BYTES, &mapB_p2, full_bar(s), kc * BK, n0, bz);
             }
           }
           __syncwarp();
@@ -148,10 +154,17 @@ __global__ void __launch_bounds__(192) igemm_tc_kernel(const __grid_constant__ C
         for (int ks = 0; ks < BK / 16; ++ks) {
           const uint64_t ah = smem_desc<BK>(a_hi + ks * 32), bh = smem_desc<BK>(b_hi + ks * 32);
           tc_mma(tmem_d, ah, bh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-          if (NSPLIT == 3) {
+          if (NSPLIT >= 3) {
             const uint64_t al = smem_desc<BK>(a_lo + ks * 32), bl = smem_desc<BK>(b_lo + ks * 32);
             tc_mma(tmem_d, ah, bl, idesc, 1u);
             tc_mma(tmem_d, al, bh, idesc, 1u);
+            if (NSPLIT == 6) {   // three bf16 planes per operand (~24 mantissa bits): + h.l2, l2.h, m.m
+              const uint64_t a2 = smem_desc<BK>(a_lo + Cfg::A_BYTES + ks * 32);
+              const uint64_t b2 = smem_desc<BK>(b_lo + Cfg::B_BYTES + ks * 32);
+              tc_mma(tmem_d, ah, b2, idesc, 1u);
+              tc_mma(tmem_d, a2, bh, idesc, 1u);
+              tc_mma(tmem_d, al, bl, idesc, 1u);
+            }
           }
         }
         tc_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
@@ -289,7 +302,7 @@ struct TcOperands {
 template <int BN, int BK, int NSPLIT, int EPI>
 static int launch_tc(const TcOperands& o, TcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BN, BK, NSPLIT>;
-  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+  CUtensorMap mA_hi, mA_lo, mA_p2, mB_hi, mB_lo, mB_p2;
   {
     cuuint64_t dims[4] = {(cuuint64_t)o.c, (cuuint64_t)o.w, (cuuint64_t)o.h, (cuuint64_t)o.n};
     cuuint64_t str[3] = {(cuuint64_t)o.c * 2, (cuuint64_t)o.w * o.c * 2, (cuuint64_t)o.a_img_stride * 2};
@@ -297,7 +310,9 @@ static int launch_tc(const TcOperands& o, TcParams& p, cudaStream_t st) {
     cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(p.TW * p.stride), (cuuint32_t)(p.TH * p.stride), 1};
     int rc = make_map(&mA_hi, o.a, 4, dims, str, box, BK, o.fp16, p.stride);
     if (rc) return rc;
-    rc = make_map(&mA_lo, NSPLIT == 3 ? o.a + o.a_plane : o.a, 4, dims, str, box, BK, o.fp16, p.stride);
+    rc = make_map(&mA_lo, NSPLIT >= 3 ? o.a + o.a_plane : o.a, 4, dims, str, box, BK, o.fp16, p.stride);
+    if (rc) return rc;
+    rc = make_map(&mA_p2, NSPLIT == 6 ? o.a + 2 * o.a_plane : o.a, 4, dims, str, box, BK, o.fp16, p.stride);
     if (rc) return rc;
   }
   {
@@ -306,7 +321,9 @@ static int launch_tc(const TcOperands& o, TcParams& p, cudaStream_t st) {
     cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
     int rc = make_map(&mB_hi, o.b, 3, dims, str, box, BK, o.fp16);
     if (rc) return rc;
-    rc = make_map(&mB_lo, NSPLIT == 3 ? o.b + o.b_plane : o.b, 3, dims, str, box, BK);
+    rc = make_map(&mB_lo, NSPLIT >= 3 ? o.b + o.b_plane : o.b, 3, dims, str, box, BK);
+    if (rc) return rc;
+    rc = make_map(&mB_p2, NSPLIT == 6 ? o.b + 2 * o.b_plane : o.b, 3, dims, str, box, BK);
     if (rc) return rc;
   }
   p.idesc = instr_desc(BN, o.fp16);
@@ -317,7 +334,7 @@ static int launch_tc(const TcOperands& o, TcParams& p, cudaStream_t st) {
   const int nrows = EPI == EPI_CONV ? p.cout : p.N;
   dim3 grid(p.tiles_x * tiles_y, (nrows + BN - 1) / BN, o.n);
   if (p.b_batched) grid = dim3((nrows + BN - 1) / BN, p.tiles_x * tiles_y, o.n);
-  kern<<<grid, 192, Cfg::SMEM, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, p);
+  kern<<<grid, 192, Cfg::SMEM, st>>>(mA_hi, mA_lo, mA_p2, mB_hi, mB_lo, mB_p2, p);
   return launched("igemm_tc_kernel");
 }
 
@@ -382,8 +399,8 @@ extern "C" int tcv_gemm_tn_tc(const void* A, long long a_plane, const void* B, l
                               int out_bf16, int in_fp16, tcv_stream_t stream) {
   TCV_REQUIRE(A && B && C, "gemm_tn_tc: null pointer");
   TCV_REQUIRE(M > 0 && N > 0 && K > 0 && K % 64 == 0, "gemm_tn_tc: K must be a positive multiple of 64");
-  const int bk = nsplit == 3 ? 32 : 64;
-  TCV_REQUIRE(nsplit == 1 || nsplit == 3, "gemm_tn_tc: nsplit must be 1 or 3");
+  const int bk = nsplit >= 3 ? 32 : 64;
+  TCV_REQUIRE(nsplit == 1 || nsplit == 3 || nsplit == 6, "gemm_tn_tc: nsplit must be 1, 3 or 6");
   TCV_REQUIRE(!in_fp16 || nsplit == 1, "gemm_tn_tc: fp16 operands only with nsplit == 1");
   TCV_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0,
               "gemm_tn_tc: pointers must be 16-byte aligned");
@@ -403,6 +420,10 @@ extern "C" int tcv_gemm_tn_tc(const void* A, long long a_plane, const void* B, l
   o.b_rows = N; o.b_z = batch;
   o.fp16 = in_fp16 != 0;
   cudaStream_t st = S(stream);
+  if (nsplit == 6) {
+    TCV_REQUIRE(!out_bf16, "gemm_tn_tc: nsplit == 6 writes fp32");
+    return launch_tc<128, 32, 6, EPI_F32>(o, p, st);
+  }
   if (nsplit == 3) {
     if (out_bf16) return launch_tc<128, 32, 3, EPI_BF16>(o, p, st);
     return launch_tc<128, 32, 3, EPI_F32>(o, p, st);

@@ -108,6 +108,9 @@ class GcaVmnEngine:
         # operand format of the P.V aggregation GEMM: "bf16x3" (3 MMAs/step; measured 3.7e-4 max-abs alpha
         # error at 384x512), "fp16" (1 MMA; 1.3e-3, over the 1e-3 bar), "bf16" (1 MMA; 8.8e-3)
         self.pv_mode = os.environ.get("TCV_PV_MODE", "bf16x3")
+        # bf16 planes per operand of the scores GEMM Q.Kn^T: 2 (three MMAs per K step, shipped) or 3 (six MMAs,
+        # fp32-grade logits; measured on B200: no parity gain on any fixture, +0.66 ms per 1080p window)
+        self.score_planes = int(os.environ.get("TCV_SCORE_PLANES", "2"))
 
     # ------------------------------------------------------------------ weights
     def _named(self) -> Dict[str, torch.Tensor]:
@@ -328,19 +331,20 @@ class GcaVmnEngine:
         O = self._empty((n, P, 2048))
         if self.use_tc_attn:
             # tcgen05 path: scores in bf16x3 (fp32-accurate logits), probabilities and values in bf16
-            Q = self._empty((2, n, P, 576), torch.bfloat16)
-            Kn = self._empty((2, n, P, 576), torch.bfloat16)
+            sp = self.score_planes
+            Q = self._empty((sp, n, P, 576), torch.bfloat16)
+            Kn = self._empty((sp, n, P, 576), torch.bfloat16)
             self._call("tcv_gca_prep", g.ptr, unknown.data_ptr(), n, h, w, Q.data_ptr(), Kn.data_ptr(),
-                       mm.data_ptr(), scales.data_ptr(), 1)
+                       mm.data_ptr(), scales.data_ptr(), sp)
             pv = {"bf16": (1, 1, 1, 0), "bf16x3": (2, 2, 3, 0), "fp16": (3, 1, 1, 1)}[self.pv_mode]
             mode, planes, nsplit, fp16 = pv
             Vt = self._empty((planes, n, 2048, P_pad), torch.bfloat16)
             self._call("tcv_gca_values", feat.ptr, n, h, w, Vt.data_ptr(), mode)
             Sm = self._empty((n, P, P_pad))
             self._call("tcv_gemm_tn_tc", Q.data_ptr(), n * P * 576, Kn.data_ptr(), n * P * 576, Sm.data_ptr(), P, P,
-                       576, P_pad, P * P_pad, n, 3, 0, 0,
+                       576, P_pad, P * P_pad, n, 6 if sp == 3 else 3, 0, 0,
                        meta=dict(kind="gca_scores_gemm_tc", flops=2 * n * P * P * 576,
-                                 bytes=n * (2 * 4 * P * 576 + 4 * P * P)))
+                                 bytes=n * (2 * 2 * sp * P * 576 + 4 * P * P)))
             Pb = self._empty((planes, n, P, P_pad), torch.bfloat16)
             self._call("tcv_gca_softmax", Sm.data_ptr(), mm.data_ptr(), n, P, P_pad, Pb.data_ptr(), mode,
                        meta=dict(kind="tcv_gca_softmax", bytes=n * P * P * (4 + 2 * planes)))

@@ -324,3 +324,112 @@ class EvalModel(nn.Module):
         plan.io["tris"].copy_(tris, non_blocking=True)
         self.run_plan(plan)
         return plan.io["alphas"].clone()
+
+
+class FullModel_VMD(nn.Module):
+    """Task wrapper with losses (models/model.py:248-357, and :15-246 for the shared parts).
+
+    forward(a [B,S,1,H,W] 0..255, fg, bg [B,S,3,H,W] BGR 0..255) -> the reference's 12-list
+    [L_alpha, L_comp, L_grad, L_dt, L_att, scaled_imgs, tris_vis, alphas, comps, scaled_gts, Fs, Bs].
+
+    Built for the inference use of the wrapper (pred_vmn.py:107-116: ``net.eval()`` + ``no_grad``): the loss
+    values are computed by fused forward kernels; there is no backward yet, so a grad-enabled / train-mode
+    call raises instead of falling back to PyTorch."""
+    TAM_OS = 8
+    FBA_L_ATT_MULTIPLIER = 1
+    ARCH_DICT = {'gca': None, 'dim': None, 'fba': None, 'index': None}     # pred_vmn.py:29 lists the keys
+    TRIMAP_CHANNEL_DICT = {'gca': 3, 'dim': 1, 'index': 1, 'fba': 8}
+    _with_att = True
+
+    def __init__(self, model, att_thres=0.3, label_smooth=0.2, dilate_kernel=None, eps=0, **kwargs):
+        super().__init__()
+        assert model.startswith('vmn'), "FullModel_VMD only support VMN arch"
+        self.att_thres = att_thres
+        self.label_smooth = label_smooth
+        self.DILATION_KERNEL = dilate_kernel
+        self.EPS = eps
+        self.IMG_SCALE = 1. / 255
+        self.register_buffer('IMG_MEAN', torch.tensor([0.485, 0.456, 0.406]).reshape([1, 1, 3, 1, 1]).float())
+        self.register_buffer('IMG_STD', torch.tensor([0.229, 0.224, 0.225]).reshape([1, 1, 3, 1, 1]).float())
+        self.model_name = model
+        self.NET = get_VMN_models(arch=model, **kwargs)
+        self.window = kwargs['agg_window']
+        self.method = model[model.rfind('_') + 1:]
+        self.TRIMAP_CHANNEL = self.TRIMAP_CHANNEL_DICT[self.method]
+
+    def _plan(self, B, S, H, W) -> Plan:
+        eng = self.NET.engine()
+        self.__dict__["_eng"] = eng
+        key = ("vmd" if self._with_att else "full", B, S, H, W, float(self.EPS))
+        plan = eng.plans.get(key)
+        if plan is not None:
+            return plan
+        plan = Plan()
+        eng._rec = plan
+        try:
+            a = eng._empty((B, S, 1, H, W)); fg = eng._empty((B, S, 3, H, W)); bg = eng._empty((B, S, 3, H, W))
+            radii = eng._empty((B,), torch.int32)
+            a.zero_(); fg.zero_(); bg.zero_(); radii.zero_()
+            x8 = eng._act(B * S, H, W, 8)
+            trimask = eng._empty((B, S, 1, H, W)); gts = eng._empty((B, S, 1, H, W)); tris_vis = eng._empty((B, S, 1, H, W))
+            fgs = eng._empty((B, S, 3, H, W)); bgs = eng._empty((B, S, 3, H, W)); imgs = eng._empty((B, S, 3, H, W))
+            tmp = eng._empty((2 * B * S * H * W,), torch.uint8)
+            alphas = eng._empty((B, S, 1, H, W)); comps = eng._empty((B, S, 3, H, W))
+            gt8 = eng._empty((B, S, H // 8, W // 8)); acc = eng._empty((6 * S,), torch.float64)
+            losses = eng._empty((5,))
+            n0 = _cabi.launch_count()
+            eng._call("tcv_preprocess_train", a.data_ptr(), fg.data_ptr(), bg.data_ptr(), B, S, H, W, float(self.EPS),
+                      radii.data_ptr(), x8.ptr, trimask.data_ptr(), gts.data_ptr(), fgs.data_ptr(), bgs.data_ptr(),
+                      imgs.data_ptr(), tris_vis.data_ptr(), tmp.data_ptr())
+            out = eng.window_program(x8, trimask.reshape(B * S, H, W), B, S, H, W)
+            att = self._with_att
+            eng._call("tcv_losses_vmd", out["pred"].data_ptr(), trimask.data_ptr(), gts.data_ptr(), fgs.data_ptr(),
+                      bgs.data_ptr(), out["attb"].data_ptr() if att else None, out["attf"].data_ptr() if att else None,
+                      out["small_mask"].data_ptr() if att else None, B, S, H, W, int(self.window),
+                      float(self.att_thres), float(self.label_smooth), float(self.FBA_L_ATT_MULTIPLIER if self.method == 'fba' else 1),
+                      alphas.data_ptr(), comps.data_ptr(), gt8.data_ptr(), acc.data_ptr(), losses.data_ptr())
+            plan.n_launch = _cabi.launch_count() - n0
+            plan.io = dict(a=a, fg=fg, bg=bg, radii=radii, losses=losses, imgs=imgs, tris_vis=tris_vis, alphas=alphas,
+                           comps=comps, gts=gts, fgs=fgs, bgs=bgs, trimask=trimask,
+                           **{k: out[k] for k in ("pred", "attb", "attf", "small_mask")})
+        finally:
+            eng._rec = None
+        eng.plans[key] = plan
+        return plan
+
+    run_plan = EvalModel.run_plan
+
+    def forward(self, a, fg, bg, wb=None, wf=None):
+        _require_cuda(a, "a")
+        self.NET._check_mode()
+        B, S = a.shape[:2]
+        H, W = a.shape[-2:]
+        assert S >= 3
+        if H % 32 or W % 32:
+            raise ValueError("tcvom_b200: H and W must be multiples of 32")
+        plan = self._plan(B, S, H, W)
+        # trimap width: the reference draws one radius per sample on the host (model.py:62)
+        rad = [int(torch.randint(0, 26, size=())) if self.DILATION_KERNEL is None else int(self.DILATION_KERNEL)
+               for _ in range(B)]
+        plan.io["radii"].copy_(torch.tensor(rad, dtype=torch.int32), non_blocking=True)
+        plan.io["a"].copy_(a, non_blocking=True)
+        plan.io["fg"].copy_(fg, non_blocking=True)
+        plan.io["bg"].copy_(bg, non_blocking=True)
+        self.run_plan(plan)
+        io = plan.io
+        L = io["losses"].clone()
+        outs = [L[0], L[1], L[2]]
+        if self._with_att:
+            outs += [L[3], L[4]]
+        return outs + [io["imgs"].clone(), io["tris_vis"].clone(), io["alphas"].clone(), io["comps"].clone(),
+                       io["gts"].clone(), io["fgs"].clone(), io["bgs"].clone()]
+
+
+class FullModel(FullModel_VMD):
+    """models/model.py:15-246 for the VMN archs: [L_alpha, L_comp, L_grad, imgs, tris_vis, alphas, comps, gts, Fs, Bs]."""
+    _with_att = False
+
+    def __init__(self, model, dilate_kernel=None, eps=0, **kwargs):
+        if not model.startswith('vmn'):
+            raise NotImplementedError("tcvom_b200: only the VMN (video) architectures are on the built path")
+        super().__init__(model, dilate_kernel=dilate_kernel, eps=eps, **kwargs)

@@ -156,3 +156,48 @@ def test_eval_forward_1080p_matches_oracle():
     err = (out - ref).abs().max().item()
     print("1088x1920 alpha max abs err", err)
     assert err < ALPHA_TOL
+
+
+def test_full_vmd_forward_matches_reference_golden():
+    """FullModel_VMD eval-mode forward (pred_vmn.py path), S=5: losses L_im / L_tc / L_af + visual outputs."""
+    import tcvom_b200
+    g = golden("train_s5.npz")
+    m = tcvom_b200.FullModel_VMD(model="vmn_gca", agg_window=7, dilate_kernel=3)
+    m.NET.load_state_dict(fixture_sd(), strict=True)
+    m = m.cuda().eval()
+    a, fg, bg = (torch.from_numpy(g[k]).float().cuda() for k in ("a", "fg", "bg"))
+    with torch.no_grad():
+        out = m(a, fg, bg)
+    assert len(out) == 12
+    losses = np.array([float(o) for o in out[:5]])
+    print("losses", losses, "ref", g["losses"])
+    # L_alpha / L_dt are means of |alpha - gt| (alpha within 1e-3); L_att is a BCE over logits of magnitude ~1e2
+    assert abs(losses[0] - g["losses"][0]) < 1e-3 and abs(losses[3] - g["losses"][3]) < 1e-3
+    assert losses[1] == 0 and losses[2] == 0
+    assert abs(losses[4] - g["losses"][4]) <= 2e-3 * abs(g["losses"][4])
+    assert np.abs(out[5].cpu().numpy() - g["scaled_imgs"]).max() < 1e-6
+    assert np.abs(out[6].cpu().numpy() - g["tris_vis"]).max() < 1e-6
+    assert np.abs(out[7].cpu().numpy() - g["alphas"]).max() < ALPHA_TOL
+    assert np.abs(out[8].cpu().numpy() - g["comps"]).max() < ALPHA_TOL
+
+
+def test_full_vmd_s3_and_random_dilation_against_oracle():
+    """S=3 (L_tc == 0, model.py:344-345) and the per-sample random trimap width (model.py:62)."""
+    import tcvom_b200
+    g = golden("train_s5.npz")
+    a, fg, bg = (torch.from_numpy(g[k][:, :3]).float() for k in ("a", "fg", "bg"))
+    a2 = torch.cat([a, a.flip(-1)], 0); fg2 = torch.cat([fg, fg.flip(-1)], 0); bg2 = torch.cat([bg, bg.flip(-1)], 0)
+    m = tcvom_b200.FullModel_VMD(model="vmn_gca", agg_window=7, dilate_kernel=None)
+    m.NET.load_state_dict(fixture_sd(), strict=True)
+    m = m.cuda().eval()
+    torch.manual_seed(5)
+    radii = [int(torch.randint(0, 26, size=())) for _ in range(2)]
+    torch.manual_seed(5)
+    with torch.no_grad():
+        out = m(a2.cuda(), fg2.cuda(), bg2.cuda())
+    ref = O.full_vmd_forward(fixture_sd(), a2, fg2, bg2, radii)
+    assert float(out[3]) == 0.0 and float(ref[3]) == 0.0
+    assert abs(float(out[0]) - float(ref[0])) < 1e-3
+    assert abs(float(out[4]) - float(ref[4])) <= 2e-3 * abs(float(ref[4])) + 1e-4
+    assert (out[6].cpu() - ref[6]).abs().max() < 1e-6          # tris_vis: same dilation radii were drawn
+    assert (out[7].cpu() - ref[7]).abs().max() < ALPHA_TOL

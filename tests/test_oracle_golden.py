@@ -50,3 +50,17 @@ def test_tam_operator_matches_reference():
     assert np.abs(feat.numpy() - g["feat"]).max() < 1e-4
     assert np.abs(attb.numpy() - g["attb"]).max() < 1e-4
     assert np.abs(attf.numpy() - g["attf"]).max() < 1e-4
+
+
+def test_full_vmd_forward_matches_reference():
+    """FullModel_VMD.forward (eval mode, S=5, fixed dilation 3): losses + visual outputs."""
+    g = golden("train_s5.npz")
+    sd = fixture_sd()
+    a, fg, bg = (torch.from_numpy(g[k]).float() for k in ("a", "fg", "bg"))
+    out = O.full_vmd_forward(sd, a, fg, bg, radii=[3])
+    losses = np.array([float(o) for o in out[:5]])
+    assert np.allclose(losses, g["losses"], rtol=2e-4, atol=1e-6), (losses, g["losses"])
+    assert np.abs(out[5].numpy() - g["scaled_imgs"]).max() < 1e-6
+    assert np.abs(out[6].numpy() - g["tris_vis"]).max() < 1e-6
+    assert np.abs(out[7].numpy() - g["alphas"]).max() < 5e-5
+    assert np.abs(out[8].numpy() - g["comps"]).max() < 5e-5

@@ -1,0 +1,30 @@
+"""One conv shape under one debug-flag setting (for ncu): python tools/conv_probe1.py cin cout h w n flags"""
+import ctypes as C, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
+import torch
+from tcvom_b200 import _cabi
+from tcvom_b200._cabi import ConvDesc
+from tc_check import split
+cin, cout, h, w, n, flags = map(int, sys.argv[1:7])
+L = _cabi.lib(); dev = "cuda"; st = torch.cuda.current_stream().cuda_stream
+x = split(torch.randn(n, h, w, cin, device=dev))
+taps = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+wf = (torch.randn(9, cin, cout, device=dev) / (cin * 9) ** 0.5).contiguous()
+wtc = torch.empty((2, 9, cout, cin), dtype=torch.bfloat16, device=dev)
+_cabi.check(L.tcv_pack_weight_tc(wf.data_ptr(), 9, cin, cout, wtc.data_ptr(), st), "pack")
+s1 = torch.rand(cout, device=dev) + 0.5; b1 = torch.randn(cout, device=dev)
+y = torch.zeros((2, n, h, w, cout), dtype=torch.bfloat16, device=dev)
+d = ConvDesc()
+d.x = x.data_ptr(); d.n, d.ih, d.iw, d.cin = n, h, w, cin
+d.w = wf.data_ptr(); d.ntaps = 9; d.w_tc = wtc.data_ptr(); d.w_tc_taps = 9
+for i, (dy, dx) in enumerate(taps):
+    d.dy[i], d.dx[i], d.wtap[i] = dy, dx, i
+d.stride, d.pad_mode = 1, 0
+d.y = y.data_ptr(); d.oh, d.ow, d.cout, d.gh, d.gw = h, w, cout, h, w
+d.oy_mul, d.oy_off, d.ox_mul, d.ox_off = 1, 0, 1, 0
+d.s1, d.b1 = s1.data_ptr(), b1.data_ptr(); d.act = 1
+L.tcv_set_debug_flags(flags)
+for _ in range(3):
+    _cabi.check(L.tcv_conv2d(C.byref(d), st), "conv")
+torch.cuda.synchronize()
