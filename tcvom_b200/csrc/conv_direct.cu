@@ -15,22 +15,27 @@ namespace tcv {
 
 constexpr int CIC = 32;  // input channels staged per weight chunk
 
-template <int COT>
+// PX output pixels (consecutive in x) per thread (PX = 2 halves the shared-memory weight traffic per FMA but
+// measured slower than PX = 1 on B200, see launch_conv).
+template <int COT, int PX>
 __global__ void __launch_bounds__(256) conv_direct_kernel(const tcv_conv_desc d) {
   extern __shared__ float wsm[];  // [ntaps][CIC][COT]
   const int cic = d.cin < CIC ? d.cin : CIC;
-  const int pix = blockIdx.x * 256 + threadIdx.x;
+  const int gwp = d.gw / PX;                       // pixel groups per row (gw % PX == 0)
+  const int grp = blockIdx.x * 256 + threadIdx.x;
   const int co0 = blockIdx.y * COT;
   const int n = blockIdx.z;
-  const bool valid = pix < d.gh * d.gw;
-  const int gy = valid ? pix / d.gw : 0;
-  const int gx = valid ? pix - gy * d.gw : 0;
+  const bool valid = grp < d.gh * gwp;
+  const int gy = valid ? grp / gwp : 0;
+  const int gx0 = valid ? (grp - gy * gwp) * PX : 0;
   const long long xplane = d.x_plane;
   const __nv_bfloat16* xin = reinterpret_cast<const __nv_bfloat16*>(d.x) + (long long)n * d.x_img_stride;
 
-  float acc[COT];
+  float acc[PX][COT];
 #pragma unroll
-  for (int j = 0; j < COT; ++j) acc[j] = 0.f;
+  for (int q = 0; q < PX; ++q)
+#pragma unroll
+    for (int j = 0; j < COT; ++j) acc[q][j] = 0.f;
 
   for (int ci0 = 0; ci0 < d.cin; ci0 += cic) {
     __syncthreads();
@@ -45,34 +50,52 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const tcv_conv_desc d)
     if (!valid) continue;
     for (int t = 0; t < d.ntaps; ++t) {
       int iy = gy * d.stride + d.dy[t];
-      int ix = gx * d.stride + d.dx[t];
-      if (d.pad_mode == TCV_PAD_REFLECT) {
-        iy = reflect(iy, d.ih);
-        ix = reflect(ix, d.iw);
-      } else if (iy < 0 || iy >= d.ih || ix < 0 || ix >= d.iw) {
-        continue;
-      }
-      const __nv_bfloat16* p = xin + ((long long)iy * d.iw + ix) * d.cin + ci0;
+      bool rowok = true;
+      if (d.pad_mode == TCV_PAD_REFLECT) iy = reflect(iy, d.ih);
+      else rowok = iy >= 0 && iy < d.ih;
+      if (!rowok) continue;
+      const __nv_bfloat16* prow = xin + (long long)iy * d.iw * d.cin + ci0;
       const float* wt = wsm + t * cic * COT;
+      int ixs[PX];
+      bool ok[PX];
+#pragma unroll
+      for (int q = 0; q < PX; ++q) {
+        int ix = (gx0 + q) * d.stride + d.dx[t];
+        if (d.pad_mode == TCV_PAD_REFLECT) { ix = reflect(ix, d.iw); ok[q] = true; }
+        else { ok[q] = ix >= 0 && ix < d.iw; ix = ok[q] ? ix : 0; }
+        ixs[q] = ix;
+      }
       for (int c8 = 0; c8 < cic; c8 += 8) {
-        float f[8];
-        load8(p + c8, xplane, f);
+        float f[PX][8];
+#pragma unroll
+        for (int q = 0; q < PX; ++q) {
+          if (ok[q]) load8(prow + (long long)ixs[q] * d.cin + c8, xplane, f[q]);
+          else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[q][k] = 0.f;
+          }
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float xv = f[k];
           const float* wp = wt + (c8 + k) * COT;
           if (COT >= 4) {
 #pragma unroll
             for (int j = 0; j < COT / 4; ++j) {
               const float4 w4 = reinterpret_cast<const float4*>(wp)[j];
-              acc[4 * j + 0] = fmaf(xv, w4.x, acc[4 * j + 0]);
-              acc[4 * j + 1] = fmaf(xv, w4.y, acc[4 * j + 1]);
-              acc[4 * j + 2] = fmaf(xv, w4.z, acc[4 * j + 2]);
-              acc[4 * j + 3] = fmaf(xv, w4.w, acc[4 * j + 3]);
+#pragma unroll
+              for (int q = 0; q < PX; ++q) {
+                const float xv = f[q][k];
+                acc[q][4 * j + 0] = fmaf(xv, w4.x, acc[q][4 * j + 0]);
+                acc[q][4 * j + 1] = fmaf(xv, w4.y, acc[q][4 * j + 1]);
+                acc[q][4 * j + 2] = fmaf(xv, w4.z, acc[q][4 * j + 2]);
+                acc[q][4 * j + 3] = fmaf(xv, w4.w, acc[q][4 * j + 3]);
+              }
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < COT; ++j) acc[j] = fmaf(xv, wp[j], acc[j]);
+            for (int j = 0; j < COT; ++j)
+#pragma unroll
+              for (int q = 0; q < PX; ++q) acc[q][j] = fmaf(f[q][k], wp[j], acc[q][j]);
           }
         }
       }
@@ -81,71 +104,75 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const tcv_conv_desc d)
   if (!valid) return;
 
   // ---- fused epilogue
-  const int oy = gy * d.oy_mul + d.oy_off;
-  const int ox = gx * d.ox_mul + d.ox_off;
   const long long oplane = (long long)d.n * d.oh * d.ow * d.cout;
-  const long long obase = (((long long)n * d.oh + oy) * d.ow + ox) * d.cout + co0;
-  if (d.s1) {
 #pragma unroll
-    for (int j = 0; j < COT; ++j) acc[j] = acc[j] * d.s1[co0 + j];
-  }
-  if (d.b1) {
+  for (int q = 0; q < PX; ++q) {
+    float* a = acc[q];
+    const int oy = gy * d.oy_mul + d.oy_off;
+    const int ox = (gx0 + q) * d.ox_mul + d.ox_off;
+    const long long obase = (((long long)n * d.oh + oy) * d.ow + ox) * d.cout + co0;
+    if (d.s1) {
 #pragma unroll
-    for (int j = 0; j < COT; ++j) acc[j] += d.b1[co0 + j];
-  }
-  if (d.res1) {
-    const int rh = d.oh >> d.res1_shift, rw = d.ow >> d.res1_shift;
-    const long long rplane = d.res1_plane;
-    const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(d.res1) +
-                             (((long long)n * rh + (oy >> d.res1_shift)) * rw + (ox >> d.res1_shift)) * d.cout + co0;
-    if (COT >= 8) {
+      for (int j = 0; j < COT; ++j) a[j] = a[j] * d.s1[co0 + j];
+    }
+    if (d.b1) {
 #pragma unroll
-      for (int j = 0; j < COT; j += 8) {
-        float f[8];
-        load8(r + j, rplane, f);
+      for (int j = 0; j < COT; ++j) a[j] += d.b1[co0 + j];
+    }
+    if (d.res1) {
+      const int rh = d.oh >> d.res1_shift, rw = d.ow >> d.res1_shift;
+      const long long rplane = d.res1_plane;
+      const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(d.res1) +
+                               (((long long)n * rh + (oy >> d.res1_shift)) * rw + (ox >> d.res1_shift)) * d.cout + co0;
+      if (COT >= 8) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[j + k] += f[k];
+        for (int j = 0; j < COT; j += 8) {
+          float f[8];
+          load8(r + j, rplane, f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) a[j + k] += f[k];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < COT; ++j) a[j] += load1(r + j, rplane);
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < COT; ++j) acc[j] += load1(r + j, rplane);
     }
-  }
 #pragma unroll
-  for (int j = 0; j < COT; ++j) acc[j] = apply_act(acc[j], d.act);
-  if (d.s2) {
+    for (int j = 0; j < COT; ++j) a[j] = apply_act(a[j], d.act);
+    if (d.s2) {
 #pragma unroll
-    for (int j = 0; j < COT; ++j) acc[j] = acc[j] * d.s2[co0 + j] + d.b2[co0 + j];
-  }
-  if (d.res2) {
-    const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(d.res2) + obase;
-    if (COT >= 8) {
+      for (int j = 0; j < COT; ++j) a[j] = a[j] * d.s2[co0 + j] + d.b2[co0 + j];
+    }
+    if (d.res2) {
+      const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(d.res2) + obase;
+      if (COT >= 8) {
 #pragma unroll
-      for (int j = 0; j < COT; j += 8) {
-        float f[8];
-        load8(r + j, d.res2_plane, f);
+        for (int j = 0; j < COT; j += 8) {
+          float f[8];
+          load8(r + j, d.res2_plane, f);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[j + k] += f[k];
+          for (int k = 0; k < 8; ++k) a[j + k] += f[k];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < COT; ++j) a[j] += load1(r + j, d.res2_plane);
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < COT; ++j) acc[j] += load1(r + j, d.res2_plane);
     }
-  }
-  if (d.y) {
-    __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(d.y) + obase;
-    if (COT >= 8) {
+    if (d.y) {
+      __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(d.y) + obase;
+      if (COT >= 8) {
 #pragma unroll
-      for (int j = 0; j < COT; j += 8) store8(y + j, oplane, acc + j);
-    } else {
+        for (int j = 0; j < COT; j += 8) store8(y + j, oplane, a + j);
+      } else {
 #pragma unroll
-      for (int j = 0; j < COT; ++j) store1(y + j, oplane, acc[j]);
+        for (int j = 0; j < COT; ++j) store1(y + j, oplane, a[j]);
+      }
     }
-  }
-  if (d.y_f32) {
-    float* y = d.y_f32 + obase;
+    if (d.y_f32) {
+      float* y = d.y_f32 + obase;
 #pragma unroll
-    for (int j = 0; j < COT; ++j) y[j] = acc[j];
+      for (int j = 0; j < COT; ++j) y[j] = a[j];
+    }
   }
 }
 
@@ -153,8 +180,14 @@ template <int COT>
 static int launch_conv(const tcv_conv_desc& d, cudaStream_t st) {
   const int cic = d.cin < CIC ? d.cin : CIC;
   const size_t smem = (size_t)d.ntaps * cic * COT * sizeof(float);
-  dim3 grid((d.gh * d.gw + 255) / 256, d.cout / COT, d.n);
-  conv_direct_kernel<COT><<<grid, 256, smem, st>>>(d);
+  // PX = 2 measured SLOWER on B200 (3.3 vs 2.6 ms per 1080p window over the six direct layers): disabled
+  if (false && d.gw % 2 == 0) {
+    dim3 grid((d.gh * (d.gw / 2) + 255) / 256, d.cout / COT, d.n);
+    conv_direct_kernel<COT, 2><<<grid, 256, smem, st>>>(d);
+  } else {
+    dim3 grid((d.gh * d.gw + 255) / 256, d.cout / COT, d.n);
+    conv_direct_kernel<COT, 1><<<grid, 256, smem, st>>>(d);
+  }
   return launched("conv_direct_kernel");
 }
 

@@ -120,30 +120,43 @@ __device__ __forceinline__ void store_operand(void* base, long long i, long long
   else reinterpret_cast<__half*>(base)[i] = __float2half_rn(v);
 }
 
+// Block = (64 consecutive patches p, one of the 16 taps, image): pixel rows are read coalesced (128
+// channels = 256 B per plane), transposed through shared memory, and written as 64-patch row segments.
 template <int MODE>
-__global__ void gca_values_kernel(const __nv_bfloat16* __restrict__ feat, int n, int h, int w, int P_pad,
-                                  void* __restrict__ Vt) {
+__global__ void __launch_bounds__(256) gca_values_kernel(const __nv_bfloat16* __restrict__ feat, int n, int h, int w,
+                                                         int P_pad, void* __restrict__ Vt) {
+  __shared__ float tile[64][FC + 1];
   const int hh = h / 2, ww = w / 2, P = hh * ww;
-  const long long total = (long long)n * VD * P_pad;
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int p = (int)(i % P_pad);
-  const int row = (int)((i / P_pad) % VD);
-  const int img = (int)(i / ((long long)P_pad * VD));
-  float v = 0.f;
-  if (p < P) {
-    const int c = row % FC, t = row / FC;
-    const int py = p / ww, px = p - py * ww;
-    const int yy = reflect(2 * py + t / 4 - 1, h), xx = reflect(2 * px + t % 4 - 1, w);
-    v = load1(feat + (((long long)img * h + yy) * w + xx) * FC + c, (long long)n * h * w * FC);
+  const int p0 = blockIdx.x * 64, t = blockIdx.y, img = blockIdx.z;
+  const long long fplane = (long long)n * h * w * FC;
+  for (int i = threadIdx.x; i < 64 * (FC / 8); i += 256) {
+    const int pp = i / (FC / 8), c8 = (i % (FC / 8)) * 8;
+    const int p = p0 + pp;
+    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (p < P) {
+      const int py = p / ww, px = p - py * ww;
+      const int yy = reflect(2 * py + t / 4 - 1, h), xx = reflect(2 * px + t % 4 - 1, w);
+      load8(feat + (((long long)img * h + yy) * w + xx) * FC + c8, fplane, f);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tile[pp][c8 + k] = f[k];
   }
-  store_operand<MODE>(Vt, i, total, v);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long total = (long long)n * VD * P_pad;
+  for (int c = warp; c < FC; c += 8) {
+    const long long o = ((long long)img * VD + t * FC + c) * P_pad + p0;
+    store_operand<MODE>(Vt, o + lane, total, tile[lane][c]);
+    store_operand<MODE>(Vt, o + lane + 32, total, tile[lane + 32][c]);
+  }
 }
 
-// one CTA per (row q, image): in-place masked softmax over keys
+// one CTA per (row q, image): masked softmax over keys with the row cached in shared memory
+// (one HBM read of the fp32 logits, one write of the operand-format probabilities)
 template <int MODE>
 __global__ void __launch_bounds__(256) gca_softmax_kernel(float* __restrict__ S, const float* __restrict__ mm, int P,
                                                           int P_pad, void* __restrict__ Pb, long long plane) {
+  extern __shared__ float srow[];   // P_pad floats
   __shared__ float red[32];
   __shared__ float bcast;
   const int q = blockIdx.x, img = blockIdx.y;
@@ -151,10 +164,17 @@ __global__ void __launch_bounds__(256) gca_softmax_kernel(float* __restrict__ S,
   const float diag = -1e4f * mm[(long long)img * P + q];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float mx = -INFINITY;
-  for (int p = threadIdx.x; p < P; p += 256) {
-    float s = row[p];
-    if (p == q) s += diag;
-    mx = fmaxf(mx, s);
+  for (int p4 = threadIdx.x * 4; p4 < P_pad; p4 += 1024) {
+    float4 v = *reinterpret_cast<const float4*>(row + p4);
+    float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int p = p4 + k;
+      if (p == q) e[k] += diag;
+      if (p >= P) e[k] = -INFINITY;
+      mx = fmaxf(mx, e[k]);
+    }
+    *reinterpret_cast<float4*>(srow + p4) = make_float4(e[0], e[1], e[2], e[3]);
   }
   mx = warp_max(mx);
   if (lane == 0) red[warp] = mx;
@@ -167,12 +187,11 @@ __global__ void __launch_bounds__(256) gca_softmax_kernel(float* __restrict__ S,
   __syncthreads();
   mx = bcast;
   float sum = 0.f;
-  for (int p = threadIdx.x; p < P; p += 256) {
-    float s = row[p];
-    if (p == q) s += diag;
-    const float e = expf(s - mx);
-    row[p] = e;
-    sum += e;
+  for (int p4 = threadIdx.x * 4; p4 < P_pad; p4 += 1024) {
+    float4 v = *reinterpret_cast<const float4*>(srow + p4);
+    v.x = expf(v.x - mx); v.y = expf(v.y - mx); v.z = expf(v.z - mx); v.w = expf(v.w - mx);   // exp(-inf) = 0 on pads
+    sum += (v.x + v.y) + (v.z + v.w);
+    *reinterpret_cast<float4*>(srow + p4) = v;
   }
   sum = warp_sum(sum);
   __syncthreads();
@@ -185,11 +204,23 @@ __global__ void __launch_bounds__(256) gca_softmax_kernel(float* __restrict__ S,
   }
   __syncthreads();
   const float inv = 1.0f / bcast;
-  if (MODE != 0) {
-    const long long o = ((long long)img * P + q) * P_pad;
-    for (int p = threadIdx.x; p < P_pad; p += 256) store_operand<MODE>(Pb, o + p, plane, p < P ? row[p] * inv : 0.f);
-  } else {
-    for (int p = threadIdx.x; p < P_pad; p += 256) row[p] = p < P ? row[p] * inv : 0.f;
+  const long long o = ((long long)img * P + q) * P_pad;
+  for (int p4 = threadIdx.x * 4; p4 < P_pad; p4 += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(srow + p4);
+    const float e[4] = {v.x * inv, v.y * inv, v.z * inv, v.w * inv};
+    if (MODE == 0) {
+      *reinterpret_cast<float4*>(row + p4) = make_float4(e[0], e[1], e[2], e[3]);
+    } else if (MODE == 2) {
+      __nv_bfloat16 hb[4], lb[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) split_bf16(e[k], hb[k], lb[k]);
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(Pb) + o + p4;
+      *reinterpret_cast<uint2*>(dst) = make_uint2(pack2(hb[0], hb[1]), pack2(hb[2], hb[3]));
+      *reinterpret_cast<uint2*>(dst + plane) = make_uint2(pack2(lb[0], lb[1]), pack2(lb[2], lb[3]));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) store_operand<MODE>(Pb, o + p4 + k, plane, e[k]);
+    }
   }
 }
 
@@ -257,7 +288,8 @@ int tcv_gca_values(const void* feat, int n, int h, int w, void* Vt, int mode, tc
   TCV_REQUIRE(h % 2 == 0 && w % 2 == 0 && h >= 4 && w >= 4, "gca_values: h,w must be even and >= 4");
   const int P = (h / 2) * (w / 2), P_pad = (P + 63) / 64 * 64;
   const long long total = (long long)n * VD * P_pad;
-  const unsigned grid = (unsigned)((total + 255) / 256);
+  (void)total;
+  const dim3 grid(P_pad / 64, 16, n);
   TCV_REQUIRE(mode >= 0 && mode <= 3, "gca_values: mode must be 0..3");
   auto F = reinterpret_cast<const __nv_bfloat16*>(feat);
   switch (mode) {
@@ -275,13 +307,21 @@ int tcv_gca_softmax(float* Sm, const float* mm, int n, int P, int P_pad, void* P
   TCV_REQUIRE(P > 0 && P_pad >= P, "gca_softmax: bad P");
   dim3 grid(P, n);
   TCV_REQUIRE(mode >= 0 && mode <= 3 && (mode == 0 || P_out), "gca_softmax: bad mode / missing output");
+  TCV_REQUIRE(P_pad % 4 == 0 && (size_t)P_pad * 4 <= 200 * 1024, "gca_softmax: row of %d keys does not fit shared memory", P_pad);
   const long long plane = (long long)n * P * P_pad;
+  const size_t smem = (size_t)P_pad * sizeof(float);
+#define TCV_SM_LAUNCH(M, OUT)                                                                               \
+  do {                                                                                                      \
+    TCV_CUDA(cudaFuncSetAttribute(gca_softmax_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    gca_softmax_kernel<M><<<grid, 256, smem, S(stream)>>>(Sm, mm, P, P_pad, OUT, plane);                      \
+  } while (0)
   switch (mode) {
-    case 0: gca_softmax_kernel<0><<<grid, 256, 0, S(stream)>>>(Sm, mm, P, P_pad, nullptr, plane); break;
-    case 1: gca_softmax_kernel<1><<<grid, 256, 0, S(stream)>>>(Sm, mm, P, P_pad, P_out, plane); break;
-    case 2: gca_softmax_kernel<2><<<grid, 256, 0, S(stream)>>>(Sm, mm, P, P_pad, P_out, plane); break;
-    default: gca_softmax_kernel<3><<<grid, 256, 0, S(stream)>>>(Sm, mm, P, P_pad, P_out, plane); break;
+    case 0: TCV_SM_LAUNCH(0, nullptr); break;
+    case 1: TCV_SM_LAUNCH(1, P_out); break;
+    case 2: TCV_SM_LAUNCH(2, P_out); break;
+    default: TCV_SM_LAUNCH(3, P_out); break;
   }
+#undef TCV_SM_LAUNCH
   return launched("gca_softmax_kernel");
 }
 
