@@ -72,6 +72,8 @@ typedef struct {
   const void* w_tc;   /* optional bf16 hi/lo [2][w_tc_taps][cout][cin] copy of w (tcv_pack_weight_tc);
                          when present and the shape qualifies, the tcgen05 implicit-GEMM path runs */
   int w_tc_taps;
+  const void* w_tc_fold; /* optional, cin == 8 3x3 only: bf16 hi/lo [2][3][cout][32] (tcv_pack_weight_fold):
+                            horizontal taps folded into K for the narrow-layer tcgen05 kernel             */
   int ntaps;
   int dy[TCV_MAX_TAPS], dx[TCV_MAX_TAPS];
   int wtap[TCV_MAX_TAPS]; /* weight slice used by tap t (identity for an ordinary conv)      */
@@ -95,10 +97,11 @@ typedef struct {
 } tcv_conv_desc;
 
 int tcv_conv2d(const tcv_conv_desc* d, tcv_stream_t stream);
-/* which kernel tcv_conv2d dispatches this descriptor to: 2 = persistent shared-halo tcgen05 conv,
+/* which kernel tcv_conv2d dispatches this descriptor to: 3 = narrow-layer tcgen05 conv (un-swizzled
+ * halo tile), 2 = persistent shared-halo tcgen05 conv,
  * 1 = tcgen05 implicit GEMM (one tap per K block), 0 = CUDA-core gather conv (no launch) */
 int tcv_conv2d_path(const tcv_conv_desc* d);
-/* selects the highest tensor-core conv kernel generation tcv_conv2d may use (1 or 2; default 2);
+/* selects the highest tensor-core conv kernel generation tcv_conv2d may use (1, 2 or 3; default 3);
  * returns the previous value.  For A/B measurements and tests. */
 int tcv_set_conv_tc_version(int v);
 /* measurement switches for kernel bring-up (bit 0: skip MMAs, 1: skip epilogue memory ops, 2/3: load
@@ -116,6 +119,10 @@ int tcv_sn_fold_pack(const float* w_bar, const float* u, const float* v, int cou
 /* bf16 hi/lo re-layout of a packed fp32 weight for the tcgen05 path:
  * packed fp32 [taps][cin][cout] -> w_tc bf16 [2][taps][cout][cin] (plane 0 = hi, plane 1 = lo) */
 int tcv_pack_weight_tc(const float* packed, int taps, int cin, int cout, void* w_tc, tcv_stream_t stream);
+
+/* folded 3x3 weights of an 8-channel-input conv: packed fp32 [9][8][cout] -> bf16 [2][3][cout][32] with
+ * w_fold[dy][co][dxi*8 + c] = packed[dy*3 + dxi][c][co] (dxi < 3), zero for dxi == 3 */
+int tcv_pack_weight_fold(const float* packed, int cout, void* w_fold, tcv_stream_t stream);
 
 /* scale = gamma / sqrt(var+eps), shift = beta - mean*scale (eval BatchNorm2d as an affine) */
 int tcv_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,

@@ -25,7 +25,8 @@ class ConvDesc(C.Structure):
     _fields_ = [
         ("x", c_void_p), ("x_plane", c_ll), ("x_img_stride", c_ll),
         ("n", c_int), ("ih", c_int), ("iw", c_int), ("cin", c_int),
-        ("w", c_void_p), ("w_tc", c_void_p), ("w_tc_taps", c_int), ("ntaps", c_int), ("dy", c_int * MAX_TAPS), ("dx", c_int * MAX_TAPS),
+        ("w", c_void_p), ("w_tc", c_void_p), ("w_tc_taps", c_int), ("w_tc_fold", c_void_p),
+        ("ntaps", c_int), ("dy", c_int * MAX_TAPS), ("dx", c_int * MAX_TAPS),
         ("wtap", c_int * MAX_TAPS),
         ("stride", c_int), ("pad_mode", c_int),
         ("y", c_void_p), ("y_f32", c_void_p),
@@ -64,6 +65,7 @@ SIGNATURES = {
     "tcv_gca_values": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "tcv_gca_softmax": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "tcv_pack_weight_tc": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_pack_weight_fold": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "tcv_gemm_tn_tc": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_ll, c_ll, c_int,
                                c_int, c_int, c_int, c_void_p]),
     "tcv_gca_fold": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

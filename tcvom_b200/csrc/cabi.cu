@@ -29,7 +29,9 @@ int conv2d_tc_supported(const tcv_conv_desc& d);
 int conv2d_tc(const tcv_conv_desc& d, cudaStream_t st);
 int conv2d_tc2_supported(const tcv_conv_desc& d);
 int conv2d_tc2(const tcv_conv_desc& d, cudaStream_t st);
-std::atomic<int> g_conv_tc_version{2};
+int conv2d_tc3_supported(const tcv_conv_desc& d);
+int conv2d_tc3(const tcv_conv_desc& d, cudaStream_t st);
+std::atomic<int> g_conv_tc_version{3};
 std::atomic<int> g_debug_flags{0};
 
 }  // namespace tcv
@@ -47,6 +49,7 @@ int tcv_conv2d_path(const tcv_conv_desc* dp) {
   tcv_conv_desc d = *dp;
   if (d.x_plane == 0) d.x_plane = (long long)d.n * d.ih * d.iw * d.cin;
   if (d.x_img_stride == 0) d.x_img_stride = (long long)d.ih * d.iw * d.cin;
+  if (g_conv_tc_version.load() >= 3 && conv2d_tc3_supported(d)) return 3;
   if (g_conv_tc_version.load() >= 2 && conv2d_tc2_supported(d)) return 2;
   return conv2d_tc_supported(d) ? 1 : 0;
 }
@@ -62,6 +65,8 @@ int tcv_conv2d(const tcv_conv_desc* dp, tcv_stream_t stream) {
   TCV_REQUIRE(dp, "conv2d: null descriptor");
   tcv_conv_desc d = *dp;
   TCV_REQUIRE(d.x && d.w && (d.y || d.y_f32), "conv2d: null tensor pointer");
+  if (d.x_plane == 0) d.x_plane = (long long)d.n * d.ih * d.iw * d.cin;
+  if (d.x_img_stride == 0) d.x_img_stride = (long long)d.ih * d.iw * d.cin;
   TCV_REQUIRE(d.n > 0 && d.ih > 0 && d.iw > 0 && d.oh > 0 && d.ow > 0 && d.gh > 0 && d.gw > 0, "conv2d: bad dims");
   TCV_REQUIRE(d.cin % 8 == 0 && (d.cin <= 32 || d.cin % 32 == 0), "conv2d: cin=%d must be 8,16,24,32 or a multiple of 32", d.cin);
   TCV_REQUIRE(d.cout >= 1, "conv2d: bad cout");
@@ -84,6 +89,7 @@ int tcv_conv2d(const tcv_conv_desc* dp, tcv_stream_t stream) {
   if (d.res1 && d.res1_plane == 0)
     d.res1_plane = (long long)d.n * (d.oh >> d.res1_shift) * (d.ow >> d.res1_shift) * d.cout;
   if (d.res2 && d.res2_plane == 0) d.res2_plane = (long long)d.n * d.oh * d.ow * d.cout;
+  if (g_conv_tc_version.load() >= 3 && conv2d_tc3_supported(d)) return conv2d_tc3(d, S(stream));
   if (g_conv_tc_version.load() >= 2 && conv2d_tc2_supported(d)) return conv2d_tc2(d, S(stream));
   if (conv2d_tc_supported(d)) return conv2d_tc(d, S(stream));
   return conv2d_direct(d, S(stream));

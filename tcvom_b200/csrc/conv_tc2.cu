@@ -17,7 +17,7 @@
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
 // warps 2..5 epilogue of accumulator 0, warps 6..9 epilogue of accumulator 1.
 // Precision: bf16x3 (Ahi.Bhi + Ahi.Blo + Alo.Bhi), fp32 accumulation in TMEM.
-#include "tc_common.cuh"
+#include "tc_epilogue.cuh"
 
 namespace tcv {
 
@@ -29,21 +29,14 @@ constexpr int V2_MAXDY = 3;  // taps per dx group
 constexpr int V2_A_SLOT_BYTES = 2 * 20480;  // hi + lo planes, up to 320 rows x 64 B each
 
 struct V2Params {
-  int gh, gw, TH, TW, tiles_x, tiles_y, n_tiles_n, n_imgs, total_work;
+  int gh, gw, TH, TW, tiles_x, tiles_y, n_tiles_n, total_work;
   int kc_iters;
   int ngroups, group_dx[V2_MAXG], ndy[V2_MAXG], dy[V2_MAXG][V2_MAXDY], wtap[V2_MAXG][V2_MAXDY];
   int dy_min, box_rows;
   int dbg;         // measurement switches (tcv_set_debug_flags): 1 no MMA, 2 no epilogue memory ops, 4 A loaded once, 8 B loaded once
   int b_resident;  // all weight tiles of a work item fit the B ring: load them once, never recycle
   uint32_t idesc;
-  // epilogue (same contract as tcv_conv_desc)
-  int oh, ow, cout, oy_mul, oy_off, ox_mul, ox_off;
-  __nv_bfloat16* y;
-  float* y_f32;
-  const float *s1, *b1, *s2, *b2;
-  const __nv_bfloat16 *res1, *res2;
-  long long res1_plane, res2_plane;
-  int res1_shift, act;
+  EpiParams epi;   // fused epilogue (same contract as tcv_conv_desc)
 };
 
 template <int BN>
@@ -179,8 +172,10 @@ __global__ void __launch_bounds__(320, 1) conv_tc2_kernel(const __grid_constant_
             const uint32_t a_hi = smem_base + sa * V2_A_SLOT_BYTES, a_lo = a_hi + a_plane_bytes;
             for (int j = 0; j < p.ndy[g]; ++j, ++ib, ++il) {
               const int sb = p.b_resident ? il : ib % SB;
-              mbar_wait(fullB(sb), p.b_resident ? 0u : ((uint32_t)(ib / SB) & 1u));
-              tc_fence_after();
+              if (!p.b_resident || iw == 0) {   // resident weights: only the first work item has to wait for them
+                mbar_wait(fullB(sb), p.b_resident ? 0u : ((uint32_t)(ib / SB) & 1u));
+                tc_fence_after();
+              }
               const uint32_t b_hi = b_base + sb * Cfg::B_SLOT_BYTES, b_lo = b_hi + Cfg::B_SLOT_BYTES / 2;
               if (elect_one()) {
                 // rows of accumulator i for vertical tap dy start (i*TH + dy - dy_min) image rows into the box
@@ -229,105 +224,8 @@ __global__ void __launch_bounds__(320, 1) conv_tc2_kernel(const __grid_constant_
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN + i * BN);
       const int ty = r / p.TW, tx = r - ty * p.TW;
       const int gy = h0 + i * p.TH + ty, gx = w0 + tx;
-      const bool valid = gy < p.gh && gx < p.gw && !(p.dbg & 2);
-      const int oy = gy * p.oy_mul + p.oy_off, ox = gx * p.ox_mul + p.ox_off;
-      const long long oplane = (long long)p.n_imgs * p.oh * p.ow * p.cout;
-      const long long obase = (((long long)img * p.oh + oy) * p.ow + ox) * p.cout + n0;
-      const int rh = p.oh >> p.res1_shift, rw = p.ow >> p.res1_shift;
-      const long long r1base = (((long long)img * rh + (oy >> p.res1_shift)) * rw + (ox >> p.res1_shift)) * p.cout + n0;
-      const bool has1 = valid && p.res1 != nullptr && !(p.dbg & 32), has2 = valid && p.res2 != nullptr && !(p.dbg & 32);
-
-      // Residual operands are fetched one 32-channel chunk AHEAD of the accumulator chunk that consumes
-      // them, and the first chunk is requested before this warp even waits for the MMAs to finish: the
-      // epilogue is latency-bound on these scattered 16-byte loads, not on bandwidth.
-      uint4 ra[2][8], rb[2][8];   // [double buffer][4 x hi, 4 x lo] for res1 / res2
-      auto fetch = [&](int c0, int slot) {
-        if (has1) {
-          const uint4* h = reinterpret_cast<const uint4*>(p.res1 + r1base + c0);
-          const uint4* l = reinterpret_cast<const uint4*>(p.res1 + r1base + c0 + p.res1_plane);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) { ra[slot][k] = __ldg(h + k); ra[slot][4 + k] = __ldg(l + k); }
-        }
-        if (has2) {
-          const uint4* h = reinterpret_cast<const uint4*>(p.res2 + obase + c0);
-          const uint4* l = reinterpret_cast<const uint4*>(p.res2 + obase + c0 + p.res2_plane);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) { rb[slot][k] = __ldg(h + k); rb[slot][4 + k] = __ldg(l + k); }
-        }
-      };
-      auto add_res = [&](const uint4* rr, float* f) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t hw[4] = {rr[k].x, rr[k].y, rr[k].z, rr[k].w};
-          const uint32_t lw[4] = {rr[4 + k].x, rr[4 + k].y, rr[4 + k].z, rr[4 + k].w};
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            f[8 * k + 2 * m] += __uint_as_float(hw[m] << 16) + __uint_as_float(lw[m] << 16);
-            f[8 * k + 2 * m + 1] += __uint_as_float(hw[m] & 0xffff0000u) + __uint_as_float(lw[m] & 0xffff0000u);
-          }
-        }
-      };
-      fetch(0, 0);
-      mbar_wait(accFull(buf), (uint32_t)(iw >> 1) & 1u);
-      tc_fence_after();
-#pragma unroll
-      for (int ci = 0; ci < BN / 32; ++ci) {
-        const int c0 = ci * 32;
-        const int slot = ci & 1;
-        uint32_t v[32];
-        tc_ld32(taddr + c0, v);
-        if (ci == BN / 32 - 1) {
-          // all TMEM reads of this warp are complete: hand the buffer back to the MMA warp early
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(accEmpty(buf));
-        } else {
-          fetch(c0 + 32, slot ^ 1);
-        }
-        if (!valid) continue;
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.s1) {
-          const float4* sv = reinterpret_cast<const float4*>(p.s1 + n0 + c0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 t = __ldg(sv + j);
-            f[4 * j] *= t.x; f[4 * j + 1] *= t.y; f[4 * j + 2] *= t.z; f[4 * j + 3] *= t.w;
-          }
-        }
-        if (p.b1) {
-          const float4* sv = reinterpret_cast<const float4*>(p.b1 + n0 + c0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 t = __ldg(sv + j);
-            f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
-          }
-        }
-        if (has1) add_res(ra[slot], f);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
-        if (p.s2) {
-          const float4* sv = reinterpret_cast<const float4*>(p.s2 + n0 + c0);
-          const float4* bv = reinterpret_cast<const float4*>(p.b2 + n0 + c0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 t = __ldg(sv + j), u = __ldg(bv + j);
-            f[4 * j] = f[4 * j] * t.x + u.x; f[4 * j + 1] = f[4 * j + 1] * t.y + u.y;
-            f[4 * j + 2] = f[4 * j + 2] * t.z + u.z; f[4 * j + 3] = f[4 * j + 3] * t.w + u.w;
-          }
-        }
-        if (has2) add_res(rb[slot], f);
-        if (p.y && !((p.dbg & 16) && f[0] != 12345.678f)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) store8(p.y + obase + c0 + j, oplane, f + j);
-        }
-        if (p.y_f32) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(p.y_f32 + obase + c0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-        }
-      }
+      conv_epilogue<BN>(p.epi, taddr, gy < p.gh && gx < p.gw, img, gy, gx, n0, accFull(buf), (uint32_t)(iw >> 1) & 1u,
+                        accEmpty(buf), lane);
     }
   }
   tc_fence_before();
@@ -398,20 +296,12 @@ static int conv_tc2_bn(const tcv_conv_desc& d, cudaStream_t st) {
   p.tiles_x = (d.gw + p.TW - 1) / p.TW;
   p.tiles_y = (d.gh + 2 * p.TH - 1) / (2 * p.TH);
   p.n_tiles_n = d.cout / BN;
-  p.n_imgs = d.n;
   p.total_work = p.tiles_x * p.tiles_y * p.n_tiles_n * d.n;
   p.kc_iters = d.cin / V2_BK;
   p.dbg = g_debug_flags.load();
   p.b_resident = (p.n_tiles_n == 1 && d.ntaps * p.kc_iters <= Cfg::B_SLOTS) ? 1 : 0;
   p.idesc = instr_desc(BN, false);
-  p.oh = d.oh; p.ow = d.ow; p.cout = d.cout;
-  p.oy_mul = d.oy_mul; p.oy_off = d.oy_off; p.ox_mul = d.ox_mul; p.ox_off = d.ox_off;
-  p.y = reinterpret_cast<__nv_bfloat16*>(d.y);
-  p.y_f32 = d.y_f32;
-  p.s1 = d.s1; p.b1 = d.b1; p.s2 = d.s2; p.b2 = d.b2;
-  p.res1 = reinterpret_cast<const __nv_bfloat16*>(d.res1);
-  p.res2 = reinterpret_cast<const __nv_bfloat16*>(d.res2);
-  p.res1_plane = d.res1_plane; p.res2_plane = d.res2_plane; p.res1_shift = d.res1_shift; p.act = d.act;
+  fill_epi(p.epi, d, p.dbg);
 
   CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
   const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(d.x);

@@ -1,0 +1,327 @@
+// tcgen05 convolution kernel for NARROW layers (Cin in {8, 32, 64}, Cout = 32) -- "v3".
+//
+// Narrow layers at full / half resolution have almost no tensor work (K <= 576); with the v2 kernel they
+// were bound by per-stage pipeline hand-shakes and by fetching the activation halo three times (once per
+// horizontal tap offset, because 64B-swizzled operand tiles can only be shifted by whole 512 B atoms).
+// This kernel stores the activation tile UN-swizzled in the canonical K-major "interleave" layout
+// (8-row x 16-byte core matrices): rows (pixels) are 16 B apart inside a core matrix, 8-row groups are SBO
+// apart, K-adjacent core matrices LBO apart -- so ANY 16-byte-aligned start address is a legal operand.
+//   * one TMA box {8 ch, TW+2 px, 2*TH+2 rows, 1, Cin/8 chunks} per work item and K chunk serves all 9 taps:
+//     tap (dy,dx) of accumulator i is the descriptor start ((i*TH+dy+1)*(TW+2) + dx+1)*16 B, SBO = one box
+//     row, LBO = one 8-channel chunk plane;
+//   * Cin = 8 (the network input: 3 image + 3 trimap + 2 pad channels): the K=16 MMA step spans TWO
+//     neighbouring pixels (LBO = 16 B), i.e. the horizontal taps are folded into K: per vertical tap dy the
+//     weights are packed as K = 32 = (dx=-1, 0, +1, zero) x 8 channels and two MMA steps cover them;
+//   * tile = 16 rows x 8 px per accumulator (a core matrix = 8 consecutive pixels of one image row), two
+//     accumulators stacked vertically, persistent CTAs, TMEM double buffering, weights resident in smem.
+// Weights keep the 64B-swizzled layout (A and B descriptors carry independent layout types).
+#include "tc_epilogue.cuh"
+
+namespace tcv {
+
+extern std::atomic<int> g_debug_flags;
+
+constexpr int V3_TH = 16, V3_TW = 8;
+constexpr int V3_MAXT = 9;
+
+struct V3Params {
+  int gh, gw, tiles_x, tiles_y, total_work;
+  int nchunk;          // Cin / 8 (1 for the folded Cin = 8 mode)
+  int fold;            // Cin == 8: horizontal taps folded into K
+  int kc_iters;        // K blocks of 32 per tap: nchunk / 4 (1 in fold mode)
+  int ntaps, dy[V3_MAXT], dx[V3_MAXT], wtap[V3_MAXT];
+  int dy_min, dx_min, box_w, box_rows;
+  int b_resident;
+  uint32_t idesc;
+  EpiParams epi;
+};
+
+template <int BN>
+struct V3Cfg {
+  static constexpr int B_SLOT_BYTES = 2 * BN * 32 * 2;       // hi + lo, one tap x one 32-wide K block
+  static constexpr int B_SLOTS = 18;                          // 9 taps x up to 2 K blocks stay resident (72 KB)
+  static constexpr int A_SLOT_BYTES = 45056;                  // hi + lo of one 10x34-pixel x 32-channel box
+  static constexpr int A_SLOTS = 3;
+  static constexpr int SMEM = A_SLOTS * A_SLOT_BYTES + B_SLOTS * B_SLOT_BYTES + 1024 + 512;
+  static constexpr int TMEM_COLS = 4 * BN;
+};
+
+// un-swizzled K-major descriptor: LBO = byte distance between K-adjacent core matrices, SBO = between
+// consecutive 8-row groups
+__device__ __forceinline__ uint64_t smem_desc_ns(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(320, 1) conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA_hi,
+                                                          const __grid_constant__ CUtensorMap mapA_lo,
+                                                          const __grid_constant__ CUtensorMap mapB_hi,
+                                                          const __grid_constant__ CUtensorMap mapB_lo,
+                                                          const __grid_constant__ V3Params p) {
+  using Cfg = V3Cfg<BN>;
+  constexpr int SA = Cfg::A_SLOTS, SB = Cfg::B_SLOTS;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_base = smem_base + SA * Cfg::A_SLOT_BYTES;
+  const uint32_t bar_base = b_base + SB * Cfg::B_SLOT_BYTES;
+  auto fullA = [&](int s) { return bar_base + 8u * s; };
+  auto emptyA = [&](int s) { return bar_base + 8u * (SA + s); };
+  auto fullB = [&](int s) { return bar_base + 8u * (2 * SA + s); };
+  auto emptyB = [&](int s) { return bar_base + 8u * (2 * SA + SB + s); };
+  auto accFull = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SB + a); };
+  auto accEmpty = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SB + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * SA + 2 * SB + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < SA; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(accFull(a), 1); mbar_init(accEmpty(a), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA_lo) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int box_px = p.box_w * p.box_rows;                  // pixels per chunk plane
+  const uint32_t chunk_bytes = (uint32_t)box_px * 16u;      // one 8-channel chunk plane of the box
+  const uint32_t a_plane_bytes = chunk_bytes * (uint32_t)(p.fold ? 1 : 4);   // one 32-channel K block (or the folded box)
+  const uint32_t a_lo_off = (a_plane_bytes + 127u) & ~127u;  // TMA destinations must be 128-byte aligned
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  auto decode = [&](int work, int& img, int& h0, int& w0) {
+    const int t = work % tiles_per_img;
+    img = work / tiles_per_img;
+    const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+    h0 = ty * 2 * V3_TH;
+    w0 = tx * V3_TW;
+  };
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    int ia = 0, ib = 0;
+    for (int work = blockIdx.x; work < p.total_work; work += gridDim.x) {
+      int img, h0, w0;
+      decode(work, img, h0, w0);
+      const bool load_b = !p.b_resident || work == (int)blockIdx.x;
+      for (int kc = 0; kc < p.kc_iters; ++kc, ++ia) {
+        const int sa = ia % SA;
+        mbar_wait(emptyA(sa), ((uint32_t)(ia / SA) & 1u) ^ 1u);
+        const uint32_t adst = smem_base + sa * Cfg::A_SLOT_BYTES;
+        if (elect_one()) {
+          mbar_expect_tx(fullA(sa), 2 * a_plane_bytes);
+          // box {8 ch, box_w px, box_rows, 1 img, 4 chunks (1 when folded)} at (0, w0+dx_min, h0+dy_min, img, 4*kc)
+          asm volatile(
+              "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+              ::"r"(adst), "l"(&mapA_hi), "r"(fullA(sa)), "r"(0), "r"(w0 + p.dx_min), "r"(h0 + p.dy_min), "r"(img),
+              "r"(4 * kc)
+              : "memory");
+          asm volatile(
+              "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+              ::"r"(adst + a_lo_off), "l"(&mapA_lo), "r"(fullA(sa)), "r"(0), "r"(w0 + p.dx_min),
+              "r"(h0 + p.dy_min), "r"(img), "r"(4 * kc)
+              : "memory");
+        }
+        __syncwarp();
+        if (!load_b) continue;
+        for (int t = 0; t < p.ntaps; ++t, ++ib) {
+          const int sb = ib % SB;
+          mbar_wait(emptyB(sb), ((uint32_t)(ib / SB) & 1u) ^ 1u);
+          const uint32_t bdst = b_base + sb * Cfg::B_SLOT_BYTES;
+          if (elect_one()) {
+            mbar_expect_tx(fullB(sb), Cfg::B_SLOT_BYTES);
+            tma_load_3d(bdst, &mapB_hi, fullB(sb), kc * 32, 0, p.wtap[t]);
+            tma_load_3d(bdst + Cfg::B_SLOT_BYTES / 2, &mapB_lo, fullB(sb), kc * 32, 0, p.wtap[t]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    int ia = 0, ib = 0, iw = 0;
+    const uint32_t row_bytes = (uint32_t)p.box_w * 16u;                       // SBO: next image row of the box
+    const uint32_t lbo = p.fold ? 16u : chunk_bytes;                          // K-adjacent core matrix
+    for (int work = blockIdx.x; work < p.total_work; work += gridDim.x, ++iw) {
+      const int buf = iw & 1;
+      mbar_wait(accEmpty(buf), ((uint32_t)(iw >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + (uint32_t)(buf * 2 * BN), d1 = d0 + (uint32_t)BN;
+      bool first = true;
+      int il = 0;
+      for (int kc = 0; kc < p.kc_iters; ++kc, ++ia) {
+        const int sa = ia % SA;
+        mbar_wait(fullA(sa), (uint32_t)(ia / SA) & 1u);
+        tc_fence_after();
+        const uint32_t a_hi = smem_base + sa * Cfg::A_SLOT_BYTES, a_lo = a_hi + a_lo_off;
+        for (int t = 0; t < p.ntaps; ++t, ++ib, ++il) {
+          const int sb = p.b_resident ? il : ib % SB;
+          if (!p.b_resident || iw == 0) {
+            mbar_wait(fullB(sb), p.b_resident ? 0u : ((uint32_t)(ib / SB) & 1u));
+            tc_fence_after();
+          }
+          const uint32_t b_hi = b_base + sb * Cfg::B_SLOT_BYTES, b_lo = b_hi + Cfg::B_SLOT_BYTES / 2;
+          if (elect_one()) {
+            // pixel offset of the tap inside the box (fold mode: dx is folded into K, start at the box's left edge)
+            const uint32_t px0 = (uint32_t)((p.dy[t] - p.dy_min) * p.box_w + (p.fold ? 0 : p.dx[t] - p.dx_min));
+            const uint32_t off0 = px0 * 16u, off1 = off0 + (uint32_t)(V3_TH * p.box_w) * 16u;
+#pragma unroll
+            for (int ks = 0; ks < ((p.epi.dbg & 1) ? 0 : 2); ++ks) {
+              // K step ks covers chunks 2ks, 2ks+1 (fold mode: pixels 2ks, 2ks+1 of the row)
+              const uint32_t kofs = p.fold ? (uint32_t)ks * 32u : (uint32_t)ks * 2u * chunk_bytes;
+              const uint64_t ah0 = smem_desc_ns(a_hi + off0 + kofs, lbo, row_bytes);
+              const uint64_t al0 = smem_desc_ns(a_lo + off0 + kofs, lbo, row_bytes);
+              const uint64_t ah1 = smem_desc_ns(a_hi + off1 + kofs, lbo, row_bytes);
+              const uint64_t al1 = smem_desc_ns(a_lo + off1 + kofs, lbo, row_bytes);
+              const uint64_t bh = smem_desc<32>(b_hi + ks * 32), bl = smem_desc<32>(b_lo + ks * 32);
+              const uint32_t acc = (first && ks == 0) ? 0u : 1u;
+              tc_mma(d0, ah0, bh, p.idesc, acc);
+              tc_mma(d1, ah1, bh, p.idesc, acc);
+              tc_mma(d0, ah0, bl, p.idesc, 1u);
+              tc_mma(d1, ah1, bl, p.idesc, 1u);
+              tc_mma(d0, al0, bh, p.idesc, 1u);
+              tc_mma(d1, al1, bh, p.idesc, 1u);
+            }
+            if (!p.b_resident) tc_commit(emptyB(sb));
+            if (t == p.ntaps - 1) {
+              tc_commit(emptyA(sa));
+              if (kc == p.kc_iters - 1) tc_commit(accFull(buf));
+            }
+          }
+          __syncwarp();
+          first = false;
+        }
+      }
+    }
+  } else {
+    // ================================ epilogue (warps 2..9) ================================
+    const int e = warp - 2;
+    const int i = e >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    int iw = 0;
+    for (int work = blockIdx.x; work < p.total_work; work += gridDim.x, ++iw) {
+      int img, h0, w0;
+      decode(work, img, h0, w0);
+      const int buf = iw & 1;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN + i * BN);
+      const int ty = r / V3_TW, tx = r - ty * V3_TW;
+      const int gy = h0 + i * V3_TH + ty, gx = w0 + tx;
+      conv_epilogue<BN>(p.epi, taddr, gy < p.gh && gx < p.gw, img, gy, gx, 0, accFull(buf), (uint32_t)(iw >> 1) & 1u,
+                        accEmpty(buf), lane);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+int conv2d_tc3_supported(const tcv_conv_desc& d) {
+  if (d.stride != 1 || d.pad_mode != TCV_PAD_ZERO) return 0;
+  if (d.cout != 32) return 0;
+  if (d.x_img_stride != (long long)d.ih * d.iw * d.cin) return 0;
+  if (d.ntaps > V3_MAXT) return 0;
+  for (int t = 0; t < d.ntaps; ++t)
+    if (d.dy[t] < -1 || d.dy[t] > 1 || d.dx[t] < -1 || d.dx[t] > 1) return 0;
+  if (d.cin == 8) {
+    if (!d.w_tc_fold || d.ntaps != 9) return 0;
+    for (int t = 0; t < 9; ++t)
+      if (d.dy[t] != t / 3 - 1 || d.dx[t] != t % 3 - 1 || d.wtap[t] != t) return 0;
+    return 1;
+  }
+  if (!d.w_tc) return 0;
+  return (d.cin == 32 || d.cin == 64) ? 1 : 0;
+}
+
+template <int BN>
+static int conv_tc3_bn(const tcv_conv_desc& d, cudaStream_t st) {
+  using Cfg = V3Cfg<BN>;
+  V3Params p;
+  memset(&p, 0, sizeof(p));
+  p.fold = d.cin == 8 ? 1 : 0;
+  p.nchunk = p.fold ? 1 : d.cin / 8;
+  p.kc_iters = p.fold ? 1 : d.cin / 32;
+  int dymin = 1, dymax = -1, dxmin = 1, dxmax = -1;
+  for (int t = 0; t < d.ntaps; ++t) {
+    dymin = d.dy[t] < dymin ? d.dy[t] : dymin; dymax = d.dy[t] > dymax ? d.dy[t] : dymax;
+    dxmin = d.dx[t] < dxmin ? d.dx[t] : dxmin; dxmax = d.dx[t] > dxmax ? d.dx[t] : dxmax;
+  }
+  if (p.fold) {
+    // one MMA row of K=32 per vertical tap: (dx=-1, 0, +1, zero-weight pixel) x 8 channels
+    p.ntaps = 3;
+    for (int t = 0; t < 3; ++t) { p.dy[t] = t - 1; p.dx[t] = -1; p.wtap[t] = t; }
+    dymin = -1; dymax = 1; dxmin = -1; dxmax = 2;
+  } else {
+    p.ntaps = d.ntaps;
+    for (int t = 0; t < d.ntaps; ++t) { p.dy[t] = d.dy[t]; p.dx[t] = d.dx[t]; p.wtap[t] = d.wtap[t]; }
+  }
+  p.dy_min = dymin; p.dx_min = dxmin;
+  p.box_w = V3_TW + (dxmax - dxmin);
+  p.box_rows = 2 * V3_TH + (dymax - dymin);
+  const int plane_bytes = p.box_w * p.box_rows * 16 * (p.fold ? 1 : 4);
+  if (((plane_bytes + 127) & ~127) + plane_bytes > Cfg::A_SLOT_BYTES) return fail(TCV_ERR_UNSUPPORTED, "conv_tc3: activation box too large");
+  p.gh = d.gh; p.gw = d.gw;
+  p.tiles_x = (d.gw + V3_TW - 1) / V3_TW;
+  p.tiles_y = (d.gh + 2 * V3_TH - 1) / (2 * V3_TH);
+  p.total_work = p.tiles_x * p.tiles_y * d.n;
+  p.b_resident = p.ntaps * p.kc_iters <= Cfg::B_SLOTS ? 1 : 0;
+  p.idesc = instr_desc(BN, false);
+  fill_epi(p.epi, d, g_debug_flags.load());
+
+  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+  const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(d.x);
+  {
+    // 5-D view of the NHWC tensor: {8 ch, W, H, N, Cin/8 chunks}; chunk stride 16 B
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return fail(TCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[5] = {8, (cuuint64_t)d.iw, (cuuint64_t)d.ih, (cuuint64_t)d.n, (cuuint64_t)(d.cin / 8)};
+    cuuint64_t str[4] = {(cuuint64_t)d.cin * 2, (cuuint64_t)d.iw * d.cin * 2, (cuuint64_t)d.x_img_stride * 2, 16};
+    cuuint32_t box[5] = {8, (cuuint32_t)p.box_w, (cuuint32_t)p.box_rows, 1, (cuuint32_t)(p.fold ? 1 : 4)};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    for (int pl = 0; pl < 2; ++pl) {
+      CUresult r = enc(pl ? &mA_lo : &mA_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
+                       const_cast<__nv_bfloat16*>(a + (pl ? d.x_plane : 0)), dims, str, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(TCV_ERR_CUDA, "conv_tc3: cuTensorMapEncodeTiled (activation view) failed (%d)", (int)r);
+    }
+  }
+  {
+    const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(p.fold ? d.w_tc_fold : d.w_tc);
+    const int kdim = p.fold ? 32 : d.cin, wt = p.fold ? 3 : d.w_tc_taps;
+    cuuint64_t dims[3] = {(cuuint64_t)kdim, (cuuint64_t)d.cout, (cuuint64_t)wt};
+    cuuint64_t str[2] = {(cuuint64_t)kdim * 2, (cuuint64_t)d.cout * kdim * 2};
+    cuuint32_t box[3] = {32, (cuuint32_t)BN, 1};
+    int rc = make_map(&mB_hi, b, 3, dims, str, box, 32);
+    if (rc) return rc;
+    rc = make_map(&mB_lo, b + (long long)wt * d.cout * kdim, 3, dims, str, box, 32);
+    if (rc) return rc;
+  }
+  auto kern = conv_tc3_kernel<BN>;
+  TCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  int dev = 0, sms = 0;
+  TCV_CUDA(cudaGetDevice(&dev));
+  TCV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = p.total_work < sms ? p.total_work : sms;
+  kern<<<grid, 320, Cfg::SMEM, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, p);
+  return launched("conv_tc3_kernel");
+}
+
+int conv2d_tc3(const tcv_conv_desc& d, cudaStream_t st) { return conv_tc3_bn<32>(d, st); }
+
+}  // namespace tcv

@@ -177,6 +177,16 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ packed, int taps
   store1(wtc + i, total, packed[((long long)t * cin + ci) * cout + co]);
 }
 
+__global__ void pack_weight_fold_kernel(const float* __restrict__ packed, int cout, __nv_bfloat16* __restrict__ wf) {
+  const int total = 3 * cout * 32;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int k = i % 32, co = (i / 32) % cout, dy = i / (32 * cout);
+  const int dxi = k / 8, c = k % 8;
+  const float v = dxi < 3 ? packed[((long long)(dy * 3 + dxi) * 8 + c) * cout + co] : 0.f;
+  store1(wf + i, total, v);
+}
+
 __global__ void bn_fold_kernel(const float* g, const float* b, const float* m, const float* v, float eps, int c,
                                float* scale, float* shift) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -293,6 +303,13 @@ int tcv_pack_weight_tc(const float* packed, int taps, int cin, int cout, void* w
   pack_weight_tc_kernel<<<blocks(total), 256, 0, S(stream)>>>(packed, taps, cin, cout,
                                                               reinterpret_cast<__nv_bfloat16*>(w_tc));
   return launched("pack_weight_tc_kernel");
+}
+
+int tcv_pack_weight_fold(const float* packed, int cout, void* w_fold, tcv_stream_t stream) {
+  TCV_REQUIRE(packed && w_fold && cout > 0, "pack_weight_fold: bad arguments");
+  pack_weight_fold_kernel<<<blocks(3 * cout * 32), 256, 0, S(stream)>>>(packed, cout,
+                                                                        reinterpret_cast<__nv_bfloat16*>(w_fold));
+  return launched("pack_weight_fold_kernel");
 }
 
 int tcv_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps, int c,

@@ -1,0 +1,139 @@
+// Fused convolution epilogue shared by the persistent tcgen05 conv kernels: TMEM accumulator ->
+// per-channel affine (BatchNorm / bias) -> residual -> activation -> affine -> residual -> split-bf16 NHWC
+// (and/or fp32) store.  One warp handles 32 accumulator rows (= 32 output pixels) x BN channels.
+#pragma once
+#include "tc_common.cuh"
+
+namespace tcv {
+
+struct EpiParams {
+  int n_imgs, oh, ow, cout, oy_mul, oy_off, ox_mul, ox_off;
+  __nv_bfloat16* y;
+  float* y_f32;
+  const float *s1, *b1, *s2, *b2;
+  const __nv_bfloat16 *res1, *res2;
+  long long res1_plane, res2_plane;
+  int res1_shift, act;
+  int dbg;
+};
+
+static inline void fill_epi(EpiParams& e, const tcv_conv_desc& d, int dbg) {
+  e.n_imgs = d.n; e.oh = d.oh; e.ow = d.ow; e.cout = d.cout;
+  e.oy_mul = d.oy_mul; e.oy_off = d.oy_off; e.ox_mul = d.ox_mul; e.ox_off = d.ox_off;
+  e.y = reinterpret_cast<__nv_bfloat16*>(d.y);
+  e.y_f32 = d.y_f32;
+  e.s1 = d.s1; e.b1 = d.b1; e.s2 = d.s2; e.b2 = d.b2;
+  e.res1 = reinterpret_cast<const __nv_bfloat16*>(d.res1);
+  e.res2 = reinterpret_cast<const __nv_bfloat16*>(d.res2);
+  e.res1_plane = d.res1_plane; e.res2_plane = d.res2_plane; e.res1_shift = d.res1_shift; e.act = d.act;
+  e.dbg = dbg;
+}
+
+// gy/gx: position of this thread's pixel in the compute grid; in_grid: inside it.  The warp waits on
+// `acc_full` (parity given), drains its 32 TMEM lanes starting at `taddr`, and arrives on `acc_empty` as soon
+// as its last tcgen05.ld has completed.
+template <int BN>
+__device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr, bool in_grid, int img, int gy, int gx,
+                                              int n0, uint32_t acc_full, uint32_t full_parity, uint32_t acc_empty,
+                                              int lane) {
+  const bool valid = in_grid && !(p.dbg & 2);
+  const int oy = gy * p.oy_mul + p.oy_off, ox = gx * p.ox_mul + p.ox_off;
+  const long long oplane = (long long)p.n_imgs * p.oh * p.ow * p.cout;
+  const long long obase = (((long long)img * p.oh + oy) * p.ow + ox) * p.cout + n0;
+  const int rh = p.oh >> p.res1_shift, rw = p.ow >> p.res1_shift;
+  const long long r1base = (((long long)img * rh + (oy >> p.res1_shift)) * rw + (ox >> p.res1_shift)) * p.cout + n0;
+  const bool has1 = valid && p.res1 != nullptr && !(p.dbg & 32), has2 = valid && p.res2 != nullptr && !(p.dbg & 32);
+
+  // Residual operands are fetched one 32-channel chunk AHEAD of the accumulator chunk that consumes them,
+  // and the first chunk is requested before this warp waits for the MMAs to finish.
+  uint4 ra[2][8], rb[2][8];   // [double buffer][4 x hi, 4 x lo] for res1 / res2
+  auto fetch = [&](int c0, int slot) {
+    if (has1) {
+      const uint4* h = reinterpret_cast<const uint4*>(p.res1 + r1base + c0);
+      const uint4* l = reinterpret_cast<const uint4*>(p.res1 + r1base + c0 + p.res1_plane);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { ra[slot][k] = __ldg(h + k); ra[slot][4 + k] = __ldg(l + k); }
+    }
+    if (has2) {
+      const uint4* h = reinterpret_cast<const uint4*>(p.res2 + obase + c0);
+      const uint4* l = reinterpret_cast<const uint4*>(p.res2 + obase + c0 + p.res2_plane);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { rb[slot][k] = __ldg(h + k); rb[slot][4 + k] = __ldg(l + k); }
+    }
+  };
+  auto add_res = [&](const uint4* rr, float* f) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t hw[4] = {rr[k].x, rr[k].y, rr[k].z, rr[k].w};
+      const uint32_t lw[4] = {rr[4 + k].x, rr[4 + k].y, rr[4 + k].z, rr[4 + k].w};
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        f[8 * k + 2 * m] += __uint_as_float(hw[m] << 16) + __uint_as_float(lw[m] << 16);
+        f[8 * k + 2 * m + 1] += __uint_as_float(hw[m] & 0xffff0000u) + __uint_as_float(lw[m] & 0xffff0000u);
+      }
+    }
+  };
+  fetch(0, 0);
+  mbar_wait(acc_full, full_parity);
+  tc_fence_after();
+#pragma unroll
+  for (int ci = 0; ci < BN / 32; ++ci) {
+    const int c0 = ci * 32;
+    const int slot = ci & 1;
+    uint32_t v[32];
+    tc_ld32(taddr + c0, v);
+    if (ci == BN / 32 - 1) {
+      // all TMEM reads of this warp are complete: hand the buffer back to the MMA warp early
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+    } else {
+      fetch(c0 + 32, slot ^ 1);
+    }
+    if (!valid) continue;
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    if (p.s1) {
+      const float4* sv = reinterpret_cast<const float4*>(p.s1 + n0 + c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = __ldg(sv + j);
+        f[4 * j] *= t.x; f[4 * j + 1] *= t.y; f[4 * j + 2] *= t.z; f[4 * j + 3] *= t.w;
+      }
+    }
+    if (p.b1) {
+      const float4* sv = reinterpret_cast<const float4*>(p.b1 + n0 + c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = __ldg(sv + j);
+        f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+      }
+    }
+    if (has1) add_res(ra[slot], f);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+    if (p.s2) {
+      const float4* sv = reinterpret_cast<const float4*>(p.s2 + n0 + c0);
+      const float4* bv = reinterpret_cast<const float4*>(p.b2 + n0 + c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = __ldg(sv + j), u = __ldg(bv + j);
+        f[4 * j] = f[4 * j] * t.x + u.x; f[4 * j + 1] = f[4 * j + 1] * t.y + u.y;
+        f[4 * j + 2] = f[4 * j + 2] * t.z + u.z; f[4 * j + 3] = f[4 * j + 3] * t.w + u.w;
+      }
+    }
+    if (has2) add_res(rb[slot], f);
+    if (p.y && !((p.dbg & 16) && f[0] != 12345.678f)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) store8(p.y + obase + c0 + j, oplane, f + j);
+    }
+    if (p.y_f32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(p.y_f32 + obase + c0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+    }
+  }
+}
+
+}  // namespace tcv

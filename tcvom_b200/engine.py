@@ -188,6 +188,11 @@ class GcaVmnEngine:
                                        v.data_ptr() if v is not None else None, cout, cin, kh, kw,
                                        1 if transposed else 0, cin_pad, ent["w"].data_ptr(),
                                        sig.data_ptr() if sig is not None else None, st), "sn_fold_pack")
+        if cin_pad == 8 and kh == 3 and cout % 32 == 0 and not transposed:
+            if "w_tc_fold" not in ent:
+                ent["w_tc_fold"] = torch.empty((2, 3, cout, 32), dtype=torch.bfloat16, device=wbar.device)
+            _cabi.check(L.tcv_pack_weight_fold(ent["w"].data_ptr(), cout, ent["w_tc_fold"].data_ptr(), st),
+                        "pack_weight_fold")
         if cin_pad % 32 == 0 and cout % 32 == 0:
             if "w_tc" not in ent:
                 ent["w_tc"] = torch.empty((2, kh * kw, cout, cin_pad), dtype=torch.bfloat16, device=wbar.device)
@@ -273,7 +278,7 @@ class GcaVmnEngine:
             nbytes += 4 * (px >> (2 * d.res1_shift)) * d.cout
         if d.res2:
             nbytes += 4 * px * d.cout
-        path = {0: "direct", 1: "tc", 2: "tc2"}[_cabi.lib().tcv_conv2d_path(C.byref(d))]
+        path = {0: "direct", 1: "tc", 2: "tc2", 3: "tc3"}[_cabi.lib().tcv_conv2d_path(C.byref(d))]
         return dict(kind=f"conv_{path}", layer=wkey, flops=flops, bytes=nbytes,
                     shape=f"{d.cin}->{d.cout} k{k} s{stride} @{d.gh}x{d.gw} n{d.n}")
 
@@ -286,6 +291,8 @@ class GcaVmnEngine:
         ent = self.w[wkey]
         if self.use_tc_conv and "w_tc" in ent:
             d.w_tc, d.w_tc_taps = ent["w_tc"].data_ptr(), ent["k"] * ent["k"]
+        if self.use_tc_conv and "w_tc_fold" in ent:
+            d.w_tc_fold = ent["w_tc_fold"].data_ptr()
         for i, (dy, dx) in enumerate(taps):
             d.dy[i], d.dx[i] = dy, dx
             d.wtap[i] = wtap[i] if wtap is not None else i

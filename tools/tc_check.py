@@ -83,6 +83,10 @@ def case_conv(cin, cout, h, w, n, kind):
     wf = (torch.randn(ntw, cin, cout, device=dev) / (cin * len(taps)) ** 0.5).contiguous()
     wtc = torch.empty((2, ntw, cout, cin), dtype=torch.bfloat16, device=dev)
     _cabi.check(L.tcv_pack_weight_tc(wf.data_ptr(), ntw, cin, cout, wtc.data_ptr(), st), "pack")
+    wfold = None
+    if cin == 8 and kind == "3x3":
+        wfold = torch.empty((2, 3, cout, 32), dtype=torch.bfloat16, device=dev)
+        _cabi.check(L.tcv_pack_weight_fold(wf.data_ptr(), cout, wfold.data_ptr(), st), "pack_fold")
     s1 = torch.rand(cout, device=dev) + 0.5; b1 = torch.randn(cout, device=dev)
     s2 = torch.rand(cout, device=dev) + 0.5; b2 = torch.randn(cout, device=dev)
     res1 = split(torch.randn(n, oh // 2, ow // 2, cout, device=dev))
@@ -95,7 +99,10 @@ def case_conv(cin, cout, h, w, n, kind):
         d.x = x.data_ptr(); d.n, d.ih, d.iw, d.cin = n, h, w, cin
         d.w = wf.data_ptr(); d.ntaps = len(taps)
         if use_tc:
-            d.w_tc = wtc.data_ptr(); d.w_tc_taps = ntw
+            if cin % 32 == 0:
+                d.w_tc = wtc.data_ptr(); d.w_tc_taps = ntw
+            if wfold is not None:
+                d.w_tc_fold = wfold.data_ptr()
         for i, (dy, dx) in enumerate(taps):
             d.dy[i], d.dx[i], d.wtap[i] = dy, dx, wt[i]
         d.stride, d.pad_mode = (2 if kind == "3x3s2" else 1), 0
@@ -134,6 +141,10 @@ CASES = {
     "conv3x3_512_512": lambda: case_conv(512, 512, 34, 60, 3, "3x3"),
     "conv3x3s2_64_128": lambda: case_conv(64, 128, 40, 56, 2, "3x3s2"),
     "conv3x3s2_32_64": lambda: case_conv(32, 64, 36, 52, 1, "3x3s2"),
+    "conv3x3_8_32_fold": lambda: case_conv(8, 32, 40, 56, 2, "3x3"),
+    "conv3x3_64_32": lambda: case_conv(64, 32, 36, 44, 2, "3x3"),
+    "deconv_32_32": lambda: case_conv(32, 32, 18, 20, 1, "deconv"),
+    "conv1x1_64_32": lambda: case_conv(64, 32, 20, 24, 1, "1x1"),
     "conv1x1_128_64": lambda: case_conv(128, 64, 16, 16, 2, "1x1"),
     "deconv_64_64": lambda: case_conv(64, 64, 9, 14, 2, "deconv"),
 }
