@@ -181,6 +181,10 @@ def run_native(args, rank, world, local_rank):
     imgs_np, tris_np = synthetic.make_window(H, W, seed=7 + rank)
     imgs_h = torch.from_numpy(imgs_np).float().pin_memory()
     tris_h = torch.from_numpy(tris_np).float().pin_memory()
+    # end-to-end arm: frames and trimaps cross PCIe as uint8 (what cv2.imread yields, pred_test.py:74-76); the
+    # reference API accepts them (EvalModel.preprocess casts with .float(), models/model.py:366-368)
+    imgs_u8 = torch.from_numpy(imgs_np).pin_memory()
+    tris_u8 = torch.from_numpy(tris_np).pin_memory()
     out_h = torch.empty((1, S, 1, H, W), dtype=torch.float32).pin_memory()
 
     from tcvom_b200 import dp
@@ -220,7 +224,7 @@ def run_native(args, rank, world, local_rank):
 
         # ---- e2e: the user-facing call with HOST buffers (pred_test.py:100-107 sequence)
         def e2e_step():
-            a = model(imgs_h.to(dev, non_blocking=True), tris_h.to(dev, non_blocking=True))
+            a = model(imgs_u8.to(dev, non_blocking=True), tris_u8.to(dev, non_blocking=True))
             out_h.copy_(a, non_blocking=True)
         for _ in range(3):
             e2e_step()
@@ -299,7 +303,7 @@ def run_native(args, rank, world, local_rank):
                             parallelism=f"dp{world} (independent windows per GPU, no collective)"),
                 clocks=clocks,
                 e2e=dict(value=e2e_value, unit=UNIT, ms_per_step=ms_e2e / args.steps,
-                         h2d_bytes_per_step=imgs_h.numel() * 4 + tris_h.numel() * 4,
+                         h2d_bytes_per_step=imgs_u8.numel() + tris_u8.numel(), input_dtype="uint8",
                          d2h_bytes_per_step=out_h.numel() * 4),
                 gpu_launches=launches, roofline=roof, cpu_baseline=cpu)
     print(json.dumps(line), flush=True)

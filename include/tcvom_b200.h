@@ -134,6 +134,11 @@ int tcv_bn_fold(const float* gamma, const float* beta, const float* mean, const 
 int tcv_preprocess_eval(const float* imgs, const float* tris, int frames, int h, int w, int dilate,
                         void* x8, float* trimask, uint8_t* tmp, tcv_stream_t stream);
 
+/* same, for uint8 frames / trimaps (the reference casts with .float(), models/model.py:366,368; moving
+ * uint8 over PCIe is 4x cheaper) */
+int tcv_preprocess_eval_u8(const uint8_t* imgs, const uint8_t* tris, int frames, int h, int w, int dilate,
+                           void* x8, float* trimask, uint8_t* tmp, tcv_stream_t stream);
+
 /* alpha[f] = trimask ? pred : tri/255 for inner frames, 0 for the first/last frame of each
  * sample.  pred fp32 [B,H,W] (centre frames only when S==3: index b*(S-2)+(s-1)). */
 int tcv_postprocess_eval(const float* pred, const float* tris, const float* trimask, int batch,
@@ -157,6 +162,9 @@ int tcv_losses_vmd(const float* pred, const float* trimask, const float* gts, co
                    const float* attb, const float* attf, const uint8_t* small_mask, int batch, int frames_per_sample,
                    int h, int w, int window, float att_thres, float label_smooth, float att_multiplier,
                    float* alphas, float* comps, float* gt8, double* acc, float* losses, tcv_stream_t stream);
+
+int tcv_postprocess_eval_u8(const float* pred, const uint8_t* tris, const float* trimask, int batch,
+                            int frames, int h, int w, float* alphas, tcv_stream_t stream);
 
 int tcv_avgpool2(const void* x, int n, int h, int w, int c, void* y, tcv_stream_t stream);
 

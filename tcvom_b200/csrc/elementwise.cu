@@ -7,10 +7,11 @@ namespace tcv {
 // ---------------------------------------------------------------------------------------------
 // EvalModel.preprocess (models/model.py:360-387, TRIMAP_CHANNEL==3 branch)
 // ---------------------------------------------------------------------------------------------
-__global__ void trimask_raw_kernel(const float* __restrict__ tris, long long total, uint8_t* __restrict__ m) {
+template <typename T>
+__global__ void trimask_raw_kernel(const T* __restrict__ tris, long long total, uint8_t* __restrict__ m) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const float st = tris[i] * (1.0f / 255);
+  const float st = (float)tris[i] * (1.0f / 255);
   m[i] = (st > 0.f) & (st < 1.f);
 }
 
@@ -39,7 +40,8 @@ __global__ void dilate_col_kernel(const uint8_t* __restrict__ in, int frames, in
   out[i] = v;
 }
 
-__global__ void preprocess_kernel(const float* __restrict__ imgs, const float* __restrict__ tris,
+template <typename T>
+__global__ void preprocess_kernel(const T* __restrict__ imgs, const T* __restrict__ tris,
                                   const uint8_t* __restrict__ mask, int frames, int h, int w,
                                   __nv_bfloat16* __restrict__ x8, float* __restrict__ trimask) {
   const long long hw = (long long)h * w;
@@ -52,10 +54,10 @@ __global__ void preprocess_kernel(const float* __restrict__ imgs, const float* _
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     // flip([2]) : output channel c (RGB) <- input channel 2-c (BGR)
-    const float s = imgs[(f * 3 + (2 - c)) * hw + p] * (1.0f / 255);
+    const float s = (float)imgs[(f * 3 + (2 - c)) * hw + p] * (1.0f / 255);
     v[c] = (s - mean[c]) / stdv[c];
   }
-  const float st = tris[i] * (1.0f / 255);
+  const float st = (float)tris[i] * (1.0f / 255);
   const bool m = mask[i] != 0;
   const int cls = m ? 1 : (int)(2.0f * st);  // .long() truncation (model.py:379)
   v[3] = cls == 0 ? 1.f : 0.f;
@@ -67,7 +69,8 @@ __global__ void preprocess_kernel(const float* __restrict__ imgs, const float* _
   trimask[i] = m ? 1.f : 0.f;
 }
 
-__global__ void postprocess_kernel(const float* __restrict__ pred, const float* __restrict__ tris,
+template <typename T>
+__global__ void postprocess_kernel(const float* __restrict__ pred, const T* __restrict__ tris,
                                    const float* __restrict__ trimask, int batch, int frames, int h, int w,
                                    float* __restrict__ alphas) {
   const long long hw = (long long)h * w;
@@ -78,7 +81,7 @@ __global__ void postprocess_kernel(const float* __restrict__ pred, const float* 
   float a = 0.f;
   if (s > 0 && s < frames - 1) {
     const float pr = pred[((long long)b * (frames - 2) + (s - 1)) * hw + p];
-    a = trimask[i] != 0.f ? pr : tris[i] * (1.0f / 255);
+    a = trimask[i] != 0.f ? pr : (float)tris[i] * (1.0f / 255);
   }
   alphas[i] = a;
 }
@@ -229,15 +232,18 @@ using namespace tcv;
 
 extern "C" {
 
-int tcv_preprocess_eval(const float* imgs, const float* tris, int frames, int h, int w, int dilate, void* x8,
-                        float* trimask, uint8_t* tmp, tcv_stream_t stream) {
+}  // extern "C"
+
+template <typename T>
+static int preprocess_eval_t(const T* imgs, const T* tris, int frames, int h, int w, int dilate, void* x8,
+                             float* trimask, uint8_t* tmp, tcv_stream_t stream) {
   TCV_REQUIRE(imgs && tris && x8 && trimask && tmp, "preprocess_eval: null pointer");
   TCV_REQUIRE(frames > 0 && h > 0 && w > 0, "preprocess_eval: bad dims");
   const long long total = (long long)frames * h * w;
   // tmp holds two byte planes: [0,total) mask, [total, 2*total) scratch for the separable dilation
   uint8_t* m0 = tmp;
   uint8_t* m1 = tmp + total;
-  trimask_raw_kernel<<<blocks(total), 256, 0, S(stream)>>>(tris, total, m0);
+  trimask_raw_kernel<T><<<blocks(total), 256, 0, S(stream)>>>(tris, total, m0);
   int rc = launched("trimask_raw_kernel");
   if (rc) return rc;
   if (dilate > 0) {
@@ -246,9 +252,21 @@ int tcv_preprocess_eval(const float* imgs, const float* tris, int frames, int h,
     dilate_col_kernel<<<blocks(total), 256, 0, S(stream)>>>(m1, frames, h, w, dilate, m0);
     if ((rc = launched("dilate_col_kernel"))) return rc;
   }
-  preprocess_kernel<<<blocks(total), 256, 0, S(stream)>>>(imgs, tris, m0, frames, h, w,
-                                                          reinterpret_cast<__nv_bfloat16*>(x8), trimask);
+  preprocess_kernel<T><<<blocks(total), 256, 0, S(stream)>>>(imgs, tris, m0, frames, h, w,
+                                                             reinterpret_cast<__nv_bfloat16*>(x8), trimask);
   return launched("preprocess_kernel");
+}
+
+extern "C" {
+
+int tcv_preprocess_eval(const float* imgs, const float* tris, int frames, int h, int w, int dilate, void* x8,
+                        float* trimask, uint8_t* tmp, tcv_stream_t stream) {
+  return preprocess_eval_t<float>(imgs, tris, frames, h, w, dilate, x8, trimask, tmp, stream);
+}
+
+int tcv_preprocess_eval_u8(const uint8_t* imgs, const uint8_t* tris, int frames, int h, int w, int dilate, void* x8,
+                           float* trimask, uint8_t* tmp, tcv_stream_t stream) {
+  return preprocess_eval_t<uint8_t>(imgs, tris, frames, h, w, dilate, x8, trimask, tmp, stream);
 }
 
 int tcv_postprocess_eval(const float* pred, const float* tris, const float* trimask, int batch, int frames,
@@ -256,7 +274,16 @@ int tcv_postprocess_eval(const float* pred, const float* tris, const float* trim
   TCV_REQUIRE(pred && tris && trimask && alphas, "postprocess_eval: null pointer");
   TCV_REQUIRE(frames >= 3, "postprocess_eval: need at least 3 frames");
   const long long total = (long long)batch * frames * h * w;
-  postprocess_kernel<<<blocks(total), 256, 0, S(stream)>>>(pred, tris, trimask, batch, frames, h, w, alphas);
+  postprocess_kernel<float><<<blocks(total), 256, 0, S(stream)>>>(pred, tris, trimask, batch, frames, h, w, alphas);
+  return launched("postprocess_kernel");
+}
+
+int tcv_postprocess_eval_u8(const float* pred, const uint8_t* tris, const float* trimask, int batch, int frames,
+                            int h, int w, float* alphas, tcv_stream_t stream) {
+  TCV_REQUIRE(pred && tris && trimask && alphas, "postprocess_eval_u8: null pointer");
+  TCV_REQUIRE(frames >= 3, "postprocess_eval_u8: need at least 3 frames");
+  const long long total = (long long)batch * frames * h * w;
+  postprocess_kernel<uint8_t><<<blocks(total), 256, 0, S(stream)>>>(pred, tris, trimask, batch, frames, h, w, alphas);
   return launched("postprocess_kernel");
 }
 

@@ -2,12 +2,12 @@
 //   * the 3x3 / 1x1 / (4 phases of the) 4x4-stride-2-transposed convolutions  (EPI_CONV)
 //   * the two guided-contextual-attention GEMMs  scores = Q.Kn^T, O = P.Vt^T  (EPI_F32 / EPI_BF16)
 //
-// Structure (one 128 x BN output tile per CTA, 192 threads):
+// Structure (one 128 x BN output tile per CTA, 320 threads):
 //   warp 0      TMA producer   cp.async.bulk.tensor (4-D NHWC activation boxes, 3-D weight boxes)
 //                              -> 64B/128B-swizzled K-major shared-memory tiles, mbarrier ring
 //   warp 1      MMA issuer     one elected thread issues tcgen05.mma (M=128, N=BN, K=16, bf16 ->
 //                              fp32 accumulators in TMEM); tcgen05.commit frees smem stages
-//   warps 2..5  epilogue       tcgen05.ld (32 lanes x 32 columns per warp) -> fused affine /
+//   warps 2..9  epilogue       tcgen05.ld (32 lanes x 32 columns per warp) -> fused affine /
 //                              residual / activation -> split-bf16 NHWC (or fp32 / bf16 GEMM output)
 //
 // Precision ("bf16x3"): activations and weights are stored as bf16 hi/lo pairs; with NSPLIT==3 each
@@ -59,7 +59,7 @@ struct TcCfg {
 };
 
 template <int BN, int BK, int NSPLIT, int EPI>
-__global__ void __launch_bounds__(192) igemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi,
+__global__ void __launch_bounds__(320) igemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi,
                                                        const __grid_constant__ CUtensorMap mapA_lo,
                                                        const __grid_constant__ CUtensorMap mapA_p2,
                                                        const __grid_constant__ CUtensorMap mapB_hi,
@@ -174,9 +174,14 @@ __global__ void __launch_bounds__(192) igemm_tc_kernel(const __grid_constant__ C
       }
     }
   } else {
-    // ================================ epilogue (warps 2..5) ================================
+    // ================================ epilogue (warps 2..9) ================================
+    // two warps per TMEM lane quarter, each draining half of the accumulator columns (the GEMM epilogues
+    // write 64 KB of fp32 per tile; with four warps the epilogue, not the MMA, bounded the scores GEMM)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;            // accumulator row = tile pixel
+    constexpr int CHALF = BN / 2 >= 32 ? BN / 2 : 32;
+    const int c_begin = ((warp - 2) >> 2) * CHALF;
+    const int c_end = c_begin + CHALF < BN ? c_begin + CHALF : BN;
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
@@ -190,7 +195,7 @@ __global__ void __launch_bounds__(192) igemm_tc_kernel(const __grid_constant__ C
       const int rh = p.oh >> p.res1_shift, rw = p.ow >> p.res1_shift;
       const long long r1base = (((long long)img * rh + (oy >> p.res1_shift)) * rw + (ox >> p.res1_shift)) * p.cout + n0;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         uint32_t v[32];
         tc_ld32(taddr + c0, v);
         if (!valid) continue;
@@ -243,7 +248,7 @@ __global__ void __launch_bounds__(192) igemm_tc_kernel(const __grid_constant__ C
       const int m = w0 + r;  // GEMM mode: TH == 1, tile rows are consecutive M indices
       const bool valid = m < p.M;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         uint32_t v[32];
         tc_ld32(taddr + c0, v);
         if (!valid) continue;
@@ -334,7 +339,7 @@ static int launch_tc(const TcOperands& o, TcParams& p, cudaStream_t st) {
   const int nrows = EPI == EPI_CONV ? p.cout : p.N;
   dim3 grid(p.tiles_x * tiles_y, (nrows + BN - 1) / BN, o.n);
   if (p.b_batched) grid = dim3((nrows + BN - 1) / BN, p.tiles_x * tiles_y, o.n);
-  kern<<<grid, 192, Cfg::SMEM, st>>>(mA_hi, mA_lo, mA_p2, mB_hi, mB_lo, mB_p2, p);
+  kern<<<grid, 320, Cfg::SMEM, st>>>(mA_hi, mA_lo, mA_p2, mB_hi, mB_lo, mB_p2, p);
   return launched("igemm_tc_kernel");
 }
 

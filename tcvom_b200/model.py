@@ -256,19 +256,21 @@ class EvalModel(nn.Module):
         self.TRIMAP_CHANNEL = 3
 
     # -- plan handling ---------------------------------------------------------------
-    def _plan(self, B, S, H, W, dev) -> Plan:
+    def _plan(self, B, S, H, W, dev, u8=False) -> Plan:
         eng = self.NET.engine()
         dil = -1 if self.DILATION_KERNEL is None else int(self.DILATION_KERNEL)
         self.__dict__["_eng"] = eng
-        key = ("eval", B, S, H, W, dil)
+        key = ("eval", B, S, H, W, dil, u8)
         plan = eng.plans.get(key)
         if plan is not None:
             return plan
         plan = Plan()
         eng._rec = plan
         try:
-            imgs = eng._empty((B, S, 3, H, W))
-            tris = eng._empty((B, S, 1, H, W))
+            in_dt = torch.uint8 if u8 else torch.float32
+            sfx = "_u8" if u8 else ""
+            imgs = eng._empty((B, S, 3, H, W), in_dt)
+            tris = eng._empty((B, S, 1, H, W), in_dt)
             x8 = eng._act(B * S, H, W, 8)
             trimask = eng._empty((B * S, H, W))
             tmp = eng._empty((2 * B * S * H * W,), torch.uint8)
@@ -276,10 +278,10 @@ class EvalModel(nn.Module):
             # inputs must hold valid data while recording runs the kernels once
             imgs.zero_(); tris.zero_()
             n0 = _cabi.launch_count()
-            eng._call("tcv_preprocess_eval", imgs.data_ptr(), tris.data_ptr(), B * S, H, W, dil, x8.ptr,
+            eng._call("tcv_preprocess_eval" + sfx, imgs.data_ptr(), tris.data_ptr(), B * S, H, W, dil, x8.ptr,
                       trimask.data_ptr(), tmp.data_ptr())
             out = eng.window_program(x8, trimask, B, S, H, W)
-            eng._call("tcv_postprocess_eval", out["pred"].data_ptr(), tris.data_ptr(), trimask.data_ptr(), B, S, H, W,
+            eng._call("tcv_postprocess_eval" + sfx, out["pred"].data_ptr(), tris.data_ptr(), trimask.data_ptr(), B, S, H, W,
                       alphas.data_ptr())
             plan.n_launch = _cabi.launch_count() - n0
             plan.io = dict(imgs=imgs, tris=tris, alphas=alphas, trimask=trimask, **{k: out[k] for k in
@@ -319,7 +321,9 @@ class EvalModel(nn.Module):
         assert Cc == 3 and S >= 3
         if H % 32 or W % 32:
             raise ValueError("tcvom_b200: H and W must be multiples of 32 (pred_test.py pads to 32)")
-        plan = self._plan(B, S, H, W, imgs.device)
+        # uint8 frames/trimaps are consumed as such (the reference casts with .float(), model.py:366-368)
+        u8 = imgs.dtype == torch.uint8 and tris.dtype == torch.uint8
+        plan = self._plan(B, S, H, W, imgs.device, u8)
         plan.io["imgs"].copy_(imgs, non_blocking=True)
         plan.io["tris"].copy_(tris, non_blocking=True)
         self.run_plan(plan)

@@ -201,3 +201,15 @@ def test_full_vmd_s3_and_random_dilation_against_oracle():
     assert abs(float(out[4]) - float(ref[4])) <= 2e-3 * abs(float(ref[4])) + 1e-4
     assert (out[6].cpu() - ref[6]).abs().max() < 1e-6          # tris_vis: same dilation radii were drawn
     assert (out[7].cpu() - ref[7]).abs().max() < ALPHA_TOL
+
+
+def test_uint8_ingest_equals_float_ingest():
+    """uint8 frames/trimaps (cv2.imread dtype) give bit-identical alphas to the float path."""
+    g = golden("eval_dil64x96.npz")
+    m = _model(int(g["dilate"]))
+    iu, tu = torch.from_numpy(g["imgs"]).cuda(), torch.from_numpy(g["tris"]).cuda()
+    with torch.no_grad():
+        a_u8 = m(iu, tu).clone()
+        a_f = m(iu.float(), tu.float())
+    assert torch.equal(a_u8, a_f)
+    assert np.abs(a_u8.cpu().numpy() - g["alphas"]).max() < ALPHA_TOL
