@@ -13,7 +13,8 @@ for r in rows:
 launches = list(per.values())
 # the capture window may start mid-plan; the plan is periodic, so rotate it to start at the first kernel
 start = next(i for i, L in enumerate(launches) if "trimask_raw" in L["name"])
-launches = launches[start:] + launches[:start]
+nxt = next((i for i, L in enumerate(launches) if i > start and "trimask_raw" in L["name"]), None)
+launches = launches[start:nxt] if nxt is not None else launches[start:] + launches[:start]
 calls = sorted((json.loads(l) for l in open(calls_jsonl)), key=lambda c: c["idx"])
 # one C-ABI call may launch several kernels (preprocess: 2-4, gca_prep: 2); align by kernel-name hints
 HINT = {"tcv_conv2d": ("conv_", "igemm_tc"), "tcv_gemm_tn_tc": ("igemm_tc",), "tcv_gemm_tn_f32": ("gemm_tn_f32",),
