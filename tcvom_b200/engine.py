@@ -81,6 +81,24 @@ class Plan:
         return [a.elapsed_time(b) for a, b in evs]
 
 
+def named_tensors(net: torch.nn.Module) -> Dict[str, torch.Tensor]:
+    """state_dict-style name -> tensor for parameters and buffers.  Also works on nn.DataParallel replicas,
+    whose parameters are plain attributes recorded in ``_former_parameters`` (torch/nn/parallel/replicate.py)
+    and therefore invisible to ``named_parameters()``."""
+    out: Dict[str, torch.Tensor] = {}
+    for mname, m in net.named_modules():
+        pre = mname + "." if mname else ""
+        for k, v in m._parameters.items():
+            if v is not None:
+                out[pre + k] = v
+        for k, v in getattr(m, "_former_parameters", {}).items():
+            out[pre + k] = v
+        for k, v in m._buffers.items():
+            if v is not None:
+                out[pre + k] = v
+    return out
+
+
 def _k(prefix: str, name: str) -> str:
     return f"{prefix}.{name}" if prefix else name
 
@@ -114,9 +132,7 @@ class GcaVmnEngine:
 
     # ------------------------------------------------------------------ weights
     def _named(self) -> Dict[str, torch.Tensor]:
-        d = dict(self.net.named_parameters())
-        d.update(dict(self.net.named_buffers()))
-        return d
+        return named_tensors(self.net)
 
     def _current_fingerprint(self):
         if self._tensors is None:

@@ -21,7 +21,7 @@ import torch
 from torch import nn
 
 from . import _cabi
-from .engine import Act, GcaVmnEngine, Plan
+from .engine import Act, GcaVmnEngine, Plan, named_tensors
 from .modules import GCADecoderParams, GCAEncoderParams, GuidedCxtAttenParams, TAMParams
 
 
@@ -40,7 +40,7 @@ _ENGINE_LOCK = threading.Lock()
 def _engine_for(module: nn.Module, window: int) -> GcaVmnEngine:
     """One engine per (module, device).  nn.DataParallel replicas share the module __dict__ (and so
     this table) but run one thread per device, so a per-device engine is never used concurrently."""
-    dev = next(module.parameters()).device
+    dev = next(iter(named_tensors(module).values())).device
     if dev.type != "cuda":
         raise RuntimeError("tcvom_b200: the module must live on a CUDA device (no CPU fallback)")
     with _ENGINE_LOCK:
@@ -304,7 +304,8 @@ class EvalModel(nn.Module):
                 with torch.cuda.stream(st):
                     plan.replay(st.cuda_stream)                     # warm-up outside capture
                     st.synchronize()
-                    with torch.cuda.graph(g, stream=st):
+                    # thread_local: nn.DataParallel replicas capture concurrently from one thread per device
+                    with torch.cuda.graph(g, stream=st, capture_error_mode="thread_local"):
                         plan.replay(torch.cuda.current_stream(dev).cuda_stream)
                 torch.cuda.current_stream(dev).wait_stream(st)
                 plan.graph = g

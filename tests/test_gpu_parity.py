@@ -213,3 +213,20 @@ def test_uint8_ingest_equals_float_ingest():
         a_f = m(iu.float(), tu.float())
     assert torch.equal(a_u8, a_f)
     assert np.abs(a_u8.cpu().numpy() - g["alphas"]).max() < ALPHA_TOL
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_data_parallel_wrapper_matches_single_gpu():
+    """pred_vmn.py:85 wraps the model in nn.DataParallel (batch = #GPUs)."""
+    g = golden("eval_batch2_64.npz")
+    m = _model()
+    imgs = torch.from_numpy(g["imgs"]).float().cuda()
+    tris = torch.from_numpy(g["tris"]).float().cuda()
+    with torch.no_grad():
+        single = m(imgs, tris).clone()
+        dp = torch.nn.DataParallel(m)
+        out1 = dp(imgs, tris).clone()
+        out2 = dp(imgs, tris)            # second call: replicas are rebuilt, plans/graphs are reused per device
+    assert torch.equal(out1, out2)
+    assert (out1 - single).abs().max() < 1e-6
+    assert np.abs(out1.cpu().numpy() - g["alphas"]).max() < ALPHA_TOL
