@@ -168,6 +168,10 @@ int tcv_postprocess_eval_u8(const float* pred, const uint8_t* tris, const float*
 
 int tcv_avgpool2(const void* x, int n, int h, int w, int c, void* y, tcv_stream_t stream);
 
+/* y [n, h+2, w+2, c] = x [n, h, w, c] with a 1-pixel reflect border (nn.ReflectionPad2d(1),
+ * res_gca_enc.py:20-33), split-bf16 NHWC */
+int tcv_pad_reflect1(const void* x, int n, int h, int w, int c, void* y, tcv_stream_t stream);
+
 /* unknown[n, y, x] = x8[n, y*8, x*8, channel 4]  (res_gca_enc.py:71) ; fp32 [n, h/8, w/8] */
 int tcv_unknown_os8(const void* x8, int n, int h, int w, float* unknown, tcv_stream_t stream);
 

@@ -63,6 +63,7 @@ SIGNATURES = {
                                      c_void_p]),
     "tcv_losses_vmd": (c_int, [c_void_p] * 8 + [c_int] * 5 + [c_float] * 3 + [c_void_p] * 6),
     "tcv_avgpool2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_pad_reflect1": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_unknown_os8": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_gca_prep": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_int, c_void_p]),

@@ -75,6 +75,16 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const tcv_conv_desc d)
             for (int k = 0; k < 8; ++k) f[q][k] = 0.f;
           }
         }
+        if constexpr (COT == 1) {
+          // single output channel (the alpha head): the 8 weights of this channel group are two float4
+          // broadcasts instead of eight scalar shared-memory loads
+          const float4 wa = *reinterpret_cast<const float4*>(wt + c8), wb = *reinterpret_cast<const float4*>(wt + c8 + 4);
+          const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+          for (int q = 0; q < PX; ++q)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[q][0] = fmaf(f[q][k], wv[k], acc[q][0]);
+        } else {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const float* wp = wt + (c8 + k) * COT;
@@ -97,6 +107,7 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const tcv_conv_desc d)
 #pragma unroll
               for (int q = 0; q < PX; ++q) acc[q][j] = fmaf(f[q][k], wp[j], acc[q][j]);
           }
+        }
         }
       }
     }

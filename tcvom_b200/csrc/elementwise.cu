@@ -115,6 +115,28 @@ __global__ void avgpool2_kernel(const __nv_bfloat16* __restrict__ x, int n, int 
   store8(y + (((long long)img * oh + oy) * ow + ox) * c + cc, (long long)n * oh * ow * c, acc);
 }
 
+// 1-pixel reflect border (nn.ReflectionPad2d(1)) materialised once so that the following stride-2 conv can
+// run on the TMA/tcgen05 path (TMA zero-fills out-of-range coordinates, it cannot reflect)
+__global__ void pad_reflect1_kernel(const __nv_bfloat16* __restrict__ x, int n, int h, int w, int c,
+                                    __nv_bfloat16* __restrict__ y) {
+  const int oh = h + 2, ow = w + 2, c8 = c / 8;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)n * oh * ow * c8;
+  if (i >= total) return;
+  const int cc = (int)(i % c8) * 8;
+  long long t = i / c8;
+  const int ox = (int)(t % ow);
+  t /= ow;
+  const int oy = (int)(t % oh);
+  const int img = (int)(t / oh);
+  const int iy = reflect(oy - 1, h), ix = reflect(ox - 1, w);
+  const long long ip = (long long)n * h * w * c, op = (long long)n * oh * ow * c;
+  const __nv_bfloat16* src = x + (((long long)img * h + iy) * w + ix) * c + cc;
+  __nv_bfloat16* dst = y + (((long long)img * oh + oy) * ow + ox) * c + cc;
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+  *reinterpret_cast<uint4*>(dst + op) = *reinterpret_cast<const uint4*>(src + ip);
+}
+
 __global__ void unknown_os8_kernel(const __nv_bfloat16* __restrict__ x8, int n, int h, int w,
                                    float* __restrict__ unk) {
   const int oh = h / 8, ow = w / 8;
@@ -294,6 +316,15 @@ int tcv_avgpool2(const void* x, int n, int h, int w, int c, void* y, tcv_stream_
   avgpool2_kernel<<<blocks(total), 256, 0, S(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, h, w, c,
                                                         reinterpret_cast<__nv_bfloat16*>(y));
   return launched("avgpool2_kernel");
+}
+
+int tcv_pad_reflect1(const void* x, int n, int h, int w, int c, void* y, tcv_stream_t stream) {
+  TCV_REQUIRE(x && y, "pad_reflect1: null pointer");
+  TCV_REQUIRE(h >= 2 && w >= 2 && c % 8 == 0, "pad_reflect1: need h,w >= 2 and c %% 8 == 0");
+  const long long total = (long long)n * (h + 2) * (w + 2) * (c / 8);
+  pad_reflect1_kernel<<<blocks(total), 256, 0, S(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, h, w, c,
+                                                            reinterpret_cast<__nv_bfloat16*>(y));
+  return launched("pad_reflect1_kernel");
 }
 
 int tcv_unknown_os8(const void* x8, int n, int h, int w, float* unknown, tcv_stream_t stream) {

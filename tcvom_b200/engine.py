@@ -242,7 +242,14 @@ class GcaVmnEngine:
         return a
 
     # ------------------------------------------------------------------ operators
-    def conv(self, x: Act, wkey: str, *, stride=1, pad=PAD_ZERO, bn: Optional[str] = None, bias=False,
+    def pad_reflect1(self, x: Act) -> Act:
+        y = self._act(x.n, x.h + 2, x.w + 2, x.c)
+        assert x.plane == x.n * x.img_elems
+        self._call("tcv_pad_reflect1", x.ptr, x.n, x.h, x.w, x.c, y.ptr,
+                   meta=dict(kind="tcv_pad_reflect1", bytes=8 * x.n * x.img_elems))
+        return y
+
+    def conv(self, x: Act, wkey: str, *, stride=1, pad=PAD_ZERO, prepadded=False, bn: Optional[str] = None, bias=False,
              act=ACT_NONE, res1: Optional[Act] = None, res1_shift=0, bn2: Optional[str] = None,
              res2: Optional[Act] = None, f32_out: Optional[torch.Tensor] = None, f32_ptr: int = 0,
              want_split=True) -> Optional[Act]:
@@ -250,7 +257,11 @@ class GcaVmnEngine:
         cout, k = ent["cout"], ent["k"]
         assert ent["cin"] == x.c, (wkey, ent["cin"], x.c)
         assert not ent["transposed"]
-        if k == 3:
+        if k == 3 and prepadded:
+            # x already carries its 1-pixel border: taps are unshifted and never leave the tensor
+            taps = [(ky, kx) for ky in range(3) for kx in range(3)]
+            oh, ow = (x.h - 3) // stride + 1, (x.w - 3) // stride + 1
+        elif k == 3:
             taps = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
             oh, ow = (x.h + 2 - 3) // stride + 1, (x.w + 2 - 3) // stride + 1
         else:
@@ -441,8 +452,13 @@ class GcaVmnEngine:
         c3 = self.conv(x1, e + ".conv3", stride=2, bn=e + ".bn3", act=ACT_RELU)
         g = x8
         for ci, bi in ((1, 3), (5, 7), (9, 11)):                                # guidance head (res_gca_enc.py:20-33)
-            g = self.conv(g, f"{e}.guidance_head.{ci}", stride=2, pad=PAD_REFLECT, act=ACT_RELU,
-                          bn2=f"{e}.guidance_head.{bi}")
+            if self.use_tc_conv and g.c % 32 == 0:
+                # 32 -> 128: reflect border materialised once, then the stride-2 tcgen05 path
+                g = self.conv(self.pad_reflect1(g), f"{e}.guidance_head.{ci}", stride=2, prepadded=True, act=ACT_RELU,
+                              bn2=f"{e}.guidance_head.{bi}")
+            else:
+                g = self.conv(g, f"{e}.guidance_head.{ci}", stride=2, pad=PAD_REFLECT, act=ACT_RELU,
+                              bn2=f"{e}.guidance_head.{bi}")
         im_fea = g
         unknown = self._empty((x8.n, x8.h // 8, x8.w // 8))
         self._call("tcv_unknown_os8", x8.ptr, x8.n, x8.h, x8.w, unknown.data_ptr())
