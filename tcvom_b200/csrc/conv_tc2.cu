@@ -44,8 +44,9 @@ struct V2Cfg {
   static constexpr int B_SLOT_BYTES = 2 * BN * V2_BK * 2;  // hi + lo
   // narrow layers are latency-bound on the activation stream: give them a deeper A ring, and enough
   // B slots to keep all 9 taps of a 32-channel layer resident (weights are then loaded once per CTA)
-  static constexpr int B_SLOTS = BN >= 128 ? 5 : (BN >= 64 ? 6 : 9);
-  static constexpr int A_SLOTS = BN >= 128 ? 3 : (BN >= 64 ? 4 : 4);
+  // BN = 64: all 18 weight tiles of a 64->64 3x3 stay resident (144 KB) next to two activation slots
+  static constexpr int B_SLOTS = BN >= 128 ? 5 : (BN >= 64 ? 18 : 9);
+  static constexpr int A_SLOTS = BN >= 128 ? 3 : (BN >= 64 ? 2 : 4);
   static constexpr int A_BYTES = A_SLOTS * V2_A_SLOT_BYTES;
   static constexpr int SMEM = A_BYTES + B_SLOTS * B_SLOT_BYTES + 1024 + 512;
   static constexpr int TMEM_COLS = 4 * BN < 32 ? 32 : 4 * BN;  // 2 buffers x 2 accumulators

@@ -32,18 +32,24 @@ struct V3Params {
   int ntaps, dy[V3_MAXT], dx[V3_MAXT], wtap[V3_MAXT];
   int dy_min, dx_min, box_w, box_rows;
   int b_resident;
-  uint32_t idesc;
+  int a_slots, b_slots;   // runtime shared-memory carve-up (resident weight tiles, activation ring)
+  uint32_t idesc;    // M=128, N=BN
+  uint32_t idesc2;   // M=128, N=2*BN: A_hi x [B_hi ; B_lo] in one MMA
   EpiParams epi;
 };
 
 template <int BN>
 struct V3Cfg {
   static constexpr int B_SLOT_BYTES = 2 * BN * 32 * 2;       // hi + lo, one tap x one 32-wide K block
-  static constexpr int B_SLOTS = 18;                          // 9 taps x up to 2 K blocks stay resident (72 KB)
+  static constexpr int MAX_B_SLOTS = 18;                      // 9 taps x up to 2 K blocks stay resident (72 KB)
   static constexpr int A_SLOT_BYTES = 45056;                  // hi + lo of one 10x34-pixel x 32-channel box
-  static constexpr int A_SLOTS = 3;
-  static constexpr int SMEM = A_SLOTS * A_SLOT_BYTES + B_SLOTS * B_SLOT_BYTES + 1024 + 512;
-  static constexpr int TMEM_COLS = 4 * BN;
+  static constexpr int MAX_A_SLOTS = 3;
+  static constexpr int STAGE_BYTES = 2 * 2 * 128 * BN * 2;    // output staging: 2 accumulators x hi/lo x 128 px x BN ch
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int TMEM_COLS = 8 * BN;                    // 2 buffers x 2 accumulators x (hi.hi | hi.lo) halves
+  static int smem_bytes(int a_slots, int b_slots) {
+    return a_slots * A_SLOT_BYTES + b_slots * B_SLOT_BYTES + STAGE_BYTES + BAR_BYTES + 1024;
+  }
 };
 
 // un-swizzled K-major descriptor: LBO = byte distance between K-adjacent core matrices, SBO = between
@@ -58,13 +64,16 @@ __global__ void __launch_bounds__(320, 1) conv_tc3_kernel(const __grid_constant_
                                                           const __grid_constant__ CUtensorMap mapA_lo,
                                                           const __grid_constant__ CUtensorMap mapB_hi,
                                                           const __grid_constant__ CUtensorMap mapB_lo,
+                                                          const __grid_constant__ CUtensorMap mapY_hi,
+                                                          const __grid_constant__ CUtensorMap mapY_lo,
                                                           const __grid_constant__ V3Params p) {
   using Cfg = V3Cfg<BN>;
-  constexpr int SA = Cfg::A_SLOTS, SB = Cfg::B_SLOTS;
+  const int SA = p.a_slots, SB = p.b_slots;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_base = smem_base + SA * Cfg::A_SLOT_BYTES;
-  const uint32_t bar_base = b_base + SB * Cfg::B_SLOT_BYTES;
+  const uint32_t stage_base = b_base + SB * Cfg::B_SLOT_BYTES;      // 1 KB aligned (slot sizes are 1 KB multiples)
+  const uint32_t bar_base = stage_base + Cfg::STAGE_BYTES;
   auto fullA = [&](int s) { return bar_base + 8u * s; };
   auto emptyA = [&](int s) { return bar_base + 8u * (SA + s); };
   auto fullB = [&](int s) { return bar_base + 8u * (2 * SA + s); };
@@ -157,7 +166,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc3_kernel(const __grid_constant_
       const int buf = iw & 1;
       mbar_wait(accEmpty(buf), ((uint32_t)(iw >> 1) & 1u) ^ 1u);
       tc_fence_after();
-      const uint32_t d0 = tmem_base + (uint32_t)(buf * 2 * BN), d1 = d0 + (uint32_t)BN;
+      const uint32_t d0 = tmem_base + (uint32_t)(buf * 4 * BN), d1 = d0 + (uint32_t)(2 * BN);
       bool first = true;
       int il = 0;
       for (int kc = 0; kc < p.kc_iters; ++kc, ++ia) {
@@ -184,14 +193,18 @@ __global__ void __launch_bounds__(320, 1) conv_tc3_kernel(const __grid_constant_
               const uint64_t al0 = smem_desc_ns(a_lo + off0 + kofs, lbo, row_bytes);
               const uint64_t ah1 = smem_desc_ns(a_hi + off1 + kofs, lbo, row_bytes);
               const uint64_t al1 = smem_desc_ns(a_lo + off1 + kofs, lbo, row_bytes);
-              const uint64_t bh = smem_desc<32>(b_hi + ks * 32), bl = smem_desc<32>(b_lo + ks * 32);
+              const uint64_t bh = smem_desc<32>(b_hi + ks * 32);
               const uint32_t acc = (first && ks == 0) ? 0u : 1u;
-              tc_mma(d0, ah0, bh, p.idesc, acc);
-              tc_mma(d1, ah1, bh, p.idesc, acc);
-              tc_mma(d0, ah0, bl, p.idesc, 1u);
-              tc_mma(d1, ah1, bl, p.idesc, 1u);
-              tc_mma(d0, al0, bh, p.idesc, 1u);
-              tc_mma(d1, al1, bh, p.idesc, 1u);
+              // The hi and lo weight planes are adjacent in the slot, so [B_hi ; B_lo] is ONE 2*BN-row operand:
+              // A_hi is read from shared memory once for both products (the narrow layers are bound by the
+              // operand reads of N=32 MMAs).  Columns [0,BN) get A_hi.B_hi (+ A_lo.B_hi below), [BN,2BN) A_hi.B_lo;
+              // the epilogue adds the two halves.
+              tc_mma(d0, ah0, bh, p.idesc2, acc);
+              tc_mma(d1, ah1, bh, p.idesc2, acc);
+              if (!(p.epi.dbg & 64)) {   // (measurement switch: skip the A_lo term)
+                tc_mma(d0, al0, bh, p.idesc, 1u);
+                tc_mma(d1, al1, bh, p.idesc, 1u);
+              }
             }
             if (!p.b_resident) tc_commit(emptyB(sb));
             if (t == p.ntaps - 1) {
@@ -206,21 +219,40 @@ __global__ void __launch_bounds__(320, 1) conv_tc3_kernel(const __grid_constant_
     }
   } else {
     // ================================ epilogue (warps 2..9) ================================
+    // TMEM -> registers -> fused epilogue -> 64B-swizzled smem tile -> TMA store: the output leaves the SM
+    // as whole 64-byte pixel rows written by the copy engine instead of 32 scattered 16-byte sectors per
+    // store instruction (the epilogue, not the MMA, bounded the 32-channel layers).
     const int e = warp - 2;
     const int i = e >> 2;
     const int q = warp & 3;
     const int r = q * 32 + lane;
+    const uint32_t stage_hi = stage_base + (uint32_t)i * (2u * 128u * BN * 2u), stage_lo = stage_hi + 128u * BN * 2u;
+    const bool issuer = (e & 3) == 0 && lane == 0;
     int iw = 0;
     for (int work = blockIdx.x; work < p.total_work; work += gridDim.x, ++iw) {
       int img, h0, w0;
       decode(work, img, h0, w0);
       const int buf = iw & 1;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN + i * BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 4 * BN + i * 2 * BN);
       const int ty = r / V3_TW, tx = r - ty * V3_TW;
       const int gy = h0 + i * V3_TH + ty, gx = w0 + tx;
+      // the previous TMA store of this accumulator group must have finished READING the staging tile
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + i) : "memory");
       conv_epilogue<BN>(p.epi, taddr, gy < p.gh && gx < p.gw, img, gy, gx, 0, accFull(buf), (uint32_t)(iw >> 1) & 1u,
-                        accEmpty(buf), lane);
+                        accEmpty(buf), lane, stage_hi, stage_lo, r, /*split_halves=*/true);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(3 + i) : "memory");
+      if (issuer && !(p.epi.dbg & 2)) {
+        const int ry = h0 + i * V3_TH;
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                     ::"l"(&mapY_hi), "r"(stage_hi), "r"(0), "r"(w0), "r"(ry), "r"(img) : "memory");
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                     ::"l"(&mapY_lo), "r"(stage_lo), "r"(0), "r"(w0), "r"(ry), "r"(img) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
     }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -233,7 +265,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc3_kernel(const __grid_constant_
 // ------------------------------------------------------------------------------------------ host
 int conv2d_tc3_supported(const tcv_conv_desc& d) {
   if (d.stride != 1 || d.pad_mode != TCV_PAD_ZERO) return 0;
-  if (d.cout != 32) return 0;
+  if (d.cout != 32 || !d.y || d.y_f32) return 0;
   if (d.x_img_stride != (long long)d.ih * d.iw * d.cin) return 0;
   if (d.ntaps > V3_MAXT) return 0;
   for (int t = 0; t < d.ntaps; ++t)
@@ -279,12 +311,29 @@ static int conv_tc3_bn(const tcv_conv_desc& d, cudaStream_t st) {
   p.tiles_x = (d.gw + V3_TW - 1) / V3_TW;
   p.tiles_y = (d.gh + 2 * V3_TH - 1) / (2 * V3_TH);
   p.total_work = p.tiles_x * p.tiles_y * d.n;
-  p.b_resident = p.ntaps * p.kc_iters <= Cfg::B_SLOTS ? 1 : 0;
+  p.b_slots = p.ntaps * p.kc_iters;                 // every weight tile stays resident
+  if (p.b_slots > Cfg::MAX_B_SLOTS) return fail(TCV_ERR_UNSUPPORTED, "conv_tc3: too many weight tiles");
+  p.b_resident = 1;
+  p.a_slots = Cfg::MAX_A_SLOTS;
+  while (p.a_slots > 2 && Cfg::smem_bytes(p.a_slots, p.b_slots) > 227 * 1024) --p.a_slots;
   p.idesc = instr_desc(BN, false);
+  p.idesc2 = instr_desc(2 * BN, false);
   fill_epi(p.epi, d, g_debug_flags.load());
 
-  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo, mY_hi, mY_lo;
   const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(d.x);
+  {
+    // output view over the compute grid: pixel (gy, gx) of image n lives at y[n][gy*oy_mul+oy_off][gx*ox_mul+ox_off]
+    const __nv_bfloat16* y = reinterpret_cast<const __nv_bfloat16*>(d.y) + ((long long)d.oy_off * d.ow + d.ox_off) * d.cout;
+    cuuint64_t dims[4] = {(cuuint64_t)d.cout, (cuuint64_t)d.gw, (cuuint64_t)d.gh, (cuuint64_t)d.n};
+    cuuint64_t str[3] = {(cuuint64_t)d.ox_mul * d.cout * 2, (cuuint64_t)d.oy_mul * d.ow * d.cout * 2,
+                         (cuuint64_t)d.oh * d.ow * d.cout * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BN, (cuuint32_t)V3_TW, (cuuint32_t)V3_TH, 1};
+    int rc = make_map(&mY_hi, y, 4, dims, str, box, 32);
+    if (rc) return rc;
+    rc = make_map(&mY_lo, y + (long long)d.n * d.oh * d.ow * d.cout, 4, dims, str, box, 32);
+    if (rc) return rc;
+  }
   {
     // 5-D view of the NHWC tensor: {8 ch, W, H, N, Cin/8 chunks}; chunk stride 16 B
     EncodeTiledFn enc = get_encode();
@@ -313,12 +362,13 @@ static int conv_tc3_bn(const tcv_conv_desc& d, cudaStream_t st) {
     if (rc) return rc;
   }
   auto kern = conv_tc3_kernel<BN>;
-  TCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  const int smem = Cfg::smem_bytes(p.a_slots, p.b_slots);
+  TCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int dev = 0, sms = 0;
   TCV_CUDA(cudaGetDevice(&dev));
   TCV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.total_work < sms ? p.total_work : sms;
-  kern<<<grid, 320, Cfg::SMEM, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, p);
+  kern<<<grid, 320, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, mY_hi, mY_lo, p);
   return launched("conv_tc3_kernel");
 }
 

@@ -32,10 +32,14 @@ static inline void fill_epi(EpiParams& e, const tcv_conv_desc& d, int dbg) {
 // gy/gx: position of this thread's pixel in the compute grid; in_grid: inside it.  The warp waits on
 // `acc_full` (parity given), drains its 32 TMEM lanes starting at `taddr`, and arrives on `acc_empty` as soon
 // as its last tcgen05.ld has completed.
+// split_halves: the accumulator is 2*BN columns wide and the two halves are summed first.
+// stage_hi/stage_lo != 0 (BN == 32 only): instead of scattered 16-byte global stores the bf16 planes of this
+// thread's row are written into 64B-swizzled shared-memory tiles (row r at stage + 64*r) for a TMA store.
 template <int BN>
 __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr, bool in_grid, int img, int gy, int gx,
                                               int n0, uint32_t acc_full, uint32_t full_parity, uint32_t acc_empty,
-                                              int lane) {
+                                              int lane, uint32_t stage_hi = 0, uint32_t stage_lo = 0, int row = 0,
+                                              bool split_halves = false) {
   const bool valid = in_grid && !(p.dbg & 2);
   const int oy = gy * p.oy_mul + p.oy_off, ox = gx * p.ox_mul + p.ox_off;
   const long long oplane = (long long)p.n_imgs * p.oh * p.ow * p.cout;
@@ -82,6 +86,12 @@ __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr
     const int slot = ci & 1;
     uint32_t v[32];
     tc_ld32(taddr + c0, v);
+    if (split_halves) {   // BN == 32: columns [32,64) hold the A_hi.B_lo partial product
+      uint32_t v2[32];
+      tc_ld32(taddr + BN + c0, v2);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+    }
     if (ci == BN / 32 - 1) {
       // all TMEM reads of this warp are complete: hand the buffer back to the MMA warp early
       tc_fence_before();
@@ -124,7 +134,24 @@ __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr
       }
     }
     if (has2) add_res(rb[slot], f);
-    if (p.y && !((p.dbg & 16) && f[0] != 12345.678f)) {
+    if (stage_hi) {
+      const uint32_t sw = (uint32_t)((row >> 1) & 3);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          __nv_bfloat16 h0, l0, h1, l1;
+          split_bf16(f[8 * k + 2 * m], h0, l0);
+          split_bf16(f[8 * k + 2 * m + 1], h1, l1);
+          h[m] = pack2(h0, h1);
+          l[m] = pack2(l0, l1);
+        }
+        const uint32_t off = (uint32_t)row * 64u + (((uint32_t)k ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+      }
+    } else if (p.y && !((p.dbg & 16) && f[0] != 12345.678f)) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8) store8(p.y + obase + c0 + j, oplane, f + j);
     }

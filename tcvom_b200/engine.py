@@ -9,6 +9,7 @@ Program restated from (reference checkout):
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 import os
 from typing import Dict, List, Optional, Tuple
@@ -115,7 +116,10 @@ class GcaVmnEngine:
         self.bias: Dict[str, torch.Tensor] = {}
         self._fingerprint = None
         self._tensors = None
-        self.plans: Dict[Tuple, Plan] = {}
+        self.plans: "collections.OrderedDict[Tuple, Plan]" = collections.OrderedDict()
+        # recorded plans own all their activation buffers (10.5 GB for a 1080p window): keep only the most
+        # recently used shapes so that a folder of differently sized clips cannot exhaust HBM
+        self.max_plans = int(os.environ.get("TCV_MAX_PLANS", "2"))
         self._rec: Optional[Plan] = None
         self.use_graphs = os.environ.get("TCV_GRAPHS", "1") == "1"
         # tcgen05 paths (default on); the CUDA-core fp32 paths stay available as the exact cross-check
@@ -214,6 +218,18 @@ class GcaVmnEngine:
                 ent["w_tc"] = torch.empty((2, kh * kw, cout, cin_pad), dtype=torch.bfloat16, device=wbar.device)
             _cabi.check(L.tcv_pack_weight_tc(ent["w"].data_ptr(), kh * kw, cin_pad, cout, ent["w_tc"].data_ptr(), st),
                         "pack_weight_tc")
+
+    def get_plan(self, key) -> Optional[Plan]:
+        plan = self.plans.get(key)
+        if plan is not None:
+            self.plans.move_to_end(key)
+        return plan
+
+    def put_plan(self, key, plan: Plan) -> None:
+        self.plans[key] = plan
+        self.plans.move_to_end(key)
+        while len(self.plans) > max(self.max_plans, 1):
+            self.plans.popitem(last=False)          # drops the buffers (and CUDA graph) of the oldest shape
 
     # ------------------------------------------------------------------ call recording
     def _call(self, fn_name: str, *args, meta: Optional[dict] = None):

@@ -261,7 +261,7 @@ class EvalModel(nn.Module):
         dil = -1 if self.DILATION_KERNEL is None else int(self.DILATION_KERNEL)
         self.__dict__["_eng"] = eng
         key = ("eval", B, S, H, W, dil, u8)
-        plan = eng.plans.get(key)
+        plan = eng.get_plan(key)
         if plan is not None:
             return plan
         plan = Plan()
@@ -289,7 +289,7 @@ class EvalModel(nn.Module):
             plan.io["feat"] = out["feat"].buf
         finally:
             eng._rec = None
-        eng.plans[key] = plan
+        eng.put_plan(key, plan)
         return plan
 
     def run_plan(self, plan: Plan) -> None:
@@ -366,7 +366,7 @@ class FullModel_VMD(nn.Module):
         eng = self.NET.engine()
         self.__dict__["_eng"] = eng
         key = ("vmd" if self._with_att else "full", B, S, H, W, float(self.EPS))
-        plan = eng.plans.get(key)
+        plan = eng.get_plan(key)
         if plan is not None:
             return plan
         plan = Plan()
@@ -399,7 +399,7 @@ class FullModel_VMD(nn.Module):
                            **{k: out[k] for k in ("pred", "attb", "attf", "small_mask")})
         finally:
             eng._rec = None
-        eng.plans[key] = plan
+        eng.put_plan(key, plan)
         return plan
 
     run_plan = EvalModel.run_plan

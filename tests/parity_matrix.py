@@ -1,5 +1,5 @@
 """Alpha-matte parity (max abs err vs reference golden vectors / CPU oracle) for each kernel-path
-combination.  python tools/parity_matrix.py [--big]"""
+combination.  python tests/parity_matrix.py [--big]   (development aid, not collected by pytest)"""
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))

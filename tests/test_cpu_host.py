@@ -68,3 +68,19 @@ def test_synthetic_window_is_deterministic():
     g = golden("eval_ring64.npz")
     imgs, tris = synthetic.make_window(64, 64, seed=7)
     assert np.array_equal(tris, g["tris"])
+
+
+def test_missing_native_library_fails_loudly(monkeypatch):
+    """No CPU / PyTorch fallback: without the .so the product path raises instead of computing elsewhere."""
+    from tcvom_b200 import _cabi
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "LIB_PATH", "/nonexistent/libtcvom_b200.so")
+    with pytest.raises(RuntimeError, match="native library not built"):
+        _cabi.lib()
+
+
+def test_product_package_does_not_import_the_oracle():
+    import pathlib
+    for f in pathlib.Path(ROOT, "tcvom_b200").rglob("*.py"):
+        src = f.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, f

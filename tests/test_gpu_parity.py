@@ -230,3 +230,24 @@ def test_data_parallel_wrapper_matches_single_gpu():
     assert torch.equal(out1, out2)
     assert (out1 - single).abs().max() < 1e-6
     assert np.abs(out1.cpu().numpy() - g["alphas"]).max() < ALPHA_TOL
+
+
+def test_plan_cache_is_bounded_and_shapes_can_alternate():
+    """Plans own GBs of buffers: only the most recent shapes are kept, evicted shapes are re-recorded."""
+    from tcvom_b200 import synthetic
+    m = _model()
+    outs = {}
+    for hw in ((64, 64), (64, 96), (96, 64), (64, 64)):
+        imgs, tris = synthetic.make_window(*hw, seed=3)
+        with torch.no_grad():
+            a = m(torch.from_numpy(imgs).cuda(), torch.from_numpy(tris).cuda()).clone()
+        if hw in outs:
+            assert torch.equal(outs[hw], a)
+        outs[hw] = a
+        assert len(m.NET.engine().plans) <= 2
+
+
+def test_shape_validation():
+    m = _model()
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 3, 3, 70, 64).cuda(), torch.zeros(1, 3, 1, 70, 64).cuda())
