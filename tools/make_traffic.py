@@ -21,7 +21,7 @@ HINT = {"tcv_conv2d": ("conv_", "igemm_tc"), "tcv_gemm_tn_tc": ("igemm_tc",), "t
         "tcv_preprocess_eval": ("trimask_raw", "dilate_", "preprocess_"), "tcv_gca_prep": ("gca_scales", "gca_prep"),
         "tcv_gca_values": ("gca_values",), "tcv_gca_softmax": ("gca_softmax",), "tcv_gca_fold": ("gca_fold",),
         "tcv_tam_attend": ("tam_attend",), "tcv_avgpool2": ("avgpool2",), "tcv_unknown_os8": ("unknown_os8",),
-        "tcv_postprocess_eval": ("postprocess",)}
+        "tcv_postprocess_eval": ("postprocess",), "tcv_pad_reflect1": ("pad_reflect1",)}
 agg = collections.defaultdict(lambda: dict(launches=0, dram_bytes=0.0, ns=0.0))
 li = 0
 for c in calls:
@@ -39,7 +39,7 @@ for c in calls:
         li += 1
         n += 1
         if fn in ("tcv_conv2d", "tcv_gemm_tn_tc", "tcv_gemm_tn_f32", "tcv_gca_values", "tcv_gca_softmax", "tcv_gca_fold",
-                  "tcv_tam_attend", "tcv_avgpool2", "tcv_unknown_os8", "tcv_postprocess_eval"):
+                  "tcv_tam_attend", "tcv_avgpool2", "tcv_unknown_os8", "tcv_postprocess_eval", "tcv_pad_reflect1"):
             break
     assert n > 0, (c, launches[li]["name"] if li < len(launches) else None)
 assert li == len(launches), (li, len(launches))
