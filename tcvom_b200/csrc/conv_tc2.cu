@@ -33,6 +33,7 @@ struct V2Params {
   int kc_iters;
   int ngroups, group_dx[V2_MAXG], ndy[V2_MAXG], dy[V2_MAXG][V2_MAXDY], wtap[V2_MAXG][V2_MAXDY];
   int dy_min, box_rows;
+  int tma_store;   // epilogue stages its output in smem and stores it with TMA (needs y, no fp32 side output)
   int dbg;         // measurement switches (tcv_set_debug_flags): 1 no MMA, 2 no epilogue memory ops, 4 A loaded once, 8 B loaded once
   int b_resident;  // all weight tiles of a work item fit the B ring: load them once, never recycle
   uint32_t idesc;
@@ -44,11 +45,11 @@ struct V2Cfg {
   static constexpr int B_SLOT_BYTES = 2 * BN * V2_BK * 2;  // hi + lo
   // narrow layers are latency-bound on the activation stream: give them a deeper A ring, and enough
   // B slots to keep all 9 taps of a 32-channel layer resident (weights are then loaded once per CTA)
-  // BN = 64: all 18 weight tiles of a 64->64 3x3 stay resident (144 KB) next to two activation slots
-  static constexpr int B_SLOTS = BN >= 128 ? 5 : (BN >= 64 ? 18 : 9);
-  static constexpr int A_SLOTS = BN >= 128 ? 3 : (BN >= 64 ? 2 : 4);
+  static constexpr int B_SLOTS = BN >= 128 ? 5 : (BN >= 64 ? 6 : 9);
+  static constexpr int A_SLOTS = BN >= 128 ? 2 : 3;
   static constexpr int A_BYTES = A_SLOTS * V2_A_SLOT_BYTES;
-  static constexpr int SMEM = A_BYTES + B_SLOTS * B_SLOT_BYTES + 1024 + 512;
+  static constexpr int STAGE_BYTES = 2 * 2 * 128 * 64;        // TMA-store staging: 2 accumulators x hi/lo x 128 rows x 64 B
+  static constexpr int SMEM = A_BYTES + B_SLOTS * B_SLOT_BYTES + STAGE_BYTES + 1024 + 512;
   static constexpr int TMEM_COLS = 4 * BN < 32 ? 32 : 4 * BN;  // 2 buffers x 2 accumulators
 };
 
@@ -57,6 +58,8 @@ __global__ void __launch_bounds__(320, 1) conv_tc2_kernel(const __grid_constant_
                                                           const __grid_constant__ CUtensorMap mapA_lo,
                                                           const __grid_constant__ CUtensorMap mapB_hi,
                                                           const __grid_constant__ CUtensorMap mapB_lo,
+                                                          const __grid_constant__ CUtensorMap mapY_hi,
+                                                          const __grid_constant__ CUtensorMap mapY_lo,
                                                           const __grid_constant__ V2Params p) {
   using Cfg = V2Cfg<BN>;
   constexpr int SB = Cfg::B_SLOTS;
@@ -64,7 +67,8 @@ __global__ void __launch_bounds__(320, 1) conv_tc2_kernel(const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_base = smem_base + Cfg::A_BYTES;
-  const uint32_t bar_base = b_base + SB * Cfg::B_SLOT_BYTES;
+  const uint32_t stage_base = b_base + SB * Cfg::B_SLOT_BYTES;
+  const uint32_t bar_base = stage_base + Cfg::STAGE_BYTES;
   auto fullA = [&](int s) { return bar_base + 8u * s; };
   auto emptyA = [&](int s) { return bar_base + 8u * (V2_A_SLOTS + s); };
   auto fullB = [&](int s) { return bar_base + 8u * (2 * V2_A_SLOTS + s); };
@@ -217,6 +221,16 @@ __global__ void __launch_bounds__(320, 1) conv_tc2_kernel(const __grid_constant_
     const int i = e >> 2;              // accumulator (upper / lower tile of the super-tile)
     const int q = warp & 3;            // TMEM lane quarter accessible to this warp
     const int r = q * 32 + lane;
+    StoreCtx stc;
+    if (p.tma_store) {
+      stc.stage_hi = stage_base + (uint32_t)i * (2u * 128u * 64u);
+      stc.stage_lo = stc.stage_hi + 128u * 64u;
+      stc.row = r;
+      stc.bar = 1 + i;
+      stc.issuer = (e & 3) == 0 && lane == 0;
+      stc.map_hi = &mapY_hi;
+      stc.map_lo = &mapY_lo;
+    }
     int iw = 0;
     for (int work = blockIdx.x; work < p.total_work; work += gridDim.x, ++iw) {
       int img, h0, w0, n0;
@@ -225,9 +239,12 @@ __global__ void __launch_bounds__(320, 1) conv_tc2_kernel(const __grid_constant_
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN + i * BN);
       const int ty = r / p.TW, tx = r - ty * p.TW;
       const int gy = h0 + i * p.TH + ty, gx = w0 + tx;
+      stc.cx = w0;
+      stc.cy = h0 + i * p.TH;
       conv_epilogue<BN>(p.epi, taddr, gy < p.gh && gx < p.gw, img, gy, gx, n0, accFull(buf), (uint32_t)(iw >> 1) & 1u,
-                        accEmpty(buf), lane);
+                        accEmpty(buf), lane, stc);
     }
+    if (stc.issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -304,9 +321,23 @@ static int conv_tc2_bn(const tcv_conv_desc& d, cudaStream_t st) {
   p.idesc = instr_desc(BN, false);
   fill_epi(p.epi, d, p.dbg);
 
-  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo, mY_hi, mY_lo;
   const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(d.x);
   const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(d.w_tc);
+  p.tma_store = (d.y != nullptr && d.y_f32 == nullptr) ? 1 : 0;
+  {
+    // output view over the compute grid (also expresses the strided placement of a transposed-conv phase)
+    const __nv_bfloat16* y0 = reinterpret_cast<const __nv_bfloat16*>(d.y ? d.y : d.x);
+    const __nv_bfloat16* y = y0 + (d.y ? ((long long)d.oy_off * d.ow + d.ox_off) * d.cout : 0);
+    cuuint64_t dims[4] = {(cuuint64_t)d.cout, (cuuint64_t)d.gw, (cuuint64_t)d.gh, (cuuint64_t)d.n};
+    cuuint64_t str[3] = {(cuuint64_t)d.ox_mul * d.cout * 2, (cuuint64_t)d.oy_mul * d.ow * d.cout * 2,
+                         (cuuint64_t)d.oh * d.ow * d.cout * 2};
+    cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+    int rc = make_map(&mY_hi, y, 4, dims, str, box, 32);
+    if (rc) return rc;
+    rc = make_map(&mY_lo, d.y ? y + (long long)d.n * d.oh * d.ow * d.cout : y, 4, dims, str, box, 32);
+    if (rc) return rc;
+  }
   {
     cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)d.iw, (cuuint64_t)d.ih, (cuuint64_t)d.n};
     cuuint64_t str[3] = {(cuuint64_t)d.cin * 2, (cuuint64_t)d.iw * d.cin * 2, (cuuint64_t)d.x_img_stride * 2};
@@ -331,7 +362,7 @@ static int conv_tc2_bn(const tcv_conv_desc& d, cudaStream_t st) {
   TCV_CUDA(cudaGetDevice(&dev));
   TCV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.total_work < sms ? p.total_work : sms;
-  kern<<<grid, 320, Cfg::SMEM, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, p);
+  kern<<<grid, 320, Cfg::SMEM, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, mY_hi, mY_lo, p);
   return launched("conv_tc2_kernel");
 }
 

@@ -226,8 +226,15 @@ __global__ void __launch_bounds__(320, 1) conv_tc3_kernel(const __grid_constant_
     const int i = e >> 2;
     const int q = warp & 3;
     const int r = q * 32 + lane;
-    const uint32_t stage_hi = stage_base + (uint32_t)i * (2u * 128u * BN * 2u), stage_lo = stage_hi + 128u * BN * 2u;
-    const bool issuer = (e & 3) == 0 && lane == 0;
+    StoreCtx stc;
+    stc.stage_hi = stage_base + (uint32_t)i * (2u * 128u * BN * 2u);
+    stc.stage_lo = stc.stage_hi + 128u * BN * 2u;
+    stc.row = r;
+    stc.bar = 1 + i;
+    stc.issuer = (e & 3) == 0 && lane == 0;
+    stc.map_hi = &mapY_hi;
+    stc.map_lo = &mapY_lo;
+    const bool issuer = stc.issuer;
     int iw = 0;
     for (int work = blockIdx.x; work < p.total_work; work += gridDim.x, ++iw) {
       int img, h0, w0;
@@ -236,21 +243,10 @@ __global__ void __launch_bounds__(320, 1) conv_tc3_kernel(const __grid_constant_
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 4 * BN + i * 2 * BN);
       const int ty = r / V3_TW, tx = r - ty * V3_TW;
       const int gy = h0 + i * V3_TH + ty, gx = w0 + tx;
-      // the previous TMA store of this accumulator group must have finished READING the staging tile
-      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + i) : "memory");
+      stc.cx = w0;
+      stc.cy = h0 + i * V3_TH;
       conv_epilogue<BN>(p.epi, taddr, gy < p.gh && gx < p.gw, img, gy, gx, 0, accFull(buf), (uint32_t)(iw >> 1) & 1u,
-                        accEmpty(buf), lane, stage_hi, stage_lo, r, /*split_halves=*/true);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync %0, 128;" ::"r"(3 + i) : "memory");
-      if (issuer && !(p.epi.dbg & 2)) {
-        const int ry = h0 + i * V3_TH;
-        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                     ::"l"(&mapY_hi), "r"(stage_hi), "r"(0), "r"(w0), "r"(ry), "r"(img) : "memory");
-        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                     ::"l"(&mapY_lo), "r"(stage_lo), "r"(0), "r"(w0), "r"(ry), "r"(img) : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
+                        accEmpty(buf), lane, stc, /*split_halves=*/true);
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }

@@ -29,17 +29,27 @@ static inline void fill_epi(EpiParams& e, const tcv_conv_desc& d, int dbg) {
   e.dbg = dbg;
 }
 
+// TMA-store path: the 4 warps that drain one accumulator stage each 32-channel chunk in a 64B-swizzled
+// shared-memory tile (row r at stage + 64*r) and one elected thread hands it to the copy engine, so the output
+// leaves the SM as whole pixel rows instead of 32 scattered 16-byte pieces per store instruction.
+struct StoreCtx {
+  uint32_t stage_hi = 0, stage_lo = 0;   // smem tiles (128 rows x 64 B each); 0: plain global stores
+  int row = 0;                           // this thread's accumulator row
+  int bar = 0;                           // named barrier pair (bar, bar + 2) private to the 4 warps
+  bool issuer = false;                   // the one thread that issues / waits for the bulk stores
+  const CUtensorMap* map_hi = nullptr;   // output views {cout, gw, gh, n} of the hi / lo plane
+  const CUtensorMap* map_lo = nullptr;
+  int cx = 0, cy = 0;                    // tile origin in the compute grid
+};
+
 // gy/gx: position of this thread's pixel in the compute grid; in_grid: inside it.  The warp waits on
 // `acc_full` (parity given), drains its 32 TMEM lanes starting at `taddr`, and arrives on `acc_empty` as soon
 // as its last tcgen05.ld has completed.
 // split_halves: the accumulator is 2*BN columns wide and the two halves are summed first.
-// stage_hi/stage_lo != 0 (BN == 32 only): instead of scattered 16-byte global stores the bf16 planes of this
-// thread's row are written into 64B-swizzled shared-memory tiles (row r at stage + 64*r) for a TMA store.
 template <int BN>
 __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr, bool in_grid, int img, int gy, int gx,
                                               int n0, uint32_t acc_full, uint32_t full_parity, uint32_t acc_empty,
-                                              int lane, uint32_t stage_hi = 0, uint32_t stage_lo = 0, int row = 0,
-                                              bool split_halves = false) {
+                                              int lane, const StoreCtx& st = StoreCtx(), bool split_halves = false) {
   const bool valid = in_grid && !(p.dbg & 2);
   const int oy = gy * p.oy_mul + p.oy_off, ox = gx * p.ox_mul + p.ox_off;
   const long long oplane = (long long)p.n_imgs * p.oh * p.ow * p.cout;
@@ -100,58 +110,76 @@ __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr
     } else {
       fetch(c0 + 32, slot ^ 1);
     }
-    if (!valid) continue;
     float f[32];
+    if (valid) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-    if (p.s1) {
-      const float4* sv = reinterpret_cast<const float4*>(p.s1 + n0 + c0);
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      if (p.s1) {
+        const float4* sv = reinterpret_cast<const float4*>(p.s1 + n0 + c0);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 t = __ldg(sv + j);
-        f[4 * j] *= t.x; f[4 * j + 1] *= t.y; f[4 * j + 2] *= t.z; f[4 * j + 3] *= t.w;
-      }
-    }
-    if (p.b1) {
-      const float4* sv = reinterpret_cast<const float4*>(p.b1 + n0 + c0);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 t = __ldg(sv + j);
-        f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
-      }
-    }
-    if (has1) add_res(ra[slot], f);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
-    if (p.s2) {
-      const float4* sv = reinterpret_cast<const float4*>(p.s2 + n0 + c0);
-      const float4* bv = reinterpret_cast<const float4*>(p.b2 + n0 + c0);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 t = __ldg(sv + j), u = __ldg(bv + j);
-        f[4 * j] = f[4 * j] * t.x + u.x; f[4 * j + 1] = f[4 * j + 1] * t.y + u.y;
-        f[4 * j + 2] = f[4 * j + 2] * t.z + u.z; f[4 * j + 3] = f[4 * j + 3] * t.w + u.w;
-      }
-    }
-    if (has2) add_res(rb[slot], f);
-    if (stage_hi) {
-      const uint32_t sw = (uint32_t)((row >> 1) & 3);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        uint32_t h[4], l[4];
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(f[8 * k + 2 * m], h0, l0);
-          split_bf16(f[8 * k + 2 * m + 1], h1, l1);
-          h[m] = pack2(h0, h1);
-          l[m] = pack2(l0, l1);
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = __ldg(sv + j);
+          f[4 * j] *= t.x; f[4 * j + 1] *= t.y; f[4 * j + 2] *= t.z; f[4 * j + 3] *= t.w;
         }
-        const uint32_t off = (uint32_t)row * 64u + (((uint32_t)k ^ sw) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
       }
-    } else if (p.y && !((p.dbg & 16) && f[0] != 12345.678f)) {
+      if (p.b1) {
+        const float4* sv = reinterpret_cast<const float4*>(p.b1 + n0 + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = __ldg(sv + j);
+          f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+        }
+      }
+      if (has1) add_res(ra[slot], f);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+      if (p.s2) {
+        const float4* sv = reinterpret_cast<const float4*>(p.s2 + n0 + c0);
+        const float4* bv = reinterpret_cast<const float4*>(p.b2 + n0 + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = __ldg(sv + j), u = __ldg(bv + j);
+          f[4 * j] = f[4 * j] * t.x + u.x; f[4 * j + 1] = f[4 * j + 1] * t.y + u.y;
+          f[4 * j + 2] = f[4 * j + 2] * t.z + u.z; f[4 * j + 3] = f[4 * j + 3] * t.w + u.w;
+        }
+      }
+      if (has2) add_res(rb[slot], f);
+    }
+    if (st.stage_hi) {
+      // the previous bulk store of this group must have finished READING the staging tile
+      if (st.issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(st.bar) : "memory");
+      if (valid) {
+        const uint32_t sw = (uint32_t)((st.row >> 1) & 3);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(f[8 * k + 2 * m], h0, l0);
+            split_bf16(f[8 * k + 2 * m + 1], h1, l1);
+            h[m] = pack2(h0, h1);
+            l[m] = pack2(l0, l1);
+          }
+          const uint32_t off = (uint32_t)st.row * 64u + (((uint32_t)k ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st.stage_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st.stage_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(st.bar + 2) : "memory");
+      if (st.issuer && !(p.dbg & 2)) {
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                     ::"l"(st.map_hi), "r"(st.stage_hi), "r"(n0 + c0), "r"(st.cx), "r"(st.cy), "r"(img) : "memory");
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                     ::"l"(st.map_lo), "r"(st.stage_lo), "r"(n0 + c0), "r"(st.cx), "r"(st.cy), "r"(img) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      continue;
+    }
+    if (!valid) continue;
+    if (p.y && !((p.dbg & 16) && f[0] != 12345.678f)) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8) store8(p.y + obase + c0 + j, oplane, f + j);
     }

@@ -10,6 +10,7 @@ from helpers import fixture_sd
 H, W = int(sys.argv[1]), int(sys.argv[2])
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 graphs = os.environ.get("TCV_GRAPHS", "1") == "1"
+_cabi.lib().tcv_set_debug_flags(int(os.environ.get("TCV_DEBUG_FLAGS", "0")))
 m = tcvom_b200.EvalModel(model="vmn_gca", agg_window=7)
 m.NET.load_state_dict(fixture_sd(), strict=True)
 m = m.cuda().eval()
