@@ -66,6 +66,30 @@ __device__ __forceinline__ float load1(const __nv_bfloat16* hi, long long plane)
   return __bfloat162float(hi[0]) + __bfloat162float(hi[plane]);
 }
 
+// two floats -> packed bf16x2 hi word and lo word (one cvt.rn.bf16x2.f32 per plane)
+__device__ __forceinline__ void split2_bf16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float r0 = x0 - __uint_as_float(hi << 16), r1 = x1 - __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// activation applied to a register array with the (uniform) selector hoisted out of the element loop
+template <int N>
+__device__ __forceinline__ void apply_act_n(float* f, int act) {
+  if (act == TCV_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) f[j] = fmaxf(f[j], 0.f);
+  } else if (act == TCV_ACT_LEAKY02) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) f[j] = f[j] > 0.f ? f[j] : 0.2f * f[j];
+  } else if (act == TCV_ACT_TANH01) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) f[j] = (tanhf(f[j]) + 1.0f) * 0.5f;
+  }
+}
+
 __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }

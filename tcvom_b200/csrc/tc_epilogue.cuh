@@ -114,7 +114,7 @@ __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr
     if (valid) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-      if (p.s1) {
+      if (p.s1 && !(p.dbg & 128)) {
         const float4* sv = reinterpret_cast<const float4*>(p.s1 + n0 + c0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -122,7 +122,7 @@ __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr
           f[4 * j] *= t.x; f[4 * j + 1] *= t.y; f[4 * j + 2] *= t.z; f[4 * j + 3] *= t.w;
         }
       }
-      if (p.b1) {
+      if (p.b1 && !(p.dbg & 128)) {
         const float4* sv = reinterpret_cast<const float4*>(p.b1 + n0 + c0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -131,9 +131,8 @@ __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr
         }
       }
       if (has1) add_res(ra[slot], f);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
-      if (p.s2) {
+      apply_act_n<32>(f, p.act);
+      if (p.s2 && !(p.dbg & 128)) {
         const float4* sv = reinterpret_cast<const float4*>(p.s2 + n0 + c0);
         const float4* bv = reinterpret_cast<const float4*>(p.b2 + n0 + c0);
 #pragma unroll
@@ -155,13 +154,7 @@ __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr
         for (int k = 0; k < 4; ++k) {
           uint32_t h[4], l[4];
 #pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(f[8 * k + 2 * m], h0, l0);
-            split_bf16(f[8 * k + 2 * m + 1], h1, l1);
-            h[m] = pack2(h0, h1);
-            l[m] = pack2(l0, l1);
-          }
+          for (int m = 0; m < 4; ++m) split2_bf16(f[8 * k + 2 * m], f[8 * k + 2 * m + 1], h[m], l[m]);
           const uint32_t off = (uint32_t)st.row * 64u + (((uint32_t)k ^ sw) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st.stage_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st.stage_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
