@@ -97,13 +97,7 @@ __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
 __device__ __forceinline__ void store8(__nv_bfloat16* hi, long long plane, const float* f) {
   uint32_t h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __nv_bfloat16 h0, l0, h1, l1;
-    split_bf16(f[2 * i], h0, l0);
-    split_bf16(f[2 * i + 1], h1, l1);
-    h[i] = pack2(h0, h1);
-    l[i] = pack2(l0, l1);
-  }
+  for (int i = 0; i < 4; ++i) split2_bf16(f[2 * i], f[2 * i + 1], h[i], l[i]);
   *reinterpret_cast<uint4*>(hi) = make_uint4(h[0], h[1], h[2], h[3]);
   *reinterpret_cast<uint4*>(hi + plane) = make_uint4(l[0], l[1], l[2], l[3]);
 }
@@ -111,13 +105,7 @@ __device__ __forceinline__ void store8(__nv_bfloat16* hi, long long plane, const
 __device__ __forceinline__ void store4(__nv_bfloat16* hi, long long plane, const float* f) {
   uint32_t h[2], l[2];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    __nv_bfloat16 h0, l0, h1, l1;
-    split_bf16(f[2 * i], h0, l0);
-    split_bf16(f[2 * i + 1], h1, l1);
-    h[i] = pack2(h0, h1);
-    l[i] = pack2(l0, l1);
-  }
+  for (int i = 0; i < 2; ++i) split2_bf16(f[2 * i], f[2 * i + 1], h[i], l[i]);
   *reinterpret_cast<uint2*>(hi) = make_uint2(h[0], h[1]);
   *reinterpret_cast<uint2*>(hi + plane) = make_uint2(l[0], l[1]);
 }

@@ -148,8 +148,7 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const tcv_conv_desc d)
         for (int j = 0; j < COT; ++j) a[j] += load1(r + j, rplane);
       }
     }
-#pragma unroll
-    for (int j = 0; j < COT; ++j) a[j] = apply_act(a[j], d.act);
+    apply_act_n<COT>(a, d.act);
     if (d.s2) {
 #pragma unroll
       for (int j = 0; j < COT; ++j) a[j] = a[j] * d.s2[co0 + j] + d.b2[co0 + j];

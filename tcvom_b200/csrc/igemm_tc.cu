@@ -219,8 +219,7 @@ __global__ void __launch_bounds__(320) igemm_tc_kernel(const __grid_constant__ C
             for (int k = 0; k < 8; ++k) f[j + k] += g[k];
           }
         }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+        apply_act_n<32>(f, p.act);
         if (p.s2) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = f[j] * __ldg(p.s2 + n0 + c0 + j) + __ldg(p.b2 + n0 + c0 + j);

@@ -114,20 +114,31 @@ __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr
     if (valid) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-      if (p.s1 && !(p.dbg & 128)) {
+      if (p.s1 && p.b1 && !(p.dbg & 128)) {           // BatchNorm affine: one FMA per element
         const float4* sv = reinterpret_cast<const float4*>(p.s1 + n0 + c0);
+        const float4* bv = reinterpret_cast<const float4*>(p.b1 + n0 + c0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 t = __ldg(sv + j);
-          f[4 * j] *= t.x; f[4 * j + 1] *= t.y; f[4 * j + 2] *= t.z; f[4 * j + 3] *= t.w;
+          const float4 t = __ldg(sv + j), u = __ldg(bv + j);
+          f[4 * j] = fmaf(f[4 * j], t.x, u.x); f[4 * j + 1] = fmaf(f[4 * j + 1], t.y, u.y);
+          f[4 * j + 2] = fmaf(f[4 * j + 2], t.z, u.z); f[4 * j + 3] = fmaf(f[4 * j + 3], t.w, u.w);
         }
-      }
-      if (p.b1 && !(p.dbg & 128)) {
-        const float4* sv = reinterpret_cast<const float4*>(p.b1 + n0 + c0);
+      } else if (!(p.dbg & 128)) {
+        if (p.s1) {
+          const float4* sv = reinterpret_cast<const float4*>(p.s1 + n0 + c0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 t = __ldg(sv + j);
-          f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = __ldg(sv + j);
+            f[4 * j] *= t.x; f[4 * j + 1] *= t.y; f[4 * j + 2] *= t.z; f[4 * j + 3] *= t.w;
+          }
+        }
+        if (p.b1) {
+          const float4* sv = reinterpret_cast<const float4*>(p.b1 + n0 + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = __ldg(sv + j);
+            f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+          }
         }
       }
       if (has1) add_res(ra[slot], f);
@@ -138,8 +149,8 @@ __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 t = __ldg(sv + j), u = __ldg(bv + j);
-          f[4 * j] = f[4 * j] * t.x + u.x; f[4 * j + 1] = f[4 * j + 1] * t.y + u.y;
-          f[4 * j + 2] = f[4 * j + 2] * t.z + u.z; f[4 * j + 3] = f[4 * j + 3] * t.w + u.w;
+          f[4 * j] = fmaf(f[4 * j], t.x, u.x); f[4 * j + 1] = fmaf(f[4 * j + 1], t.y, u.y);
+          f[4 * j + 2] = fmaf(f[4 * j + 2], t.z, u.z); f[4 * j + 3] = fmaf(f[4 * j + 3], t.w, u.w);
         }
       }
       if (has2) add_res(rb[slot], f);
