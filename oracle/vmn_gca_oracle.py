@@ -42,13 +42,51 @@ def sn_sigma(sd: SD, p: str) -> torch.Tensor:
     return sd[p + ".module.weight_u"].dot(w.reshape(h, -1).mv(sd[p + ".module.weight_v"]))
 
 
+class TrainMode:
+    """Context manager switching the primitives below to the reference's ``.train()`` semantics:
+    SpectralNorm runs one power-iteration step per call and stores u, v back into ``sd``
+    (GCA/ops.py:25-36,74-80); BatchNorm2d uses batch statistics and updates ``running_mean`` /
+    ``running_var`` / ``num_batches_tracked`` in ``sd`` (momentum 0.1).  ``sd`` values that are leaves with
+    ``requires_grad`` receive gradients through ordinary autograd (u, v are constants, like ``.data``)."""
+    active = False
+
+    def __enter__(self):
+        TrainMode.active = True
+        return self
+
+    def __exit__(self, *exc):
+        TrainMode.active = False
+        return False
+
+
 def sn_weight(sd: SD, p: str) -> torch.Tensor:
-    """Eval-mode SpectralNorm weight: W_bar / sigma -- GCA/ops.py:38-45,74-80."""
+    """SpectralNorm weight: W_bar / sigma.  Eval: stored u, v (GCA/ops.py:38-45,74-80); train
+    (``TrainMode``): one power iteration first, u/v updated in place (GCA/ops.py:25-36)."""
+    if TrainMode.active:
+        w = sd[p + ".module.weight_bar"]
+        u, v = sd[p + ".module.weight_u"], sd[p + ".module.weight_v"]
+        h = w.shape[0]
+        with torch.no_grad():
+            wm = w.detach().reshape(h, -1)
+            nv = wm.t().mv(u)
+            v = nv / (nv.norm() + 1e-12)
+            nu = wm.mv(v)
+            u = nu / (nu.norm() + 1e-12)
+            # rebind (like the reference's ``u.data = ...``): autograd keeps the tensors of earlier calls
+            sd[p + ".module.weight_u"], sd[p + ".module.weight_v"] = u, v
+        sigma = u.dot(w.reshape(h, -1).mv(v))
+        return w / sigma
     return sd[p + ".module.weight_bar"] / sn_sigma(sd, p)
 
 
 def bn(x: torch.Tensor, sd: SD, p: str) -> torch.Tensor:
-    """Eval-mode BatchNorm2d (running statistics)."""
+    """BatchNorm2d: running statistics in eval mode, batch statistics (+ running-stat update) under
+    ``TrainMode``."""
+    if TrainMode.active:
+        if p + ".num_batches_tracked" in sd:
+            sd[p + ".num_batches_tracked"] += 1
+        return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"],
+                            sd[p + ".weight"], sd[p + ".bias"], True, 0.1, BN_EPS)
     return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"],
                         sd[p + ".weight"], sd[p + ".bias"], False, 0.0, BN_EPS)
 
@@ -328,11 +366,16 @@ def train_preprocess(a, fg, bg, radii, eps=0.0):
     return dict(imgs=imgs, fgs=fgs, bgs=bgs, gts=gts, tris=onehot, trimask=trimask, x6=torch.cat([norm, onehot], 2))
 
 
-def full_vmd_forward(sd: SD, a, fg, bg, radii, window=7, att_thres=0.3, label_smooth=0.2, eps=0.0):
-    """FullModel_VMD.forward for vmn_gca with the network in eval mode -- models/model.py:258-357
-    (single_image_loss :94-127, L_att :285-323, _dtSSD :326-345).  Returns the reference's 12-list."""
+def full_vmd_forward(sd: SD, a, fg, bg, radii, window=7, att_thres=0.3, label_smooth=0.2, eps=0.0, train=False):
+    """FullModel_VMD.forward for vmn_gca -- models/model.py:258-357 (single_image_loss :94-127, L_att :285-323,
+    _dtSSD :326-345).  Returns the reference's 12-list.  ``train=False``: network in eval mode under no_grad
+    (pred_vmn.py:107-116); ``train=True``: ``.train()`` semantics with autograd enabled (train_ddp.py:52-65) --
+    ``sd`` is updated in place (u, v, running statistics) and its ``requires_grad`` leaves get gradients when
+    the caller backpropagates the returned losses."""
     with torch.no_grad():
         pp = train_preprocess(a, fg, bg, radii, eps)
+    import contextlib
+    with (TrainMode() if train else contextlib.nullcontext()), torch.set_grad_enabled(bool(train)):
         B, S = a.shape[:2]
         frames = [pp["x6"][:, i] for i in range(S)]
         masks = [pp["trimask"][:, i] for i in range(S)]

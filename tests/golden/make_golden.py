@@ -171,5 +171,54 @@ def main(only_train=False):
         print("train losses", [float(o) for o in out[:5]])
 
 
+LOSS_WEIGHTS = (1.0, 1.0, 1.0, 0.5, 0.25)     # train_ddp.py:61
+GRAD_STRIDE = 257                               # every 257th element of each flattened gradient is stored
+
+
+def grad_sample(g):
+    """whole tensor when small, else every GRAD_STRIDE-th element"""
+    f = g.detach().flatten()
+    return f if f.numel() <= 8192 else f[::GRAD_STRIDE]
+
+
+def train_step_golden(B=2, S=5, H=64, W=64):
+    """One reference training step (train_ddp.py:52-65 without the optimizer): FullModel_VMD in .train() mode,
+    loss = L_alpha + L_comp + L_grad + 0.5 L_dt + 0.25 L_att, backward.  Stores the losses, every gradient's
+    L2 norm / sum and a strided sample, and the state the forward mutates (spectral-norm u/v, BatchNorm
+    running statistics).  dilate_kernel is fixed so that no host RNG is involved."""
+    from helpers_golden import load_full
+    full = load_full()
+    tm = FullModel_VMD(model="vmn_gca", agg_window=7, dilate_kernel=3)
+    tm.NET.load_state_dict(full, strict=True)
+    tm.train()
+    aa, ff, bb = [], [], []
+    for b in range(B):
+        a, fg, bg = train_inputs(H, W, S=S, seed=31 + 10 * b)
+        aa.append(a); ff.append(fg); bb.append(bg)
+    a, fg, bg = np.concatenate(aa), np.concatenate(ff), np.concatenate(bb)
+    out = tm(torch.from_numpy(a).float(), torch.from_numpy(fg).float(), torch.from_numpy(bg).float())
+    loss = sum(wt * o.mean() for wt, o in zip(LOSS_WEIGHTS, out[:5]))
+    tm.zero_grad()
+    loss.backward()
+    res = dict(a=a, fg=fg, bg=bg, losses=np.array([float(o) for o in out[:5]], np.float64),
+               alphas=out[7].detach().numpy())
+    names = []
+    for n, p in tm.NET.named_parameters():
+        if not p.requires_grad:
+            continue
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        names.append(n)
+        res["gn:" + n] = np.array([float(g.double().norm()), float(g.double().sum())])
+        res["gs:" + n] = grad_sample(g).numpy().copy()
+    for k, v in tm.NET.state_dict().items():
+        if k.endswith(("weight_u", "weight_v", "running_mean", "running_var", "num_batches_tracked")):
+            res["st:" + k] = v.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "train_step_s5.npz"), **res)
+    print("train step losses", res["losses"], "params", len(names))
+
+
 if __name__ == "__main__":
-    main(only_train="--only-train" in sys.argv)
+    if "--train-step" in sys.argv:
+        train_step_golden()
+    else:
+        main(only_train="--only-train" in sys.argv)
