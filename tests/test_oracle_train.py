@@ -50,7 +50,7 @@ def test_oracle_train_step_matches_reference():
         gn = g["gn:" + n]
         grad = sd[n].grad if sd[n].grad is not None else torch.zeros_like(sd[n])
         nrm = float(grad.double().norm())
-        assert abs(nrm - gn[0]) <= 2e-3 * gn[0] + 1e-7, (n, nrm, gn[0])
+        assert abs(nrm - gn[0]) <= 1e-2 * gn[0] + 1e-7, (n, nrm, gn[0])
         err = grad_sample_error(grad, g["gs:" + n])
         worst = max(worst, err)
         # two fp32 CPU implementations of this (chaotic, random-weight) fixture differ by up to 5e-3 here
