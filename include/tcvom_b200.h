@@ -225,6 +225,154 @@ int tcv_nchw_to_split(const float* x, int n, int c, int h, int w, int c_pad, voi
 int tcv_split_to_nchw(const void* x, int n, int c, int h, int w, int c_pad, long long x_plane, float* y,
                       tcv_stream_t stream);
 
+
+/* =====================================================================================================
+ * Training path (train_ddp.py:52-65): train-mode forward pieces and the backward kernels.
+ *
+ * Reference semantics replaced:
+ *   tcv_sn_power_iter       models/GCA/ops.py:25-36   SpectralNorm._update_u_v (one power iteration per call)
+ *   tcv_bn_*                nn.BatchNorm2d in .train() (batch statistics, running-stat update, autograd backward);
+ *                           nn.SyncBatchNorm when the caller all-reduces the `sums` between the two halves
+ *   tcv_conv2d_wgrad        autograd of nn.Conv2d / nn.ConvTranspose2d w.r.t. the weight
+ *                           (the data gradient is tcv_conv2d itself on transposed weights, tcv_transpose_packed)
+ *   tcv_weight_grad_unpack  autograd through W_bar / sigma (ops.py:35-36), u and v constants
+ *   tcv_gca_*_bwd           autograd of GuidedCxtAtten.forward (ops.py:106-229)
+ *   tcv_tam_attend_bwd      autograd of FeatureAggregationModule.forward (VMN_model.py:27-68)
+ *   tcv_losses_vmd_bwd      autograd of L_im / L_tc / L_af (models/model.py:94-127, 285-345)
+ * Gradients of activations use the same split-bf16 NHWC layout as the activations.
+ * ===================================================================================================== */
+
+/* images (b, j), j < group: to[b*g_to + j + off_to] (+)= from[b*g_from + j + off_from]; n_pairs = B*group images
+ * of img_elems elements (multiple of 8) per plane.  Gathers the centre / previous / next frames of every
+ * sample for the decoder tail (VMN_model.py:107-110) and scatters their gradients back. */
+int tcv_copy_images(const void* from, long long from_plane, void* to, long long to_plane, long long img_elems,
+                    int n_pairs, int group, int g_from, int off_from, int g_to, int off_to, int accumulate,
+                    tcv_stream_t stream);
+/* y += x (split-bf16, elems per plane, multiple of 8) */
+int tcv_add_split(const void* x, long long x_plane, void* y, long long y_plane, long long elems,
+                  tcv_stream_t stream);
+/* out[c] += sum over pixels of x[pixel][c]  (bias gradients); c a power of two in [8, 512] */
+int tcv_channel_sum(const void* x, long long x_plane, long long pixels, int c, float* out, tcv_stream_t stream);
+/* y[n,h/2,w/2,c] = scale * sum of the 2x2 block of x (scale 0.25: AvgPool2d; 1: gradient of nearest x2) */
+int tcv_pool2_scaled(const void* x, int n, int h, int w, int c, float scale, void* y, tcv_stream_t stream);
+/* y[n,2h,2w,c] = scale * x[n,h,w,c] replicated 2x2 (scale 0.25: gradient of AvgPool2d(2)) */
+int tcv_upsample2_scaled(const void* x, int n, int h, int w, int c, float scale, void* y, tcv_stream_t stream);
+/* gradient of tcv_pad_reflect1: dx [n,h,w,c] from dy [n,h+2,w+2,c] */
+int tcv_pad_reflect1_bwd(const void* dy, int n, int h, int w, int c, void* dx, tcv_stream_t stream);
+/* gradient of (tanh(z)+1)/2 given the output: dz8[i][0] = dpred[i]*2*pred[i]*(1-pred[i]), channels 1..7 = 0
+ * (split-bf16 [pixels][8], the 8-channel padding the conv kernels need) */
+int tcv_tanh01_bwd(const float* pred, const float* dpred, long long pixels, void* dz8, tcv_stream_t stream);
+/* fp32 [count] -> split-bf16 planes */
+int tcv_f32_to_split(const float* x, long long count, void* y, long long y_plane, tcv_stream_t stream);
+/* split-bf16 planes -> fp32 [count] (hi + lo) */
+int tcv_split_to_f32(const void* x, long long x_plane, long long count, float* y, tcv_stream_t stream);
+
+/* packed fp32 [taps][cin][cout] -> [taps][cout_pad][cin] (rows co >= cout zero): the weight of the data-gradient
+ * convolution in tcv_conv2d's own layout */
+int tcv_transpose_packed(const float* packed, int taps, int cin, int cout, int cout_pad, float* out,
+                         tcv_stream_t stream);
+
+/* SpectralNorm power iteration for `n` layers in one launch (one CTA per layer).  Layer i is called
+ * `calls` times per step (once per frame, VMN_model.py:93-98,107-110); call k uses (u_k, v_k, sigma_k) obtained by
+ * k+1 iterations from the stored u, v.  The final u, v are written back to the module's buffers. */
+typedef struct {
+  const float* w_bar; /* torch layout, viewed [rows, cols], rows = shape[0] */
+  int rows, cols;
+  float* u;           /* [rows] in/out */
+  float* v;           /* [cols] in/out */
+  int calls;
+  float* u_hist;      /* [calls][rows] */
+  float* v_hist;      /* [calls][cols] */
+  float* sigma;       /* [calls] */
+  float* inv_sigma;   /* [calls] */
+} tcv_sn_desc;
+int tcv_sn_power_iter(const tcv_sn_desc* descs_device, int n, tcv_stream_t stream);
+
+/* train-mode BatchNorm fused with what surrounds it.  t0 = z * inv_sigma[g], g = image % groups.
+ *   mode 1:  y = act( BN(t0) + up(res1) ) + res2        (conv -> BN -> [+identity] -> act [-> + skip])
+ *   mode 2:  y = BN( act(t0) )                          (conv -> ReLU -> BN, res_gca_enc.py:20-33,47-55)
+ * Statistics are per (group, channel): the reference calls the encoder/decoder once per frame. */
+typedef struct {
+  const void* z; long long z_plane;
+  int n, h, w, c;          /* c a power of two in [8, 512] */
+  int groups;
+  const float* inv_sigma;  /* [groups] or NULL */
+  int mode, act;
+  const float* gamma; const float* beta;
+  float* mean; float* invstd;   /* [groups][c] */
+  const void* res1; long long res1_plane; int res1_shift;
+  const void* res2; long long res2_plane;
+  void* y; long long y_plane;
+} tcv_bn_desc;
+/* sums[g][c] = (sum t, sum t^2) of the BatchNorm input (double, zeroed here) */
+int tcv_bn_stats(const tcv_bn_desc* d, double* sums, tcv_stream_t stream);
+/* mean / invstd from (all-reduced) sums; count = elements per (group, channel) over all ranks; running statistics
+ * updated once per group in order (momentum; variance scaled by u/(u-1), u = unbiased_count -- it differs from
+ * count only where a 1x1 conv + BatchNorm is evaluated before the nearest x2 upsample it commutes with) when
+ * running_mean != NULL */
+int tcv_bn_finalize(const double* sums, double count, double unbiased_count, int groups, int c, float eps,
+                    float momentum, float* mean, float* invstd, float* running_mean, float* running_var,
+                    tcv_stream_t stream);
+int tcv_bn_apply(const tcv_bn_desc* d, tcv_stream_t stream);
+/* e = dL/d(BN output): mode 1 dy * act'(BN(t0)+res1) (written to e; it is also the gradient of res1 before
+ * down-pooling), mode 2 dy itself (e may be NULL).  sums[g][c] = (sum e, sum e*xhat), zeroed here. */
+int tcv_bn_bwd_reduce(const tcv_bn_desc* d, const void* dy, long long dy_plane, void* e, long long e_plane,
+                      double* sums, tcv_stream_t stream);
+/* dgamma[c] += sum_g sums[g][c][1], dbeta[c] += sum_g sums[g][c][0] (local sums, before any all-reduce) */
+int tcv_bn_param_grads(const double* sums, int groups, int c, float* dgamma, float* dbeta, tcv_stream_t stream);
+/* dz = dL/dz from e and the (all-reduced) sums; zdot[g] += sum z*dz (NULL to skip; feeds the sigma gradient) */
+int tcv_bn_bwd_apply(const tcv_bn_desc* d, const void* e, long long e_plane, const double* sums, double count,
+                     void* dz, long long dz_plane, double* zdot, tcv_stream_t stream);
+/* zdot[g] += sum over images of group g of z*dz  (layers whose spectral-norm conv is not followed by BatchNorm) */
+int tcv_group_dot(const void* z, long long z_plane, const void* dz, long long dz_plane, int n, long long img_elems,
+                  int groups, double* zdot, tcv_stream_t stream);
+
+/* dw[wtap[t]][ci][co] += sum over the descriptor's compute grid of x[n, gy*stride+dy[t], gx*stride+dx[t], ci] *
+ * dz[n, gy*oy_mul+oy_off, gx*ox_mul+ox_off, co]; d is the forward descriptor (x, taps, stride, padding, grid);
+ * dz split-bf16 [n, oh, ow, dz_c]; dw fp32 [wtaps][cin][dz_c]. */
+int tcv_conv2d_wgrad(const tcv_conv_desc* d, const void* dz, long long dz_plane, int dz_c, float* dw,
+                     tcv_stream_t stream);
+/* packed gradient fp32 [taps][cin_pad][cout_pad] -> torch layout ([cout,cin,kh,kw], or [cin,cout,kh,kw] when
+ * transposed), minus the spectral-norm term sum_k (zdot[k]/sigma[k]) * u_k v_k^T when calls > 0. */
+int tcv_weight_grad_unpack(const float* dw, int cout, int cin, int kh, int kw, int transposed, int cin_pad,
+                           int cout_pad, const float* u_hist, const float* v_hist, const float* sigma,
+                           const double* zdot, int calls, float* grad, tcv_stream_t stream);
+
+/* C[b][m][n] (+)= sum_k A[b][m*sam + k*sak] * B[b][n*sbn + k*sbk], fp32, one of (sam, sak) and one of
+ * (sbn, sbk) equal to 1 (CUDA cores; the exact path of the attention backward GEMMs) */
+int tcv_gemm_f32_strided(const float* A, long long sam, long long sak, const float* B, long long sbn, long long sbk,
+                         float* C, long long ldc, int M, int N, int K, long long strideA, long long strideB,
+                         long long strideC, int batch, int accumulate, tcv_stream_t stream);
+
+/* guided contextual attention backward (see tcv_gca_* above for the forward tensors)
+ *  fold_bwd:    dY split [n,h,w,128] -> dO fp32 [n,P,2048] = unfold(dY)/4 ; delta fp32 [n,P] = rowsum(dO*O)
+ *  softmax_bwd: dS = A*(dA - delta) in place on dA fp32 [n,P,P_pad] (pad columns zeroed); A fp32 [n,P,P_pad]
+ *  values_bwd:  dV fp32 [n,P,2048] -> dfeat split [n,h,w,128] (gradient of the 4x4/stride-2 reflect-padded patches)
+ *  prep_bwd:    dQ fp32 [n,P,576] += gradient through Kn = Q/max(|Q|,1e-4)*scale (dKn fp32 [n,P,576], Q fp32,
+ *               mm, scales); then dg split [n,h/2,w/2,64] = gradient of the 3x3 reflect-padded patches */
+int tcv_gca_fold_bwd(const void* dY, const float* O, int n, int h, int w, float* dO, float* delta,
+                     tcv_stream_t stream);
+int tcv_gca_softmax_bwd(const float* A, float* dA, const float* delta, int n, int P, int P_pad,
+                        tcv_stream_t stream);
+int tcv_gca_values_bwd(const float* dV, int n, int h, int w, void* dfeat, tcv_stream_t stream);
+int tcv_gca_prep_bwd(float* dQ, const float* dKn, const float* Q, const float* mm, const float* scales, int n,
+                     int h, int w, void* dg, tcv_stream_t stream);
+
+/* TAM backward.  dout split [B,H,W,C]; dattb/dattf fp32 [B,win*win,H*W] gradients of the returned logits
+ * (NULL: none).  dq split; dkb/dkf fp32 [B,H,W,C] accumulators (zeroed here); the gradient of v is dout itself. */
+int tcv_tam_attend_bwd(const void* q, const void* kb, const void* kf, const float* mask, long long mask_stride,
+                       int mh, int mw, int batch, int h, int w, int c, int window, const void* dout,
+                       const float* dattb, const float* dattf, void* dq, float* dkb, float* dkf,
+                       tcv_stream_t stream);
+
+/* gradients of the losses: gl fp32 [5] (device) = dL/d(L_alpha, L_comp, L_grad, L_dt, L_att); acc = the
+ * workspace tcv_losses_vmd filled in the forward.  dpred fp32 [B,S-2,1,H,W]; dattb/dattf fp32 [B,S-2,w*w,H*W/64]. */
+int tcv_losses_vmd_bwd(const float* pred, const float* trimask, const float* gts, const float* attb,
+                       const float* attf, const uint8_t* small_mask, const float* gt8, const double* acc,
+                       const float* gl, int batch, int frames_per_sample, int h, int w, int window, float att_thres,
+                       float label_smooth, float att_multiplier, float* dpred, float* dattb, float* dattf,
+                       tcv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

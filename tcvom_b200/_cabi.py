@@ -38,6 +38,31 @@ class ConvDesc(C.Structure):
     ]
 
 
+class BnDesc(C.Structure):
+    """Mirror of ``tcv_bn_desc`` (train-mode BatchNorm fused with 1/sigma, activation and residuals)."""
+    _fields_ = [
+        ("z", c_void_p), ("z_plane", c_ll),
+        ("n", c_int), ("h", c_int), ("w", c_int), ("c", c_int),
+        ("groups", c_int), ("inv_sigma", c_void_p),
+        ("mode", c_int), ("act", c_int),
+        ("gamma", c_void_p), ("beta", c_void_p), ("mean", c_void_p), ("invstd", c_void_p),
+        ("res1", c_void_p), ("res1_plane", c_ll), ("res1_shift", c_int),
+        ("res2", c_void_p), ("res2_plane", c_ll),
+        ("y", c_void_p), ("y_plane", c_ll),
+    ]
+
+
+class SnDesc(C.Structure):
+    """Mirror of ``tcv_sn_desc`` (one spectral-norm layer of the batched power iteration)."""
+    _fields_ = [
+        ("w_bar", c_void_p), ("rows", c_int), ("cols", c_int), ("u", c_void_p), ("v", c_void_p),
+        ("calls", c_int), ("u_hist", c_void_p), ("v_hist", c_void_p), ("sigma", c_void_p),
+        ("inv_sigma", c_void_p),
+    ]
+
+
+c_double = C.c_double
+
 # name -> (restype, argtypes); every symbol include/tcvom_b200.h declares
 SIGNATURES = {
     "tcv_version": (c_int, []),
@@ -80,6 +105,41 @@ SIGNATURES = {
                                c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tcv_nchw_to_split": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
     "tcv_split_to_nchw": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_void_p, c_void_p]),
+    # ---- training path
+    "tcv_copy_images": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                c_void_p]),
+    "tcv_add_split": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_ll, c_void_p]),
+    "tcv_channel_sum": (c_int, [c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p]),
+    "tcv_pool2_scaled": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "tcv_upsample2_scaled": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "tcv_pad_reflect1_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_tanh01_bwd": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_void_p]),
+    "tcv_f32_to_split": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p]),
+    "tcv_split_to_f32": (c_int, [c_void_p, c_ll, c_ll, c_void_p, c_void_p]),
+    "tcv_transpose_packed": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_sn_power_iter": (c_int, [c_void_p, c_int, c_void_p]),
+    "tcv_bn_stats": (c_int, [C.POINTER(BnDesc), c_void_p, c_void_p]),
+    "tcv_bn_finalize": (c_int, [c_void_p, c_double, c_double, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p]),
+    "tcv_bn_apply": (c_int, [C.POINTER(BnDesc), c_void_p]),
+    "tcv_bn_bwd_reduce": (c_int, [C.POINTER(BnDesc), c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p]),
+    "tcv_bn_param_grads": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "tcv_bn_bwd_apply": (c_int, [C.POINTER(BnDesc), c_void_p, c_ll, c_void_p, c_double, c_void_p, c_ll, c_void_p,
+                                 c_void_p]),
+    "tcv_group_dot": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_ll, c_int, c_void_p, c_void_p]),
+    "tcv_conv2d_wgrad": (c_int, [C.POINTER(ConvDesc), c_void_p, c_ll, c_int, c_void_p, c_void_p]),
+    "tcv_weight_grad_unpack": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "tcv_gemm_f32_strided": (c_int, [c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll, c_void_p, c_ll, c_int, c_int, c_int,
+                                     c_ll, c_ll, c_ll, c_int, c_int, c_void_p]),
+    "tcv_gca_fold_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "tcv_gca_softmax_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "tcv_gca_values_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_gca_prep_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                 c_void_p]),
+    "tcv_tam_attend_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int,
+                                   c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tcv_losses_vmd_bwd": (c_int, [c_void_p] * 9 + [c_int] * 5 + [c_float] * 3 + [c_void_p] * 4),
 }
 
 _lib = None

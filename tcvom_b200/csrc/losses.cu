@@ -226,6 +226,89 @@ __global__ void loss_finalize_kernel(const double* __restrict__ acc, int B, int 
   out[4] = (float)(laf / (S - 2)) * mult;
 }
 
+
+// ---- loss gradients (autograd of L_im / L_tc / L_af) ----------------------------------------------------
+__device__ __forceinline__ float sgn(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
+__device__ __forceinline__ double safe_count(const double* acc, int S, int c, int B, int h, int w) {
+  return fmin(fmax(acc[S + c], 1.001e-5), (double)B * h * w + 1.0);
+}
+
+// dpred[b, ci, p] for the inner frame s = ci + 1 (only unknown-region pixels carry gradient, model.py:102)
+__global__ void loss_im_tc_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ trimask,
+                                      const float* __restrict__ gts, const double* __restrict__ acc,
+                                      const float* __restrict__ gl, int B, int S, int h, int w,
+                                      float* __restrict__ dpred) {
+  const long long hw = (long long)h * w;
+  const long long total = (long long)B * (S - 2) * hw;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long p = i % hw;
+  const int ci = (int)((i / hw) % (S - 2));
+  const int b = (int)(i / (hw * (S - 2)));
+  const int s = ci + 1;
+  const long long f = ((long long)b * S + s) * hw + p;
+  const float m = trimask[f];
+  float grad = 0.f;
+  if (m != 0.f) {
+    const float pr = pred[i], g = gts[f];
+    const float g_alpha = gl[0], g_dt = gl[3];
+    grad = g_alpha * sgn(pr - g) * m / (float)(safe_count(acc, S, s, B, h, w) * (S - 2));
+    if (S >= 5 && pr >= 0.f && pr <= 1.f) {
+      const float al = fminf(fmaxf(pr, 0.f), 1.f);
+      if (s <= S - 3) {                                   // pair (s, s+1), masked by frame s
+        const float m1 = trimask[f + hw], g1 = gts[f + hw];
+        const float al1 = fminf(fmaxf(m1 != 0.f ? pred[i + hw] : g1, 0.f), 1.f);
+        const float D = (al - al1) - (g - g1);
+        grad += g_dt * sgn(D) * m / (float)(safe_count(acc, S, s, B, h, w) * (S - 3));
+      }
+      if (s - 1 >= 1) {                                   // pair (s-1, s), masked by frame s-1
+        const float m0 = trimask[f - hw], g0 = gts[f - hw];
+        if (m0 != 0.f) {
+          const float al0 = fminf(fmaxf(pred[i - hw], 0.f), 1.f);   // m0 != 0: refine = pred
+          const float D = (al0 - al) - (g0 - g);
+          grad -= g_dt * sgn(D) * m0 / (float)(safe_count(acc, S, s - 1, B, h, w) * (S - 3));
+        }
+      }
+    }
+  }
+  dpred[i] = grad;
+}
+
+__global__ void loss_af_bwd_kernel(const float* __restrict__ attb, const float* __restrict__ attf,
+                                   const uint8_t* __restrict__ small_mask, const float* __restrict__ gt8,
+                                   const double* __restrict__ acc, const float* __restrict__ gl, int B, int S, int h8,
+                                   int w8, int window, float thres, float smooth, float mult,
+                                   float* __restrict__ dattb, float* __restrict__ dattf) {
+  const int N8 = h8 * w8, w2 = window * window, r = window / 2;
+  const long long total = (long long)B * (S - 2) * w2 * N8;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int n = (int)(i % N8);
+  const int j = (int)((i / N8) % w2);
+  const int ci = (int)((i / ((long long)N8 * w2)) % (S - 2));
+  const int b = (int)(i / ((long long)N8 * w2 * (S - 2)));
+  const int s = ci + 1;
+  float gb = 0.f, gf = 0.f;
+  if (small_mask[((long long)b * (S - 2) + ci) * N8 + n]) {
+    const int y = n / w8, x = n - y * w8;
+    const int yy = y + j / window - r, xx = x + j % window - r;
+    const bool in = yy >= 0 && yy < h8 && xx >= 0 && xx < w8;
+    const float* g = gt8 + (long long)b * S * N8;
+    const float cg = g[(long long)s * N8 + n];
+    const float bgv = in ? g[(long long)(s - 1) * N8 + yy * w8 + xx] : 0.f;
+    const float fgv = in ? g[(long long)(s + 1) * N8 + yy * w8 + xx] : 0.f;
+    const float tb = fabsf(cg - bgv) < thres ? 1.0f - smooth : 0.f;
+    const float tf = fabsf(cg - fgv) < thres ? 1.0f - smooth : 0.f;
+    const float xb = attb[i], xf = attf[i];
+    // d/dx BCEWithLogits(mean over u*w2 elements) = (sigmoid(x) - t) / (u*w2); L_att = mean_c (Lb + Lf)/2 * mult
+    const float k = gl[4] * mult * 0.5f / (float)(acc[5 * S + s] * w2 * (S - 2));
+    gb = k * (1.0f / (1.0f + expf(-xb)) - tb);
+    gf = k * (1.0f / (1.0f + expf(-xf)) - tf);
+  }
+  dattb[i] = gb;
+  dattf[i] = gf;
+}
+
 }  // namespace tcv
 
 using namespace tcv;
@@ -280,6 +363,29 @@ int tcv_losses_vmd(const float* pred, const float* trimask, const float* gts, co
   }
   loss_finalize_kernel<<<1, 32, 0, S(stream)>>>(acc, batch, Sn, h, w, window * window, att_multiplier, losses);
   return launched("loss_finalize_kernel");
+}
+
+int tcv_losses_vmd_bwd(const float* pred, const float* trimask, const float* gts, const float* attb,
+                       const float* attf, const uint8_t* small_mask, const float* gt8, const double* acc,
+                       const float* gl, int batch, int frames_per_sample, int h, int w, int window, float att_thres,
+                       float label_smooth, float att_multiplier, float* dpred, float* dattb, float* dattf,
+                       tcv_stream_t stream) {
+  TCV_REQUIRE(pred && trimask && gts && acc && gl && dpred, "losses_vmd_bwd: null pointer");
+  TCV_REQUIRE(frames_per_sample >= 3, "losses_vmd_bwd: need S >= 3");
+  const int Sn = frames_per_sample;
+  const long long total = (long long)batch * (Sn - 2) * h * w;
+  loss_im_tc_bwd_kernel<<<nblocks(total), 256, 0, S(stream)>>>(pred, trimask, gts, acc, gl, batch, Sn, h, w, dpred);
+  int rc = launched("loss_im_tc_bwd_kernel");
+  if (rc) return rc;
+  if (attb && attf && small_mask && dattb && dattf) {
+    TCV_REQUIRE(gt8, "losses_vmd_bwd: gt8 workspace of the forward required");
+    const int h8 = h / 8, w8 = w / 8;
+    const long long ta = (long long)batch * (Sn - 2) * window * window * h8 * w8;
+    loss_af_bwd_kernel<<<nblocks(ta), 256, 0, S(stream)>>>(attb, attf, small_mask, gt8, acc, gl, batch, Sn, h8, w8,
+                                                          window, att_thres, label_smooth, att_multiplier, dattb, dattf);
+    rc = launched("loss_af_bwd_kernel");
+  }
+  return rc;
 }
 
 }  // extern "C"

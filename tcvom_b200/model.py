@@ -22,6 +22,7 @@ from torch import nn
 
 from . import _cabi
 from .engine import Act, GcaVmnEngine, Plan, named_tensors
+from .train_engine import TrainEngine
 from .modules import GCADecoderParams, GCAEncoderParams, GuidedCxtAttenParams, TAMParams
 
 
@@ -52,6 +53,46 @@ def _engine_for(module: nn.Module, window: int) -> GcaVmnEngine:
             eng = table[dev.index] = GcaVmnEngine(window)
     eng.refresh_weights(module)
     return eng
+
+
+def _train_engine_for(module: nn.Module, window: int) -> TrainEngine:
+    """One training engine per (module, device); weights are re-packed from the parameters on every step."""
+    dev = next(iter(named_tensors(module).values())).device
+    if dev.type != "cuda":
+        raise RuntimeError("tcvom_b200: the module must live on a CUDA device (no CPU fallback)")
+    with _ENGINE_LOCK:
+        table = module.__dict__.get("_train_engines")
+        if table is None:
+            table = module.__dict__["_train_engines"] = {}
+        eng = table.get(dev.index)
+        if eng is None:
+            eng = table[dev.index] = TrainEngine(window)
+    eng.refresh_weights(module)
+    sync = any(isinstance(m, nn.SyncBatchNorm) for m in module.modules())
+    dist = torch.distributed
+    eng.sync_bn = bool(sync and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+    eng.world = dist.get_world_size() if eng.sync_bn else 1
+    return eng
+
+
+class _TrainStepFn(torch.autograd.Function):
+    """Autograd boundary of the native training step: forward = train-mode network + losses on the sm_100a
+    kernels, backward = the native tape; the trainable parameters are the differentiable inputs, so
+    ``loss.backward()`` / DistributedDataParallel see ordinary ``.grad`` accumulation (train_ddp.py:63-64)."""
+
+    @staticmethod
+    def forward(ctx, wrapper, a, fg, bg, *params):
+        st = wrapper._train_forward(a, fg, bg)
+        ctx.wrapper, ctx.st = wrapper, st
+        vis = tuple(st[k] for k in ("imgs", "tris_vis", "alphas", "comps", "gts", "fgs", "bgs"))
+        ctx.mark_non_differentiable(*vis)
+        return (st["losses"],) + vis
+
+    @staticmethod
+    def backward(ctx, gl, *unused):
+        grads = ctx.wrapper._train_backward(ctx.st, gl)
+        ctx.st = None
+        return (None, None, None, None) + tuple(grads)
 
 
 class _OpEngineMixin:
@@ -404,9 +445,87 @@ class FullModel_VMD(nn.Module):
 
     run_plan = EvalModel.run_plan
 
+    # -- training step (train_ddp.py:52-65) --------------------------------------------
+    def _train_forward(self, a, fg, bg) -> dict:
+        """Train-mode forward on the native kernels: preprocess, VMN (batch-statistics BatchNorm, SpectralNorm
+        power iteration), losses.  Returns the tensors the backward needs plus the visualisation outputs."""
+        if self.method != 'gca':
+            raise NotImplementedError("tcvom_b200: training is built for vmn_gca only")
+        if getattr(self.NET, "freeze_backbone", False):
+            raise NotImplementedError("tcvom_b200: freeze_backbone training (pretrain_ddp.py) is not built")
+        B, S = a.shape[:2]
+        H, W = a.shape[-2:]
+        dev = a.device
+        eng = _train_engine_for(self.NET, int(self.window))
+        f32 = torch.float32
+        rad = [int(torch.randint(0, 26, size=())) if self.DILATION_KERNEL is None else int(self.DILATION_KERNEL)
+               for _ in range(B)]
+        radii = torch.tensor(rad, dtype=torch.int32).to(dev)
+        a = a.contiguous().float(); fg = fg.contiguous().float(); bg = bg.contiguous().float()
+        x8 = Act.empty(B * S, H, W, 8, dev)
+        mk = lambda c: torch.empty((B, S, c, H, W), dtype=f32, device=dev)
+        trimask, gts, tris_vis = mk(1), mk(1), mk(1)
+        fgs, bgs, imgs = mk(3), mk(3), mk(3)
+        tmp = torch.empty((2 * B * S * H * W,), dtype=torch.uint8, device=dev)
+        eng._call("tcv_preprocess_train", a.data_ptr(), fg.data_ptr(), bg.data_ptr(), B, S, H, W, float(self.EPS),
+                  radii.data_ptr(), x8.ptr, trimask.data_ptr(), gts.data_ptr(), fgs.data_ptr(), bgs.data_ptr(),
+                  imgs.data_ptr(), tris_vis.data_ptr(), tmp.data_ptr())
+        out = eng.train_forward(x8, trimask, B, S, H, W)
+        alphas, comps = mk(1), mk(3)
+        gt8 = torch.empty((B, S, H // 8, W // 8), dtype=f32, device=dev)
+        acc = torch.empty((6 * S,), dtype=torch.float64, device=dev)
+        losses = torch.empty((5,), dtype=f32, device=dev)
+        att = self._with_att
+        mult = float(self.FBA_L_ATT_MULTIPLIER if self.method == 'fba' else 1)
+        eng._call("tcv_losses_vmd", out["pred"].data_ptr(), trimask.data_ptr(), gts.data_ptr(), fgs.data_ptr(),
+                  bgs.data_ptr(), out["attb"].data_ptr() if att else None, out["attf"].data_ptr() if att else None,
+                  out["small_mask"].data_ptr() if att else None, B, S, H, W, int(self.window), float(self.att_thres),
+                  float(self.label_smooth), mult, alphas.data_ptr(), comps.data_ptr(), gt8.data_ptr(), acc.data_ptr(),
+                  losses.data_ptr())
+        return dict(eng=eng, B=B, S=S, H=H, W=W, losses=losses, imgs=imgs, tris_vis=tris_vis, alphas=alphas,
+                    comps=comps, gts=gts, fgs=fgs, bgs=bgs, trimask=trimask, gt8=gt8, acc=acc, mult=mult, **out)
+
+    def _train_backward(self, st: dict, gl: torch.Tensor):
+        eng: TrainEngine = st["eng"]
+        B, S, H, W = st["B"], st["S"], st["H"], st["W"]
+        att = self._with_att
+        gl = gl.contiguous().float()
+        dpred = torch.empty_like(st["pred"])
+        dattb = torch.empty_like(st["attb"]) if att else None
+        dattf = torch.empty_like(st["attf"]) if att else None
+        eng._call("tcv_losses_vmd_bwd", st["pred"].data_ptr(), st["trimask"].data_ptr(), st["gts"].data_ptr(),
+                  st["attb"].data_ptr() if att else None, st["attf"].data_ptr() if att else None,
+                  st["small_mask"].data_ptr() if att else None, st["gt8"].data_ptr(), st["acc"].data_ptr(),
+                  gl.data_ptr(), B, S, H, W, int(self.window), float(self.att_thres), float(self.label_smooth),
+                  st["mult"], dpred.data_ptr(), dattb.data_ptr() if att else None, dattf.data_ptr() if att else None)
+        eng.train_backward(dpred, dattb, dattf)
+        return eng.collect_grads(self._train_param_names)
+
+    def _train_step(self, a, fg, bg):
+        named = named_tensors(self.NET)
+        names = [n for n, t in named.items() if isinstance(t, nn.Parameter) and t.requires_grad]
+        self.__dict__["_train_param_names"] = names
+        params = [named[n] for n in names]
+        if torch.is_grad_enabled():
+            res = _TrainStepFn.apply(self, a, fg, bg, *params)
+            L, vis = res[0], list(res[1:])
+        else:
+            st = self._train_forward(a, fg, bg)
+            st["eng"].tape = []
+            L = st["losses"]
+            vis = [st[k] for k in ("imgs", "tris_vis", "alphas", "comps", "gts", "fgs", "bgs")]
+        outs = [L[0], L[1], L[2]]
+        if self._with_att:
+            outs += [L[3], L[4]]
+        return outs + vis
+
     def forward(self, a, fg, bg, wb=None, wf=None):
         _require_cuda(a, "a")
-        self.NET._check_mode()
+        if self.NET.training:
+            if a.shape[-2] % 32 or a.shape[-1] % 32:
+                raise ValueError("tcvom_b200: H and W must be multiples of 32")
+            assert a.shape[1] >= 3
+            return self._train_step(a, fg, bg)
         B, S = a.shape[:2]
         H, W = a.shape[-2:]
         assert S >= 3

@@ -1,0 +1,83 @@
+"""GPU: the native training path (train-mode forward + backward kernels behind the C ABI).
+
+Operator level: every tape operator of tcvom_b200.train_engine against torch autograd / the CPU oracle on
+seeded inputs (tools/train_check.py holds the checks).  Step level: one FullModel_VMD training step against one
+step of the UNMODIFIED reference (tests/golden/train_step_s5.npz): losses, alphas, all 228 gradients, the
+spectral-norm u/v and BatchNorm running statistics the forward mutates."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tc():
+    import train_check
+    return train_check
+
+
+@pytest.fixture(scope="module")
+def model(tc):
+    return tc.make_net()
+
+
+def test_sn_power_iteration(tc, model):
+    assert tc.check_sn(model)
+
+
+CONV_CASES = [
+    ("3x3 s1 64->64 bn relu +res1", "encoder.layer1.0.conv2", "encoder.layer1.0.bn2", 64, (16, 24), dict(act=1, res1=True)),
+    ("3x3 s2 64->128 bn relu", "encoder.layer2.0.conv1", "encoder.layer2.0.bn1", 64, (16, 24), dict(stride=2, act=1)),
+    ("1x1 64->128 bn", "encoder.layer2.0.downsample.1", "encoder.layer2.0.downsample.2", 64, (8, 12), dict()),
+    ("3x3 s1 32->32 bn relu", "encoder.conv2", "encoder.bn2", 32, (32, 32), dict(act=1)),
+    ("3x3 s2 32->64 bn relu", "encoder.conv3", "encoder.bn3", 32, (32, 32), dict(stride=2, act=1)),
+    ("shortcut relu->bn", "encoder.shortcut.3.0", "encoder.shortcut.3.2", 128, (8, 8), dict(mode=2, act=1)),
+    ("guidance 16->32 reflect s2", "encoder.guidance_head.5", "encoder.guidance_head.7", 16, (16, 16),
+     dict(stride=2, mode=2, act=1, reflect="prepadded")),
+    ("guidance 32->128 reflect s2", "encoder.guidance_head.9", "encoder.guidance_head.11", 32, (16, 16),
+     dict(stride=2, mode=2, act=1, reflect="prepadded")),
+    ("3x3 s1 512->512 +res1", "encoder.layer_bottleneck.1.conv2", "encoder.layer_bottleneck.1.bn2", 512, (4, 4),
+     dict(act=1, res1=True)),
+    ("deconv 256->256", "decoder.layer2.0.conv1", "decoder.layer2.0.bn1", 256, (4, 6), dict(act=2, deconv=True)),
+    ("3x3 256->128 +res1 +res2", "decoder.layer2.0.conv2", "decoder.layer2.0.bn2", 256, (8, 12),
+     dict(act=2, res1=True, res2=True)),
+    ("deconv 32->32 +res2", "decoder.conv1", "decoder.bn1", 32, (16, 16), dict(act=2, deconv=True, res2=True)),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_bn_forward_backward(tc, model, case):
+    name, wkey, bnkey, cin, hw, kw = case
+    assert tc.check_conv_bn(model, name, wkey, bnkey, cin, hw, **kw)
+
+
+def test_gca_forward_backward(tc, model):
+    assert tc.check_gca(model)
+
+
+def test_tam_forward_backward(tc, model):
+    assert tc.check_tam(model)
+
+
+def test_full_training_step_matches_reference(tc):
+    ok, rows, errs = tc.check_full_step(verbose=True)
+    assert errs["losses"] < 2e-3, errs
+    assert errs["alphas"] < 1e-3, errs
+    assert errs["state"] < 1e-3, errs
+    assert ok, (errs, rows[:5])
+
+
+def test_train_mode_without_grad_runs_forward_only(model):
+    import numpy as np
+    from helpers import golden
+    g = golden("train_step_s5.npz")
+    a, fg, bg = (torch.from_numpy(g[k]).float().cuda() for k in ("a", "fg", "bg"))
+    with torch.no_grad():
+        out = model(a, fg, bg)
+    assert len(out) == 12 and all(torch.isfinite(o).all() for o in out[:5])

@@ -1,0 +1,342 @@
+"""Operator-level bring-up checks of the training path on a GPU box: every forward/backward operator of
+tcvom_b200.train_engine against torch autograd (fp32, TF32 off) / the CPU oracle.  Prints one line per check
+(relative L2 errors); ``python tools/train_check.py`` exits non-zero when a check is over its bound.
+tests/test_gpu_train.py imports the same checks."""
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import tcvom_b200  # noqa: E402
+from helpers import fixture_sd  # noqa: E402
+from oracle import vmn_gca_oracle as O  # noqa: E402
+from tcvom_b200 import _cabi  # noqa: E402
+from tcvom_b200._cabi import ACT_LEAKY02, ACT_NONE, ACT_RELU, PAD_REFLECT  # noqa: E402
+from tcvom_b200.engine import Act  # noqa: E402
+from tcvom_b200.model import _train_engine_for  # noqa: E402
+from tcvom_b200.train_engine import TAct  # noqa: E402
+
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+DEV = "cuda:0"
+RESULTS = []
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / max(float(b.norm()), 1e-20))
+
+
+def report(name, errs, bound):
+    worst = max(errs.values()) if errs else 0.0
+    ok = worst <= bound and all(math.isfinite(v) for v in errs.values())
+    RESULTS.append((name, ok))
+    print(("PASS " if ok else "FAIL ") + name + "  " + "  ".join(f"{k}={v:.2e}" for k, v in errs.items()), flush=True)
+    return ok
+
+
+def to_act(t):
+    """NCHW fp32 cuda tensor -> split-bf16 NHWC Act"""
+    n, c, h, w = t.shape
+    a = Act.empty(n, h, w, c, t.device)
+    st = torch.cuda.current_stream().cuda_stream
+    _cabi.check(_cabi.lib().tcv_nchw_to_split(t.contiguous().data_ptr(), n, c, h, w, c, a.ptr, 0, st), "nchw_to_split")
+    return a
+
+
+def from_act(a):
+    y = torch.empty((a.n, a.c, a.h, a.w), dtype=torch.float32, device=a.buf.device)
+    st = torch.cuda.current_stream().cuda_stream
+    _cabi.check(_cabi.lib().tcv_split_to_nchw(a.ptr, a.n, a.c, a.h, a.w, a.c, 0, y.data_ptr(), st), "split_to_nchw")
+    return y
+
+
+def make_net():
+    model = tcvom_b200.FullModel_VMD(model="vmn_gca", agg_window=7, dilate_kernel=3)
+    model.NET.load_state_dict(fixture_sd(), strict=True)
+    return model.to(DEV).train()
+
+
+def rnd(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(DEV)
+
+
+def run_tape(eng):
+    for fn in reversed(eng.tape):
+        fn()
+    eng.tape = []
+
+
+def sn_weights(eng, sd, p, transposed=False):
+    """per-call W_bar/sigma_k as torch expressions of the leaf W_bar (u_k, v_k constants)"""
+    s = eng.sn[p]
+    W = sd[p + ".module.weight_bar"]
+    rows = W.shape[0]
+    return [W / s["u_hist"][k].dot(W.reshape(rows, -1).mv(s["v_hist"][k])) for k in range(s["calls"])]
+
+
+def ref_bn(t, gamma, beta, groups):
+    """train-mode BN per statistics group (image i -> group i % groups)"""
+    out = torch.empty_like(t)
+    for g in range(groups):
+        out[g::groups] = F.batch_norm(t[g::groups], None, None, gamma, beta, True, 0.0, 1e-5)
+    return out
+
+
+def check_conv_bn(model, name, wkey, bnkey, cin, hw, *, stride=1, mode=1, act=ACT_NONE, res1=False, res2=False,
+                  reflect=None, deconv=False, groups=2, B=2, bound=2e-3):
+    """conv/deconv (+1/sigma) -> BN -> act with residuals: forward, dx, dW_bar, dgamma, dbeta"""
+    net = model.NET
+    eng = _train_engine_for(net, 7)
+    eng.tape = []
+    eng.dw.clear(); eng.dbias.clear(); eng.dbn.clear()
+    eng.spectral_norm_step(groups, groups)
+    # force the layer's call count = groups regardless of where it lives
+    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "weight_u" not in k and "weight_v" not in k
+                                              and "running" not in k)
+          for k, v in tcvom_b200.engine.named_tensors(net).items() if k.startswith((wkey, bnkey))}
+    if eng.sn[wkey]["calls"] != groups:
+        return report(name, dict(skipped=0.0), 1.0)
+    n = B * groups
+    h, w = hw
+    x = rnd((n, cin, h, w), 1)
+    xt = TAct(to_act(x), groups)
+    cout = eng.w[wkey]["cout"]
+    oh, ow = (2 * h, 2 * w) if deconv else ((h // stride), (w // stride))
+    r1 = TAct(to_act(rnd((n, cout, oh, ow), 2)), groups) if res1 else None
+    r2 = TAct(to_act(rnd((n, cout, oh, ow), 3)), groups) if res2 else None
+    if deconv:
+        out = eng.bn_op(eng.deconv_op(xt, wkey), bnkey, mode=mode, act=act, snkey=wkey, res1=r1, res2=r2)
+    elif reflect == "prepadded":
+        out = eng.conv_bn(eng.pad_reflect_op(xt), wkey, bnkey, stride=stride, prepadded=True, mode=mode, act=act)
+    elif reflect == "direct":
+        out = eng.conv_bn(xt, wkey, bnkey, stride=stride, pad=PAD_REFLECT, mode=mode, act=act)
+    else:
+        out = eng.conv_bn(xt, wkey, bnkey, stride=stride, mode=mode, act=act, res1=r1, res2=r2)
+    y = from_act(out.a)
+    dy = rnd(tuple(y.shape), 4)
+    out.g, out.g_owned = to_act(dy), True
+    run_tape(eng)
+    pname = wkey + ".module.weight_bar"
+    grads = eng.collect_grads([pname, bnkey + ".weight", bnkey + ".bias"])
+    # ---- torch reference
+    xr = from_act(xt.a).requires_grad_(True)            # the split-bf16 rounded input is the common input
+    Ws = sn_weights(eng, sd, wkey)
+    k = eng.w[wkey]["k"]
+    zs = []
+    for g in range(groups):
+        xg = xr[g::groups]
+        if deconv:
+            zs.append(F.conv_transpose2d(xg, Ws[g], None, 2, 1))
+        elif reflect:
+            zs.append(F.conv2d(F.pad(xg, (1, 1, 1, 1), mode="reflect"), Ws[g], None, stride, 0))
+        else:
+            zs.append(F.conv2d(xg, Ws[g], None, stride, k // 2))
+    z = torch.stack(zs, 1).reshape((n,) + tuple(zs[0].shape[1:]))       # image i = b*groups + g
+    gamma, beta = sd[bnkey + ".weight"], sd[bnkey + ".bias"]
+    actf = {ACT_NONE: lambda t: t, ACT_RELU: torch.relu, ACT_LEAKY02: lambda t: F.leaky_relu(t, 0.2)}[act]
+    r1r = from_act(r1.a).requires_grad_(True) if res1 else None
+    r2r = from_act(r2.a).requires_grad_(True) if res2 else None
+    if mode == 1:
+        t = ref_bn(z, gamma, beta, groups)
+        if res1:
+            t = t + r1r
+        t = actf(t)
+        if res2:
+            t = t + r2r
+    else:
+        t = ref_bn(actf(z), gamma, beta, groups)
+    ins = [xr, sd[pname], gamma, beta] + ([r1r] if res1 else []) + ([r2r] if res2 else [])
+    gr = torch.autograd.grad(t, ins, from_act(to_act(dy)))
+    errs = dict(y=rel(y, t.detach()), dx=rel(from_act(xt.g), gr[0]), dW=rel(grads[0], gr[1]), dgamma=rel(grads[1], gr[2]),
+                dbeta=rel(grads[2], gr[3]))
+    i = 4
+    if res1:
+        errs["dres1"] = rel(from_act(r1.g), gr[i]); i += 1
+    if res2:
+        errs["dres2"] = rel(from_act(r2.g), gr[i])
+    return report(name, errs, bound)
+
+
+def check_sn(model):
+    net = model.NET
+    sd0 = {k: v.detach().clone().cpu() for k, v in tcvom_b200.engine.named_tensors(net).items()}
+    eng = _train_engine_for(net, 7)
+    eng.spectral_norm_step(5, 3)
+    errs = {}
+    for p in ("encoder.conv1", "encoder.layer_bottleneck.1.conv2", "decoder.layer3.0.conv1", "decoder.conv1"):
+        sd = {k: v.clone() for k, v in sd0.items() if k.startswith(p + ".module")}
+        calls = eng.sn[p]["calls"]
+        sig = []
+        with O.TrainMode():
+            for _ in range(calls):
+                w = O.sn_weight(sd, p)
+                sig.append(float((sd[p + ".module.weight_bar"].flatten()[0] / w.flatten()[0])))
+        errs[p.split(".")[-2] + ".sigma"] = rel(eng.sn[p]["sigma"], torch.tensor(sig))
+        errs[p.split(".")[-2] + ".u"] = rel(tcvom_b200.engine.named_tensors(net)[p + ".module.weight_u"], sd[p + ".module.weight_u"])
+    # restore u/v so that later checks start from the fixture state
+    with torch.no_grad():
+        for k, v in tcvom_b200.engine.named_tensors(net).items():
+            if k.endswith(("weight_u", "weight_v")):
+                v.copy_(sd0[k])
+    return report("sn_power_iter", errs, 1e-4)
+
+
+def check_gca(model, bound=3e-3):
+    net = model.NET
+    eng = _train_engine_for(net, 7)
+    eng.tape = []
+    eng.dw.clear(); eng.dbias.clear(); eng.dbn.clear()
+    eng.spectral_norm_step(2, 2)
+    p = "decoder.gca"
+    n, h, w = 2, 8, 12
+    f = rnd((n, 128, h, w), 11)
+    al = rnd((n, 128, h, w), 12)
+    unk = (rnd((n, 1, h, w), 13) > 0.3).float()
+    ft, at = TAct(to_act(f), 2), TAct(to_act(al), 2)
+    out = eng.gca_op(p, ft, at, unk.reshape(n, h, w).contiguous())
+    y = from_act(out.a)
+    dy = rnd(tuple(y.shape), 14)
+    out.g, out.g_owned = to_act(dy), True
+    run_tape(eng)
+    names = [p + ".guidance_conv.weight", p + ".guidance_conv.bias", p + ".W.0.weight", p + ".W.1.weight", p + ".W.1.bias"]
+    grads = eng.collect_grads(names)
+    sd = {k: v.detach().clone().cpu().requires_grad_(k in names)
+          for k, v in tcvom_b200.engine.named_tensors(net).items() if k.startswith(p)}
+    fr = from_act(ft.a).cpu().requires_grad_(True)
+    ar = from_act(at.a).cpu().requires_grad_(True)
+    outs = []
+    with O.TrainMode():
+        for g in range(2):                      # one call per group (statistics of W.1 are per call)
+            outs.append(O.gca_attention(sd, p, fr[g::2], ar[g::2], unk.cpu()[g::2]))
+    t = torch.stack(outs, 1).reshape(y.shape)
+    gr = torch.autograd.grad(t, [fr, ar] + [sd[k] for k in names], from_act(to_act(dy)).cpu())
+    errs = dict(y=rel(y, t.detach()), dim_fea=rel(from_act(ft.g), gr[0]), dfeat=rel(from_act(at.g), gr[1]))
+    for i, k in enumerate(names):
+        errs["d" + k[len(p) + 1:]] = rel(grads[i], gr[2 + i])
+    return report("gca_op", errs, bound)
+
+
+def check_tam(model, bound=2e-3):
+    net = model.NET
+    eng = _train_engine_for(net, 7)
+    eng.tape = []
+    eng.dw.clear(); eng.dbias.clear(); eng.dbn.clear()
+    p = "decoder.fam"
+    n, h, w = 2, 6, 8
+    xs = [rnd((n, 128, h, w), 21 + i) for i in range(3)]
+    mask = (rnd((n, 1, 8 * h, 8 * w), 25) > -0.5).float()
+    ts = [TAct(to_act(t), 1) for t in xs]
+    attb = torch.empty((n, 49, h * w), device=DEV); attf = torch.empty_like(attb)
+    sm = torch.empty((n, 1, h, w), dtype=torch.uint8, device=DEV)
+    datt = {}
+    out = eng.tam_op(p, ts[0], ts[1], ts[2], mask.reshape(n, 8 * h, 8 * w).contiguous(), 8 * h, 8 * w, attb, attf, sm, datt)
+    y = from_act(out.a)
+    dy = rnd(tuple(y.shape), 26)
+    datt["b"], datt["f"] = rnd(tuple(attb.shape), 27, 0.1), rnd(tuple(attf.shape), 28, 0.1)
+    out.g, out.g_owned = to_act(dy), True
+    run_tape(eng)
+    names = [p + f".{c}_conv.{k}" for c in ("key", "query", "value") for k in ("weight", "bias")]
+    grads = eng.collect_grads(names)
+    sd = {k: v.detach().clone().cpu().requires_grad_(True)
+          for k, v in tcvom_b200.engine.named_tensors(net).items() if k.startswith(p)}
+    xr = [from_act(t.a).cpu().requires_grad_(True) for t in ts]
+    feat, lb, lf, m = O.tam(sd, p, xr[0], xr[1], xr[2], mask.cpu())
+    gr = torch.autograd.grad([feat, lb, lf], xr + [sd[k] for k in names],
+                             [from_act(to_act(dy)).cpu(), datt["b"].cpu(), datt["f"].cpu()])
+    errs = dict(y=rel(y, feat.detach()), attb=rel(attb, lb.detach()))
+    for i, nm in enumerate(("dx", "dxb", "dxf")):
+        errs[nm] = rel(from_act(ts[i].g), gr[i])
+    for i, k in enumerate(names):
+        errs["d" + k[len(p) + 1:]] = rel(grads[i], gr[3 + i])
+    return report("tam_op", errs, bound)
+
+
+LOSS_WEIGHTS = (1.0, 1.0, 1.0, 0.5, 0.25)
+GRAD_STRIDE = 257
+
+
+def check_full_step(verbose=True, bound=5e-2):
+    """One native training step against one training step of the unmodified reference
+    (tests/golden/train_step_s5.npz): losses, alphas, every gradient, spectral-norm u/v, BN running statistics."""
+    from helpers import golden, key_table
+    g = golden("train_step_s5.npz")
+    model = make_net()
+    a, fg, bg = (torch.from_numpy(g[k]).float().to(DEV) for k in ("a", "fg", "bg"))
+    n0 = _cabi.launch_count()
+    out = model(a, fg, bg)
+    loss = sum(w * o.mean() for w, o in zip(LOSS_WEIGHTS, out[:5]))
+    model.zero_grad()
+    loss.backward()
+    torch.cuda.synchronize()
+    launches = _cabi.launch_count() - n0
+    losses = np.array([float(o) for o in out[:5]])
+    errs = dict(losses=float(np.abs(losses - g["losses"]).max() / np.abs(g["losses"]).max()),
+                alphas=float((out[7].detach().cpu() - torch.from_numpy(g["alphas"])).abs().max()))
+    named = dict(model.NET.named_parameters())
+    rows = []
+    for n in key_table()["trainable"]:
+        grad = named[n].grad
+        grad = grad if grad is not None else torch.zeros_like(named[n])
+        f = grad.detach().flatten().cpu()
+        smp = f if f.numel() <= 8192 else f[::GRAD_STRIDE]
+        ref = torch.from_numpy(g["gs:" + n])
+        e = float((smp.double() - ref.double()).norm()) / max(float(ref.double().norm()), 1e-12)
+        rows.append((e, n, float(g["gn:" + n][0]), float(grad.double().norm())))
+    rows.sort(reverse=True)
+    errs["grad_worst"] = rows[0][0]
+    errs["grad_median"] = rows[len(rows) // 2][0]
+    st_err = 0.0
+    sd = model.NET.state_dict()
+    worst_st = None
+    for k in g.files:
+        if k.startswith("st:"):
+            ref = torch.from_numpy(g[k]).float()
+            got = sd[k[3:]].detach().cpu().float()
+            e = float((got - ref).abs().max()) / max(1.0, float(ref.abs().max()))
+            if e > st_err:
+                st_err, worst_st = e, k
+    errs["state"] = st_err
+    if verbose:
+        print("losses native", losses, "reference", g["losses"], "launches", launches)
+        print("worst state tensor", worst_st)
+        for r in rows[:12]:
+            print("  grad rel-L2 %.3e  %-52s ref|g|=%.3e  got|g|=%.3e" % r)
+    return report("full_train_step", errs, bound), rows, errs
+
+
+def main():
+    model = make_net()
+    check_sn(model)
+    e, d = "encoder", "decoder"
+    check_conv_bn(model, "3x3 s1 64->64 bn relu +res1", e + ".layer1.0.conv2", e + ".layer1.0.bn2", 64, (16, 24), act=ACT_RELU, res1=True)
+    check_conv_bn(model, "3x3 s2 64->128 bn relu", e + ".layer2.0.conv1", e + ".layer2.0.bn1", 64, (16, 24), stride=2, act=ACT_RELU)
+    check_conv_bn(model, "1x1 64->128 bn", e + ".layer2.0.downsample.1", e + ".layer2.0.downsample.2", 64, (8, 12))
+    check_conv_bn(model, "3x3 s1 32->32 bn relu", e + ".conv2", e + ".bn2", 32, (32, 32), act=ACT_RELU)
+    check_conv_bn(model, "3x3 s2 32->64 bn relu", e + ".conv3", e + ".bn3", 32, (32, 32), stride=2, act=ACT_RELU)
+    check_conv_bn(model, "shortcut 3x3 128->128 relu bn", e + ".shortcut.3.0", e + ".shortcut.3.2", 128, (8, 8), mode=2, act=ACT_RELU)
+    check_conv_bn(model, "guidance 16->32 s2 reflect (prepadded)", e + ".guidance_head.5", e + ".guidance_head.7", 16, (16, 16), stride=2, mode=2, act=ACT_RELU, reflect="prepadded")
+    check_conv_bn(model, "guidance 32->128 s2 reflect (prepadded)", e + ".guidance_head.9", e + ".guidance_head.11", 32, (16, 16), stride=2, mode=2, act=ACT_RELU, reflect="prepadded")
+    check_conv_bn(model, "3x3 s1 512->512 bn relu +res1", e + ".layer_bottleneck.1.conv2", e + ".layer_bottleneck.1.bn2", 512, (4, 4), act=ACT_RELU, res1=True)
+    check_conv_bn(model, "deconv 4x4 s2 256->256 bn leaky", d + ".layer2.0.conv1", d + ".layer2.0.bn1", 256, (4, 6), act=ACT_LEAKY02, deconv=True)
+    check_conv_bn(model, "3x3 s1 256->128 bn leaky +res1 +res2", d + ".layer2.0.conv2", d + ".layer2.0.bn2", 256, (8, 12), act=ACT_LEAKY02, res1=True, res2=True)
+    check_conv_bn(model, "deconv 4x4 s2 64->64 bn leaky", d + ".layer4.0.conv1", d + ".layer4.0.bn1", 64, (8, 8), act=ACT_LEAKY02, deconv=True)
+    check_conv_bn(model, "deconv 4x4 s2 32->32 bn leaky +res2", d + ".conv1", d + ".bn1", 32, (16, 16), act=ACT_LEAKY02, deconv=True, res2=True)
+    check_gca(model)
+    check_tam(model)
+    check_full_step()
+    bad = [n for n, ok in RESULTS if not ok]
+    print("FAILED:" if bad else "ALL PASS", bad)
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
