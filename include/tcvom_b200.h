@@ -332,6 +332,21 @@ int tcv_group_dot(const void* z, long long z_plane, const void* dz, long long dz
  * dz split-bf16 [n, oh, ow, dz_c]; dw fp32 [wtaps][cin][dz_c]. */
 int tcv_conv2d_wgrad(const tcv_conv_desc* d, const void* dz, long long dz_plane, int dz_c, float* dw,
                      tcv_stream_t stream);
+/* Tensor-core weight gradient of the stride-1 gather convolutions (3x3, 1x1, the phases of the 4x4/stride-2 deconv).
+ *  transpose_pad: split-bf16 NHWC [n,h,w,c], sub-sampled (gy*mul+off_y, gx*mul+off_x) -> channel-major planes with a
+ *                 zero ring: xt[ch][(img*(gh+2)+gy+1)*row_stride + gx+1+shift], gh = h/mul, row_stride >= gw+2;
+ *                 rows of ktot elements (ktot % 8 == 0, ktot >= n*(gh+2)*row_stride), lo plane xt_plane elements
+ *                 after the hi plane.  shift in {-1,0,1} bakes a horizontal tap offset into the copy.
+ *  wgrad_tc:      dw[wtap[t]][ci][co] += sum_p xt[ci][p + dy[t]*row_stride + dx[t]] * zt[co][p]:
+ *                 one split-K tcgen05 GEMM (bf16x3) per tap; partial fp32 [nsplit][cin][cout] workspace.
+ *                 dy[t]*row_stride + dx[t] must be a multiple of 8 (TMA needs 16-byte aligned inner coordinates):
+ *                 use row_stride % 8 == 0, dx = 0 and a zt copy shifted by the tap's horizontal offset. */
+int tcv_transpose_pad(const void* x, long long x_plane, int n, int h, int w, int c, int mul, int off_y, int off_x,
+                      int row_stride, int shift, void* xt, long long xt_plane, long long ktot, tcv_stream_t stream);
+int tcv_wgrad_tc(const void* xt, long long xt_plane, const void* zt, long long zt_plane, int cin, int cout,
+                 long long ktot, int row_stride, int ntaps, const int* dy, const int* dx, const int* wtap,
+                 float* partial, int nsplit, float* dw, int dw_cout, tcv_stream_t stream);
+
 /* packed gradient fp32 [taps][cin_pad][cout_pad] -> torch layout ([cout,cin,kh,kw], or [cin,cout,kh,kw] when
  * transposed), minus the spectral-norm term sum_k (zdot[k]/sigma[k]) * u_k v_k^T when calls > 0. */
 int tcv_weight_grad_unpack(const float* dw, int cout, int cin, int kh, int kw, int transposed, int cin_pad,

@@ -31,6 +31,10 @@ struct TcParams {
   int dy[TCV_MAX_TAPS], dx[TCV_MAX_TAPS], wtap[TCV_MAX_TAPS];
   uint32_t idesc;  // tcgen05 instruction descriptor (operand format bf16 or fp16)
   int b_batched;  // GEMM mode: third weight-map coordinate = blockIdx.z instead of the tap index
+  // split-K GEMM mode (weight gradients): blockIdx.z selects the K range [z*split_k, (z+1)*split_k) of ONE
+  // [rows][K] operand pair instead of a batch entry; koff shifts the A operand along K (filter-tap offset in the
+  // zero-ringed channel-major activation; TMA zero-fills coordinates outside [0, K))
+  int split_k, koff;
   // conv epilogue
   int n_imgs, oh, ow, cout, oy_mul, oy_off, ox_mul, ox_off;
   __nv_bfloat16* y;
@@ -87,6 +91,8 @@ __global__ void __launch_bounds__(320) igemm_tc_kernel(const __grid_constant__ C
   const int n0 = (p.b_batched ? blockIdx.x : blockIdx.y) * BN;
   const int img = blockIdx.z;
   const int total_iters = p.ntaps * p.kc_iters;
+  const int kbase = p.split_k ? img * p.split_k : 0;
+  const int aimg = p.split_k ? 0 : img;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -114,7 +120,7 @@ __global__ void __launch_bounds__(320) igemm_tc_kernel(const __grid_constant__ C
       int it = 0;
       for (int t = 0; t < p.ntaps; ++t) {
         const int cw = w0 * p.stride + p.dx[t], ch = h0 * p.stride + p.dy[t];
-        const int bz = p.b_batched ? img : p.wtap[t];
+        const int bz = p.b_batched ? aimg : p.wtap[t];
         for (int kc = 0; kc < p.kc_iters; ++kc, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -122,15 +128,16 @@ __global__ void __launch_bounds__(320) igemm_tc_kernel(const __grid_constant__ C
           const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
           if (elect_one()) {
             mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
-            tma_load_4d(st, &mapA_hi, full_bar(s), kc * BK, cw, ch, img);
-            tma_load_3d(st + Cfg::PLANES * Cfg::A_BYTES, &mapB_hi, full_bar(s), kc * BK, n0, bz);
+            const int ka = kbase + kc * BK + p.koff, kb = kbase + kc * BK;
+            tma_load_4d(st, &mapA_hi, full_bar(s), ka, cw, ch, aimg);
+            tma_load_3d(st + Cfg::PLANES * Cfg::A_BYTES, &mapB_hi, full_bar(s), kb, n0, bz);
             if (NSPLIT >= 3) {
-              tma_load_4d(st + Cfg::A_BYTES, &mapA_lo, full_bar(s), kc * BK, cw, ch, img);
-              tma_load_3d(st + Cfg::PLANES * Cfg::A_BYTES + Cfg::B_BYTES, &mapB_lo, full_bar(s), kc * BK, n0, bz);
+              tma_load_4d(st + Cfg::A_BYTES, &mapA_lo, full_bar(s), ka, cw, ch, aimg);
+              tma_load_3d(st + Cfg::PLANES * Cfg::A_BYTES + Cfg::B_BYTES, &mapB_lo, full_bar(s), kb, n0, bz);
             }
             if (NSPLIT == 6) {
-              tma_load_4d(st + 2 * Cfg::A_BYTES, &mapA_p2, full_bar(s), kc * BK, cw, ch, img);
-              tma_load_3d(st + 3 * Cfg::A_BYTES + 2 * Cfg::B_BYTES, &mapB_p2, full_bar(s), kc * BK, n0, bz);
+              tma_load_4d(st + 2 * Cfg::A_BYTES, &mapA_p2, full_bar(s), ka, cw, ch, aimg);
+              tma_load_3d(st + 3 * Cfg::A_BYTES + 2 * Cfg::B_BYTES, &mapB_p2, full_bar(s), kb, n0, bz);
             }
           }
           __syncwarp();
@@ -301,6 +308,7 @@ struct TcOperands {
   long long b_plane;
   int b_rows, b_z;
   bool fp16;                // operands are IEEE half instead of bf16 (NSPLIT == 1 GEMMs only)
+  int grid_z = 0;           // split-K mode: number of K slices (grid.z)
 };
 
 template <int BN, int BK, int NSPLIT, int EPI>
@@ -336,8 +344,9 @@ static int launch_tc(const TcOperands& o, TcParams& p, cudaStream_t st) {
   p.tiles_x = (p.gw + p.TW - 1) / p.TW;
   const int tiles_y = (p.gh + p.TH - 1) / p.TH;
   const int nrows = EPI == EPI_CONV ? p.cout : p.N;
-  dim3 grid(p.tiles_x * tiles_y, (nrows + BN - 1) / BN, o.n);
-  if (p.b_batched) grid = dim3((nrows + BN - 1) / BN, p.tiles_x * tiles_y, o.n);
+  const int gz = p.split_k ? o.grid_z : o.n;
+  dim3 grid(p.tiles_x * tiles_y, (nrows + BN - 1) / BN, gz);
+  if (p.b_batched) grid = dim3((nrows + BN - 1) / BN, p.tiles_x * tiles_y, gz);
   kern<<<grid, 320, Cfg::SMEM, st>>>(mA_hi, mA_lo, mA_p2, mB_hi, mB_lo, mB_p2, p);
   return launched("igemm_tc_kernel");
 }
@@ -434,4 +443,69 @@ extern "C" int tcv_gemm_tn_tc(const void* A, long long a_plane, const void* B, l
   }
   if (out_bf16) return launch_tc<256, 64, 1, EPI_BF16>(o, p, st);
   return launch_tc<256, 64, 1, EPI_F32>(o, p, st);
+}
+
+
+// ---- weight gradient on the tensor cores ---------------------------------------------------------------
+// dw[wtap[t]][ci][co] += sum_p XT[ci][p + dy[t]*row + dx[t]] * ZT[co][p]: per filter tap one split-K GEMM over the
+// zero-ringed channel-major copies of the activation and of the output gradient (tcv_transpose_pad), bf16x3,
+// partial sums per K slice in `partial`, then one reduction kernel.
+namespace tcv {
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit, int ntaps, int cin, int cout,
+                                    const int* __restrict__ wtap_dev, int t0, int wt, float* __restrict__ dw,
+                                    int dw_cout) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cin * cout) return;
+  const int ci = i / cout, co = i - ci * cout;
+  float s = 0.f;
+  for (int k = 0; k < nsplit; ++k) s += partial[((long long)k * cin + ci) * cout + co];
+  dw[((long long)wt * cin + ci) * dw_cout + co] += s;
+}
+}  // namespace tcv
+
+extern "C" int tcv_wgrad_tc(const void* xt, long long xt_plane, const void* zt, long long zt_plane, int cin, int cout,
+                            long long ktot, int row_stride, int ntaps, const int* dy, const int* dx, const int* wtap,
+                            float* partial, int nsplit, float* dw, int dw_cout, tcv_stream_t stream) {
+  TCV_REQUIRE(xt && zt && partial && dw && dy && dx && wtap, "wgrad_tc: null pointer");
+  TCV_REQUIRE(cin > 0 && cout > 0 && cout % 4 == 0 && ktot > 0 && ktot % 8 == 0 && ktot < (1LL << 31),
+              "wgrad_tc: bad geometry (cout %% 4, ktot %% 8)");
+  TCV_REQUIRE(ntaps >= 1 && ntaps <= TCV_MAX_TAPS && nsplit >= 1, "wgrad_tc: bad ntaps / nsplit");
+  for (int t = 0; t < ntaps; ++t)
+    TCV_REQUIRE((dy[t] * row_stride + dx[t]) % 8 == 0, "wgrad_tc: tap %d offset %d not a multiple of 8 elements", t,
+                dy[t] * row_stride + dx[t]);
+  TCV_REQUIRE(((uintptr_t)xt & 15) == 0 && ((uintptr_t)zt & 15) == 0 && xt_plane % 8 == 0 && zt_plane % 8 == 0,
+              "wgrad_tc: operands must be 16-byte aligned");
+  cudaStream_t st = S(stream);
+  long long chunk = (ktot + nsplit - 1) / nsplit;
+  chunk = (chunk + 31) / 32 * 32;
+  const int slices = (int)((ktot + chunk - 1) / chunk);
+  for (int t = 0; t < ntaps; ++t) {
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.gh = 1; p.gw = cin; p.TH = 1; p.TW = 128;
+    p.ntaps = 1; p.kc_iters = (int)(chunk / 32); p.stride = 1;
+    p.b_batched = 1;
+    p.split_k = (int)chunk;
+    p.koff = dy[t] * row_stride + dx[t];
+    p.c = partial; p.ldc = cout; p.c_batch_stride = (long long)cin * cout; p.M = cin; p.N = cout;
+    TcOperands o;
+    o.a = reinterpret_cast<const __nv_bfloat16*>(xt);
+    o.a_plane = xt_plane;
+    o.n = 1; o.h = 1; o.w = cin; o.c = (int)ktot; o.a_img_stride = (long long)cin * ktot;
+    o.b = reinterpret_cast<const __nv_bfloat16*>(zt);
+    o.b_plane = zt_plane;
+    o.b_rows = cout; o.b_z = 1;
+    o.fp16 = false;
+    o.grid_z = slices;
+    int rc;
+    if (cout % 128 == 0) rc = launch_tc<128, 32, 3, EPI_F32>(o, p, st);
+    else if (cout % 64 == 0) rc = launch_tc<64, 32, 3, EPI_F32>(o, p, st);
+    else rc = launch_tc<32, 32, 3, EPI_F32>(o, p, st);
+    if (rc) return rc;
+    wgrad_reduce_kernel<<<(cin * cout + 255) / 256, 256, 0, st>>>(partial, slices, ntaps, cin, cout, nullptr, t, wtap[t],
+                                                                 dw, dw_cout);
+    rc = launched("wgrad_reduce_kernel");
+    if (rc) return rc;
+  }
+  return TCV_OK;
 }

@@ -190,6 +190,42 @@ __global__ void transpose_packed_kernel(const float* __restrict__ in, int taps, 
   out[i] = co < cout ? in[((long long)t * cin + ci) * cout + co] : 0.f;
 }
 
+
+// NHWC split-bf16 -> channel-major, zero-ringed: xt[ch][(img*(gh+2) + gy+1)*row + gx+1+shift] = x[img][gy*mul+oy][gx*mul+ox][ch]
+// (the K-major operand layout of the tensor-core weight-gradient GEMM; the ring makes every 3x3 tap a pure shift;
+// rows are padded to a multiple of 8 elements and horizontal tap offsets are baked in as `shift`, because TMA only
+// accepts 16-byte aligned coordinates in the innermost dimension -- measured: unaligned ones fault).
+// 32 pixels x 32 channels per block through shared memory, planes moved as raw 16-bit elements.
+__global__ void __launch_bounds__(256) transpose_pad_kernel(const uint16_t* __restrict__ x, long long x_plane, int h, int w,
+                                                            int c, int mul, int oy, int ox, int gh, int gw, int cblocks,
+                                                            int row, int shift, uint16_t* __restrict__ xt,
+                                                            long long xt_plane, long long ktot) {
+  __shared__ uint16_t tile[2][32][34];
+  const int img = blockIdx.z / cblocks, cb = blockIdx.z % cblocks;
+  const int gy = blockIdx.y, gx0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int pp = ty; pp < 32; pp += 8) {
+    const int gx = gx0 + pp, ch = cb * 32 + tx;
+    uint16_t a = 0, b = 0;
+    if (gx < gw && ch < c) {
+      const long long src = (((long long)img * h + (gy * mul + oy)) * w + (gx * mul + ox)) * c + ch;
+      a = x[src];
+      b = x[src + x_plane];
+    }
+    tile[0][pp][tx] = a;
+    tile[1][pp][tx] = b;
+  }
+  __syncthreads();
+  for (int cc = ty; cc < 32; cc += 8) {
+    const int gx = gx0 + tx, ch = cb * 32 + cc;
+    if (gx < gw && ch < c) {
+      const long long dst = (long long)ch * ktot + ((long long)img * (gh + 2) + gy + 1) * row + gx + 1 + shift;
+      xt[dst] = tile[0][tx][cc];
+      xt[dst + xt_plane] = tile[1][tx][cc];
+    }
+  }
+}
+
 // ---- SpectralNorm power iteration: one CTA per layer --------------------------------------------------
 __device__ float block_sum_1024(float v, float* red) {
   v = warp_sum(v);
@@ -386,6 +422,23 @@ int tcv_weight_grad_unpack(const float* dw, int cout, int cin, int kh, int kw, i
   weight_grad_unpack_kernel<<<nb(total), 256, 0, S(stream)>>>(dw, cout, cin, kh, kw, transposed, cin_pad, cout_pad,
                                                              u_hist, v_hist, sigma, zdot, calls, grad);
   return launched("weight_grad_unpack_kernel");
+}
+
+int tcv_transpose_pad(const void* x, long long x_plane, int n, int h, int w, int c, int mul, int off_y, int off_x,
+                      int row_stride, int shift, void* xt, long long xt_plane, long long ktot, tcv_stream_t stream) {
+  TCV_REQUIRE(x && xt && n > 0 && c > 0 && mul >= 1 && h % mul == 0 && w % mul == 0, "transpose_pad: bad arguments");
+  const int gh = h / mul, gw = w / mul;
+  TCV_REQUIRE(row_stride >= gw + 2 && shift >= -1 && shift <= 1, "transpose_pad: row_stride < gw+2 or |shift| > 1");
+  TCV_REQUIRE(ktot >= (long long)n * (gh + 2) * row_stride && xt_plane >= (long long)c * ktot, "transpose_pad: output too small");
+  if (x_plane == 0) x_plane = (long long)n * h * w * c;
+  TCV_CUDA(cudaMemsetAsync(xt, 0, sizeof(uint16_t) * (size_t)c * ktot, S(stream)));
+  TCV_CUDA(cudaMemsetAsync(reinterpret_cast<uint16_t*>(xt) + xt_plane, 0, sizeof(uint16_t) * (size_t)c * ktot, S(stream)));
+  const int cblocks = (c + 31) / 32;
+  dim3 grid((gw + 31) / 32, gh, n * cblocks);
+  transpose_pad_kernel<<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const uint16_t*>(x), x_plane, h, w, c, mul, off_y,
+                                                   off_x, gh, gw, cblocks, row_stride, shift,
+                                                   reinterpret_cast<uint16_t*>(xt), xt_plane, ktot);
+  return launched("transpose_pad_kernel");
 }
 
 }  // extern "C"

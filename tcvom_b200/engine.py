@@ -235,6 +235,14 @@ class GcaVmnEngine:
     def _call(self, fn_name: str, *args, meta: Optional[dict] = None):
         fn = getattr(_cabi.lib(), fn_name)
         st = torch.cuda.current_stream(self.device).cuda_stream
+        prof = getattr(self, "_prof", None)
+        if prof is not None:                      # per-call CUDA-event timing (measurement helper, tools/train_bench.py)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(torch.cuda.current_stream(self.device))
+            _cabi.check(fn(*args, st), fn_name)
+            e1.record(torch.cuda.current_stream(self.device))
+            prof.append((fn_name, (meta or {}).get("tag", ""), e0, e1))
+            return
         _cabi.check(fn(*args, st), fn_name)
         if self._rec is not None:
             self._rec.calls.append((fn, args, fn_name))

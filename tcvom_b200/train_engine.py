@@ -52,6 +52,10 @@ class TrainEngine(GcaVmnEngine):
         self.sync_bn = False
         self.process_group = None
         self.world = 1
+        # weight gradients of the stride-1 convs / deconv phases on the tensor cores (split-K tcgen05 GEMM over
+        # channel-major copies); TCV_TC_WGRAD=0 keeps the CUDA-core fp32 kernel everywhere (exact cross-check)
+        import os
+        self.use_tc_wgrad = os.environ.get("TCV_TC_WGRAD", "1") == "1"
 
     # ------------------------------------------------------------------ per-step weight state
     def refresh_weights(self, net: torch.nn.Module, force=False) -> None:
@@ -170,6 +174,42 @@ class TrainEngine(GcaVmnEngine):
                                             dtype=torch.float32, device=self.device)
         return t
 
+    # ------------------------------------------------------------------ weight gradient
+    def _transpose_pad(self, a: Act, mul: int, oy: int, ox: int, row: int, shift: int, ktot: int) -> torch.Tensor:
+        t = torch.empty((2, a.c, ktot), dtype=torch.bfloat16, device=self.device)
+        self._call("tcv_transpose_pad", a.ptr, a.plane, a.n, a.h, a.w, a.c, mul, oy, ox, row, shift, t.data_ptr(),
+                   a.c * ktot, ktot)
+        return t
+
+    def _wgrad(self, d: ConvDesc, xa: Act, dz: Act, dz_c: int, dw: torch.Tensor, mul=1, oy=0, ox=0, xt=None):
+        """dw += weight gradient of the conv described by the forward descriptor ``d``.  Stride-1 zero-padded
+        taps within one pixel run on the tensor cores; everything else (stride-2, reflect) on CUDA cores.
+        Returns the channel-major copy of x (reusable by the other phases of a deconv)."""
+        taps_ok = all(abs(d.dy[t]) <= 1 and abs(d.dx[t]) <= 1 for t in range(d.ntaps))
+        if not (self.use_tc_wgrad and d.stride == 1 and d.pad_mode == PAD_ZERO and taps_ok and dz_c % 8 == 0):
+            self._call("tcv_conv2d_wgrad", C.byref(d), dz.ptr, dz.plane, dz_c, dw.data_ptr())
+            return None
+        gh, gw = d.gh, d.gw
+        assert (gh, gw) == (xa.h, xa.w) and (dz.h, dz.w) == (gh * mul, gw * mul) and dz.c == dz_c
+        row = (gw + 2 + 7) // 8 * 8                  # 16-byte aligned rows: vertical tap shifts stay TMA-legal
+        ktot = xa.n * (gh + 2) * row
+        if xt is None:
+            xt = self._transpose_pad(xa, 1, 0, 0, row, 0, ktot)
+        cin = xa.c
+        tiles = ((cin + 127) // 128) * ((dz_c + 127) // 128)
+        nsplit = max(1, min(ktot // 2048, (2 * 148 + tiles - 1) // tiles))
+        partial = torch.empty((nsplit, cin, dz_c), dtype=torch.float32, device=self.device)
+        for sx in sorted({d.dx[t] for t in range(d.ntaps)}):
+            # horizontal offset baked into a shifted copy of dz: sum_p x[p + dy*row + sx] z[p] = sum_q x[q + dy*row] z[q - sx]
+            zt = self._transpose_pad(dz, mul, oy, ox, row, sx, ktot)
+            ts = [t for t in range(d.ntaps) if d.dx[t] == sx]
+            IntArr = C.c_int * len(ts)
+            dy, dx = IntArr(*[d.dy[t] for t in ts]), IntArr(*([0] * len(ts)))
+            wt = IntArr(*[d.wtap[t] for t in ts])
+            self._call("tcv_wgrad_tc", xt.data_ptr(), cin * ktot, zt.data_ptr(), dz_c * ktot, cin, dz_c, ktot, row, len(ts),
+                       dy, dx, wt, partial.data_ptr(), nsplit, dw.data_ptr(), dz_c)
+        return xt
+
     # ------------------------------------------------------------------ convolution (raw, no BatchNorm)
     def _fwd_geometry(self, x: Act, k: int, stride: int, prepadded: bool):
         if k == 3 and prepadded:
@@ -204,7 +244,7 @@ class TrainEngine(GcaVmnEngine):
             if dz is None:
                 return
             L = _cabi.lib()
-            self._call("tcv_conv2d_wgrad", C.byref(d), dz.ptr, dz.plane, cpad, self._dw(wkey, cpad).data_ptr())
+            self._wgrad(d, xa, dz, cpad, self._dw(wkey, cpad))
             if bias:
                 db = self.dbias.setdefault(wkey, torch.zeros((cpad,), dtype=torch.float32, device=self.device))
                 self._call("tcv_channel_sum", dz.ptr, dz.plane, dz.n * dz.h * dz.w, cpad, db.data_ptr())
@@ -280,8 +320,9 @@ class TrainEngine(GcaVmnEngine):
             dz = z.g
             if dz is None:
                 return
-            for d in descs:
-                self._call("tcv_conv2d_wgrad", C.byref(d), dz.ptr, dz.plane, cout, self._dw(wkey).data_ptr())
+            xt = None
+            for i, d in enumerate(descs):
+                xt = self._wgrad(d, xa, dz, cout, self._dw(wkey), mul=2, oy=i // 2, ox=i % 2, xt=xt)
             if x.needs_grad:
                 te = self.w[wkey + "#T"]
                 dx = self._act(xa.n, xa.h, xa.w, xa.c)
