@@ -366,64 +366,89 @@ def train_preprocess(a, fg, bg, radii, eps=0.0):
     return dict(imgs=imgs, fgs=fgs, bgs=bgs, gts=gts, tris=onehot, trimask=trimask, x6=torch.cat([norm, onehot], 2))
 
 
-def full_vmd_forward(sd: SD, a, fg, bg, radii, window=7, att_thres=0.3, label_smooth=0.2, eps=0.0, train=False):
+def vmd_losses(pp, preds, attb, attf, small, window=7, att_thres=0.3, label_smooth=0.2, rows=None):
+    """The loss half of FullModel_VMD.forward -- models/model.py:94-127 (L_im), :285-323 (L_af), :326-345 (L_tc) --
+    on the batch rows ``rows`` (a slice; default: the whole batch).  Returns (L_alpha, L_dt, L_att, alphas, comps)."""
+    sl = rows if rows is not None else slice(None)
+    gts, trimask = pp["gts"][sl], pp["trimask"][sl]
+    fgs, bgs = pp["fgs"][sl], pp["bgs"][sl]
+    B, S = gts.shape[:2]
+    preds = [p[sl] for p in preds]
+    alphas: List[Optional[torch.Tensor]] = [None] * S
+    comps: List[Optional[torch.Tensor]] = [None] * S
+    L_alpha = []
+    for c in range(1, S - 1):
+        m = trimask[:, c].float()
+        refine = torch.where(m.bool(), preds[c], gts[:, c])
+        alphas[c] = refine
+        comps[c] = fgs[:, c] * refine + bgs[:, c] * (1.0 - refine)
+        L_alpha.append(l1_mask(refine, gts[:, c], m))
+    L_alpha = sum(L_alpha) / float(len(L_alpha))
+    for i in (0, S - 1):
+        alphas[i] = torch.zeros_like(alphas[1])
+        comps[i] = torch.zeros_like(comps[1])
+    alphas_t = torch.stack(alphas, 1).clamp(0, 1)
+    comps_t = torch.stack(comps, 1).clamp(0, 1)
+    # attention-map loss
+    H8, W8 = gts.shape[-2] // 8, gts.shape[-1] // 8
+    L_att = []
+    bce = torch.nn.BCEWithLogitsLoss(reduction="mean")
+    for c in range(1, S - 1):
+        bgt = F.avg_pool2d(gts[:, c - 1], 8, 8)
+        fgt = F.avg_pool2d(gts[:, c + 1], 8, 8)
+        cgt = F.avg_pool2d(gts[:, c], 8, 8)
+        m = small[c][sl].reshape(B, -1)
+        if m.float().sum() == 0:
+            L_att.append(torch.zeros_like(L_alpha))
+            continue
+        bb = attb[c][sl].reshape(B, -1, H8 * W8).permute(1, 0, 2)[:, m]
+        ff = attf[c][sl].reshape(B, -1, H8 * W8).permute(1, 0, 2)[:, m]
+        bu = F.unfold(bgt, window, padding=window // 2).reshape(B, -1, H8 * W8).permute(1, 0, 2)[:, m]
+        fu = F.unfold(fgt, window, padding=window // 2).reshape(B, -1, H8 * W8).permute(1, 0, 2)[:, m]
+        cg = cgt.reshape(B, 1, H8 * W8).permute(1, 0, 2)[:, m]
+        tb = (torch.abs(cg - bu) < att_thres).float() * (1 - label_smooth)
+        tf = (torch.abs(cg - fu) < att_thres).float() * (1 - label_smooth)
+        L_att.append((bce(bb, tb) + bce(ff, tf)) / 2.0)
+    L_att = sum(L_att) / float(len(L_att))
+    if S >= 5:
+        L_dt = []
+        for c in range(1, S - 2):
+            L_dt.append(l1_mask(alphas_t[:, c] - alphas_t[:, c + 1], gts[:, c] - gts[:, c + 1], trimask[:, c]))
+        L_dt = sum(L_dt) / float(len(L_dt))
+    else:
+        L_dt = torch.zeros_like(L_att)
+    return L_alpha, L_dt, L_att, alphas_t, comps_t
+
+
+def full_vmd_forward(sd: SD, a, fg, bg, radii, window=7, att_thres=0.3, label_smooth=0.2, eps=0.0, train=False,
+                     rank_rows=None):
     """FullModel_VMD.forward for vmn_gca -- models/model.py:258-357 (single_image_loss :94-127, L_att :285-323,
     _dtSSD :326-345).  Returns the reference's 12-list.  ``train=False``: network in eval mode under no_grad
     (pred_vmn.py:107-116); ``train=True``: ``.train()`` semantics with autograd enabled (train_ddp.py:52-65) --
     ``sd`` is updated in place (u, v, running statistics) and its ``requires_grad`` leaves get gradients when
-    the caller backpropagates the returned losses."""
+    the caller backpropagates the returned losses.
+
+    ``rank_rows`` (list of batch slices) emulates DistributedDataParallel + SyncBatchNorm (train_ddp.py:270-280):
+    the network sees the whole batch (global BatchNorm statistics) while every rank computes the losses on its own
+    rows; the first five entries are then lists with one loss per rank (DDP averages the ranks' gradients, i.e.
+    differentiates the mean of the per-rank totals)."""
     with torch.no_grad():
         pp = train_preprocess(a, fg, bg, radii, eps)
     import contextlib
     with (TrainMode() if train else contextlib.nullcontext()), torch.set_grad_enabled(bool(train)):
-        B, S = a.shape[:2]
+        S = a.shape[1]
         frames = [pp["x6"][:, i] for i in range(S)]
         masks = [pp["trimask"][:, i] for i in range(S)]
         preds, attb, attf, small, _ = vmn_forward(sd, frames, masks, window)
         gts, trimask = pp["gts"], pp["trimask"]
-        alphas: List[Optional[torch.Tensor]] = [None] * S
-        comps: List[Optional[torch.Tensor]] = [None] * S
-        L_alpha = []
-        for c in range(1, S - 1):
-            m = trimask[:, c].float()
-            refine = torch.where(m.bool(), preds[c], gts[:, c])
-            alphas[c] = refine
-            comps[c] = pp["fgs"][:, c] * refine + pp["bgs"][:, c] * (1.0 - refine)
-            L_alpha.append(l1_mask(refine, gts[:, c], m))
-        L_alpha = sum(L_alpha) / float(len(L_alpha))
-        zero = torch.zeros_like(L_alpha)
-        for i in (0, S - 1):
-            alphas[i] = torch.zeros_like(alphas[1])
-            comps[i] = torch.zeros_like(comps[1])
-        alphas_t = torch.stack(alphas, 1).clamp(0, 1)
-        comps_t = torch.stack(comps, 1).clamp(0, 1)
-        # attention-map loss
-        H8, W8 = a.shape[-2] // 8, a.shape[-1] // 8
-        L_att = []
-        bce = torch.nn.BCEWithLogitsLoss(reduction="mean")
-        for c in range(1, S - 1):
-            bgt = F.avg_pool2d(gts[:, c - 1], 8, 8)
-            fgt = F.avg_pool2d(gts[:, c + 1], 8, 8)
-            cgt = F.avg_pool2d(gts[:, c], 8, 8)
-            m = small[c].reshape(B, -1)
-            if m.float().sum() == 0:
-                L_att.append(torch.zeros_like(L_alpha))
-                continue
-            bb = attb[c].reshape(B, -1, H8 * W8).permute(1, 0, 2)[:, m]
-            ff = attf[c].reshape(B, -1, H8 * W8).permute(1, 0, 2)[:, m]
-            bu = F.unfold(bgt, window, padding=window // 2).reshape(B, -1, H8 * W8).permute(1, 0, 2)[:, m]
-            fu = F.unfold(fgt, window, padding=window // 2).reshape(B, -1, H8 * W8).permute(1, 0, 2)[:, m]
-            cg = cgt.reshape(B, 1, H8 * W8).permute(1, 0, 2)[:, m]
-            tb = (torch.abs(cg - bu) < att_thres).float() * (1 - label_smooth)
-            tf = (torch.abs(cg - fu) < att_thres).float() * (1 - label_smooth)
-            L_att.append((bce(bb, tb) + bce(ff, tf)) / 2.0)
-        L_att = sum(L_att) / float(len(L_att))
-        if S >= 5:
-            L_dt = []
-            for c in range(1, S - 2):
-                L_dt.append(l1_mask(alphas_t[:, c] - alphas_t[:, c + 1], gts[:, c] - gts[:, c + 1], trimask[:, c]))
-            L_dt = sum(L_dt) / float(len(L_dt))
-        else:
-            L_dt = torch.zeros_like(L_att)
         tris_vis = torch.where(trimask.bool(), torch.ones_like(gts) * 128 * (1.0 / 255), gts)
+        if rank_rows is not None:
+            per = [vmd_losses(pp, preds, attb, attf, small, window, att_thres, label_smooth, rows=r) for r in rank_rows]
+            zero = [torch.zeros_like(p[0]) for p in per]
+            return [[p[0] for p in per], zero, [z.clone() for z in zero], [p[1] for p in per], [p[2] for p in per],
+                    pp["imgs"], tris_vis, torch.cat([p[3] for p in per]), torch.cat([p[4] for p in per]), gts,
+                    pp["fgs"], pp["bgs"]]
+        L_alpha, L_dt, L_att, alphas_t, comps_t = vmd_losses(pp, preds, attb, attf, small, window, att_thres,
+                                                             label_smooth)
+        zero = torch.zeros_like(L_alpha)
     return [L_alpha, zero, zero.clone(), L_dt, L_att, pp["imgs"], tris_vis, alphas_t, comps_t, gts, pp["fgs"], pp["bgs"]]

@@ -81,3 +81,17 @@ def test_train_mode_without_grad_runs_forward_only(model):
     with torch.no_grad():
         out = model(a, fg, bg)
     assert len(out) == 12 and all(torch.isfinite(o).all() for o in out[:5])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_ddp_syncbn_two_ranks():
+    """train_ddp.py's recipe (SyncBatchNorm + DistributedDataParallel over NCCL) on 2 GPUs: tools/ddp_check.py."""
+    import json
+    import subprocess
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tools", "ddp_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert line, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.loads(line[-1])
+    assert res["ok"], res
