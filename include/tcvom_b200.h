@@ -365,10 +365,17 @@ int tcv_gemm_f32_strided(const float* A, long long sam, long long sak, const flo
  *  values_bwd:  dV fp32 [n,P,2048] -> dfeat split [n,h,w,128] (gradient of the 4x4/stride-2 reflect-padded patches)
  *  prep_bwd:    dQ fp32 [n,P,576] += gradient through Kn = Q/max(|Q|,1e-4)*scale (dKn fp32 [n,P,576], Q fp32,
  *               mm, scales); then dg split [n,h/2,w/2,64] = gradient of the 3x3 reflect-padded patches */
-int tcv_gca_fold_bwd(const void* dY, const float* O, int n, int h, int w, float* dO, float* delta,
+int tcv_gca_fold_bwd(const void* dY, const float* O, int n, int h, int w, float* dO, float* delta, void* dO_split,
                      tcv_stream_t stream);
-int tcv_gca_softmax_bwd(const float* A, float* dA, const float* delta, int n, int P, int P_pad,
+int tcv_gca_softmax_bwd(const float* A, float* dA, const float* delta, int n, int P, int P_pad, void* dS_split,
                         tcv_stream_t stream);
+/* out[b][c][r] = in[b][r][c] on both planes of a split-bf16 matrix (rows x cols, row stride ld_in, batch stride bs_in
+ * elements); output rows of ld_out >= rows elements, zero-filled beyond `rows`.  Produces the K-major operands of the
+ * tensor-core GEMMs of the attention backward (dO_split / dS_split above are optional split-bf16 copies, planes
+ * n*P*2048 resp. n*P*P_pad elements apart). */
+int tcv_transpose_planes(const void* in, long long in_plane, int rows, int cols, long long ld_in, long long bs_in,
+                         void* out, long long out_plane, long long ld_out, long long bs_out, int batch,
+                         tcv_stream_t stream);
 int tcv_gca_values_bwd(const float* dV, int n, int h, int w, void* dfeat, tcv_stream_t stream);
 int tcv_gca_prep_bwd(float* dQ, const float* dKn, const float* Q, const float* mm, const float* scales, int n,
                      int h, int w, void* dg, tcv_stream_t stream);

@@ -136,8 +136,10 @@ SIGNATURES = {
                                        c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "tcv_gemm_f32_strided": (c_int, [c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll, c_void_p, c_ll, c_int, c_int, c_int,
                                      c_ll, c_ll, c_ll, c_int, c_int, c_void_p]),
-    "tcv_gca_fold_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "tcv_gca_softmax_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "tcv_gca_fold_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tcv_gca_softmax_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_transpose_planes": (c_int, [c_void_p, c_ll, c_int, c_int, c_ll, c_ll, c_void_p, c_ll, c_ll, c_ll, c_int,
+                                     c_void_p]),
     "tcv_gca_values_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_gca_prep_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                  c_void_p]),

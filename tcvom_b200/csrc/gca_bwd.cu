@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(256) gemm_f32_strided_kernel(const float* __re
 // one CTA of 128 threads per patch q: thread = channel, loop over the 16 taps
 __global__ void __launch_bounds__(128) gca_fold_bwd_kernel(const __nv_bfloat16* __restrict__ dY,
                                                            const float* __restrict__ O, int n, int h, int w,
-                                                           float* __restrict__ dO, float* __restrict__ delta) {
+                                                           float* __restrict__ dO, float* __restrict__ delta,
+                                                           __nv_bfloat16* __restrict__ dO_split) {
   __shared__ float red[4];
   const int hh = h / 2, ww = w / 2, P = hh * ww;
   const int q = blockIdx.x, img = blockIdx.y;
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(128) gca_fold_bwd_kernel(const __nv_bfloat16* 
     if (y >= 0 && y < h && x >= 0 && x < w)
       v = 0.25f * load1(dY + (((long long)img * h + y) * w + x) * FC + c, plane);
     dO[row + t * FC + c] = v;
+    if (dO_split) store1(dO_split + row + t * FC + c, (long long)n * P * VD, v);
     dot = fmaf(v, O[row + t * FC + c], dot);
   }
   dot = warp_sum(dot);
@@ -103,12 +105,46 @@ __global__ void __launch_bounds__(128) gca_fold_bwd_kernel(const __nv_bfloat16* 
 }
 
 __global__ void gca_softmax_bwd_kernel(const float* __restrict__ A, float* __restrict__ dA,
-                                       const float* __restrict__ delta, int P, int P_pad, long long rows) {
+                                       const float* __restrict__ delta, int P, int P_pad, long long rows,
+                                       __nv_bfloat16* __restrict__ dS_split) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * P_pad) return;
   const long long r = i / P_pad;
   const int p = (int)(i - r * P_pad);
-  dA[i] = p < P ? A[i] * (dA[i] - delta[r]) : 0.f;
+  const float v = p < P ? A[i] * (dA[i] - delta[r]) : 0.f;
+  dA[i] = v;
+  if (dS_split) store1(dS_split + i, rows * P_pad, v);
+}
+
+// out[b][c][r] = in[b][r][c] for both planes of a split-bf16 matrix (raw 16-bit moves), r >= rows zero-filled up to ld_out
+__global__ void __launch_bounds__(256) transpose_planes_kernel(const uint16_t* __restrict__ in, long long in_plane,
+                                                               int rows, int cols, long long ld_in, long long bs_in,
+                                                               uint16_t* __restrict__ out, long long out_plane,
+                                                               long long ld_out, long long bs_out) {
+  __shared__ uint16_t tile[2][32][34];
+  const int b = blockIdx.z;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int rr = ty; rr < 32; rr += 8) {
+    const int r = r0 + rr, c = c0 + tx;
+    uint16_t a = 0, l = 0;
+    if (r < rows && c < cols) {
+      const long long src = (long long)b * bs_in + (long long)r * ld_in + c;
+      a = in[src];
+      l = in[src + in_plane];
+    }
+    tile[0][rr][tx] = a;
+    tile[1][rr][tx] = l;
+  }
+  __syncthreads();
+  for (int cc = ty; cc < 32; cc += 8) {
+    const int c = c0 + cc, r = r0 + tx;
+    if (c < cols && r < ld_out) {
+      const long long dst = (long long)b * bs_out + (long long)c * ld_out + r;
+      out[dst] = tile[0][tx][cc];
+      out[dst + out_plane] = tile[1][tx][cc];
+    }
+  }
 }
 
 // dfeat[y][x][c] = sum over (py,ty),(px,tx) with reflect(2py+ty-1) = y, reflect(2px+tx-1) = x of dV[p][(ty*4+tx)*128+c]
@@ -237,21 +273,34 @@ int tcv_gemm_f32_strided(const float* A, long long sam, long long sak, const flo
   return launched("gemm_f32_strided_kernel");
 }
 
-int tcv_gca_fold_bwd(const void* dY, const float* O, int n, int h, int w, float* dO, float* delta,
+int tcv_transpose_planes(const void* in, long long in_plane, int rows, int cols, long long ld_in, long long bs_in,
+                         void* out, long long out_plane, long long ld_out, long long bs_out, int batch,
+                         tcv_stream_t stream) {
+  TCV_REQUIRE(in && out && rows > 0 && cols > 0 && ld_in >= cols && ld_out >= rows && batch > 0,
+              "transpose_planes: bad arguments");
+  dim3 grid((cols + 31) / 32, (unsigned)((ld_out + 31) / 32), batch);
+  transpose_planes_kernel<<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const uint16_t*>(in), in_plane, rows, cols, ld_in,
+                                                      bs_in, reinterpret_cast<uint16_t*>(out), out_plane, ld_out, bs_out);
+  return launched("transpose_planes_kernel");
+}
+
+int tcv_gca_fold_bwd(const void* dY, const float* O, int n, int h, int w, float* dO, float* delta, void* dO_split,
                      tcv_stream_t stream) {
   TCV_REQUIRE(dY && O && dO && delta, "gca_fold_bwd: null pointer");
   TCV_REQUIRE(h % 2 == 0 && w % 2 == 0 && h >= 4 && w >= 4, "gca_fold_bwd: h,w must be even and >= 4");
   dim3 grid((h / 2) * (w / 2), n);
-  gca_fold_bwd_kernel<<<grid, 128, 0, S(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(dY), O, n, h, w, dO, delta);
+  gca_fold_bwd_kernel<<<grid, 128, 0, S(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(dY), O, n, h, w, dO, delta,
+                                                   reinterpret_cast<__nv_bfloat16*>(dO_split));
   return launched("gca_fold_bwd_kernel");
 }
 
-int tcv_gca_softmax_bwd(const float* A, float* dA, const float* delta, int n, int P, int P_pad,
+int tcv_gca_softmax_bwd(const float* A, float* dA, const float* delta, int n, int P, int P_pad, void* dS_split,
                         tcv_stream_t stream) {
   TCV_REQUIRE(A && dA && delta && P > 0 && P_pad >= P, "gca_softmax_bwd: bad arguments");
   const long long rows = (long long)n * P;
   const long long total = rows * P_pad;
-  gca_softmax_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(A, dA, delta, P, P_pad, rows);
+  gca_softmax_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(A, dA, delta, P, P_pad, rows,
+                                                                                reinterpret_cast<__nv_bfloat16*>(dS_split));
   return launched("gca_softmax_bwd_kernel");
 }
 

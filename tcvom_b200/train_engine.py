@@ -501,52 +501,90 @@ class TrainEngine(GcaVmnEngine):
                    P_pad, P * P_pad, n, 3, 0, 0)
         Pb = torch.empty((2, n, P, P_pad), dtype=torch.bfloat16, device=dev)
         self._call("tcv_gca_softmax", Sm.data_ptr(), mm.data_ptr(), n, P, P_pad, Pb.data_ptr(), 2)
-        del Sm, Q, Kn
+        del Sm
         self._call("tcv_gemm_tn_tc", Pb.data_ptr(), n * P * P_pad, Vt.data_ptr(), n * 2048 * P_pad, O.data_ptr(), P, 2048,
                    P_pad, 2048, P * 2048, n, 3, 0, 0)
-        del Vt
+        if not self.use_tc_attn:
+            Q = Kn = Vt = None
         Ya = self._act(n, h, w, 128)
         self._call("tcv_gca_fold", O.data_ptr(), n, h, w, Ya.ptr)
         Y = TAct(Ya, feat.groups)
+
+        bf16 = torch.bfloat16
+
+        def transpose(src, rows, cols, ld_in, ld_out):
+            """split-bf16 [2][n][rows][ld_in] -> [2][n][cols][ld_out] (K-major operand of the next GEMM)"""
+            out = torch.empty((2, n, cols, ld_out), dtype=bf16, device=dev)
+            self._call("tcv_transpose_planes", src.data_ptr(), n * rows * ld_in, rows, cols, ld_in, rows * ld_in,
+                       out.data_ptr(), n * cols * ld_out, ld_out, cols * ld_out, n)
+            return out
+
+        def gemm_tc(A_, a_rows, B_, b_rows, K_, C_, ldc):
+            """C[n][a_rows][ldc] = A[n][a_rows][K] . B[n][b_rows][K]^T on the tensor cores (bf16x3)"""
+            self._call("tcv_gemm_tn_tc", A_.data_ptr(), n * a_rows * K_, B_.data_ptr(), n * b_rows * K_, C_.data_ptr(),
+                       a_rows, b_rows, K_, ldc, a_rows * ldc, n, 3, 0, 0)
 
         def backward():
             dY = Y.g
             if dY is None:
                 return
+            tc = self.use_tc_attn
             dO = torch.empty((n, P, 2048), dtype=f32, device=dev)
+            dO_s = torch.empty((2, n, P, 2048), dtype=bf16, device=dev) if tc else None
             delta = torch.empty((n, P), dtype=f32, device=dev)
-            self._call("tcv_gca_fold_bwd", dY.ptr, O.data_ptr(), n, h, w, dO.data_ptr(), delta.data_ptr())
+            self._call("tcv_gca_fold_bwd", dY.ptr, O.data_ptr(), n, h, w, dO.data_ptr(), delta.data_ptr(),
+                       dO_s.data_ptr() if tc else None)
             A = torch.empty((n, P, P_pad), dtype=f32, device=dev)
             self._call("tcv_split_to_f32", Pb.data_ptr(), n * P * P_pad, n * P * P_pad, A.data_ptr())
-            V32 = torch.empty((n, 2048, P_pad), dtype=f32, device=dev)
-            self._call("tcv_gca_values", fa.ptr, n, h, w, V32.data_ptr(), 0)
             dA = torch.empty((n, P, P_pad), dtype=f32, device=dev)
-            # dA[q,p] = sum_d dO[q,d] * Vt[d,p]
-            self._call("tcv_gemm_f32_strided", dO.data_ptr(), 2048, 1, V32.data_ptr(), 1, P_pad, dA.data_ptr(), P_pad,
-                       P, P, 2048, P * 2048, 2048 * P_pad, P * P_pad, n, 0)
-            self._call("tcv_gca_softmax_bwd", A.data_ptr(), dA.data_ptr(), delta.data_ptr(), n, P, P_pad)
-            dS = dA
-            if feat.needs_grad:
-                # dV[p,d] = sum_q A[q,p] * dO[q,d]
-                dV = torch.empty((n, P, 2048), dtype=f32, device=dev)
-                self._call("tcv_gemm_f32_strided", A.data_ptr(), 1, P_pad, dO.data_ptr(), 1, 2048, dV.data_ptr(), 2048,
-                           P, 2048, P, P * P_pad, P * 2048, P * 2048, n, 0)
-                dfeat = self._act(n, h, w, 128)
-                self._call("tcv_gca_values_bwd", dV.data_ptr(), n, h, w, dfeat.ptr)
-                self._acc(feat, dfeat, True)
-            Q32 = torch.empty((n, P, 576), dtype=f32, device=dev)
-            K32 = torch.empty((n, P, 576), dtype=f32, device=dev)
-            mm2 = torch.empty((n, P), dtype=f32, device=dev)
-            sc2 = torch.empty((n, 2), dtype=f32, device=dev)
-            self._call("tcv_gca_prep", ga.ptr, unknown.data_ptr(), n, h, w, Q32.data_ptr(), K32.data_ptr(),
-                       mm2.data_ptr(), sc2.data_ptr(), 0)
-            dQ = torch.empty((n, P, 576), dtype=f32, device=dev)
-            dKn = torch.empty((n, P, 576), dtype=f32, device=dev)
-            # dQ[q,c] = sum_p dS[q,p] * Kn[p,c] ; dKn[p,c] = sum_q dS[q,p] * Q[q,c]
-            self._call("tcv_gemm_f32_strided", dS.data_ptr(), P_pad, 1, K32.data_ptr(), 1, 576, dQ.data_ptr(), 576,
-                       P, 576, P, P * P_pad, P * 576, P * 576, n, 0)
-            self._call("tcv_gemm_f32_strided", dS.data_ptr(), 1, P_pad, Q32.data_ptr(), 1, 576, dKn.data_ptr(), 576,
-                       P, 576, P, P * P_pad, P * 576, P * 576, n, 0)
+            if tc:
+                # dA[q,p] = sum_d dO[q,d] V[p,d]
+                V_s = transpose(Vt, 2048, P, P_pad, 2048)
+                gemm_tc(dO_s, P, V_s, P, 2048, dA, P_pad)
+                del V_s
+                dS_s = torch.empty((2, n, P, P_pad), dtype=bf16, device=dev)
+                self._call("tcv_gca_softmax_bwd", A.data_ptr(), dA.data_ptr(), delta.data_ptr(), n, P, P_pad,
+                           dS_s.data_ptr())
+                if feat.needs_grad:
+                    # dV[p,d] = sum_q A[q,p] dO[q,d]
+                    dV = torch.empty((n, P, 2048), dtype=f32, device=dev)
+                    gemm_tc(transpose(Pb, P, P, P_pad, P_pad), P, transpose(dO_s, P, 2048, 2048, P_pad), 2048, P_pad, dV, 2048)
+                    dfeat = self._act(n, h, w, 128)
+                    self._call("tcv_gca_values_bwd", dV.data_ptr(), n, h, w, dfeat.ptr)
+                    self._acc(feat, dfeat, True)
+                Q32 = torch.empty((n, P, 576), dtype=f32, device=dev)
+                self._call("tcv_split_to_f32", Q.data_ptr(), n * P * 576, n * P * 576, Q32.data_ptr())
+                dQ = torch.empty((n, P, 576), dtype=f32, device=dev)
+                dKn = torch.empty((n, P, 576), dtype=f32, device=dev)
+                # dQ[q,c] = sum_p dS[q,p] Kn[p,c] ; dKn[p,c] = sum_q dS[q,p] Q[q,c]
+                gemm_tc(dS_s, P, transpose(Kn, P, 576, 576, P_pad), 576, P_pad, dQ, 576)
+                gemm_tc(transpose(dS_s, P, P, P_pad, P_pad), P, transpose(Q, P, 576, 576, P_pad), 576, P_pad, dKn, 576)
+            else:
+                V32 = torch.empty((n, 2048, P_pad), dtype=f32, device=dev)
+                self._call("tcv_gca_values", fa.ptr, n, h, w, V32.data_ptr(), 0)
+                self._call("tcv_gemm_f32_strided", dO.data_ptr(), 2048, 1, V32.data_ptr(), 1, P_pad, dA.data_ptr(), P_pad,
+                           P, P, 2048, P * 2048, 2048 * P_pad, P * P_pad, n, 0)
+                self._call("tcv_gca_softmax_bwd", A.data_ptr(), dA.data_ptr(), delta.data_ptr(), n, P, P_pad, None)
+                dS = dA
+                if feat.needs_grad:
+                    dV = torch.empty((n, P, 2048), dtype=f32, device=dev)
+                    self._call("tcv_gemm_f32_strided", A.data_ptr(), 1, P_pad, dO.data_ptr(), 1, 2048, dV.data_ptr(), 2048,
+                               P, 2048, P, P * P_pad, P * 2048, P * 2048, n, 0)
+                    dfeat = self._act(n, h, w, 128)
+                    self._call("tcv_gca_values_bwd", dV.data_ptr(), n, h, w, dfeat.ptr)
+                    self._acc(feat, dfeat, True)
+                Q32 = torch.empty((n, P, 576), dtype=f32, device=dev)
+                K32 = torch.empty((n, P, 576), dtype=f32, device=dev)
+                mm2 = torch.empty((n, P), dtype=f32, device=dev)
+                sc2 = torch.empty((n, 2), dtype=f32, device=dev)
+                self._call("tcv_gca_prep", ga.ptr, unknown.data_ptr(), n, h, w, Q32.data_ptr(), K32.data_ptr(),
+                           mm2.data_ptr(), sc2.data_ptr(), 0)
+                dQ = torch.empty((n, P, 576), dtype=f32, device=dev)
+                dKn = torch.empty((n, P, 576), dtype=f32, device=dev)
+                self._call("tcv_gemm_f32_strided", dS.data_ptr(), P_pad, 1, K32.data_ptr(), 1, 576, dQ.data_ptr(), 576,
+                           P, 576, P, P * P_pad, P * 576, P * 576, n, 0)
+                self._call("tcv_gemm_f32_strided", dS.data_ptr(), 1, P_pad, Q32.data_ptr(), 1, 576, dKn.data_ptr(), 576,
+                           P, 576, P, P * P_pad, P * 576, P * 576, n, 0)
             dg = self._act(n, h // 2, w // 2, 64)
             self._call("tcv_gca_prep_bwd", dQ.data_ptr(), dKn.data_ptr(), Q32.data_ptr(), mm.data_ptr(),
                        scales.data_ptr(), n, h, w, dg.ptr)
