@@ -338,7 +338,8 @@ int tcv_conv2d_wgrad(const tcv_conv_desc* d, const void* dz, long long dz_plane,
  *                 rows of ktot elements (ktot % 8 == 0, ktot >= n*(gh+2)*row_stride), lo plane xt_plane elements
  *                 after the hi plane.  shift in {-1,0,1} bakes a horizontal tap offset into the copy.
  *  wgrad_tc:      dw[wtap[t]][ci][co] += sum_p xt[ci][p + dy[t]*row_stride + dx[t]] * zt[co][p]:
- *                 one split-K tcgen05 GEMM (bf16x3) per tap; partial fp32 [nsplit][cin][cout] workspace.
+ *                 split-K tcgen05 GEMMs (bf16x3), one per tap or -- for <= 64 output channels -- one per call with the
+ *                 (up to 3) taps stacked along N; partial fp32 [nsplit][cin][3*cout] workspace.
  *                 dy[t]*row_stride + dx[t] must be a multiple of 8 (TMA needs 16-byte aligned inner coordinates):
  *                 use row_stride % 8 == 0, dx = 0 and a zt copy shifted by the tap's horizontal offset. */
 int tcv_transpose_pad(const void* x, long long x_plane, int n, int h, int w, int c, int mul, int off_y, int off_x,

@@ -35,6 +35,10 @@ struct TcParams {
   // [rows][K] operand pair instead of a batch entry; koff shifts the A operand along K (filter-tap offset in the
   // zero-ringed channel-major activation; TMA zero-fills coordinates outside [0, K))
   int split_k, koff;
+  // stacked-B mode (weight gradients of <= 64-channel layers): the B tile is nstack sub-tiles of sub_rows rows, sub-tile
+  // j loaded at K offset -bkoff[j] (vertical filter taps), so one MMA of N = nstack*sub_rows columns serves nstack taps
+  int nstack, sub_rows, bkoff[3];
+  uint32_t stage_tx;  // bytes per pipeline stage when they differ from the full tile (0: Cfg::STAGE_BYTES)
   // conv epilogue
   int n_imgs, oh, ow, cout, oy_mul, oy_off, ox_mul, ox_off;
   __nv_bfloat16* y;
@@ -127,13 +131,22 @@ __global__ void __launch_bounds__(320) igemm_tc_kernel(const __grid_constant__ C
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
           if (elect_one()) {
-            mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+            mbar_expect_tx(full_bar(s), p.stage_tx ? p.stage_tx : (uint32_t)Cfg::STAGE_BYTES);
             const int ka = kbase + kc * BK + p.koff, kb = kbase + kc * BK;
             tma_load_4d(st, &mapA_hi, full_bar(s), ka, cw, ch, aimg);
-            tma_load_3d(st + Cfg::PLANES * Cfg::A_BYTES, &mapB_hi, full_bar(s), kb, n0, bz);
-            if (NSPLIT >= 3) {
-              tma_load_4d(st + Cfg::A_BYTES, &mapA_lo, full_bar(s), ka, cw, ch, aimg);
-              tma_load_3d(st + Cfg::PLANES * Cfg::A_BYTES + Cfg::B_BYTES, &mapB_lo, full_bar(s), kb, n0, bz);
+            if (NSPLIT >= 3) tma_load_4d(st + Cfg::A_BYTES, &mapA_lo, full_bar(s), ka, cw, ch, aimg);
+            if (p.nstack > 1) {
+              const uint32_t sub = (uint32_t)p.sub_rows * BK * 2;
+              for (int j = 0; j < p.nstack; ++j) {
+                tma_load_3d(st + Cfg::PLANES * Cfg::A_BYTES + j * sub, &mapB_hi, full_bar(s), kb - p.bkoff[j], 0, 0);
+                if (NSPLIT >= 3)
+                  tma_load_3d(st + Cfg::PLANES * Cfg::A_BYTES + Cfg::B_BYTES + j * sub, &mapB_lo, full_bar(s),
+                              kb - p.bkoff[j], 0, 0);
+              }
+            } else {
+              tma_load_3d(st + Cfg::PLANES * Cfg::A_BYTES, &mapB_hi, full_bar(s), kb, n0, bz);
+              if (NSPLIT >= 3)
+                tma_load_3d(st + Cfg::PLANES * Cfg::A_BYTES + Cfg::B_BYTES, &mapB_lo, full_bar(s), kb, n0, bz);
             }
             if (NSPLIT == 6) {
               tma_load_4d(st + 2 * Cfg::A_BYTES, &mapA_p2, full_bar(s), ka, cw, ch, aimg);
@@ -330,7 +343,7 @@ static int launch_tc(const TcOperands& o, TcParams& p, cudaStream_t st) {
   {
     cuuint64_t dims[3] = {(cuuint64_t)o.c, (cuuint64_t)o.b_rows, (cuuint64_t)o.b_z};
     cuuint64_t str[2] = {(cuuint64_t)o.c * 2, (cuuint64_t)o.b_rows * o.c * 2};
-    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(p.nstack > 1 ? p.sub_rows : BN), 1};
     int rc = make_map(&mB_hi, o.b, 3, dims, str, box, BK, o.fp16);
     if (rc) return rc;
     rc = make_map(&mB_lo, NSPLIT >= 3 ? o.b + o.b_plane : o.b, 3, dims, str, box, BK);
@@ -338,7 +351,9 @@ static int launch_tc(const TcOperands& o, TcParams& p, cudaStream_t st) {
     rc = make_map(&mB_p2, NSPLIT == 6 ? o.b + 2 * o.b_plane : o.b, 3, dims, str, box, BK);
     if (rc) return rc;
   }
-  p.idesc = instr_desc(BN, o.fp16);
+  p.idesc = instr_desc(p.nstack > 1 ? p.nstack * p.sub_rows : BN, o.fp16);
+  if (p.nstack > 1)
+    p.stage_tx = (uint32_t)(Cfg::PLANES * (Cfg::A_BYTES + p.nstack * p.sub_rows * BK * 2));
   auto kern = igemm_tc_kernel<BN, BK, NSPLIT, EPI>;
   TCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));  // per device
   p.tiles_x = (p.gw + p.TW - 1) / p.TW;
@@ -451,15 +466,18 @@ extern "C" int tcv_gemm_tn_tc(const void* A, long long a_plane, const void* B, l
 // zero-ringed channel-major copies of the activation and of the output gradient (tcv_transpose_pad), bf16x3,
 // partial sums per K slice in `partial`, then one reduction kernel.
 namespace tcv {
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit, int ntaps, int cin, int cout,
-                                    const int* __restrict__ wtap_dev, int t0, int wt, float* __restrict__ dw,
-                                    int dw_cout) {
+// partial [nsplit][cin][nstack*cout] -> dw[wt[j]][ci][co] += sum over slices
+struct WgTaps { int wt[3]; };
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit, int nstack, int cin, int cout,
+                                    WgTaps taps, float* __restrict__ dw, int dw_cout) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= cin * cout) return;
-  const int ci = i / cout, co = i - ci * cout;
+  const int ncol = nstack * cout;
+  if (i >= cin * ncol) return;
+  const int ci = i / ncol, col = i - ci * ncol;
+  const int j = col / cout, co = col - j * cout;
   float s = 0.f;
-  for (int k = 0; k < nsplit; ++k) s += partial[((long long)k * cin + ci) * cout + co];
-  dw[((long long)wt * cin + ci) * dw_cout + co] += s;
+  for (int k = 0; k < nsplit; ++k) s += partial[((long long)k * cin + ci) * ncol + col];
+  dw[((long long)taps.wt[j] * cin + ci) * dw_cout + co] += s;
 }
 }  // namespace tcv
 
@@ -479,15 +497,26 @@ extern "C" int tcv_wgrad_tc(const void* xt, long long xt_plane, const void* zt, 
   long long chunk = (ktot + nsplit - 1) / nsplit;
   chunk = (chunk + 31) / 32 * 32;
   const int slices = (int)((ktot + chunk - 1) / chunk);
-  for (int t = 0; t < ntaps; ++t) {
+  // <= 64 output channels: the (up to 3) taps of this call are stacked along N (one GEMM, A streamed once)
+  const bool stack = ntaps > 1 && ntaps <= 3 && cout % 8 == 0 && ntaps * cout <= 256 && (ntaps * cout) % 16 == 0;
+  for (int t = 0; t < ntaps; t += stack ? ntaps : 1) {
     TcParams p;
     memset(&p, 0, sizeof(p));
     p.gh = 1; p.gw = cin; p.TH = 1; p.TW = 128;
     p.ntaps = 1; p.kc_iters = (int)(chunk / 32); p.stride = 1;
     p.b_batched = 1;
     p.split_k = (int)chunk;
-    p.koff = dy[t] * row_stride + dx[t];
-    p.c = partial; p.ldc = cout; p.c_batch_stride = (long long)cin * cout; p.M = cin; p.N = cout;
+    WgTaps wt;
+    wt.wt[0] = wt.wt[1] = wt.wt[2] = wtap[t];
+    const int ns = stack ? ntaps : 1;
+    if (stack) {
+      p.nstack = ntaps; p.sub_rows = cout;
+      for (int j = 0; j < ntaps; ++j) { p.bkoff[j] = dy[j] * row_stride + dx[j]; wt.wt[j] = wtap[j]; }
+    } else {
+      p.koff = dy[t] * row_stride + dx[t];
+    }
+    const int ncol = ns * cout;
+    p.c = partial; p.ldc = ncol; p.c_batch_stride = (long long)cin * ncol; p.M = cin; p.N = ncol;
     TcOperands o;
     o.a = reinterpret_cast<const __nv_bfloat16*>(xt);
     o.a_plane = xt_plane;
@@ -498,12 +527,16 @@ extern "C" int tcv_wgrad_tc(const void* xt, long long xt_plane, const void* zt, 
     o.fp16 = false;
     o.grid_z = slices;
     int rc;
-    if (cout % 128 == 0) rc = launch_tc<128, 32, 3, EPI_F32>(o, p, st);
+    if (stack) {
+      if (ncol > 128) rc = launch_tc<256, 32, 3, EPI_F32>(o, p, st);
+      else if (ncol > 64) rc = launch_tc<128, 32, 3, EPI_F32>(o, p, st);
+      else if (ncol > 32) rc = launch_tc<64, 32, 3, EPI_F32>(o, p, st);
+      else rc = launch_tc<32, 32, 3, EPI_F32>(o, p, st);
+    } else if (cout % 128 == 0) rc = launch_tc<128, 32, 3, EPI_F32>(o, p, st);
     else if (cout % 64 == 0) rc = launch_tc<64, 32, 3, EPI_F32>(o, p, st);
     else rc = launch_tc<32, 32, 3, EPI_F32>(o, p, st);
     if (rc) return rc;
-    wgrad_reduce_kernel<<<(cin * cout + 255) / 256, 256, 0, st>>>(partial, slices, ntaps, cin, cout, nullptr, t, wtap[t],
-                                                                 dw, dw_cout);
+    wgrad_reduce_kernel<<<(cin * ncol + 255) / 256, 256, 0, st>>>(partial, slices, ns, cin, cout, wt, dw, dw_cout);
     rc = launched("wgrad_reduce_kernel");
     if (rc) return rc;
   }

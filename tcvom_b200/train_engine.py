@@ -178,7 +178,7 @@ class TrainEngine(GcaVmnEngine):
     def _transpose_pad(self, a: Act, mul: int, oy: int, ox: int, row: int, shift: int, ktot: int) -> torch.Tensor:
         t = torch.empty((2, a.c, ktot), dtype=torch.bfloat16, device=self.device)
         self._call("tcv_transpose_pad", a.ptr, a.plane, a.n, a.h, a.w, a.c, mul, oy, ox, row, shift, t.data_ptr(),
-                   a.c * ktot, ktot)
+                   a.c * ktot, ktot, meta=dict(tag=f"c{a.c} K{ktot}"))
         return t
 
     def _wgrad(self, d: ConvDesc, xa: Act, dz: Act, dz_c: int, dw: torch.Tensor, mul=1, oy=0, ox=0, xt=None):
@@ -198,7 +198,7 @@ class TrainEngine(GcaVmnEngine):
         cin = xa.c
         tiles = ((cin + 127) // 128) * ((dz_c + 127) // 128)
         nsplit = max(1, min(ktot // 2048, (2 * 148 + tiles - 1) // tiles))
-        partial = torch.empty((nsplit, cin, dz_c), dtype=torch.float32, device=self.device)
+        partial = torch.empty((nsplit, cin, 3 * dz_c), dtype=torch.float32, device=self.device)
         for sx in sorted({d.dx[t] for t in range(d.ntaps)}):
             # horizontal offset baked into a shifted copy of dz: sum_p x[p + dy*row + sx] z[p] = sum_q x[q + dy*row] z[q - sx]
             zt = self._transpose_pad(dz, mul, oy, ox, row, sx, ktot)
@@ -207,7 +207,8 @@ class TrainEngine(GcaVmnEngine):
             dy, dx = IntArr(*[d.dy[t] for t in ts]), IntArr(*([0] * len(ts)))
             wt = IntArr(*[d.wtap[t] for t in ts])
             self._call("tcv_wgrad_tc", xt.data_ptr(), cin * ktot, zt.data_ptr(), dz_c * ktot, cin, dz_c, ktot, row, len(ts),
-                       dy, dx, wt, partial.data_ptr(), nsplit, dw.data_ptr(), dz_c)
+                       dy, dx, wt, partial.data_ptr(), nsplit, dw.data_ptr(), dz_c,
+                       meta=dict(tag=f"cin{cin} cout{dz_c} K{ktot} taps{len(ts)} split{nsplit}"))
         return xt
 
     # ------------------------------------------------------------------ convolution (raw, no BatchNorm)

@@ -88,6 +88,12 @@ def main():
         for name, tag, x0, x1 in eng._prof:
             agg[name][0] += x0.elapsed_time(x1)
             agg[name][1] += 1
+        top = collections.defaultdict(lambda: [0.0, 0])
+        for name, tag, x0, x1 in eng._prof:
+            if tag:
+                top[name + " " + tag][0] += x0.elapsed_time(x1)
+                top[name + " " + tag][1] += 1
+        res["top_tagged_ms"] = {k: [round(v[0], 3), v[1]] for k, v in sorted(top.items(), key=lambda kv: -kv[1][0])[:24]}
         eng._prof = None
         res["breakdown_ms"] = {k: [round(v[0], 3), v[1]] for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
     print(json.dumps(res))

@@ -54,7 +54,7 @@ def run(name):
     Arr = C.c_int * nt
     dy, dx, wt = Arr(*[t[0] for t in taps]), Arr(*[t[1] for t in taps]), Arr(*range(nt))
     nsplit = 3
-    partial = torch.empty((nsplit, c["cin"], c["cout"]), device="cuda")
+    partial = torch.empty((nsplit, c["cin"], 3 * c["cout"]), device="cuda")
     dw = torch.zeros((nt, c["cin"], c["cout"]), device="cuda")
     for sx in sorted({t[1] for t in taps}):
         _cabi.check(L.tcv_transpose_pad(za.ptr, za.plane, za.n, za.h, za.w, za.c, 1, 0, 0, row, sx, zt.data_ptr(), c["cout"] * ktot, ktot, st), "tp")
