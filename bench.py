@@ -161,6 +161,67 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------- training step (configs[2] / [3])
+TRAIN_B, TRAIN_S, TRAIN_HW = 4, 5, 512
+TRAIN_GFLOP_PER_SAMPLE = 1310.95        # 5-frame sample, fwd+bwd, 512x512 (reference FlopCounterMode)
+LOSS_WEIGHTS = (1.0, 1.0, 1.0, 0.5, 0.25)   # train_ddp.py:61
+
+
+def run_train_section(args, rank, world, dev, barrier, max_over_ranks):
+    """Secondary measurement: the native training step (FullModel_VMD fwd + losses + bwd + Adam, train_ddp.py:52-65)
+    at BASELINE.json configs[2]'s shape, batch 4 per GPU; with N > 1 under SyncBatchNorm + DistributedDataParallel
+    over NCCL exactly like train_ddp.py:270-280 (configs[3]'s recipe).  Reported next to, not instead of, the
+    headline forward metric."""
+    import torch
+    import tcvom_b200
+    from tcvom_b200 import _cabi, synthetic
+    from helpers import fixture_sd
+    model = tcvom_b200.FullModel_VMD(model="vmn_gca", agg_window=7, dilate_kernel=None)
+    model.NET.load_state_dict(fixture_sd(), strict=True)
+    if world > 1:
+        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model).to(dev)
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], output_device=dev.index,
+                                                          find_unused_parameters=True)
+    else:
+        model = model.to(dev)
+    model.train()
+    a, fg, bg = (torch.from_numpy(t).float().to(dev)
+                 for t in synthetic.make_train_batch(TRAIN_B, TRAIN_S, TRAIN_HW, TRAIN_HW, seed=21 + 100 * rank))
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-5, weight_decay=1e-4)
+    torch.manual_seed(1234 + rank)
+
+    def step():
+        out = model(a, fg, bg)
+        loss = sum(w * o.mean() for w, o in zip(LOSS_WEIGHTS, out[:5]))
+        model.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(2):
+        step()
+    steps = 5
+    barrier()
+    n0 = _cabi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    samples = world * TRAIN_B
+    n_params = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    return dict(workload=f"GCA+TAM train step (L_im+L_tc+L_af fwd+bwd+Adam) {TRAIN_HW}x{TRAIN_HW} crop, batch {TRAIN_B}/GPU, "
+                         f"S={TRAIN_S} (configs[2]; N>1: SyncBatchNorm + DDP over NCCL, configs[3] recipe)",
+                ms_per_step=ms, samples_per_s=samples / (ms / 1e3),
+                centre_windows_per_s=samples * (TRAIN_S - 2) / (ms / 1e3),
+                algorithmic_tflops=samples * TRAIN_GFLOP_PER_SAMPLE / (ms / 1e3) / 1e3, steps=steps, warmup=2,
+                gpu_launches_per_step=(_cabi.launch_count() - n0) // steps, loss=float(loss.detach()),
+                grad_allreduce_mb=(4 * n_params / 1e6) if world > 1 else 0.0, sync_batchnorm=world > 1,
+                peak_mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30)
+
+
 # ------------------------------------------------------------------------------------- native arm
 def run_native(args, rank, world, local_rank):
     import torch
@@ -281,6 +342,13 @@ def run_native(args, rank, world, local_rank):
                     roof["traffic"] = t["dram_bytes_per_launch"]       # ncu dram__bytes_read+write, per launch
                     roof["algorithmic_bytes_per_launch"] = top["bytes"] / top["n"]
 
+    train = None
+    if not args.no_train:
+        model.NET.engine().plans.clear()           # release the forward plan's 10 GB of activations
+        del plan
+        torch.cuda.empty_cache()
+        train = run_train_section(args, rank, world, dev, barrier, max_over_ranks)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -308,7 +376,7 @@ def run_native(args, rank, world, local_rank):
                 e2e=dict(value=e2e_value, unit=UNIT, ms_per_step=ms_e2e / args.steps,
                          h2d_bytes_per_step=imgs_u8.numel() + tris_u8.numel(), input_dtype="uint8",
                          d2h_bytes_per_step=out_h.numel() * 4),
-                gpu_launches=launches, roofline=roof, cpu_baseline=cpu)
+                gpu_launches=launches, roofline=roof, cpu_baseline=cpu, train_step=train)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -321,6 +389,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
     ap.add_argument("--dump-calls", default=None, help="write the per-launch timing table (JSON lines) here")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -77,6 +77,24 @@ def make_window(H: int, W: int, seed: int = 7, frames: int = 3, batch: int = 1,
     return imgs, tris
 
 
+def make_train_batch(B: int, S: int, H: int, W: int, seed: int = 21):
+    """Synthetic training batch shaped like what dataset/VMD.py:300-301 hands to FullModel_VMD (SURVEY.md section 8d,
+    config 3): alpha uint8 [B,S,1,H,W] with a soft-edged moving blob (every frame has unknown pixels), fg / bg uint8
+    [B,S,3,H,W] low-frequency texture + noise (BGR 0..255)."""
+    yy, xx = np.mgrid[0:H, 0:W]
+    a = np.zeros((B, S, 1, H, W), np.uint8)
+    fg = np.zeros((B, S, 3, H, W), np.uint8)
+    bg = np.zeros((B, S, 3, H, W), np.uint8)
+    for b in range(B):
+        for s in range(S):
+            cy, cx = H / 2 + 2 * s - 3 + 5 * b, W / 2 + 3 * s - 5 - 4 * b
+            r = np.sqrt((yy - cy) ** 2 + (xx - cx) ** 2)
+            a[b, s, 0] = np.round(np.clip((min(H, W) / 3.0 - r) / (min(H, W) / 6.0), 0, 1) * 255)
+        fg[b] = make_window(H, W, seed=seed + 1 + 10 * b, frames=S)[0][0]
+        bg[b] = make_window(H, W, seed=seed + 2 + 10 * b, frames=S)[0][0]
+    return a, fg, bg
+
+
 # ----------------------------------------------------------------------------- fixture weights
 def _xavier(tag: str, shape, seed: int) -> np.ndarray:
     rf = int(np.prod(shape[2:])) if len(shape) > 2 else 1

@@ -22,18 +22,7 @@ LOSS_WEIGHTS = (1.0, 1.0, 1.0, 0.5, 0.25)
 
 
 def train_inputs(B, S, H, W, seed=21):
-    yy, xx = np.mgrid[0:H, 0:W]
-    a = np.zeros((B, S, 1, H, W), np.uint8)
-    fg = np.zeros((B, S, 3, H, W), np.uint8)
-    bg = np.zeros((B, S, 3, H, W), np.uint8)
-    for b in range(B):
-        for s in range(S):
-            cy, cx = H / 2 + 2 * s - 3 + 5 * b, W / 2 + 3 * s - 5 - 4 * b
-            r = np.sqrt((yy - cy) ** 2 + (xx - cx) ** 2)
-            a[b, s, 0] = np.round(np.clip((min(H, W) / 3.0 - r) / (min(H, W) / 6.0), 0, 1) * 255)
-        fg[b] = synthetic.make_window(H, W, seed=seed + 1 + 10 * b, frames=S)[0][0]
-        bg[b] = synthetic.make_window(H, W, seed=seed + 2 + 10 * b, frames=S)[0][0]
-    return a, fg, bg
+    return synthetic.make_train_batch(B, S, H, W, seed)
 
 
 def main():
