@@ -348,6 +348,13 @@ int tcv_wgrad_tc(const void* xt, long long xt_plane, const void* zt, long long z
                  long long ktot, int row_stride, int ntaps, const int* dy, const int* dx, const int* wtap,
                  float* partial, int nsplit, float* dw, int dw_cout, tcv_stream_t stream);
 
+/* Same weight gradient, read straight from the NHWC tensors: MN-major tcgen05 operands (a TMA box of 64 channels x
+ * TWxTH pixels is already the canonical [K = pixel][MN = channel] SWIZZLE_128B layout), filter taps as (W, H) shifts
+ * of the x box with TMA zero fill, deconv phases through a traversal stride of 2 on dz; fp32 atomics into dw.
+ * d = the forward descriptor (stride 1, zero padding, gh == ih); dz split-bf16 [n, oh, ow, dz_c]. */
+int tcv_conv2d_wgrad_nhwc_tc(const tcv_conv_desc* d, const void* dz, long long dz_plane, int dz_c, float* dw,
+                             tcv_stream_t stream);
+
 /* packed gradient fp32 [taps][cin_pad][cout_pad] -> torch layout ([cout,cin,kh,kw], or [cin,cout,kh,kw] when
  * transposed), minus the spectral-norm term sum_k (zdot[k]/sigma[k]) * u_k v_k^T when calls > 0. */
 int tcv_weight_grad_unpack(const float* dw, int cout, int cin, int kh, int kw, int transposed, int cin_pad,

@@ -132,6 +132,7 @@ SIGNATURES = {
                                   c_void_p, c_ll, c_ll, c_void_p]),
     "tcv_wgrad_tc": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_ll, c_int, c_int, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "tcv_conv2d_wgrad_nhwc_tc": (c_int, [C.POINTER(ConvDesc), c_void_p, c_ll, c_int, c_void_p, c_void_p]),
     "tcv_weight_grad_unpack": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "tcv_gemm_f32_strided": (c_int, [c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll, c_void_p, c_ll, c_int, c_int, c_int,

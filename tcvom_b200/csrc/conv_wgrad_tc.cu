@@ -1,0 +1,243 @@
+// Weight gradient on the tensor cores, read straight from the NHWC activations (no transposed copies):
+//   dw[wtap[t]][ci][co] += sum_{img,y,x} x[img, y+dy[t], x+dx[t], ci] * dz[img, y*mul+oy, x*mul+ox, co]
+// is a GEMM with M = ci, N = co and the reduction over pixels.  In NHWC a pixel's channels are contiguous, so a
+// TMA box {64 channels, TW, TH, 1} lands in shared memory as [K = pixel][MN = channel] rows of 128 B: exactly the
+// canonical MN-major SWIZZLE_128B operand layout of tcgen05.mma (cute::UMMA make_umma_desc<Major::MN>:
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -- 64 channels contiguous, 8 pixels per 1024-byte atom,
+// SBO = 1024 B between pixel groups, LBO = bytes between 64-channel blocks).  Both operands are MN-major
+// (instruction-descriptor bits 15/16).  The filter tap is a shift of the x box in (W, H); TMA zero-fills
+// out-of-image coordinates, which is the convolution's zero padding; the deconv phases read dz with a
+// traversal stride of 2.  Precision: bf16x3 (hi.hi + hi.lo + lo.hi) like every other tensor-core kernel here.
+//
+// One CTA = one (filter tap, 128x{64,128} tile of the (ci, co) plane, slice of the pixel tiles); 192 threads:
+// warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue (TMEM -> fp32 atomics into dw).
+#include "tc_common.cuh"
+
+namespace tcv {
+
+constexpr int WG_KT = 64;                 // pixels per pipeline stage
+constexpr int WG_BLK = WG_KT * 128;       // bytes of one 64-channel block of a stage (8 KB)
+constexpr int WG_STAGES = 3;
+
+struct WgParams {
+  int n, gh, gw, TW, TH, tiles_x, tiles_y, total_tiles, tiles_per_slice;
+  int ntaps, dy[TCV_MAX_TAPS], dx[TCV_MAX_TAPS], wtap[TCV_MAX_TAPS];
+  int cin, cout, dz_c, mul, oy, ox;
+  int nblk;               // 64-channel blocks of the N tile (1 or 2)
+  int n_tiles_n;
+  uint32_t idesc;
+  float* dw;
+};
+
+// MN-major SWIZZLE_128B shared-memory descriptor: LBO between 64-element MN blocks, SBO = 1024 B between 8-row K groups
+__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t addr, uint32_t lbo_bytes) {
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX_hi,
+                                                            const __grid_constant__ CUtensorMap mapX_lo,
+                                                            const __grid_constant__ CUtensorMap mapZ_hi,
+                                                            const __grid_constant__ CUtensorMap mapZ_lo,
+                                                            const __grid_constant__ WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int stage_bytes = (4 + 2 * p.nblk) * WG_BLK;     // A: 2 blocks x 2 planes, B: nblk blocks x 2 planes
+  const uint32_t bar_base = smem_base + WG_STAGES * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (WG_STAGES + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * WG_STAGES);
+  const uint32_t tmem_slot = accum_bar + 8u;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x;                                // filter tap (fastest: the taps of a slice share L2 lines)
+  const int slice = blockIdx.y;
+  const int mt = blockIdx.z / p.n_tiles_n, nt = blockIdx.z % p.n_tiles_n;
+  const int ci0 = mt * 128, co0 = nt * (64 * p.nblk);
+  const int tile_begin = slice * p.tiles_per_slice;
+  const int tile_end = min(tile_begin + p.tiles_per_slice, p.total_tiles);
+  const int iters = tile_end - tile_begin;
+  const uint32_t ncols = 64u * p.nblk;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapZ_hi) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot_ptr;
+
+  if (iters > 0) {
+    if (warp == 0) {
+      // ================================ TMA producer ================================
+      const int tdy = p.dy[t], tdx = p.dx[t];
+      for (int it = 0; it < iters; ++it) {
+        const int tile = tile_begin + it;
+        const int tx = tile % p.tiles_x;
+        const int ty = (tile / p.tiles_x) % p.tiles_y;
+        const int img = tile / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * p.TW, y0 = ty * p.TH;
+        const int s = it % WG_STAGES;
+        const uint32_t ph = (uint32_t)(it / WG_STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t st = smem_base + s * stage_bytes;
+        if (elect_one()) {
+          mbar_expect_tx(full_bar(s), (uint32_t)stage_bytes);
+          // A = x shifted by the tap: blocks (channels ci0.., ci0+64..) x planes (hi, lo)
+          tma_load_4d(st + 0 * WG_BLK, &mapX_hi, full_bar(s), ci0, x0 + tdx, y0 + tdy, img);
+          tma_load_4d(st + 1 * WG_BLK, &mapX_hi, full_bar(s), ci0 + 64, x0 + tdx, y0 + tdy, img);
+          tma_load_4d(st + 2 * WG_BLK, &mapX_lo, full_bar(s), ci0, x0 + tdx, y0 + tdy, img);
+          tma_load_4d(st + 3 * WG_BLK, &mapX_lo, full_bar(s), ci0 + 64, x0 + tdx, y0 + tdy, img);
+          // B = dz (sub-sampled by mul for the deconv phases)
+          const int zx = x0 * p.mul + p.ox, zy = y0 * p.mul + p.oy;
+          for (int b = 0; b < p.nblk; ++b) {
+            tma_load_4d(st + (4 + b) * WG_BLK, &mapZ_hi, full_bar(s), co0 + 64 * b, zx, zy, img);
+            tma_load_4d(st + (4 + p.nblk + b) * WG_BLK, &mapZ_lo, full_bar(s), co0 + 64 * b, zx, zy, img);
+          }
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1) {
+      // ================================ MMA issuer ================================
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % WG_STAGES;
+        const uint32_t ph = (uint32_t)(it / WG_STAGES) & 1u;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t st = smem_base + s * stage_bytes;
+        const uint32_t a_hi = st, a_lo = st + 2 * WG_BLK;
+        const uint32_t b_hi = st + 4 * WG_BLK, b_lo = b_hi + p.nblk * WG_BLK;
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < WG_KT / 16; ++ks) {
+            const uint32_t koff = ks * 16 * 128;           // 16 pixels further along K
+            const uint64_t ah = smem_desc_mn(a_hi + koff, WG_BLK), al = smem_desc_mn(a_lo + koff, WG_BLK);
+            const uint64_t bh = smem_desc_mn(b_hi + koff, WG_BLK), bl = smem_desc_mn(b_lo + koff, WG_BLK);
+            tc_mma(tmem_d, ah, bh, p.idesc, (it > 0 || ks > 0) ? 1u : 0u);
+            tc_mma(tmem_d, ah, bl, p.idesc, 1u);
+            tc_mma(tmem_d, al, bh, p.idesc, 1u);
+          }
+          tc_commit(empty_bar(s));
+          if (it == iters - 1) tc_commit(accum_bar);
+        }
+        __syncwarp();
+      }
+    } else {
+      // ================================ epilogue (warps 2..5) ================================
+      const int q = warp & 3;                      // TMEM lane quarter this warp may access
+      const int r = q * 32 + lane;                 // accumulator row = input channel within the tile
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+      const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
+      const int ci = ci0 + r;
+      float* out = p.dw + ((long long)p.wtap[t] * p.cin + ci) * p.dz_c + co0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < (int)ncols; c0 += 32) {
+        uint32_t v[32];
+        tc_ld32(taddr + c0, v);
+        if (ci >= p.cin) continue;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float f = __uint_as_float(v[j]);
+          if (co0 + c0 + j < p.dz_c && f != 0.f) atomicAdd(out + c0 + j, f);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(ncols) : "memory");
+  }
+}
+
+static int make_nhwc_map(CUtensorMap* m, const __nv_bfloat16* base, int c, int w, int h, int n, int tw, int th, int trav) {
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t str[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)(tw * trav), (cuuint32_t)(th * trav), 1};
+  return make_map(m, base, 4, dims, str, box, /*bk: 64 -> SWIZZLE_128B*/ 64, false, trav);
+}
+
+int conv2d_wgrad_tc_supported(const tcv_conv_desc& d, int dz_c) {
+  if (d.stride != 1 || d.pad_mode != TCV_PAD_ZERO) return 0;
+  if (d.cin % 8 != 0 || dz_c % 8 != 0) return 0;
+  if (d.x_img_stride != (long long)d.ih * d.iw * d.cin) return 0;
+  if (d.oy_mul != d.ox_mul || (d.oy_mul != 1 && d.oy_mul != 2)) return 0;
+  if (d.gh != d.ih || d.gw != d.iw) return 0;
+  return 1;
+}
+
+int conv2d_wgrad_tc(const tcv_conv_desc& d, const __nv_bfloat16* dz, long long dz_plane, int dz_c, float* dw,
+                    cudaStream_t st) {
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = d.n; p.gh = d.gh; p.gw = d.gw;
+  if (d.gw >= 64) { p.TW = 64; p.TH = 1; }
+  else if (d.gw >= 32) { p.TW = 32; p.TH = 2; }
+  else if (d.gw >= 16) { p.TW = 16; p.TH = 4; }
+  else { p.TW = 8; p.TH = 8; }
+  p.tiles_x = (d.gw + p.TW - 1) / p.TW;
+  p.tiles_y = (d.gh + p.TH - 1) / p.TH;
+  p.total_tiles = d.n * p.tiles_x * p.tiles_y;
+  p.ntaps = d.ntaps;
+  for (int t = 0; t < d.ntaps; ++t) { p.dy[t] = d.dy[t]; p.dx[t] = d.dx[t]; p.wtap[t] = d.wtap[t]; }
+  p.cin = d.cin; p.cout = d.cout; p.dz_c = dz_c;
+  p.mul = d.oy_mul; p.oy = d.oy_off; p.ox = d.ox_off;
+  p.nblk = dz_c > 64 ? 2 : 1;
+  const int ntile = 64 * p.nblk;
+  p.n_tiles_n = (dz_c + ntile - 1) / ntile;
+  const int n_tiles_m = (d.cin + 127) / 128;
+  // D = f32, A = B = bf16, both MN-major (bits 15, 16), M = 128, N = ntile
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(ntile >> 3) << 17) |
+            ((uint32_t)(128 >> 4) << 24);
+  p.dw = dw;
+  const int mn = n_tiles_m * p.n_tiles_n;
+  int slices = (4 * 148 + d.ntaps * mn - 1) / (d.ntaps * mn);
+  const int max_slices = (p.total_tiles + 3) / 4;          // at least 4 pixel tiles (256 pixels) per CTA
+  if (slices > max_slices) slices = max_slices;
+  if (slices < 1) slices = 1;
+  p.tiles_per_slice = (p.total_tiles + slices - 1) / slices;
+  slices = (p.total_tiles + p.tiles_per_slice - 1) / p.tiles_per_slice;
+
+  CUtensorMap mX_hi, mX_lo, mZ_hi, mZ_lo;
+  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(d.x);
+  int rc = make_nhwc_map(&mX_hi, x, d.cin, d.iw, d.ih, d.n, p.TW, p.TH, 1);
+  if (rc) return rc;
+  if ((rc = make_nhwc_map(&mX_lo, x + d.x_plane, d.cin, d.iw, d.ih, d.n, p.TW, p.TH, 1))) return rc;
+  if ((rc = make_nhwc_map(&mZ_hi, dz, dz_c, d.ow, d.oh, d.n, p.TW, p.TH, p.mul))) return rc;
+  if ((rc = make_nhwc_map(&mZ_lo, dz + dz_plane, dz_c, d.ow, d.oh, d.n, p.TW, p.TH, p.mul))) return rc;
+  const int smem = WG_STAGES * (4 + 2 * p.nblk) * WG_BLK + 1024 + 256;
+  TCV_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  dim3 grid(d.ntaps, slices, mn);
+  conv_wgrad_tc_kernel<<<grid, 192, smem, st>>>(mX_hi, mX_lo, mZ_hi, mZ_lo, p);
+  return launched("conv_wgrad_tc_kernel");
+}
+
+}  // namespace tcv
+
+using namespace tcv;
+
+extern "C" int tcv_conv2d_wgrad_nhwc_tc(const tcv_conv_desc* dp, const void* dz, long long dz_plane, int dz_c, float* dw,
+                                        tcv_stream_t stream) {
+  TCV_REQUIRE(dp && dz && dw, "conv2d_wgrad_nhwc_tc: null pointer");
+  tcv_conv_desc d = *dp;
+  if (d.x_plane == 0) d.x_plane = (long long)d.n * d.ih * d.iw * d.cin;
+  if (d.x_img_stride == 0) d.x_img_stride = (long long)d.ih * d.iw * d.cin;
+  if (dz_plane == 0) dz_plane = (long long)d.n * d.oh * d.ow * dz_c;
+  TCV_REQUIRE(conv2d_wgrad_tc_supported(d, dz_c), "conv2d_wgrad_nhwc_tc: shape not supported (stride-1 zero-padded only)");
+  TCV_REQUIRE(((uintptr_t)d.x & 15) == 0 && ((uintptr_t)dz & 15) == 0 && d.x_plane % 8 == 0 && dz_plane % 8 == 0,
+              "conv2d_wgrad_nhwc_tc: operands must be 16-byte aligned");
+  return conv2d_wgrad_tc(d, reinterpret_cast<const __nv_bfloat16*>(dz), dz_plane, dz_c, dw, S(stream));
+}

@@ -55,7 +55,9 @@ class TrainEngine(GcaVmnEngine):
         # weight gradients of the stride-1 convs / deconv phases on the tensor cores (split-K tcgen05 GEMM over
         # channel-major copies); TCV_TC_WGRAD=0 keeps the CUDA-core fp32 kernel everywhere (exact cross-check)
         import os
-        self.use_tc_wgrad = os.environ.get("TCV_TC_WGRAD", "1") == "1"
+        self.use_tc_wgrad = os.environ.get("TCV_TC_WGRAD", "1") != "0"
+        # "2": the NHWC-direct kernel (MN-major operands, no channel-major copies); "1": the split-K GEMM over copies
+        self.wgrad_nhwc = os.environ.get("TCV_TC_WGRAD", "2") == "2"
 
     # ------------------------------------------------------------------ per-step weight state
     def refresh_weights(self, net: torch.nn.Module, force=False) -> None:
@@ -191,6 +193,10 @@ class TrainEngine(GcaVmnEngine):
             return None
         gh, gw = d.gh, d.gw
         assert (gh, gw) == (xa.h, xa.w) and (dz.h, dz.w) == (gh * mul, gw * mul) and dz.c == dz_c
+        if self.wgrad_nhwc:
+            self._call("tcv_conv2d_wgrad_nhwc_tc", C.byref(d), dz.ptr, dz.plane, dz_c, dw.data_ptr(),
+                       meta=dict(tag=f"cin{xa.c} cout{dz_c} px{xa.n * gh * gw} taps{d.ntaps}"))
+            return None
         row = (gw + 2 + 7) // 8 * 8                  # 16-byte aligned rows: vertical tap shifts stay TMA-legal
         ktot = xa.n * (gh + 2) * row
         if xt is None:

@@ -64,11 +64,25 @@ def run(name):
                                    row, len(ts), A2(*[taps[i][0] for i in ts]), A2(*([0] * len(ts))), A2(*ts),
                                    partial.data_ptr(), nsplit, dw.data_ptr(), c["cout"], st), "wgrad_tc")
     torch.cuda.synchronize()
+    # NHWC-direct kernel on the same problem
+    from tcvom_b200._cabi import ConvDesc
+    d = ConvDesc()
+    d.x, d.x_plane, d.x_img_stride = xa.ptr, xa.plane, xa.img_elems
+    d.n, d.ih, d.iw, d.cin = xa.n, xa.h, xa.w, xa.c
+    d.ntaps = nt
+    for i, tp in enumerate(taps):
+        d.dy[i], d.dx[i], d.wtap[i] = tp[0], tp[1], i
+    d.stride, d.pad_mode = 1, 0
+    d.oh, d.ow, d.cout, d.gh, d.gw = xa.h, xa.w, c["cout"], xa.h, xa.w
+    d.oy_mul, d.oy_off, d.ox_mul, d.ox_off = 1, 0, 1, 0
+    dw2 = torch.zeros((nt, c["cin"], c["cout"]), device="cuda")
+    _cabi.check(L.tcv_conv2d_wgrad_nhwc_tc(C.byref(d), za.ptr, za.plane, c["cout"], dw2.data_ptr(), st), "wgrad_nhwc")
+    torch.cuda.synchronize()
     w = torch.zeros((c["cout"], c["cin"], k, k), device="cuda", requires_grad=True)
     y = F.conv2d(xr, w, None, 1, k // 2)
     (gw,) = torch.autograd.grad(y, w, from_act(za))
     ref = gw.permute(2, 3, 1, 0).reshape(len(all_taps), c["cin"], c["cout"])[[all_taps.index(t) for t in taps]]
-    print(name, "wgrad err", rel(dw, ref))
+    print(name, "wgrad err", rel(dw, ref), "nhwc-direct err", rel(dw2, ref))
 
 
 if __name__ == "__main__":
