@@ -351,7 +351,8 @@ int tcv_wgrad_tc(const void* xt, long long xt_plane, const void* zt, long long z
 /* Same weight gradient, read straight from the NHWC tensors: MN-major tcgen05 operands (a TMA box of 64 channels x
  * TWxTH pixels is already the canonical [K = pixel][MN = channel] SWIZZLE_128B layout), filter taps as (W, H) shifts
  * of the x box with TMA zero fill, deconv phases through a traversal stride of 2 on dz; fp32 atomics into dw.
- * d = the forward descriptor (stride 1, zero padding, gh == ih); dz split-bf16 [n, oh, ow, dz_c]. */
+ * d = the forward descriptor (stride 1 or 2 -- x is then read with a traversal stride --, zero padding or a pre-padded
+ * input); dz split-bf16 [n, oh, ow, dz_c]. */
 int tcv_conv2d_wgrad_nhwc_tc(const tcv_conv_desc* d, const void* dz, long long dz_plane, int dz_c, float* dw,
                              tcv_stream_t stream);
 

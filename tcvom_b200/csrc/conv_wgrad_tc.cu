@@ -6,8 +6,8 @@
 // ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -- 64 channels contiguous, 8 pixels per 1024-byte atom,
 // SBO = 1024 B between pixel groups, LBO = bytes between 64-channel blocks).  Both operands are MN-major
 // (instruction-descriptor bits 15/16).  The filter tap is a shift of the x box in (W, H); TMA zero-fills
-// out-of-image coordinates, which is the convolution's zero padding; the deconv phases read dz with a
-// traversal stride of 2.  Precision: bf16x3 (hi.hi + hi.lo + lo.hi) like every other tensor-core kernel here.
+// out-of-image coordinates, which is the convolution's zero padding; stride-2 convs read x and the deconv phases
+// read dz with a TMA traversal stride of 2.  Precision: bf16x3 (hi.hi + hi.lo + lo.hi) like every other tensor-core kernel here.
 //
 // One CTA = one (filter tap, 128x{64,128} tile of the (ci, co) plane, slice of the pixel tiles); 192 threads:
 // warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue (TMEM -> fp32 atomics into dw).
@@ -23,6 +23,7 @@ struct WgParams {
   int n, gh, gw, TW, TH, tiles_x, tiles_y, total_tiles, tiles_per_slice;
   int ntaps, dy[TCV_MAX_TAPS], dx[TCV_MAX_TAPS], wtap[TCV_MAX_TAPS];
   int cin, cout, dz_c, mul, oy, ox;
+  int xmul;               // input pixels per output pixel (conv stride): x is read with a traversal stride
   int nblk;               // 64-channel blocks of the N tile (1 or 2)
   int n_tiles_n;
   uint32_t idesc;
@@ -96,10 +97,11 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
         if (elect_one()) {
           mbar_expect_tx(full_bar(s), (uint32_t)stage_bytes);
           // A = x shifted by the tap: blocks (channels ci0.., ci0+64..) x planes (hi, lo)
-          tma_load_4d(st + 0 * WG_BLK, &mapX_hi, full_bar(s), ci0, x0 + tdx, y0 + tdy, img);
-          tma_load_4d(st + 1 * WG_BLK, &mapX_hi, full_bar(s), ci0 + 64, x0 + tdx, y0 + tdy, img);
-          tma_load_4d(st + 2 * WG_BLK, &mapX_lo, full_bar(s), ci0, x0 + tdx, y0 + tdy, img);
-          tma_load_4d(st + 3 * WG_BLK, &mapX_lo, full_bar(s), ci0 + 64, x0 + tdx, y0 + tdy, img);
+          const int ax = x0 * p.xmul + tdx, ay = y0 * p.xmul + tdy;
+          tma_load_4d(st + 0 * WG_BLK, &mapX_hi, full_bar(s), ci0, ax, ay, img);
+          tma_load_4d(st + 1 * WG_BLK, &mapX_hi, full_bar(s), ci0 + 64, ax, ay, img);
+          tma_load_4d(st + 2 * WG_BLK, &mapX_lo, full_bar(s), ci0, ax, ay, img);
+          tma_load_4d(st + 3 * WG_BLK, &mapX_lo, full_bar(s), ci0 + 64, ax, ay, img);
           // B = dz (sub-sampled by mul for the deconv phases)
           const int zx = x0 * p.mul + p.ox, zy = y0 * p.mul + p.oy;
           for (int b = 0; b < p.nblk; ++b) {
@@ -171,11 +173,11 @@ static int make_nhwc_map(CUtensorMap* m, const __nv_bfloat16* base, int c, int w
 }
 
 int conv2d_wgrad_tc_supported(const tcv_conv_desc& d, int dz_c) {
-  if (d.stride != 1 || d.pad_mode != TCV_PAD_ZERO) return 0;
+  if ((d.stride != 1 && d.stride != 2) || d.pad_mode != TCV_PAD_ZERO) return 0;
   if (d.cin % 8 != 0 || dz_c % 8 != 0) return 0;
   if (d.x_img_stride != (long long)d.ih * d.iw * d.cin) return 0;
   if (d.oy_mul != d.ox_mul || (d.oy_mul != 1 && d.oy_mul != 2)) return 0;
-  if (d.gh != d.ih || d.gw != d.iw) return 0;
+  if (d.stride == 2 && d.oy_mul != 1) return 0;
   return 1;
 }
 
@@ -195,6 +197,7 @@ int conv2d_wgrad_tc(const tcv_conv_desc& d, const __nv_bfloat16* dz, long long d
   for (int t = 0; t < d.ntaps; ++t) { p.dy[t] = d.dy[t]; p.dx[t] = d.dx[t]; p.wtap[t] = d.wtap[t]; }
   p.cin = d.cin; p.cout = d.cout; p.dz_c = dz_c;
   p.mul = d.oy_mul; p.oy = d.oy_off; p.ox = d.ox_off;
+  p.xmul = d.stride;
   p.nblk = dz_c > 64 ? 2 : 1;
   const int ntile = 64 * p.nblk;
   p.n_tiles_n = (dz_c + ntile - 1) / ntile;
@@ -213,9 +216,9 @@ int conv2d_wgrad_tc(const tcv_conv_desc& d, const __nv_bfloat16* dz, long long d
 
   CUtensorMap mX_hi, mX_lo, mZ_hi, mZ_lo;
   const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(d.x);
-  int rc = make_nhwc_map(&mX_hi, x, d.cin, d.iw, d.ih, d.n, p.TW, p.TH, 1);
+  int rc = make_nhwc_map(&mX_hi, x, d.cin, d.iw, d.ih, d.n, p.TW, p.TH, d.stride);
   if (rc) return rc;
-  if ((rc = make_nhwc_map(&mX_lo, x + d.x_plane, d.cin, d.iw, d.ih, d.n, p.TW, p.TH, 1))) return rc;
+  if ((rc = make_nhwc_map(&mX_lo, x + d.x_plane, d.cin, d.iw, d.ih, d.n, p.TW, p.TH, d.stride))) return rc;
   if ((rc = make_nhwc_map(&mZ_hi, dz, dz_c, d.ow, d.oh, d.n, p.TW, p.TH, p.mul))) return rc;
   if ((rc = make_nhwc_map(&mZ_lo, dz + dz_plane, dz_c, d.ow, d.oh, d.n, p.TW, p.TH, p.mul))) return rc;
   const int smem = WG_STAGES * (4 + 2 * p.nblk) * WG_BLK + 1024 + 256;
@@ -236,7 +239,7 @@ extern "C" int tcv_conv2d_wgrad_nhwc_tc(const tcv_conv_desc* dp, const void* dz,
   if (d.x_plane == 0) d.x_plane = (long long)d.n * d.ih * d.iw * d.cin;
   if (d.x_img_stride == 0) d.x_img_stride = (long long)d.ih * d.iw * d.cin;
   if (dz_plane == 0) dz_plane = (long long)d.n * d.oh * d.ow * dz_c;
-  TCV_REQUIRE(conv2d_wgrad_tc_supported(d, dz_c), "conv2d_wgrad_nhwc_tc: shape not supported (stride-1 zero-padded only)");
+  TCV_REQUIRE(conv2d_wgrad_tc_supported(d, dz_c), "conv2d_wgrad_nhwc_tc: shape not supported (zero-padded / pre-padded stride 1 or 2 only)");
   TCV_REQUIRE(((uintptr_t)d.x & 15) == 0 && ((uintptr_t)dz & 15) == 0 && d.x_plane % 8 == 0 && dz_plane % 8 == 0,
               "conv2d_wgrad_nhwc_tc: operands must be 16-byte aligned");
   return conv2d_wgrad_tc(d, reinterpret_cast<const __nv_bfloat16*>(dz), dz_plane, dz_c, dw, S(stream));

@@ -187,16 +187,16 @@ class TrainEngine(GcaVmnEngine):
         """dw += weight gradient of the conv described by the forward descriptor ``d``.  Stride-1 zero-padded
         taps within one pixel run on the tensor cores; everything else (stride-2, reflect) on CUDA cores.
         Returns the channel-major copy of x (reusable by the other phases of a deconv)."""
+        if self.use_tc_wgrad and self.wgrad_nhwc and d.pad_mode == PAD_ZERO and dz_c % 8 == 0:
+            self._call("tcv_conv2d_wgrad_nhwc_tc", C.byref(d), dz.ptr, dz.plane, dz_c, dw.data_ptr(),
+                       meta=dict(tag=f"cin{xa.c} cout{dz_c} px{xa.n * d.gh * d.gw} taps{d.ntaps} s{d.stride}"))
+            return None
         taps_ok = all(abs(d.dy[t]) <= 1 and abs(d.dx[t]) <= 1 for t in range(d.ntaps))
         if not (self.use_tc_wgrad and d.stride == 1 and d.pad_mode == PAD_ZERO and taps_ok and dz_c % 8 == 0):
             self._call("tcv_conv2d_wgrad", C.byref(d), dz.ptr, dz.plane, dz_c, dw.data_ptr())
             return None
         gh, gw = d.gh, d.gw
         assert (gh, gw) == (xa.h, xa.w) and (dz.h, dz.w) == (gh * mul, gw * mul) and dz.c == dz_c
-        if self.wgrad_nhwc:
-            self._call("tcv_conv2d_wgrad_nhwc_tc", C.byref(d), dz.ptr, dz.plane, dz_c, dw.data_ptr(),
-                       meta=dict(tag=f"cin{xa.c} cout{dz_c} px{xa.n * gh * gw} taps{d.ntaps}"))
-            return None
         row = (gw + 2 + 7) // 8 * 8                  # 16-byte aligned rows: vertical tap shifts stay TMA-legal
         ktot = xa.n * (gh + 2) * row
         if xt is None:
@@ -669,12 +669,10 @@ class TrainEngine(GcaVmnEngine):
         c3 = self.conv_bn(x1, e + ".conv3", e + ".bn3", stride=2, act=ACT_RELU)
         g = x8
         for ci, bi in ((1, 3), (5, 7), (9, 11)):
-            if g is x8:
-                g = self.conv_bn(g, f"{e}.guidance_head.{ci}", f"{e}.guidance_head.{bi}", stride=2, pad=PAD_REFLECT,
-                                 mode=2, act=ACT_RELU)
-            else:
-                g = self.conv_bn(self.pad_reflect_op(g), f"{e}.guidance_head.{ci}", f"{e}.guidance_head.{bi}", stride=2,
-                                 prepadded=True, mode=2, act=ACT_RELU)
+            # reflect border materialised once (ReflectionPad2d(1), res_gca_enc.py:20-33): the stride-2 conv and both of
+            # its gradients then run on the zero-padding-free "pre-padded" tensor-core paths
+            g = self.conv_bn(self.pad_reflect_op(g), f"{e}.guidance_head.{ci}", f"{e}.guidance_head.{bi}", stride=2,
+                             prepadded=True, mode=2, act=ACT_RELU)
         im_fea = g
         xa = x8.a
         unknown = torch.empty((xa.n, xa.h // 8, xa.w // 8), dtype=torch.float32, device=self.device)
