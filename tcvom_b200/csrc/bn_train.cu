@@ -13,23 +13,24 @@
 
 namespace tcv {
 
-constexpr int BN_PIX = 2048;  // pixels of one image per block
+constexpr int BN_PIX_MAX = 2048;  // most pixels of one image per block (fewer when the tensor is small: the grid
+                                  // should cover the 148 SMs several times, see bn_pix())
 
 struct BnGeom {
   int c8, lanes, cg, lane;
-  long long p0, p1;
+  int p0, p1;
   int img, g;
 };
 
-__device__ __forceinline__ BnGeom bn_geom(const tcv_bn_desc& d) {
+__device__ __forceinline__ BnGeom bn_geom(const tcv_bn_desc& d, int pix) {
   BnGeom q;
   q.c8 = d.c / 8;
   q.lanes = 256 / q.c8;
   q.cg = threadIdx.x % q.c8;
   q.lane = threadIdx.x / q.c8;
-  const long long hw = (long long)d.h * d.w;
-  q.p0 = (long long)blockIdx.x * BN_PIX;
-  q.p1 = min(q.p0 + BN_PIX, hw);
+  const int hw = d.h * d.w;
+  q.p0 = blockIdx.x * pix;
+  q.p1 = min(q.p0 + pix, hw);
   q.img = blockIdx.y;
   q.g = q.img % d.groups;
   return q;
@@ -60,15 +61,15 @@ __device__ __forceinline__ void bn_block_reduce(const BnGeom& q, float* s0, floa
   }
 }
 
-__global__ void __launch_bounds__(256) bn_stats_kernel(const tcv_bn_desc d, double* __restrict__ sums) {
+__global__ void __launch_bounds__(256) bn_stats_kernel(const tcv_bn_desc d, double* __restrict__ sums, int pix) {
   __shared__ float red[256][17];
-  const BnGeom q = bn_geom(d);
+  const BnGeom q = bn_geom(d, pix);
   const __nv_bfloat16* z = reinterpret_cast<const __nv_bfloat16*>(d.z) + (long long)q.img * d.h * d.w * d.c + q.cg * 8;
   const float is = d.inv_sigma ? d.inv_sigma[q.g] : 1.f;
   float s0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (long long p = q.p0 + q.lane; p < q.p1; p += q.lanes) {
+  for (int p = q.p0 + q.lane; p < q.p1; p += q.lanes) {
     float f[8];
-    load8(z + p * d.c, d.z_plane, f);
+    load8(z + (long long)p * d.c, d.z_plane, f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       float t = f[k] * is;
@@ -152,9 +153,9 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const tcv_bn_desc d) {
 
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const tcv_bn_desc d, const __nv_bfloat16* __restrict__ dy,
                                                             long long dy_plane, __nv_bfloat16* __restrict__ e,
-                                                            long long e_plane, double* __restrict__ sums) {
+                                                            long long e_plane, double* __restrict__ sums, int pix) {
   __shared__ float red[256][17];
-  const BnGeom q = bn_geom(d);
+  const BnGeom q = bn_geom(d, pix);
   const long long ibase = (long long)q.img * d.h * d.w;
   const int ch = q.cg * 8;
   const float is = d.inv_sigma ? d.inv_sigma[q.g] : 1.f;
@@ -167,14 +168,14 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const tcv_bn_desc d,
     be[k] = d.beta[ch + k];
   }
   float s0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (long long p = q.p0 + q.lane; p < q.p1; p += q.lanes) {
+  for (int p = q.p0 + q.lane; p < q.p1; p += q.lanes) {
     const long long pix = ibase + p;
     float f[8], gy[8], xh[8];
     load8(reinterpret_cast<const __nv_bfloat16*>(d.z) + pix * d.c + ch, d.z_plane, f);
     load8(dy + pix * d.c + ch, dy_plane, gy);
     if (d.mode == 1) {
       float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      if (d.res1) load_res1(d, q.img, (int)(p / d.w), (int)(p % d.w), ch, r);
+      if (d.res1) load_res1(d, q.img, p / d.w, p % d.w, ch, r);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         xh[k] = (f[k] * is - mu[k]) * iv[k];
@@ -211,9 +212,9 @@ __global__ void bn_param_grads_kernel(const double* __restrict__ sums, int group
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const tcv_bn_desc d, const __nv_bfloat16* __restrict__ e,
                                                            long long e_plane, const double* __restrict__ sums,
                                                            double count, __nv_bfloat16* __restrict__ dz,
-                                                           long long dz_plane, double* __restrict__ zdot) {
+                                                           long long dz_plane, double* __restrict__ zdot, int pix) {
   __shared__ double dred[8];
-  const BnGeom q = bn_geom(d);
+  const BnGeom q = bn_geom(d, pix);
   const long long ibase = (long long)q.img * d.h * d.w;
   const int ch = q.cg * 8;
   const float is = d.inv_sigma ? d.inv_sigma[q.g] : 1.f;
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const tcv_bn_desc d, 
     m2[k] = (float)(sums[((long long)q.g * d.c + ch + k) * 2 + 1] / count);
   }
   float dot = 0.f;
-  for (long long p = q.p0 + q.lane; p < q.p1; p += q.lanes) {
+  for (int p = q.p0 + q.lane; p < q.p1; p += q.lanes) {
     const long long pix = ibase + p;
     float f[8], ge[8], o[8];
     load8(reinterpret_cast<const __nv_bfloat16*>(d.z) + pix * d.c + ch, d.z_plane, f);
@@ -305,8 +306,20 @@ static tcv_bn_desc with_defaults(const tcv_bn_desc* dp) {
   return d;
 }
 
-static dim3 bn_grid(const tcv_bn_desc& d) {
-  return dim3((unsigned)(((long long)d.h * d.w + BN_PIX - 1) / BN_PIX), (unsigned)d.n);
+// pixels per block: as many as BN_PIX_MAX, but few enough that the grid covers the 148 SMs ~4 times (the OS8..OS32
+// tensors have only a few thousand pixels per image; with a fixed 2048 their grids were 10-40 blocks)
+static int bn_pix(const tcv_bn_desc& d) {
+  const long long total = (long long)d.n * d.h * d.w;
+  long long pix = (total + 4 * 148 - 1) / (4 * 148);
+  const int lanes = 256 / (d.c / 8);
+  const long long lo = 2LL * lanes;
+  if (pix < lo) pix = lo;
+  if (pix > BN_PIX_MAX) pix = BN_PIX_MAX;
+  return (int)((pix + lanes - 1) / lanes * lanes);
+}
+
+static dim3 bn_grid(const tcv_bn_desc& d, int pix) {
+  return dim3((unsigned)(((long long)d.h * d.w + pix - 1) / pix), (unsigned)d.n);
 }
 
 }  // namespace tcv
@@ -321,7 +334,8 @@ int tcv_bn_stats(const tcv_bn_desc* dp, double* sums, tcv_stream_t stream) {
   int rc = check_desc(d, "bn_stats");
   if (rc) return rc;
   TCV_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * d.groups * d.c, S(stream)));
-  bn_stats_kernel<<<bn_grid(d), 256, 0, S(stream)>>>(d, sums);
+  const int pix = bn_pix(d);
+  bn_stats_kernel<<<bn_grid(d, pix), 256, 0, S(stream)>>>(d, sums, pix);
   return launched("bn_stats_kernel");
 }
 
@@ -354,10 +368,11 @@ int tcv_bn_bwd_reduce(const tcv_bn_desc* dp, const void* dy, long long dy_plane,
   TCV_REQUIRE(d.mode == 2 || e, "bn_bwd_reduce: mode 1 needs the e output");
   const long long full = (long long)d.n * d.h * d.w * d.c;
   TCV_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * d.groups * d.c, S(stream)));
-  bn_bwd_reduce_kernel<<<bn_grid(d), 256, 0, S(stream)>>>(d, reinterpret_cast<const __nv_bfloat16*>(dy),
-                                                         dy_plane ? dy_plane : full,
-                                                         reinterpret_cast<__nv_bfloat16*>(e), e_plane ? e_plane : full,
-                                                         sums);
+  const int pix = bn_pix(d);
+  bn_bwd_reduce_kernel<<<bn_grid(d, pix), 256, 0, S(stream)>>>(d, reinterpret_cast<const __nv_bfloat16*>(dy),
+                                                              dy_plane ? dy_plane : full,
+                                                              reinterpret_cast<__nv_bfloat16*>(e),
+                                                              e_plane ? e_plane : full, sums, pix);
   return launched("bn_bwd_reduce_kernel");
 }
 
@@ -374,10 +389,11 @@ int tcv_bn_bwd_apply(const tcv_bn_desc* dp, const void* e, long long e_plane, co
   int rc = check_desc(d, "bn_bwd_apply");
   if (rc) return rc;
   const long long full = (long long)d.n * d.h * d.w * d.c;
-  bn_bwd_apply_kernel<<<bn_grid(d), 256, 0, S(stream)>>>(d, reinterpret_cast<const __nv_bfloat16*>(e),
-                                                        e_plane ? e_plane : full, sums, count,
-                                                        reinterpret_cast<__nv_bfloat16*>(dz),
-                                                        dz_plane ? dz_plane : full, zdot);
+  const int pix = bn_pix(d);
+  bn_bwd_apply_kernel<<<bn_grid(d, pix), 256, 0, S(stream)>>>(d, reinterpret_cast<const __nv_bfloat16*>(e),
+                                                             e_plane ? e_plane : full, sums, count,
+                                                             reinterpret_cast<__nv_bfloat16*>(dz),
+                                                             dz_plane ? dz_plane : full, zdot, pix);
   return launched("bn_bwd_apply_kernel");
 }
 

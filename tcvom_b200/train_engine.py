@@ -369,7 +369,8 @@ class TrainEngine(GcaVmnEngine):
             assert res2.a.c == c and res2.a.n == za.n and res2.a.h == za.h and res2.a.w == za.w, bnkey
             d.res2, d.res2_plane = res2.a.ptr, res2.a.plane
         d.y, d.y_plane = y.ptr, y.plane
-        self._call("tcv_bn_stats", C.byref(d), sums.data_ptr())
+        tag = dict(tag=f"c{c} px{za.n * za.h * za.w} m{mode}{'r1' if res1 is not None else ''}{'r2' if res2 is not None else ''}")
+        self._call("tcv_bn_stats", C.byref(d), sums.data_ptr(), meta=tag)
         count = float((za.n // groups) * za.h * za.w)
         if self.sync_bn:
             torch.distributed.all_reduce(sums, group=self.process_group)
@@ -380,7 +381,7 @@ class TrainEngine(GcaVmnEngine):
         nbt = self.named.get(bnkey + ".num_batches_tracked")
         if nbt is not None:
             nbt += groups
-        self._call("tcv_bn_apply", C.byref(d))
+        self._call("tcv_bn_apply", C.byref(d), meta=tag)
         out = TAct(y, groups)
         keep = (mean, invstd, gamma, beta)
 
@@ -392,10 +393,10 @@ class TrainEngine(GcaVmnEngine):
             bsums = torch.empty((groups, c, 2), dtype=torch.float64, device=dev)
             if mode == 1:
                 e = self._act(za.n, za.h, za.w, c)
-                self._call("tcv_bn_bwd_reduce", C.byref(d), dy.ptr, dy.plane, e.ptr, e.plane, bsums.data_ptr())
+                self._call("tcv_bn_bwd_reduce", C.byref(d), dy.ptr, dy.plane, e.ptr, e.plane, bsums.data_ptr(), meta=tag)
             else:
                 e = dy
-                self._call("tcv_bn_bwd_reduce", C.byref(d), dy.ptr, dy.plane, None, 0, bsums.data_ptr())
+                self._call("tcv_bn_bwd_reduce", C.byref(d), dy.ptr, dy.plane, None, 0, bsums.data_ptr(), meta=tag)
             dg, db = self.dbn.get(bnkey, (None, None))
             if dg is None:
                 dg = torch.zeros((c,), dtype=torch.float32, device=dev)
@@ -406,7 +407,7 @@ class TrainEngine(GcaVmnEngine):
                 torch.distributed.all_reduce(bsums, group=self.process_group)
             dz = self._act(za.n, za.h, za.w, c)
             self._call("tcv_bn_bwd_apply", C.byref(d), e.ptr, e.plane, bsums.data_ptr(), count, dz.ptr, dz.plane,
-                       sn["zdot"].data_ptr() if sn is not None else None)
+                       sn["zdot"].data_ptr() if sn is not None else None, meta=tag)
             self._acc(z, dz, True)
             if res1 is not None and res1.needs_grad:
                 if res1_shift:

@@ -70,6 +70,7 @@ def test_full_training_step_matches_reference(tc):
     assert errs["losses"] < 2e-3, errs
     assert errs["alphas"] < 1e-3, errs
     assert errs["state"] < 1e-3, errs
+    assert errs["grad_median"] < 4e-2, errs
     assert ok, (errs, rows[:5])
 
 
