@@ -272,7 +272,7 @@ int tcv_split_to_f32(const void* x, long long x_plane, long long count, float* y
 int tcv_transpose_packed(const float* packed, int taps, int cin, int cout, int cout_pad, float* out,
                          tcv_stream_t stream);
 
-/* SpectralNorm power iteration for `n` layers in one launch (one CTA per layer).  Layer i is called
+/* SpectralNorm power iteration for `n` layers in one launch (one 8-CTA cluster per layer; rows <= 512, cols <= 8192).  Layer i is called
  * `calls` times per step (once per frame, VMN_model.py:93-98,107-110); call k uses (u_k, v_k, sigma_k) obtained by
  * k+1 iterations from the stored u, v.  The final u, v are written back to the module's buffers. */
 typedef struct {

@@ -3,7 +3,11 @@
 // convolutions, SpectralNorm power iteration (models/GCA/ops.py:25-36) and the unpacking of packed weight
 // gradients into the torch parameter layout including the d(sigma) term of W_bar / sigma.
 // All HBM-bound single-pass kernels on split-bf16 NHWC tensors (see include/tcvom_b200.h).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace tcv {
 
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(256) transpose_pad_kernel(const uint16_t* __re
   }
 }
 
-// ---- SpectralNorm power iteration: one CTA per layer --------------------------------------------------
+// ---- SpectralNorm power iteration --------------------------------------------------
 __device__ float block_sum_1024(float v, float* red) {
   v = warp_sum(v);
   __syncthreads();
@@ -241,52 +245,82 @@ __device__ float block_sum_1024(float v, float* red) {
   return red[32];
 }
 
-__global__ void __launch_bounds__(1024) sn_power_iter_kernel(const tcv_sn_desc* __restrict__ descs) {
+// One thread-block CLUSTER of 8 CTAs per layer (a single CTA streaming a 512x4608 weight ten times took 5.7 ms for
+// the 70 layers, 8 % of the training step): phase 1 splits the columns of v = W^T u over the CTAs, phase 2 the rows of
+// t = W v; the two scalar norms are reduced through distributed shared memory; u / v travel through global memory
+// (cluster.sync() orders it).
+constexpr int SN_CLUSTER = 8;
+constexpr int SN_MAX_COLS_SLICE = 1024;   // 512x(512*4*4) deconv weight: 8192 / 8
+constexpr int SN_MAX_ROWS_SLICE = 64;     // 512 / 8
+
+__device__ __forceinline__ float cluster_sum(cg::cluster_group& cluster, float* slot, float v, float* red) {
+  v = block_sum_1024(v, red);
+  if (threadIdx.x == 0) *slot = v;
+  cluster.sync();
+  float t = 0.f;
+  for (int r = 0; r < SN_CLUSTER; ++r) t += *cluster.map_shared_rank(slot, r);
+  return t;
+}
+
+__global__ void __cluster_dims__(SN_CLUSTER, 1, 1) __launch_bounds__(1024)
+    sn_power_iter_kernel(const tcv_sn_desc* __restrict__ descs) {
   __shared__ float red[33];
-  const tcv_sn_desc d = descs[blockIdx.x];
+  __shared__ float part[4];                         // [iteration parity][phase]: a slot is rewritten two syncs later
+  __shared__ float vacc[SN_MAX_COLS_SLICE];
+  __shared__ float tloc[SN_MAX_ROWS_SLICE];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const tcv_sn_desc d = descs[blockIdx.x / SN_CLUSTER];
   const int rows = d.rows, cols = d.cols;
   const float* W = d.w_bar;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int cs = (cols + SN_CLUSTER - 1) / SN_CLUSTER, c0 = min(rank * cs, cols), c1 = min(c0 + cs, cols);
+  const int rs = (rows + SN_CLUSTER - 1) / SN_CLUSTER, r0 = min(rank * rs, rows), r1 = min(r0 + rs, rows);
   for (int k = 0; k < d.calls; ++k) {
     const float* u_prev = k == 0 ? d.u : d.u_hist + (long long)(k - 1) * rows;
     float* vk = d.v_hist + (long long)k * cols;
     float* uk = d.u_hist + (long long)k * rows;
-    // v = normalize(W^T u): one thread per column, rows streamed (coalesced across threads)
-    float ss = 0.f;
-    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-      float a = 0.f;
-      for (int r = 0; r < rows; ++r) a = fmaf(W[(long long)r * cols + c], u_prev[r], a);
-      vk[c] = a;
-      ss += a * a;
-    }
-    ss = block_sum_1024(ss, red);
-    const float invv = 1.0f / (sqrtf(ss) + 1e-12f);
-    for (int c = threadIdx.x; c < cols; c += blockDim.x) vk[c] *= invv;
+    // ---- phase 1: v[c0:c1] = sum_r W[r][c] u[r]  (lanes = 32 consecutive columns, warps stride the rows)
+    for (int c = threadIdx.x; c < c1 - c0; c += blockDim.x) vacc[c] = 0.f;
     __syncthreads();
-    // t = W v: one warp per row
+    for (int cb = c0; cb < c1; cb += 32) {
+      const int c = cb + lane;
+      float a = 0.f;
+      if (c < c1)
+        for (int r = warp; r < rows; r += nwarp) a = fmaf(W[(long long)r * cols + c], u_prev[r], a);
+      if (c < c1) atomicAdd(&vacc[c - c0], a);
+    }
+    __syncthreads();
+    float ss = 0.f;
+    for (int c = threadIdx.x; c < c1 - c0; c += blockDim.x) ss += vacc[c] * vacc[c];
+    ss = cluster_sum(cluster, &part[(k & 1) * 2], ss, red);
+    const float invv = 1.0f / (sqrtf(ss) + 1e-12f);
+    for (int c = threadIdx.x; c < c1 - c0; c += blockDim.x) vk[c0 + c] = vacc[c] * invv;
+    cluster.sync();                                 // v complete and visible to the whole cluster
+    // ---- phase 2: t[r0:r1] = W[r] . v  (one warp per row)
     float tt = 0.f;
-    for (int r = warp; r < rows; r += nwarp) {
+    for (int r = r0 + warp; r < r1; r += nwarp) {
       float a = 0.f;
       for (int c = lane; c < cols; c += 32) a = fmaf(W[(long long)r * cols + c], vk[c], a);
       a = warp_sum(a);
-      if (lane == 0) { uk[r] = a; tt += a * a; }
+      if (lane == 0) { tloc[r - r0] = a; tt += a * a; }
     }
-    tt = block_sum_1024(tt, red);
+    tt = cluster_sum(cluster, &part[(k & 1) * 2 + 1], tt, red);
     const float nrm = sqrtf(tt);
     const float invu = 1.0f / (nrm + 1e-12f);
-    for (int r = threadIdx.x; r < rows; r += blockDim.x) uk[r] *= invu;
-    if (threadIdx.x == 0) {
-      const float sigma = tt * invu;                 // u . (W v) = |Wv|^2 / (|Wv| + 1e-12)
+    for (int r = threadIdx.x; r < r1 - r0; r += blockDim.x) uk[r0 + r] = tloc[r] * invu;
+    if (rank == 0 && threadIdx.x == 0) {
+      const float sigma = tt * invu;                // u . (W v) = |Wv|^2 / (|Wv| + 1e-12)
       d.sigma[k] = sigma;
       d.inv_sigma[k] = 1.0f / sigma;
     }
-    __syncthreads();
+    cluster.sync();                                 // u complete and visible
   }
   if (d.calls > 0) {
     const float* ul = d.u_hist + (long long)(d.calls - 1) * rows;
     const float* vl = d.v_hist + (long long)(d.calls - 1) * cols;
-    for (int r = threadIdx.x; r < rows; r += blockDim.x) d.u[r] = ul[r];
-    for (int c = threadIdx.x; c < cols; c += blockDim.x) d.v[c] = vl[c];
+    for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) d.u[r] = ul[r];
+    for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x) d.v[c] = vl[c];
   }
 }
 
@@ -409,7 +443,7 @@ int tcv_transpose_packed(const float* packed, int taps, int cin, int cout, int c
 
 int tcv_sn_power_iter(const tcv_sn_desc* descs_device, int n, tcv_stream_t stream) {
   TCV_REQUIRE(descs_device && n > 0, "sn_power_iter: no layers");
-  sn_power_iter_kernel<<<n, 1024, 0, S(stream)>>>(descs_device);
+  sn_power_iter_kernel<<<n * SN_CLUSTER, 1024, 0, S(stream)>>>(descs_device);   // one cluster of 8 CTAs per layer
   return launched("sn_power_iter_kernel");
 }
 

@@ -55,6 +55,12 @@ class TrainEngine(GcaVmnEngine):
         # weight gradients of the stride-1 convs / deconv phases on the tensor cores (split-K tcgen05 GEMM over
         # channel-major copies); TCV_TC_WGRAD=0 keeps the CUDA-core fp32 kernel everywhere (exact cross-check)
         import os
+        # small accumulators (weight / bias / BatchNorm-parameter gradients, sigma dot products) are carved out of ONE
+        # zero-filled buffer per step: they were ~700 separate fill kernels (2.6 ms) per step
+        self._arena = None
+        self._arena_off = 0
+        self._arena_need = 0
+        self._nbt: List = []
         self.use_tc_wgrad = os.environ.get("TCV_TC_WGRAD", "1") != "0"
         # "2": the NHWC-direct kernel (MN-major operands, no channel-major copies); "1": the split-K GEMM over copies
         self.wgrad_nhwc = os.environ.get("TCV_TC_WGRAD", "2") == "2"
@@ -136,8 +142,9 @@ class TrainEngine(GcaVmnEngine):
                                       v_hist=torch.empty((calls, cols), dtype=torch.float32, device=self.device),
                                       sigma=torch.empty((calls,), dtype=torch.float32, device=self.device),
                                       isig=torch.empty((calls,), dtype=torch.float32, device=self.device),
-                                      zdot=torch.zeros((calls,), dtype=torch.float64, device=self.device))
-            s["zdot"].zero_()
+                                      zdot=None)
+            assert rows <= 512 and cols <= 8192, (p, rows, cols)      # cluster kernel's shared-memory slices
+            s["zdot"] = self._zeros((calls,), torch.float64)
             d = descs[i]
             d.w_bar, d.rows, d.cols, d.u, d.v, d.calls = wbar.data_ptr(), rows, cols, u.data_ptr(), v.data_ptr(), calls
             d.u_hist, d.v_hist = s["u_hist"].data_ptr(), s["v_hist"].data_ptr()
@@ -149,6 +156,24 @@ class TrainEngine(GcaVmnEngine):
         for p in keys:                       # u / v were updated in place by the kernel: tell torch (version counters)
             for sfx in (".module.weight_u", ".module.weight_v"):
                 torch.autograd.graph.increment_version(self.named[p + sfx])
+
+    # ------------------------------------------------------------------ zero arena
+    def _arena_begin(self) -> None:
+        need = self._arena_need
+        self._arena = torch.zeros((need,), dtype=torch.uint8, device=self.device) if need else None
+        self._arena_off, self._arena_need = 0, 0
+
+    def _zeros(self, shape, dtype=torch.float32) -> torch.Tensor:
+        n = 1
+        for v in shape:
+            n *= v
+        nbytes = (n * torch.empty((), dtype=dtype).element_size() + 255) // 256 * 256
+        self._arena_need += nbytes
+        if self._arena is not None and self._arena_off + nbytes <= self._arena.numel():
+            t = self._arena[self._arena_off:self._arena_off + nbytes].view(dtype)[:n].view(shape)
+            self._arena_off += nbytes
+            return t
+        return torch.zeros(shape, dtype=dtype, device=self.device)
 
     # ------------------------------------------------------------------ tape helpers
     def _acc(self, t: Optional[TAct], g: Act, owned: bool) -> None:
@@ -172,8 +197,7 @@ class TrainEngine(GcaVmnEngine):
         t = self.dw.get(wkey)
         if t is None:
             ent = self.w[wkey]
-            t = self.dw[wkey] = torch.zeros((ent["k"] * ent["k"], ent["cin"], cout_pad or ent["cout"]),
-                                            dtype=torch.float32, device=self.device)
+            t = self.dw[wkey] = self._zeros((ent["k"] * ent["k"], ent["cin"], cout_pad or ent["cout"]))
         return t
 
     # ------------------------------------------------------------------ weight gradient
@@ -253,7 +277,9 @@ class TrainEngine(GcaVmnEngine):
             L = _cabi.lib()
             self._wgrad(d, xa, dz, cpad, self._dw(wkey, cpad))
             if bias:
-                db = self.dbias.setdefault(wkey, torch.zeros((cpad,), dtype=torch.float32, device=self.device))
+                db = self.dbias.get(wkey)
+                if db is None:
+                    db = self.dbias[wkey] = self._zeros((cpad,))
                 self._call("tcv_channel_sum", dz.ptr, dz.plane, dz.n * dz.h * dz.w, cpad, db.data_ptr())
             if x.needs_grad:
                 self._acc(x, self._dgrad(dz, wkey, xa, k, stride, prepadded), True)
@@ -380,7 +406,7 @@ class TrainEngine(GcaVmnEngine):
                    self.named[bnkey + ".running_var"].data_ptr())
         nbt = self.named.get(bnkey + ".num_batches_tracked")
         if nbt is not None:
-            nbt += groups
+            self._nbt.append((nbt, groups))
         self._call("tcv_bn_apply", C.byref(d), meta=tag)
         out = TAct(y, groups)
         keep = (mean, invstd, gamma, beta)
@@ -399,8 +425,7 @@ class TrainEngine(GcaVmnEngine):
                 self._call("tcv_bn_bwd_reduce", C.byref(d), dy.ptr, dy.plane, None, 0, bsums.data_ptr(), meta=tag)
             dg, db = self.dbn.get(bnkey, (None, None))
             if dg is None:
-                dg = torch.zeros((c,), dtype=torch.float32, device=dev)
-                db = torch.zeros((c,), dtype=torch.float32, device=dev)
+                dg, db = self._zeros((c,)), self._zeros((c,))
                 self.dbn[bnkey] = (dg, db)
             self._call("tcv_bn_param_grads", bsums.data_ptr(), groups, c, dg.data_ptr(), db.data_ptr())
             if self.sync_bn:
@@ -698,6 +723,8 @@ class TrainEngine(GcaVmnEngine):
         """VMN.forward in train mode on preprocessed input; records the tape.  trimask fp32 [B,S,1,H,W]."""
         self.tape = []
         self.dw.clear(); self.dbias.clear(); self.dbn.clear()
+        self._arena_begin()
+        self._nbt = []
         ncen = S - 2
         self.spectral_norm_step(S, ncen)
         N8 = (H // 8) * (W // 8)
@@ -724,6 +751,9 @@ class TrainEngine(GcaVmnEngine):
         self.head_in = t
         self.head = self.conv_op(t, "decoder.conv2", bias=True, act=ACT_TANH01, f32_out=pred)
         self.pred = pred
+        if self._nbt:                                   # num_batches_tracked += calls, one fused update for all layers
+            torch._foreach_add_([t_ for t_, _ in self._nbt], [int(g_) for _, g_ in self._nbt])
+            self._nbt = []
         return dict(pred=pred, attb=attb, attf=attf, small_mask=sm)
 
     def train_backward(self, dpred: torch.Tensor, dattb: Optional[torch.Tensor], dattf: Optional[torch.Tensor]) -> None:

@@ -97,7 +97,7 @@ def check_conv_bn(model, name, wkey, bnkey, cin, hw, *, stride=1, mode=1, act=AC
     net = model.NET
     eng = _train_engine_for(net, 7)
     eng.tape = []
-    eng.dw.clear(); eng.dbias.clear(); eng.dbn.clear()
+    eng.dw.clear(); eng.dbias.clear(); eng.dbn.clear(); eng._arena_begin(); eng._nbt = []
     eng.spectral_norm_step(groups, groups)
     # force the layer's call count = groups regardless of where it lives
     sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "weight_u" not in k and "weight_v" not in k
@@ -170,6 +170,7 @@ def check_sn(model):
     net = model.NET
     sd0 = {k: v.detach().clone().cpu() for k, v in tcvom_b200.engine.named_tensors(net).items()}
     eng = _train_engine_for(net, 7)
+    eng._arena_begin()
     eng.spectral_norm_step(5, 3)
     errs = {}
     for p in ("encoder.conv1", "encoder.layer_bottleneck.1.conv2", "decoder.layer3.0.conv1", "decoder.conv1"):
@@ -194,7 +195,7 @@ def check_gca(model, bound=3e-3):
     net = model.NET
     eng = _train_engine_for(net, 7)
     eng.tape = []
-    eng.dw.clear(); eng.dbias.clear(); eng.dbn.clear()
+    eng.dw.clear(); eng.dbias.clear(); eng.dbn.clear(); eng._arena_begin(); eng._nbt = []
     eng.spectral_norm_step(2, 2)
     p = "decoder.gca"
     n, h, w = 2, 8, 12
@@ -229,7 +230,7 @@ def check_tam(model, bound=2e-3):
     net = model.NET
     eng = _train_engine_for(net, 7)
     eng.tape = []
-    eng.dw.clear(); eng.dbias.clear(); eng.dbn.clear()
+    eng.dw.clear(); eng.dbias.clear(); eng.dbn.clear(); eng._arena_begin(); eng._nbt = []
     p = "decoder.fam"
     n, h, w = 2, 6, 8
     xs = [rnd((n, 128, h, w), 21 + i) for i in range(3)]
