@@ -16,24 +16,29 @@
 namespace tcv {
 
 constexpr int WG_KT = 64;                 // pixels per pipeline stage
-constexpr int WG_BLK = WG_KT * 128;       // bytes of one 64-channel block of a stage (8 KB)
-constexpr int WG_STAGES = 3;
+constexpr int WG_MAX_STAGES = 8;
+constexpr int WG_SMEM_BUDGET = 192 * 1024;
 
 struct WgParams {
   int n, gh, gw, TW, TH, tiles_x, tiles_y, total_tiles, tiles_per_slice;
   int ntaps, dy[TCV_MAX_TAPS], dx[TCV_MAX_TAPS], wtap[TCV_MAX_TAPS];
   int cin, cout, dz_c, mul, oy, ox;
   int xmul;               // input pixels per output pixel (conv stride): x is read with a traversal stride
-  int nblk;               // 64-channel blocks of the N tile (1 or 2)
+  // operand geometry: a channel block is one TMA box of row_bytes/2 channels (128 B rows: SWIZZLE_128B, 64 channels;
+  // 64 B rows: SWIZZLE_64B, 32 channels -- layers with <= 32 channels on both sides move half the bytes).  The MMA is
+  // always M = 128: with a_nblk == 1 the leading-dimension offset of the A descriptor is 0, so the rows beyond the first
+  // block alias it (their accumulator rows are duplicates and never stored) instead of streaming zero-filled boxes.
+  int row_bytes, a_nblk, nblk, stages;
   int n_tiles_n;
   uint32_t idesc;
   float* dw;
 };
 
-// MN-major SWIZZLE_128B shared-memory descriptor: LBO between 64-element MN blocks, SBO = 1024 B between 8-row K groups
-__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t addr, uint32_t lbo_bytes) {
-  return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
-         (1ull << 46) | (2ull << 61);
+// MN-major shared-memory descriptor: LBO between channel blocks, SBO = 8 pixel rows; layout 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t addr, uint32_t lbo_bytes, uint32_t row_bytes) {
+  const uint64_t layout = row_bytes == 128 ? 2 : 4;
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)((8 * row_bytes) >> 4) << 32) |
+         (1ull << 46) | (layout << 61);
 }
 
 __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX_hi,
@@ -43,11 +48,14 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
                                                             const __grid_constant__ WgParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int stage_bytes = (4 + 2 * p.nblk) * WG_BLK;     // A: 2 blocks x 2 planes, B: nblk blocks x 2 planes
+  const int WG_BLK = WG_KT * p.row_bytes;                // bytes of one channel block of a stage
+  const int WG_STAGES = p.stages;
+  const int cblk = p.row_bytes / 2;                      // channels per block
+  const int stage_bytes = 2 * (p.a_nblk + p.nblk) * WG_BLK;   // A: a_nblk blocks x 2 planes, B: nblk blocks x 2 planes
   const uint32_t bar_base = smem_base + WG_STAGES * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (WG_STAGES + s); };
-  const uint32_t accum_bar = bar_base + 8u * (2 * WG_STAGES);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (WG_MAX_STAGES + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * WG_MAX_STAGES);
   const uint32_t tmem_slot = accum_bar + 8u;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -55,11 +63,11 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
   const int t = blockIdx.x;                                // filter tap (fastest: the taps of a slice share L2 lines)
   const int slice = blockIdx.y;
   const int mt = blockIdx.z / p.n_tiles_n, nt = blockIdx.z % p.n_tiles_n;
-  const int ci0 = mt * 128, co0 = nt * (64 * p.nblk);
+  const int ci0 = mt * 128, co0 = nt * (cblk * p.nblk);
   const int tile_begin = slice * p.tiles_per_slice;
   const int tile_end = min(tile_begin + p.tiles_per_slice, p.total_tiles);
   const int iters = tile_end - tile_begin;
-  const uint32_t ncols = 64u * p.nblk;
+  const uint32_t ncols = (uint32_t)(cblk * p.nblk);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < WG_STAGES; ++s) {
@@ -98,15 +106,16 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
           mbar_expect_tx(full_bar(s), (uint32_t)stage_bytes);
           // A = x shifted by the tap: blocks (channels ci0.., ci0+64..) x planes (hi, lo)
           const int ax = x0 * p.xmul + tdx, ay = y0 * p.xmul + tdy;
-          tma_load_4d(st + 0 * WG_BLK, &mapX_hi, full_bar(s), ci0, ax, ay, img);
-          tma_load_4d(st + 1 * WG_BLK, &mapX_hi, full_bar(s), ci0 + 64, ax, ay, img);
-          tma_load_4d(st + 2 * WG_BLK, &mapX_lo, full_bar(s), ci0, ax, ay, img);
-          tma_load_4d(st + 3 * WG_BLK, &mapX_lo, full_bar(s), ci0 + 64, ax, ay, img);
+          for (int b = 0; b < p.a_nblk; ++b) {
+            tma_load_4d(st + b * WG_BLK, &mapX_hi, full_bar(s), ci0 + cblk * b, ax, ay, img);
+            tma_load_4d(st + (p.a_nblk + b) * WG_BLK, &mapX_lo, full_bar(s), ci0 + cblk * b, ax, ay, img);
+          }
           // B = dz (sub-sampled by mul for the deconv phases)
           const int zx = x0 * p.mul + p.ox, zy = y0 * p.mul + p.oy;
+          const uint32_t bst = st + 2 * p.a_nblk * WG_BLK;
           for (int b = 0; b < p.nblk; ++b) {
-            tma_load_4d(st + (4 + b) * WG_BLK, &mapZ_hi, full_bar(s), co0 + 64 * b, zx, zy, img);
-            tma_load_4d(st + (4 + p.nblk + b) * WG_BLK, &mapZ_lo, full_bar(s), co0 + 64 * b, zx, zy, img);
+            tma_load_4d(bst + b * WG_BLK, &mapZ_hi, full_bar(s), co0 + cblk * b, zx, zy, img);
+            tma_load_4d(bst + (p.nblk + b) * WG_BLK, &mapZ_lo, full_bar(s), co0 + cblk * b, zx, zy, img);
           }
         }
         __syncwarp();
@@ -119,14 +128,15 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
         const uint32_t st = smem_base + s * stage_bytes;
-        const uint32_t a_hi = st, a_lo = st + 2 * WG_BLK;
-        const uint32_t b_hi = st + 4 * WG_BLK, b_lo = b_hi + p.nblk * WG_BLK;
+        const uint32_t a_hi = st, a_lo = st + p.a_nblk * WG_BLK;
+        const uint32_t b_hi = st + 2 * p.a_nblk * WG_BLK, b_lo = b_hi + p.nblk * WG_BLK;
+        const uint32_t a_lbo = p.a_nblk > 1 ? (uint32_t)WG_BLK : 0u, rb = (uint32_t)p.row_bytes;
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < WG_KT / 16; ++ks) {
-            const uint32_t koff = ks * 16 * 128;           // 16 pixels further along K
-            const uint64_t ah = smem_desc_mn(a_hi + koff, WG_BLK), al = smem_desc_mn(a_lo + koff, WG_BLK);
-            const uint64_t bh = smem_desc_mn(b_hi + koff, WG_BLK), bl = smem_desc_mn(b_lo + koff, WG_BLK);
+            const uint32_t koff = ks * 16 * rb;            // 16 pixels further along K
+            const uint64_t ah = smem_desc_mn(a_hi + koff, a_lbo, rb), al = smem_desc_mn(a_lo + koff, a_lbo, rb);
+            const uint64_t bh = smem_desc_mn(b_hi + koff, WG_BLK, rb), bl = smem_desc_mn(b_lo + koff, WG_BLK, rb);
             tc_mma(tmem_d, ah, bh, p.idesc, (it > 0 || ks > 0) ? 1u : 0u);
             tc_mma(tmem_d, ah, bl, p.idesc, 1u);
             tc_mma(tmem_d, al, bh, p.idesc, 1u);
@@ -165,11 +175,12 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
   }
 }
 
-static int make_nhwc_map(CUtensorMap* m, const __nv_bfloat16* base, int c, int w, int h, int n, int tw, int th, int trav) {
+static int make_nhwc_map(CUtensorMap* m, const __nv_bfloat16* base, int c, int w, int h, int n, int tw, int th, int trav,
+                         int cblk) {
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t str[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)(tw * trav), (cuuint32_t)(th * trav), 1};
-  return make_map(m, base, 4, dims, str, box, /*bk: 64 -> SWIZZLE_128B*/ 64, false, trav);
+  cuuint32_t box[4] = {(cuuint32_t)cblk, (cuuint32_t)(tw * trav), (cuuint32_t)(th * trav), 1};
+  return make_map(m, base, 4, dims, str, box, /*bk: 64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B*/ cblk, false, trav);
 }
 
 int conv2d_wgrad_tc_supported(const tcv_conv_desc& d, int dz_c) {
@@ -198,8 +209,12 @@ int conv2d_wgrad_tc(const tcv_conv_desc& d, const __nv_bfloat16* dz, long long d
   p.cin = d.cin; p.cout = d.cout; p.dz_c = dz_c;
   p.mul = d.oy_mul; p.oy = d.oy_off; p.ox = d.ox_off;
   p.xmul = d.stride;
-  p.nblk = dz_c > 64 ? 2 : 1;
-  const int ntile = 64 * p.nblk;
+  const bool narrow = d.cin <= 32 && dz_c <= 32;
+  p.row_bytes = narrow ? 64 : 128;
+  const int cblk = p.row_bytes / 2;
+  p.nblk = dz_c > cblk ? 2 : 1;
+  p.a_nblk = d.cin > cblk ? 2 : 1;
+  const int ntile = cblk * p.nblk;
   p.n_tiles_n = (dz_c + ntile - 1) / ntile;
   const int n_tiles_m = (d.cin + 127) / 128;
   // D = f32, A = B = bf16, both MN-major (bits 15, 16), M = 128, N = ntile
@@ -216,12 +231,15 @@ int conv2d_wgrad_tc(const tcv_conv_desc& d, const __nv_bfloat16* dz, long long d
 
   CUtensorMap mX_hi, mX_lo, mZ_hi, mZ_lo;
   const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(d.x);
-  int rc = make_nhwc_map(&mX_hi, x, d.cin, d.iw, d.ih, d.n, p.TW, p.TH, d.stride);
+  int rc = make_nhwc_map(&mX_hi, x, d.cin, d.iw, d.ih, d.n, p.TW, p.TH, d.stride, cblk);
   if (rc) return rc;
-  if ((rc = make_nhwc_map(&mX_lo, x + d.x_plane, d.cin, d.iw, d.ih, d.n, p.TW, p.TH, d.stride))) return rc;
-  if ((rc = make_nhwc_map(&mZ_hi, dz, dz_c, d.ow, d.oh, d.n, p.TW, p.TH, p.mul))) return rc;
-  if ((rc = make_nhwc_map(&mZ_lo, dz + dz_plane, dz_c, d.ow, d.oh, d.n, p.TW, p.TH, p.mul))) return rc;
-  const int smem = WG_STAGES * (4 + 2 * p.nblk) * WG_BLK + 1024 + 256;
+  if ((rc = make_nhwc_map(&mX_lo, x + d.x_plane, d.cin, d.iw, d.ih, d.n, p.TW, p.TH, d.stride, cblk))) return rc;
+  if ((rc = make_nhwc_map(&mZ_hi, dz, dz_c, d.ow, d.oh, d.n, p.TW, p.TH, p.mul, cblk))) return rc;
+  if ((rc = make_nhwc_map(&mZ_lo, dz + dz_plane, dz_c, d.ow, d.oh, d.n, p.TW, p.TH, p.mul, cblk))) return rc;
+  const int stage_bytes = 2 * (p.a_nblk + p.nblk) * WG_KT * p.row_bytes;
+  p.stages = WG_SMEM_BUDGET / stage_bytes;
+  if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
+  const int smem = p.stages * stage_bytes + 1024 + 256;
   TCV_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid(d.ntaps, slices, mn);
   conv_wgrad_tc_kernel<<<grid, 192, smem, st>>>(mX_hi, mX_lo, mZ_hi, mZ_lo, p);
