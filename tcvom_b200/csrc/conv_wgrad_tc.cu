@@ -30,6 +30,11 @@ struct WgParams {
   // block alias it (their accumulator rows are duplicates and never stored) instead of streaming zero-filled boxes.
   int row_bytes, a_nblk, nblk, stages;
   int n_tiles_n;
+  // stacked-tap mode (both sides <= 64 channels): the roles are swapped -- A = dz (M side = output channels, one
+  // block, aliased up to M = 128), B = the x boxes of `tpg` filter taps stacked along N (LBO = one block), so one
+  // MMA of N = tpg * cblk columns serves tpg taps.  An MN-major MMA costs ~100 cycles per K = 16 step almost
+  // independently of N (measured), so the narrow layers want few, wide MMAs.
+  int swap, tpg, ngroups;
   uint32_t idesc;
   float* dw;
 };
@@ -51,7 +56,9 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
   const int WG_BLK = WG_KT * p.row_bytes;                // bytes of one channel block of a stage
   const int WG_STAGES = p.stages;
   const int cblk = p.row_bytes / 2;                      // channels per block
-  const int stage_bytes = 2 * (p.a_nblk + p.nblk) * WG_BLK;   // A: a_nblk blocks x 2 planes, B: nblk blocks x 2 planes
+  // wide: A = x (a_nblk blocks), B = dz (nblk blocks); stacked: A = dz (1 block), B = x boxes of tpg taps
+  const int nb_a = p.swap ? 1 : p.a_nblk, nb_b = p.swap ? p.tpg : p.nblk;
+  const int stage_bytes = 2 * (nb_a + nb_b) * WG_BLK;
   const uint32_t bar_base = smem_base + WG_STAGES * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (WG_MAX_STAGES + s); };
@@ -60,14 +67,18 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t = blockIdx.x;                                // filter tap (fastest: the taps of a slice share L2 lines)
+  const int t = blockIdx.x;                                // filter tap / tap group (fastest: they share L2 lines)
+  const int t0 = p.swap ? t * p.tpg : t;                   // first tap of this CTA
+  const int nt_here = p.swap ? min(p.tpg, p.ntaps - t0) : 1;
   const int slice = blockIdx.y;
   const int mt = blockIdx.z / p.n_tiles_n, nt = blockIdx.z % p.n_tiles_n;
   const int ci0 = mt * 128, co0 = nt * (cblk * p.nblk);
   const int tile_begin = slice * p.tiles_per_slice;
   const int tile_end = min(tile_begin + p.tiles_per_slice, p.total_tiles);
   const int iters = tile_end - tile_begin;
-  const uint32_t ncols = (uint32_t)(cblk * p.nblk);
+  const uint32_t ncols_used = (uint32_t)(cblk * (p.swap ? p.tpg : p.nblk));
+  uint32_t ncols = 32;                                     // TMEM allocation: power of two >= columns used
+  while (ncols < ncols_used) ncols <<= 1;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < WG_STAGES; ++s) {
@@ -91,7 +102,6 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
   if (iters > 0) {
     if (warp == 0) {
       // ================================ TMA producer ================================
-      const int tdy = p.dy[t], tdx = p.dx[t];
       for (int it = 0; it < iters; ++it) {
         const int tile = tile_begin + it;
         const int tx = tile % p.tiles_x;
@@ -103,19 +113,29 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
         mbar_wait(empty_bar(s), ph ^ 1u);
         const uint32_t st = smem_base + s * stage_bytes;
         if (elect_one()) {
-          mbar_expect_tx(full_bar(s), (uint32_t)stage_bytes);
-          // A = x shifted by the tap: blocks (channels ci0.., ci0+64..) x planes (hi, lo)
-          const int ax = x0 * p.xmul + tdx, ay = y0 * p.xmul + tdy;
-          for (int b = 0; b < p.a_nblk; ++b) {
-            tma_load_4d(st + b * WG_BLK, &mapX_hi, full_bar(s), ci0 + cblk * b, ax, ay, img);
-            tma_load_4d(st + (p.a_nblk + b) * WG_BLK, &mapX_lo, full_bar(s), ci0 + cblk * b, ax, ay, img);
-          }
-          // B = dz (sub-sampled by mul for the deconv phases)
-          const int zx = x0 * p.mul + p.ox, zy = y0 * p.mul + p.oy;
-          const uint32_t bst = st + 2 * p.a_nblk * WG_BLK;
-          for (int b = 0; b < p.nblk; ++b) {
-            tma_load_4d(bst + b * WG_BLK, &mapZ_hi, full_bar(s), co0 + cblk * b, zx, zy, img);
-            tma_load_4d(bst + (p.nblk + b) * WG_BLK, &mapZ_lo, full_bar(s), co0 + cblk * b, zx, zy, img);
+          const int zx = x0 * p.mul + p.ox, zy = y0 * p.mul + p.oy;   // dz (sub-sampled by mul for the deconv phases)
+          const uint32_t bst = st + 2 * nb_a * WG_BLK;
+          if (p.swap) {
+            mbar_expect_tx(full_bar(s), (uint32_t)(2 * (1 + nt_here) * WG_BLK));
+            tma_load_4d(st, &mapZ_hi, full_bar(s), 0, zx, zy, img);
+            tma_load_4d(st + WG_BLK, &mapZ_lo, full_bar(s), 0, zx, zy, img);
+            for (int j = 0; j < nt_here; ++j) {              // x shifted by each tap of the group
+              const int ax = x0 * p.xmul + p.dx[t0 + j], ay = y0 * p.xmul + p.dy[t0 + j];
+              tma_load_4d(bst + j * WG_BLK, &mapX_hi, full_bar(s), 0, ax, ay, img);
+              tma_load_4d(bst + (nb_b + j) * WG_BLK, &mapX_lo, full_bar(s), 0, ax, ay, img);
+            }
+          } else {
+            mbar_expect_tx(full_bar(s), (uint32_t)stage_bytes);
+            // A = x shifted by the tap: blocks (channels ci0.., ci0+cblk..) x planes (hi, lo)
+            const int ax = x0 * p.xmul + p.dx[t], ay = y0 * p.xmul + p.dy[t];
+            for (int b = 0; b < p.a_nblk; ++b) {
+              tma_load_4d(st + b * WG_BLK, &mapX_hi, full_bar(s), ci0 + cblk * b, ax, ay, img);
+              tma_load_4d(st + (p.a_nblk + b) * WG_BLK, &mapX_lo, full_bar(s), ci0 + cblk * b, ax, ay, img);
+            }
+            for (int b = 0; b < p.nblk; ++b) {
+              tma_load_4d(bst + b * WG_BLK, &mapZ_hi, full_bar(s), co0 + cblk * b, zx, zy, img);
+              tma_load_4d(bst + (p.nblk + b) * WG_BLK, &mapZ_lo, full_bar(s), co0 + cblk * b, zx, zy, img);
+            }
           }
         }
         __syncwarp();
@@ -128,18 +148,20 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
         const uint32_t st = smem_base + s * stage_bytes;
-        const uint32_t a_hi = st, a_lo = st + p.a_nblk * WG_BLK;
-        const uint32_t b_hi = st + 2 * p.a_nblk * WG_BLK, b_lo = b_hi + p.nblk * WG_BLK;
-        const uint32_t a_lbo = p.a_nblk > 1 ? (uint32_t)WG_BLK : 0u, rb = (uint32_t)p.row_bytes;
+        const uint32_t a_hi = st, a_lo = st + nb_a * WG_BLK;
+        const uint32_t b_hi = st + 2 * nb_a * WG_BLK, b_lo = b_hi + nb_b * WG_BLK;
+        const uint32_t a_lbo = nb_a > 1 ? (uint32_t)WG_BLK : 0u, rb = (uint32_t)p.row_bytes;
+        // the last tap group may hold fewer taps: its MMAs are narrower (idesc N field, bits 17..22)
+        const uint32_t idesc = p.swap ? ((p.idesc & ~(0x3Fu << 17)) | ((uint32_t)((nt_here * cblk) >> 3) << 17)) : p.idesc;
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < WG_KT / 16; ++ks) {
             const uint32_t koff = ks * 16 * rb;            // 16 pixels further along K
             const uint64_t ah = smem_desc_mn(a_hi + koff, a_lbo, rb), al = smem_desc_mn(a_lo + koff, a_lbo, rb);
             const uint64_t bh = smem_desc_mn(b_hi + koff, WG_BLK, rb), bl = smem_desc_mn(b_lo + koff, WG_BLK, rb);
-            tc_mma(tmem_d, ah, bh, p.idesc, (it > 0 || ks > 0) ? 1u : 0u);
-            tc_mma(tmem_d, ah, bl, p.idesc, 1u);
-            tc_mma(tmem_d, al, bh, p.idesc, 1u);
+            tc_mma(tmem_d, ah, bh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+            tc_mma(tmem_d, ah, bl, idesc, 1u);
+            tc_mma(tmem_d, al, bh, idesc, 1u);
           }
           tc_commit(empty_bar(s));
           if (it == iters - 1) tc_commit(accum_bar);
@@ -153,17 +175,35 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
       mbar_wait(accum_bar, 0);
       tc_fence_after();
       const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
-      const int ci = ci0 + r;
-      float* out = p.dw + ((long long)p.wtap[t] * p.cin + ci) * p.dz_c + co0;
+      if (p.swap) {
+        // rows = output channels (duplicates beyond the block are skipped), columns = (tap of the group, input channel)
+        const bool row_ok = r < cblk && r < p.dz_c;
 #pragma unroll 1
-      for (int c0 = 0; c0 < (int)ncols; c0 += 32) {
-        uint32_t v[32];
-        tc_ld32(taddr + c0, v);
-        if (ci >= p.cin) continue;
+        for (int c0 = 0; c0 < nt_here * cblk; c0 += 32) {
+          uint32_t v[32];
+          tc_ld32(taddr + c0, v);
+          if (!row_ok) continue;
+          const int j = c0 / cblk, cc0 = c0 - j * cblk;
+          float* out = p.dw + ((long long)p.wtap[t0 + j] * p.cin + cc0) * p.dz_c + r;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float f = __uint_as_float(v[j]);
-          if (co0 + c0 + j < p.dz_c && f != 0.f) atomicAdd(out + c0 + j, f);
+          for (int i = 0; i < 32; ++i) {
+            const float f = __uint_as_float(v[i]);
+            if (cc0 + i < p.cin && f != 0.f) atomicAdd(out + (long long)i * p.dz_c, f);
+          }
+        }
+      } else {
+        const int ci = ci0 + r;
+        float* out = p.dw + ((long long)p.wtap[t] * p.cin + ci) * p.dz_c + co0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < (int)ncols_used; c0 += 32) {
+          uint32_t v[32];
+          tc_ld32(taddr + c0, v);
+          if (ci >= p.cin) continue;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float f = __uint_as_float(v[j]);
+            if (co0 + c0 + j < p.dz_c && f != 0.f) atomicAdd(out + c0 + j, f);
+          }
         }
       }
     }
@@ -221,8 +261,18 @@ int conv2d_wgrad_tc(const tcv_conv_desc& d, const __nv_bfloat16* dz, long long d
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(ntile >> 3) << 17) |
             ((uint32_t)(128 >> 4) << 24);
   p.dw = dw;
-  const int mn = n_tiles_m * p.n_tiles_n;
-  int slices = (4 * 148 + d.ntaps * mn - 1) / (d.ntaps * mn);
+  int mn = n_tiles_m * p.n_tiles_n;
+  int grid_x = d.ntaps;
+  if (d.cin <= cblk && dz_c <= cblk) {
+    p.swap = 1;
+    p.ngroups = (d.ntaps * cblk + 255) / 256;
+    p.tpg = (d.ntaps + p.ngroups - 1) / p.ngroups;
+    p.ngroups = (d.ntaps + p.tpg - 1) / p.tpg;
+    grid_x = p.ngroups;
+    mn = 1;
+    p.idesc = (p.idesc & ~(0x3Fu << 17)) | ((uint32_t)((p.tpg * cblk) >> 3) << 17);
+  }
+  int slices = (4 * 148 + grid_x * mn - 1) / (grid_x * mn);
   const int max_slices = (p.total_tiles + 3) / 4;          // at least 4 pixel tiles (256 pixels) per CTA
   if (slices > max_slices) slices = max_slices;
   if (slices < 1) slices = 1;
@@ -236,12 +286,12 @@ int conv2d_wgrad_tc(const tcv_conv_desc& d, const __nv_bfloat16* dz, long long d
   if ((rc = make_nhwc_map(&mX_lo, x + d.x_plane, d.cin, d.iw, d.ih, d.n, p.TW, p.TH, d.stride, cblk))) return rc;
   if ((rc = make_nhwc_map(&mZ_hi, dz, dz_c, d.ow, d.oh, d.n, p.TW, p.TH, p.mul, cblk))) return rc;
   if ((rc = make_nhwc_map(&mZ_lo, dz + dz_plane, dz_c, d.ow, d.oh, d.n, p.TW, p.TH, p.mul, cblk))) return rc;
-  const int stage_bytes = 2 * (p.a_nblk + p.nblk) * WG_KT * p.row_bytes;
+  const int stage_bytes = 2 * (p.swap ? 1 + p.tpg : p.a_nblk + p.nblk) * WG_KT * p.row_bytes;
   p.stages = WG_SMEM_BUDGET / stage_bytes;
   if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
   const int smem = p.stages * stage_bytes + 1024 + 256;
   TCV_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  dim3 grid(d.ntaps, slices, mn);
+  dim3 grid(grid_x, slices, mn);
   conv_wgrad_tc_kernel<<<grid, 192, smem, st>>>(mX_hi, mX_lo, mZ_hi, mZ_lo, p);
   return launched("conv_wgrad_tc_kernel");
 }
