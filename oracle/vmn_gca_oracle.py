@@ -295,8 +295,8 @@ def eval_preprocess(imgs, tris, dilate_kernel=None):
 
     imgs [B,S,3,H,W] BGR 0..255; tris [B,S,1,H,W] in {0,128,255}.
     Returns (x6 [B,S,6,H,W], trimask float [B,S,1,H,W])."""
-    mean = torch.tensor(IMG_MEAN).reshape(1, 1, 3, 1, 1)
-    std = torch.tensor(IMG_STD).reshape(1, 1, 3, 1, 1)
+    mean = torch.tensor(IMG_MEAN, device=imgs.device).reshape(1, 1, 3, 1, 1)
+    std = torch.tensor(IMG_STD, device=imgs.device).reshape(1, 1, 3, 1, 1)
     scaled = imgs.float().flip([2]) * (1.0 / 255)
     norm = (scaled - mean) / std
     st = tris.float() * (1.0 / 255)
@@ -346,8 +346,8 @@ def train_preprocess(a, fg, bg, radii, eps=0.0):
     """FullModel.preprocess + make_trimap, TRIMAP_CHANNEL == 3 -- models/model.py:54-92.
     a [B,S,1,H,W], fg/bg [B,S,3,H,W] (BGR 0..255); radii: dilation radius per sample (the reference draws
     torch.randint(0, 26) per sample when DILATION_KERNEL is None, model.py:62)."""
-    mean = torch.tensor(IMG_MEAN).reshape(1, 1, 3, 1, 1)
-    std = torch.tensor(IMG_STD).reshape(1, 1, 3, 1, 1)
+    mean = torch.tensor(IMG_MEAN, device=a.device).reshape(1, 1, 3, 1, 1)
+    std = torch.tensor(IMG_STD, device=a.device).reshape(1, 1, 3, 1, 1)
     gts = a * (1.0 / 255)
     fgs = fg.flip([2]) * (1.0 / 255)
     bgs = bg.flip([2]) * (1.0 / 255)

@@ -95,6 +95,27 @@ class _TrainStepFn(torch.autograd.Function):
         return (None, None, None, None) + tuple(grads)
 
 
+class _VMNTrainFn(torch.autograd.Function):
+    """Autograd boundary at the plugin seam: VMN.forward in train mode (the reference's own FullModel_VMD computes the
+    losses on top with torch).  Differentiable outputs: preds of the centre frames and the TAM logits."""
+
+    @staticmethod
+    def forward(ctx, net, x8, trimask, B, S, H, W, *params):
+        eng = _train_engine_for(net, int(net.decoder.fam.window))
+        out = eng.train_forward(x8, trimask, B, S, H, W)
+        ctx.eng, ctx.names = eng, net.__dict__["_train_param_names"]
+        ctx.mark_non_differentiable(out["small_mask"])
+        return out["pred"], out["attb"], out["attf"], out["small_mask"]
+
+    @staticmethod
+    def backward(ctx, dpred, dattb, dattf, _):
+        eng = ctx.eng
+        z = lambda g, like: g.contiguous().float() if g is not None else torch.zeros_like(like)
+        eng.train_backward(z(dpred, eng.pred), dattb.contiguous().float() if dattb is not None else None,
+                           dattf.contiguous().float() if dattf is not None else None)
+        return (None,) * 7 + tuple(eng.collect_grads(ctx.names))
+
+
 class _OpEngineMixin:
     """Gives a standalone operator module (TAM / GCA) its own small engine over its parameters."""
 
@@ -207,21 +228,63 @@ class VMN(nn.Module):
         return new
 
     def _check_mode(self):
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError(
-                "tcvom_b200: the training path (backward kernels, train-mode BatchNorm/SpectralNorm) is not "
-                "built yet; call .eval() / torch.no_grad() for inference.  No PyTorch fallback is provided.")
         if self.training:
             raise NotImplementedError(
-                "tcvom_b200: train-mode forward (batch-statistics BatchNorm, SpectralNorm power iteration) is "
-                "not built yet; call .eval().")
+                "tcvom_b200: this entry point is inference-only; the training step goes through "
+                "FullModel_VMD / FullModel / VMN.forward in .train() mode.")
+
+    def _forward_train(self, images, masks):
+        """Train-mode VMN.forward (VMN_model.py:83-113) on the native training engine, autograd-connected."""
+        if self.freeze_backbone:
+            raise NotImplementedError("tcvom_b200: freeze_backbone training (pretrain_ddp.py) is not built")
+        S = len(images)
+        for i in range(S):
+            images[i] = images[i].squeeze(1)
+        x0 = images[0]
+        _require_cuda(x0, "images")
+        B, Cin, H, W = x0.shape
+        assert Cin == 6, "vmn_gca takes 3 image + 3 trimap channels"
+        if H % 32 or W % 32:
+            raise ValueError("tcvom_b200: H and W must be multiples of 32")
+        L = _cabi.lib()
+        st = _stream(x0.device)
+        x8 = Act.empty(B * S, H, W, 8, x0.device)
+        trimask = torch.empty((B, S, 1, H, W), dtype=torch.float32, device=x0.device)
+        for i in range(S):
+            xi = images[i].detach().contiguous().float()
+            for b in range(B):
+                n = b * S + i
+                _cabi.check(L.tcv_nchw_to_split(xi[b].data_ptr(), 1, 6, H, W, 8, x8.slice(n, n + 1).ptr, x8.plane, st),
+                            "nchw_to_split")
+            trimask[:, i] = masks[i].reshape(B, 1, H, W).float()
+        named = named_tensors(self)
+        names = [n for n, t in named.items() if isinstance(t, nn.Parameter) and t.requires_grad]
+        self.__dict__["_train_param_names"] = names
+        params = [named[n] for n in names]
+        if torch.is_grad_enabled():
+            pred, attb_t, attf_t, sm = _VMNTrainFn.apply(self, x8, trimask, B, S, H, W, *params)
+        else:
+            eng = _train_engine_for(self, int(self.decoder.fam.window))
+            out = eng.train_forward(x8, trimask, B, S, H, W)
+            eng.tape = []
+            pred, attb_t, attf_t, sm = out["pred"], out["attb"], out["attf"], out["small_mask"]
+        preds = [None] * S; attb = [None] * S; attf = [None] * S; small = [None] * S
+        for i in range(1, S - 1):
+            preds[i] = pred[:, i - 1]
+            attb[i] = attb_t[:, i - 1]
+            attf[i] = attf_t[:, i - 1]
+            small[i] = sm[:, i - 1].bool()
+        preds[0] = torch.zeros_like(preds[1])
+        preds[-1] = torch.zeros_like(preds[-2])
+        return preds, attb, attf, small
 
     def forward(self, images: List[torch.Tensor], masks: Sequence[torch.Tensor], extras=None):
         """images: list of S tensors [B,1,6,H,W] (normalised RGB + one-hot trimap); masks: S tensors
         [B,1,1,H,W].  Returns (preds, attb, attf, small_mask) exactly like VMN_model.py:113."""
         if extras is not None:
             raise NotImplementedError("tcvom_b200: `extras` is only used by the FBA base network")
-        self._check_mode()
+        if self.training:
+            return self._forward_train(images, masks)
         S = len(images)
         for i in range(S):
             images[i] = images[i].squeeze(1)                        # VMN_model.py:94 (in-place list update)

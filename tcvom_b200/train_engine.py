@@ -241,6 +241,12 @@ class TrainEngine(GcaVmnEngine):
                        meta=dict(tag=f"cin{cin} cout{dz_c} K{ktot} taps{len(ts)} split{nsplit}"))
         return xt
 
+    def _ctag(self, d: ConvDesc, what: str) -> dict:
+        if getattr(self, "_prof", None) is None:
+            return {}
+        path = {0: "direct", 1: "tc", 2: "tc2", 3: "tc3"}[_cabi.lib().tcv_conv2d_path(C.byref(d))]
+        return dict(tag=f"{what} {path} {d.cin}->{d.cout} t{d.ntaps} s{d.stride} px{d.n * d.gh * d.gw}")
+
     # ------------------------------------------------------------------ convolution (raw, no BatchNorm)
     def _fwd_geometry(self, x: Act, k: int, stride: int, prepadded: bool):
         if k == 3 and prepadded:
@@ -266,7 +272,7 @@ class TrainEngine(GcaVmnEngine):
         y = None if head else self._act(xa.n, oh, ow, cout)
         d = self._desc(xa, ent["w"].data_ptr(), taps, stride, pad, y, oh, ow, cout, oh, ow, 1, 0, 1, 0, wkey, None, bias,
                        act, None, 0, None, None, f32_out.data_ptr() if head else 0)
-        self._call("tcv_conv2d", C.byref(d))
+        self._call("tcv_conv2d", C.byref(d), meta=self._ctag(d, "fwd"))
         z = TAct(y, x.groups)
         cpad = (cout + 7) // 8 * 8
 
@@ -302,7 +308,7 @@ class TrainEngine(GcaVmnEngine):
                 taps = [(0, 0)]
             d = self._desc(dz, ent["w"].data_ptr(), taps, 1, PAD_ZERO, dx, xa.h, xa.w, cin_f, xa.h, xa.w, 1, 0, 1, 0, tk,
                            None, False, ACT_NONE, None, 0, None, None, 0)
-            self._call("tcv_conv2d", C.byref(d))
+            self._call("tcv_conv2d", C.byref(d), meta=self._ctag(d, "dgrad"))
             return dx
         assert stride == 2 and xa.h % 2 == 0 and xa.w % 2 == 0
         if k == 1:
@@ -324,7 +330,7 @@ class TrainEngine(GcaVmnEngine):
                 wtap = [ky * 3 + kx for ky, oy in rows for kx, ox in cols]
                 d = self._desc(dz, ent["w"].data_ptr(), taps, 1, PAD_ZERO, dx, xa.h, xa.w, cin_f, xa.h // 2, xa.w // 2,
                                2, py, 2, px, tk, None, False, ACT_NONE, None, 0, None, None, 0, wtap=wtap)
-                self._call("tcv_conv2d", C.byref(d))
+                self._call("tcv_conv2d", C.byref(d), meta=self._ctag(d, "dgrad-s2phase"))
         return dx
 
     def deconv_op(self, x: TAct, wkey: str) -> TAct:
@@ -345,7 +351,7 @@ class TrainEngine(GcaVmnEngine):
                 wtap = [ky * 4 + kx for ky, dy in kys for kx, dx in kxs]
                 d = self._desc(xa, ent["w"].data_ptr(), taps, 1, PAD_ZERO, y, oh, ow, cout, xa.h, xa.w, 2, py, 2, px,
                                wkey, None, False, ACT_NONE, None, 0, None, None, 0, wtap=wtap)
-                self._call("tcv_conv2d", C.byref(d))
+                self._call("tcv_conv2d", C.byref(d), meta=self._ctag(d, "fwd-deconv"))
                 descs.append(d)
         z = TAct(y, x.groups)
 
@@ -362,7 +368,7 @@ class TrainEngine(GcaVmnEngine):
                 taps = [(ky - 1, kx - 1) for ky in range(4) for kx in range(4)]
                 dd = self._desc(dz, te["w"].data_ptr(), taps, 2, PAD_ZERO, dx, xa.h, xa.w, xa.c, xa.h, xa.w, 1, 0, 1, 0,
                                 wkey + "#T", None, False, ACT_NONE, None, 0, None, None, 0)
-                self._call("tcv_conv2d", C.byref(dd))
+                self._call("tcv_conv2d", C.byref(dd), meta=self._ctag(dd, "dgrad-deconv"))
                 self._acc(x, dx, True)
             z.g = None
         self.tape.append(backward)
