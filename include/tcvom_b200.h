@@ -262,6 +262,11 @@ int tcv_pad_reflect1_bwd(const void* dy, int n, int h, int w, int c, void* dx, t
 /* gradient of (tanh(z)+1)/2 given the output: dz8[i][0] = dpred[i]*2*pred[i]*(1-pred[i]), channels 1..7 = 0
  * (split-bf16 [pixels][8], the 8-channel padding the conv kernels need) */
 int tcv_tanh01_bwd(const float* pred, const float* dpred, long long pixels, void* dz8, tcv_stream_t stream);
+/* Alpha head on the tensor-core conv path: decoder.conv2 (32 -> 1, VMN_GCA.py:46) is run as a 32 -> 32 conv whose
+ * output channels 1..31 have zero weights; pred[i] = (tanh(x[i][0]) + 1) / 2 (VMN_GCA.py:47) and the gradient
+ * dz[i][0] = dpred[i]*2*pred[i]*(1-pred[i]), dz[i][1..c-1] = 0.  x / dz split-bf16 [pixels][c]. */
+int tcv_head_tanh01(const void* x, long long x_plane, long long pixels, int c, float* pred, tcv_stream_t stream);
+int tcv_head_tanh01_bwd(const float* pred, const float* dpred, long long pixels, int c, void* dz, tcv_stream_t stream);
 /* fp32 [count] -> split-bf16 planes */
 int tcv_f32_to_split(const float* x, long long count, void* y, long long y_plane, tcv_stream_t stream);
 /* split-bf16 planes -> fp32 [count] (hi + lo) */

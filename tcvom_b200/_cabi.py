@@ -114,6 +114,8 @@ SIGNATURES = {
     "tcv_upsample2_scaled": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "tcv_pad_reflect1_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_tanh01_bwd": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_void_p]),
+    "tcv_head_tanh01": (c_int, [c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p]),
+    "tcv_head_tanh01_bwd": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p]),
     "tcv_f32_to_split": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p]),
     "tcv_split_to_f32": (c_int, [c_void_p, c_ll, c_ll, c_void_p, c_void_p]),
     "tcv_transpose_packed": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -165,6 +165,29 @@ __global__ void tanh01_bwd_kernel(const float* __restrict__ pred, const float* _
   store8(dz8 + i * 8, pixels * 8, f);
 }
 
+// alpha head on the tensor-core path: the 32 -> 1 conv runs as a 32 -> 32 conv with zero-padded output channels;
+// pred = (tanh(channel 0) + 1) / 2  (VMN_GCA.py:47), and its gradient goes back into channel 0 only
+__global__ void head_tanh01_kernel(const __nv_bfloat16* __restrict__ x, long long plane, long long pixels, int c,
+                                   float* __restrict__ pred) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pixels) return;
+  pred[i] = (tanhf(load1(x + i * c, plane)) + 1.0f) * 0.5f;
+}
+
+__global__ void head_tanh01_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ dpred, long long pixels,
+                                       int c8, __nv_bfloat16* __restrict__ dz) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pixels * c8) return;
+  const long long px = i / c8;
+  const int g = (int)(i - px * c8);
+  float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (g == 0) {
+    const float y = pred[px];
+    f[0] = dpred[px] * 2.0f * y * (1.0f - y);
+  }
+  store8(dz + i * 8, pixels * c8 * 8, f);
+}
+
 __global__ void f32_to_split_kernel(const float* __restrict__ x, long long count4, __nv_bfloat16* __restrict__ y,
                                     long long plane) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -418,6 +441,20 @@ int tcv_tanh01_bwd(const float* pred, const float* dpred, long long pixels, void
   TCV_REQUIRE(pred && dpred && dz8 && pixels > 0, "tanh01_bwd: null pointer");
   tanh01_bwd_kernel<<<nb(pixels), 256, 0, S(stream)>>>(pred, dpred, pixels, reinterpret_cast<__nv_bfloat16*>(dz8));
   return launched("tanh01_bwd_kernel");
+}
+
+int tcv_head_tanh01(const void* x, long long x_plane, long long pixels, int c, float* pred, tcv_stream_t stream) {
+  TCV_REQUIRE(x && pred && pixels > 0 && c >= 1, "head_tanh01: bad arguments");
+  head_tanh01_kernel<<<nb(pixels), 256, 0, S(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                       x_plane ? x_plane : pixels * c, pixels, c, pred);
+  return launched("head_tanh01_kernel");
+}
+
+int tcv_head_tanh01_bwd(const float* pred, const float* dpred, long long pixels, int c, void* dz, tcv_stream_t stream) {
+  TCV_REQUIRE(pred && dpred && dz && pixels > 0 && c % 8 == 0, "head_tanh01_bwd: bad arguments");
+  head_tanh01_bwd_kernel<<<nb(pixels * (c / 8)), 256, 0, S(stream)>>>(pred, dpred, pixels, c / 8,
+                                                                     reinterpret_cast<__nv_bfloat16*>(dz));
+  return launched("head_tanh01_bwd_kernel");
 }
 
 int tcv_f32_to_split(const float* x, long long count, void* y, long long y_plane, tcv_stream_t stream) {

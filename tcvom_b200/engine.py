@@ -182,6 +182,8 @@ class GcaVmnEngine:
                 b = named.get(p + ".bias")
                 if b is not None:
                     self.bias[p] = b
+                if t.shape[0] == 1 and t.shape[1] % 32 == 0 and t.shape[2] == 3:
+                    self._pack_head32(L, st, p, t, b)
             elif name.endswith(".running_var"):
                 p = name[: -len(".running_var")]
                 c = t.numel()
@@ -218,6 +220,25 @@ class GcaVmnEngine:
                 ent["w_tc"] = torch.empty((2, kh * kw, cout, cin_pad), dtype=torch.bfloat16, device=wbar.device)
             _cabi.check(L.tcv_pack_weight_tc(ent["w"].data_ptr(), kh * kw, cin_pad, cout, ent["w_tc"].data_ptr(), st),
                         "pack_weight_tc")
+
+    HEAD32 = "#head32"
+
+    def _pack_head32(self, L, st, p, w, b):
+        """The 1-channel alpha head (decoder.conv2) as a 32-output-channel conv with zero-padded weights, so that it
+        (and, in training, both of its gradients) runs on the tensor-core conv kernels; tcv_head_tanh01 reads channel 0."""
+        key = p + self.HEAD32
+        pads = self.__dict__.setdefault("_head32_pads", {})
+        if key not in pads or pads[key][0].device != w.device:
+            pads[key] = (torch.zeros((32,) + tuple(w.shape[1:]), dtype=torch.float32, device=w.device),
+                         torch.zeros((32,), dtype=torch.float32, device=w.device))
+        wpad, bpad = pads[key]
+        with torch.no_grad():
+            wpad[0].copy_(w[0])
+            if b is not None:
+                bpad[:1].copy_(b)
+        self._pack(L, st, key, wpad, None, None, None, transposed=False)      # in place: recorded plans stay valid
+        self.w[key]["cout_real"] = 1
+        self.bias[key] = bpad
 
     def get_plan(self, key) -> Optional[Plan]:
         plan = self.plans.get(key)
@@ -514,7 +535,13 @@ class GcaVmnEngine:
         t = self._dec_layer(t, "decoder.layer3", DEC_LAYERS[2][2], fea[2])
         t = self._dec_layer(t, "decoder.layer4", DEC_LAYERS[3][2], fea[1])
         t = self.deconv4x4s2(t, "decoder.conv1", bn="decoder.bn1", act=ACT_LEAKY02, res2=fea[0])
-        self.conv(t, "decoder.conv2", bias=True, act=ACT_TANH01, f32_ptr=pred_ptr, want_split=False)
+        hk = "decoder.conv2" + self.HEAD32
+        if self.use_tc_conv and hk in self.w and os.environ.get("TCV_HEAD32", "1") == "1":
+            z = self.conv(t, hk, bias=True)
+            self._call("tcv_head_tanh01", z.ptr, z.plane, z.n * z.h * z.w, z.c, pred_ptr,
+                       meta=dict(kind="tcv_head_tanh01", bytes=z.n * z.h * z.w * (2 * 32 + 4)))
+        else:
+            self.conv(t, "decoder.conv2", bias=True, act=ACT_TANH01, f32_ptr=pred_ptr, want_split=False)
 
     def window_program(self, x8: Act, trimask: torch.Tensor, B: int, S: int, H: int, W: int) -> dict:
         """Runs (and records) the whole VMN forward on preprocessed input.  trimask fp32 [B*S,H,W]."""

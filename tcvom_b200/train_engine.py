@@ -61,6 +61,7 @@ class TrainEngine(GcaVmnEngine):
         self._arena_off = 0
         self._arena_need = 0
         self._nbt: List = []
+        self.use_head32 = os.environ.get("TCV_HEAD32", "1") == "1"
         self.use_tc_wgrad = os.environ.get("TCV_TC_WGRAD", "1") != "0"
         # "2": the NHWC-direct kernel (MN-major operands, no channel-major copies); "1": the split-K GEMM over copies
         self.wgrad_nhwc = os.environ.get("TCV_TC_WGRAD", "2") == "2"
@@ -95,6 +96,12 @@ class TrainEngine(GcaVmnEngine):
                 b = named.get(p + ".bias")
                 if b is not None:
                     self.bias[p] = b
+                if self.use_head32 and t.shape[0] == 1 and t.shape[1] % 32 == 0 and t.shape[2] == 3:
+                    # alpha head as a zero-padded 32-channel conv: its forward and both gradients run on tcgen05
+                    self._pack_head32(L, st, p, t, b)
+                    hk = p + self.HEAD32
+                    self.w[hk].update(param=name, sn=False, bias_param=p + ".bias")
+                    self.w[p].pop("param")
         for p, ent in list(self.w.items()):
             if p.endswith("#T"):
                 continue
@@ -755,7 +762,13 @@ class TrainEngine(GcaVmnEngine):
         t = self.bn_op(self.deconv_op(t, "decoder.conv1"), "decoder.bn1", act=ACT_LEAKY02, snkey="decoder.conv1",
                        res2=fea[0])
         self.head_in = t
-        self.head = self.conv_op(t, "decoder.conv2", bias=True, act=ACT_TANH01, f32_out=pred)
+        hk = "decoder.conv2" + self.HEAD32
+        if self.use_head32 and hk in self.w:
+            self.head = self.conv_op(t, hk, bias=True)
+            ha = self.head.a
+            self._call("tcv_head_tanh01", ha.ptr, ha.plane, ha.n * ha.h * ha.w, ha.c, pred.data_ptr())
+        else:
+            self.head = self.conv_op(t, "decoder.conv2", bias=True, act=ACT_TANH01, f32_out=pred)
         self.pred = pred
         if self._nbt:                                   # num_batches_tracked += calls, one fused update for all layers
             torch._foreach_add_([t_ for t_, _ in self._nbt], [int(g_) for _, g_ in self._nbt])
@@ -766,9 +779,13 @@ class TrainEngine(GcaVmnEngine):
         """Runs the tape in reverse from dL/dpred (fp32 [B,ncen,1,H,W]) and the TAM-logit gradients of L_af."""
         n = dpred.numel()
         hin = self.head_in.a
-        dz8 = self._act(hin.n, hin.h, hin.w, 8)
-        self._call("tcv_tanh01_bwd", self.pred.data_ptr(), dpred.data_ptr(), n, dz8.ptr)
-        self.head.g, self.head.g_owned = dz8, True
+        if self.head.a is not None:              # padded 32-channel head
+            dz = self._act(hin.n, hin.h, hin.w, self.head.a.c)
+            self._call("tcv_head_tanh01_bwd", self.pred.data_ptr(), dpred.data_ptr(), n, dz.c, dz.ptr)
+        else:
+            dz = self._act(hin.n, hin.h, hin.w, 8)
+            self._call("tcv_tanh01_bwd", self.pred.data_ptr(), dpred.data_ptr(), n, dz.ptr)
+        self.head.g, self.head.g_owned = dz, True
         self.datt["b"], self.datt["f"] = dattb, dattf
         for fn in reversed(self.tape):
             fn()
@@ -787,7 +804,7 @@ class TrainEngine(GcaVmnEngine):
                     out.append(torch.zeros_like(prm)); continue
                 grad = torch.empty_like(prm)
                 sn = self.sn.get(p) if ent.get("sn") else None
-                cout, cin = ent["cout"], ent["cin_real"]
+                cout, cin = ent.get("cout_real", ent["cout"]), ent["cin_real"]
                 self._call("tcv_weight_grad_unpack", dw.data_ptr(), cout, cin, ent["k"], ent["k"],
                            1 if ent["transposed"] else 0, ent["cin"], dw.shape[2],
                            sn["u_hist"].data_ptr() if sn else None, sn["v_hist"].data_ptr() if sn else None,
@@ -795,7 +812,10 @@ class TrainEngine(GcaVmnEngine):
                            sn["calls"] if sn else 0, grad.data_ptr())
                 out.append(grad)
             elif name.endswith(".bias") and name[: -len(".bias")] in self.bias:
-                db = self.dbias.get(name[: -len(".bias")])
+                bkey = name[: -len(".bias")]
+                if self.use_head32 and bkey + self.HEAD32 in self.w:
+                    bkey = bkey + self.HEAD32
+                db = self.dbias.get(bkey)
                 out.append(db[: prm.numel()].clone() if db is not None else torch.zeros_like(prm))
             elif name.endswith((".weight", ".bias")) and name.rsplit(".", 1)[0] in self.dbn:
                 dg, db = self.dbn[name.rsplit(".", 1)[0]]
