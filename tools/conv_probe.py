@@ -13,7 +13,7 @@ dev = "cuda"
 st = torch.cuda.current_stream().cuda_stream
 
 
-def run(cin, cout, h, w, n, res=True):
+def run(cin, cout, h, w, n, res=True, sweep=None):
     torch.manual_seed(1)
     x = split(torch.randn(n, h, w, cin, device=dev))
     taps = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
@@ -37,9 +37,9 @@ def run(cin, cout, h, w, n, res=True):
         d.res1 = res1.data_ptr()
     d.act = 1
     flops = 2 * n * h * w * 9 * cin * cout
-    for ver in (3, 2):
+    for ver in ((2,) if sweep else (3, 2)):
         L.tcv_set_conv_tc_version(ver)
-        for flags in ((0, 64, 1) if ver == 3 else (0,)):
+        for flags in (sweep if sweep else ((0, 64, 1) if ver == 3 else (0,))):
             L.tcv_set_debug_flags(flags)
             for _ in range(3):
                 _cabi.check(L.tcv_conv2d(C.byref(d), st), "conv")
@@ -53,5 +53,10 @@ def run(cin, cout, h, w, n, res=True):
     L.tcv_set_debug_flags(0); L.tcv_set_conv_tc_version(2)
 
 
-run(32, 32, 1088, 1920, 3, res=False)
-run(32, 32, 544, 960, 3)
+if len(sys.argv) >= 6:      # python tools/conv_probe.py cin cout h w n : conv_tc2 under its measurement switches
+    cin, cout, h, w, n = map(int, sys.argv[1:6])
+    # 1 no MMA, 2 no epilogue memory ops, 4 activations loaded once, 8 weights loaded once
+    run(cin, cout, h, w, n, sweep=(0, 1, 2, 3, 4, 8, 12, 15))
+else:
+    run(32, 32, 1088, 1920, 3, res=False)
+    run(32, 32, 544, 960, 3)
