@@ -90,6 +90,9 @@ class _TrainStepFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gl, *unused):
+        if ctx.st is None:
+            raise RuntimeError("tcvom_b200: the native training step was already back-propagated once "
+                               "(retain_graph / double backward are not supported)")
         grads = ctx.wrapper._train_backward(ctx.st, gl)
         ctx.st = None
         return (None, None, None, None) + tuple(grads)
@@ -110,6 +113,9 @@ class _VMNTrainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dpred, dattb, dattf, _):
         eng = ctx.eng
+        if eng is None or not eng.tape:
+            raise RuntimeError("tcvom_b200: the native VMN step was already back-propagated once "
+                               "(retain_graph / double backward are not supported)")
         z = lambda g, like: g.contiguous().float() if g is not None else torch.zeros_like(like)
         eng.train_backward(z(dpred, eng.pred), dattb.contiguous().float() if dattb is not None else None,
                            dattf.contiguous().float() if dattf is not None else None)

@@ -417,6 +417,8 @@ class TrainEngine(GcaVmnEngine):
         self._call("tcv_bn_finalize", sums.data_ptr(), count, count * unbias_mul, groups, c, BN_EPS, BN_MOMENTUM,
                    mean.data_ptr(), invstd.data_ptr(), self.named[bnkey + ".running_mean"].data_ptr(),
                    self.named[bnkey + ".running_var"].data_ptr())
+        for sfx in (".running_mean", ".running_var"):       # written by the kernel: tell torch (version counters)
+            torch.autograd.graph.increment_version(self.named[bnkey + sfx])
         nbt = self.named.get(bnkey + ".num_batches_tracked")
         if nbt is not None:
             self._nbt.append((nbt, groups))

@@ -172,6 +172,8 @@ EDGE_CASES = {
     "no_unknown_sample": dict(B=2, S=5, blank=1, cls="FullModel_VMD"),
     # the plain FullModel wrapper (3 losses, no attention loss)
     "fullmodel": dict(B=1, S=5, blank=None, cls="FullModel"),
+    # non-square frame: partial pixel tiles in every tensor-core kernel (OS16 grid 4 x 6, OS32 2 x 3)
+    "rect64x96": dict(B=1, S=3, blank=None, cls="FullModel_VMD", hw=(64, 96)),
 }
 
 
@@ -182,7 +184,8 @@ def test_train_step_edge_cases_match_oracle(case):
     from helpers import fixture_sd
     from tcvom_b200 import synthetic
     c = EDGE_CASES[case]
-    a, fg, bg = synthetic.make_train_batch(c["B"], c["S"], 64, 64, seed=77)
+    h, w = c.get("hw", (64, 64))
+    a, fg, bg = synthetic.make_train_batch(c["B"], c["S"], h, w, seed=77)
     if c["blank"] is not None:
         a[c["blank"]] = 255                       # fully opaque sample: no 0 < alpha < 1 pixel in any frame
     a, fg, bg = (torch.from_numpy(t).float().cuda() for t in (a, fg, bg))
