@@ -575,6 +575,10 @@ class FullModel_VMD(nn.Module):
         names = [n for n, t in named.items() if isinstance(t, nn.Parameter) and t.requires_grad]
         self.__dict__["_train_param_names"] = names
         params = [named[n] for n in names]
+        if torch.is_grad_enabled() and not names:
+            # e.g. an nn.DataParallel replica (its parameters are plain tensors): gradients could not flow back
+            raise RuntimeError("tcvom_b200: no trainable nn.Parameter reachable from this module -- training under "
+                               "nn.DataParallel is not supported, use DistributedDataParallel (train_ddp.py:275-280)")
         if torch.is_grad_enabled():
             res = _TrainStepFn.apply(self, a, fg, bg, *params)
             L, vis = res[0], list(res[1:])

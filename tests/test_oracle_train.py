@@ -56,3 +56,21 @@ def test_oracle_train_step_matches_reference():
         # two fp32 CPU implementations of this (chaotic, random-weight) fixture differ by up to 5e-3 here
         assert err < 2e-2, (n, err)
     print("worst relative gradient-sample error", worst)
+
+
+def test_rank_rows_emulation_is_consistent_with_the_whole_batch():
+    """One 'rank' covering the whole batch must reproduce the ordinary losses; two ranks give per-rank losses whose
+    alpha outputs concatenate to the whole-batch tensor (SyncBatchNorm view: the network still sees both samples)."""
+    g = golden("train_step_s5.npz")
+    a, fg, bg = (torch.from_numpy(g[k]).float() for k in ("a", "fg", "bg"))
+    B = a.shape[0]
+    sd = {k: v.clone() for k, v in fixture_sd().items()}
+    whole = O.full_vmd_forward(sd, a, fg, bg, [3] * B, train=True)
+    sd = {k: v.clone() for k, v in fixture_sd().items()}
+    one = O.full_vmd_forward(sd, a, fg, bg, [3] * B, train=True, rank_rows=[slice(0, B)])
+    for i in (0, 3, 4):
+        assert abs(float(whole[i]) - float(one[i][0])) < 1e-6
+    sd = {k: v.clone() for k, v in fixture_sd().items()}
+    two = O.full_vmd_forward(sd, a, fg, bg, [3] * B, train=True, rank_rows=[slice(r, r + 1) for r in range(B)])
+    assert len(two[0]) == B
+    assert float((two[7].detach() - whole[7].detach()).abs().max()) < 1e-6
