@@ -138,3 +138,30 @@ def fixture_state_dict(shapes: Dict[str, tuple], seed: int = 0, small_npz: str =
         else:
             out[k] = torch.from_numpy(seeded_tensor(k, tuple(shp), seed))
     return out
+
+
+# ----------------------------------------------------------------------------- FBA fixture weights
+def seeded_tensor_fba(key: str, shape, shapes: Dict[str, tuple], seed: int = 0) -> np.ndarray:
+    """Fixture value of one ``vmn_fba`` state_dict entry (203 keys, no calibrated part: GroupNorm has no running
+    statistics).  Plain random init saturates alpha = clamp(out[:, 0], 0, 1) at 0 for 99.7 % of the pixels
+    (measured on the reference), which would make an alpha parity test vacuous: the last 1x1 conv's alpha row is
+    rescaled and biased so that the unknown band is spread over (0, 1)."""
+    if len(shape) == 4:
+        w = _xavier(key, shape, seed)
+        if key.endswith("conv_up4.4.weight"):
+            w[0] *= 0.6
+        return w
+    if key.endswith(".weight"):                                # GroupNorm gamma
+        return _rng(key, seed).uniform(0.8, 1.2, size=shape).astype(np.float32)
+    sibling = shapes.get(key[: -len(".bias")] + ".weight")
+    if sibling is not None and len(sibling) == 1:              # GroupNorm beta
+        return _rng(key, seed).uniform(-0.1, 0.1, size=shape).astype(np.float32)
+    b = _rng(key, seed).uniform(-0.05, 0.05, size=shape).astype(np.float32)   # conv bias
+    if key.endswith("conv_up4.4.bias"):
+        b[0] = 0.5
+    return b
+
+
+def fixture_state_dict_fba(shapes: Dict[str, tuple], seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Fixture checkpoint of ``get_VMN_models('vmn_fba')`` (shapes: state_dict key -> shape)."""
+    return {k: torch.from_numpy(seeded_tensor_fba(k, tuple(s), shapes, seed)) for k, s in shapes.items()}

@@ -36,3 +36,16 @@ def fixture_sd():
 
 def op_inputs(tag, shape, seed=11):
     return synthetic._rng(tag, seed).standard_normal(size=shape).astype(np.float32)
+
+
+def key_table_fba():
+    with open(os.path.join(GOLDEN, "vmn_fba_keys.json")) as f:
+        return json.load(f)
+
+
+def fixture_sd_fba():
+    """The seeded ``vmn_fba`` fixture checkpoint (203 keys, CPU fp32)."""
+    if "fba" not in _SD:
+        shapes = {k: tuple(s) for k, s in key_table_fba()["state_dict"]}
+        _SD["fba"] = synthetic.fixture_state_dict_fba(shapes, 0)
+    return _SD["fba"]
