@@ -45,6 +45,7 @@ typedef void* tcv_stream_t; /* cudaStream_t */
 #define TCV_ACT_RELU 1
 #define TCV_ACT_LEAKY02 2
 #define TCV_ACT_TANH01 3 /* (tanh(x)+1)/2 -- VMN_GCA.py:47 */
+#define TCV_ACT_LEAKY001 4 /* nn.LeakyReLU() default slope 0.01 -- FBA/models.py:266-300 */
 
 #define TCV_PAD_ZERO 0
 #define TCV_PAD_REFLECT 1
@@ -408,6 +409,91 @@ int tcv_losses_vmd_bwd(const float* pred, const float* trimask, const float* gts
                        const float* gl, int batch, int frames_per_sample, int h, int w, int window, float att_thres,
                        float label_smooth, float att_multiplier, float* dpred, float* dattb, float* dattf,
                        tcv_stream_t stream);
+
+
+/* =====================================================================================================
+ * FBA base network (config 5 "FBA+TAM forward").  The convolutions, the TAM and the
+ * eval pre-processing reuse the entry points above; what FBA adds is below.
+ *
+ * Reference semantics replaced:
+ *   tcv_ws_pack               models/FBA/layers_WS.py:13-23    Conv2d.forward (weight standardisation)
+ *   tcv_gn_*                  models/FBA/layers_WS.py:26-27, models/FBA/models.py:239-243   nn.GroupNorm(32, C)
+ *   tcv_maxpool3s2            models/FBA/resnet_GN_WS.py:102   nn.MaxPool2d(3, 2, 1) (indices unused by the decoder)
+ *   tcv_adaptive_avgpool      models/FBA/models.py:264         nn.AdaptiveAvgPool2d(scale) of the pyramid pooling
+ *   tcv_bilinear              models/VMN/VMN_FBA.py:27-30,36,41,46   F.interpolate(bilinear, align_corners=False)
+ *   tcv_copy_channels         torch.cat along channels          VMN_FBA.py:31,38,43
+ *   tcv_fba_encode_inputs     models/model.py:366-368,379-386  EvalModel.preprocess, TRIMAP_CHANNEL == 8
+ *   tcv_fba_edt_cols/rows     utils/utils.py:12-39             dt() + trimap_transform (exact Euclidean transform)
+ *   tcv_fba_cat_inputs        models/VMN/VMN_FBA.py:47         cat(x, conv_out[-6][:, :3], img, two_chan_trimap)
+ *   tcv_fba_fusion            models/VMN/VMN_FBA.py:51-57, models/FBA/models.py:246-255
+ *   tcv_postprocess_eval_fba  models/model.py:426-446          EvalModel.forward tail for method 'fba'
+ * All activations are split-bf16 NHWC; channel counts, channel offsets and row strides are multiples of 8.
+ * ===================================================================================================== */
+
+/* w fp32 [cout,cin,kh,kw] (torch layout) -> packed fp32 [kh*kw][cin_pad][cout_pad] (tcv_conv2d's weight layout; rows
+ * ci >= cin and columns co >= cout are zero).  standardize != 0: per output channel (w - mean) / (sqrt(var + 1e-12)
+ * + 1e-5) with the unbiased variance over cin*kh*kw elements (layers_WS.py:16-21). */
+int tcv_ws_pack(const float* w, int cout, int cin, int kh, int kw, int standardize, int cin_pad, int cout_pad,
+                float* packed, tcv_stream_t stream);
+
+/* GroupNorm over x split-bf16 [n][pixels][c] (dense), c/8 a power of two <= 256:
+ *  stats:    sums[n][c][2] (double, zeroed here) = per (image, channel) sum and sum of squares
+ *  finalize: per (image, group of c/groups channels) mean / biased variance -> per (image, channel)
+ *            scale = gamma*invstd, shift = beta - mean*scale  (fp32 [n][c] each)
+ *  apply:    y[n][pixel][y_off + ch] (row stride y_c elements, hi/lo planes y_plane apart; 0: n*pixels*y_c)
+ *            = act( x*scale + shift + res ), res split-bf16 [n][pixels][c] or NULL */
+int tcv_gn_stats(const void* x, long long x_plane, int n, long long pixels, int c, double* sums, tcv_stream_t stream);
+int tcv_gn_finalize(const double* sums, int n, long long pixels, int c, int groups, const float* gamma,
+                    const float* beta, float eps, float* scale, float* shift, tcv_stream_t stream);
+int tcv_gn_apply(const void* x, long long x_plane, int n, long long pixels, int c, const float* scale,
+                 const float* shift, const void* res, long long res_plane, int act, void* y, long long y_plane,
+                 int y_c, int y_off, tcv_stream_t stream);
+
+/* y [n, (h-1)/2+1, (w-1)/2+1, c] = 3x3 / stride 2 / pad 1 max pooling of x [n,h,w,c] */
+int tcv_maxpool3s2(const void* x, int n, int h, int w, int c, void* y, tcv_stream_t stream);
+
+/* y dense [n,s,s,c] = adaptive average pooling (bins [floor(i*h/s), ceil((i+1)*h/s))) of channels
+ * [x_off, x_off+c) of x [n,h,w,x_c]; c % 64 == 0 */
+int tcv_adaptive_avgpool(const void* x, long long x_plane, int n, int h, int w, int c, int x_c, int x_off, int s,
+                         void* y, tcv_stream_t stream);
+
+/* y[n,oh,ow, y_off..y_off+c) (row stride y_c) = bilinear resize (align_corners=False, torch semantics) of x dense
+ * [n,ih,iw,c] */
+int tcv_bilinear(const void* x, int n, int ih, int iw, int c, void* y, long long y_plane, int oh, int ow, int y_c,
+                 int y_off, tcv_stream_t stream);
+
+/* y[p][y_off + ch] = x[p][x_off + ch], ch < c, p < pixels (rows of x_c / y_c elements; planes 0: pixels*row) */
+int tcv_copy_channels(const void* x, long long x_plane, int x_c, int x_off, void* y, long long y_plane, int y_c,
+                      int y_off, int c, long long pixels, tcv_stream_t stream);
+
+/* EvalModel.preprocess for 'fba'.  imgs [F,3,H,W] BGR 0..255 and tris [F,1,H,W] (fp32, or uint8 when is_u8) ->
+ * x16 split-bf16 [F,H,W,16]: ch 0..2 normalised RGB, 9 = (tri*1/255 == 0), 10 = (tri*1/255 == 1), 11..13 RGB/255
+ * (the decoder's `img` extra; the stem's weights for channels 11..15 are zero), 14..15 zero.  Channels 3..8 are
+ * written by tcv_fba_edt_rows. */
+int tcv_fba_encode_inputs(const void* imgs, const void* tris, int is_u8, int frames, int h, int w, void* x16,
+                          tcv_stream_t stream);
+/* exact squared Euclidean distance to the nearest seed pixel of channel 9 (k = 0) / 10 (k = 1) of x16, separable:
+ *  cols: g int32 [F][2][H][W] = vertical distance to the nearest seed of the same column (1 << 20: none)
+ *  rows: d2 = min_x' (x-x')^2 + g[y][x']^2 ; x16 channel 3+3k+j = exp(-(sqrt(d2))^2 / (2*(f_j*320)^2)),
+ *        f = (0.02, 0.08, 0.16) (utils.py:34-37); 0 when the image holds no seed of that kind */
+int tcv_fba_edt_cols(const void* x16, int frames, int h, int w, int* g, tcv_stream_t stream);
+int tcv_fba_edt_rows(const int* g, int frames, int h, int w, void* x16, tcv_stream_t stream);
+
+/* channels [y_off, y_off+8) of y = x16 channels (0,1,2, 11,12,13, 9,10); [y_off+8, y_off+32) = 0.
+ * x16_plane: elements between the hi and lo plane of x16 (0: pixels*16) */
+int tcv_fba_cat_inputs(const void* x16, long long x16_plane, long long pixels, void* y, long long y_plane, int y_c,
+                       int y_off, tcv_stream_t stream);
+
+/* o8 split-bf16 [n,H,W,8] (7 used) + x16 of the same frames (first image at x16, images x16_img_stride elements
+ * apart) -> pred fp32 [n,7,H,W]: alpha = clamp(o0,0,1), F = sigmoid(o1..3), B = sigmoid(o4..6), then fba_fusion */
+int tcv_fba_fusion(const void* o8, const void* x16, long long x16_plane, long long x16_img_stride, int n, int h, int w,
+                   float* pred, tcv_stream_t stream);
+
+/* pred fp32 [B*(S-2),7,H,W] (inner frames) -> alphas [B,S,1,H,W], Fs, Bs [B,S,3,H,W]: where(trimask, pred, tri/255
+ * resp. RGB/255), zeros for the first / last frame of every sample.  imgs/tris as in tcv_fba_encode_inputs. */
+int tcv_postprocess_eval_fba(const float* pred, const void* imgs, const void* tris, int is_u8, const float* trimask,
+                             int batch, int frames, int h, int w, float* alphas, float* Fs, float* Bs,
+                             tcv_stream_t stream);
 
 #ifdef __cplusplus
 }

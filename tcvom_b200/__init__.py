@@ -4,7 +4,7 @@ Public surface mirrors the reference's operator/plugin interface for this path:
 ``get_VMN_models``, ``VMN``, ``FeatureAggregationModule``, ``GuidedCxtAtten``, ``EvalModel``.
 """
 from .model import (EvalModel, FeatureAggregationModule, FullModel, FullModel_VMD, GuidedCxtAtten, VMN,  # noqa: F401
-                    get_VMN_models)
+                    VMN_FBA, get_VMN_models)
 
 __version__ = "0.1.0"
 
@@ -12,11 +12,12 @@ __version__ = "0.1.0"
 def install(native_wrapper: bool = True):
     """Hooks this package into an importable reference checkout (``models`` on ``sys.path``).
 
-    * ``models.VMN.get_VMN_models('vmn_gca', ...)`` -> :func:`tcvom_b200.get_VMN_models`
+    * ``models.VMN.get_VMN_models('vmn_gca' | 'vmn_fba', ...)`` -> :func:`tcvom_b200.get_VMN_models`
       (the plugin seam ``models/model.py:39-44`` calls at construction time); other archs are
       forwarded to the reference untouched;
     * with ``native_wrapper`` also ``models.model.EvalModel`` -> :class:`tcvom_b200.EvalModel`
-      when it is built for ``vmn_gca`` (fused preprocess / postprocess kernels, CUDA-graph replay).
+      when it is built for ``vmn_gca`` / ``vmn_fba`` (fused preprocess / postprocess kernels, CUDA-graph
+      replay; for ``vmn_fba`` also the trimap distance transforms on the GPU instead of ``cv2``).
 
     Call it before the reference script imports ``models.model``."""
     import importlib
@@ -34,7 +35,7 @@ def install(native_wrapper: bool = True):
     orig_factory = ref_vmn.get_VMN_models
 
     def factory(arch, *args, **kwargs):
-        if arch == "vmn_gca":
+        if arch in ("vmn_gca", "vmn_fba"):
             return get_VMN_models(arch, *args, **kwargs)
         return orig_factory(arch, *args, **kwargs)
 
@@ -48,7 +49,7 @@ def install(native_wrapper: bool = True):
             """EvalModel('vmn_gca', ...) -> native wrapper; anything else -> reference class."""
 
             def __new__(cls, model, *args, **kwargs):
-                if model == "vmn_gca":
+                if model in ("vmn_gca", "vmn_fba"):
                     return EvalModel(model, *args, **kwargs)
                 return orig_eval(model, *args, **kwargs)
 

@@ -13,7 +13,7 @@ import threading
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtcvom_b200.so")
 
-ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_TANH01 = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_TANH01, ACT_LEAKY001 = 0, 1, 2, 3, 4
 PAD_ZERO, PAD_REFLECT = 0, 1
 MAX_TAPS = 16
 
@@ -149,6 +149,26 @@ SIGNATURES = {
     "tcv_tam_attend_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int,
                                    c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tcv_losses_vmd_bwd": (c_int, [c_void_p] * 9 + [c_int] * 5 + [c_float] * 3 + [c_void_p] * 4),
+    # ---- FBA base network
+    "tcv_ws_pack": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_gn_stats": (c_int, [c_void_p, c_ll, c_int, c_ll, c_int, c_void_p, c_void_p]),
+    "tcv_gn_finalize": (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                                c_void_p]),
+    "tcv_gn_apply": (c_int, [c_void_p, c_ll, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p,
+                             c_ll, c_int, c_int, c_void_p]),
+    "tcv_maxpool3s2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_adaptive_avgpool": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                     c_void_p]),
+    "tcv_bilinear": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_int,
+                             c_void_p]),
+    "tcv_copy_channels": (c_int, [c_void_p, c_ll, c_int, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_ll, c_void_p]),
+    "tcv_fba_encode_inputs": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_fba_edt_cols": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_fba_edt_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_fba_cat_inputs": (c_int, [c_void_p, c_ll, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p]),
+    "tcv_fba_fusion": (c_int, [c_void_p, c_void_p, c_ll, c_ll, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_postprocess_eval_fba": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                         c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -12,7 +12,7 @@ pids=()
 for s in $SRCS; do
   o=$OUT/${s%.cu}.o
   OBJS="$OBJS $o"
-  if [ ! -f $o ] || [ $s -nt $o ] || [ common.cuh -nt $o ] || [ tc_common.cuh -nt $o ] || [ tc_epilogue.cuh -nt $o ] || [ ../../include/tcvom_b200.h -nt $o ]; then
+  if [ ! -f $o ] || [ $s -nt $o ] || [ common.cuh -nt $o ] || [ tc_common.cuh -nt $o ] || [ tc_epilogue.cuh -nt $o ] || [ fba_body.h -nt $o ] || [ ../../include/tcvom_b200.h -nt $o ]; then
     $NVCC $FLAGS ${EXTRA_FLAGS} -c $s -o $o &
     pids+=($!)
   fi

@@ -87,6 +87,9 @@ __device__ __forceinline__ void apply_act_n(float* f, int act) {
   } else if (act == TCV_ACT_TANH01) {
 #pragma unroll
     for (int j = 0; j < N; ++j) f[j] = (tanhf(f[j]) + 1.0f) * 0.5f;
+  } else if (act == TCV_ACT_LEAKY001) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) f[j] = f[j] > 0.f ? f[j] : 0.01f * f[j];
   }
 }
 
@@ -129,6 +132,7 @@ __device__ __forceinline__ float apply_act(float t, int act) {
     case TCV_ACT_RELU: return fmaxf(t, 0.f);
     case TCV_ACT_LEAKY02: return t > 0.f ? t : 0.2f * t;
     case TCV_ACT_TANH01: return (tanhf(t) + 1.0f) * 0.5f;
+    case TCV_ACT_LEAKY001: return t > 0.f ? t : 0.01f * t;
     default: return t;
   }
 }

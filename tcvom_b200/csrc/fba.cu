@@ -1,0 +1,292 @@
+// FBA base-network kernels: weight standardisation, GroupNorm, pooling, bilinear
+// resize, channel concatenation, the distance-transform trimap encoding, the fusion head and the EvalModel tail.
+// Everything here is HBM-bound byte shuffling around the tcgen05 convolutions (tcv_conv2d): one work item per
+// 16-byte channel vector (coalesced NHWC access), no shared-memory staging needed except for the reductions.
+// The per-work-item bodies live in fba_body.h so that the CPU test-suite can execute the same index arithmetic.
+#include "common.cuh"
+#include "fba_body.h"
+
+namespace tcv {
+
+using namespace tcv_fba;
+
+template <typename P, void (*BODY)(ll, const P&)>
+__global__ void __launch_bounds__(256) body_kernel(const P p, const ll total) {
+  const ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) BODY(i, p);
+}
+
+template <typename P, void (*BODY)(ll, const P&)>
+static int launch_body(const P& p, ll total, cudaStream_t st, const char* what) {
+  if (total <= 0) return TCV_OK;
+  const ll blocks = (total + 255) / 256;
+  if (blocks > 0x7fffffffLL) return fail(TCV_ERR_INVALID, "%s: too many work items", what);
+  body_kernel<P, BODY><<<(unsigned)blocks, 256, 0, st>>>(p, total);
+  return launched(what);
+}
+
+static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// ---------------------------------------------------------------------------------- weight standardisation + packing
+// one block per output channel (rows co >= cout write zeros)
+__global__ void __launch_bounds__(256) ws_pack_kernel(const float* __restrict__ w, int cout, int cin, int taps,
+                                                      int standardize, int cin_pad, int cout_pad,
+                                                      float* __restrict__ packed) {
+  const int co = blockIdx.x;
+  const int cnt = cin * taps;
+  __shared__ double red[256];
+  __shared__ double s_mean, s_inv;
+  double mean = 0.0, inv = 1.0;
+  if (co < cout && standardize) {
+    const float* row = w + (ll)co * cnt;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < cnt; i += 256) s += row[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) s_mean = red[0] / cnt;
+    __syncthreads();
+    mean = s_mean;
+    double ss = 0.0;
+    for (int i = threadIdx.x; i < cnt; i += 256) {
+      const double d = (double)row[i] - mean;
+      ss += d * d;
+    }
+    red[threadIdx.x] = ss;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    // torch.var: unbiased (cnt - 1); std = sqrt(var + 1e-12) + 1e-5   (layers_WS.py:19-20)
+    if (threadIdx.x == 0) s_inv = 1.0 / (sqrt(red[0] / (cnt > 1 ? cnt - 1 : 1) + 1e-12) + 1e-5);
+    __syncthreads();
+    inv = s_inv;
+  }
+  // packed[t][ci][co] = w[co][ci][t]
+  for (int i = threadIdx.x; i < cin_pad * taps; i += 256) {
+    const int ci = i / taps, t = i - ci * taps;
+    float v = 0.f;
+    if (co < cout && ci < cin) v = (float)(((double)w[((ll)co * cin + ci) * taps + t] - mean) * inv);
+    packed[((ll)t * cin_pad + ci) * cout_pad + co] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------- GroupNorm statistics
+// grid (pixel chunks, images); 256 threads = (256/cv) pixel lanes x cv channel vectors, cv = c/8 <= 256
+__global__ void __launch_bounds__(256) gn_stats_kernel(const uint16_t* __restrict__ x, ll x_plane, ll pixels, int c,
+                                                       int chunk, double* __restrict__ sums) {
+  __shared__ double red[256][17];
+  const int cv = c >> 3;
+  const int lanes = 256 / cv;
+  const int vec = threadIdx.x % cv, lane = threadIdx.x / cv;
+  const int img = blockIdx.y;
+  const ll p0 = (ll)blockIdx.x * chunk;
+  ll p1 = p0 + chunk;
+  if (p1 > pixels) p1 = pixels;
+  double s[8], ss[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = ss[k] = 0.0;
+  for (ll px = p0 + lane; px < p1; px += lanes) {
+    float f[8];
+    ld8(x + ((ll)img * pixels + px) * c + vec * 8, x_plane, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s[k] += (double)f[k];
+      ss[k] += (double)f[k] * (double)f[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    red[threadIdx.x][k] = s[k];
+    red[threadIdx.x][8 + k] = ss[k];
+  }
+  __syncthreads();
+  // thread t < cv*16 sums one (vector, slot) column over the pixel lanes
+  for (int t = threadIdx.x; t < cv * 16; t += 256) {
+    const int v = t / 16, slot = t % 16;
+    double a = 0.0;
+    for (int l = 0; l < lanes; ++l) a += red[l * cv + v][slot];
+    const int ch = v * 8 + (slot & 7);
+    atomicAdd(sums + ((ll)img * c + ch) * 2 + (slot >> 3), a);
+  }
+}
+
+// ---------------------------------------------------------------------------------- adaptive average pooling
+// grid (s*s, images, c/64); 256 threads = 32 pixel lanes x 8 channel vectors
+__global__ void __launch_bounds__(256) adaptive_avgpool_kernel(const uint16_t* __restrict__ x, ll x_plane, int n, int h,
+                                                               int w, int c, int x_c, int x_off, int s,
+                                                               uint16_t* __restrict__ y) {
+  __shared__ float red[256][9];
+  const int bi = blockIdx.x / s, bj = blockIdx.x % s;
+  const int img = blockIdx.y;
+  const int vec = threadIdx.x & 7, lane = threadIdx.x >> 3;
+  const int ch = blockIdx.z * 64 + vec * 8;
+  const int y0 = bin_start(bi, h, s), y1 = bin_end(bi, h, s);
+  const int x0 = bin_start(bj, w, s), x1 = bin_end(bj, w, s);
+  const int rw = x1 - x0, cnt = (y1 - y0) * rw;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int i = lane; i < cnt; i += 32) {
+    const int yy = y0 + i / rw, xx = x0 + i % rw;
+    float f[8];
+    ld8(x + (((ll)img * h + yy) * w + xx) * x_c + x_off + ch, x_plane, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += f[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[threadIdx.x][k] = acc[k];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int v = threadIdx.x >> 3, k = threadIdx.x & 7;
+    float a = 0.f;
+    for (int l = 0; l < 32; ++l) a += red[l * 8 + v][k];
+    const ll yplane = (ll)n * s * s * c;
+    st1(y + (((ll)img * s + bi) * s + bj) * c + blockIdx.z * 64 + v * 8 + k, yplane, a / (float)cnt);
+  }
+}
+
+}  // namespace tcv
+
+using namespace tcv;
+using namespace tcv_fba;
+
+#define U16(p) reinterpret_cast<uint16_t*>(p)
+#define CU16(p) reinterpret_cast<const uint16_t*>(p)
+
+extern "C" {
+
+int tcv_ws_pack(const float* w, int cout, int cin, int kh, int kw, int standardize, int cin_pad, int cout_pad,
+                float* packed, tcv_stream_t stream) {
+  TCV_REQUIRE(w && packed, "ws_pack: null pointer");
+  TCV_REQUIRE(cout > 0 && cin > 0 && kh > 0 && kw > 0 && cin_pad >= cin && cout_pad >= cout, "ws_pack: bad dims");
+  ws_pack_kernel<<<cout_pad, 256, 0, S(stream)>>>(w, cout, cin, kh * kw, standardize, cin_pad, cout_pad, packed);
+  return launched("ws_pack_kernel");
+}
+
+int tcv_gn_stats(const void* x, long long x_plane, int n, long long pixels, int c, double* sums, tcv_stream_t stream) {
+  TCV_REQUIRE(x && sums && n > 0 && pixels > 0, "gn_stats: bad arguments");
+  TCV_REQUIRE(c % 8 == 0 && pow2(c / 8) && c / 8 <= 256, "gn_stats: c/8 must be a power of two <= 256 (c=%d)", c);
+  if (x_plane == 0) x_plane = (long long)n * pixels * c;
+  TCV_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)n * c, S(stream)));
+  // ~4 blocks per SM over all images; every block owns one contiguous pixel chunk of one image
+  long long chunks = (148 * 4 + n - 1) / n;
+  const int lanes = 256 / (c / 8);
+  if (chunks * lanes > pixels) chunks = (pixels + lanes - 1) / lanes;
+  if (chunks < 1) chunks = 1;
+  const int chunk = (int)((pixels + chunks - 1) / chunks);
+  dim3 grid((unsigned)((pixels + chunk - 1) / chunk), n);
+  gn_stats_kernel<<<grid, 256, 0, S(stream)>>>(CU16(x), x_plane, pixels, c, chunk, sums);
+  return launched("gn_stats_kernel");
+}
+
+int tcv_gn_finalize(const double* sums, int n, long long pixels, int c, int groups, const float* gamma,
+                    const float* beta, float eps, float* scale, float* shift, tcv_stream_t stream) {
+  TCV_REQUIRE(sums && gamma && beta && scale && shift, "gn_finalize: null pointer");
+  TCV_REQUIRE(n > 0 && pixels > 0 && groups > 0 && c % groups == 0, "gn_finalize: bad dims");
+  GnFinalizeP p{sums, n, c, groups, pixels, gamma, beta, eps, scale, shift};
+  return launch_body<GnFinalizeP, gn_finalize_body>(p, (ll)n * groups, S(stream), "gn_finalize_kernel");
+}
+
+int tcv_gn_apply(const void* x, long long x_plane, int n, long long pixels, int c, const float* scale,
+                 const float* shift, const void* res, long long res_plane, int act, void* y, long long y_plane,
+                 int y_c, int y_off, tcv_stream_t stream) {
+  TCV_REQUIRE(x && scale && shift && y, "gn_apply: null pointer");
+  TCV_REQUIRE(n > 0 && pixels > 0 && c % 8 == 0 && y_c % 8 == 0 && y_off % 8 == 0 && y_off + c <= y_c,
+              "gn_apply: bad dims");
+  TCV_REQUIRE(act >= TCV_ACT_NONE && act <= TCV_ACT_LEAKY001, "gn_apply: unknown activation");
+  if (x_plane == 0) x_plane = (long long)n * pixels * c;
+  if (res && res_plane == 0) res_plane = (long long)n * pixels * c;
+  if (y_plane == 0) y_plane = (long long)n * pixels * y_c;
+  GnApplyP p{CU16(x), x_plane, n, c, pixels, scale, shift, CU16(res), res_plane, act, U16(y), y_plane, y_c, y_off};
+  return launch_body<GnApplyP, gn_apply_body>(p, (ll)n * pixels * (c / 8), S(stream), "gn_apply_kernel");
+}
+
+int tcv_maxpool3s2(const void* x, int n, int h, int w, int c, void* y, tcv_stream_t stream) {
+  TCV_REQUIRE(x && y && n > 0 && h > 0 && w > 0 && c % 8 == 0, "maxpool3s2: bad arguments");
+  PoolP p{CU16(x), n, h, w, c, (h - 1) / 2 + 1, (w - 1) / 2 + 1, U16(y)};
+  return launch_body<PoolP, maxpool3s2_body>(p, (ll)n * p.oh * p.ow * (c / 8), S(stream), "maxpool3s2_kernel");
+}
+
+int tcv_adaptive_avgpool(const void* x, long long x_plane, int n, int h, int w, int c, int x_c, int x_off, int s,
+                         void* y, tcv_stream_t stream) {
+  TCV_REQUIRE(x && y && n > 0 && h > 0 && w > 0 && s > 0, "adaptive_avgpool: bad arguments");
+  TCV_REQUIRE(c % 64 == 0 && x_c % 8 == 0 && x_off % 8 == 0 && x_off + c <= x_c, "adaptive_avgpool: bad channels");
+  if (x_plane == 0) x_plane = (long long)n * h * w * x_c;
+  dim3 grid(s * s, n, c / 64);
+  adaptive_avgpool_kernel<<<grid, 256, 0, S(stream)>>>(CU16(x), x_plane, n, h, w, c, x_c, x_off, s, U16(y));
+  return launched("adaptive_avgpool_kernel");
+}
+
+int tcv_bilinear(const void* x, int n, int ih, int iw, int c, void* y, long long y_plane, int oh, int ow, int y_c,
+                 int y_off, tcv_stream_t stream) {
+  TCV_REQUIRE(x && y && n > 0 && ih > 0 && iw > 0 && oh > 0 && ow > 0, "bilinear: bad arguments");
+  TCV_REQUIRE(c % 8 == 0 && y_c % 8 == 0 && y_off % 8 == 0 && y_off + c <= y_c, "bilinear: bad channels");
+  if (y_plane == 0) y_plane = (long long)n * oh * ow * y_c;
+  BilinearP p{CU16(x), n, ih, iw, c, U16(y), y_plane, oh, ow, y_c, y_off};
+  return launch_body<BilinearP, bilinear_body>(p, (ll)n * oh * ow * (c / 8), S(stream), "bilinear_kernel");
+}
+
+int tcv_copy_channels(const void* x, long long x_plane, int x_c, int x_off, void* y, long long y_plane, int y_c,
+                      int y_off, int c, long long pixels, tcv_stream_t stream) {
+  TCV_REQUIRE(x && y && pixels > 0, "copy_channels: bad arguments");
+  TCV_REQUIRE(c % 8 == 0 && x_c % 8 == 0 && y_c % 8 == 0 && x_off % 8 == 0 && y_off % 8 == 0 && x_off + c <= x_c &&
+                  y_off + c <= y_c, "copy_channels: bad channels");
+  if (x_plane == 0) x_plane = pixels * x_c;
+  if (y_plane == 0) y_plane = pixels * y_c;
+  CopyP p{CU16(x), x_plane, x_c, x_off, U16(y), y_plane, y_c, y_off, c, pixels};
+  return launch_body<CopyP, copy_channels_body>(p, pixels * (c / 8), S(stream), "copy_channels_kernel");
+}
+
+int tcv_fba_encode_inputs(const void* imgs, const void* tris, int is_u8, int frames, int h, int w, void* x16,
+                          tcv_stream_t stream) {
+  TCV_REQUIRE(imgs && tris && x16 && frames > 0 && h > 0 && w > 0, "fba_encode_inputs: bad arguments");
+  EncodeP p{imgs, tris, is_u8, frames, h, w, U16(x16)};
+  return launch_body<EncodeP, fba_encode_body>(p, (ll)frames * h * w, S(stream), "fba_encode_kernel");
+}
+
+int tcv_fba_edt_cols(const void* x16, int frames, int h, int w, int* g, tcv_stream_t stream) {
+  TCV_REQUIRE(x16 && g && frames > 0 && h > 0 && w > 0, "fba_edt_cols: bad arguments");
+  TCV_REQUIRE(h < TCV_EDT_INF && w < TCV_EDT_INF, "fba_edt_cols: image too large");
+  EdtP p{U16(const_cast<void*>(x16)), frames, h, w, g};
+  return launch_body<EdtP, fba_edt_cols_body>(p, (ll)frames * 2 * w, S(stream), "fba_edt_cols_kernel");
+}
+
+int tcv_fba_edt_rows(const int* g, int frames, int h, int w, void* x16, tcv_stream_t stream) {
+  TCV_REQUIRE(x16 && g && frames > 0 && h > 0 && w > 0, "fba_edt_rows: bad arguments");
+  EdtP p{U16(x16), frames, h, w, const_cast<int*>(g)};
+  return launch_body<EdtP, fba_edt_rows_body>(p, (ll)frames * 2 * h * w, S(stream), "fba_edt_rows_kernel");
+}
+
+int tcv_fba_cat_inputs(const void* x16, long long x16_plane, long long pixels, void* y, long long y_plane, int y_c,
+                       int y_off, tcv_stream_t stream) {
+  TCV_REQUIRE(x16 && y && pixels > 0 && y_c % 8 == 0 && y_off % 8 == 0 && y_off + 32 <= y_c,
+              "fba_cat_inputs: bad arguments");
+  if (y_plane == 0) y_plane = pixels * y_c;
+  if (x16_plane == 0) x16_plane = pixels * 16;
+  CatP p{CU16(x16), x16_plane, pixels, U16(y), y_plane, y_c, y_off};
+  return launch_body<CatP, fba_cat_inputs_body>(p, pixels, S(stream), "fba_cat_inputs_kernel");
+}
+
+int tcv_fba_fusion(const void* o8, const void* x16, long long x16_plane, long long x16_img_stride, int n, int h, int w,
+                   float* pred, tcv_stream_t stream) {
+  TCV_REQUIRE(o8 && x16 && pred && n > 0 && h > 0 && w > 0 && x16_plane > 0, "fba_fusion: bad arguments");
+  if (x16_img_stride == 0) x16_img_stride = (long long)h * w * 16;
+  FusionP p{CU16(o8), CU16(x16), x16_plane, x16_img_stride, n, h, w, pred};
+  return launch_body<FusionP, fba_fusion_body>(p, (ll)n * h * w, S(stream), "fba_fusion_kernel");
+}
+
+int tcv_postprocess_eval_fba(const float* pred, const void* imgs, const void* tris, int is_u8, const float* trimask,
+                             int batch, int frames, int h, int w, float* alphas, float* Fs, float* Bs,
+                             tcv_stream_t stream) {
+  TCV_REQUIRE(pred && imgs && tris && trimask && alphas && Fs && Bs, "postprocess_eval_fba: null pointer");
+  TCV_REQUIRE(batch > 0 && frames >= 3 && h > 0 && w > 0, "postprocess_eval_fba: bad dims");
+  PostP p{pred, imgs, tris, is_u8, trimask, batch, frames, h, w, alphas, Fs, Bs};
+  return launch_body<PostP, postprocess_fba_body>(p, (ll)batch * frames * h * w, S(stream), "postprocess_fba_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,467 @@
+// Per-work-item bodies of the FBA-path kernels (fba.cu) as host/device inline functions.
+//
+// One work item = what one CUDA thread does.  fba.cu wraps every body in a __global__ kernel
+// (`i = blockIdx.x * blockDim.x + threadIdx.x; if (i < total) body(i, p)`); the test double of the C ABI under
+// tests/host_emul/ compiles THIS header with g++ and runs `for (i = 0; i < total; ++i) body(i, p)`, so the index
+// arithmetic of these kernels is exercised by the CPU test-suite against the oracle (there is no GPU in the build
+// container).  Only the 16-byte vector load/store differs between the two builds (ld8 / st8 below).
+//
+// Layout: split-bf16 NHWC, hi plane at p, lo plane `plane` elements later, value = hi + lo.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#ifdef __CUDACC__
+#define TCV_HD __host__ __device__ __forceinline__
+#else
+#define TCV_HD static inline
+#endif
+
+namespace tcv_fba {
+
+typedef long long ll;
+
+TCV_HD float bf_to_f(uint16_t b) {
+  const uint32_t u = (uint32_t)b << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+// round to nearest even, the rounding of __float2bfloat16_rn (finite values; NaN stays NaN)
+TCV_HD uint16_t f_to_bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40u);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+TCV_HD float ld1(const uint16_t* p, ll plane) { return bf_to_f(p[0]) + bf_to_f(p[plane]); }
+TCV_HD void st1(uint16_t* p, ll plane, float v) {
+  const uint16_t h = f_to_bf(v);
+  p[0] = h;
+  p[plane] = f_to_bf(v - bf_to_f(h));
+}
+// 8 consecutive channels (16-byte aligned)
+TCV_HD void ld8(const uint16_t* p, ll plane, float* f) {
+#ifdef __CUDA_ARCH__
+  const uint4 a = *reinterpret_cast<const uint4*>(p);
+  const uint4 b = *reinterpret_cast<const uint4*>(p + plane);
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(aw[i] << 16) + __uint_as_float(bw[i] << 16);
+    f[2 * i + 1] = __uint_as_float(aw[i] & 0xffff0000u) + __uint_as_float(bw[i] & 0xffff0000u);
+  }
+#else
+  for (int i = 0; i < 8; ++i) f[i] = ld1(p + i, plane);
+#endif
+}
+TCV_HD void st8(uint16_t* p, ll plane, const float* f) {
+#ifdef __CUDA_ARCH__
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint16_t h0 = f_to_bf(f[2 * i]), h1 = f_to_bf(f[2 * i + 1]);
+    const uint16_t l0 = f_to_bf(f[2 * i] - bf_to_f(h0)), l1 = f_to_bf(f[2 * i + 1] - bf_to_f(h1));
+    h[i] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+    l[i] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(p + plane) = make_uint4(l[0], l[1], l[2], l[3]);
+#else
+  for (int i = 0; i < 8; ++i) st1(p + i, plane, f[i]);
+#endif
+}
+
+TCV_HD float act_fn(float t, int act) {
+  switch (act) {
+    case 1: return t > 0.f ? t : 0.f;                      // TCV_ACT_RELU
+    case 2: return t > 0.f ? t : 0.2f * t;                 // TCV_ACT_LEAKY02
+    case 3: return (tanhf(t) + 1.0f) * 0.5f;               // TCV_ACT_TANH01
+    case 4: return t > 0.f ? t : 0.01f * t;                // TCV_ACT_LEAKY001
+    default: return t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ GroupNorm
+struct GnFinalizeP {
+  const double* sums;  // [n][c][2]
+  int n, c, groups;
+  ll pixels;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  float* scale;  // [n][c]
+  float* shift;
+};
+// work item = (image, group); total = n * groups
+TCV_HD void gn_finalize_body(ll i, const GnFinalizeP& p) {
+  const int img = (int)(i / p.groups), g = (int)(i % p.groups);
+  const int cpg = p.c / p.groups;
+  double s = 0.0, ss = 0.0;
+  for (int k = 0; k < cpg; ++k) {
+    const double* q = p.sums + ((ll)img * p.c + g * cpg + k) * 2;
+    s += q[0];
+    ss += q[1];
+  }
+  const double cnt = (double)cpg * (double)p.pixels;
+  const double mean = s / cnt;
+  double var = ss / cnt - mean * mean;  // biased, as nn.GroupNorm
+  if (var < 0.0) var = 0.0;
+  const double invstd = 1.0 / sqrt(var + (double)p.eps);
+  for (int k = 0; k < cpg; ++k) {
+    const int ch = g * cpg + k;
+    const double sc = (double)p.gamma[ch] * invstd;
+    p.scale[(ll)img * p.c + ch] = (float)sc;
+    p.shift[(ll)img * p.c + ch] = (float)((double)p.beta[ch] - mean * sc);
+  }
+}
+
+struct GnApplyP {
+  const uint16_t* x;
+  ll x_plane;
+  int n, c;
+  ll pixels;
+  const float* scale;
+  const float* shift;
+  const uint16_t* res;
+  ll res_plane;
+  int act;
+  uint16_t* y;
+  ll y_plane;
+  int y_c, y_off;
+};
+// work item = 8 channels of one pixel; total = n * pixels * c / 8
+TCV_HD void gn_apply_body(ll i, const GnApplyP& p) {
+  const int cv = p.c / 8;
+  const ll pix = i / cv;
+  const int ch = (int)(i % cv) * 8;
+  const int img = (int)(pix / p.pixels);
+  float f[8];
+  ld8(p.x + pix * p.c + ch, p.x_plane, f);
+  const float* sc = p.scale + (ll)img * p.c + ch;
+  const float* sh = p.shift + (ll)img * p.c + ch;
+  for (int k = 0; k < 8; ++k) f[k] = f[k] * sc[k] + sh[k];
+  if (p.res) {
+    float r[8];
+    ld8(p.res + pix * p.c + ch, p.res_plane, r);
+    for (int k = 0; k < 8; ++k) f[k] += r[k];
+  }
+  for (int k = 0; k < 8; ++k) f[k] = act_fn(f[k], p.act);
+  st8(p.y + pix * p.y_c + p.y_off + ch, p.y_plane, f);
+}
+
+// ------------------------------------------------------------------------------------------ pooling / resize / copies
+struct PoolP {
+  const uint16_t* x;
+  int n, h, w, c, oh, ow;
+  uint16_t* y;
+};
+// 3x3 / stride 2 / pad 1 max pooling; work item = 8 channels of one output pixel; total = n*oh*ow*c/8
+TCV_HD void maxpool3s2_body(ll i, const PoolP& p) {
+  const int cv = p.c / 8;
+  const int ch = (int)(i % cv) * 8;
+  ll t = i / cv;
+  const int ox = (int)(t % p.ow);
+  t /= p.ow;
+  const int oy = (int)(t % p.oh);
+  const int img = (int)(t / p.oh);
+  const ll xplane = (ll)p.n * p.h * p.w * p.c, yplane = (ll)p.n * p.oh * p.ow * p.c;
+  float m[8];
+  for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int iy = 2 * oy + dy;
+    if (iy < 0 || iy >= p.h) continue;
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int ix = 2 * ox + dx;
+      if (ix < 0 || ix >= p.w) continue;
+      float f[8];
+      ld8(p.x + (((ll)img * p.h + iy) * p.w + ix) * p.c + ch, xplane, f);
+      for (int k = 0; k < 8; ++k) m[k] = f[k] > m[k] ? f[k] : m[k];
+    }
+  }
+  st8(p.y + (((ll)img * p.oh + oy) * p.ow + ox) * p.c + ch, yplane, m);
+}
+
+// bins of nn.AdaptiveAvgPool2d: [floor(i*in/out), ceil((i+1)*in/out))
+TCV_HD int bin_start(int i, int in, int out) { return (int)(((ll)i * in) / out); }
+TCV_HD int bin_end(int i, int in, int out) { return (int)((((ll)i + 1) * in + out - 1) / out); }
+
+struct BilinearP {
+  const uint16_t* x;
+  int n, ih, iw, c;
+  uint16_t* y;
+  ll y_plane;
+  int oh, ow, y_c, y_off;
+};
+// torch's area_pixel_compute_source_index + guard_index_and_lambda (align_corners=False, float32 arithmetic)
+TCV_HD void src_index(int dst, int in, int out, int* i0, int* i1, float* l0, float* l1) {
+  const float scale = (float)in / (float)out;
+  float s = scale * ((float)dst + 0.5f) - 0.5f;
+  if (s < 0.f) s = 0.f;
+  int a = (int)s;
+  if (a > in - 1) a = in - 1;
+  float lam = s - (float)a;
+  lam = lam < 0.f ? 0.f : (lam > 1.f ? 1.f : lam);
+  *i0 = a;
+  *i1 = a + (a < in - 1 ? 1 : 0);
+  *l1 = lam;
+  *l0 = 1.f - lam;
+}
+// work item = 8 channels of one output pixel; total = n*oh*ow*c/8
+TCV_HD void bilinear_body(ll i, const BilinearP& p) {
+  const int cv = p.c / 8;
+  const int ch = (int)(i % cv) * 8;
+  ll t = i / cv;
+  const int ox = (int)(t % p.ow);
+  t /= p.ow;
+  const int oy = (int)(t % p.oh);
+  const int img = (int)(t / p.oh);
+  int y0, y1, x0, x1;
+  float ly0, ly1, lx0, lx1;
+  src_index(oy, p.ih, p.oh, &y0, &y1, &ly0, &ly1);
+  src_index(ox, p.iw, p.ow, &x0, &x1, &lx0, &lx1);
+  const ll xplane = (ll)p.n * p.ih * p.iw * p.c;
+  const uint16_t* b = p.x + (ll)img * p.ih * p.iw * p.c + ch;
+  float a00[8], a01[8], a10[8], a11[8], o[8];
+  ld8(b + ((ll)y0 * p.iw + x0) * p.c, xplane, a00);
+  ld8(b + ((ll)y0 * p.iw + x1) * p.c, xplane, a01);
+  ld8(b + ((ll)y1 * p.iw + x0) * p.c, xplane, a10);
+  ld8(b + ((ll)y1 * p.iw + x1) * p.c, xplane, a11);
+  for (int k = 0; k < 8; ++k)
+    o[k] = ly0 * (lx0 * a00[k] + lx1 * a01[k]) + ly1 * (lx0 * a10[k] + lx1 * a11[k]);
+  st8(p.y + (((ll)img * p.oh + oy) * p.ow + ox) * p.y_c + p.y_off + ch, p.y_plane, o);
+}
+
+struct CopyP {
+  const uint16_t* x;
+  ll x_plane;
+  int x_c, x_off;
+  uint16_t* y;
+  ll y_plane;
+  int y_c, y_off, c;
+  ll pixels;
+};
+// work item = 8 channels of one pixel; total = pixels * c / 8.  Bit copy of both planes.
+TCV_HD void copy_channels_body(ll i, const CopyP& p) {
+  const int cv = p.c / 8;
+  const ll pix = i / cv;
+  const int ch = (int)(i % cv) * 8;
+  const uint16_t* s = p.x + pix * p.x_c + p.x_off + ch;
+  uint16_t* d = p.y + pix * p.y_c + p.y_off + ch;
+#ifdef __CUDA_ARCH__
+  *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(s);
+  *reinterpret_cast<uint4*>(d + p.y_plane) = *reinterpret_cast<const uint4*>(s + p.x_plane);
+#else
+  for (int k = 0; k < 8; ++k) {
+    d[k] = s[k];
+    d[k + p.y_plane] = s[k + p.x_plane];
+  }
+#endif
+}
+
+// ------------------------------------------------------------------------------------------ FBA input encoding
+struct EncodeP {
+  const void* imgs;  // [F,3,H,W] BGR
+  const void* tris;  // [F,1,H,W]
+  int is_u8, frames, h, w;
+  uint16_t* x16;
+};
+TCV_HD float in_val(const void* p, int is_u8, ll idx) {
+  return is_u8 ? (float)reinterpret_cast<const uint8_t*>(p)[idx] : reinterpret_cast<const float*>(p)[idx];
+}
+// work item = one pixel of one frame; total = F*H*W
+TCV_HD void fba_encode_body(ll i, const EncodeP& p) {
+  const ll hw = (ll)p.h * p.w;
+  const int f = (int)(i / hw);
+  const ll pix = i % hw;
+  const ll plane = (ll)p.frames * hw * 16;
+  uint16_t* o = p.x16 + i * 16;
+  const float scale = 1.0f / 255;  // IMG_SCALE (models/model.py:34)
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+  for (int c = 0; c < 3; ++c) {
+    // .flip([2]): output channel c (RGB) reads input channel 2-c (BGR)   (models/model.py:366-367)
+    const float s = in_val(p.imgs, p.is_u8, ((ll)f * 3 + (2 - c)) * hw + pix) * scale;
+    st1(o + c, plane, (s - mean[c]) / stdv[c]);
+    st1(o + 11 + c, plane, s);
+  }
+  const float t = in_val(p.tris, p.is_u8, (ll)f * hw + pix) * scale;
+  st1(o + 9, plane, t == 0.f ? 1.f : 0.f);   // trimap2b (models/model.py:381)
+  st1(o + 10, plane, t == 1.f ? 1.f : 0.f);  // trimap2f (models/model.py:380)
+  st1(o + 14, plane, 0.f);
+  st1(o + 15, plane, 0.f);
+}
+
+#define TCV_EDT_INF (1 << 20)
+struct EdtP {
+  uint16_t* x16;
+  int frames, h, w;
+  int* g;  // [F][2][H][W]
+};
+// work item = one column of one (frame, k); total = F*2*W.  Two sweeps: distance to the nearest seed above, below.
+TCV_HD void fba_edt_cols_body(ll i, const EdtP& p) {
+  const int x = (int)(i % p.w);
+  const int k = (int)((i / p.w) % 2);
+  const int f = (int)(i / (2 * (ll)p.w));
+  const ll hw = (ll)p.h * p.w;
+  const uint16_t* src = p.x16 + (ll)f * hw * 16 + 9 + k;  // hi plane is exact for 0 / 1
+  int* g = p.g + ((ll)f * 2 + k) * hw;
+  int d = TCV_EDT_INF;
+  for (int y = 0; y < p.h; ++y) {
+    const bool seed = bf_to_f(src[((ll)y * p.w + x) * 16]) != 0.f;
+    d = seed ? 0 : (d >= TCV_EDT_INF ? TCV_EDT_INF : d + 1);
+    g[(ll)y * p.w + x] = d;
+  }
+  d = TCV_EDT_INF;
+  for (int y = p.h - 1; y >= 0; --y) {
+    const int cur = g[(ll)y * p.w + x];
+    d = cur == 0 ? 0 : (d >= TCV_EDT_INF ? TCV_EDT_INF : d + 1);
+    if (d < cur) g[(ll)y * p.w + x] = d;
+  }
+}
+// work item = one pixel of one (frame, k); total = F*2*H*W.  Exact lower envelope by outward search:
+// a column x' can only improve the minimum while (x-x')^2 < best.
+TCV_HD void fba_edt_rows_body(ll i, const EdtP& p) {
+  const ll hw = (ll)p.h * p.w;
+  const int x = (int)(i % p.w);
+  const int y = (int)((i / p.w) % p.h);
+  const int k = (int)((i / hw) % 2);
+  const int f = (int)(i / (2 * hw));
+  const int* row = p.g + (((ll)f * 2 + k) * p.h + y) * p.w;
+  const ll inf2 = (ll)TCV_EDT_INF * TCV_EDT_INF;
+  ll best = row[x] >= TCV_EDT_INF ? inf2 : (ll)row[x] * row[x];
+  for (int r = 1; r < p.w; ++r) {
+    if ((ll)r * r >= best) break;
+    if (x - r >= 0) {
+      const int gv = row[x - r];
+      if (gv < TCV_EDT_INF) {
+        const ll v = (ll)r * r + (ll)gv * gv;
+        best = v < best ? v : best;
+      }
+    }
+    if (x + r < p.w) {
+      const int gv = row[x + r];
+      if (gv < TCV_EDT_INF) {
+        const ll v = (ll)r * r + (ll)gv * gv;
+        best = v < best ? v : best;
+      }
+    }
+  }
+  uint16_t* o = p.x16 + ((ll)f * hw + (ll)y * p.w + x) * 16 + 3 + 3 * k;
+  const ll plane = (ll)p.frames * hw * 16;
+  float e[3] = {0.f, 0.f, 0.f};
+  if (best < inf2) {
+    const float d = sqrtf((float)best);  // cv2.distanceTransform(DIST_L2, precise) returns the float32 distance
+    const float m = -(d * d);           // -dt(...)**2   (utils/utils.py:33)
+    // 2*(f*L)^2 with L = 320: 81.92, 1310.72, 5242.88 (utils/utils.py:34-37)
+    e[0] = expf(m / 81.92f);
+    e[1] = expf(m / 1310.72f);
+    e[2] = expf(m / 5242.88f);
+  }
+  for (int j = 0; j < 3; ++j) st1(o + j, plane, e[j]);
+}
+
+struct CatP {
+  const uint16_t* x16;
+  ll x16_plane;
+  ll pixels;
+  uint16_t* y;
+  ll y_plane;
+  int y_c, y_off;
+};
+// work item = one pixel; channels y_off.. = (normalised RGB, RGB/255, trimap2 bg, fg), then 24 zero channels
+TCV_HD void fba_cat_inputs_body(ll i, const CatP& p) {
+  const ll xplane = p.x16_plane;
+  const uint16_t* s = p.x16 + i * 16;
+  const int src[8] = {0, 1, 2, 11, 12, 13, 9, 10};
+  float f[8];
+  for (int k = 0; k < 8; ++k) f[k] = ld1(s + src[k], xplane);
+  uint16_t* d = p.y + i * p.y_c + p.y_off;
+  st8(d, p.y_plane, f);
+  for (int k = 0; k < 8; ++k) f[k] = 0.f;
+  st8(d + 8, p.y_plane, f);
+  st8(d + 16, p.y_plane, f);
+  st8(d + 24, p.y_plane, f);
+}
+
+struct FusionP {
+  const uint16_t* o8;
+  const uint16_t* x16;
+  ll x16_plane, x16_img_stride;
+  int n, h, w;
+  float* pred;  // [n,7,H,W]
+};
+TCV_HD float clamp01(float v) { return v < 0.f ? 0.f : (v > 1.f ? 1.f : v); }
+// work item = one pixel; VMN_FBA.py:51-57 + FBA/models.py:246-255
+TCV_HD void fba_fusion_body(ll i, const FusionP& p) {
+  const ll hw = (ll)p.h * p.w;
+  const int img_i = (int)(i / hw);
+  const ll pix = i % hw;
+  float o[8];
+  ld8(p.o8 + i * 8, (ll)p.n * hw * 8, o);
+  const uint16_t* xs = p.x16 + (ll)img_i * p.x16_img_stride + pix * 16 + 11;
+  float img[3], F[3], B[3];
+  for (int c = 0; c < 3; ++c) {
+    img[c] = ld1(xs + c, p.x16_plane);
+    F[c] = 1.0f / (1.0f + expf(-o[1 + c]));
+    B[c] = 1.0f / (1.0f + expf(-o[4 + c]));
+  }
+  float alpha = clamp01(o[0]);
+  float num = 0.f, den = 0.f;
+  for (int c = 0; c < 3; ++c) {
+    const float Fn = alpha * img[c] + (1.f - alpha * alpha) * F[c] - alpha * (1.f - alpha) * B[c];
+    const float Bn = (1.f - alpha) * img[c] + (2.f * alpha - alpha * alpha) * B[c] - alpha * (1.f - alpha) * Fn;
+    F[c] = clamp01(Fn);
+    B[c] = clamp01(Bn);
+  }
+  for (int c = 0; c < 3; ++c) {
+    num += (img[c] - B[c]) * (F[c] - B[c]);
+    den += (F[c] - B[c]) * (F[c] - B[c]);
+  }
+  const float la = 0.1f;
+  alpha = clamp01((alpha * la + num) / (den + la));
+  float* out = p.pred + (ll)img_i * 7 * hw + pix;
+  out[0] = alpha;
+  for (int c = 0; c < 3; ++c) {
+    out[(1 + c) * hw] = F[c];
+    out[(4 + c) * hw] = B[c];
+  }
+}
+
+struct PostP {
+  const float* pred;  // [B*(S-2),7,H,W]
+  const void* imgs;
+  const void* tris;
+  int is_u8;
+  const float* trimask;  // [B,S,H,W]
+  int batch, frames, h, w;
+  float* alphas;  // [B,S,1,H,W]
+  float* Fs;      // [B,S,3,H,W]
+  float* Bs;
+};
+// work item = one pixel of one frame; total = B*S*H*W   (models/model.py:426-446)
+TCV_HD void postprocess_fba_body(ll i, const PostP& p) {
+  const ll hw = (ll)p.h * p.w;
+  const ll fr = i / hw, pix = i % hw;
+  const int s = (int)(fr % p.frames), b = (int)(fr / p.frames);
+  float a = 0.f, F[3] = {0.f, 0.f, 0.f}, B[3] = {0.f, 0.f, 0.f};
+  if (s > 0 && s < p.frames - 1) {
+    const float scale = 1.0f / 255;
+    const bool m = p.trimask[i] != 0.f;
+    const float* pr = p.pred + ((ll)b * (p.frames - 2) + (s - 1)) * 7 * hw + pix;
+    a = m ? pr[0] : in_val(p.tris, p.is_u8, i) * scale;
+    for (int c = 0; c < 3; ++c) {
+      const float im = in_val(p.imgs, p.is_u8, (fr * 3 + (2 - c)) * hw + pix) * scale;
+      F[c] = m ? pr[(1 + c) * hw] : im;
+      B[c] = m ? pr[(4 + c) * hw] : im;
+    }
+  }
+  p.alphas[i] = a;
+  for (int c = 0; c < 3; ++c) {
+    p.Fs[(fr * 3 + c) * hw + pix] = F[c];
+    p.Bs[(fr * 3 + c) * hw + pix] = B[c];
+  }
+}
+
+}  // namespace tcv_fba

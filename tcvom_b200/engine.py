@@ -253,9 +253,12 @@ class GcaVmnEngine:
             self.plans.popitem(last=False)          # drops the buffers (and CUDA graph) of the oldest shape
 
     # ------------------------------------------------------------------ call recording
+    def _stream_ptr(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
     def _call(self, fn_name: str, *args, meta: Optional[dict] = None):
         fn = getattr(_cabi.lib(), fn_name)
-        st = torch.cuda.current_stream(self.device).cuda_stream
+        st = self._stream_ptr()
         prof = getattr(self, "_prof", None)
         if prof is not None:                      # per-call CUDA-event timing (measurement helper, tools/train_bench.py)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -22,6 +22,8 @@ from torch import nn
 
 from . import _cabi
 from .engine import Act, GcaVmnEngine, Plan, named_tensors
+from .fba_engine import FbaVmnEngine
+from .fba_modules import FBADecoderParams, FBAEncoderParams
 from .train_engine import TrainEngine
 from .modules import GCADecoderParams, GCAEncoderParams, GuidedCxtAttenParams, TAMParams
 
@@ -38,7 +40,7 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
 _ENGINE_LOCK = threading.Lock()
 
 
-def _engine_for(module: nn.Module, window: int) -> GcaVmnEngine:
+def _engine_for(module: nn.Module, window: int, engine_cls=GcaVmnEngine) -> GcaVmnEngine:
     """One engine per (module, device).  nn.DataParallel replicas share the module __dict__ (and so
     this table) but run one thread per device, so a per-device engine is never used concurrently."""
     dev = next(iter(named_tensors(module).values())).device
@@ -50,7 +52,7 @@ def _engine_for(module: nn.Module, window: int) -> GcaVmnEngine:
             table = module.__dict__["_engines"] = {}
         eng = table.get(dev.index)
         if eng is None:
-            eng = table[dev.index] = GcaVmnEngine(window)
+            eng = table[dev.index] = engine_cls(window)
     eng.refresh_weights(module)
     return eng
 
@@ -328,14 +330,81 @@ class VMN(nn.Module):
         return preds, attb, attf, small
 
 
+class _FBADecoder(FBADecoderParams):
+    def train(self, mode=True):
+        super().train(mode)
+        if self.freeze_backbone:                                  # VMN_FBA.py:12-16
+            print('Set FBA decoder feature extraction part in eval() mode.')
+            self.conv_up1.eval()
+        return self
+
+
+class VMN_FBA(VMN):
+    """Video matting network (VMN_model.py:70-113) with the FBA base net (models/VMN/__init__.py:18-21), native
+    inference forward.  ``extras[i] = [RGB/255 [B,3,H,W], two-channel trimap [B,2,H,W]]`` (models/model.py:404-405)."""
+
+    def engine(self) -> FbaVmnEngine:
+        return _engine_for(self, self.decoder.fam.window, FbaVmnEngine)
+
+    def forward(self, images: List[torch.Tensor], masks: Sequence[torch.Tensor], extras=None):
+        if self.training:
+            raise NotImplementedError("tcvom_b200: vmn_fba is built for inference (BASELINE configs[4]); call .eval()")
+        if extras is None:
+            raise ValueError("tcvom_b200: vmn_fba needs `extras` (scaled image and two-channel trimap per frame)")
+        S = len(images)
+        for i in range(S):
+            images[i] = images[i].squeeze(1)                        # VMN_model.py:94 (in-place list update)
+        x0 = images[0]
+        _require_cuda(x0, "images")
+        B, Cin, H, W = x0.shape
+        assert Cin == 11, "vmn_fba takes 3 image + 6 transformed-trimap + 2 trimap channels"
+        if H % 32 or W % 32:
+            raise ValueError("tcvom_b200: H and W must be multiples of 32 (pred_test.py pads to 32)")
+        eng = self.engine()
+        L = _cabi.lib()
+        st = _stream(x0.device)
+        x16 = Act.empty(B * S, H, W, 16, x0.device)
+        x16.buf.zero_()
+        trimask = torch.empty((B * S, H, W), dtype=torch.float32, device=x0.device)
+        for i in range(S):
+            # channels 0..10 = the network input, 11..13 = the decoder's `img` extra (zero stem weights); the
+            # two-channel trimap extra equals input channels 9..10 (models/model.py:382-385, 404-405)
+            xi = torch.cat([images[i].float(), extras[i][0].float()], dim=1).contiguous()
+            mi = masks[i].reshape(B, H, W).float()
+            for b in range(B):
+                n = b * S + i
+                _cabi.check(L.tcv_nchw_to_split(xi[b].data_ptr(), 1, 14, H, W, 16, x16.slice(n, n + 1).ptr, x16.plane,
+                                                st), "nchw_to_split")
+                trimask[n].copy_(mi[b])
+        out = eng.window_program(x16, trimask, B, S, H, W)
+        preds: List[Optional[torch.Tensor]] = [None] * S
+        attb: List[Optional[torch.Tensor]] = [None] * S
+        attf: List[Optional[torch.Tensor]] = [None] * S
+        small: List[Optional[torch.Tensor]] = [None] * S
+        for i in range(1, S - 1):
+            preds[i] = out["pred"][:, i - 1]
+            attb[i] = out["attb"][:, i - 1]
+            attf[i] = out["attf"][:, i - 1]
+            small[i] = out["small_mask"][:, i - 1].bool()
+        preds[0] = torch.zeros_like(preds[1])
+        preds[-1] = torch.zeros_like(preds[-2])
+        return preds, attb, attf, small
+
+
 def get_VMN_models(arch, agg_window, agg_reduction=1, freeze_backbone=False, **kwargs):
     """Plugin seam of the reference (models/VMN/__init__.py:11-29)."""
-    if arch != 'vmn_gca':
-        if arch in ('vmn_dim', 'vmn_fba', 'vmn_index'):
-            raise NotImplementedError(f"tcvom_b200: base network '{arch}' is outside the built hot path (vmn_gca)")
+    if arch not in ('vmn_gca', 'vmn_fba'):
+        if arch in ('vmn_dim', 'vmn_index'):
+            raise NotImplementedError(f"tcvom_b200: base network '{arch}' is outside the built hot path "
+                                      "(vmn_gca, vmn_fba)")
         raise ValueError
     if agg_reduction != 1:
         raise NotImplementedError("tcvom_b200: agg_reduction != 1 is not supported")
+    if arch == 'vmn_fba':
+        e = FBAEncoderParams()
+        d = _FBADecoder(agg_reduction, int(agg_window), freeze_backbone=freeze_backbone)
+        d.fam = FeatureAggregationModule(256, agg_reduction, int(agg_window))
+        return VMN_FBA(encoder=e, decoder=d, freeze_backbone=freeze_backbone)
     e = GCAEncoderParams()
     d = _GCADecoder(agg_reduction, int(agg_window), freeze_backbone=freeze_backbone)
     d.fam = FeatureAggregationModule(128, agg_reduction, int(agg_window))
@@ -363,9 +432,50 @@ class EvalModel(nn.Module):
         self.NET = get_VMN_models(arch=model, **kwargs)
         self.window = kwargs['agg_window']
         self.method = model[model.rfind('_') + 1:]
-        self.TRIMAP_CHANNEL = 3
+        self.TRIMAP_CHANNEL = 8 if self.method == 'fba' else 3
 
     # -- plan handling ---------------------------------------------------------------
+    def _plan_fba(self, B, S, H, W, u8=False) -> Plan:
+        """EvalModel.forward for method 'fba' (models/model.py:389-446) as one recorded plan: trimask (+ dilation),
+        input encoding incl. the distance transforms, the VMN program, the where()-tail."""
+        eng = self.NET.engine()
+        dil = -1 if self.DILATION_KERNEL is None else int(self.DILATION_KERNEL)
+        self.__dict__["_eng"] = eng
+        key = ("eval_fba", B, S, H, W, dil, u8)
+        plan = eng.get_plan(key)
+        if plan is not None:
+            return plan
+        plan = Plan()
+        eng._rec = plan
+        try:
+            in_dt = torch.uint8 if u8 else torch.float32
+            sfx = "_u8" if u8 else ""
+            imgs = eng._empty((B, S, 3, H, W), in_dt)
+            tris = eng._empty((B, S, 1, H, W), in_dt)
+            x8 = eng._act(B * S, H, W, 8)                       # by-product of the shared trimask kernel (unused)
+            x16 = eng._act(B * S, H, W, 16)
+            trimask = eng._empty((B * S, H, W))
+            tmp = eng._empty((2 * B * S * H * W,), torch.uint8)
+            alphas = eng._empty((B, S, 1, H, W))
+            Fs = eng._empty((B, S, 3, H, W))
+            Bs = eng._empty((B, S, 3, H, W))
+            imgs.zero_(); tris.zero_()
+            n0 = _cabi.launch_count()
+            eng._call("tcv_preprocess_eval" + sfx, imgs.data_ptr(), tris.data_ptr(), B * S, H, W, dil, x8.ptr,
+                      trimask.data_ptr(), tmp.data_ptr())
+            eng.encode_inputs(imgs, tris, B * S, H, W, x16)
+            out = eng.window_program(x16, trimask, B, S, H, W)
+            eng._call("tcv_postprocess_eval_fba", out["pred"].data_ptr(), imgs.data_ptr(), tris.data_ptr(),
+                      1 if u8 else 0, trimask.data_ptr(), B, S, H, W, alphas.data_ptr(), Fs.data_ptr(), Bs.data_ptr())
+            plan.n_launch = _cabi.launch_count() - n0
+            plan.io = dict(imgs=imgs, tris=tris, alphas=alphas, Fs=Fs, Bs=Bs, trimask=trimask, x16=x16.buf,
+                           **{k: out[k] for k in ("pred", "attb", "attf", "small_mask")})
+            plan.io["feat"] = out["feat"].buf
+        finally:
+            eng._rec = None
+        eng.put_plan(key, plan)
+        return plan
+
     def _plan(self, B, S, H, W, dev, u8=False) -> Plan:
         eng = self.NET.engine()
         dil = -1 if self.DILATION_KERNEL is None else int(self.DILATION_KERNEL)
@@ -425,8 +535,6 @@ class EvalModel(nn.Module):
 
     def forward(self, imgs, tris):
         _require_cuda(imgs, "imgs")
-        if self.method == 'fba':
-            raise NotImplementedError
         self.NET._check_mode()
         B, S, Cc, H, W = imgs.shape
         assert Cc == 3 and S >= 3
@@ -434,6 +542,12 @@ class EvalModel(nn.Module):
             raise ValueError("tcvom_b200: H and W must be multiples of 32 (pred_test.py pads to 32)")
         # uint8 frames/trimaps are consumed as such (the reference casts with .float(), model.py:366-368)
         u8 = imgs.dtype == torch.uint8 and tris.dtype == torch.uint8
+        if self.method == 'fba':
+            plan = self._plan_fba(B, S, H, W, u8)
+            plan.io["imgs"].copy_(imgs, non_blocking=True)
+            plan.io["tris"].copy_(tris, non_blocking=True)
+            self.run_plan(plan)
+            return plan.io["alphas"].clone(), plan.io["Fs"].clone(), plan.io["Bs"].clone()
         plan = self._plan(B, S, H, W, imgs.device, u8)
         plan.io["imgs"].copy_(imgs, non_blocking=True)
         plan.io["tris"].copy_(tris, non_blocking=True)
@@ -459,6 +573,9 @@ class FullModel_VMD(nn.Module):
     def __init__(self, model, att_thres=0.3, label_smooth=0.2, dilate_kernel=None, eps=0, **kwargs):
         super().__init__()
         assert model.startswith('vmn'), "FullModel_VMD only support VMN arch"
+        if model != 'vmn_gca':
+            raise NotImplementedError("tcvom_b200: the loss wrappers are built for vmn_gca; vmn_fba is built for "
+                                      "inference through EvalModel / the VMN seam (BASELINE configs[4])")
         self.att_thres = att_thres
         self.label_smooth = label_smooth
         self.DILATION_KERNEL = dilate_kernel

@@ -48,7 +48,22 @@ def test_get_vmn_models_error_behaviour():
     with pytest.raises(ValueError):
         tcvom_b200.get_VMN_models("nope", agg_window=7)   # VMN/__init__.py:26-27
     with pytest.raises(NotImplementedError):
-        tcvom_b200.get_VMN_models("vmn_fba", agg_window=7)
+        tcvom_b200.get_VMN_models("vmn_dim", agg_window=7)
+
+
+def test_fba_state_dict_contract_matches_reference_layout():
+    import tcvom_b200
+    from helpers import fixture_sd_fba, key_table_fba
+    net = tcvom_b200.get_VMN_models("vmn_fba", agg_window=7)
+    kt = key_table_fba()
+    mine = [[k, list(v.shape)] for k, v in net.state_dict().items()]
+    assert mine == kt["state_dict"]                      # names, shapes AND order (203 keys)
+    assert [n for n, p in net.named_parameters() if p.requires_grad] == kt["trainable"]
+    net.load_state_dict(fixture_sd_fba(), strict=True)
+    m = tcvom_b200.EvalModel(model="vmn_fba", agg_window=7, dilate_kernel=None)
+    assert m.TRIMAP_CHANNEL == 8 and len(m.NET.state_dict()) == 203
+    with pytest.raises(RuntimeError):                    # CPU tensors: no fallback
+        m.eval()(torch.zeros(1, 3, 3, 64, 64), torch.zeros(1, 3, 1, 64, 64))
 
 
 def test_cpu_module_refuses_to_run():
