@@ -271,3 +271,29 @@ class FbaVmnEngine(GcaVmnEngine):
         self._call("tcv_fba_edt_cols", x16.ptr, frames, H, W, g.data_ptr())
         self._call("tcv_fba_edt_rows", g.data_ptr(), frames, H, W, x16.ptr,
                    meta=dict(kind="tcv_fba_edt_rows", bytes=frames * H * W * 2 * (4 + 12)))
+
+    def eval_program(self, B: int, S: int, H: int, W: int, dilate: int, u8: bool) -> dict:
+        """EvalModel.forward for method 'fba' (models/model.py:389-446) on static buffers: trimask (+ optional
+        dilation, the kernel shared with vmn_gca), input encoding, the VMN program, the where()-tail.  Returns the
+        io tensors (inputs ``imgs`` / ``tris`` to be filled before a replay; outputs ``alphas`` / ``Fs`` / ``Bs``)."""
+        in_dt = torch.uint8 if u8 else torch.float32
+        sfx = "_u8" if u8 else ""
+        imgs = self._empty((B, S, 3, H, W), in_dt)
+        tris = self._empty((B, S, 1, H, W), in_dt)
+        x8 = self._act(B * S, H, W, 8)                          # by-product of the shared trimask kernel (unused)
+        x16 = self._act(B * S, H, W, 16)
+        trimask = self._empty((B * S, H, W))
+        tmp = self._empty((2 * B * S * H * W,), torch.uint8)
+        alphas = self._empty((B, S, 1, H, W))
+        Fs = self._empty((B, S, 3, H, W))
+        Bs = self._empty((B, S, 3, H, W))
+        imgs.zero_(); tris.zero_()                              # recording runs the kernels once: valid inputs
+        self._call("tcv_preprocess_eval" + sfx, imgs.data_ptr(), tris.data_ptr(), B * S, H, W, dilate, x8.ptr,
+                   trimask.data_ptr(), tmp.data_ptr())
+        self.encode_inputs(imgs, tris, B * S, H, W, x16)
+        out = self.window_program(x16, trimask, B, S, H, W)
+        self._call("tcv_postprocess_eval_fba", out["pred"].data_ptr(), imgs.data_ptr(), tris.data_ptr(),
+                   1 if u8 else 0, trimask.data_ptr(), B, S, H, W, alphas.data_ptr(), Fs.data_ptr(), Bs.data_ptr())
+        io = dict(imgs=imgs, tris=tris, alphas=alphas, Fs=Fs, Bs=Bs, trimask=trimask, x16=x16.buf,
+                  feat=out["feat"].buf, **{k: out[k] for k in ("pred", "attb", "attf", "small_mask")})
+        return io

@@ -448,29 +448,9 @@ class EvalModel(nn.Module):
         plan = Plan()
         eng._rec = plan
         try:
-            in_dt = torch.uint8 if u8 else torch.float32
-            sfx = "_u8" if u8 else ""
-            imgs = eng._empty((B, S, 3, H, W), in_dt)
-            tris = eng._empty((B, S, 1, H, W), in_dt)
-            x8 = eng._act(B * S, H, W, 8)                       # by-product of the shared trimask kernel (unused)
-            x16 = eng._act(B * S, H, W, 16)
-            trimask = eng._empty((B * S, H, W))
-            tmp = eng._empty((2 * B * S * H * W,), torch.uint8)
-            alphas = eng._empty((B, S, 1, H, W))
-            Fs = eng._empty((B, S, 3, H, W))
-            Bs = eng._empty((B, S, 3, H, W))
-            imgs.zero_(); tris.zero_()
             n0 = _cabi.launch_count()
-            eng._call("tcv_preprocess_eval" + sfx, imgs.data_ptr(), tris.data_ptr(), B * S, H, W, dil, x8.ptr,
-                      trimask.data_ptr(), tmp.data_ptr())
-            eng.encode_inputs(imgs, tris, B * S, H, W, x16)
-            out = eng.window_program(x16, trimask, B, S, H, W)
-            eng._call("tcv_postprocess_eval_fba", out["pred"].data_ptr(), imgs.data_ptr(), tris.data_ptr(),
-                      1 if u8 else 0, trimask.data_ptr(), B, S, H, W, alphas.data_ptr(), Fs.data_ptr(), Bs.data_ptr())
+            plan.io = eng.eval_program(B, S, H, W, dil, u8)
             plan.n_launch = _cabi.launch_count() - n0
-            plan.io = dict(imgs=imgs, tris=tris, alphas=alphas, Fs=Fs, Bs=Bs, trimask=trimask, x16=x16.buf,
-                           **{k: out[k] for k in ("pred", "attb", "attf", "small_mask")})
-            plan.io["feat"] = out["feat"].buf
         finally:
             eng._rec = None
         eng.put_plan(key, plan)

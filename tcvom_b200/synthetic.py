@@ -145,20 +145,23 @@ def seeded_tensor_fba(key: str, shape, shapes: Dict[str, tuple], seed: int = 0) 
     """Fixture value of one ``vmn_fba`` state_dict entry (203 keys, no calibrated part: GroupNorm has no running
     statistics).  Plain random init saturates alpha = clamp(out[:, 0], 0, 1) at 0 for 99.7 % of the pixels
     (measured on the reference), which would make an alpha parity test vacuous: the last 1x1 conv's alpha row is
-    rescaled and biased so that the unknown band is spread over (0, 1)."""
+    rescaled and its bias zeroed so that the unknown band is spread over (0, 1) (mean 0.55, std 0.27, 10 % saturated)."""
     if len(shape) == 4:
         w = _xavier(key, shape, seed)
         if key.endswith("conv_up4.4.weight"):
             w[0] *= 0.6
         return w
     if key.endswith(".weight"):                                # GroupNorm gamma
-        return _rng(key, seed).uniform(0.8, 1.2, size=shape).astype(np.float32)
+        g = _rng(key, seed).uniform(0.8, 1.2, size=shape).astype(np.float32)
+        if ".bn3." in key:
+            g *= 0.3        # damped residual branches: a random-weight ResNet-50 amplifies rounding noise ~500x otherwise
+        return g
     sibling = shapes.get(key[: -len(".bias")] + ".weight")
     if sibling is not None and len(sibling) == 1:              # GroupNorm beta
         return _rng(key, seed).uniform(-0.1, 0.1, size=shape).astype(np.float32)
     b = _rng(key, seed).uniform(-0.05, 0.05, size=shape).astype(np.float32)   # conv bias
     if key.endswith("conv_up4.4.bias"):
-        b[0] = 0.5
+        b[0] = 0.0
     return b
 
 

@@ -1,0 +1,346 @@
+// TEST DOUBLE of the tcvom_b200 C ABI for the CPU test-suite (tests/test_host_emul_fba.py).  NOT a product path and
+// not a fallback: nothing under tcvom_b200/ can load it; the tests substitute it for libtcvom_b200.so by
+// monkey-patching tcvom_b200._cabi._lib so that the HOST program of FbaVmnEngine (which kernels run, in which
+// order, on which buffers, with which descriptors) can be executed on host memory and compared with the oracle
+// in the GPU-less build container.
+//
+// * the FBA element-wise kernels execute the very same per-work-item bodies as the CUDA kernels
+//   (tcvom_b200/csrc/fba_body.h), looped over the work items;
+// * tcv_conv2d, tcv_tam_attend, tcv_preprocess_eval, tcv_ws_pack, tcv_gn_stats, tcv_adaptive_avgpool are independent
+//   naive restatements of the semantics documented in include/tcvom_b200.h.
+// Only the entry points the FBA eval program uses are provided.
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/tcvom_b200.h"
+#include "../../tcvom_b200/csrc/fba_body.h"
+
+using namespace tcv_fba;
+
+static long long g_launches = 0;
+static const char* g_err = "";
+
+#define REQ(c, msg) do { if (!(c)) { g_err = msg; return TCV_ERR_INVALID; } } while (0)
+
+template <typename P, void (*BODY)(ll, const P&)>
+static int run_body(const P& p, ll total) {
+#pragma omp parallel for schedule(static)
+  for (ll i = 0; i < total; ++i) BODY(i, p);
+  ++g_launches;
+  return 0;
+}
+
+static std::vector<float> to_float(const uint16_t* x, ll plane, ll img_stride, int n, ll img_elems) {
+  std::vector<float> f((size_t)n * img_elems);
+#pragma omp parallel for
+  for (ll i = 0; i < (ll)n * img_elems; ++i) {
+    const ll img = i / img_elems, e = i % img_elems;
+    f[i] = ld1(x + img * img_stride + e, plane);
+  }
+  return f;
+}
+
+static int reflect_idx(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * n - 2 - i;
+  return i;
+}
+
+template <typename T>
+static int preprocess_eval_t(const T* tris, int frames, int h, int w, int dilate, float* trimask) {
+  const ll hw = (ll)h * w;
+  std::vector<uint8_t> m((size_t)frames * hw);
+  for (ll i = 0; i < frames * hw; ++i) {
+    const float s = (float)tris[i] * (1.0f / 255);
+    m[i] = (s > 0.f && s < 1.f) ? 1 : 0;
+  }
+  for (int f = 0; f < frames; ++f)
+    for (int y = 0; y < h; ++y)
+      for (int x = 0; x < w; ++x) {
+        uint8_t v = 0;
+        if (dilate > 0) {
+          for (int yy = y - dilate; yy <= y + dilate && !v; ++yy)
+            for (int xx = x - dilate; xx <= x + dilate && !v; ++xx)
+              if (yy >= 0 && yy < h && xx >= 0 && xx < w && m[f * hw + (ll)yy * w + xx]) v = 1;
+        } else {
+          v = m[f * hw + (ll)y * w + x];
+        }
+        trimask[f * hw + (ll)y * w + x] = v ? 1.f : 0.f;
+      }
+  ++g_launches;
+  return 0;
+}
+extern "C" {
+
+int tcv_version(void) { return 100; }
+const char* tcv_last_error(void) { return g_err; }
+long long tcv_launch_count(void) { return g_launches; }
+int tcv_conv2d_path(const tcv_conv_desc*) { return 0; }
+int tcv_pack_weight_tc(const float*, int, int, int, void*, tcv_stream_t) { return 0; }
+
+int tcv_conv2d(const tcv_conv_desc* dp, tcv_stream_t) {
+  tcv_conv_desc d = *dp;
+  REQ(d.x && d.w && (d.y || d.y_f32), "conv2d: null");
+  REQ(d.cin % 8 == 0 && (d.cin <= 32 || d.cin % 32 == 0), "conv2d: cin");
+  REQ(d.ntaps >= 1 && d.ntaps <= TCV_MAX_TAPS, "conv2d: ntaps");
+  REQ(d.stride == 1 || d.stride == 2, "conv2d: stride");
+  REQ((d.gh - 1) * d.oy_mul + d.oy_off < d.oh && (d.gw - 1) * d.ox_mul + d.ox_off < d.ow, "conv2d: grid");
+  const ll img_elems = (ll)d.ih * d.iw * d.cin;
+  if (d.x_plane == 0) d.x_plane = (ll)d.n * img_elems;
+  if (d.x_img_stride == 0) d.x_img_stride = img_elems;
+  if (d.res1 && d.res1_plane == 0) d.res1_plane = (ll)d.n * (d.oh >> d.res1_shift) * (d.ow >> d.res1_shift) * d.cout;
+  if (d.res2 && d.res2_plane == 0) d.res2_plane = (ll)d.n * d.oh * d.ow * d.cout;
+  const std::vector<float> X = to_float((const uint16_t*)d.x, d.x_plane, d.x_img_stride, d.n, img_elems);
+  const ll oplane = (ll)d.n * d.oh * d.ow * d.cout;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int n = 0; n < d.n; ++n)
+    for (int gy = 0; gy < d.gh; ++gy) {
+      std::vector<float> acc(d.cout);
+      for (int gx = 0; gx < d.gw; ++gx) {
+        for (int j = 0; j < d.cout; ++j) acc[j] = 0.f;
+        for (int t = 0; t < d.ntaps; ++t) {
+          int iy = gy * d.stride + d.dy[t], ix = gx * d.stride + d.dx[t];
+          if (d.pad_mode == TCV_PAD_REFLECT) { iy = reflect_idx(iy, d.ih); ix = reflect_idx(ix, d.iw); }
+          else if (iy < 0 || iy >= d.ih || ix < 0 || ix >= d.iw) continue;
+          const float* xp = X.data() + (ll)n * img_elems + ((ll)iy * d.iw + ix) * d.cin;
+          const float* wp = d.w + (ll)d.wtap[t] * d.cin * d.cout;
+          for (int ci = 0; ci < d.cin; ++ci) {
+            const float xv = xp[ci];
+            const float* wr = wp + (ll)ci * d.cout;
+            for (int j = 0; j < d.cout; ++j) acc[j] += xv * wr[j];
+          }
+        }
+        const int oy = gy * d.oy_mul + d.oy_off, ox = gx * d.ox_mul + d.ox_off;
+        const ll obase = (((ll)n * d.oh + oy) * d.ow + ox) * d.cout;
+        for (int j = 0; j < d.cout; ++j) {
+          float a = acc[j];
+          if (d.s1) a *= d.s1[j];
+          if (d.b1) a += d.b1[j];
+          if (d.res1) {
+            const int rh = d.oh >> d.res1_shift, rw = d.ow >> d.res1_shift;
+            a += ld1((const uint16_t*)d.res1 + (((ll)n * rh + (oy >> d.res1_shift)) * rw + (ox >> d.res1_shift)) * d.cout + j,
+                     d.res1_plane);
+          }
+          a = act_fn(a, d.act);
+          if (d.s2) a = a * d.s2[j] + d.b2[j];
+          if (d.res2) a += ld1((const uint16_t*)d.res2 + obase + j, d.res2_plane);
+          if (d.y) st1((uint16_t*)d.y + obase + j, oplane, a);
+          if (d.y_f32) d.y_f32[obase + j] = a;
+        }
+      }
+    }
+  ++g_launches;
+  return 0;
+}
+
+int tcv_preprocess_eval(const float*, const float* tris, int frames, int h, int w, int dilate, void*, float* trimask,
+                        uint8_t*, tcv_stream_t) {
+  return preprocess_eval_t<float>(tris, frames, h, w, dilate, trimask);
+}
+int tcv_preprocess_eval_u8(const uint8_t*, const uint8_t* tris, int frames, int h, int w, int dilate, void*,
+                           float* trimask, uint8_t*, tcv_stream_t) {
+  return preprocess_eval_t<uint8_t>(tris, frames, h, w, dilate, trimask);
+}
+
+int tcv_nchw_to_split(const float* x, int n, int c, int h, int w, int c_pad, void* y, long long y_plane, tcv_stream_t) {
+  const ll hw = (ll)h * w;
+  if (y_plane == 0) y_plane = (ll)n * hw * c_pad;
+  for (ll i = 0; i < (ll)n * hw * c_pad; ++i) {
+    const int cc = (int)(i % c_pad);
+    const ll p = (i / c_pad) % hw, img = i / (c_pad * hw);
+    st1((uint16_t*)y + i, y_plane, cc < c ? x[(img * c + cc) * hw + p] : 0.f);
+  }
+  ++g_launches;
+  return 0;
+}
+
+// VMN_model.py:27-68 after the q/k/v convolutions (see tcv_tam_attend in the header)
+int tcv_tam_attend(const void* q, const void* v, const void* kb, const void* kf, const float* mask,
+                   long long mask_stride, int mh, int mw, int batch, int h, int w, int c, int window, void* out,
+                   float* attb, float* attf, uint8_t* small_mask, tcv_stream_t) {
+  const ll N = (ll)h * w, plane = (ll)batch * N * c;
+  const int w2 = window * window, r = window / 2;
+  const float inv = 1.0f / sqrtf((float)c);
+#pragma omp parallel for schedule(static)
+  for (ll gp = 0; gp < batch * N; ++gp) {
+    const int b = (int)(gp / N), pix = (int)(gp % N), y = pix / w, x = pix % w;
+    const int my = (int)(((ll)y * mh) / h), mx = (int)(((ll)x * mw) / w);
+    const bool m = mask[(ll)b * mask_stride + (ll)my * mw + mx] != 0.f;
+    small_mask[gp] = m ? 1 : 0;
+    std::vector<float> o(c), qv(c), logit(w2);
+    const ll base = gp * c;
+    for (int ch = 0; ch < c; ++ch) o[ch] = ld1((const uint16_t*)v + base + ch, plane);
+    for (int nb = 0; nb < 2; ++nb) {
+      const uint16_t* k = (const uint16_t*)(nb == 0 ? kb : kf);
+      float* att = nb == 0 ? attb : attf;
+      if (!m) {
+        for (int j = 0; j < w2; ++j) att[((ll)b * w2 + j) * N + pix] = 0.f;
+        continue;
+      }
+      for (int ch = 0; ch < c; ++ch) qv[ch] = ld1((const uint16_t*)q + base + ch, plane);
+      float mxv = -INFINITY;
+      for (int j = 0; j < w2; ++j) {
+        const int yy = y + j / window - r, xx = x + j % window - r;
+        float dsum = 0.f;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w)
+          for (int ch = 0; ch < c; ++ch) dsum += qv[ch] * ld1(k + ((ll)b * N + (ll)yy * w + xx) * c + ch, plane);
+        logit[j] = dsum * inv;
+        att[((ll)b * w2 + j) * N + pix] = logit[j];
+        mxv = fmaxf(mxv, logit[j]);
+      }
+      float den = 0.f;
+      for (int j = 0; j < w2; ++j) den += expf(logit[j] - mxv);
+      for (int j = 0; j < w2; ++j) {
+        const int yy = y + j / window - r, xx = x + j % window - r;
+        if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
+        const float a = expf(logit[j] - mxv) / den;
+        for (int ch = 0; ch < c; ++ch) o[ch] += a * ld1(k + ((ll)b * N + (ll)yy * w + xx) * c + ch, plane);
+      }
+    }
+    for (int ch = 0; ch < c; ++ch) st1((uint16_t*)out + base + ch, plane, o[ch]);
+  }
+  ++g_launches;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ FBA entry points
+int tcv_ws_pack(const float* w, int cout, int cin, int kh, int kw, int standardize, int cin_pad, int cout_pad,
+                float* packed, tcv_stream_t) {
+  const int taps = kh * kw, cnt = cin * taps;
+  memset(packed, 0, sizeof(float) * (size_t)taps * cin_pad * cout_pad);
+  for (int co = 0; co < cout; ++co) {
+    double mean = 0.0, inv = 1.0;
+    if (standardize) {
+      for (int i = 0; i < cnt; ++i) mean += w[(ll)co * cnt + i];
+      mean /= cnt;
+      double ss = 0.0;
+      for (int i = 0; i < cnt; ++i) { const double dd = w[(ll)co * cnt + i] - mean; ss += dd * dd; }
+      inv = 1.0 / (sqrt(ss / (cnt - 1) + 1e-12) + 1e-5);
+    }
+    for (int ci = 0; ci < cin; ++ci)
+      for (int t = 0; t < taps; ++t)
+        packed[((ll)t * cin_pad + ci) * cout_pad + co] = (float)((w[((ll)co * cin + ci) * taps + t] - mean) * inv);
+  }
+  ++g_launches;
+  return 0;
+}
+
+int tcv_gn_stats(const void* x, long long x_plane, int n, long long pixels, int c, double* sums, tcv_stream_t) {
+  if (x_plane == 0) x_plane = (ll)n * pixels * c;
+  for (ll i = 0; i < (ll)n * c * 2; ++i) sums[i] = 0.0;
+  for (int img = 0; img < n; ++img)
+    for (ll p = 0; p < pixels; ++p)
+      for (int ch = 0; ch < c; ++ch) {
+        const double v = ld1((const uint16_t*)x + ((ll)img * pixels + p) * c + ch, x_plane);
+        sums[((ll)img * c + ch) * 2] += v;
+        sums[((ll)img * c + ch) * 2 + 1] += v * v;
+      }
+  ++g_launches;
+  return 0;
+}
+
+int tcv_gn_finalize(const double* sums, int n, long long pixels, int c, int groups, const float* gamma,
+                    const float* beta, float eps, float* scale, float* shift, tcv_stream_t) {
+  GnFinalizeP p{sums, n, c, groups, pixels, gamma, beta, eps, scale, shift};
+  return run_body<GnFinalizeP, gn_finalize_body>(p, (ll)n * groups);
+}
+
+int tcv_gn_apply(const void* x, long long x_plane, int n, long long pixels, int c, const float* scale,
+                 const float* shift, const void* res, long long res_plane, int act, void* y, long long y_plane,
+                 int y_c, int y_off, tcv_stream_t) {
+  REQ(c % 8 == 0 && y_c % 8 == 0 && y_off % 8 == 0 && y_off + c <= y_c, "gn_apply: dims");
+  if (x_plane == 0) x_plane = (ll)n * pixels * c;
+  if (res && res_plane == 0) res_plane = (ll)n * pixels * c;
+  if (y_plane == 0) y_plane = (ll)n * pixels * y_c;
+  GnApplyP p{(const uint16_t*)x, x_plane, n, c, pixels, scale, shift, (const uint16_t*)res, res_plane, act,
+             (uint16_t*)y, y_plane, y_c, y_off};
+  return run_body<GnApplyP, gn_apply_body>(p, (ll)n * pixels * (c / 8));
+}
+
+int tcv_maxpool3s2(const void* x, int n, int h, int w, int c, void* y, tcv_stream_t) {
+  PoolP p{(const uint16_t*)x, n, h, w, c, (h - 1) / 2 + 1, (w - 1) / 2 + 1, (uint16_t*)y};
+  return run_body<PoolP, maxpool3s2_body>(p, (ll)n * p.oh * p.ow * (c / 8));
+}
+
+int tcv_adaptive_avgpool(const void* x, long long x_plane, int n, int h, int w, int c, int x_c, int x_off, int s,
+                         void* y, tcv_stream_t) {
+  REQ(c % 64 == 0 && x_off + c <= x_c, "adaptive_avgpool: dims");
+  if (x_plane == 0) x_plane = (ll)n * h * w * x_c;
+  const ll yplane = (ll)n * s * s * c;
+  for (int img = 0; img < n; ++img)
+    for (int i = 0; i < s; ++i)
+      for (int j = 0; j < s; ++j) {
+        const int y0 = bin_start(i, h, s), y1 = bin_end(i, h, s);   // the bin arithmetic the CUDA kernel uses
+        const int x0 = bin_start(j, w, s), x1 = bin_end(j, w, s);
+        for (int ch = 0; ch < c; ++ch) {
+          float a = 0.f;
+          for (int yy = y0; yy < y1; ++yy)
+            for (int xx = x0; xx < x1; ++xx)
+              a += ld1((const uint16_t*)x + (((ll)img * h + yy) * w + xx) * x_c + x_off + ch, x_plane);
+          st1((uint16_t*)y + (((ll)img * s + i) * s + j) * c + ch, yplane, a / (float)((y1 - y0) * (x1 - x0)));
+        }
+      }
+  ++g_launches;
+  return 0;
+}
+
+int tcv_bilinear(const void* x, int n, int ih, int iw, int c, void* y, long long y_plane, int oh, int ow, int y_c,
+                 int y_off, tcv_stream_t) {
+  REQ(c % 8 == 0 && y_c % 8 == 0 && y_off % 8 == 0 && y_off + c <= y_c, "bilinear: dims");
+  if (y_plane == 0) y_plane = (ll)n * oh * ow * y_c;
+  BilinearP p{(const uint16_t*)x, n, ih, iw, c, (uint16_t*)y, y_plane, oh, ow, y_c, y_off};
+  return run_body<BilinearP, bilinear_body>(p, (ll)n * oh * ow * (c / 8));
+}
+
+int tcv_copy_channels(const void* x, long long x_plane, int x_c, int x_off, void* y, long long y_plane, int y_c,
+                      int y_off, int c, long long pixels, tcv_stream_t) {
+  REQ(c % 8 == 0 && x_off + c <= x_c && y_off + c <= y_c, "copy_channels: dims");
+  if (x_plane == 0) x_plane = pixels * x_c;
+  if (y_plane == 0) y_plane = pixels * y_c;
+  CopyP p{(const uint16_t*)x, x_plane, x_c, x_off, (uint16_t*)y, y_plane, y_c, y_off, c, pixels};
+  return run_body<CopyP, copy_channels_body>(p, pixels * (c / 8));
+}
+
+int tcv_fba_encode_inputs(const void* imgs, const void* tris, int is_u8, int frames, int h, int w, void* x16,
+                          tcv_stream_t) {
+  EncodeP p{imgs, tris, is_u8, frames, h, w, (uint16_t*)x16};
+  return run_body<EncodeP, fba_encode_body>(p, (ll)frames * h * w);
+}
+
+int tcv_fba_edt_cols(const void* x16, int frames, int h, int w, int* g, tcv_stream_t) {
+  EdtP p{(uint16_t*)x16, frames, h, w, g};
+  return run_body<EdtP, fba_edt_cols_body>(p, (ll)frames * 2 * w);
+}
+
+int tcv_fba_edt_rows(const int* g, int frames, int h, int w, void* x16, tcv_stream_t) {
+  EdtP p{(uint16_t*)x16, frames, h, w, (int*)g};
+  return run_body<EdtP, fba_edt_rows_body>(p, (ll)frames * 2 * h * w);
+}
+
+int tcv_fba_cat_inputs(const void* x16, long long x16_plane, long long pixels, void* y, long long y_plane, int y_c,
+                       int y_off, tcv_stream_t) {
+  REQ(y_off + 32 <= y_c, "fba_cat_inputs: dims");
+  if (y_plane == 0) y_plane = pixels * y_c;
+  if (x16_plane == 0) x16_plane = pixels * 16;
+  CatP p{(const uint16_t*)x16, x16_plane, pixels, (uint16_t*)y, y_plane, y_c, y_off};
+  return run_body<CatP, fba_cat_inputs_body>(p, pixels);
+}
+
+int tcv_fba_fusion(const void* o8, const void* x16, long long x16_plane, long long x16_img_stride, int n, int h, int w,
+                   float* pred, tcv_stream_t) {
+  if (x16_img_stride == 0) x16_img_stride = (ll)h * w * 16;
+  FusionP p{(const uint16_t*)o8, (const uint16_t*)x16, x16_plane, x16_img_stride, n, h, w, pred};
+  return run_body<FusionP, fba_fusion_body>(p, (ll)n * h * w);
+}
+
+int tcv_postprocess_eval_fba(const float* pred, const void* imgs, const void* tris, int is_u8, const float* trimask,
+                             int batch, int frames, int h, int w, float* alphas, float* Fs, float* Bs, tcv_stream_t) {
+  PostP p{pred, imgs, tris, is_u8, trimask, batch, frames, h, w, alphas, Fs, Bs};
+  return run_body<PostP, postprocess_fba_body>(p, (ll)batch * frames * h * w);
+}
+
+}  // extern "C"

@@ -1,0 +1,275 @@
+"""GPU parity tests of the FBA+TAM path (BASELINE configs[4]) through the C ABI:
+the FBA kernels against plain PyTorch fp32 references, the FBA-specific convolution shapes (dilation, 1x1 /
+stride 2, 2048- and 3072-channel reductions, the chained 7x7 stem) against torch conv2d, the input encoding
+(incl. the exact distance transform) and the whole EvalModel('vmn_fba') against the golden vectors produced by the
+unmodified reference and against the CPU oracle.
+
+Tolerance: 1e-3 max abs on the alpha matte (north_star), same bar for the F / B colour planes."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import fixture_sd_fba, golden
+from oracle import vmn_fba_oracle as O
+
+pytestmark = pytest.mark.gpu
+ALPHA_TOL = 1e-3
+CASES = ["ring64", "ring96x128", "allunk64", "nounk64", "dil64x96", "batch2_64"]
+DEV = "cuda:0"
+
+
+def _engine():
+    from tcvom_b200.fba_engine import FbaVmnEngine
+    eng = FbaVmnEngine(7)
+    eng.device = torch.device(DEV)
+    return eng
+
+
+def _to_act(t, c_pad=None):
+    from tcvom_b200.engine import Act
+    n, c, h, w = t.shape
+    c_pad = c_pad or c
+    a = Act.empty(n, h, w, c_pad, torch.device(DEV))
+    x = torch.zeros(n, h, w, c_pad, device=DEV)
+    x[..., :c] = t.to(DEV).permute(0, 2, 3, 1)
+    hi = x.bfloat16()
+    a.buf[0].copy_(hi)
+    a.buf[1].copy_((x - hi.float()).bfloat16())
+    return a
+
+
+def _from_act(a, c=None):
+    return a.float()[..., : (c or a.c)].permute(0, 3, 1, 2).contiguous()
+
+
+def _model(dilate=None):
+    import tcvom_b200
+    m = tcvom_b200.EvalModel(model="vmn_fba", agg_window=7, dilate_kernel=dilate)
+    m.NET.load_state_dict(fixture_sd_fba(), strict=True)
+    return m.to(DEV).eval()
+
+
+# ------------------------------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("c,h,w,n", [(64, 5, 7, 2), (256, 1, 1, 3), (256, 6, 6, 1), (2048, 9, 12, 2), (1024, 17, 30, 1)])
+def test_groupnorm_kernels(c, h, w, n):
+    from tcvom_b200.engine import Act
+    eng = _engine()
+    torch.manual_seed(c + h)
+    x = torch.randn(n, c, h, w) * 2 + 0.3
+    res = torch.randn(n, c, h, w)
+    g, b = (torch.rand(c) + 0.5).to(DEV), (torch.randn(c) * 0.1).to(DEV)
+    eng.gn_params["p"] = (g, b)
+    xa, ra = _to_act(x), _to_act(res)
+    y = eng.gn(xa, "p", 1, res=ra)
+    ref = F.relu(F.group_norm(_from_act(xa), 32, g, b, 1e-5) + _from_act(ra))
+    assert float((_from_act(y) - ref).abs().max()) < 1e-4
+    wide = Act.empty(n, h, w, c + 64, torch.device(DEV))
+    wide.buf.zero_()
+    eng.gn(xa, "p", 4, out=wide, out_off=32)
+    got = _from_act(wide)
+    ref = F.leaky_relu(F.group_norm(_from_act(xa), 32, g, b, 1e-5), 0.01)
+    assert float((got[:, 32:32 + c] - ref).abs().max()) < 1e-4
+    assert float(got[:, :32].abs().max()) == 0 and float(got[:, 32 + c:].abs().max()) == 0
+
+
+def test_pool_resize_copy_kernels():
+    from tcvom_b200.engine import Act
+    eng = _engine()
+    torch.manual_seed(1)
+    x = torch.randn(2, 64, 19, 26)
+    xa = _to_act(x)
+    xf = _from_act(xa)
+    assert torch.equal(_from_act(eng.maxpool(xa)), F.max_pool2d(xf, 3, 2, 1))
+    for (oh, ow) in ((38, 52), (17, 5), (19, 26), (136, 240)):
+        out = Act.empty(2, oh, ow, 96, torch.device(DEV))
+        out.buf.zero_()
+        eng.bilinear(xa, oh, ow, out, 8)
+        ref = F.interpolate(xf, (oh, ow), mode="bilinear", align_corners=False)
+        assert float((_from_act(out)[:, 8:72] - ref).abs().max()) < 5e-5, (oh, ow)
+    x = torch.randn(2, 128, 17, 30)
+    xa = _to_act(x)
+    for s in (1, 2, 3, 6):
+        pooled = Act.empty(2, s, s, 64, torch.device(DEV))
+        eng._call("tcv_adaptive_avgpool", xa.ptr, xa.plane, 2, 17, 30, 64, 128, 64, s, pooled.ptr)
+        ref = F.adaptive_avg_pool2d(_from_act(xa)[:, 64:], s)
+        assert float((_from_act(pooled) - ref).abs().max()) < 2e-5, s
+    dst = Act.empty(2, 17, 30, 192, torch.device(DEV))
+    dst.buf.zero_()
+    eng.copy_channels(xa, 32, 64, dst, 128)
+    assert torch.equal(_from_act(dst)[:, 128:], _from_act(xa)[:, 32:96])
+    assert float(_from_act(dst)[:, :128].abs().max()) == 0
+
+
+def test_weight_standardisation_pack():
+    from tcvom_b200 import _cabi
+    eng = _engine()
+    for shape in ((7, 11, 3, 3), (256, 2048, 1, 1), (64, 11, 7, 7)):
+        w = torch.randn(*shape)
+        eng.w.pop("k", None)
+        eng._pack_fba(_cabi.lib(), eng._stream_ptr(), "k", w.to(DEV), True)
+        ent = eng.w["k"]
+        cout, cin, kh, kw = shape
+        ref = O.ws_weight(w).permute(2, 3, 1, 0).reshape(kh * kw, cin, cout)
+        got = ent["w"].cpu()
+        assert float((got[:, :cin, :cout] - ref).abs().max()) < 2e-5, shape
+        assert float(got[:, cin:].abs().max() if got.shape[1] > cin else 0) == 0
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,dil,h,w,n", [
+    (256, 256, 3, 1, 2, 17, 30, 2),       # layer3 dilated 3x3 (tcgen05, halo 4)
+    (512, 512, 3, 1, 4, 17, 30, 1),       # layer4 dilated 3x3 (halo 8: 16x8 tiles)
+    (512, 512, 3, 1, 4, 8, 8, 3),         # same at the golden size
+    (256, 512, 1, 2, 1, 16, 20, 2),       # stride-2 1x1 downsample
+    (128, 128, 3, 2, 1, 16, 20, 2),       # stride-2 3x3
+    (2048, 256, 1, 1, 1, 1, 1, 3),        # pyramid pooling 1x1 on a 1x1 map
+    (2048, 256, 1, 1, 1, 3, 3, 2),
+    (3072, 256, 3, 1, 1, 8, 8, 1),        # conv_up1.0
+    (1024, 2048, 1, 1, 1, 8, 10, 1),      # widest 1x1
+    (320, 64, 3, 1, 1, 32, 32, 1),        # conv_up3.0
+    (96, 32, 3, 1, 1, 64, 64, 1),         # conv_up4.0
+    (32, 16, 3, 1, 1, 40, 48, 1),         # conv_up4.2 (CUDA cores)
+    (16, 8, 1, 1, 1, 40, 48, 1),          # conv_up4.4 (CUDA cores)
+])
+def test_fba_conv_shapes(cin, cout, k, stride, dil, h, w, n):
+    from tcvom_b200 import _cabi
+    eng = _engine()
+    torch.manual_seed(cin + cout + dil)
+    x = torch.randn(n, cin, h, w)
+    wt = torch.randn(cout, cin, k, k) / (cin * k * k) ** 0.5
+    b = torch.randn(cout).to(DEV)
+    eng._pack_fba(_cabi.lib(), eng._stream_ptr(), "c", wt.to(DEV), False)
+    eng.bias["c"] = b
+    xa = _to_act(x)
+    y = eng.convf(xa, "c", stride=stride, dilation=dil, bias=True, act=4)
+    ref = F.leaky_relu(F.conv2d(_from_act(xa).double(), wt.to(DEV).double(), b.double(), stride, dil * (k // 2), dil), 0.01)
+    err = float((_from_act(y).double() - ref).abs().max())
+    print(f"{cin}->{cout} k{k} s{stride} d{dil} @{h}x{w}: max abs err {err:.2e}")
+    assert err < 2e-4 * max(1.0, float(ref.abs().max()))
+
+
+def test_stem_7x7_chain():
+    from tcvom_b200 import _cabi
+    eng = _engine()
+    x = torch.randn(2, 11, 34, 46)
+    wt = torch.randn(64, 11, 7, 7) * 0.05
+    eng._pack_fba(_cabi.lib(), eng._stream_ptr(), "stem", wt.to(DEV), False)
+    xa = _to_act(x, 16)
+    y = eng.conv7x7s2(xa, "stem")
+    ref = F.conv2d(_from_act(xa, 11), wt.to(DEV), None, 2, 3)
+    assert float((_from_act(y) - ref).abs().max()) < 2e-4
+
+
+# ------------------------------------------------------------------------------------------ input encoding
+@pytest.mark.parametrize("u8", [True, False])
+def test_input_encoding_matches_reference(u8):
+    from tcvom_b200.engine import Act
+    g = golden("fba_ring64.npz")
+    eng = _engine()
+    imgs, tris = torch.from_numpy(g["imgs"]).to(DEV), torch.from_numpy(g["tris"]).to(DEV)
+    if not u8:
+        imgs, tris = imgs.float(), tris.float()
+    B, S, _, H, W = imgs.shape
+    x16 = Act.empty(B * S, H, W, 16, torch.device(DEV))
+    eng.encode_inputs(imgs.contiguous(), tris.contiguous(), B * S, H, W, x16)
+    got = _from_act(x16).cpu()
+    ref = torch.from_numpy(g["x11"]).reshape(B * S, 11, H, W)
+    assert float((got[:, :11] - ref).abs().max()) < 2e-5
+    assert float(got[:, 14:].abs().max()) == 0
+
+
+def test_distance_transform_vs_oracle_large():
+    """1088 x 1920 trimaps with far-apart seeds: the exact transform against scipy's (the oracle's)."""
+    from tcvom_b200.engine import Act
+    from tcvom_b200 import synthetic
+    eng = _engine()
+    H, W = 1088, 1920
+    _, tris = synthetic.make_window(H, W, seed=3)
+    tris = torch.from_numpy(tris[0])                       # [3,1,H,W]
+    tris[2] = 128
+    tris[2, 0, 500, 1500] = 255                            # one fg pixel, no bg at all
+    imgs = torch.zeros(3, 3, H, W, dtype=torch.uint8)
+    x16 = Act.empty(3, H, W, 16, torch.device(DEV))
+    eng.encode_inputs(imgs.to(DEV), tris.to(DEV), 3, H, W, x16)
+    got = _from_act(x16).cpu()
+    _, x11, _, _ = O.eval_preprocess(imgs[None].float(), tris[None].float())
+    assert float((got[:, 3:11] - x11[0, :, 3:11]).abs().max()) < 2e-5
+    assert float(got[2, 3:6].abs().max()) == 0
+
+
+# ------------------------------------------------------------------------------------------ whole model
+@pytest.mark.parametrize("case", CASES)
+def test_eval_forward_matches_reference_golden(case):
+    g = golden(f"fba_{case}.npz")
+    dil = int(g["dilate"])
+    m = _model(None if dil < 0 else dil)
+    imgs = torch.from_numpy(g["imgs"]).to(DEV)             # uint8 ingest
+    tris = torch.from_numpy(g["tris"]).to(DEV)
+    with torch.no_grad():
+        alphas, Fs, Bs = m(imgs, tris)
+    plan = list(m.NET.engine().plans.values())[0]
+    assert np.array_equal(plan.io["trimask"].reshape(g["trimask"].shape).cpu().numpy().astype(np.uint8), g["trimask"])
+    err = lambda a, b: float(np.abs(a.cpu().numpy() - b.astype(np.float32)).max())
+    ea = err(alphas, g["alphas"])
+    print(case, "alpha max abs err", ea, "F", err(Fs[:, 1], g["Fs"]), "B", err(Bs[:, 1], g["Bs"]))
+    assert ea < ALPHA_TOL
+    assert err(plan.io["pred"][:, 0], g["pred1"]) < ALPHA_TOL
+    assert err(Fs[:, 1], g["Fs"]) < 2e-3 and err(Bs[:, 1], g["Bs"]) < 2e-3      # golden stored as fp16
+    assert np.array_equal(plan.io["small_mask"][:, 0].bool().cpu().numpy(), g["small_mask1"])
+    for k, ref in (("attb", g["attb1"]), ("attf", g["attf1"])):
+        assert err(plan.io[k][:, 0], ref) <= 3e-3 * max(1.0, float(np.abs(ref.astype(np.float32)).max()))
+    assert float(alphas[:, 0].abs().max()) == 0 and float(alphas[:, -1].abs().max()) == 0
+
+
+def test_eval_forward_float_ingest_and_graph_replay():
+    g = golden("fba_ring64.npz")
+    m = _model()
+    imgs, tris = torch.from_numpy(g["imgs"]).to(DEV), torch.from_numpy(g["tris"]).to(DEV)
+    with torch.no_grad():
+        a1 = m(imgs, tris)[0].clone()
+        a2 = m(imgs, tris)[0].clone()                      # CUDA-graph replay of the recorded plan
+        a3 = m(imgs.float(), tris.float())[0].clone()      # fp32 ingest: same numbers
+        a4 = m(imgs.flip(-1).contiguous(), tris.flip(-1).contiguous())[0]
+    assert torch.equal(a1, a2) and torch.equal(a1, a3)
+    assert not torch.equal(a1, a4)
+
+
+def test_vmn_seam_matches_oracle():
+    """models.VMN.get_VMN_models('vmn_fba') called the way models/model.py:401-406 does."""
+    import tcvom_b200
+    from tcvom_b200 import synthetic
+    sd = fixture_sd_fba()
+    net = tcvom_b200.get_VMN_models("vmn_fba", agg_window=7)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(DEV).eval()
+    imgs, tris = synthetic.make_window(64, 96, seed=5)
+    ti, tt = torch.from_numpy(imgs).float(), torch.from_numpy(tris).float()
+    scaled, x11, trimask, trimap2 = O.eval_preprocess(ti, tt)
+    S = 3
+    frames = [x11[:, i] for i in range(S)]
+    masks = [trimask[:, i] for i in range(S)]
+    extras = [(scaled[:, i], trimap2[:, i]) for i in range(S)]
+    with torch.no_grad():
+        ref = O.vmn_forward(sd, frames, masks, extras, 7)
+        inputs = [f.unsqueeze(1).to(DEV) for f in frames]
+        out = net(inputs, tuple(mk.unsqueeze(1).to(DEV) for mk in masks),
+                  extras=[[e[0].to(DEV), e[1].to(DEV)] for e in extras])
+    assert out[0][0].shape == (1, 7, 64, 96) and float(out[0][0].abs().max()) == 0
+    assert float((out[0][1].cpu() - ref[0][1]).abs().max()) < ALPHA_TOL
+    assert torch.equal(out[3][1].cpu(), ref[3][1])
+    with pytest.raises(ValueError):
+        net([f.unsqueeze(1).to(DEV) for f in frames], tuple(mk.unsqueeze(1).to(DEV) for mk in masks))
+
+
+def test_eval_forward_256_vs_oracle():
+    from tcvom_b200 import synthetic
+    m = _model()
+    imgs, tris = synthetic.make_window(256, 256, seed=11)
+    ti, tt = torch.from_numpy(imgs), torch.from_numpy(tris)
+    with torch.no_grad():
+        alphas, Fs, Bs = m(ti.to(DEV), tt.to(DEV))
+        ra, rF, rB = O.eval_forward(fixture_sd_fba(), ti.float(), tt.float())
+    ea = float((alphas.cpu() - ra).abs().max())
+    print("256x256 alpha max abs err vs oracle", ea)
+    assert ea < ALPHA_TOL
+    assert float((Fs.cpu() - rF).abs().max()) < ALPHA_TOL and float((Bs.cpu() - rB).abs().max()) < ALPHA_TOL
