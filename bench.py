@@ -28,6 +28,7 @@ H, W, S = 1088, 1920, 3
 METRIC = "1080p 3-frame windows/sec (GCA+TAM forward)"
 UNIT = "windows/s"
 GFLOP_PER_WINDOW = 3843.57          # BASELINE.md section 2 (FlopCounterMode on the reference)
+FBA_GFLOP_PER_WINDOW = 7111.6       # EvalModel('vmn_fba') at 1088x1920 (223.1 GFLOP @256^2)
 
 
 def window_gflop(h, w):
@@ -222,6 +223,60 @@ def run_train_section(args, rank, world, dev, barrier, max_over_ranks):
                 peak_mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30)
 
 
+def run_fba_section(args, rank, world, dev, max_over_ranks):
+    """Secondary measurement: EvalModel('vmn_fba') forward on one 1088x1920 3-frame window per GPU (BASELINE.json
+    configs[4], the second base network behind the same plugin seam).  Inputs resident in HBM, CUDA-graph replay;
+    reported next to, not instead of, the headline metric.  A failure on a rank is reported, not raised (the
+    collective below must still be entered by every rank)."""
+    import torch
+    import tcvom_b200
+    from tcvom_b200 import synthetic
+    from helpers import fixture_sd_fba
+    ms_local, info, err = -1.0, {}, None
+    try:
+        model = tcvom_b200.EvalModel(model="vmn_fba", agg_window=7, dilate_kernel=None)
+        model.NET.load_state_dict(fixture_sd_fba(), strict=True)
+        model = model.to(dev).eval()
+        imgs_np, tris_np = synthetic.make_window(H, W, seed=7 + rank)
+        imgs, tris = torch.from_numpy(imgs_np).to(dev), torch.from_numpy(tris_np).to(dev)
+        steps = 5
+        with torch.no_grad():
+            out = model(imgs, tris)
+            plan = list(model.NET.engine().plans.values())[0]
+            for _ in range(3):
+                model.run_plan(plan)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                model.run_plan(plan)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms_local = e0.elapsed_time(e1) / steps
+            kinds = {}
+            if rank == 0:
+                plan.replay_timed(dev)
+                for m, t in zip(plan.meta, plan.replay_timed(dev)):
+                    kinds[m["kind"]] = kinds.get(m["kind"], 0.0) + t
+            info = dict(gpu_launches_per_window=plan.n_launch, steps=steps, warmup=3,
+                        peak_mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+                        finite=bool(torch.isfinite(out[0]).all()),
+                        breakdown_ms={k: round(v, 3) for k, v in sorted(kinds.items(), key=lambda kv: -kv[1])})
+        model.NET.engine().plans.clear()
+        del plan, model
+        torch.cuda.empty_cache()
+    except Exception as e:                                     # noqa: BLE001 - reported in the JSON line
+        err = f"{type(e).__name__}: {e}"
+    ms = max_over_ranks(ms_local)
+    any_failed = max_over_ranks(1.0 if (err is not None or ms_local < 0) else 0.0) > 0
+    if any_failed:
+        return dict(workload="FBA+TAM forward 1080p (configs[4])", error=err or "failed on another rank")
+    return dict(workload="FBA+TAM forward-only 1080p 3-frame window, batch 1 per GPU (configs[4]; reference FLOP count "
+                         f"{FBA_GFLOP_PER_WINDOW:.1f} GFLOP/window, convolutions only)",
+                ms_per_window=ms, windows_per_s=world * 1e3 / ms,
+                algorithmic_tflops=FBA_GFLOP_PER_WINDOW / ms, **info)
+
+
 # ------------------------------------------------------------------------------------- native arm
 def run_native(args, rank, world, local_rank):
     import torch
@@ -349,6 +404,12 @@ def run_native(args, rank, world, local_rank):
         torch.cuda.empty_cache()
         train = run_train_section(args, rank, world, dev, barrier, max_over_ranks)
 
+    fba = None
+    if not args.no_fba:
+        model.NET.engine().plans.clear()
+        torch.cuda.empty_cache()
+        fba = run_fba_section(args, rank, world, dev, max_over_ranks)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -376,7 +437,7 @@ def run_native(args, rank, world, local_rank):
                 e2e=dict(value=e2e_value, unit=UNIT, ms_per_step=ms_e2e / args.steps,
                          h2d_bytes_per_step=imgs_u8.numel() + tris_u8.numel(), input_dtype="uint8",
                          d2h_bytes_per_step=out_h.numel() * 4),
-                gpu_launches=launches, roofline=roof, cpu_baseline=cpu, train_step=train)
+                gpu_launches=launches, roofline=roof, cpu_baseline=cpu, train_step=train, fba_forward=fba)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -390,6 +451,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
+    ap.add_argument("--no-fba", action="store_true", help="skip the secondary FBA+TAM forward measurement (configs[4])")
     ap.add_argument("--dump-calls", default=None, help="write the per-launch timing table (JSON lines) here")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -418,6 +418,7 @@ int tcv_losses_vmd_bwd(const float* pred, const float* trimask, const float* gts
  * Reference semantics replaced:
  *   tcv_ws_pack               models/FBA/layers_WS.py:13-23    Conv2d.forward (weight standardisation)
  *   tcv_gn_*                  models/FBA/layers_WS.py:26-27, models/FBA/models.py:239-243   nn.GroupNorm(32, C)
+ *   tcv_space_to_depth2, tcv_s2d_pack_stem   models/FBA/resnet_GN_WS.py:98 (the 7x7 stem conv, with tcv_conv2d)
  *   tcv_maxpool3s2            models/FBA/resnet_GN_WS.py:102   nn.MaxPool2d(3, 2, 1) (indices unused by the decoder)
  *   tcv_adaptive_avgpool      models/FBA/models.py:264         nn.AdaptiveAvgPool2d(scale) of the pyramid pooling
  *   tcv_bilinear              models/VMN/VMN_FBA.py:27-30,36,41,46   F.interpolate(bilinear, align_corners=False)
@@ -465,6 +466,14 @@ int tcv_bilinear(const void* x, int n, int ih, int iw, int c, void* y, long long
 /* y[p][y_off + ch] = x[p][x_off + ch], ch < c, p < pixels (rows of x_c / y_c elements; planes 0: pixels*row) */
 int tcv_copy_channels(const void* x, long long x_plane, int x_c, int x_off, void* y, long long y_plane, int y_c,
                       int y_off, int c, long long pixels, tcv_stream_t stream);
+
+/* The 7x7 / stride-2 / pad-3 stem (resnet_GN_WS.py:98) as a 4x4 / stride-1 convolution (taps -2..1) over the 2x2
+ * space-to-depth image, so that it runs as ONE 16-tap tcgen05 launch of tcv_conv2d:
+ *  space_to_depth2: x [n,h,w,c] (h, w even) -> y dense [n,h/2,w/2,4c], y[.., (py*2+px)*c + ch] = x[2Y+py, 2X+px, ch]
+ *  s2d_pack_stem:   packed 7x7 weights fp32 [49][cin_pad][cout] -> fp32 [16][4*cin_pad][cout], tap (ty+2)*4+(tx+2),
+ *                   row (py*2+px)*cin_pad + c = w[ky = 2ty+py+3][kx = 2tx+px+3][c] (zero outside the 7x7 support) */
+int tcv_space_to_depth2(const void* x, long long x_plane, int n, int h, int w, int c, void* y, tcv_stream_t stream);
+int tcv_s2d_pack_stem(const float* w49, int cin_pad, int cout, float* out, tcv_stream_t stream);
 
 /* EvalModel.preprocess for 'fba'.  imgs [F,3,H,W] BGR 0..255 and tris [F,1,H,W] (fp32, or uint8 when is_u8) ->
  * x16 split-bf16 [F,H,W,16]: ch 0..2 normalised RGB, 9 = (tri*1/255 == 0), 10 = (tri*1/255 == 1), 11..13 RGB/255

@@ -280,6 +280,20 @@ int tcv_fba_fusion(const void* o8, const void* x16, long long x16_plane, long lo
   return launch_body<FusionP, fba_fusion_body>(p, (ll)n * h * w, S(stream), "fba_fusion_kernel");
 }
 
+int tcv_space_to_depth2(const void* x, long long x_plane, int n, int h, int w, int c, void* y, tcv_stream_t stream) {
+  TCV_REQUIRE(x && y && n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0 && c % 8 == 0,
+              "space_to_depth2: bad arguments");
+  if (x_plane == 0) x_plane = (long long)n * h * w * c;
+  S2dP p{CU16(x), x_plane, n, h, w, c, U16(y)};
+  return launch_body<S2dP, space_to_depth2_body>(p, (ll)n * h * w * (c / 8), S(stream), "space_to_depth2_kernel");
+}
+
+int tcv_s2d_pack_stem(const float* w49, int cin_pad, int cout, float* out, tcv_stream_t stream) {
+  TCV_REQUIRE(w49 && out && cin_pad > 0 && cout > 0, "s2d_pack_stem: bad arguments");
+  S2dPackP p{w49, cin_pad, cout, out};
+  return launch_body<S2dPackP, s2d_pack_stem_body>(p, (ll)16 * 4 * cin_pad * cout, S(stream), "s2d_pack_stem_kernel");
+}
+
 int tcv_postprocess_eval_fba(const float* pred, const void* imgs, const void* tris, int is_u8, const float* trimask,
                              int batch, int frames, int h, int w, float* alphas, float* Fs, float* Bs,
                              tcv_stream_t stream) {

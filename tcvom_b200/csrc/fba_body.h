@@ -464,4 +464,57 @@ TCV_HD void postprocess_fba_body(ll i, const PostP& p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------ 7x7 / stride-2 stem on the tensor cores
+// A k=7, s=2, p=3 convolution over c channels equals a k=4, s=1 convolution (taps -2..1) over the 2x2
+// space-to-depth image with 4c channels: input row 2*oy + ky - 3 = 2*(oy + ty) + py with ty = floor((ky-3)/2),
+// py = (ky-3) mod 2.  For the 16-channel FBA input that is ONE 16-tap, K = 1024 tcgen05 launch instead of four
+// CUDA-core launches.
+struct S2dP {
+  const uint16_t* x;
+  ll x_plane;
+  int n, h, w, c;  // h, w even
+  uint16_t* y;     // dense [n, h/2, w/2, 4c], channel (py*2+px)*c + ch
+};
+// work item = 8 channels of one input pixel; total = n*h*w*c/8
+TCV_HD void space_to_depth2_body(ll i, const S2dP& p) {
+  const int cv = p.c / 8;
+  const int ch = (int)(i % cv) * 8;
+  ll t = i / cv;
+  const int x = (int)(t % p.w);
+  t /= p.w;
+  const int y = (int)(t % p.h);
+  const int img = (int)(t / p.h);
+  const int oh = p.h / 2, ow = p.w / 2;
+  const ll yplane = (ll)p.n * oh * ow * 4 * p.c;
+  const uint16_t* s = p.x + (((ll)img * p.h + y) * p.w + x) * p.c + ch;
+  uint16_t* d = p.y + (((ll)img * oh + (y >> 1)) * ow + (x >> 1)) * (4 * p.c) + ((y & 1) * 2 + (x & 1)) * p.c + ch;
+#ifdef __CUDA_ARCH__
+  *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(s);
+  *reinterpret_cast<uint4*>(d + yplane) = *reinterpret_cast<const uint4*>(s + p.x_plane);
+#else
+  for (int k = 0; k < 8; ++k) {
+    d[k] = s[k];
+    d[k + yplane] = s[k + p.x_plane];
+  }
+#endif
+}
+
+struct S2dPackP {
+  const float* w49;  // packed 7x7 weights [49][cin_pad][cout]
+  int cin_pad, cout;
+  float* out;        // [16][4*cin_pad][cout], tap t = (ty+2)*4 + (tx+2)
+};
+// work item = one output element; total = 16 * 4*cin_pad * cout
+TCV_HD void s2d_pack_stem_body(ll i, const S2dPackP& p) {
+  const int co = (int)(i % p.cout);
+  const int ch = (int)((i / p.cout) % (4 * p.cin_pad));
+  const int t = (int)(i / ((ll)p.cout * 4 * p.cin_pad));
+  const int ty = t / 4 - 2, tx = t % 4 - 2;
+  const int q = ch / p.cin_pad, c = ch % p.cin_pad;
+  const int ky = 2 * ty + (q >> 1) + 3, kx = 2 * tx + (q & 1) + 3;
+  float v = 0.f;
+  if (ky >= 0 && ky < 7 && kx >= 0 && kx < 7) v = p.w49[((ll)(ky * 7 + kx) * p.cin_pad + c) * p.cout + co];
+  p.out[i] = v;
+}
+
 }  // namespace tcv_fba

@@ -14,6 +14,7 @@ a concatenation buffer fused into the last pass).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -26,6 +27,14 @@ from .fba_modules import GN_GROUPS, PPM_SCALES, RES_LAYERS, block_config
 GN_EPS = 1e-5
 # decoder convolutions that are layers_WS.Conv2d (FBA/models.py:263-292); conv_up4.* and fam.* are plain nn.Conv2d
 _WS_DECODER = ("decoder.ppm.", "decoder.conv_up1.", "decoder.conv_up2.", "decoder.conv_up3.")
+
+
+# channel padding beyond the kernels' minimum: conv_up4.2 (32 -> 16) is computed as 32 -> 32 with zero weights / bias
+# for the extra outputs so that it runs on the narrow-layer tcgen05 kernel instead of the CUDA cores; conv_up4.4 then
+# reads 32 channels (zero weights for the padding)
+_PAD_OVERRIDE = {"decoder.conv_up4.2": dict(cout_pad=32), "decoder.conv_up4.4": dict(cin_pad=32)}
+STEM = "encoder.conv1"
+STEM_S2D = STEM + "#s2d"
 
 
 def _round_up(v: int, m: int) -> int:
@@ -92,6 +101,8 @@ class FbaVmnEngine(GcaVmnEngine):
         cout, cin, kh, kw = w.shape
         cin_pad = _round_up(cin, 8) if cin <= 32 else _round_up(cin, 32)
         cout_pad = _round_up(cout, 8)
+        ov = _PAD_OVERRIDE.get(p, {})
+        cin_pad, cout_pad = ov.get("cin_pad", cin_pad), ov.get("cout_pad", cout_pad)
         ent = self.w.get(p)
         if ent is None:
             ent = self.w[p] = dict(w=torch.empty((kh * kw, cin_pad, cout_pad), dtype=torch.float32, device=w.device),
@@ -102,6 +113,17 @@ class FbaVmnEngine(GcaVmnEngine):
             if "w_tc" not in ent:
                 ent["w_tc"] = torch.empty((2, kh * kw, cout_pad, cin_pad), dtype=torch.bfloat16, device=w.device)
             _cabi.check(L.tcv_pack_weight_tc(ent["w"].data_ptr(), kh * kw, cin_pad, cout_pad, ent["w_tc"].data_ptr(), st),
+                        "pack_weight_tc")
+        if p == STEM and kh == 7:
+            # the stem as a 16-tap 4x4 convolution over the 2x2 space-to-depth input (tcgen05 path)
+            e2 = self.w.get(STEM_S2D)
+            if e2 is None:
+                e2 = self.w[STEM_S2D] = dict(
+                    w=torch.empty((16, 4 * cin_pad, cout_pad), dtype=torch.float32, device=w.device),
+                    w_tc=torch.empty((2, 16, cout_pad, 4 * cin_pad), dtype=torch.bfloat16, device=w.device),
+                    cout=cout_pad, cout_real=cout, cin=4 * cin_pad, cin_real=4 * cin_pad, k=4, transposed=False)
+            _cabi.check(L.tcv_s2d_pack_stem(ent["w"].data_ptr(), cin_pad, cout_pad, e2["w"].data_ptr(), st), "s2d_pack_stem")
+            _cabi.check(L.tcv_pack_weight_tc(e2["w"].data_ptr(), 16, 4 * cin_pad, cout_pad, e2["w_tc"].data_ptr(), st),
                         "pack_weight_tc")
 
     # ------------------------------------------------------------------ operators
@@ -119,9 +141,28 @@ class FbaVmnEngine(GcaVmnEngine):
         self._call("tcv_conv2d", C.byref(d), meta=self._conv_meta(d, wkey, x, k, stride))
         return y
 
+    def stem_s2d(self, x: Act, wkey: str = STEM) -> Act:
+        """The 7x7 / stride-2 / pad-3 stem (resnet_GN_WS.py:98) on the tensor cores: 2x2 space-to-depth of the
+        16-channel input, then ONE 16-tap (4x4, offsets -2..1) stride-1 convolution with K = 16 * 64."""
+        key = wkey + "#s2d"
+        ent = self.w[key]
+        assert x.h % 2 == 0 and x.w % 2 == 0 and ent["cin"] == 4 * x.c
+        oh, ow, cout = x.h // 2, x.w // 2, ent["cout"]
+        xs = self._act(x.n, oh, ow, 4 * x.c)
+        self._call("tcv_space_to_depth2", x.ptr, x.plane, x.n, x.h, x.w, x.c, xs.ptr,
+                   meta=dict(kind="tcv_space_to_depth2", bytes=8 * x.n * x.img_elems))
+        taps = [(ty, tx) for ty in range(-2, 2) for tx in range(-2, 2)]
+        y = self._act(x.n, oh, ow, cout)
+        d = self._desc(xs, ent["w"].data_ptr(), taps, 1, PAD_ZERO, y, oh, ow, cout, oh, ow, 1, 0, 1, 0, key, None,
+                       False, ACT_NONE, None, 0, None, None, 0)
+        meta = self._conv_meta(d, key, xs, 4, 1)
+        meta.update(flops=2 * x.n * oh * ow * 49 * self.w[wkey]["cin_real"] * self.w[wkey]["cout_real"], layer=wkey)
+        self._call("tcv_conv2d", C.byref(d), meta=meta)
+        return y
+
     def conv7x7s2(self, x: Act, wkey: str) -> Act:
-        """The 7x7 / stride-2 / pad-3 stem (resnet_GN_WS.py:98) as four partial convolutions of <= 14 taps each
-        (tcv_conv2d takes at most 16 taps), chained through the residual input of the epilogue."""
+        """The same stem as four partial CUDA-core convolutions of <= 14 taps each (tcv_conv2d takes at most 16 taps),
+        chained through the residual input of the epilogue.  Kept as the cross-check of stem_s2d (TCV_FBA_STEM=direct)."""
         ent = self.w[wkey]
         cout = ent["cout"]
         assert ent["k"] == 7 and ent["cin"] == x.c
@@ -193,7 +234,8 @@ class FbaVmnEngine(GcaVmnEngine):
     def per_frame(self, x16: Act) -> dict:
         """encoder + pyramid-pooling head for all frames at once (VMN_model.py:93-98)."""
         e, d = "encoder", "decoder"
-        c1 = self.gn(self.conv7x7s2(x16, e + ".conv1"), e + ".bn1", ACT_RELU)            # conv_out[1], OS2, 64 ch
+        stem = self.conv7x7s2 if os.environ.get("TCV_FBA_STEM", "s2d") == "direct" else self.stem_s2d
+        c1 = self.gn(stem(x16, e + ".conv1"), e + ".bn1", ACT_RELU)                      # conv_out[1], OS2, 64 ch
         x = self.maxpool(c1)
         l1 = None
         cat = None

@@ -337,6 +337,18 @@ int tcv_fba_fusion(const void* o8, const void* x16, long long x16_plane, long lo
   return run_body<FusionP, fba_fusion_body>(p, (ll)n * h * w);
 }
 
+int tcv_space_to_depth2(const void* x, long long x_plane, int n, int h, int w, int c, void* y, tcv_stream_t) {
+  REQ(h % 2 == 0 && w % 2 == 0 && c % 8 == 0, "space_to_depth2: dims");
+  if (x_plane == 0) x_plane = (ll)n * h * w * c;
+  S2dP p{(const uint16_t*)x, x_plane, n, h, w, c, (uint16_t*)y};
+  return run_body<S2dP, space_to_depth2_body>(p, (ll)n * h * w * (c / 8));
+}
+
+int tcv_s2d_pack_stem(const float* w49, int cin_pad, int cout, float* out, tcv_stream_t) {
+  S2dPackP p{w49, cin_pad, cout, out};
+  return run_body<S2dPackP, s2d_pack_stem_body>(p, (ll)16 * 4 * cin_pad * cout);
+}
+
 int tcv_postprocess_eval_fba(const float* pred, const void* imgs, const void* tris, int is_u8, const float* trimask,
                              int batch, int frames, int h, int w, float* alphas, float* Fs, float* Bs, tcv_stream_t) {
   PostP p{pred, imgs, tris, is_u8, trimask, batch, frames, h, w, alphas, Fs, Bs};

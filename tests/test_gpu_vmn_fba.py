@@ -128,8 +128,10 @@ def test_weight_standardisation_pack():
     (1024, 2048, 1, 1, 1, 8, 10, 1),      # widest 1x1
     (320, 64, 3, 1, 1, 32, 32, 1),        # conv_up3.0
     (96, 32, 3, 1, 1, 64, 64, 1),         # conv_up4.0
-    (32, 16, 3, 1, 1, 40, 48, 1),         # conv_up4.2 (CUDA cores)
-    (16, 8, 1, 1, 1, 40, 48, 1),          # conv_up4.4 (CUDA cores)
+    (32, 16, 3, 1, 1, 40, 48, 1),         # conv_up4.2 unpadded (CUDA cores)
+    (32, 32, 3, 1, 1, 40, 48, 1),         # conv_up4.2 as shipped: outputs padded to 32 (narrow-layer tcgen05 kernel)
+    (16, 8, 1, 1, 1, 40, 48, 1),          # conv_up4.4 unpadded (CUDA cores)
+    (32, 8, 1, 1, 1, 40, 48, 1),          # conv_up4.4 as shipped (CUDA cores)
 ])
 def test_fba_conv_shapes(cin, cout, k, stride, dil, h, w, n):
     from tcvom_b200 import _cabi
@@ -146,6 +148,25 @@ def test_fba_conv_shapes(cin, cout, k, stride, dil, h, w, n):
     err = float((_from_act(y).double() - ref).abs().max())
     print(f"{cin}->{cout} k{k} s{stride} d{dil} @{h}x{w}: max abs err {err:.2e}")
     assert err < 2e-4 * max(1.0, float(ref.abs().max()))
+
+
+def test_stem_space_to_depth_tc():
+    """The shipped stem: 2x2 space-to-depth + one 16-tap tcgen05 convolution, against fp64 torch and the chained
+    CUDA-core version."""
+    from tcvom_b200 import _cabi
+    from tcvom_b200.fba_engine import STEM
+    eng = _engine()
+    torch.manual_seed(5)
+    x = torch.randn(2, 11, 36, 44)
+    wt = torch.randn(64, 11, 7, 7) * 0.05
+    eng._pack_fba(_cabi.lib(), eng._stream_ptr(), STEM, wt.to(DEV), True)
+    xa = _to_act(x, 16)
+    y = eng.stem_s2d(xa, STEM)
+    ref = F.conv2d(_from_act(xa, 11).double(), O.ws_weight(wt).to(DEV).double(), None, 2, 3)
+    err = float((_from_act(y).double() - ref).abs().max())
+    print("s2d stem max abs err", err)
+    assert err < 2e-4 * max(1.0, float(ref.abs().max()))
+    assert float((_from_act(eng.conv7x7s2(xa, STEM)).double() - ref).abs().max()) < 2e-4 * max(1.0, float(ref.abs().max()))
 
 
 def test_stem_7x7_chain():

@@ -171,6 +171,25 @@ def test_conv_double_matches_torch(emu):
     assert float((from_act(y) - ref).abs().max()) < 1e-4
 
 
+def test_stem_space_to_depth_matches_torch(emu):
+    """7x7 / stride 2 / pad 3 == 4x4 / stride 1 (taps -2..1) over the 2x2 space-to-depth image (the tcgen05 stem)."""
+    from tcvom_b200 import _cabi
+    from tcvom_b200.fba_engine import STEM
+    eng = make_engine()
+    torch.manual_seed(3)
+    x = torch.randn(2, 11, 12, 18)
+    xa = to_act(x, 16)
+    w = torch.randn(64, 11, 7, 7) * 0.05
+    eng._pack_fba(_cabi.lib(), 0, STEM, w, True)
+    y = eng.stem_s2d(xa, STEM)
+    from oracle import vmn_fba_oracle as O
+    ref = F.conv2d(from_act(xa, 11), O.ws_weight(w), None, 2, 3)
+    assert tuple(y.buf.shape[1:]) == (2, 6, 9, 64)
+    tol = 2e-5 * max(1.0, float(ref.abs().max()))           # split-bf16 storage: 2^-17 relative
+    assert float((from_act(y) - ref).abs().max()) < tol
+    assert float((from_act(eng.conv7x7s2(xa, STEM)) - ref).abs().max()) < tol
+
+
 # ------------------------------------------------------------------------------------------ input encoding
 @pytest.mark.parametrize("name", ["fba_ring64.npz"])
 def test_input_encoding_matches_reference(emu, name):
