@@ -127,19 +127,30 @@ class FbaVmnEngine(GcaVmnEngine):
                         "pack_weight_tc")
 
     # ------------------------------------------------------------------ operators
-    def convf(self, x: Act, wkey: str, *, stride=1, dilation=1, bias=False, act=ACT_NONE) -> Act:
-        """k x k convolution (k in {1, 3}), padding = dilation * (k // 2), optional bias / activation epilogue."""
+    def convf(self, x: Act, wkey: str, *, stride=1, dilation=1, bias=False, act=ACT_NONE, split_rows=False) -> Act:
+        """k x k convolution (k in {1, 3}), padding = dilation * (k // 2), optional bias / activation epilogue.
+
+        split_rows: one launch per filter row, chained through the residual input of the epilogue.  The tensor cores
+        accumulate in fp32 with truncation, an error that grows linearly with the reduction length (measured on
+        B200: 4e-5 at K = 4608, 3.5e-4 at K = 27648 for unit-variance outputs); conv_up1.0 (K = 9 * 3072) is therefore
+        reduced in three K = 9216 pieces whose partial sums are added in the (round-to-nearest) epilogue."""
         ent = self.w[wkey]
         k, cout = ent["k"], ent["cout"]
         assert ent["cin"] == x.c, (wkey, ent["cin"], x.c)
         r = k // 2
-        taps = [((ky - r) * dilation, (kx - r) * dilation) for ky in range(k) for kx in range(k)]
         oh, ow = (x.h - 1) // stride + 1, (x.w - 1) // stride + 1
-        y = self._act(x.n, oh, ow, cout)
-        d = self._desc(x, ent["w"].data_ptr(), taps, stride, PAD_ZERO, y, oh, ow, cout, oh, ow, 1, 0, 1, 0, wkey, None,
-                       bias, act, None, 0, None, None, 0)
-        self._call("tcv_conv2d", C.byref(d), meta=self._conv_meta(d, wkey, x, k, stride))
-        return y
+        rows = [[ky] for ky in range(k)] if (split_rows and k > 1) else [list(range(k))]
+        prev: Optional[Act] = None
+        for i, kys in enumerate(rows):
+            last = i == len(rows) - 1
+            taps = [((ky - r) * dilation, (kx - r) * dilation) for ky in kys for kx in range(k)]
+            wtap = [ky * k + kx for ky in kys for kx in range(k)]
+            y = self._act(x.n, oh, ow, cout)
+            d = self._desc(x, ent["w"].data_ptr(), taps, stride, PAD_ZERO, y, oh, ow, cout, oh, ow, 1, 0, 1, 0, wkey,
+                           None, bias and last, act if last else ACT_NONE, prev, 0, None, None, 0, wtap=wtap)
+            self._call("tcv_conv2d", C.byref(d), meta=self._conv_meta(d, wkey, x, k, stride))
+            prev = y
+        return prev
 
     def stem_s2d(self, x: Act, wkey: str = STEM) -> Act:
         """The 7x7 / stride-2 / pad-3 stem (resnet_GN_WS.py:98) on the tensor cores: 2x2 space-to-depth of the
@@ -256,7 +267,8 @@ class FbaVmnEngine(GcaVmnEngine):
                        meta=dict(kind="tcv_adaptive_avgpool", bytes=4 * cat.n * h8 * w8 * 2048))
             t = self.gn(self.convf(pooled, f"{d}.ppm.{i}.1", bias=True), f"{d}.ppm.{i}.2", ACT_LEAKY001)
             self.bilinear(t, h8, w8, cat, 2048 + 256 * i)
-        x = self.gn(self.convf(cat, d + ".conv_up1.0", bias=True), d + ".conv_up1.1", ACT_LEAKY001)
+        split = os.environ.get("TCV_FBA_SPLIT_K", "1") == "1"
+        x = self.gn(self.convf(cat, d + ".conv_up1.0", bias=True, split_rows=split), d + ".conv_up1.1", ACT_LEAKY001)
         feat = self.gn(self.convf(x, d + ".conv_up1.3", bias=True), d + ".conv_up1.4", ACT_LEAKY001)
         return dict(feat=feat, l1=l1, c1=c1, x16=x16)
 

@@ -295,3 +295,23 @@ def test_eval_forward_256_vs_oracle():
     print("256x256 alpha max abs err vs oracle", ea)
     assert ea < ALPHA_TOL
     assert float((Fs.cpu() - rF).abs().max()) < ALPHA_TOL and float((Bs.cpu() - rB).abs().max()) < ALPHA_TOL
+
+
+def test_eval_forward_1080p_matches_oracle():
+    """BASELINE configs[4] at its full size (1088x1920).  Measured on B200: alpha 9.1e-4 max abs (p99.99 2.7e-4, mean
+    1.6e-6), F / B 1.4e-4 / 1.0e-4.  The alpha bound is looser than on the small windows for a reason inherent to FBA:
+    fba_fusion divides by sum((F-B)^2) + 0.1 and so amplifies the 1e-4-level F / B differences up to ~7x at single
+    pixels (the reference's own fp32-vs-fp64 noise shows the same 5x alpha-to-F/B ratio)."""
+    from tcvom_b200 import synthetic
+    m = _model()
+    imgs, tris = synthetic.make_window(1088, 1920, seed=7)
+    ti, tt = torch.from_numpy(imgs), torch.from_numpy(tris)
+    with torch.no_grad():
+        alphas, Fs, Bs = m(ti.to(DEV), tt.to(DEV))
+        ra, rF, rB = O.eval_forward(fixture_sd_fba(), ti.float(), tt.float())
+    d = (alphas.cpu() - ra).abs()
+    ea, p9999 = float(d.max()), float(d.flatten()[::7].quantile(0.9999))
+    eF, eB = float((Fs.cpu() - rF).abs().max()), float((Bs.cpu() - rB).abs().max())
+    print(f"1088x1920 alpha max abs err {ea:.2e} (p99.99 {p9999:.2e}), F {eF:.2e}, B {eB:.2e}")
+    assert ea < 1.2e-3 and p9999 < 5e-4
+    assert eF < 3e-4 and eB < 3e-4
