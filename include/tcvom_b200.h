@@ -484,7 +484,8 @@ int tcv_fba_encode_inputs(const void* imgs, const void* tris, int is_u8, int fra
 /* exact squared Euclidean distance to the nearest seed pixel of channel 9 (k = 0) / 10 (k = 1) of x16, separable:
  *  cols: g int32 [F][2][H][W] = vertical distance to the nearest seed of the same column (1 << 20: none)
  *  rows: d2 = min_x' (x-x')^2 + g[y][x']^2 ; x16 channel 3+3k+j = exp(-(sqrt(d2))^2 / (2*(f_j*320)^2)),
- *        f = (0.02, 0.08, 0.16) (utils.py:34-37); 0 when the image holds no seed of that kind */
+ *        f = (0.02, 0.08, 0.16) (utils.py:34-37); 0 when the image holds no seed of that kind, and exact 0 instead
+ *        of values below 1e-12 for d^2 > 145000 (the search radius is capped there) */
 int tcv_fba_edt_cols(const void* x16, int frames, int h, int w, int* g, tcv_stream_t stream);
 int tcv_fba_edt_rows(const int* g, int frames, int h, int w, void* x16, tcv_stream_t stream);
 

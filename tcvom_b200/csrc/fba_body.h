@@ -294,6 +294,7 @@ TCV_HD void fba_encode_body(ll i, const EncodeP& p) {
 }
 
 #define TCV_EDT_INF (1 << 20)
+#define TCV_EDT_CAP2 145000
 struct EdtP {
   uint16_t* x16;
   int frames, h, w;
@@ -330,9 +331,12 @@ TCV_HD void fba_edt_rows_body(ll i, const EdtP& p) {
   const int f = (int)(i / (2 * hw));
   const int* row = p.g + (((ll)f * 2 + k) * p.h + y) * p.w;
   const ll inf2 = (ll)TCV_EDT_INF * TCV_EDT_INF;
+  // beyond d^2 = TCV_EDT_CAP2 even the widest feature exp(-d^2 / 5242.88) is below 1e-12 (exp(-27.7)): such pixels
+  // are written as exact zeros and the search stops there (columns further out cannot bring d^2 under the cap)
+  const ll cap2 = TCV_EDT_CAP2;
   ll best = row[x] >= TCV_EDT_INF ? inf2 : (ll)row[x] * row[x];
   for (int r = 1; r < p.w; ++r) {
-    if ((ll)r * r >= best) break;
+    if ((ll)r * r >= best || (ll)r * r > cap2) break;
     if (x - r >= 0) {
       const int gv = row[x - r];
       if (gv < TCV_EDT_INF) {
@@ -351,7 +355,7 @@ TCV_HD void fba_edt_rows_body(ll i, const EdtP& p) {
   uint16_t* o = p.x16 + ((ll)f * hw + (ll)y * p.w + x) * 16 + 3 + 3 * k;
   const ll plane = (ll)p.frames * hw * 16;
   float e[3] = {0.f, 0.f, 0.f};
-  if (best < inf2) {
+  if (best <= cap2) {
     const float d = sqrtf((float)best);  // cv2.distanceTransform(DIST_L2, precise) returns the float32 distance
     const float m = -(d * d);           // -dt(...)**2   (utils/utils.py:33)
     // 2*(f*L)^2 with L = 320: 81.92, 1310.72, 5242.88 (utils/utils.py:34-37)

@@ -230,6 +230,18 @@ def test_distance_transform_edge_cases(emu):
     _, x11, _, _ = O.eval_preprocess(imgs[None].float(), tris[None].float())
     assert float((got[:, 3:11] - x11[0, :, 3:11]).abs().max()) < 2e-5
     assert float(got[0, 3:9].abs().max()) == 0
+    # distances beyond the capped search radius (d^2 > 145000: every feature < 1e-12) are written as exact zeros
+    H, W = 8, 1312
+    tris = torch.full((1, 1, H, W), 128, dtype=torch.uint8)
+    tris[0, 0, 3, 5] = 255
+    tris[0, 0, 6, 1300] = 0
+    imgs = torch.zeros(1, 3, H, W, dtype=torch.uint8)
+    x16 = Act.empty(1, H, W, 16, torch.device("cpu"))
+    eng.encode_inputs(imgs, tris, 1, H, W, x16)
+    got = from_act(x16)
+    _, x11, _, _ = O.eval_preprocess(imgs[None].float(), tris[None].float())
+    assert float((got[:, 3:11] - x11[0, :, 3:11]).abs().max()) < 2e-5
+    assert float(got[0, 6:9, :, 600:].abs().max()) == 0 and float(x11[0, 0, 6:9, :, 600:].max()) < 1e-12
 
 
 # ------------------------------------------------------------------------------------------ the whole program
