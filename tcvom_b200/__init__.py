@@ -9,12 +9,14 @@ from .model import (EvalModel, FeatureAggregationModule, FullModel, FullModel_VM
 __version__ = "0.1.0"
 
 
-def install(native_wrapper: bool = True):
+def install(native_wrapper: bool = True, fba_seam: bool = False):
     """Hooks this package into an importable reference checkout (``models`` on ``sys.path``).
 
-    * ``models.VMN.get_VMN_models('vmn_gca' | 'vmn_fba', ...)`` -> :func:`tcvom_b200.get_VMN_models`
+    * ``models.VMN.get_VMN_models('vmn_gca', ...)`` -> :func:`tcvom_b200.get_VMN_models`
       (the plugin seam ``models/model.py:39-44`` calls at construction time); other archs are
-      forwarded to the reference untouched;
+      forwarded to the reference untouched.  ``fba_seam=True`` also routes ``'vmn_fba'`` through the seam -- the
+      native FBA network is inference-only, so leave it off when the reference's own training wrappers
+      (``FullModel_VMD('vmn_fba')``) are to keep working;
     * with ``native_wrapper`` also ``models.model.EvalModel`` -> :class:`tcvom_b200.EvalModel`
       when it is built for ``vmn_gca`` / ``vmn_fba`` (fused preprocess / postprocess kernels, CUDA-graph
       replay; for ``vmn_fba`` also the trimap distance transforms on the GPU instead of ``cv2``).
@@ -35,7 +37,7 @@ def install(native_wrapper: bool = True):
     orig_factory = ref_vmn.get_VMN_models
 
     def factory(arch, *args, **kwargs):
-        if arch in ("vmn_gca", "vmn_fba"):
+        if arch == "vmn_gca" or (arch == "vmn_fba" and fba_seam):
             return get_VMN_models(arch, *args, **kwargs)
         return orig_factory(arch, *args, **kwargs)
 
