@@ -1,0 +1,106 @@
+"""Property tests (hypothesis) of the FBA kernel bodies on random ragged shapes, run on the C-ABI test double
+(tests/host_emul): the index arithmetic of tcvom_b200/csrc/fba_body.h against plain PyTorch / scipy.  CPU only."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+from hypothesis import given, settings, strategies as st
+
+from test_host_emul_fba import emu, from_act, make_engine, to_act  # noqa: F401  (emu is a fixture)
+
+DEV = torch.device("cpu")
+SET = settings(max_examples=25, deadline=None)
+
+
+@SET
+@given(n=st.integers(1, 2), c8=st.integers(1, 4), h=st.integers(1, 13), w=st.integers(1, 13),
+       oh=st.integers(1, 21), ow=st.integers(1, 21), seed=st.integers(0, 10 ** 6))
+def test_bilinear_any_size(emu, n, c8, h, w, oh, ow, seed):
+    from tcvom_b200.engine import Act
+    eng = make_engine()
+    c = 8 * c8
+    x = torch.randn(n, c, h, w, generator=torch.Generator().manual_seed(seed))
+    xa = to_act(x)
+    out = Act.empty(n, oh, ow, c + 16, DEV)
+    out.buf.zero_()
+    eng.bilinear(xa, oh, ow, out, 8)
+    ref = F.interpolate(from_act(xa), (oh, ow), mode="bilinear", align_corners=False)
+    got = from_act(out)
+    assert float((got[:, 8:8 + c] - ref).abs().max()) < 5e-5
+    assert float(got[:, :8].abs().max()) == 0 and float(got[:, 8 + c:].abs().max()) == 0
+
+
+@SET
+@given(n=st.integers(1, 2), h=st.integers(1, 15), w=st.integers(1, 15), seed=st.integers(0, 10 ** 6))
+def test_maxpool_any_size(emu, n, h, w, seed):
+    eng = make_engine()
+    x = torch.randn(n, 8, h, w, generator=torch.Generator().manual_seed(seed))
+    xa = to_act(x)
+    assert torch.equal(from_act(eng.maxpool(xa)), F.max_pool2d(from_act(xa), 3, 2, 1))
+
+
+@SET
+@given(h=st.integers(1, 14), w=st.integers(1, 14), s=st.sampled_from([1, 2, 3, 6]), seed=st.integers(0, 10 ** 6))
+def test_adaptive_avgpool_any_size(emu, h, w, s, seed):
+    from tcvom_b200.engine import Act
+    eng = make_engine()
+    x = torch.randn(1, 64, h, w, generator=torch.Generator().manual_seed(seed))
+    xa = to_act(x)
+    pooled = Act.empty(1, s, s, 64, DEV)
+    eng._call("tcv_adaptive_avgpool", xa.ptr, xa.plane, 1, h, w, 64, 64, 0, s, pooled.ptr)
+    assert float((from_act(pooled) - F.adaptive_avg_pool2d(from_act(xa), s)).abs().max()) < 2e-5
+
+
+@SET
+@given(n=st.integers(1, 3), c=st.sampled_from([64, 128, 256]), px=st.integers(1, 40), act=st.sampled_from([0, 1, 4]),
+       seed=st.integers(0, 10 ** 6))
+def test_groupnorm_any_size(emu, n, c, px, act, seed):
+    eng = make_engine()
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, c, px, 1, generator=g) * 3 + 1
+    gam, bet = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g)
+    eng.gn_params["p"] = (gam, bet)
+    xa = to_act(x)
+    y = from_act(eng.gn(xa, "p", act))
+    ref = F.group_norm(from_act(xa), 32, gam, bet, 1e-5)
+    ref = {0: ref, 1: F.relu(ref), 4: F.leaky_relu(ref, 0.01)}[act]
+    # a group of c/32 channels x px pixels can have a tiny variance: compare relative to the normalised scale
+    assert float((y - ref).abs().max()) < 2e-4 * max(1.0, float(ref.abs().max()))
+
+
+@SET
+@given(h=st.integers(2, 24), w=st.integers(2, 40), p_fg=st.floats(0.0, 0.2), p_bg=st.floats(0.0, 0.2),
+       seed=st.integers(0, 10 ** 6))
+def test_distance_transform_random_trimaps(emu, h, w, p_fg, p_bg, seed):
+    """exact Euclidean distance features on random sparse seeds (incl. frames without any seed) vs scipy."""
+    from oracle import vmn_fba_oracle as O
+    from tcvom_b200.engine import Act
+    eng = make_engine()
+    rng = np.random.default_rng(seed)
+    u = rng.uniform(size=(2, 1, h, w))
+    tri = np.full((2, 1, h, w), 128, np.uint8)
+    tri[u < p_fg] = 255
+    tri[u > 1 - p_bg] = 0
+    tris = torch.from_numpy(tri)
+    imgs = torch.zeros(2, 3, h, w, dtype=torch.uint8)
+    x16 = Act.empty(2, h, w, 16, DEV)
+    eng.encode_inputs(imgs, tris, 2, h, w, x16)
+    _, x11, _, _ = O.eval_preprocess(imgs[None].float(), tris[None].float())
+    assert float((from_act(x16)[:, 3:11] - x11[0, :, 3:11]).abs().max()) < 2e-5
+
+
+@SET
+@given(h2=st.integers(1, 8), w2=st.integers(1, 8), seed=st.integers(0, 10 ** 6))
+def test_space_to_depth_stem_any_size(emu, h2, w2, seed):
+    from oracle import vmn_fba_oracle as O
+    from tcvom_b200 import _cabi
+    from tcvom_b200.fba_engine import STEM
+    eng = make_engine()
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(1, 11, 2 * h2, 2 * w2, generator=g)
+    w = torch.randn(64, 11, 7, 7, generator=g) * 0.05
+    eng._pack_fba(_cabi.lib(), 0, STEM, w, True)
+    xa = to_act(x, 16)
+    y = from_act(eng.stem_s2d(xa, STEM))
+    ref = F.conv2d(from_act(xa, 11), O.ws_weight(w), None, 2, 3)
+    assert float((y - ref).abs().max()) < 3e-5 * max(1.0, float(ref.abs().max()))
