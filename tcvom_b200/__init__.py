@@ -5,6 +5,7 @@ Public surface mirrors the reference's operator/plugin interface for this path:
 """
 from .model import (EvalModel, FeatureAggregationModule, FullModel, FullModel_VMD, GuidedCxtAtten, VMN,  # noqa: F401
                     VMN_FBA, get_VMN_models)
+from .stream import FrameStream  # noqa: F401
 
 __version__ = "0.1.0"
 

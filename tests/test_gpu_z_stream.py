@@ -1,0 +1,63 @@
+"""GPU tests of tcvom_b200.FrameStream (per-frame feature reuse across sliding windows):
+the streamed mattes must equal what EvalModel.forward returns for every 3-frame window of the clip (same kernels on
+the same values; the FBA path's GroupNorm sums are grouped differently for 1 and 3 images per launch -- fp64 partials, but a
+scale / shift can land on the neighbouring float -- hence a 5e-5 bound there instead of bit equality)."""
+import pytest
+import torch
+
+from helpers import fixture_sd, fixture_sd_fba
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _clip(H, W, frames, seed):
+    from tcvom_b200 import synthetic
+    imgs, tris = synthetic.make_window(H, W, seed=seed, frames=frames)
+    return torch.from_numpy(imgs).to(DEV), torch.from_numpy(tris).to(DEV)
+
+
+@pytest.mark.parametrize("arch,dilate", [("vmn_gca", None), ("vmn_gca", 3), ("vmn_fba", None)])
+def test_stream_equals_windowed_forward(arch, dilate):
+    import tcvom_b200
+    m = tcvom_b200.EvalModel(model=arch, agg_window=7, dilate_kernel=dilate)
+    m.NET.load_state_dict(fixture_sd() if arch == "vmn_gca" else fixture_sd_fba(), strict=True)
+    m = m.to(DEV).eval()
+    H, W, T = 64, 96, 6
+    imgs, tris = _clip(H, W, T, seed=15)
+    tol = 5e-5 if arch == "vmn_fba" else 1e-6
+    with torch.no_grad():
+        stream = tcvom_b200.FrameStream(m, H, W, u8=True)
+        outs = [stream.push(imgs[0, t], tris[0, t]) for t in range(T)]
+        assert outs[0] is None and outs[1] is None
+        for t in range(1, T - 1):
+            ref = m(imgs[:, t - 1:t + 2].contiguous(), tris[:, t - 1:t + 2].contiguous())
+            got = outs[t + 1]
+            if arch == "vmn_fba":
+                for g, r in zip(got, ref):
+                    assert float((g - r[0, 1]).abs().max()) < tol
+            else:
+                assert float((got - ref[0, 1]).abs().max()) < tol
+        # a new clip after reset(): the first two pushes return nothing again, the third equals the window
+        stream.reset()
+        assert stream.push(imgs[0, 2], tris[0, 2]) is None and stream.push(imgs[0, 3], tris[0, 3]) is None
+        got = stream.push(imgs[0, 4], tris[0, 4])
+        ref = m(imgs[:, 2:5].contiguous(), tris[:, 2:5].contiguous())
+        a = got[0] if arch == "vmn_fba" else got
+        r = ref[0] if arch == "vmn_fba" else ref
+        assert float((a - r[0, 1]).abs().max()) < tol
+
+
+def test_stream_rejects_cpu_frames_and_train_mode():
+    import tcvom_b200
+    m = tcvom_b200.EvalModel(model="vmn_gca", agg_window=7)
+    m.NET.load_state_dict(fixture_sd(), strict=True)
+    m = m.to(DEV).eval()
+    stream = tcvom_b200.FrameStream(m, 64, 64)
+    with pytest.raises(RuntimeError):
+        stream.push(torch.zeros(3, 64, 64, dtype=torch.uint8), torch.zeros(1, 64, 64, dtype=torch.uint8))
+    with pytest.raises(ValueError):
+        tcvom_b200.FrameStream(m, 60, 64)
+    m.train()
+    with pytest.raises(NotImplementedError):
+        tcvom_b200.FrameStream(m, 64, 64)

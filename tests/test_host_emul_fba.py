@@ -277,3 +277,46 @@ def test_eval_program_matches_reference_golden(emu, name):
     for k, ref in (("attb", g["attb1"]), ("attf", g["attf1"])):
         assert err(io[k][:, 0].numpy(), ref) < 3e-3 * max(1.0, float(np.abs(ref.astype(np.float32)).max()))
     assert float(io["alphas"][:, 0].abs().max()) == 0 and float(io["alphas"][:, -1].abs().max()) == 0
+
+
+def test_frame_stream_equals_windowed_program(emu):
+    """tcvom_b200.FrameStream (per-frame feature reuse across sliding windows) against the windowed
+    program on every window of a 5-frame clip: same kernels on the same values."""
+    import tcvom_b200
+    from tcvom_b200 import synthetic
+    from tcvom_b200.engine import Plan
+    from tcvom_b200.stream import FrameStream
+    net = tcvom_b200.get_VMN_models("vmn_fba", agg_window=7)
+    net.load_state_dict(fixture_sd_fba(), strict=True)
+    m = tcvom_b200.EvalModel(model="vmn_fba", agg_window=7, dilate_kernel=2)
+    m.NET = net
+    m.eval()
+    eng = make_engine()
+    eng.refresh_weights(net)
+    H, W = 32, 64
+    imgs, tris = synthetic.make_window(H, W, seed=4, frames=5)
+    imgs, tris = torch.from_numpy(imgs), torch.from_numpy(tris)
+
+    class HostStream(FrameStream):
+        def _run(self, plan):
+            plan.replay(0)
+
+        @staticmethod
+        def _check_input(img):
+            pass
+
+    stream = HostStream(m, H, W, u8=True, engine=eng)
+    outs = [stream.push(imgs[0, t], tris[0, t]) for t in range(5)]
+    assert outs[0] is None and outs[1] is None
+    plan = Plan()
+    eng._rec = plan
+    io = eng.eval_program(1, 3, H, W, 2, True)
+    eng._rec = None
+    for t in range(1, 4):
+        io["imgs"].copy_(imgs[:, t - 1:t + 2]); io["tris"].copy_(tris[:, t - 1:t + 2])
+        plan.replay(0)
+        a, Fg, Bg = outs[t + 1]
+        assert float((a - io["alphas"][0, 1]).abs().max()) < 1e-6
+        assert float((Fg - io["Fs"][0, 1]).abs().max()) < 1e-6 and float((Bg - io["Bs"][0, 1]).abs().max()) < 1e-6
+    stream.reset()
+    assert stream.push(imgs[0, 0], tris[0, 0]) is None
