@@ -1,11 +1,19 @@
-"""GPU tests of tcvom_b200.FrameStream (per-frame feature reuse across sliding windows):
+"""GPU checks of tcvom_b200.FrameStream -- written after round 1's GPU budget was spent, so they live here and not
+under tests/ until they have run green on a B200 once:   python -m pytest tools/stream_check.py -q -m gpu
+(then: git mv tools/stream_check.py tests/test_gpu_z_stream.py).
+
+GPU tests of tcvom_b200.FrameStream (per-frame feature reuse across sliding windows):
 the streamed mattes must equal what EvalModel.forward returns for every 3-frame window of the clip (same kernels on
 the same values; the FBA path's GroupNorm sums are grouped differently for 1 and 3 images per launch -- fp64 partials, but a
 scale / shift can land on the neighbouring float -- hence a 5e-5 bound there instead of bit equality)."""
 import pytest
 import torch
 
-from helpers import fixture_sd, fixture_sd_fba
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from helpers import fixture_sd, fixture_sd_fba  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
