@@ -320,3 +320,32 @@ def test_frame_stream_equals_windowed_program(emu):
         assert float((Fg - io["Fs"][0, 1]).abs().max()) < 1e-6 and float((Bg - io["Bs"][0, 1]).abs().max()) < 1e-6
     stream.reset()
     assert stream.push(imgs[0, 0], tris[0, 0]) is None
+
+
+def test_eval_program_five_frame_samples_match_oracle(emu):
+    """S = 5 (three centre frames per sample, tail launched with ncen = 3) and B = 2 against the CPU oracle."""
+    import tcvom_b200
+    from oracle import vmn_fba_oracle as O
+    from tcvom_b200 import synthetic
+    from tcvom_b200.engine import Plan
+    sd = fixture_sd_fba()
+    net = tcvom_b200.get_VMN_models("vmn_fba", agg_window=7)
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    eng = make_engine()
+    eng.refresh_weights(net)
+    B, S, H, W = 2, 5, 32, 32
+    imgs, tris = synthetic.make_window(H, W, seed=21, frames=S, batch=B)
+    imgs, tris = torch.from_numpy(imgs), torch.from_numpy(tris)
+    plan = Plan()
+    eng._rec = plan
+    io = eng.eval_program(B, S, H, W, -1, False)
+    eng._rec = None
+    io["imgs"].copy_(imgs.float()); io["tris"].copy_(tris.float())
+    plan.replay(0)
+    with torch.no_grad():
+        ra, rF, rB = O.eval_forward(sd, imgs.float(), tris.float())
+    assert float((io["alphas"] - ra).abs().max()) < 1e-3
+    assert float((io["Fs"] - rF).abs().max()) < 1e-3 and float((io["Bs"] - rB).abs().max()) < 1e-3
+    assert float(io["alphas"][:, 0].abs().max()) == 0 and float(io["alphas"][:, -1].abs().max()) == 0
+    assert float(io["alphas"][:, 1:4].abs().max()) > 0

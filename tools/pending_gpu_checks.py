@@ -1,6 +1,6 @@
-"""GPU checks of tcvom_b200.FrameStream -- written after round 1's GPU budget was spent, so they live here and not
-under tests/ until they have run green on a B200 once:   python -m pytest tools/stream_check.py -q -m gpu
-(then: git mv tools/stream_check.py tests/test_gpu_z_stream.py).
+"""GPU checks written after round 1's GPU budget was spent, so they live here and not under tests/ until they have run
+green on a B200 once:   python -m pytest tools/pending_gpu_checks.py -q -m gpu     (then move them under tests/).
+Their host logic is already covered on the CPU by tests/test_host_emul_fba.py (C-ABI test double).
 
 GPU tests of tcvom_b200.FrameStream (per-frame feature reuse across sliding windows):
 the streamed mattes must equal what EvalModel.forward returns for every 3-frame window of the clip (same kernels on
@@ -69,3 +69,21 @@ def test_stream_rejects_cpu_frames_and_train_mode():
     m.train()
     with pytest.raises(NotImplementedError):
         tcvom_b200.FrameStream(m, 64, 64)
+
+
+def test_fba_five_frame_samples_match_oracle():
+    """EvalModel('vmn_fba') with S = 5 and B = 2 (tail launched with three centre frames per sample) vs the CPU oracle."""
+    import tcvom_b200
+    from oracle import vmn_fba_oracle as O
+    from tcvom_b200 import synthetic
+    sd = fixture_sd_fba()
+    m = tcvom_b200.EvalModel(model="vmn_fba", agg_window=7)
+    m.NET.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()
+    imgs, tris = synthetic.make_window(64, 64, seed=21, frames=5, batch=2)
+    ti, tt = torch.from_numpy(imgs), torch.from_numpy(tris)
+    with torch.no_grad():
+        a, Fg, Bg = m(ti.to(DEV), tt.to(DEV))
+        ra, rF, rB = O.eval_forward(sd, ti.float(), tt.float())
+    assert float((a.cpu() - ra).abs().max()) < 1e-3
+    assert float((Fg.cpu() - rF).abs().max()) < 1e-3 and float((Bg.cpu() - rB).abs().max()) < 1e-3
