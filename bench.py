@@ -123,6 +123,22 @@ def cpu_oracle_time(sample_hw, threads, reps=1):
     return ts
 
 
+def cpu_oracle_time_fba(sample_hw, threads):
+    """Times the FBA+TAM CPU oracle (oracle/vmn_fba_oracle.py) on one 3-frame window (seconds)."""
+    import torch
+    from helpers import fixture_sd_fba
+    from oracle import vmn_fba_oracle as OF
+    from tcvom_b200 import synthetic
+    torch.set_num_threads(threads)
+    h, w = sample_hw
+    imgs, tris = synthetic.make_window(h, w, seed=7)
+    ti, tt = torch.from_numpy(imgs).float(), torch.from_numpy(tris).float()
+    sd = fixture_sd_fba()
+    t0 = time.perf_counter()
+    OF.eval_forward(sd, ti, tt)
+    return time.perf_counter() - t0
+
+
 def pick_cpu_sample(threads, budget_s, n_steps):
     """Largest window size whose estimated oracle time fits the budget.  The estimate scales a
     256x480 probe by the reference FLOP model; the returned value is always MEASURED on the
@@ -267,6 +283,20 @@ def run_fba_section(args, rank, world, dev, max_over_ranks):
         torch.cuda.empty_cache()
     except Exception as e:                                     # noqa: BLE001 - reported in the JSON line
         err = f"{type(e).__name__}: {e}"
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and err is None:
+        # the CPU oracle of this config on the box's host cores, one bounded sample (a half-resolution window costs
+        # ~2 s on 16 cores; the conv-only FLOP model scales it to a 1088x1920 window)
+        try:
+            threads = os.cpu_count() or 1
+            hw = (544, 960)
+            t = cpu_oracle_time_fba(hw, threads)
+            frac = (hw[0] * hw[1]) / float(H * W)
+            cpu = dict(value=frac / t, unit=UNIT, cores=threads, kind="port",
+                       sample=f"one 3-frame {hw[0]}x{hw[1]} FBA+TAM window ({t:.2f} s) = {frac:.4f} of a 1088x1920 window "
+                              f"(convolution FLOPs scale with the pixel count)")
+        except Exception as e:                                 # noqa: BLE001
+            cpu = dict(error=f"{type(e).__name__}: {e}")
     ms = max_over_ranks(ms_local)
     any_failed = max_over_ranks(1.0 if (err is not None or ms_local < 0) else 0.0) > 0
     if any_failed:
@@ -274,7 +304,7 @@ def run_fba_section(args, rank, world, dev, max_over_ranks):
     return dict(workload="FBA+TAM forward-only 1080p 3-frame window, batch 1 per GPU (configs[4]; reference FLOP count "
                          f"{FBA_GFLOP_PER_WINDOW:.1f} GFLOP/window, convolutions only)",
                 ms_per_window=ms, windows_per_s=world * 1e3 / ms,
-                algorithmic_tflops=FBA_GFLOP_PER_WINDOW / ms, **info)
+                algorithmic_tflops=FBA_GFLOP_PER_WINDOW / ms, cpu_baseline=cpu, **info)
 
 
 # ------------------------------------------------------------------------------------- native arm
