@@ -106,7 +106,9 @@ int tcv_conv2d_path(const tcv_conv_desc* d);
  * returns the previous value.  For A/B measurements and tests. */
 int tcv_set_conv_tc_version(int v);
 /* measurement switches for kernel bring-up (bit 0: skip MMAs, 1: skip epilogue memory ops, 2/3: load
- * activations / weights only once).  Results are WRONG when non-zero; default 0.  Returns the old value. */
+ * activations / weights only once; bits 4..7: further epilogue switches).  Results are WRONG when any of bits 0..7
+ * is set; default 0.  Bit 8 (256) is a tuning switch with unchanged results: N = 64 instead of N = 128 tiles in the shared-halo conv kernel when that
+ * shortens the persistent schedule.  Returns the old value. */
 int tcv_set_debug_flags(int flags);
 
 /* sigma = u^T W v  (W viewed [rows, cols], rows = w_bar.shape[0]); then packs W/sigma into the

@@ -366,8 +366,30 @@ static int conv_tc2_bn(const tcv_conv_desc& d, cudaStream_t st) {
   return launched("conv_tc2_kernel");
 }
 
+// Tuning switch (tcv_set_debug_flags bit 8 = 256, results unchanged, default off; to be A/B-measured): prefer N = 64
+// tiles over N = 128 when that shortens the schedule.  A persistent grid of 148 CTAs runs ceil(items / 148) rounds; the
+// deep layers have few items (512->512 @34x60x3: 96 items = 0.65 rounds, 256->256 @68x120x3: 192 items = 1.3 rounds
+// -> 2), so halving the item size can cut the quantisation loss although a narrower tile re-reads the activations.
+static bool prefer_bn64(const tcv_conv_desc& d) {
+  V2Params p;
+  memset(&p, 0, sizeof(p));
+  if (!build_groups(d, p)) return false;
+  int th = 8, tw = 16;
+  pick_tile2(d.gh, d.gw, p.box_rows, &th, &tw);
+  const long long tiles = (long long)((d.gw + tw - 1) / tw) * ((d.gh + 2 * th - 1) / (2 * th)) * d.n;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long i128 = tiles * (d.cout / 128), i64 = tiles * (d.cout / 64);
+  const double t128 = (double)((i128 + sms - 1) / sms);          // rounds x cost of an N = 128 item (1.0)
+  const double t64 = (double)((i64 + sms - 1) / sms) * 0.56;     // an N = 64 item: half the MMAs, same activation boxes
+  return t64 < t128;
+}
+
 int conv2d_tc2(const tcv_conv_desc& d, cudaStream_t st) {
-  if (d.cout % 128 == 0) return conv_tc2_bn<128>(d, st);
+  if (d.cout % 128 == 0) {
+    if ((g_debug_flags.load() & 256) && prefer_bn64(d)) return conv_tc2_bn<64>(d, st);
+    return conv_tc2_bn<128>(d, st);
+  }
   if (d.cout % 64 == 0) return conv_tc2_bn<64>(d, st);
   return conv_tc2_bn<32>(d, st);
 }
