@@ -331,7 +331,9 @@ def run_native(args, rank, world, local_rank):
     # reference API accepts them (EvalModel.preprocess casts with .float(), models/model.py:366-368)
     imgs_u8 = torch.from_numpy(imgs_np).pin_memory()
     tris_u8 = torch.from_numpy(tris_np).pin_memory()
-    out_h = torch.empty((1, S, 1, H, W), dtype=torch.float32).pin_memory()
+    # pred_test.py:107-110 reads back the CENTRE frame's matte only (`model(imgs, tris).squeeze()[c]...cpu()`); the first /
+    # last frame of the returned tensor are zeros by contract (models/model.py:419-421)
+    out_h = torch.empty((1, 1, 1, H, W), dtype=torch.float32).pin_memory()
 
     from tcvom_b200 import dp
 
@@ -371,7 +373,7 @@ def run_native(args, rank, world, local_rank):
         # ---- e2e: the user-facing call with HOST buffers (pred_test.py:100-107 sequence)
         def e2e_step():
             a = model(imgs_u8.to(dev, non_blocking=True), tris_u8.to(dev, non_blocking=True))
-            out_h.copy_(a, non_blocking=True)
+            out_h.copy_(a[:, S // 2:S // 2 + 1], non_blocking=True)
         for _ in range(3):
             e2e_step()
         barrier()
