@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const uint16_t* __restric
   double s[8], ss[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) s[k] = ss[k] = 0.0;
+#pragma unroll 4   // several 16-byte load pairs in flight per thread (the loop is latency-bound otherwise)
   for (ll px = p0 + lane; px < p1; px += lanes) {
     float f[8];
     ld8(x + ((ll)img * pixels + px) * c + vec * 8, x_plane, f);
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__(256) adaptive_avgpool_kernel(const uint16_t* _
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll 4
   for (int i = lane; i < cnt; i += 32) {
     const int yy = y0 + i / rw, xx = x0 + i % rw;
     float f[8];
