@@ -176,7 +176,9 @@ int tcv_gn_stats(const void* x, long long x_plane, int n, long long pixels, int 
   if (x_plane == 0) x_plane = (long long)n * pixels * c;
   TCV_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)n * c, S(stream)));
   // ~4 blocks per SM over all images; every block owns one contiguous pixel chunk of one image
-  long long chunks = (148 * 4 + n - 1) / n;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long chunks = ((long long)sms * 4 + n - 1) / n;
   const int lanes = 256 / (c / 8);
   if (chunks * lanes > pixels) chunks = (pixels + lanes - 1) / lanes;
   if (chunks < 1) chunks = 1;
