@@ -349,3 +349,43 @@ def test_eval_program_five_frame_samples_match_oracle(emu):
     assert float((io["Fs"] - rF).abs().max()) < 1e-3 and float((io["Bs"] - rB).abs().max()) < 1e-3
     assert float(io["alphas"][:, 0].abs().max()) == 0 and float(io["alphas"][:, -1].abs().max()) == 0
     assert float(io["alphas"][:, 1:4].abs().max()) > 0
+
+
+def test_weight_cache_follows_load_state_dict(emu):
+    """SURVEY 8b state / ownership: packed (weight-standardised) weights are derived caches, re-derived in place when
+    the parameters change, so a RECORDED plan picks up a new checkpoint without being re-recorded."""
+    import tcvom_b200
+    from oracle import vmn_fba_oracle as O
+    from tcvom_b200 import synthetic
+    from tcvom_b200.engine import Plan
+    sd = fixture_sd_fba()
+    net = tcvom_b200.get_VMN_models("vmn_fba", agg_window=7)
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    eng = make_engine()
+    eng.refresh_weights(net)
+    fp0 = eng._fingerprint
+    eng.refresh_weights(net)
+    assert eng._fingerprint == fp0                         # nothing changed: no re-packing
+    H = W = 32
+    imgs, tris = synthetic.make_window(H, W, seed=2)
+    imgs, tris = torch.from_numpy(imgs), torch.from_numpy(tris)
+    plan = Plan()
+    eng._rec = plan
+    io = eng.eval_program(1, 3, H, W, -1, True)
+    eng._rec = None
+    io["imgs"].copy_(imgs); io["tris"].copy_(tris)
+    plan.replay(0)
+    a0 = io["alphas"].clone()
+    sd2 = {k: v.clone() for k, v in sd.items()}
+    g = torch.Generator().manual_seed(9)
+    for k in ("decoder.conv_up4.0.weight", "encoder.layer2.1.conv2.weight", "decoder.conv_up1.1.weight"):
+        sd2[k] = sd2[k] * (1.0 + 0.2 * torch.randn(sd2[k].shape, generator=g))
+    net.load_state_dict(sd2, strict=True)                  # in-place copy_: parameter versions change
+    eng.refresh_weights(net)
+    assert eng._fingerprint != fp0
+    plan.replay(0)                                         # same recorded calls, same buffers
+    with torch.no_grad():
+        ra, _, _ = O.eval_forward(sd2, imgs.float(), tris.float())
+    assert float((io["alphas"] - ra).abs().max()) < 1e-3
+    assert float((io["alphas"] - a0).abs().max()) > 1e-3   # and the result did change
