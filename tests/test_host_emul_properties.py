@@ -9,7 +9,7 @@ from hypothesis import given, settings, strategies as st
 from test_host_emul_fba import emu, from_act, make_engine, to_act  # noqa: F401  (emu is a fixture)
 
 DEV = torch.device("cpu")
-SET = settings(max_examples=25, deadline=None)
+SET = settings(max_examples=40, deadline=None, derandomize=True, database=None)   # same examples every run
 
 
 @SET
@@ -62,10 +62,11 @@ def test_groupnorm_any_size(emu, n, c, px, act, seed):
     eng.gn_params["p"] = (gam, bet)
     xa = to_act(x)
     y = from_act(eng.gn(xa, "p", act))
-    ref = F.group_norm(from_act(xa), 32, gam, bet, 1e-5)
+    # fp64 reference: a group of c/32 channels x px pixels can have a tiny variance, where torch's own fp32 group_norm is
+    # off by 6e-3 (hypothesis found n=1, c=64, px=1, seed=115) while the kernel (fp64 statistics) stays at 4e-5
+    ref = F.group_norm(from_act(xa).double(), 32, gam.double(), bet.double(), 1e-5)
     ref = {0: ref, 1: F.relu(ref), 4: F.leaky_relu(ref, 0.01)}[act]
-    # a group of c/32 channels x px pixels can have a tiny variance: compare relative to the normalised scale
-    assert float((y - ref).abs().max()) < 2e-4 * max(1.0, float(ref.abs().max()))
+    assert float((y.double() - ref).abs().max()) < 2e-4 * max(1.0, float(ref.abs().max()))
 
 
 @SET
