@@ -152,8 +152,7 @@ class GcaVmnEngine:
             self._tensors = None
         named = self._named()
         dev = next(iter(named.values())).device
-        if dev.type != "cuda":
-            raise RuntimeError("tcvom_b200: the module must live on a CUDA device (no CPU fallback)")
+        self._check_device(dev)
         if self.device is not None and dev != self.device:
             self.w.clear(); self.aff.clear(); self.bias.clear(); self.plans.clear()
             self._tensors = None
@@ -162,7 +161,7 @@ class GcaVmnEngine:
         if not force and fp == self._fingerprint:
             return
         L = _cabi.lib()
-        st = torch.cuda.current_stream(dev).cuda_stream
+        st = self._stream_ptr()
         sig = getattr(self, "_sigma_ws", None)
         if sig is None or sig.device != dev:
             sig = self._sigma_ws = torch.empty(256, dtype=torch.float32, device=dev)
@@ -253,6 +252,11 @@ class GcaVmnEngine:
             self.plans.popitem(last=False)          # drops the buffers (and CUDA graph) of the oldest shape
 
     # ------------------------------------------------------------------ call recording
+    @staticmethod
+    def _check_device(dev: torch.device) -> None:
+        if dev.type != "cuda":
+            raise RuntimeError("tcvom_b200: the module must live on a CUDA device (no CPU fallback)")
+
     def _stream_ptr(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 

@@ -92,11 +92,6 @@ class FbaVmnEngine(GcaVmnEngine):
                 self.gn_params[p] = (t, named[p + ".bias"])
         self._fingerprint = fp
 
-    @staticmethod
-    def _check_device(dev: torch.device) -> None:
-        if dev.type != "cuda":
-            raise RuntimeError("tcvom_b200: the module must live on a CUDA device (no CPU fallback)")
-
     def _pack_fba(self, L, st, p, w, standardize: bool) -> None:
         cout, cin, kh, kw = w.shape
         cin_pad = _round_up(cin, 8) if cin <= 32 else _round_up(cin, 32)

@@ -51,13 +51,17 @@ static int reflect_idx(int i, int n) {
 }
 
 template <typename T>
-static int preprocess_eval_t(const T* tris, int frames, int h, int w, int dilate, float* trimask) {
+static int preprocess_eval_t(const T* imgs, const T* tris, int frames, int h, int w, int dilate, void* x8v,
+                             float* trimask) {
   const ll hw = (ll)h * w;
   std::vector<uint8_t> m((size_t)frames * hw);
   for (ll i = 0; i < frames * hw; ++i) {
     const float s = (float)tris[i] * (1.0f / 255);
     m[i] = (s > 0.f && s < 1.f) ? 1 : 0;
   }
+  uint16_t* x8 = (uint16_t*)x8v;
+  const ll plane = (ll)frames * hw * 8;
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
   for (int f = 0; f < frames; ++f)
     for (int y = 0; y < h; ++y)
       for (int x = 0; x < w; ++x) {
@@ -69,11 +73,41 @@ static int preprocess_eval_t(const T* tris, int frames, int h, int w, int dilate
         } else {
           v = m[f * hw + (ll)y * w + x];
         }
-        trimask[f * hw + (ll)y * w + x] = v ? 1.f : 0.f;
+        const ll i = f * hw + (ll)y * w + x;
+        trimask[i] = v ? 1.f : 0.f;
+        // EvalModel.preprocess, TRIMAP_CHANNEL == 3 (models/model.py:366-379): normalised RGB + one-hot {bg, unknown, fg}
+        float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int c = 0; c < 3; ++c) {
+          const float sc = (float)imgs[((ll)f * 3 + (2 - c)) * hw + (ll)y * w + x] * (1.0f / 255);
+          o[c] = (sc - mean[c]) / stdv[c];
+        }
+        const float st = (float)tris[i] * (1.0f / 255);
+        const int cls = v ? 1 : (int)(2.0f * st);
+        o[3 + cls] = 1.f;
+        for (int c = 0; c < 8; ++c) st1(x8 + i * 8 + c, plane, o[c]);
       }
   ++g_launches;
   return 0;
 }
+
+template <typename T>
+static int postprocess_eval_t(const float* pred, const T* tris, const float* trimask, int batch, int frames, int h, int w,
+                              float* alphas) {
+  const ll hw = (ll)h * w;
+  for (ll i = 0; i < (ll)batch * frames * hw; ++i) {
+    const ll f = i / hw, p = i % hw;
+    const int b = (int)(f / frames), s = (int)(f % frames);
+    float a = 0.f;
+    if (s > 0 && s < frames - 1) {
+      const float pr = pred[((ll)b * (frames - 2) + (s - 1)) * hw + p];
+      a = trimask[i] != 0.f ? pr : (float)tris[i] * (1.0f / 255);
+    }
+    alphas[i] = a;
+  }
+  ++g_launches;
+  return 0;
+}
+
 extern "C" {
 
 int tcv_version(void) { return 100; }
@@ -137,13 +171,246 @@ int tcv_conv2d(const tcv_conv_desc* dp, tcv_stream_t) {
   return 0;
 }
 
-int tcv_preprocess_eval(const float*, const float* tris, int frames, int h, int w, int dilate, void*, float* trimask,
-                        uint8_t*, tcv_stream_t) {
-  return preprocess_eval_t<float>(tris, frames, h, w, dilate, trimask);
+int tcv_preprocess_eval(const float* imgs, const float* tris, int frames, int h, int w, int dilate, void* x8,
+                        float* trimask, uint8_t*, tcv_stream_t) {
+  return preprocess_eval_t<float>(imgs, tris, frames, h, w, dilate, x8, trimask);
 }
-int tcv_preprocess_eval_u8(const uint8_t*, const uint8_t* tris, int frames, int h, int w, int dilate, void*,
+int tcv_preprocess_eval_u8(const uint8_t* imgs, const uint8_t* tris, int frames, int h, int w, int dilate, void* x8,
                            float* trimask, uint8_t*, tcv_stream_t) {
-  return preprocess_eval_t<uint8_t>(tris, frames, h, w, dilate, trimask);
+  return preprocess_eval_t<uint8_t>(imgs, tris, frames, h, w, dilate, x8, trimask);
+}
+int tcv_postprocess_eval(const float* pred, const float* tris, const float* trimask, int batch, int frames, int h, int w,
+                         float* alphas, tcv_stream_t) {
+  return postprocess_eval_t<float>(pred, tris, trimask, batch, frames, h, w, alphas);
+}
+int tcv_postprocess_eval_u8(const float* pred, const uint8_t* tris, const float* trimask, int batch, int frames, int h,
+                            int w, float* alphas, tcv_stream_t) {
+  return postprocess_eval_t<uint8_t>(pred, tris, trimask, batch, frames, h, w, alphas);
+}
+
+// ------------------------------------------------------------------------------------------ vmn_gca entry points
+// (naive restatements of the semantics documented in include/tcvom_b200.h; fp32 operand formats only: the engine is
+// driven with use_tc_attn = False in the host-logic tests)
+int tcv_pack_weight_fold(const float*, int, void*, tcv_stream_t) { return 0; }
+
+int tcv_sn_fold_pack(const float* w_bar, const float* u, const float* v, int cout, int cin, int kh, int kw,
+                     int transposed, int cin_pad, float* packed, float* sigma_out, tcv_stream_t) {
+  const int taps = kh * kw;
+  double sigma = 1.0;
+  if (u) {   // sigma = u^T W v, W = w_bar viewed [shape[0], rest]  (GCA/ops.py:38-45)
+    const int rows = transposed ? cin : cout, cols = (transposed ? cout : cin) * taps;
+    sigma = 0.0;
+    for (int r = 0; r < rows; ++r) {
+      double sr = 0.0;
+      for (int c = 0; c < cols; ++c) sr += (double)w_bar[(ll)r * cols + c] * v[c];
+      sigma += sr * u[r];
+    }
+  }
+  if (sigma_out) *sigma_out = (float)sigma;
+  for (int t = 0; t < taps; ++t)
+    for (int ci = 0; ci < cin_pad; ++ci)
+      for (int co = 0; co < cout; ++co) {
+        float val = 0.f;
+        if (ci < cin) {
+          const ll src = transposed ? (((ll)ci * cout + co) * taps + t) : (((ll)co * cin + ci) * taps + t);
+          val = u ? w_bar[src] / (float)sigma : w_bar[src];
+        }
+        packed[((ll)t * cin_pad + ci) * cout + co] = val;
+      }
+  ++g_launches;
+  return 0;
+}
+
+int tcv_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps, int c,
+                float* scale, float* shift, tcv_stream_t) {
+  for (int i = 0; i < c; ++i) {
+    const float s = gamma[i] / sqrtf(var[i] + eps);
+    scale[i] = s;
+    shift[i] = beta[i] - mean[i] * s;
+  }
+  ++g_launches;
+  return 0;
+}
+
+int tcv_avgpool2(const void* x, int n, int h, int w, int c, void* y, tcv_stream_t) {
+  const int oh = h / 2, ow = w / 2;
+  const ll ip = (ll)n * h * w * c, op = (ll)n * oh * ow * c;
+  for (int img = 0; img < n; ++img)
+    for (int oy = 0; oy < oh; ++oy)
+      for (int ox = 0; ox < ow; ++ox)
+        for (int ch = 0; ch < c; ++ch) {
+          float a = 0.f;
+          for (int dy = 0; dy < 2; ++dy)
+            for (int dx = 0; dx < 2; ++dx)
+              a += ld1((const uint16_t*)x + (((ll)img * h + 2 * oy + dy) * w + 2 * ox + dx) * c + ch, ip);
+          st1((uint16_t*)y + (((ll)img * oh + oy) * ow + ox) * c + ch, op, a * 0.25f);
+        }
+  ++g_launches;
+  return 0;
+}
+
+int tcv_pad_reflect1(const void* x, int n, int h, int w, int c, void* y, tcv_stream_t) {
+  const int oh = h + 2, ow = w + 2;
+  const ll ip = (ll)n * h * w * c, op = (ll)n * oh * ow * c;
+  for (int img = 0; img < n; ++img)
+    for (int oy = 0; oy < oh; ++oy)
+      for (int ox = 0; ox < ow; ++ox) {
+        const int iy = reflect_idx(oy - 1, h), ix = reflect_idx(ox - 1, w);
+        const uint16_t* src = (const uint16_t*)x + (((ll)img * h + iy) * w + ix) * c;
+        uint16_t* dst = (uint16_t*)y + (((ll)img * oh + oy) * ow + ox) * c;
+        for (int ch = 0; ch < c; ++ch) { dst[ch] = src[ch]; dst[ch + op] = src[ch + ip]; }
+      }
+  ++g_launches;
+  return 0;
+}
+
+int tcv_unknown_os8(const void* x8, int n, int h, int w, float* unknown, tcv_stream_t) {
+  const int oh = h / 8, ow = w / 8;
+  for (int img = 0; img < n; ++img)
+    for (int oy = 0; oy < oh; ++oy)
+      for (int ox = 0; ox < ow; ++ox)
+        unknown[((ll)img * oh + oy) * ow + ox] = bf_to_f(((const uint16_t*)x8)[(((ll)img * h + oy * 8) * w + ox * 8) * 8 + 4]);
+  ++g_launches;
+  return 0;
+}
+
+// GCA/ops.py:106-229 (see the header): g [n,h/2,w/2,64] split-bf16 (guidance_conv at stride 2), unknown fp32 [n,h,w]
+int tcv_gca_prep(const void* g, const float* unknown, int n, int h, int w, void* Qv, void* Knv, float* mm, float* scales,
+                 int bf16_split, tcv_stream_t) {
+  REQ(bf16_split == 0, "gca_prep: the test double provides the fp32 operand format only");
+  const int hh = h / 2, ww = w / 2, P = hh * ww, GC = 64, QD = 576;
+  const ll gplane = (ll)n * P * GC;
+  float* Q = (float*)Qv;
+  float* Kn = (float*)Knv;
+  for (int img = 0; img < n; ++img) {
+    const float* u = unknown + (ll)img * h * w;
+    double s = 0.0;
+    for (int y = 0; y < hh; ++y)
+      for (int x = 0; x < ww; ++x) s += u[(2 * y) * w + 2 * x];
+    const float um = (float)(s / (hh * ww)), km = 1.0f - um;
+    scales[2 * img] = fminf(fmaxf(sqrtf(um / km), 0.1f), 10.f);
+    scales[2 * img + 1] = fminf(fmaxf(sqrtf(km / um), 0.1f), 10.f);
+    for (int p = 0; p < P; ++p) {
+      const int py = p / ww, px = p % ww;
+      float* q = Q + ((ll)img * P + p) * QD;
+      float ss = 0.f, usum = 0.f;
+      for (int t = 0; t < 9; ++t) {
+        const int yy = reflect_idx(py + t / 3 - 1, hh), xx = reflect_idx(px + t % 3 - 1, ww);
+        for (int c = 0; c < GC; ++c) {
+          const float val = ld1((const uint16_t*)g + ((ll)img * P + (ll)yy * ww + xx) * GC + c, gplane);
+          q[t * GC + c] = val;
+          ss += val * val;
+        }
+        usum += u[(2 * yy) * w + 2 * xx];
+      }
+      const float m = usum > 0.f ? 1.f : 0.f;
+      const float inv = (m > 0.f ? scales[2 * img] : scales[2 * img + 1]) / fmaxf(sqrtf(ss), 1e-4f);
+      float* k = Kn + ((ll)img * P + p) * QD;
+      for (int i = 0; i < QD; ++i) k[i] = q[i] * inv;
+      mm[(ll)img * P + p] = m;
+    }
+  }
+  ++g_launches;
+  return 0;
+}
+
+int tcv_gca_values(const void* feat, int n, int h, int w, void* Vtv, int mode, tcv_stream_t) {
+  REQ(mode == 0, "gca_values: the test double provides the fp32 operand format only");
+  const int hh = h / 2, ww = w / 2, P = hh * ww, P_pad = (P + 63) / 64 * 64, FC = 128, VD = 2048;
+  const ll fplane = (ll)n * h * w * FC;
+  float* Vt = (float*)Vtv;
+  for (int img = 0; img < n; ++img)
+    for (int t = 0; t < 16; ++t)
+      for (int c = 0; c < FC; ++c)
+        for (int p = 0; p < P_pad; ++p) {
+          float val = 0.f;
+          if (p < P) {
+            const int py = p / ww, px = p % ww;
+            const int yy = reflect_idx(2 * py + t / 4 - 1, h), xx = reflect_idx(2 * px + t % 4 - 1, w);
+            val = ld1((const uint16_t*)feat + (((ll)img * h + yy) * w + xx) * FC + c, fplane);
+          }
+          Vt[((ll)img * VD + t * FC + c) * P_pad + p] = val;
+        }
+  ++g_launches;
+  return 0;
+}
+
+int tcv_gemm_tn_f32(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc,
+                    long long strideA, long long strideB, long long strideC, int batch, tcv_stream_t) {
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < batch; ++b)
+    for (int m = 0; m < M; ++m)
+      for (int nn = 0; nn < N; ++nn) {
+        const float* a = A + b * strideA + (ll)m * lda;
+        const float* bb = B + b * strideB + (ll)nn * ldb;
+        float acc = 0.f;
+        for (int k = 0; k < K; ++k) acc += a[k] * bb[k];
+        C[b * strideC + (ll)m * ldc + nn] = acc;
+      }
+  ++g_launches;
+  return 0;
+}
+
+int tcv_gca_softmax(float* S, const float* mm, int n, int P, int P_pad, void*, int mode, tcv_stream_t) {
+  REQ(mode == 0, "gca_softmax: the test double provides the fp32 operand format only");
+  for (int img = 0; img < n; ++img)
+    for (int q = 0; q < P; ++q) {
+      float* row = S + ((ll)img * P + q) * P_pad;
+      row[q] += -1e4f * mm[(ll)img * P + q];
+      float mx = -INFINITY;
+      for (int p = 0; p < P; ++p) mx = fmaxf(mx, row[p]);
+      float sum = 0.f;
+      for (int p = 0; p < P; ++p) { row[p] = expf(row[p] - mx); sum += row[p]; }
+      for (int p = 0; p < P; ++p) row[p] /= sum;
+      for (int p = P; p < P_pad; ++p) row[p] = 0.f;
+    }
+  ++g_launches;
+  return 0;
+}
+
+int tcv_gca_fold(const float* O, int n, int h, int w, void* Y, tcv_stream_t) {
+  const int hh = h / 2, ww = w / 2, P = hh * ww, FC = 128, VD = 2048;
+  const ll yplane = (ll)n * h * w * FC;
+  for (int img = 0; img < n; ++img)
+    for (int y = 0; y < h; ++y)
+      for (int x = 0; x < w; ++x)
+        for (int c = 0; c < FC; ++c) {
+          float acc = 0.f;
+          // output pixel (y, x) is covered by patch (qy, qx) at tap (ty, tx) iff y = 2*qy + ty - 1, x = 2*qx + tx - 1
+          for (int ty = 0; ty < 4; ++ty) {
+            if ((y + 1 - ty) % 2 != 0 || y + 1 - ty < 0) continue;
+            const int qy = (y + 1 - ty) / 2;
+            if (qy >= hh) continue;
+            for (int tx = 0; tx < 4; ++tx) {
+              if ((x + 1 - tx) % 2 != 0 || x + 1 - tx < 0) continue;
+              const int qx = (x + 1 - tx) / 2;
+              if (qx >= ww) continue;
+              acc += O[((ll)img * P + qy * ww + qx) * VD + (ty * 4 + tx) * FC + c];
+            }
+          }
+          st1((uint16_t*)Y + (((ll)img * h + y) * w + x) * FC + c, yplane, acc * 0.25f);
+        }
+  ++g_launches;
+  return 0;
+}
+
+int tcv_head_tanh01(const void* x, long long x_plane, long long pixels, int c, float* pred, tcv_stream_t) {
+  if (x_plane == 0) x_plane = pixels * c;
+  for (ll i = 0; i < pixels; ++i) pred[i] = (tanhf(ld1((const uint16_t*)x + i * c, x_plane)) + 1.0f) * 0.5f;
+  ++g_launches;
+  return 0;
+}
+
+int tcv_split_to_nchw(const void* x, int n, int c, int h, int w, int c_pad, long long x_plane, float* y, tcv_stream_t) {
+  const ll hw = (ll)h * w;
+  if (x_plane == 0) x_plane = (ll)n * hw * c_pad;
+  for (ll i = 0; i < (ll)n * c * hw; ++i) {
+    const ll p = i % hw, img = i / (hw * c);
+    const int cc = (int)((i / hw) % c);
+    y[i] = ld1((const uint16_t*)x + (img * hw + p) * c_pad + cc, x_plane);
+  }
+  ++g_launches;
+  return 0;
 }
 
 int tcv_nchw_to_split(const float* x, int n, int c, int h, int w, int c_pad, void* y, long long y_plane, tcv_stream_t) {
