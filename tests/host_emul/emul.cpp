@@ -277,11 +277,13 @@ int tcv_unknown_os8(const void* x8, int n, int h, int w, float* unknown, tcv_str
 // GCA/ops.py:106-229 (see the header): g [n,h/2,w/2,64] split-bf16 (guidance_conv at stride 2), unknown fp32 [n,h,w]
 int tcv_gca_prep(const void* g, const float* unknown, int n, int h, int w, void* Qv, void* Knv, float* mm, float* scales,
                  int bf16_split, tcv_stream_t) {
-  REQ(bf16_split == 0, "gca_prep: the test double provides the fp32 operand format only");
+  REQ(bf16_split == 0 || bf16_split == 2 || bf16_split == 3, "gca_prep: planes must be 0, 2 or 3");
   const int hh = h / 2, ww = w / 2, P = hh * ww, GC = 64, QD = 576;
   const ll gplane = (ll)n * P * GC;
-  float* Q = (float*)Qv;
-  float* Kn = (float*)Knv;
+  std::vector<float> qbuf, kbuf;
+  if (bf16_split) { qbuf.resize((size_t)n * P * QD); kbuf.resize((size_t)n * P * QD); }
+  float* Q = bf16_split ? qbuf.data() : (float*)Qv;
+  float* Kn = bf16_split ? kbuf.data() : (float*)Knv;
   for (int img = 0; img < n; ++img) {
     const float* u = unknown + (ll)img * h * w;
     double s = 0.0;
@@ -310,15 +312,30 @@ int tcv_gca_prep(const void* g, const float* unknown, int n, int h, int w, void*
       mm[(ll)img * P + p] = m;
     }
   }
+  if (bf16_split) {   // bf16 planes [split][n][P][576]: hi, (mid,) lo
+    const ll plane = (ll)n * P * QD;
+    for (ll i = 0; i < plane; ++i) {
+      float a = Q[i], b = Kn[i];
+      for (int pl = 0; pl < bf16_split; ++pl) {
+        const uint16_t ha = f_to_bf(a), hb = f_to_bf(b);
+        ((uint16_t*)Qv)[pl * plane + i] = ha;
+        ((uint16_t*)Knv)[pl * plane + i] = hb;
+        a -= bf_to_f(ha);
+        b -= bf_to_f(hb);
+      }
+    }
+  }
   ++g_launches;
   return 0;
 }
 
 int tcv_gca_values(const void* feat, int n, int h, int w, void* Vtv, int mode, tcv_stream_t) {
-  REQ(mode == 0, "gca_values: the test double provides the fp32 operand format only");
+  REQ(mode >= 0 && mode <= 2, "gca_values: the test double provides fp32 / bf16 / split-bf16 operands (not fp16)");
   const int hh = h / 2, ww = w / 2, P = hh * ww, P_pad = (P + 63) / 64 * 64, FC = 128, VD = 2048;
   const ll fplane = (ll)n * h * w * FC;
-  float* Vt = (float*)Vtv;
+  std::vector<float> vbuf;
+  if (mode) vbuf.resize((size_t)n * VD * P_pad);
+  float* Vt = mode ? vbuf.data() : (float*)Vtv;
   for (int img = 0; img < n; ++img)
     for (int t = 0; t < 16; ++t)
       for (int c = 0; c < FC; ++c)
@@ -331,6 +348,13 @@ int tcv_gca_values(const void* feat, int n, int h, int w, void* Vtv, int mode, t
           }
           Vt[((ll)img * VD + t * FC + c) * P_pad + p] = val;
         }
+  if (mode) {
+    const ll total = (ll)n * VD * P_pad;
+    for (ll i = 0; i < total; ++i) {
+      if (mode == 1) ((uint16_t*)Vtv)[i] = f_to_bf(Vt[i]);
+      else st1((uint16_t*)Vtv + i, total, Vt[i]);
+    }
+  }
   ++g_launches;
   return 0;
 }
@@ -351,8 +375,8 @@ int tcv_gemm_tn_f32(const float* A, const float* B, float* C, int M, int N, int 
   return 0;
 }
 
-int tcv_gca_softmax(float* S, const float* mm, int n, int P, int P_pad, void*, int mode, tcv_stream_t) {
-  REQ(mode == 0, "gca_softmax: the test double provides the fp32 operand format only");
+int tcv_gca_softmax(float* S, const float* mm, int n, int P, int P_pad, void* P_out, int mode, tcv_stream_t) {
+  REQ(mode >= 0 && mode <= 2 && (mode == 0 || P_out), "gca_softmax: fp32 / bf16 / split-bf16 outputs only");
   for (int img = 0; img < n; ++img)
     for (int q = 0; q < P; ++q) {
       float* row = S + ((ll)img * P + q) * P_pad;
@@ -363,7 +387,48 @@ int tcv_gca_softmax(float* S, const float* mm, int n, int P, int P_pad, void*, i
       for (int p = 0; p < P; ++p) { row[p] = expf(row[p] - mx); sum += row[p]; }
       for (int p = 0; p < P; ++p) row[p] /= sum;
       for (int p = P; p < P_pad; ++p) row[p] = 0.f;
+      if (mode) {
+        const ll plane = (ll)n * P * P_pad, o = ((ll)img * P + q) * P_pad;
+        for (int p = 0; p < P_pad; ++p) {
+          if (mode == 1) ((uint16_t*)P_out)[o + p] = f_to_bf(row[p]);
+          else st1((uint16_t*)P_out + o + p, plane, row[p]);
+        }
+      }
     }
+  ++g_launches;
+  return 0;
+}
+
+// C[b] = A[b] * B[b]^T with bf16 operand planes (see tcv_gemm_tn_tc in the header): nsplit 1: Ahi.Bhi; 3: hi.hi + hi.lo +
+// lo.hi; 6: three planes, hh + hm + mh + hl + lh + mm.  fp32 accumulation, fp32 output.
+int tcv_gemm_tn_tc(const void* A, long long a_plane, const void* B, long long b_plane, void* C, int M, int N, int K,
+                   long long ldc, long long c_batch_stride, int batch, int nsplit, int out_bf16, int in_fp16, tcv_stream_t) {
+  REQ(!out_bf16 && !in_fp16, "gemm_tn_tc: the test double provides bf16 operands and fp32 output only");
+  REQ(nsplit == 1 || nsplit == 3 || nsplit == 6, "gemm_tn_tc: nsplit");
+  REQ(K % 64 == 0, "gemm_tn_tc: K % 64");
+  const int np = nsplit == 1 ? 1 : (nsplit == 3 ? 2 : 3);
+  // which (plane of A, plane of B) products are summed
+  const int pairs[6][2] = {{0, 0}, {0, 1}, {1, 0}, {0, 2}, {2, 0}, {1, 1}};
+  std::vector<float> af((size_t)np * M * K), bf((size_t)np * N * K);
+  for (int b = 0; b < batch; ++b) {
+    for (int pl = 0; pl < np; ++pl) {
+      for (ll i = 0; i < (ll)M * K; ++i) af[(ll)pl * M * K + i] = bf_to_f(((const uint16_t*)A)[pl * a_plane + (ll)b * M * K + i]);
+      for (ll i = 0; i < (ll)N * K; ++i) bf[(ll)pl * N * K + i] = bf_to_f(((const uint16_t*)B)[pl * b_plane + (ll)b * N * K + i]);
+    }
+#pragma omp parallel for schedule(static)
+    for (int m = 0; m < M; ++m)
+      for (int nn = 0; nn < N; ++nn) {
+        float acc = 0.f;
+        for (int t = 0; t < nsplit; ++t) {
+          const float* a = af.data() + (ll)pairs[t][0] * M * K + (ll)m * K;
+          const float* bb = bf.data() + (ll)pairs[t][1] * N * K + (ll)nn * K;
+          float s2 = 0.f;
+          for (int k = 0; k < K; ++k) s2 += a[k] * bb[k];
+          acc += s2;
+        }
+        ((float*)C)[b * c_batch_stride + (ll)m * ldc + nn] = acc;
+      }
+  }
   ++g_launches;
   return 0;
 }

@@ -1,7 +1,7 @@
 """Host-logic tests of the vmn_gca inference path in the GPU-less build container: the program of GcaVmnEngine (weight
 folding / packing, which C-ABI calls run on which buffers, the recorded plan) is executed on host memory against the
-test double of the C ABI (tests/host_emul/emul.cpp: naive restatements of every entry point the eval path uses, fp32
-operand formats for the attention GEMMs) and compared with the golden vectors produced by the unmodified reference.
+test double of the C ABI (tests/host_emul/emul.cpp: naive restatements of every entry point the eval path uses, incl. the
+bf16 operand planes of the attention GEMMs) and compared with the golden vectors produced by the unmodified reference.
 Test infrastructure only; the real parity tests are the ``-m gpu`` ones."""
 import numpy as np
 import pytest
@@ -28,8 +28,7 @@ def make_gca_engine(window=7):
 
     eng = HostEmuEngine(window)
     eng.device = torch.device("cpu")
-    eng.use_tc_attn = False            # the double provides the fp32 operand formats of the attention kernels
-    return eng
+    return eng                         # default program: bf16x3 operand planes for both attention GEMMs (use_tc_attn)
 
 
 def record_eval(eng, B, S, H, W, dil, u8):
@@ -81,6 +80,26 @@ def test_window_program_matches_reference_golden(emu, case):
     for mine, ref in ((io["attb"][:, 0], g["attb1"]), (io["attf"][:, 0], g["attf1"])):
         assert np.abs(mine.numpy() - ref).max() <= 2e-3 * max(1.0, np.abs(ref).max())
     assert float(io["alphas"][:, 0].abs().max()) == 0 and float(io["alphas"][:, -1].abs().max()) == 0
+
+
+@pytest.mark.parametrize("variant", ["fp32_attn", "six_term_scores", "bf16_pv"])
+def test_attention_program_variants(emu, variant):
+    """The other operand formats of the attention program: exact fp32 GEMMs (TCV_TC_ATTN=0), three-plane scores
+    (TCV_SCORE_PLANES=3), single-plane bf16 aggregation (TCV_PV_MODE=bf16; known to miss 1e-3: only its wiring)."""
+    g = golden("eval_ring64.npz")
+    eng = make_gca_engine()
+    if variant == "fp32_attn":
+        eng.use_tc_attn = False
+    elif variant == "six_term_scores":
+        eng.score_planes = 3
+    else:
+        eng.pv_mode = "bf16"
+    eng.refresh_weights(_net())
+    imgs, tris = torch.from_numpy(g["imgs"]), torch.from_numpy(g["tris"])
+    plan, io = record_eval(eng, 1, 3, 64, 64, -1, True)
+    io["imgs"].copy_(imgs); io["tris"].copy_(tris)
+    plan.replay(0)
+    assert np.abs(io["alphas"].numpy() - g["alphas"]).max() < (2e-2 if variant == "bf16_pv" else 1e-3)
 
 
 def test_cuda_core_conv_program_matches_too(emu):
