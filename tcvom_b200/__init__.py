@@ -4,7 +4,7 @@ Public surface mirrors the reference's operator/plugin interface for this path:
 ``get_VMN_models``, ``VMN``, ``FeatureAggregationModule``, ``GuidedCxtAtten``, ``EvalModel``.
 """
 from .model import (EvalModel, FeatureAggregationModule, FullModel, FullModel_VMD, GuidedCxtAtten, VMN,  # noqa: F401
-                    VMN_FBA, get_VMN_models)
+                    VMN_FBA, get_VMN_models, trimap_transform)
 from .stream import FrameStream  # noqa: F401
 
 __version__ = "0.1.0"

@@ -391,6 +391,38 @@ class VMN_FBA(VMN):
         return preds, attb, attf, small
 
 
+def _trimap_transform_impl(trimap: torch.Tensor, stream_ptr: int) -> torch.Tensor:
+    B, S, C2, H, W = trimap.shape
+    assert C2 == 2, "trimap: tensor [B, S, 2, H, W] (background, foreground one-hot)"
+    L = _cabi.lib()
+    F_ = B * S
+    dev = trimap.device
+    # the distance-transform kernels read their seeds from channels 9 / 10 of the 16-channel FBA input tensor and
+    # write the six features into channels 3..8 (include/tcvom_b200.h, tcv_fba_edt_*)
+    x = torch.zeros((F_, 16, H, W), dtype=torch.float32, device=dev)
+    # seeds = pixels where cv2 sees a zero: ((1 - tk) * 255).astype(uint8) == 0   (utils/utils.py:21,32)
+    x[:, 9:11] = (((1.0 - trimap.reshape(F_, 2, H, W)) * 255).to(torch.uint8) == 0).float()
+    x16 = Act.empty(F_, H, W, 16, dev)
+    g = torch.empty((F_, 2, H, W), dtype=torch.int32, device=dev)
+    out = torch.empty((F_, 16, H, W), dtype=torch.float32, device=dev)
+    _cabi.check(L.tcv_nchw_to_split(x.data_ptr(), F_, 16, H, W, 16, x16.ptr, 0, stream_ptr), "nchw_to_split")
+    _cabi.check(L.tcv_fba_edt_cols(x16.ptr, F_, H, W, g.data_ptr(), stream_ptr), "fba_edt_cols")
+    _cabi.check(L.tcv_fba_edt_rows(g.data_ptr(), F_, H, W, x16.ptr, stream_ptr), "fba_edt_rows")
+    _cabi.check(L.tcv_split_to_nchw(x16.ptr, F_, 16, H, W, 16, 0, out.data_ptr(), stream_ptr), "split_to_nchw")
+    return out[:, 3:9].reshape(B, S, 6, H, W).contiguous()
+
+
+def trimap_transform(trimap: torch.Tensor) -> torch.Tensor:
+    """Drop-in for ``utils.utils.trimap_transform`` (utils/utils.py:25-39): trimap [B,S,2,H,W] (one-hot background /
+    foreground) -> clicks [B,S,6,H,W] = exp(-d^2 / (2 (f*320)^2)), f in (0.02, 0.08, 0.16), d = Euclidean distance to the
+    nearest background resp. foreground pixel.  The reference moves every frame to the host for ``cv2.distanceTransform``;
+    here the exact transform runs on the GPU (``tcv_fba_edt_cols`` / ``tcv_fba_edt_rows``).  A channel without any seed
+    gives zeros (like the reference: cv2 returns +huge there, and :31 skips a kind that is absent from the whole batch);
+    values below 1e-12 are written as exact zeros."""
+    _require_cuda(trimap, "trimap")
+    return _trimap_transform_impl(trimap.float(), _stream(trimap.device))
+
+
 def get_VMN_models(arch, agg_window, agg_reduction=1, freeze_backbone=False, **kwargs):
     """Plugin seam of the reference (models/VMN/__init__.py:11-29)."""
     if arch not in ('vmn_gca', 'vmn_fba'):

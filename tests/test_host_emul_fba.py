@@ -389,3 +389,22 @@ def test_weight_cache_follows_load_state_dict(emu):
         ra, _, _ = O.eval_forward(sd2, imgs.float(), tris.float())
     assert float((io["alphas"] - ra).abs().max()) < 1e-3
     assert float((io["alphas"] - a0).abs().max()) > 1e-3   # and the result did change
+
+
+def test_trimap_transform_operator_matches_reference_semantics(emu):
+    """tcvom_b200.trimap_transform (drop-in for utils/utils.py:25-39) against the oracle's restatement (scipy EDT, pinned
+    to the reference's cv2 output by the fba goldens)."""
+    from oracle import vmn_fba_oracle as O
+    from tcvom_b200.model import _trimap_transform_impl
+    rng = np.random.default_rng(3)
+    t = np.zeros((2, 3, 2, 24, 40), np.float32)
+    u = rng.uniform(size=(2, 3, 24, 40))
+    t[:, :, 0] = u < 0.05
+    t[:, :, 1] = u > 0.97
+    t[1, 2] = 0                                              # a frame without any seed
+    trimap = torch.from_numpy(t)
+    got = _trimap_transform_impl(trimap, 0)
+    ref = O.trimap_transform(trimap)
+    assert got.shape == ref.shape == (2, 3, 6, 24, 40)
+    assert float((got - ref).abs().max()) < 2e-5
+    assert float(got[1, 2].abs().max()) == 0

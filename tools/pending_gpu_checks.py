@@ -87,3 +87,18 @@ def test_fba_five_frame_samples_match_oracle():
         ra, rF, rB = O.eval_forward(sd, ti.float(), tt.float())
     assert float((a.cpu() - ra).abs().max()) < 1e-3
     assert float((Fg.cpu() - rF).abs().max()) < 1e-3 and float((Bg.cpu() - rB).abs().max()) < 1e-3
+
+
+def test_trimap_transform_operator():
+    """tcvom_b200.trimap_transform (drop-in for utils/utils.py:25-39) vs the oracle on a 1088x1920 trimap pair."""
+    import numpy as np
+    import tcvom_b200
+    from oracle import vmn_fba_oracle as O
+    rng = np.random.default_rng(3)
+    u = rng.uniform(size=(1, 2, 1088, 1920))
+    t = np.zeros((1, 2, 2, 1088, 1920), np.float32)
+    t[:, :, 0] = u < 0.0005
+    t[:, :, 1] = u > 0.9999
+    trimap = torch.from_numpy(t)
+    got = tcvom_b200.trimap_transform(trimap.to(DEV)).cpu()
+    assert float((got - O.trimap_transform(trimap)).abs().max()) < 2e-5
