@@ -476,6 +476,11 @@ int tcv_copy_channels(const void* x, long long x_plane, int x_c, int x_off, void
  *                   row (py*2+px)*cin_pad + c = w[ky = 2ty+py+3][kx = 2tx+px+3][c] (zero outside the 7x7 support) */
 int tcv_space_to_depth2(const void* x, long long x_plane, int n, int h, int w, int c, void* y, tcv_stream_t stream);
 int tcv_s2d_pack_stem(const float* w49, int cin_pad, int cout, float* out, tcv_stream_t stream);
+/* the same rewrite for any k x k / stride-2 convolution with zero padding `pad` (pad = 0: pre-padded input):
+ * T x T / stride-1 taps t0 .. t0+T-1, t0 = floor(-pad/2), T = floor((k-1-pad)/2) - t0 + 1 (k3 p1: taps -1..0; k3 p0: 0..1).
+ * src fp32 [k*k][cin_src][cout_src] -> out fp32 [T*T][4*cin_dst][cout_dst] (zero rows / columns for the padding) */
+int tcv_s2d_pack(const float* src, int k, int pad, int cin_src, int cout_src, int cin_dst, int cout_dst, float* out,
+                 tcv_stream_t stream);
 
 /* EvalModel.preprocess for 'fba'.  imgs [F,3,H,W] BGR 0..255 and tris [F,1,H,W] (fp32, or uint8 when is_u8) ->
  * x16 split-bf16 [F,H,W,16]: ch 0..2 normalised RGB, 9 = (tri*1/255 == 0), 10 = (tri*1/255 == 1), 11..13 RGB/255

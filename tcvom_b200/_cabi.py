@@ -164,6 +164,7 @@ SIGNATURES = {
     "tcv_copy_channels": (c_int, [c_void_p, c_ll, c_int, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_ll, c_void_p]),
     "tcv_space_to_depth2": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_s2d_pack_stem": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_s2d_pack": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_fba_encode_inputs": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_fba_edt_cols": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_fba_edt_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -521,4 +521,26 @@ TCV_HD void s2d_pack_stem_body(ll i, const S2dPackP& p) {
   p.out[i] = v;
 }
 
+// generic form of the rewrite: a k x k / stride-2 convolution with zero padding `pad` (or pad = 0 on a pre-padded input)
+// equals a T x T / stride-1 convolution with tap offsets t0 .. t0+T-1 over the 2x2 space-to-depth image:
+// input row 2*oy + ky - pad = 2*(oy + ty) + py  =>  ky = 2*ty + py + pad,  t0 = floor(-pad / 2),  T = floor((k-1-pad)/2) - t0 + 1
+struct S2dPackGenP {
+  const float* src;  // packed k x k weights [k*k][cin_src][cout_src]
+  int k, pad, t0, T, cin_src, cout_src, cin_dst, cout_dst;
+  float* out;        // [T*T][4*cin_dst][cout_dst], tap (ty-t0)*T + (tx-t0), row (py*2+px)*cin_dst + c; zero padding elsewhere
+};
+// work item = one output element; total = T*T * 4*cin_dst * cout_dst
+TCV_HD void s2d_pack_body(ll i, const S2dPackGenP& p) {
+  const int co = (int)(i % p.cout_dst);
+  const int ch = (int)((i / p.cout_dst) % (4 * p.cin_dst));
+  const int t = (int)(i / ((ll)p.cout_dst * 4 * p.cin_dst));
+  const int ty = t / p.T + p.t0, tx = t % p.T + p.t0;
+  const int q = ch / p.cin_dst, c = ch % p.cin_dst;
+  const int ky = 2 * ty + (q >> 1) + p.pad, kx = 2 * tx + (q & 1) + p.pad;
+  float v = 0.f;
+  if (ky >= 0 && ky < p.k && kx >= 0 && kx < p.k && c < p.cin_src && co < p.cout_src)
+    v = p.src[((ll)(ky * p.k + kx) * p.cin_src + c) * p.cout_src + co];
+  p.out[i] = v;
+}
+
 }  // namespace tcv_fba

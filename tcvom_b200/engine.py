@@ -133,6 +133,10 @@ class GcaVmnEngine:
         # bf16 planes per operand of the scores GEMM Q.Kn^T: 2 (three MMAs per K step, shipped) or 3 (six MMAs,
         # fp32-grade logits; measured on B200: no parity gain on any fixture, +0.66 ms per 1080p window)
         self.score_planes = int(os.environ.get("TCV_SCORE_PLANES", "2"))
+        # opt-in (default off, to be A/B-measured on a GPU): the three stride-2 layers with 8 / 16 input channels
+        # (encoder.conv1, guidance_head.1 / .5), which run on the CUDA-core kernel, as stride-1 2x2-tap convolutions over
+        # the 2x2 space-to-depth image on the tcgen05 kernels (same rewrite as the FBA stem, tcv_s2d_pack)
+        self.s2d_stride2 = os.environ.get("TCV_S2D_STRIDE2", "0") == "1"
 
     # ------------------------------------------------------------------ weights
     def _named(self) -> Dict[str, torch.Tensor]:
@@ -193,6 +197,8 @@ class GcaVmnEngine:
                 _cabi.check(L.tcv_bn_fold(named[p + ".weight"].data_ptr(), named[p + ".bias"].data_ptr(),
                                           named[p + ".running_mean"].data_ptr(), t.data_ptr(), BN_EPS, c,
                                           s.data_ptr(), b.data_ptr(), st), "bn_fold")
+        if self.s2d_stride2:
+            self._derive_s2d(L, st)
         self._fingerprint = fp
 
     def _pack(self, L, st, p, wbar, u, v, sig, transposed):
@@ -238,6 +244,62 @@ class GcaVmnEngine:
         self._pack(L, st, key, wpad, None, None, None, transposed=False)      # in place: recorded plans stay valid
         self.w[key]["cout_real"] = 1
         self.bias[key] = bpad
+
+    S2D = "#s2d"
+    # (layer, zero padding of the 3x3 / stride-2 conv: 1 = zero-padded input, 0 = reflect border materialised first,
+    #  input channels per sub-pixel, output channels incl. padding, BatchNorm whose affine needs the same padding)
+    S2D_LAYERS = (("encoder.conv1", 1, 8, 32, None),
+                  ("encoder.guidance_head.1", 0, 8, 32, "encoder.guidance_head.3"),
+                  ("encoder.guidance_head.5", 0, 32, 32, None))
+
+    def _derive_s2d(self, L, st) -> None:
+        """Space-to-depth forms of the stride-2 layers (opt-in TCV_S2D_STRIDE2): weights [T*T][4*cin][cout] + their
+        tensor-core copies, zero-padded BatchNorm affines.  Updated in place like every other derived buffer."""
+        for key, pad, cin_dst, cout_dst, bn in self.S2D_LAYERS:
+            if key not in self.w:
+                continue
+            src = self.w[key]
+            assert src["k"] == 3 and src["cin"] <= cin_dst and src["cout"] <= cout_dst, key
+            ent = self.w.get(key + self.S2D)
+            dev = src["w"].device
+            if ent is None:
+                ent = self.w[key + self.S2D] = dict(
+                    w=torch.empty((4, 4 * cin_dst, cout_dst), dtype=torch.float32, device=dev),
+                    w_tc=torch.empty((2, 4, cout_dst, 4 * cin_dst), dtype=torch.bfloat16, device=dev),
+                    cout=cout_dst, cin=4 * cin_dst, cin_real=4 * src.get("cin_real", src["cin"]), k=2, transposed=False,
+                    t0=-1 if pad else 0)
+            _cabi.check(L.tcv_s2d_pack(src["w"].data_ptr(), 3, pad, src["cin"], src["cout"], cin_dst, cout_dst,
+                                       ent["w"].data_ptr(), st), "s2d_pack")
+            _cabi.check(L.tcv_pack_weight_tc(ent["w"].data_ptr(), 4, 4 * cin_dst, cout_dst, ent["w_tc"].data_ptr(), st),
+                        "pack_weight_tc")
+            if bn is not None and bn in self.aff:
+                sc, sh = self.aff[bn]
+                pk = bn + self.S2D
+                if pk not in self.aff or self.aff[pk][0].device != dev:
+                    self.aff[pk] = (torch.zeros(cout_dst, dtype=torch.float32, device=dev),
+                                    torch.zeros(cout_dst, dtype=torch.float32, device=dev))
+                with torch.no_grad():
+                    self.aff[pk][0][: sc.numel()].copy_(sc)
+                    self.aff[pk][1][: sh.numel()].copy_(sh)
+
+    def conv_s2d(self, x: Act, wkey: str, *, bn: Optional[str] = None, act=ACT_NONE, bn2: Optional[str] = None) -> Act:
+        """3x3 / stride-2 convolution of `x` through its space-to-depth form: x [n,h,w,c] -> [n,h/2,w/2,4c], then a
+        stride-1 2x2-tap convolution (taps -1..0 for a zero-padded conv; 0..1 when `x` already carries its border)."""
+        ent = self.w[wkey + self.S2D]
+        assert x.h % 2 == 0 and x.w % 2 == 0 and ent["cin"] == 4 * x.c, (wkey, ent["cin"], x.c)
+        assert x.plane == x.n * x.img_elems
+        xs = self._act(x.n, x.h // 2, x.w // 2, 4 * x.c)
+        self._call("tcv_space_to_depth2", x.ptr, x.plane, x.n, x.h, x.w, x.c, xs.ptr,
+                   meta=dict(kind="tcv_space_to_depth2", bytes=8 * x.n * x.img_elems))
+        t0 = ent["t0"]
+        taps = [(ty, tx) for ty in (t0, t0 + 1) for tx in (t0, t0 + 1)]
+        oh, ow = (xs.h, xs.w) if t0 < 0 else (xs.h - 1, xs.w - 1)
+        cout = ent["cout"]
+        y = self._act(x.n, oh, ow, cout)
+        d = self._desc(xs, ent["w"].data_ptr(), taps, 1, PAD_ZERO, y, oh, ow, cout, oh, ow, 1, 0, 1, 0, wkey + self.S2D,
+                       bn, False, act, None, 0, bn2, None, 0)
+        self._call("tcv_conv2d", C.byref(d), meta=self._conv_meta(d, wkey + self.S2D, xs, 2, 1))
+        return y
 
     def get_plan(self, key) -> Optional[Plan]:
         plan = self.plans.get(key)
@@ -499,12 +561,21 @@ class GcaVmnEngine:
     def per_frame(self, x8: Act) -> dict:
         """encoder + decoder head for all frames at once (VMN_model.py:93-98)."""
         e = "encoder"
-        c1 = self.conv(x8, e + ".conv1", stride=2, bn=e + ".bn1", act=ACT_RELU)
+        s2d = self.s2d_stride2 and self.use_tc_conv
+        if s2d:
+            c1 = self.conv_s2d(x8, e + ".conv1", bn=e + ".bn1", act=ACT_RELU)
+        else:
+            c1 = self.conv(x8, e + ".conv1", stride=2, bn=e + ".bn1", act=ACT_RELU)
         x1 = self.conv(c1, e + ".conv2", bn=e + ".bn2", act=ACT_RELU)
         c3 = self.conv(x1, e + ".conv3", stride=2, bn=e + ".bn3", act=ACT_RELU)
         g = x8
         for ci, bi in ((1, 3), (5, 7), (9, 11)):                                # guidance head (res_gca_enc.py:20-33)
-            if self.use_tc_conv and g.c % 32 == 0:
+            if s2d and ci in (1, 5):
+                # reflect border materialised once, then the space-to-depth form (output channels of .1 padded 16 -> 32
+                # with zero weights / affine, which .5 reads through zero weight rows)
+                g = self.conv_s2d(self.pad_reflect1(g), f"{e}.guidance_head.{ci}", act=ACT_RELU,
+                                  bn2=f"{e}.guidance_head.{bi}" + (self.S2D if ci == 1 else ""))
+            elif self.use_tc_conv and g.c % 32 == 0:
                 # 32 -> 128: reflect border materialised once, then the stride-2 tcgen05 path
                 g = self.conv(self.pad_reflect1(g), f"{e}.guidance_head.{ci}", stride=2, prepadded=True, act=ACT_RELU,
                               bn2=f"{e}.guidance_head.{bi}")

@@ -681,6 +681,14 @@ int tcv_s2d_pack_stem(const float* w49, int cin_pad, int cout, float* out, tcv_s
   return run_body<S2dPackP, s2d_pack_stem_body>(p, (ll)16 * 4 * cin_pad * cout);
 }
 
+static int floordiv2(int a) { return a >= 0 ? a / 2 : -((-a + 1) / 2); }
+int tcv_s2d_pack(const float* src, int k, int pad, int cin_src, int cout_src, int cin_dst, int cout_dst, float* out,
+                 tcv_stream_t) {
+  const int t0 = floordiv2(-pad), T = floordiv2(k - 1 - pad) - t0 + 1;
+  S2dPackGenP p{src, k, pad, t0, T, cin_src, cout_src, cin_dst, cout_dst, out};
+  return run_body<S2dPackGenP, s2d_pack_body>(p, (ll)T * T * 4 * cin_dst * cout_dst);
+}
+
 int tcv_postprocess_eval_fba(const float* pred, const void* imgs, const void* tris, int is_u8, const float* trimask,
                              int batch, int frames, int h, int w, float* alphas, float* Fs, float* Bs, tcv_stream_t) {
   PostP p{pred, imgs, tris, is_u8, trimask, batch, frames, h, w, alphas, Fs, Bs};

@@ -147,3 +147,25 @@ def test_frame_stream_gca_equals_windowed_program(emu):
         io["imgs"].copy_(imgs[:, t - 1:t + 2]); io["tris"].copy_(tris[:, t - 1:t + 2])
         plan.replay(0)
         assert float((outs[t + 1] - io["alphas"][0, 1]).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("case", ["ring64", "dil64x96"])
+def test_space_to_depth_stride2_program(emu, case):
+    """Opt-in TCV_S2D_STRIDE2 program: encoder.conv1 and guidance_head.1 / .5 (3x3, stride 2; zero resp. reflect padding)
+    as 2x2-tap stride-1 convolutions over the 2x2 space-to-depth image == the default program, and the goldens."""
+    g = golden(f"eval_{case}.npz")
+    imgs, tris = torch.from_numpy(g["imgs"]), torch.from_numpy(g["tris"])
+    B, S, _, H, W = imgs.shape
+    res = {}
+    for s2d in (False, True):
+        eng = make_gca_engine()
+        eng.s2d_stride2 = s2d
+        eng.refresh_weights(_net())
+        plan, io = record_eval(eng, B, S, H, W, int(g["dilate"]), True)
+        io["imgs"].copy_(imgs); io["tris"].copy_(tris)
+        plan.replay(0)
+        res[s2d] = io["alphas"].clone()
+        kinds = [m["kind"] for m in plan.meta]
+        assert ("tcv_space_to_depth2" in kinds) == s2d
+    assert np.abs(res[True].numpy() - g["alphas"]).max() < 1e-3
+    assert float((res[True] - res[False]).abs().max()) < 5e-5
