@@ -59,7 +59,7 @@ def make_window(H: int, W: int, seed: int = 7, frames: int = 3, batch: int = 1,
         for s in range(frames):
             for c in range(3):
                 tex = _upsample_bilinear(base[c], H + 16, W + 16)
-                oy, ox = 2 * s, 3 * s                       # texture drifts 2-3 px per frame
+                oy, ox = (2 * s) % 17, (3 * s) % 17         # texture drifts 2-3 px per frame (wraps inside the 16 px margin)
                 t = tex[oy:oy + H, ox:ox + W] + rng.normal(0, 4.0, size=(H, W))
                 imgs[b, s, c] = np.clip(np.floor(t), 0, 255).astype(np.uint8)
             if trimap == "all_unknown":

@@ -1,19 +1,13 @@
-"""GPU checks written after round 1's GPU budget was spent, so they live here and not under tests/ until they have run
-green on a B200 once:   python -m pytest tools/pending_gpu_checks.py -q -m gpu     (then move them under tests/).
-Their host logic is already covered on the CPU by tests/test_host_emul_fba.py (C-ABI test double).
+"""GPU tests of tcvom_b200.FrameStream (per-frame feature reuse across sliding windows), the
+FBA path at S=5 / B=2 and the trimap_transform drop-in (first green on a B200 in round 2, gpurun call 1).
 
-GPU tests of tcvom_b200.FrameStream (per-frame feature reuse across sliding windows):
-the streamed mattes must equal what EvalModel.forward returns for every 3-frame window of the clip (same kernels on
+The streamed mattes must equal what EvalModel.forward returns for every 3-frame window of the clip (same kernels on
 the same values; the FBA path's GroupNorm sums are grouped differently for 1 and 3 images per launch -- fp64 partials, but a
 scale / shift can land on the neighbouring float -- hence a 5e-5 bound there instead of bit equality)."""
 import pytest
 import torch
 
-import os
-import sys
-
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
-from helpers import fixture_sd, fixture_sd_fba  # noqa: E402
+from helpers import fixture_sd, fixture_sd_fba
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 {
   echo "== pending GPU checks (FrameStream == windowed forward, FBA S=5/B=2, trimap_transform)"
-  timeout 120 python -m pytest tools/pending_gpu_checks.py -q -m gpu -p no:cacheprovider 2>&1 | tail -5
+  timeout 120 python -m pytest tests/test_gpu_z_stream.py -q -m gpu -p no:cacheprovider 2>&1 | tail -5
   echo "== FrameStream frames/s vs windowed"
   timeout 90 python tools/stream_bench.py vmn_gca 1088 1920 12 2>&1 | tail -1
   timeout 90 python tools/stream_bench.py vmn_fba 1088 1920 8 2>&1 | tail -1
