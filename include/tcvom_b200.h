@@ -196,6 +196,30 @@ int tcv_gca_softmax(float* S, const float* mm, int n, int P, int P_pad, void* P_
                     tcv_stream_t stream);
 int tcv_gca_fold(const float* O, int n, int h, int w, void* Y, tcv_stream_t stream);
 
+/* ---- shift-sum form of the aggregation  fold(A.V; k4,s2,p1)/4  (GCA/ops.py:112-118,204; tcvom_b200/csrc/gca.cu):
+ * with hh = h/2, ww = w/2, the key grid padded to (hh+1) x (ww+1) (Pk positions, ld = Pk rounded up to 64),
+ *     Y[2my+ry-1][2mx+rx-1][c] = 1/4 * sum_p' A2[m][p'] * F_r[p'][c],    A2[m][p'] = sum_{a in {0,1}^2} A[m-a][p'-a]
+ * -- one [Pk x ld].[ld x 512] GEMM instead of [P x P].[P x 2048] + overlap-add (3.8x fewer FLOPs, exact).
+ *  prep_grid:     like tcv_gca_prep(bf16_split = 2), but Kn rows live on the padded key grid: Kn bf16 planes [2][n][Pk][576],
+ *                 row py*(ww+1)+px, zero rows at px == ww / py == hh.  S = Q.Kn^T is then fp32 [n][P][ld].
+ *  values_parity: feat split-bf16 [n,h,w,128] -> Ft planes [2][n][512][ld], row (ry*2+rx)*128+c, column p' on the padded grid
+ *                 = feat_reflect[2p'y+ry-1][2p'x+rx-1][c]; columns >= Pk zero
+ *  rowstats:      stats fp32 [n][P][2] = (max, 1/sum exp) of S[q][:] - 1e4*[key == q]*mm[q] over the real key columns;
+ *                 normalise != 0: S is overwritten by A = softmax (zeros at the pad columns)
+ *  shift_add:     A2 planes [2][n][Pk][ld] from the normalised A [n][P][ld] (rowstats with normalise): 4 shifted row reads
+ *  softmax_shift: A2 planes [2][n][Pk][ld]: A2[m][j] = sum_a softmax(S)[m-a][j - (ay*(ww+1)+ax)] (pad columns zero),
+ *                 from S and stats (rowstats without normalise): same result as shift_add, exponentials in the consumer
+ *  unfold_parity: O2 fp32 [n][Pk][512] -> Y split-bf16 [n,h,w,128] (each output pixel read from exactly one entry, /4) */
+int tcv_gca_prep_grid(const void* g, const float* unknown, int n, int h, int w, void* Q, void* Kn, float* mm,
+                      float* scales, tcv_stream_t stream);
+int tcv_gca_values_parity(const void* feat, int n, int h, int w, int ld, void* Ft, tcv_stream_t stream);
+int tcv_gca_rowstats(float* S, const float* mm, int n, int h, int w, int ld, float* stats, int normalise,
+                     tcv_stream_t stream);
+int tcv_gca_shift_add(const float* A, int n, int h, int w, int ld, void* A2, tcv_stream_t stream);
+int tcv_gca_softmax_shift(const float* S, const float* stats, const float* mm, int n, int h, int w, int ld, void* A2,
+                          tcv_stream_t stream);
+int tcv_gca_unfold_parity(const float* O2, int n, int h, int w, void* Y, tcv_stream_t stream);
+
 /* C[b] = A[b] * B[b]^T, fp32 row-major, A [M,K] lda, B [N,K] ldb, C [M,N] ldc, K % 8 == 0,
  * batch strides in elements. */
 int tcv_gemm_tn_f32(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb,

@@ -99,6 +99,13 @@ SIGNATURES = {
     "tcv_gemm_tn_tc": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_ll, c_ll, c_int,
                                c_int, c_int, c_int, c_void_p]),
     "tcv_gca_fold": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_gca_prep_grid": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]),
+    "tcv_gca_values_parity": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_gca_rowstats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "tcv_gca_shift_add": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_gca_softmax_shift": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_gca_unfold_parity": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_gemm_tn_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_ll, c_ll, c_ll, c_int, c_void_p]),
     "tcv_tam_attend": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int,

@@ -334,3 +334,380 @@ int tcv_gca_fold(const float* O, int n, int h, int w, void* Y, tcv_stream_t stre
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// Shift-sum form of the aggregation  Y = fold(A.V; k4,s2,p1)/4  (ops.py:112-118,204).
+//
+// Tap k = 2a + r (a, r in {0,1} per axis) of patch q = (qy,qx) lands on output row 2(qy+ay)+ry-1 and reads, through A[q,p],
+// feature row 2(py+ay)+ry-1 of the reflect-padded feature.  With m = q + a and p' = p + a on the (hh+1) x (ww+1) grid:
+//     Y[2my+ry-1][2mx+rx-1][c] = 1/4 * sum_p' A2[m][p'] * F_r[p'][c]
+//     A2[m][p'] = sum_{a in {0,1}^2} A[m-a][p'-a]            (terms outside the hh x ww patch grid are zero)
+//     F_r[p'][c] = feat_reflect[2p'y+ry-1][2p'x+rx-1][c]     (4 parities x 128 channels = 512 columns)
+// i.e. ONE [Pk x Pk].[Pk x 512] GEMM (Pk = (hh+1)(ww+1)) instead of [P x P].[P x 2048] followed by an overlap-add:
+// 3.8x fewer FLOPs, every output pixel written exactly once.  Exact (a re-association of the same sums).
+//
+// To make "p' - a" a plain column shift the KEYS live on the padded grid: Kn row index = py*(ww+1)+px with zero rows at
+// px == ww / py == hh, so S = Q.Kn^T is [P][ld] (ld = Pk rounded up to 64) and A2[m][j] = sum_a A[m-a][j - (ay*(ww+1)+ax)].
+// =====================================================================================================================
+namespace tcv {
+
+// zero rows of Kn at the pad positions of the (hh+1) x (ww+1) key grid: one warp per (pad row, plane, image)
+__global__ void gca_kn_pad_zero_kernel(__nv_bfloat16* __restrict__ Kn, int n, int hh, int ww, int planes) {
+  const int Pk = (hh + 1) * (ww + 1), npad = hh + ww + 1;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= npad * planes * n) return;
+  const int i = warp % npad, pl = (warp / npad) % planes, img = warp / (npad * planes);
+  const int row = i < hh ? i * (ww + 1) + ww : hh * (ww + 1) + (i - hh);
+  uint4* dst = reinterpret_cast<uint4*>(Kn + ((long long)(pl * n + img) * Pk + row) * QD);
+  for (int k = lane; k < QD * 2 / 16; k += 32) dst[k] = make_uint4(0, 0, 0, 0);
+}
+
+// one warp per patch; like gca_prep_kernel<2> but Kn rows on the padded key grid
+__global__ void gca_prep_grid_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ unknown, int n, int h,
+                                     int w, const float* __restrict__ scales, __nv_bfloat16* __restrict__ Qo,
+                                     __nv_bfloat16* __restrict__ Ko, float* __restrict__ mm) {
+  const int hh = h / 2, ww = w / 2, P = hh * ww, Pk = (hh + 1) * (ww + 1);
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n * P) return;
+  const int img = warp / P, p = warp - img * P;
+  const int py = p / ww, px = p - py * ww;
+  const long long gplane = (long long)n * P * GC;
+  const __nv_bfloat16* gi = g + (long long)img * P * GC;
+  const float* u = unknown + (long long)img * h * w;
+  float q[18];
+  float ss = 0.f, usum = 0.f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int yy = reflect(py + t / 3 - 1, hh), xx = reflect(px + t % 3 - 1, ww);
+    const __nv_bfloat16* src = gi + ((long long)yy * ww + xx) * GC + 2 * lane;
+    const uint32_t a = *reinterpret_cast<const uint32_t*>(src);
+    const uint32_t b = *reinterpret_cast<const uint32_t*>(src + gplane);
+    q[2 * t] = __uint_as_float(a << 16) + __uint_as_float(b << 16);
+    q[2 * t + 1] = __uint_as_float(a & 0xffff0000u) + __uint_as_float(b & 0xffff0000u);
+    ss += q[2 * t] * q[2 * t] + q[2 * t + 1] * q[2 * t + 1];
+    usum += u[(2 * yy) * w + 2 * xx];
+  }
+  ss = warp_sum(ss);
+  const float m = usum > 0.f ? 1.f : 0.f;
+  const float scale = m > 0.f ? scales[2 * img] : scales[2 * img + 1];
+  const float inv = scale / fmaxf(sqrtf(ss), 1e-4f);
+  __nv_bfloat16* qo = Qo + ((long long)img * P + p) * QD;
+  __nv_bfloat16* ko = Ko + ((long long)img * Pk + py * (ww + 1) + px) * QD;
+  const long long qplane = (long long)n * P * QD, kplane = (long long)n * Pk * QD;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    uint32_t hi, lo;
+    split2_bf16(q[2 * t], q[2 * t + 1], hi, lo);
+    *reinterpret_cast<uint32_t*>(qo + t * GC + 2 * lane) = hi;
+    *reinterpret_cast<uint32_t*>(qo + qplane + t * GC + 2 * lane) = lo;
+    split2_bf16(q[2 * t] * inv, q[2 * t + 1] * inv, hi, lo);
+    *reinterpret_cast<uint32_t*>(ko + t * GC + 2 * lane) = hi;
+    *reinterpret_cast<uint32_t*>(ko + kplane + t * GC + 2 * lane) = lo;
+  }
+  if (lane == 0) mm[(long long)img * P + p] = m;
+}
+
+// Ft[img][(ry*2+rx)*128 + c][p'] = feat_reflect[2p'y+ry-1][2p'x+rx-1][c] on the (hh+1)x(ww+1) grid, split-bf16 planes
+// [2][n][512][ld].  Block = (64 consecutive p', parity r, image): coalesced pixel reads, smem transpose, 64-p' row segments.
+__global__ void __launch_bounds__(256) gca_values_parity_kernel(const __nv_bfloat16* __restrict__ feat, int n, int h,
+                                                                int w, int ld, __nv_bfloat16* __restrict__ Ft) {
+  __shared__ float tile[64][FC + 1];
+  const int hh = h / 2, ww = w / 2, Pk = (hh + 1) * (ww + 1);
+  const int p0 = blockIdx.x * 64, r = blockIdx.y, img = blockIdx.z;
+  const int ry = r >> 1, rx = r & 1;
+  const long long fplane = (long long)n * h * w * FC;
+  for (int i = threadIdx.x; i < 64 * (FC / 8); i += 256) {
+    const int pp = i / (FC / 8), c8 = (i % (FC / 8)) * 8;
+    const int p = p0 + pp;
+    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (p < Pk) {
+      const int py = p / (ww + 1), px = p - py * (ww + 1);
+      const int yy = reflect(2 * py + ry - 1, h), xx = reflect(2 * px + rx - 1, w);
+      load8(feat + (((long long)img * h + yy) * w + xx) * FC + c8, fplane, f);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tile[pp][c8 + k] = f[k];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long total = (long long)n * 4 * FC * ld;
+  for (int c = warp; c < FC; c += 8) {
+    const long long o = ((long long)img * 4 * FC + r * FC + c) * ld + p0;
+    uint32_t hi, lo;
+    split2_bf16(tile[2 * lane][c], tile[2 * lane + 1][c], hi, lo);
+    *reinterpret_cast<uint32_t*>(Ft + o + 2 * lane) = hi;
+    *reinterpret_cast<uint32_t*>(Ft + total + o + 2 * lane) = lo;
+  }
+}
+
+// validity of key-grid column j (a real patch, not a pad position) and the logit with the self-mask applied
+struct KeyGrid {
+  int ww1, Pv;   // ww + 1 ; hh * (ww+1): columns >= Pv are the pad row / beyond the grid
+  __device__ __forceinline__ bool valid(int j) const { return j >= 0 && j < Pv && (j % ww1) != ww1 - 1; }
+};
+
+// stats[img][q] = (row max, 1 / sum exp) of S[q][:] - 1e4*[col == q]*mm[q] over the valid key columns; one CTA per row
+template <bool NORMALISE>
+__global__ void __launch_bounds__(256) gca_rowstats_kernel(const float* __restrict__ S, const float* __restrict__ mm,
+                                                           int hh, int ww, int ld, float2* __restrict__ stats) {
+  extern __shared__ float srow[];   // ld floats
+  __shared__ float red[8];
+  __shared__ float bcast;
+  const int P = hh * ww;
+  const int q = blockIdx.x, img = blockIdx.y;
+  const KeyGrid kg{ww + 1, hh * (ww + 1)};
+  const int qj = (q / ww) * (ww + 1) + (q % ww);
+  const float* row = S + ((long long)img * P + q) * ld;
+  const float diag = -1e4f * mm[(long long)img * P + q];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float mx = -INFINITY;
+  for (int j4 = threadIdx.x * 4; j4 < ld; j4 += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(row + j4);
+    float e[4] = {v.x, v.y, v.z, v.w};
+    int col = j4 % kg.ww1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = j4 + k;
+      if (j == qj) e[k] += diag;
+      if (j >= kg.Pv || col == ww) e[k] = -INFINITY;
+      if (++col == kg.ww1) col = 0;
+      mx = fmaxf(mx, e[k]);
+    }
+    *reinterpret_cast<float4*>(srow + j4) = make_float4(e[0], e[1], e[2], e[3]);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (warp == 0) {
+    float t = lane < 8 ? red[lane] : -INFINITY;
+    t = warp_max(t);
+    if (lane == 0) bcast = t;
+  }
+  __syncthreads();
+  mx = bcast;
+  float sum = 0.f;
+  for (int j4 = threadIdx.x * 4; j4 < ld; j4 += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(srow + j4);
+    sum += (expf(v.x - mx) + expf(v.y - mx)) + (expf(v.z - mx) + expf(v.w - mx));
+  }
+  sum = warp_sum(sum);
+  __syncthreads();
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  if (warp == 0) {
+    float t = lane < 8 ? red[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) {
+      stats[(long long)img * P + q] = make_float2(mx, 1.0f / t);
+      bcast = 1.0f / t;
+    }
+  }
+  if (!NORMALISE) return;
+  __syncthreads();
+  const float inv = bcast;
+  float* out = const_cast<float*>(row);
+  for (int j4 = threadIdx.x * 4; j4 < ld; j4 += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(srow + j4);   // exp(-inf) = 0 at the pad columns
+    *reinterpret_cast<float4*>(out + j4) =
+        make_float4(expf(v.x - mx) * inv, expf(v.y - mx) * inv, expf(v.z - mx) * inv, expf(v.w - mx) * inv);
+  }
+}
+
+// A2[img][m][j] = sum_a A[m - a][j - shift_a] from the normalised probabilities (gca_rowstats_kernel<true> wrote them in
+// place of S, zeros at the pad columns): 4 coalesced row reads (L2: a row is re-read by its 4 consumers within 2 key-grid
+// rows), one split-bf16 write.  One CTA per (row m, image).
+__global__ void __launch_bounds__(256) gca_shift_add_kernel(const float* __restrict__ A, int n, int hh, int ww, int ld,
+                                                            __nv_bfloat16* __restrict__ A2) {
+  const int P = hh * ww, ww1 = ww + 1, Pk = (hh + 1) * ww1;
+  const int m = blockIdx.x, img = blockIdx.y;
+  const int my = m / ww1, mx = m - my * ww1;
+  const float* rows[4];
+  int sh[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int qy = my - (a >> 1), qx = mx - (a & 1);
+    const bool ok = qy >= 0 && qy < hh && qx >= 0 && qx < ww;
+    sh[a] = (a >> 1) * ww1 + (a & 1);
+    rows[a] = ok ? A + ((long long)img * P + qy * ww + qx) * ld - sh[a] : nullptr;
+  }
+  const long long plane = (long long)n * Pk * ld;
+  __nv_bfloat16* out = A2 + ((long long)img * Pk + m) * ld;
+  for (int j = threadIdx.x * 2; j < ld; j += 512) {
+    float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      if (rows[a] == nullptr) continue;
+      if (j >= sh[a]) v0 += __ldg(rows[a] + j);
+      if (j + 1 >= sh[a]) v1 += __ldg(rows[a] + j + 1);
+    }
+    uint32_t hi, lo;
+    split2_bf16(v0, v1, hi, lo);
+    *reinterpret_cast<uint32_t*>(out + j) = hi;
+    *reinterpret_cast<uint32_t*>(out + plane + j) = lo;
+  }
+}
+
+// A2[img][m][j] = sum_a softmax(S)[m - a][j - shift_a], split-bf16 planes [2][n][Pk][ld].
+// CTA = (column chunk of CW, row m, image): the <= 4 source rows are exponentiated once into shared memory (chunk + halo of
+// ww+2 columns on the left), then summed at the four shifts.
+constexpr int A2_CW = 2048;
+__global__ void __launch_bounds__(256) gca_softmax_shift_kernel(const float* __restrict__ S, const float2* __restrict__ stats,
+                                                                const float* __restrict__ mm, int n, int hh, int ww, int ld,
+                                                                int halo, __nv_bfloat16* __restrict__ A2) {
+  extern __shared__ float sm[];     // 4 rows of (halo + A2_CW) floats
+  const int P = hh * ww, ww1 = ww + 1, Pk = (hh + 1) * ww1;
+  const int j0 = blockIdx.x * A2_CW, m = blockIdx.y, img = blockIdx.z;
+  const int my = m / ww1, mx = m - my * ww1;
+  const KeyGrid kg{ww1, hh * ww1};
+  const int rw = halo + A2_CW;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int qy = my - (a >> 1), qx = mx - (a & 1);
+    float* dst = sm + a * rw;
+    if (qy < 0 || qy >= hh || qx < 0 || qx >= ww) {
+      for (int i = threadIdx.x * 4; i < rw; i += 1024) *reinterpret_cast<float4*>(dst + i) = make_float4(0, 0, 0, 0);
+      continue;
+    }
+    const int q = qy * ww + qx, qj = qy * ww1 + qx;
+    const float* row = S + ((long long)img * P + q) * ld;
+    const float2 st = stats[(long long)img * P + q];
+    const float diag = -1e4f * mm[(long long)img * P + q];
+    for (int i = threadIdx.x * 4; i < rw; i += 1024) {
+      const int j4 = j0 - halo + i;
+      float e[4] = {0.f, 0.f, 0.f, 0.f};
+      if (j4 >= 0 && j4 < ld) {
+        const float4 v = *reinterpret_cast<const float4*>(row + j4);
+        const float s[4] = {v.x, v.y, v.z, v.w};
+        int col = j4 % ww1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int j = j4 + k;
+          const float t = s[k] + (j == qj ? diag : 0.f);
+          e[k] = (j < kg.Pv && col != ww) ? expf(t - st.x) * st.y : 0.f;
+          if (++col == ww1) col = 0;
+        }
+      }
+      *reinterpret_cast<float4*>(dst + i) = make_float4(e[0], e[1], e[2], e[3]);
+    }
+  }
+  __syncthreads();
+  const long long plane = (long long)n * Pk * ld;
+  __nv_bfloat16* out = A2 + ((long long)img * Pk + m) * ld + j0;
+  const int s1 = 1, s2 = ww1, s3 = ww1 + 1;
+  const float* r0 = sm + halo;
+  const float* r1 = sm + rw + halo - s1;
+  const float* r2 = sm + 2 * rw + halo - s2;
+  const float* r3 = sm + 3 * rw + halo - s3;
+  for (int i = threadIdx.x * 2; i < A2_CW && j0 + i < ld; i += 512) {
+    const float v0 = (r0[i] + r1[i]) + (r2[i] + r3[i]);
+    const float v1 = (r0[i + 1] + r1[i + 1]) + (r2[i + 1] + r3[i + 1]);
+    uint32_t hi, lo;
+    split2_bf16(v0, v1, hi, lo);
+    *reinterpret_cast<uint32_t*>(out + i) = hi;
+    *reinterpret_cast<uint32_t*>(out + plane + i) = lo;
+  }
+}
+
+// Y[img][2my+ry-1][2mx+rx-1][c] = O2[img][m][(ry*2+rx)*128 + c] / 4   (every output pixel exactly once)
+__global__ void gca_unfold_parity_kernel(const float* __restrict__ O2, int n, int h, int w, __nv_bfloat16* __restrict__ Y) {
+  const int ww1 = w / 2 + 1, Pk = (h / 2 + 1) * ww1;
+  const long long total = (long long)n * h * w * (FC / 4);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % (FC / 4)) * 4;
+  long long t = i / (FC / 4);
+  const int x = (int)(t % w);
+  t /= w;
+  const int y = (int)(t % h);
+  const int img = (int)(t / h);
+  const int ry = (y + 1) & 1, rx = (x + 1) & 1;
+  const int my = (y + 1 - ry) >> 1, mx = (x + 1 - rx) >> 1;
+  const float4 o = *reinterpret_cast<const float4*>(O2 + ((long long)img * Pk + my * ww1 + mx) * (4 * FC) +
+                                                    (ry * 2 + rx) * FC + c);
+  const float acc[4] = {o.x * 0.25f, o.y * 0.25f, o.z * 0.25f, o.w * 0.25f};
+  store4(Y + (((long long)img * h + y) * w + x) * FC + c, (long long)n * h * w * FC, acc);
+}
+
+}  // namespace tcv
+
+extern "C" {
+
+int tcv_gca_prep_grid(const void* g, const float* unknown, int n, int h, int w, void* Q, void* Kn, float* mm,
+                      float* scales, tcv_stream_t stream) {
+  TCV_REQUIRE(g && unknown && Q && Kn && mm && scales, "gca_prep_grid: null pointer");
+  TCV_REQUIRE(n > 0 && h >= 4 && w >= 4 && h % 2 == 0 && w % 2 == 0, "gca_prep_grid: h,w must be even and >= 4");
+  gca_scales_kernel<<<n, 256, 0, S(stream)>>>(unknown, h, w, scales);
+  int rc = launched("gca_scales_kernel");
+  if (rc) return rc;
+  const int hh = h / 2, ww = w / 2;
+  const long long pad_warps = (long long)(hh + ww + 1) * 2 * n;
+  gca_kn_pad_zero_kernel<<<(unsigned)((pad_warps * 32 + 255) / 256), 256, 0, S(stream)>>>(
+      reinterpret_cast<__nv_bfloat16*>(Kn), n, hh, ww, 2);
+  rc = launched("gca_kn_pad_zero_kernel");
+  if (rc) return rc;
+  const long long warps = (long long)n * hh * ww;
+  gca_prep_grid_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, S(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(g), unknown, n, h, w, scales, reinterpret_cast<__nv_bfloat16*>(Q),
+      reinterpret_cast<__nv_bfloat16*>(Kn), mm);
+  return launched("gca_prep_grid_kernel");
+}
+
+int tcv_gca_values_parity(const void* feat, int n, int h, int w, int ld, void* Ft, tcv_stream_t stream) {
+  TCV_REQUIRE(feat && Ft, "gca_values_parity: null pointer");
+  TCV_REQUIRE(n > 0 && h % 2 == 0 && w % 2 == 0 && h >= 4 && w >= 4, "gca_values_parity: h,w must be even and >= 4");
+  const int Pk = (h / 2 + 1) * (w / 2 + 1);
+  TCV_REQUIRE(ld % 64 == 0 && ld >= Pk, "gca_values_parity: ld must be a multiple of 64 and >= (h/2+1)*(w/2+1)");
+  gca_values_parity_kernel<<<dim3(ld / 64, 4, n), 256, 0, S(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(feat), n, h, w,
+                                                                      ld, reinterpret_cast<__nv_bfloat16*>(Ft));
+  return launched("gca_values_parity_kernel");
+}
+
+int tcv_gca_rowstats(float* Sm, const float* mm, int n, int h, int w, int ld, float* stats, int normalise,
+                     tcv_stream_t stream) {
+  TCV_REQUIRE(Sm && mm && stats, "gca_rowstats: null pointer");
+  const int hh = h / 2, ww = w / 2;
+  TCV_REQUIRE(n > 0 && hh > 0 && ww > 0 && ld % 4 == 0 && ld >= (hh + 1) * (ww + 1), "gca_rowstats: bad geometry");
+  TCV_REQUIRE((size_t)ld * 4 <= 200 * 1024, "gca_rowstats: row of %d keys does not fit shared memory", ld);
+  const size_t smem = (size_t)ld * sizeof(float);
+  TCV_CUDA(cudaFuncSetAttribute(gca_rowstats_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TCV_CUDA(cudaFuncSetAttribute(gca_rowstats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (normalise)
+    gca_rowstats_kernel<true><<<dim3(hh * ww, n), 256, smem, S(stream)>>>(Sm, mm, hh, ww, ld, reinterpret_cast<float2*>(stats));
+  else
+    gca_rowstats_kernel<false><<<dim3(hh * ww, n), 256, smem, S(stream)>>>(Sm, mm, hh, ww, ld, reinterpret_cast<float2*>(stats));
+  return launched("gca_rowstats_kernel");
+}
+
+int tcv_gca_shift_add(const float* A, int n, int h, int w, int ld, void* A2, tcv_stream_t stream) {
+  TCV_REQUIRE(A && A2, "gca_shift_add: null pointer");
+  const int hh = h / 2, ww = w / 2, Pk = (hh + 1) * (ww + 1);
+  TCV_REQUIRE(n > 0 && hh > 0 && ww > 0 && ld % 2 == 0 && ld >= Pk, "gca_shift_add: bad geometry");
+  gca_shift_add_kernel<<<dim3(Pk, n), 256, 0, S(stream)>>>(A, n, hh, ww, ld, reinterpret_cast<__nv_bfloat16*>(A2));
+  return launched("gca_shift_add_kernel");
+}
+
+int tcv_gca_softmax_shift(const float* Sm, const float* stats, const float* mm, int n, int h, int w, int ld, void* A2,
+                          tcv_stream_t stream) {
+  TCV_REQUIRE(Sm && stats && mm && A2, "gca_softmax_shift: null pointer");
+  const int hh = h / 2, ww = w / 2, Pk = (hh + 1) * (ww + 1);
+  TCV_REQUIRE(n > 0 && hh > 0 && ww > 0 && ld % 4 == 0 && ld >= Pk, "gca_softmax_shift: bad geometry");
+  const int halo = (ww + 2 + 3) / 4 * 4;
+  const size_t smem = (size_t)4 * (halo + A2_CW) * sizeof(float);
+  TCV_REQUIRE(smem <= 200 * 1024, "gca_softmax_shift: halo of %d columns does not fit shared memory", halo);
+  TCV_CUDA(cudaFuncSetAttribute(gca_softmax_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gca_softmax_shift_kernel<<<dim3((ld + A2_CW - 1) / A2_CW, Pk, n), 256, smem, S(stream)>>>(
+      Sm, reinterpret_cast<const float2*>(stats), mm, n, hh, ww, ld, halo, reinterpret_cast<__nv_bfloat16*>(A2));
+  return launched("gca_softmax_shift_kernel");
+}
+
+int tcv_gca_unfold_parity(const float* O2, int n, int h, int w, void* Y, tcv_stream_t stream) {
+  TCV_REQUIRE(O2 && Y, "gca_unfold_parity: null pointer");
+  TCV_REQUIRE(n > 0 && h % 2 == 0 && w % 2 == 0, "gca_unfold_parity: h,w must be even");
+  const long long total = (long long)n * h * w * (FC / 4);
+  gca_unfold_parity_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(O2, n, h, w,
+                                                                                  reinterpret_cast<__nv_bfloat16*>(Y));
+  return launched("gca_unfold_parity_kernel");
+}
+
+}  // extern "C"

@@ -133,6 +133,10 @@ class GcaVmnEngine:
         # bf16 planes per operand of the scores GEMM Q.Kn^T: 2 (three MMAs per K step, shipped) or 3 (six MMAs,
         # fp32-grade logits; measured on B200: no parity gain on any fixture, +0.66 ms per 1080p window)
         self.score_planes = int(os.environ.get("TCV_SCORE_PLANES", "2"))
+        # aggregation GEMM in its shift-sum form (default; TCV_GCA_SHIFT_SUM=0: the unfold-values + overlap-add form,
+        # 3.8x the FLOPs, kept as the cross-check)
+        self.gca_softmax_in_consumer = os.environ.get("TCV_GCA_SOFTMAX_IN_CONSUMER", "0") == "1"
+        self.gca_shift_sum = os.environ.get("TCV_GCA_SHIFT_SUM", "1") == "1" and self.pv_mode == "bf16x3"
         # opt-in (default off, to be A/B-measured on a GPU): the three stride-2 layers with 8 / 16 input channels
         # (encoder.conv1, guidance_head.1 / .5), which run on the CUDA-core kernel, as stride-1 2x2-tap convolutions over
         # the 2x2 space-to-depth image on the tcgen05 kernels (same rewrite as the FBA stem, tcv_s2d_pack)
@@ -477,6 +481,8 @@ class GcaVmnEngine:
         mm = self._empty((n, P))
         scales = self._empty((n, 2))
         O = self._empty((n, P, 2048))
+        if self.use_tc_attn and self.gca_shift_sum:
+            return self._gca_shift_sum(p, g, feat, unknown, mm, scales)
         if self.use_tc_attn:
             # tcgen05 path: scores in bf16x3 (fp32-accurate logits), probabilities and values in bf16
             sp = self.score_planes
@@ -518,6 +524,50 @@ class GcaVmnEngine:
                                  bytes=4 * n * (P * P + 2048 * P + P * 2048)))
         Y = self._act(n, h, w, 128)
         self._call("tcv_gca_fold", O.data_ptr(), n, h, w, Y.ptr)
+        self.last_gca_scales = scales
+        return self.conv(Y, _k(p, "W.0"), bn=_k(p, "W.1"), res1=feat)
+
+    def _gca_shift_sum(self, p: str, g: Act, feat: Act, unknown: torch.Tensor, mm, scales) -> Act:
+        """The aggregation half of GuidedCxtAtten.forward in its shift-sum form (csrc/gca.cu, include/tcvom_b200.h):
+        fold(A.V)/4 == A2.F on the (hh+1) x (ww+1) grid -- [Pk x ld].[ld x 512] instead of [P x P].[P x 2048] + overlap-add
+        (ops.py:112-118,204).  All three GEMM operands are split-bf16 (three MMAs per K step)."""
+        n, h, w = feat.n, feat.h, feat.w
+        hh, ww = h // 2, w // 2
+        P, Pk = hh * ww, (hh + 1) * (ww + 1)
+        ld = (Pk + 63) // 64 * 64
+        Q = self._empty((2, n, P, 576), torch.bfloat16)
+        Kn = self._empty((2, n, Pk, 576), torch.bfloat16)
+        self._call("tcv_gca_prep_grid", g.ptr, unknown.data_ptr(), n, h, w, Q.data_ptr(), Kn.data_ptr(), mm.data_ptr(),
+                   scales.data_ptr())
+        Ft = self._empty((2, n, 512, ld), torch.bfloat16)
+        self._call("tcv_gca_values_parity", feat.ptr, n, h, w, ld, Ft.data_ptr(),
+                   meta=dict(kind="tcv_gca_values_parity", bytes=n * (4 * h * w * 128 + 4 * 512 * ld)))
+        Sm = self._empty((n, P, ld))
+        self._call("tcv_gemm_tn_tc", Q.data_ptr(), n * P * 576, Kn.data_ptr(), n * Pk * 576, Sm.data_ptr(), P, Pk,
+                   576, ld, P * ld, n, 3, 0, 0,
+                   meta=dict(kind="gca_scores_gemm_tc", flops=2 * n * P * P * 576,
+                             bytes=n * (2 * 2 * 2 * P * 576 + 4 * P * P)))
+        stats = self._empty((n, P, 2))
+        A2 = self._empty((2, n, Pk, ld), torch.bfloat16)
+        if self.gca_softmax_in_consumer:
+            self._call("tcv_gca_rowstats", Sm.data_ptr(), mm.data_ptr(), n, h, w, ld, stats.data_ptr(), 0,
+                       meta=dict(kind="tcv_gca_rowstats", bytes=4 * n * P * ld))
+            self._call("tcv_gca_softmax_shift", Sm.data_ptr(), stats.data_ptr(), mm.data_ptr(), n, h, w, ld, A2.data_ptr(),
+                       meta=dict(kind="tcv_gca_softmax_shift", bytes=n * (4 * P * ld + 4 * Pk * ld)))
+        else:
+            self._call("tcv_gca_rowstats", Sm.data_ptr(), mm.data_ptr(), n, h, w, ld, stats.data_ptr(), 1,
+                       meta=dict(kind="tcv_gca_softmax", bytes=8 * n * P * ld))
+            self._call("tcv_gca_shift_add", Sm.data_ptr(), n, h, w, ld, A2.data_ptr(),
+                       meta=dict(kind="tcv_gca_shift_add", bytes=n * (4 * P * ld + 4 * Pk * ld)))
+        O2 = self._empty((n, Pk, 512))
+        # flops: the reference's count for this aggregation (2*P*P*2048 per image); executed: 2*Pk*ld*512 (x3 split)
+        self._call("tcv_gemm_tn_tc", A2.data_ptr(), n * Pk * ld, Ft.data_ptr(), n * 512 * ld, O2.data_ptr(), Pk, 512, ld,
+                   512, Pk * 512, n, 3, 0, 0,
+                   meta=dict(kind="gca_pv_gemm_tc", flops=2 * n * P * P * 2048, flops_executed=2 * n * Pk * ld * 512,
+                             bytes=n * (4 * (Pk * ld + 512 * ld) + 4 * Pk * 512)))
+        Y = self._act(n, h, w, 128)
+        self._call("tcv_gca_unfold_parity", O2.data_ptr(), n, h, w, Y.ptr,
+                   meta=dict(kind="tcv_gca_unfold_parity", bytes=n * (4 * Pk * 512 + 4 * h * w * 128)))
         self.last_gca_scales = scales
         return self.conv(Y, _k(p, "W.0"), bn=_k(p, "W.1"), res1=feat)
 

@@ -459,6 +459,126 @@ int tcv_gca_fold(const float* O, int n, int h, int w, void* Y, tcv_stream_t) {
   return 0;
 }
 
+// ---- shift-sum form of the aggregation (see include/tcvom_b200.h): independent naive restatements
+int tcv_gca_prep_grid(const void* g, const float* unknown, int n, int h, int w, void* Qv, void* Knv, float* mm, float* scales,
+                      tcv_stream_t st) {
+  const int hh = h / 2, ww = w / 2, P = hh * ww, Pk = (hh + 1) * (ww + 1), QD = 576;
+  std::vector<uint16_t> kn((size_t)2 * n * P * QD);
+  int rc = tcv_gca_prep(g, unknown, n, h, w, Qv, kn.data(), mm, scales, 2, st);
+  if (rc) return rc;
+  uint16_t* K = (uint16_t*)Knv;
+  memset(K, 0, (size_t)2 * n * Pk * QD * sizeof(uint16_t));
+  for (int pl = 0; pl < 2; ++pl)
+    for (int img = 0; img < n; ++img)
+      for (int p = 0; p < P; ++p)
+        memcpy(K + (((ll)pl * n + img) * Pk + (p / ww) * (ww + 1) + p % ww) * QD, kn.data() + (((ll)pl * n + img) * P + p) * QD,
+               QD * sizeof(uint16_t));
+  return 0;
+}
+
+int tcv_gca_values_parity(const void* feat, int n, int h, int w, int ld, void* Ftv, tcv_stream_t) {
+  const int hh = h / 2, ww = w / 2, Pk = (hh + 1) * (ww + 1), FC = 128;
+  REQ(ld % 64 == 0 && ld >= Pk, "gca_values_parity: ld");
+  const ll fplane = (ll)n * h * w * FC, total = (ll)n * 4 * FC * ld;
+  for (int img = 0; img < n; ++img)
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < FC; ++c)
+        for (int p = 0; p < ld; ++p) {
+          float val = 0.f;
+          if (p < Pk) {
+            const int py = p / (ww + 1), px = p % (ww + 1);
+            const int yy = reflect_idx(2 * py + (r >> 1) - 1, h), xx = reflect_idx(2 * px + (r & 1) - 1, w);
+            val = ld1((const uint16_t*)feat + (((ll)img * h + yy) * w + xx) * FC + c, fplane);
+          }
+          st1((uint16_t*)Ftv + ((ll)img * 4 * FC + r * FC + c) * ld + p, total, val);
+        }
+  ++g_launches;
+  return 0;
+}
+
+static bool key_valid(int j, int hh, int ww) { return j >= 0 && j < hh * (ww + 1) && j % (ww + 1) != ww; }
+
+int tcv_gca_rowstats(float* S, const float* mm, int n, int h, int w, int ld, float* stats, int normalise, tcv_stream_t) {
+  const int hh = h / 2, ww = w / 2, P = hh * ww;
+  for (int img = 0; img < n; ++img)
+    for (int q = 0; q < P; ++q) {
+      const float* row = S + ((ll)img * P + q) * ld;
+      const int qj = (q / ww) * (ww + 1) + q % ww;
+      const float diag = -1e4f * mm[(ll)img * P + q];
+      float mx = -INFINITY;
+      for (int j = 0; j < ld; ++j)
+        if (key_valid(j, hh, ww)) mx = fmaxf(mx, row[j] + (j == qj ? diag : 0.f));
+      float sum = 0.f;
+      for (int j = 0; j < ld; ++j)
+        if (key_valid(j, hh, ww)) sum += expf(row[j] + (j == qj ? diag : 0.f) - mx);
+      stats[2 * ((ll)img * P + q)] = mx;
+      stats[2 * ((ll)img * P + q) + 1] = 1.0f / sum;
+      if (normalise) {
+        float* out = S + ((ll)img * P + q) * ld;
+        for (int j = 0; j < ld; ++j)
+          out[j] = key_valid(j, hh, ww) ? expf(out[j] + (j == qj ? diag : 0.f) - mx) * (1.0f / sum) : 0.f;
+      }
+    }
+  ++g_launches;
+  return 0;
+}
+
+int tcv_gca_shift_add(const float* A, int n, int h, int w, int ld, void* A2v, tcv_stream_t) {
+  const int hh = h / 2, ww = w / 2, P = hh * ww, ww1 = ww + 1, Pk = (hh + 1) * ww1;
+  const ll plane = (ll)n * Pk * ld;
+  for (int img = 0; img < n; ++img)
+    for (int m = 0; m < Pk; ++m)
+      for (int j = 0; j < ld; ++j) {
+        float acc = 0.f;
+        for (int a = 0; a < 4; ++a) {
+          const int qy = m / ww1 - (a >> 1), qx = m % ww1 - (a & 1);
+          const int js = j - ((a >> 1) * ww1 + (a & 1));
+          if (qy < 0 || qy >= hh || qx < 0 || qx >= ww || js < 0) continue;
+          acc += A[((ll)img * P + qy * ww + qx) * ld + js];
+        }
+        st1((uint16_t*)A2v + ((ll)img * Pk + m) * ld + j, plane, acc);
+      }
+  ++g_launches;
+  return 0;
+}
+
+int tcv_gca_softmax_shift(const float* S, const float* stats, const float* mm, int n, int h, int w, int ld, void* A2v,
+                          tcv_stream_t) {
+  const int hh = h / 2, ww = w / 2, P = hh * ww, ww1 = ww + 1, Pk = (hh + 1) * ww1;
+  const ll plane = (ll)n * Pk * ld;
+  for (int img = 0; img < n; ++img)
+    for (int m = 0; m < Pk; ++m)
+      for (int j = 0; j < ld; ++j) {
+        float acc[4] = {0, 0, 0, 0};
+        for (int a = 0; a < 4; ++a) {
+          const int qy = m / ww1 - (a >> 1), qx = m % ww1 - (a & 1);
+          const int js = j - ((a >> 1) * ww1 + (a & 1));
+          if (qy < 0 || qy >= hh || qx < 0 || qx >= ww || !key_valid(js, hh, ww)) continue;
+          const ll q = (ll)img * P + qy * ww + qx;
+          const float t = S[q * ld + js] + (js == qy * ww1 + qx ? -1e4f * mm[q] : 0.f);
+          acc[a] = expf(t - stats[2 * q]) * stats[2 * q + 1];
+        }
+        st1((uint16_t*)A2v + ((ll)img * Pk + m) * ld + j, plane, (acc[0] + acc[1]) + (acc[2] + acc[3]));
+      }
+  ++g_launches;
+  return 0;
+}
+
+int tcv_gca_unfold_parity(const float* O2, int n, int h, int w, void* Y, tcv_stream_t) {
+  const int ww1 = w / 2 + 1, Pk = (h / 2 + 1) * ww1, FC = 128;
+  const ll yplane = (ll)n * h * w * FC;
+  for (int img = 0; img < n; ++img)
+    for (int y = 0; y < h; ++y)
+      for (int x = 0; x < w; ++x) {
+        const int ry = (y + 1) % 2, rx = (x + 1) % 2, my = (y + 1 - ry) / 2, mx = (x + 1 - rx) / 2;
+        for (int c = 0; c < FC; ++c)
+          st1((uint16_t*)Y + (((ll)img * h + y) * w + x) * FC + c, yplane,
+              O2[((ll)img * Pk + my * ww1 + mx) * 4 * FC + (ry * 2 + rx) * FC + c] * 0.25f);
+      }
+  ++g_launches;
+  return 0;
+}
+
 int tcv_head_tanh01(const void* x, long long x_plane, long long pixels, int c, float* pred, tcv_stream_t) {
   if (x_plane == 0) x_plane = pixels * c;
   for (ll i = 0; i < pixels; ++i) pred[i] = (tanhf(ld1((const uint16_t*)x + i * c, x_plane)) + 1.0f) * 0.5f;

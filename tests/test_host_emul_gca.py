@@ -168,4 +168,29 @@ def test_space_to_depth_stride2_program(emu, case):
         kinds = [m["kind"] for m in plan.meta]
         assert ("tcv_space_to_depth2" in kinds) == s2d
     assert np.abs(res[True].numpy() - g["alphas"]).max() < 1e-3
-    assert float((res[True] - res[False]).abs().max()) < 5e-5
+    assert float((res[True] - res[False]).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("case", ["ring64", "ring96x128", "allunk64"])
+def test_shift_sum_aggregation_equals_fold_program(emu, case):
+    """Default program (aggregation as A2.F on the padded grid, csrc/gca.cu) == the unfold-values + overlap-add program
+    (TCV_GCA_SHIFT_SUM=0) and the reference goldens: GuidedCxtAtten's fold(A.V)/4 (GCA/ops.py:112-118,204) re-associated."""
+    g = golden(f"eval_{case}.npz")
+    imgs, tris = torch.from_numpy(g["imgs"]), torch.from_numpy(g["tris"])
+    B, S, _, H, W = imgs.shape
+    res = {}
+    for ss in (False, True, "consumer"):
+        eng = make_gca_engine()
+        eng.gca_shift_sum = bool(ss)
+        eng.gca_softmax_in_consumer = ss == "consumer"      # exponentials in the shift kernel instead of a normalise pass
+        eng.refresh_weights(_net())
+        plan, io = record_eval(eng, B, S, H, W, int(g["dilate"]), True)
+        io["imgs"].copy_(imgs); io["tris"].copy_(tris)
+        plan.replay(0)
+        res[ss] = io["alphas"].clone()
+        kinds = [m["kind"] for m in plan.meta]
+        assert ("tcv_gca_shift_add" in kinds) == (ss is True) and ("tcv_gca_softmax_shift" in kinds) == (ss == "consumer")
+        assert ("tcv_gca_fold" in kinds) == (not ss)
+    assert np.abs(res[True].numpy() - g["alphas"]).max() < 1e-3
+    assert float((res[True] - res[False]).abs().max()) < 1e-4
+    assert float((res[True] - res["consumer"]).abs().max()) < 5e-5
