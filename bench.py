@@ -4,7 +4,8 @@ windows per second, one process per GPU, windows sharded across ranks (weak scal
 collective).
 
   python bench.py --gpus N --steps K --warmup W             # native sm_100a path
-  python bench.py --impl reference --gpus N --steps K ...   # CPU oracle port on the host cores
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path on the host cores (unmodified
+                                                            # reference from baseline/_ref, else the CPU oracle port)
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
 """
@@ -29,6 +30,20 @@ METRIC = "1080p 3-frame windows/sec (GCA+TAM forward)"
 UNIT = "windows/s"
 GFLOP_PER_WINDOW = 3843.57          # BASELINE.md section 2 (FlopCounterMode on the reference)
 FBA_GFLOP_PER_WINDOW = 7111.6       # EvalModel('vmn_fba') at 1088x1920 (223.1 GFLOP @256^2)
+
+
+JSON_OUT = sys.stdout     # the ONE JSON line goes here; main() points sys.stdout at stderr so that library / reference
+                          # chatter (e.g. the reference FBA's "modifying input layer ..." print) cannot pollute it
+
+
+def bench_config(world):
+    """The `config` object of the JSON line -- ONE definition for both arms, so that the driver's same_config check compares
+    identical dicts (round-1 verdict: the two arms described the same workload with different strings)."""
+    return dict(workload="GCA+TAM forward-only 1080p 3-frame window, batch 1 per GPU (configs[1])",
+                frames=S, height=H, width=W, windows_per_step_per_gpu=1,
+                weights="calibrated random-init fixture (tests/golden)",
+                l2="working set per step (>8 GB of activations) exceeds the 126 MB L2; no flush needed",
+                parallelism=f"dp{world} (independent windows per GPU, no collective)")
 
 
 def window_gflop(h, w):
@@ -104,22 +119,55 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------- CPU arm
+_REF_CPU = {}
+
+
+def cpu_kind():
+    """"reference": the UNMODIFIED reference modules from baseline/_ref (baseline/install_ref.py) on the host cores;
+    "port": the CPU oracle (oracle/vmn_gca_oracle.py) when that copy is not present."""
+    from baseline import ref_env
+    return "reference" if ref_env.available() else "port"
+
+
+def _reference_eval_model_cpu(arch):
+    """EvalModel(arch) of the unmodified reference on the CPU, fixture weights loaded (strict=True, pred_test.py:90-94)."""
+    if arch not in _REF_CPU:
+        import torch
+        from baseline import ref_env
+        from helpers import fixture_sd, fixture_sd_fba
+        ref_env.activate()
+        from models.model import EvalModel
+        ref = getattr(EvalModel, "_reference", EvalModel)
+        m = ref(model=arch, agg_window=7, dilate_kernel=None)
+        m.NET.load_state_dict(fixture_sd() if arch == "vmn_gca" else fixture_sd_fba(), strict=True)
+        _REF_CPU[arch] = m.eval()
+    return _REF_CPU[arch]
+
+
 def cpu_oracle_time(sample_hw, threads, reps=1):
-    """Times the CPU oracle (torch fp32 restatement of the reference) on one 3-frame window."""
+    """Times the reference's CPU path on one 3-frame window: the unmodified reference modules when baseline/_ref is present
+    (cpu_kind() == "reference"), else the CPU oracle port (torch fp32 restatement of the reference)."""
     import torch
     from helpers import fixture_sd
-    from oracle import vmn_gca_oracle as O
     from tcvom_b200 import synthetic
     torch.set_num_threads(threads)
     h, w = sample_hw
     imgs, tris = synthetic.make_window(h, w, seed=7)
     ti, tt = torch.from_numpy(imgs).float(), torch.from_numpy(tris).float()
-    sd = fixture_sd()
+    if cpu_kind() == "reference":
+        m = _reference_eval_model_cpu("vmn_gca")
+        run = lambda: m(ti, tt)
+    else:
+        from oracle import vmn_gca_oracle as O
+        sd = fixture_sd()
+        run = lambda: O.eval_forward(sd, ti, tt)
+    from baseline import ref_env
     ts = []
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        O.eval_forward(sd, ti, tt)
-        ts.append(time.perf_counter() - t0)
+    with torch.no_grad(), ref_env.on_cpu():
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            run()
+            ts.append(time.perf_counter() - t0)
     return ts
 
 
@@ -133,6 +181,13 @@ def cpu_oracle_time_fba(sample_hw, threads):
     h, w = sample_hw
     imgs, tris = synthetic.make_window(h, w, seed=7)
     ti, tt = torch.from_numpy(imgs).float(), torch.from_numpy(tris).float()
+    if cpu_kind() == "reference":
+        m = _reference_eval_model_cpu("vmn_fba")
+        from baseline import ref_env
+        with torch.no_grad(), ref_env.on_cpu():
+            t0 = time.perf_counter()
+            m(ti, tt)
+            return time.perf_counter() - t0
     sd = fixture_sd_fba()
     t0 = time.perf_counter()
     OF.eval_forward(sd, ti, tt)
@@ -165,17 +220,19 @@ def run_reference(args, rank, world):
         cpu_oracle_time(hw, threads)
     dt = time.perf_counter() - t0
     value = args.steps * frac / dt
+    kind = cpu_kind()
+    world = args.gpus
     sample = (f"one 3-frame {hw[0]}x{hw[1]} window per step = {frac:.4f} of a 1088x1920 window by the "
-              f"reference FLOP model (BASELINE.md section 2)")
+              f"reference FLOP model (BASELINE.md section 2); " +
+              ("unmodified reference modules (baseline/_ref) on the CPU" if kind == "reference" else "CPU oracle port"))
     line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload="GCA+TAM forward-only 1080p 3-frame window, batch 1 (configs[1])",
-                            frames=S, height=H, width=W, weights="calibrated random-init fixture"),
-                cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind="port", sample=sample),
+                config=bench_config(world),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind=kind, sample=sample),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------- training step (configs[2] / [3])
@@ -184,7 +241,10 @@ TRAIN_GFLOP_PER_SAMPLE = 1310.95        # 5-frame sample,
 LOSS_WEIGHTS = (1.0, 1.0, 1.0, 0.5, 0.25)   # train_ddp.py:61
 
 
-def run_train_section(args, rank, world, dev, barrier, max_over_ranks):
+TRAIN_1080_GFLOP_PER_SAMPLE = 20000.0   # 1088x1920, S=5, fwd 6 661 GFLOP, fwd+bwd ~3x
+
+
+def run_train_section(args, rank, world, dev, barrier, max_over_ranks, shape=None):
     """Secondary measurement: the native training step (FullModel_VMD fwd + losses + bwd + Adam, train_ddp.py:52-65)
     at BASELINE.json configs[2]'s shape, batch 4 per GPU; with N > 1 under SyncBatchNorm + DistributedDataParallel
     over NCCL exactly like train_ddp.py:270-280 (configs[3]'s recipe).  Reported next to, not instead of, the
@@ -193,6 +253,9 @@ def run_train_section(args, rank, world, dev, barrier, max_over_ranks):
     import tcvom_b200
     from tcvom_b200 import _cabi, synthetic
     from helpers import fixture_sd
+    # shape = (batch per GPU, frames, H, W, timed steps, reference GFLOP per sample-step, label)
+    TRAIN_B, TRAIN_S, TH_, TW_, steps, gflop, label = shape or (4, 5, 512, 512, 5, TRAIN_GFLOP_PER_SAMPLE, "configs[2]")
+    torch.cuda.reset_peak_memory_stats(dev)
     model = tcvom_b200.FullModel_VMD(model="vmn_gca", agg_window=7, dilate_kernel=None)
     model.NET.load_state_dict(fixture_sd(), strict=True)
     if world > 1:
@@ -203,7 +266,7 @@ def run_train_section(args, rank, world, dev, barrier, max_over_ranks):
         model = model.to(dev)
     model.train()
     a, fg, bg = (torch.from_numpy(t).float().to(dev)
-                 for t in synthetic.make_train_batch(TRAIN_B, TRAIN_S, TRAIN_HW, TRAIN_HW, seed=21 + 100 * rank))
+                 for t in synthetic.make_train_batch(TRAIN_B, TRAIN_S, TH_, TW_, seed=21 + 100 * rank))
     opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-5, weight_decay=1e-4)
     torch.manual_seed(1234 + rank)
 
@@ -217,7 +280,6 @@ def run_train_section(args, rank, world, dev, barrier, max_over_ranks):
 
     for _ in range(2):
         step()
-    steps = 5
     barrier()
     n0 = _cabi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -229,14 +291,20 @@ def run_train_section(args, rank, world, dev, barrier, max_over_ranks):
     ms = max_over_ranks(e0.elapsed_time(e1)) / steps
     samples = world * TRAIN_B
     n_params = sum(p.numel() for p in model.parameters() if p.requires_grad)
-    return dict(workload=f"GCA+TAM train step (L_im+L_tc+L_af fwd+bwd+Adam) {TRAIN_HW}x{TRAIN_HW} crop, batch {TRAIN_B}/GPU, "
-                         f"S={TRAIN_S} (configs[2]; N>1: SyncBatchNorm + DDP over NCCL, configs[3] recipe)",
+    out = dict(workload=f"GCA+TAM train step (L_im+L_tc+L_af fwd+bwd+Adam) {TH_}x{TW_}, batch {TRAIN_B}/GPU, "
+                         f"S={TRAIN_S} ({label}; N>1: SyncBatchNorm + DDP over NCCL, train_ddp.py:270-280)",
                 ms_per_step=ms, samples_per_s=samples / (ms / 1e3),
                 centre_windows_per_s=samples * (TRAIN_S - 2) / (ms / 1e3),
-                algorithmic_tflops=samples * TRAIN_GFLOP_PER_SAMPLE / (ms / 1e3) / 1e3, steps=steps, warmup=2,
+                algorithmic_tflops=samples * gflop / (ms / 1e3) / 1e3, steps=steps, warmup=2,
                 gpu_launches_per_step=(_cabi.launch_count() - n0) // steps, loss=float(loss.detach()),
                 grad_allreduce_mb=(4 * n_params / 1e6) if world > 1 else 0.0, sync_batchnorm=world > 1,
                 peak_mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30)
+    # release the step's arena before the next section
+    net = model.module.NET if world > 1 else model.NET
+    getattr(net, "_train_engines", {}).clear()
+    del model, opt, a, fg, bg, loss
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_fba_section(args, rank, world, dev, max_over_ranks):
@@ -292,7 +360,7 @@ def run_fba_section(args, rank, world, dev, max_over_ranks):
             hw = (544, 960)
             t = cpu_oracle_time_fba(hw, threads)
             frac = (hw[0] * hw[1]) / float(H * W)
-            cpu = dict(value=frac / t, unit=UNIT, cores=threads, kind="port",
+            cpu = dict(value=frac / t, unit=UNIT, cores=threads, kind=cpu_kind(),
                        sample=f"one 3-frame {hw[0]}x{hw[1]} FBA+TAM window ({t:.2f} s) = {frac:.4f} of a 1088x1920 window "
                               f"(convolution FLOPs scale with the pixel count)")
         except Exception as e:                                 # noqa: BLE001
@@ -305,6 +373,124 @@ def run_fba_section(args, rank, world, dev, max_over_ranks):
                          f"{FBA_GFLOP_PER_WINDOW:.1f} GFLOP/window, convolutions only)",
                 ms_per_window=ms, windows_per_s=world * 1e3 / ms,
                 algorithmic_tflops=FBA_GFLOP_PER_WINDOW / ms, cpu_baseline=cpu, **info)
+
+
+# ------------------------------------------------------------------------------------- reference on the same GPU
+def run_gpu_eager_section(dev):
+    """What the hot path costs TODAY on this GPU without this repo: the reference's PyTorch modules (eager, cuDNN / cuBLAS,
+    NCHW fp32) on cuda:0 -- the unmodified reference from baseline/_ref when present ("reference"), else the oracle port
+    ("port").  configs[1] forward, configs[2] train step, configs[4] FBA forward; each with TF32 off (fp32-accurate, what
+    the 1e-3 contract is stated against) and with TF32 on + cudnn.benchmark (train_ddp.py:189-191 / torch defaults).
+    A reported baseline like cpu_baseline: never on the measured path."""
+    import torch
+    from helpers import fixture_sd, fixture_sd_fba
+    from tcvom_b200 import synthetic
+    from baseline import ref_env
+    kind = "reference" if ref_env.available() else "port"
+    out = dict(kind=kind, device=torch.cuda.get_device_name(dev))
+
+    def timed(fn, warm, reps):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
+    if kind == "reference":
+        ref_env.activate()
+        import models.model as RM
+        Eval = getattr(RM.EvalModel, "_reference", RM.EvalModel)
+        VMD = getattr(RM.FullModel_VMD, "_reference", RM.FullModel_VMD)
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    try:
+        for tag, tf32 in (("fp32", False), ("tf32_cudnn_benchmark", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.benchmark = tf32
+            res = {}
+            # ---- configs[1]: GCA+TAM forward, one 1088x1920 window
+            try:
+                imgs, tris = (torch.from_numpy(t).float().to(dev) for t in synthetic.make_window(H, W, seed=7))
+                if kind == "reference":
+                    m = Eval(model="vmn_gca", agg_window=7, dilate_kernel=None)
+                    m.NET.load_state_dict(fixture_sd(), strict=True)
+                    m = m.to(dev).eval()
+                    fn = lambda: m(imgs, tris)
+                else:
+                    from oracle import vmn_gca_oracle as O
+                    sd = {k: v.to(dev) for k, v in fixture_sd().items()}
+                    fn = lambda: O.eval_forward(sd, imgs, tris)
+                with torch.no_grad():
+                    ms = timed(fn, 2, 5)
+                res["forward_1080p"] = dict(ms_per_window=ms, windows_per_s=1e3 / ms)
+                del fn
+            except Exception as e:                             # noqa: BLE001
+                res["forward_1080p"] = dict(error=f"{type(e).__name__}: {e}")
+            torch.cuda.empty_cache()
+            # ---- configs[2]: train step 512x512, batch 4, S=5 (fwd + losses + bwd + Adam)
+            try:
+                a, fg, bg = (torch.from_numpy(t).float().to(dev)
+                             for t in synthetic.make_train_batch(TRAIN_B, TRAIN_S, TRAIN_HW, TRAIN_HW, seed=21))
+                torch.manual_seed(1234)
+                if kind == "reference":
+                    tm = VMD(model="vmn_gca", agg_window=7)
+                    tm.NET.load_state_dict(fixture_sd(), strict=True)
+                    tm = tm.to(dev).train()
+                    opt = torch.optim.Adam([p for p in tm.parameters() if p.requires_grad], lr=1e-5, weight_decay=1e-4)
+
+                    def fn():
+                        o = tm(a, fg, bg)
+                        loss = sum(w * x.mean() for w, x in zip(LOSS_WEIGHTS, o[:5]))
+                        tm.zero_grad()
+                        loss.backward()
+                        opt.step()
+                else:
+                    from oracle import vmn_gca_oracle as O
+                    sd = {k: v.to(dev).requires_grad_(v.dtype.is_floating_point and not k.endswith(
+                        ("_u", "_v", "running_mean", "running_var"))) for k, v in fixture_sd().items()}
+                    params = [v for v in sd.values() if v.requires_grad]
+                    opt = torch.optim.Adam(params, lr=1e-5, weight_decay=1e-4)
+
+                    def fn():
+                        o = O.full_vmd_forward(sd, a, fg, bg, [3] * TRAIN_B, train=True)
+                        loss = sum(w * x.mean() for w, x in zip(LOSS_WEIGHTS, o[:5]))
+                        opt.zero_grad()
+                        loss.backward()
+                        opt.step()
+                ms = timed(fn, 1, 2)
+                res["train_512"] = dict(ms_per_step=ms, samples_per_s=TRAIN_B * 1e3 / ms)
+                del fn, opt
+            except Exception as e:                             # noqa: BLE001
+                res["train_512"] = dict(error=f"{type(e).__name__}: {e}")
+            torch.cuda.empty_cache()
+            # ---- configs[4]: FBA+TAM forward, one 1088x1920 window (incl. the reference's host cv2 distance transforms)
+            try:
+                imgs, tris = (torch.from_numpy(t).float().to(dev) for t in synthetic.make_window(H, W, seed=7))
+                if kind == "reference":
+                    m = Eval(model="vmn_fba", agg_window=7, dilate_kernel=None)
+                    m.NET.load_state_dict(fixture_sd_fba(), strict=True)
+                    m = m.to(dev).eval()
+                    fn = lambda: m(imgs, tris)
+                else:
+                    from oracle import vmn_fba_oracle as OF
+                    sd = {k: v.to(dev) for k, v in fixture_sd_fba().items()}
+                    fn = lambda: OF.eval_forward(sd, imgs, tris)
+                with torch.no_grad():
+                    ms = timed(fn, 1, 3)
+                res["fba_forward_1080p"] = dict(ms_per_window=ms, windows_per_s=1e3 / ms)
+                del fn
+            except Exception as e:                             # noqa: BLE001
+                res["fba_forward_1080p"] = dict(error=f"{type(e).__name__}: {e}")
+            torch.cuda.empty_cache()
+            out[tag] = res
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    return out
 
 
 # ------------------------------------------------------------------------------------- native arm
@@ -429,12 +615,19 @@ def run_native(args, rank, world, local_rank):
                     roof["traffic"] = t["dram_bytes_per_launch"]       # ncu dram__bytes_read+write, per launch
                     roof["algorithmic_bytes_per_launch"] = top["bytes"] / top["n"]
 
-    train = None
+    train = train_1080 = None
     if not args.no_train:
         model.NET.engine().plans.clear()           # release the forward plan's 10 GB of activations
         del plan
         torch.cuda.empty_cache()
         train = run_train_section(args, rank, world, dev, barrier, max_over_ranks)
+        try:
+            train_1080 = run_train_section(args, rank, world, dev, barrier, max_over_ranks,
+                                           shape=(1, 5, H, W, 3, TRAIN_1080_GFLOP_PER_SAMPLE, "configs[3]"))
+        except Exception as e:                                 # noqa: BLE001 - reported in the JSON line
+            if world > 1:
+                raise                                          # a rank that fails alone would dead-lock the others
+            train_1080 = dict(error=f"{type(e).__name__}: {e}")
 
     fba = None
     if not args.no_fba:
@@ -447,30 +640,34 @@ def run_native(args, rank, world, local_rank):
             dist.destroy_process_group()
         return
 
+    eager = None
+    if world == 1 and not args.no_eager_baseline:
+        try:
+            eager = run_gpu_eager_section(dev)
+        except Exception as e:                                 # noqa: BLE001
+            eager = dict(error=f"{type(e).__name__}: {e}")
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         hw = pick_cpu_sample(threads, 30.0, 1)
         t = min(cpu_oracle_time(hw, threads, reps=1))
         frac = window_gflop(*hw) / window_gflop(H, W)
-        cpu = dict(value=frac / t, unit=UNIT, cores=threads, kind="port",
+        cpu = dict(value=frac / t, unit=UNIT, cores=threads, kind=cpu_kind(),
                    sample=f"one 3-frame {hw[0]}x{hw[1]} window ({t:.2f} s) = {frac:.4f} of a 1088x1920 window by the "
                           f"reference FLOP model")
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="bf16x3 (split-bf16 storage, fp32 accumulate)", data="synthetic",
-                config=dict(workload="GCA+TAM forward-only 1080p 3-frame window, batch 1 per GPU (configs[1])",
-                            frames=S, height=H, width=W, windows_per_step_per_gpu=1,
-                            weights="calibrated random-init fixture (tests/golden)",
-                            l2="working set per step (>8 GB of activations) exceeds the 126 MB L2; no flush needed",
-                            parallelism=f"dp{world} (independent windows per GPU, no collective)"),
+                config=bench_config(world),
                 clocks=clocks,
                 e2e=dict(value=e2e_value, unit=UNIT, ms_per_step=ms_e2e / args.steps,
                          h2d_bytes_per_step=imgs_u8.numel() + tris_u8.numel(), input_dtype="uint8",
                          d2h_bytes_per_step=out_h.numel() * 4),
-                gpu_launches=launches, roofline=roof, cpu_baseline=cpu, train_step=train, fba_forward=fba)
-    print(json.dumps(line), flush=True)
+                gpu_launches=launches, roofline=roof, cpu_baseline=cpu, gpu_eager_baseline=eager, train_step=train,
+                train_step_1080p=train_1080, fba_forward=fba)
+    print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -482,10 +679,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true",
+                    help="skip the reference-on-this-GPU measurement (PyTorch eager, N=1 only)")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
     ap.add_argument("--no-fba", action="store_true", help="skip the secondary FBA+TAM forward measurement (configs[4])")
     ap.add_argument("--dump-calls", default=None, help="write the per-launch timing table (JSON lines) here")
     args = ap.parse_args()
+    sys.stdout = sys.stderr
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -135,6 +135,8 @@ class GcaVmnEngine:
         self.score_planes = int(os.environ.get("TCV_SCORE_PLANES", "2"))
         # aggregation GEMM in its shift-sum form (default; TCV_GCA_SHIFT_SUM=0: the unfold-values + overlap-add form,
         # 3.8x the FLOPs, kept as the cross-check)
+        # windowed forward: shortcut branches 0..2 only for the centre frames that consume them (see per_frame)
+        self.centre_shortcuts = os.environ.get("TCV_CENTRE_SHORTCUTS", "1") == "1"
         self.gca_softmax_in_consumer = os.environ.get("TCV_GCA_SOFTMAX_IN_CONSUMER", "0") == "1"
         self.gca_shift_sum = os.environ.get("TCV_GCA_SHIFT_SUM", "1") == "1" and self.pv_mode == "bf16x3"
         # opt-in (default off, to be A/B-measured on a GPU): the three stride-2 layers with 8 / 16 input channels
@@ -149,7 +151,7 @@ class GcaVmnEngine:
     def _current_fingerprint(self):
         if self._tensors is None:
             self._tensors = list(self._named().values())
-        return (tuple(t._version for t in self._tensors), self._tensors[0].data_ptr())
+        return (tuple(t._version for t in self._tensors), tuple(t.data_ptr() for t in self._tensors))
 
     def refresh_weights(self, net: torch.nn.Module, force=False) -> None:
         """(Re)derives folded/packed weights when parameters changed (load_state_dict, optimizer step,
@@ -161,6 +163,9 @@ class GcaVmnEngine:
         named = self._named()
         dev = next(iter(named.values())).device
         self._check_device(dev)
+        if dev.type == "cuda" and torch.cuda.current_device() != dev.index:
+            with torch.cuda.device(dev):
+                return self.refresh_weights(net, force)
         if self.device is not None and dev != self.device:
             self.w.clear(); self.aff.clear(); self.bias.clear(); self.plans.clear()
             self._tensors = None
@@ -188,7 +193,7 @@ class GcaVmnEngine:
                 self._pack(L, st, p, t, None, None, None, transposed=False)
                 b = named.get(p + ".bias")
                 if b is not None:
-                    self.bias[p] = b
+                    self._own_bias(p, b)
                 if t.shape[0] == 1 and t.shape[1] % 32 == 0 and t.shape[2] == 3:
                     self._pack_head32(L, st, p, t, b)
             elif name.endswith(".running_var"):
@@ -204,6 +209,20 @@ class GcaVmnEngine:
         if self.s2d_stride2:
             self._derive_s2d(L, st)
         self._fingerprint = fp
+
+    def _own_bias(self, p: str, b: torch.Tensor) -> None:
+        """Engine-owned copy of a conv bias, updated in place: recorded plans / CUDA graphs bake in device pointers, and a
+        module parameter's storage is not stable (nn.DataParallel broadcasts fresh replica tensors on every forward)."""
+        own = self.bias.get(p)
+        if own is None or own.device != b.device or own.shape != b.shape:
+            own = self.bias[p] = torch.empty_like(b, memory_format=torch.contiguous_format)
+        with torch.no_grad():
+            own.copy_(b)
+
+    def invalidate(self) -> None:
+        """Forces the next call to re-derive every folded / packed weight.  Needed only after parameter updates that
+        bypass torch's version counter (``p.data.copy_()``, ``vector_to_parameters``, EMA swaps through ``.data``)."""
+        self._fingerprint = None
 
     def _pack(self, L, st, p, wbar, u, v, sig, transposed):
         if transposed:
@@ -327,6 +346,18 @@ class GcaVmnEngine:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def _call(self, fn_name: str, *args, meta: Optional[dict] = None):
+        with self._device_guard():
+            self._call_on_device(fn_name, *args, meta=meta)
+
+    def _device_guard(self):
+        """Kernels, memsets and tensor-map setup run on the CURRENT device while the stream comes from the module's device:
+        make them agree for callers that moved the model with .to('cuda:1') without torch.cuda.set_device(1)."""
+        if self.device is not None and self.device.type == "cuda":
+            return torch.cuda.device(self.device)
+        import contextlib
+        return contextlib.nullcontext()
+
+    def _call_on_device(self, fn_name: str, *args, meta: Optional[dict] = None):
         fn = getattr(_cabi.lib(), fn_name)
         st = self._stream_ptr()
         prof = getattr(self, "_prof", None)
@@ -608,8 +639,15 @@ class GcaVmnEngine:
                 x = self.conv(o, bp + ".conv2", bn=bp + ".bn2", res1=x, act=ACT_LEAKY02, res2=last)
         return x
 
-    def per_frame(self, x8: Act) -> dict:
-        """encoder + decoder head for all frames at once (VMN_model.py:93-98)."""
+    def per_frame(self, x8: Act, shortcuts: str = "all") -> dict:
+        """encoder + decoder head for all frames at once (VMN_model.py:93-98).
+
+        shortcuts="all": the five shortcut branches of every frame (res_gca_enc.py:84-88), as the reference computes them
+        (FrameStream caches them per frame: every frame becomes a centre frame once).  shortcuts="head": only branches 3
+        and 4, which the per-frame decoder head consumes (VMN_GCA.py:28-31); branches 0..2 are read by the decoder TAIL of
+        CENTRE frames only (VMN_GCA.py:38-44), so `tail` computes them for exactly those frames from the returned sources
+        -- the reference evaluates them for the end frames too and throws the result away (a 3-frame window: 2/3 of the two
+        full-resolution and the half- / quarter-resolution branch convolutions are dead code; same values for the rest)."""
         e = "encoder"
         s2d = self.s2d_stride2 and self.use_tc_conv
         if s2d:
@@ -645,11 +683,17 @@ class GcaVmnEngine:
                 cur = self._enc_block(cur, f"{e}.{name}.{i}", stride if i == 0 else 1)
             feats.append(cur)
         x2, x3, x4, emb = feats
-        fea = [self._shortcut(t, f"{e}.shortcut.{i}") for i, t in enumerate((x8, x1, x2, x3, x4))]
+        srcs = (x8, x1, x2, x3, x4)
+        assert shortcuts in ("all", "head")
+        fea = [self._shortcut(t, f"{e}.shortcut.{i}") if (shortcuts == "all" or i >= 3) else None
+               for i, t in enumerate(srcs)]
         d = self._dec_layer(emb, "decoder.layer1", DEC_LAYERS[0][2], fea[4])
         d = self._dec_layer(d, "decoder.layer2", DEC_LAYERS[1][2], fea[3])
         feat = self.gca("decoder.gca", im_fea, d, unknown)
-        return dict(fea=fea, feat=feat, im_fea=im_fea, unknown=unknown)
+        out = dict(fea=fea, feat=feat, im_fea=im_fea, unknown=unknown)
+        if shortcuts == "head":
+            out["shortcut_src"] = list(srcs[:3])
+        return out
 
     def tail(self, pf: dict, n0: int, ncen: int, mask_ptr: int, mask_stride: int, H: int, W: int, pred_ptr: int,
              attb_ptr: int, attf_ptr: int, sm_ptr: int) -> None:
@@ -658,7 +702,9 @@ class GcaVmnEngine:
         x = feat.slice(n0 + 1, n0 + 1 + ncen)
         xb = feat.slice(n0, n0 + ncen)
         xf = feat.slice(n0 + 2, n0 + 2 + ncen)
-        fea = [f.slice(n0 + 1, n0 + 1 + ncen) for f in pf["fea"]]
+        fea = [f.slice(n0 + 1, n0 + 1 + ncen) if f is not None else
+               (self._shortcut(pf["shortcut_src"][i].slice(n0 + 1, n0 + 1 + ncen), f"encoder.shortcut.{i}") if i < 3 else None)
+               for i, f in enumerate(pf["fea"])]
         t = self.tam("decoder.fam", x, xb, xf, mask_ptr, mask_stride, H, W, attb_ptr, attf_ptr, sm_ptr)
         t = self._dec_layer(t, "decoder.layer3", DEC_LAYERS[2][2], fea[2])
         t = self._dec_layer(t, "decoder.layer4", DEC_LAYERS[3][2], fea[1])
@@ -681,7 +727,7 @@ class GcaVmnEngine:
         attb = self._empty((B, ncen, w2, N8))
         attf = self._empty((B, ncen, w2, N8))
         sm = self._empty((B, ncen, 1, H // 8, W // 8), torch.uint8)
-        pf = self.per_frame(x8)
+        pf = self.per_frame(x8, shortcuts="head" if self.centre_shortcuts else "all")
         for b in range(B):
             n0 = b * S
             self.tail(pf, n0, ncen, trimask.data_ptr() + 4 * (n0 + 1) * H * W, H * W, H, W,

@@ -86,10 +86,18 @@ class FbaVmnEngine(GcaVmnEngine):
                             pads[p] = torch.zeros(cout_pad, dtype=torch.float32, device=dev)
                         with torch.no_grad():
                             pads[p][: b.numel()].copy_(b)
-                        b = pads[p]
-                    self.bias[p] = b
+                        self.bias[p] = pads[p]
+                    else:
+                        self._own_bias(p, b)
             elif t.dim() == 1:
-                self.gn_params[p] = (t, named[p + ".bias"])
+                # engine-owned copies (see GcaVmnEngine._own_bias): plans record these pointers
+                own = self.gn_params.get(p)
+                gb = named[p + ".bias"]
+                if own is None or own[0].device != dev or own[0].shape != t.shape:
+                    own = self.gn_params[p] = (torch.empty_like(t), torch.empty_like(gb))
+                with torch.no_grad():
+                    own[0].copy_(t)
+                    own[1].copy_(gb)
         self._fingerprint = fp
 
     def _pack_fba(self, L, st, p, w, standardize: bool) -> None:

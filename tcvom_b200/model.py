@@ -86,6 +86,7 @@ class _TrainStepFn(torch.autograd.Function):
     def forward(ctx, wrapper, a, fg, bg, *params):
         st = wrapper._train_forward(a, fg, bg)
         ctx.wrapper, ctx.st = wrapper, st
+        ctx.step_id = st["eng"].step_id
         vis = tuple(st[k] for k in ("imgs", "tris_vis", "alphas", "comps", "gts", "fgs", "bgs"))
         ctx.mark_non_differentiable(*vis)
         return (st["losses"],) + vis
@@ -95,6 +96,14 @@ class _TrainStepFn(torch.autograd.Function):
         if ctx.st is None:
             raise RuntimeError("tcvom_b200: the native training step was already back-propagated once "
                                "(retain_graph / double backward are not supported)")
+        eng = ctx.st["eng"]
+        if eng.step_id != ctx.step_id or not eng.tape:
+            # the engine keeps ONE tape / set of gradient accumulators: a second train-mode forward (another micro-batch,
+            # or a no_grad forward in train mode) replaced the state this node needs.  Plain autograd would support the
+            # pattern; silently back-propagating the other step's tape would not be the same thing.
+            raise RuntimeError("tcvom_b200: another train-mode forward ran on this module before backward(); call "
+                               "loss.backward() after every forward (gradient accumulation over micro-batches works "
+                               "that way: forward, backward, forward, backward, optimizer.step())")
         grads = ctx.wrapper._train_backward(ctx.st, gl)
         ctx.st = None
         return (None, None, None, None) + tuple(grads)
@@ -109,15 +118,17 @@ class _VMNTrainFn(torch.autograd.Function):
         eng = _train_engine_for(net, int(net.decoder.fam.window))
         out = eng.train_forward(x8, trimask, B, S, H, W)
         ctx.eng, ctx.names = eng, net.__dict__["_train_param_names"]
+        ctx.step_id = eng.step_id
         ctx.mark_non_differentiable(out["small_mask"])
         return out["pred"], out["attb"], out["attf"], out["small_mask"]
 
     @staticmethod
     def backward(ctx, dpred, dattb, dattf, _):
         eng = ctx.eng
-        if eng is None or not eng.tape:
-            raise RuntimeError("tcvom_b200: the native VMN step was already back-propagated once "
-                               "(retain_graph / double backward are not supported)")
+        if eng is None or not eng.tape or eng.step_id != ctx.step_id:
+            raise RuntimeError("tcvom_b200: the native VMN step was already back-propagated once, or another train-mode "
+                               "forward ran on this module before backward() (retain_graph / double backward / two "
+                               "forwards before one backward are not supported)")
         z = lambda g, like: g.contiguous().float() if g is not None else torch.zeros_like(like)
         eng.train_backward(z(dpred, eng.pred), dattb.contiguous().float() if dattb is not None else None,
                            dattf.contiguous().float() if dattf is not None else None)
@@ -209,6 +220,10 @@ class VMN(nn.Module):
         self.encoder = encoder
         self.decoder = decoder
         self.freeze_backbone = freeze_backbone
+        # per-device engine tables, created HERE so that nn.DataParallel replicas (shallow __dict__ copies made on every
+        # forward) always share them with the wrapped module instead of re-recording plans per call
+        self.__dict__["_engines"] = {}
+        self.__dict__["_train_engines"] = {}
 
     def train(self, mode=True):
         super().train(mode)
@@ -230,7 +245,10 @@ class VMN(nn.Module):
         memo[id(self)] = new
         import copy
         for k, v in self.__dict__.items():
-            if k == "_engines":
+            if k in ("_engines", "_train_engines"):
+                new.__dict__[k] = {}
+                continue
+            if k == "_train_param_names":
                 continue
             new.__dict__[k] = copy.deepcopy(v, memo)
         return new
@@ -528,6 +546,9 @@ class EvalModel(nn.Module):
         """Replays the recorded kernel sequence on the current stream (CUDA graph when enabled)."""
         eng = self._eng
         dev = eng.device
+        if torch.cuda.current_device() != dev.index:       # model moved with .to('cuda:N') without set_device(N)
+            with torch.cuda.device(dev):
+                return self.run_plan(plan)
         if eng.use_graphs:
             if plan.graph is None:
                 st = torch.cuda.Stream(dev)
@@ -604,7 +625,8 @@ class FullModel_VMD(nn.Module):
     def _plan(self, B, S, H, W) -> Plan:
         eng = self.NET.engine()
         self.__dict__["_eng"] = eng
-        key = ("vmd" if self._with_att else "full", B, S, H, W, float(self.EPS))
+        key = ("vmd" if self._with_att else "full", B, S, H, W, float(self.EPS), float(self.att_thres),
+               float(self.label_smooth), int(self.window))      # every value the recorded tcv_losses_vmd call bakes in
         plan = eng.get_plan(key)
         if plan is not None:
             return plan

@@ -737,6 +737,7 @@ class TrainEngine(GcaVmnEngine):
     def train_forward(self, x8a: Act, trimask: torch.Tensor, B: int, S: int, H: int, W: int) -> dict:
         """VMN.forward in train mode on preprocessed input; records the tape.  trimask fp32 [B,S,1,H,W]."""
         self.tape = []
+        self.step_id = getattr(self, "step_id", 0) + 1       # stamps the autograd node (model._TrainStepFn / _VMNTrainFn)
         self.dw.clear(); self.dbias.clear(); self.dbn.clear()
         self._arena_begin()
         self._nbt = []

@@ -1,0 +1,129 @@
+"""GPU: the reference's OWN entry scripts, unmodified, running on the native package through tcvom_b200.install()
+(the boundary is `pred_test.py` / `train_ddp.py` + `models.model.EvalModel` / `FullModel_VMD`).
+
+baseline/_ref is an unedited copy of the reference tree (baseline/install_ref.py; git-ignored, shipped to the GPU box);
+tools/run_reference_script.py runs a script from it under runpy after the import shims of baseline/ref_env.py (stub
+matplotlib / yacs / imgaug; synthetic stand-in for the VideoMatting108 dataset).  Skipped when baseline/_ref is absent.
+
+  * pred_test.py:86-139  -- fork-free single-GPU path: EvalModel(...) -> strict=True checkpoint load -> PNG out; the
+    PNGs are compared with the CPU oracle's mattes (and with the reference's own modules run the same way on the GPU);
+  * train_ddp.py:40-100,270-298 -- one epoch of two iterations under SyncBatchNorm + DistributedDataParallel over NCCL
+    (--local_rank launcher, one process per GPU): finite losses, checkpoint written, parameters moved."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import fixture_sd
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref")
+RUNNER = os.path.join(ROOT, "tools", "run_reference_script.py")
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "models")),
+                                                  reason="baseline/_ref not installed (python baseline/install_ref.py)")]
+
+
+def _run(args, env=None, timeout=600):
+    e = dict(os.environ)
+    e.update(env or {})
+    r = subprocess.run([sys.executable, RUNNER] + args, cwd=ROOT, env=e, capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
+    return r
+
+
+def _write_clip(folder, H, W, frames):
+    import cv2
+    from tcvom_b200 import synthetic
+    imgs, tris = synthetic.make_window(H, W, seed=31, frames=frames)
+    os.makedirs(folder, exist_ok=True)
+    for t in range(frames):
+        cv2.imwrite(os.path.join(folder, f"{t:04d}_rgb.png"), np.ascontiguousarray(imgs[0, t].transpose(1, 2, 0)))
+        cv2.imwrite(os.path.join(folder, f"{t:04d}_trimap.png"), tris[0, t, 0])
+    return imgs, tris
+
+
+def test_pred_test_script_runs_on_the_native_package(tmp_path):
+    import cv2
+    import torch.nn.functional as F
+    from oracle import vmn_gca_oracle as O
+    H, W, T = 90, 120, 5                       # not a multiple of 32: exercises TestFolder.possible_pad (reflect)
+    data = tmp_path / "data"
+    imgs, tris = _write_clip(str(data / "clip0"), H, W, T)
+    ckpt = str(tmp_path / "fixture.pth")
+    sd = fixture_sd()
+    torch.save(sd, ckpt)
+    outs = {}
+    for arm, flags in (("native", ["--native"]), ("reference", [])):
+        save = str(tmp_path / f"out_{arm}")
+        _run(flags + ["pred_test.py", "--model", "vmn_gca", "--load", ckpt, "--data", str(data), "--save", save,
+                      "--gpu", "0"])
+        outs[arm] = [cv2.imread(os.path.join(save, "clip0", f"{t:04d}_alpha.png"), cv2.IMREAD_GRAYSCALE) for t in range(T)]
+        assert all(o is not None and o.shape == (H, W) for o in outs[arm]), arm
+    # oracle on the same windows (pred_test.py:34-40: neighbours mirrored at the clip ends; reflect pad to x32)
+    ti = F.pad(torch.from_numpy(imgs[0]).float(), (0, 128 - W, 0, 96 - H), mode="reflect")
+    tt = F.pad(torch.from_numpy(tris[0]).float(), (0, 128 - W, 0, 96 - H), mode="reflect")
+    worst = 0
+    for c in range(T):
+        p = c + 1 if c == 0 else c - 1
+        n = c - 1 if c == T - 1 else c + 1
+        ref = O.eval_forward(sd, ti[[p, c, n]][None], tt[[p, c, n]][None])[0, 1, 0, :H, :W].numpy()
+        want = np.uint8(ref * 255)
+        for arm in outs:
+            d = np.abs(outs[arm][c].astype(np.int32) - want.astype(np.int32)).max()
+            worst = max(worst, d)
+            # native: 1e-3 on alpha = at most one grey level after the uint8 truncation.  The reference's own modules on
+            # the GPU run their convolutions in TF32 (torch default; the script does not turn it off) and were measured
+            # 2 levels off the fp32 CPU result on a B200, so that arm only gets a sanity bound.
+            assert d <= (1 if arm == "native" else 4), (arm, c, d)
+        assert np.abs(outs["native"][c].astype(np.int32) - outs["reference"][c].astype(np.int32)).max() <= 4
+    unknown = (tris[0, :, 0] == 128).mean()
+    assert unknown > 0.05 and any(len(np.unique(o)) > 8 for o in outs["native"]), "vacuous clip"
+
+
+def _train_cfg(tmp_path, ckpt):
+    cfg = tmp_path / "gca_tiny.yaml"
+    cfg.write_text(
+        "MODEL: 'vmn_gca'\nAGG_WINDOW: 7\n"
+        "SYSTEM:\n  NUM_WORKERS: 0\n  RANDOM_SEED: 777\n  OUTDIR: '%s'\n"
+        "DATASET:\n  PATH: ''\n"
+        "TRAIN:\n  LOAD_CKPT: '%s'\n  BATCH_SIZE_PER_GPU: 1\n  VAL_BATCH_SIZE_PER_GPU: 1\n  BASE_LR: 1e-5\n"
+        "  LR_STRATEGY: 'poly'\n  TRAIN_INPUT_SIZE: (64, 64)\n  VAL_INPUT_SIZE: (64, 64)\n  TOTAL_STEPS: 1\n"
+        "  PRINT_FREQ: 1\n  IMAGE_FREQ: 500\n" % (tmp_path / "train_log", ckpt))
+    return str(cfg)
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_train_ddp_script_runs_on_the_native_package(tmp_path, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    ckpt = str(tmp_path / "fixture.pth")
+    sd = fixture_sd()
+    torch.save(sd, ckpt)
+    cfg = _train_cfg(tmp_path, ckpt)
+    port = 29650 + world
+    procs = []
+    for r in range(world):
+        e = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(r), WORLD_SIZE=str(world),
+                 LOCAL_RANK=str(r), TCVOM_STUB_DATASET_LEN=str(2 * world))
+        procs.append(subprocess.Popen([sys.executable, RUNNER, "--native", "--synthetic-dataset", "train_ddp.py", "--cfg", cfg,
+                                       "--local_rank", str(r)], cwd=ROOT, env=e, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    logs = []
+    for p in procs:
+        out, _ = p.communicate(timeout=900)
+        logs.append(out)
+        assert p.returncode == 0, out[-4000:]
+    # rank 0 logged one line per iteration (train_ddp.py:86-98) and saved NET.state_dict() (train_ddp.py:331-338)
+    lines = [l for l in logs[0].splitlines() if l.startswith("Iter:[")]
+    assert len(lines) == 2, logs[0][-3000:]
+    losses = [float(l.split("Current: Loss: ")[1].split(",")[0]) for l in lines]
+    assert all(np.isfinite(losses)) and all(l > 0 for l in losses), lines
+    out_dir = tmp_path / "train_log" / "gca_tiny"
+    saved = torch.load(str(out_dir / "checkpoint_1.pth.tar"), map_location="cpu")
+    assert list(saved.keys()) == list(sd.keys())
+    moved = max(float((saved[k].float() - sd[k].float()).abs().max()) for k in sd if k.endswith("weight_bar"))
+    assert 0 < moved < 1e-2 and all(torch.isfinite(v.float()).all() for v in saved.values())

@@ -207,3 +207,26 @@ def test_train_step_edge_cases_match_oracle(case):
     # noise-floor bounds (see tools/determinism_probe.py; smaller batches are noisier): these cases pin the BRANCH
     # semantics -- the losses above -- and guard against gross gradient errors
     assert med < 8e-2 and worst < 3e-1, (med, worst)
+
+
+def test_two_forwards_before_backward_raise_instead_of_mixing_tapes():
+    """The engine keeps one tape: back-propagating step 1 after step 2's forward must raise, not silently run step 2's
+    tape (plain autograd supports the pattern; a wrong gradient would be the worst answer)."""
+    import tcvom_b200
+    from tcvom_b200 import synthetic
+    from helpers import fixture_sd
+    tm = tcvom_b200.FullModel_VMD(model="vmn_gca", agg_window=7, dilate_kernel=2)
+    tm.NET.load_state_dict(fixture_sd(), strict=True)
+    tm = tm.to("cuda:0").train()
+    a, fg, bg = (torch.from_numpy(t).float().cuda() for t in synthetic.make_train_batch(1, 3, 64, 64, seed=3))
+    o1 = tm(a, fg, bg)
+    o2 = tm(a, fg, bg)
+    with pytest.raises(RuntimeError, match="another train-mode forward"):
+        o1[0].mean().backward()
+    o2[0].mean().backward()                                   # the latest step is intact
+    assert all(torch.isfinite(p.grad).all() for p in tm.NET.parameters() if p.grad is not None)
+    o3 = tm(a, fg, bg)
+    with torch.no_grad():
+        tm(a, fg, bg)                                         # a no_grad train-mode forward also replaces the tape
+    with pytest.raises(RuntimeError, match="another train-mode forward"):
+        o3[0].mean().backward()

@@ -194,3 +194,31 @@ def test_shift_sum_aggregation_equals_fold_program(emu, case):
     assert np.abs(res[True].numpy() - g["alphas"]).max() < 1e-3
     assert float((res[True] - res[False]).abs().max()) < 1e-4
     assert float((res[True] - res["consumer"]).abs().max()) < 5e-5
+
+
+def test_recorded_pointers_survive_replaced_parameters(emu):
+    """Plans / CUDA graphs bake in device pointers: conv biases must be engine-owned copies updated in place, because a
+    module parameter's storage is not stable (nn.DataParallel hands every forward freshly broadcast replica tensors).
+    A plan recorded against net A must give net B's result after refresh_weights(net B) -- without re-recording."""
+    g = golden("eval_ring64.npz")
+    imgs, tris = torch.from_numpy(g["imgs"]), torch.from_numpy(g["tris"])
+    B, S, _, H, W = imgs.shape
+    eng = make_gca_engine()
+    net_a = _net()
+    with torch.no_grad():
+        for k, v in net_a.state_dict().items():
+            if k.endswith(".bias") and ("fam" in k or "guidance_conv" in k or k == "decoder.conv2.bias"):
+                v.add_(0.3)                                     # net A: different conv biases than the fixture
+    eng.refresh_weights(net_a)
+    ptrs = {k: v.data_ptr() for k, v in eng.bias.items()}
+    plan, io = record_eval(eng, B, S, H, W, int(g["dilate"]), True)
+    io["imgs"].copy_(imgs); io["tris"].copy_(tris)
+    plan.replay(0)
+    assert np.abs(io["alphas"].numpy() - g["alphas"]).max() > 1e-3      # the biases matter
+    net_b = _net()                                                      # fresh tensors, fixture values
+    del net_a
+    eng.refresh_weights(net_b)
+    assert {k: v.data_ptr() for k, v in eng.bias.items()} == ptrs
+    assert all(v.data_ptr() not in {t.data_ptr() for t in net_b.state_dict().values()} for v in eng.bias.values())
+    plan.replay(0)                                                      # the SAME recorded plan
+    assert np.abs(io["alphas"].numpy() - g["alphas"]).max() < 1e-3
