@@ -1,0 +1,346 @@
+// Persistent tcgen05 GEMM for the two guided-contextual-attention products (GCA/ops.py:177,204):
+//     C[b] = A[b] . B[b]^T      A bf16 hi/lo planes [batch][M][K], B likewise [batch][N][K], C fp32 [batch][M][ldc]
+// bf16x3 (Ahi.Bhi + Ahi.Blo + Alo.Bhi, fp32 accumulation in TMEM), K-major operands through TMA (SWIZZLE_64B, BK = 32).
+//
+// Why a second GEMM kernel (the first one, igemm_tc.cu, computes one 128 x 128 tile per CTA): the scores product has
+// K = 576 only, so a 128 x 128 tile streams 576 KB of operands through shared memory for 6.9 k cycles of MMA work -- 83 B/clk
+// of TMA writes on top of the 128 B/clk an M=128,N=128 MMA reads (both operands in shared memory).  Shared memory, not
+// the tensor pipe, bounded it (59 % of the bf16 peak incl. the 3x split).  This kernel uses
+//   * CG = 2: a CTA PAIR (cluster of 2, tcgen05.mma.cta_group::2) per 256 x 256 tile: each CTA stages its own 128 rows
+//     of A and HALF of the B tile; per SM the MMA reads 8 KB per 128 cycles (64 B/clk) and TMA writes 42 B/clk;
+//   * CG = 1: one CTA per 128 x 256 tile (96 B/clk MMA reads + 62 B/clk TMA), kept as the cross-check / fallback;
+//   * persistent CTAs (one pair per two SMs), double-buffered TMEM accumulator (2 x 256 columns): the 8 epilogue warps
+//     write tile k while TMA / MMA work on tile k+1; N-fastest tile order (an A row panel stays in L2).
+//
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA only) + TMEM owner, warps 2..9 epilogue
+// (two warps per TMEM lane quarter, 128 columns each).
+//
+// 2-CTA protocol (per CTA shared memory holds the same barrier layout):
+//   full[s]    lives in the LEADER (the MMA issuer waits there): the leader's producer expects 2 x STAGE bytes, both CTAs'
+//              TMA loads (cp.async.bulk.tensor ... .cta_group::2) complete_tx on it;
+//   empty[s]   one per CTA; tcgen05.commit.cta_group::2 ... multicast::cluster arrives on both;
+//   accFull[b] one per CTA (each CTA's epilogue reads its own 128 accumulator rows); multicast commit;
+//   accEmpty[b] in the LEADER, 16 arrivals (8 epilogue warps of each CTA; the peer arrives through mapa).
+#include "tc_common.cuh"
+
+namespace tcv {
+
+extern std::atomic<int> g_debug_flags;
+
+struct G2Params {
+  int M, N, batch;
+  int tiles_m, tiles_n, total_tiles;
+  int kc_iters;
+  float* c;
+  long long ldc, c_batch_stride;
+  uint32_t idesc;
+};
+
+template <int CG>
+struct G2Cfg {
+  static constexpr int BK = 32;
+  static constexpr int BN = 256;
+  static constexpr int A_PLANE = 128 * BK * 2;        // 8 KB: this CTA's 128 rows of A
+  static constexpr int B_ROWS = BN / CG;              // rows of the B tile this CTA stages
+  static constexpr int B_PLANE = B_ROWS * BK * 2;
+  static constexpr int STAGE = 2 * (A_PLANE + B_PLANE);   // hi + lo planes: 32 KB (pair) / 48 KB (single)
+  static constexpr int STAGES = CG == 2 ? 6 : 4;          // 192 KB
+  static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+};
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1,
+                                                 int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+
+template <int CG>
+__global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi,
+                                                          const __grid_constant__ CUtensorMap mapA_lo,
+                                                          const __grid_constant__ CUtensorMap mapB_hi,
+                                                          const __grid_constant__ CUtensorMap mapB_lo,
+                                                          const __grid_constant__ G2Params p) {
+  using Cfg = G2Cfg<CG>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto acc_full = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto acc_empty = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_rank() : 0u;
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x / CG, npairs = gridDim.x / CG;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), 8 * CG);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB_lo) : "memory");
+  }
+  if (warp == 1) {
+    if constexpr (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int tiles_per_batch = p.tiles_m * p.tiles_n;
+  auto decode = [&](int tile, int& b, int& tm, int& tn) {
+    b = tile / tiles_per_batch;
+    const int r = tile - b * tiles_per_batch;
+    tm = r / p.tiles_n;          // N-tiles fastest: consecutive tiles share one A row panel
+    tn = r - tm * p.tiles_n;
+  };
+
+  if (warp == 0) {
+    // ================================ TMA producer (every CTA) ================================
+    int it = 0;
+    for (int tile = pair; tile < p.total_tiles; tile += npairs) {
+      int b, tm, tn;
+      decode(tile, b, tm, tn);
+      const int m0 = tm * 128 * CG + (int)rank * 128;
+      const int n0 = tn * Cfg::BN + (int)rank * Cfg::B_ROWS;
+      for (int kc = 0; kc < p.kc_iters; ++kc, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(empty_bar(s), (((uint32_t)(it / STAGES)) & 1u) ^ 1u);
+        const uint32_t st = smem_base + s * Cfg::STAGE;
+        if (elect_one()) {
+          const int k0 = kc * Cfg::BK;
+          if constexpr (CG == 2) {
+            if (leader) mbar_expect_tx(full_bar(s), 2u * Cfg::STAGE);
+            const uint32_t fb = mapa(full_bar(s), 0);
+            tma_load_3d_pair(st, &mapA_hi, fb, k0, m0, b);
+            tma_load_3d_pair(st + Cfg::A_PLANE, &mapA_lo, fb, k0, m0, b);
+            tma_load_3d_pair(st + 2 * Cfg::A_PLANE, &mapB_hi, fb, k0, n0, b);
+            tma_load_3d_pair(st + 2 * Cfg::A_PLANE + Cfg::B_PLANE, &mapB_lo, fb, k0, n0, b);
+          } else {
+            mbar_expect_tx(full_bar(s), (uint32_t)Cfg::STAGE);
+            tma_load_3d(st, &mapA_hi, full_bar(s), k0, m0, b);
+            tma_load_3d(st + Cfg::A_PLANE, &mapA_lo, full_bar(s), k0, m0, b);
+            tma_load_3d(st + 2 * Cfg::A_PLANE, &mapB_hi, full_bar(s), k0, n0, b);
+            tma_load_3d(st + 2 * Cfg::A_PLANE + Cfg::B_PLANE, &mapB_lo, full_bar(s), k0, n0, b);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader CTA only) ================================
+    if (leader) {
+      int it = 0, iw = 0;
+      for (int tile = pair; tile < p.total_tiles; tile += npairs, ++iw) {
+        const int buf = iw & 1;
+        mbar_wait(acc_empty(buf), (((uint32_t)(iw >> 1)) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(buf * Cfg::BN);
+        for (int kc = 0; kc < p.kc_iters; ++kc, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(full_bar(s), ((uint32_t)(it / STAGES)) & 1u);
+          tc_fence_after();
+          const uint32_t st = smem_base + s * Cfg::STAGE;
+          const uint32_t a_hi = st, a_lo = st + Cfg::A_PLANE;
+          const uint32_t b_hi = st + 2 * Cfg::A_PLANE, b_lo = b_hi + Cfg::B_PLANE;
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < Cfg::BK / 16; ++ks) {
+              const uint64_t ah = smem_desc<Cfg::BK>(a_hi + ks * 32), al = smem_desc<Cfg::BK>(a_lo + ks * 32);
+              const uint64_t bh = smem_desc<Cfg::BK>(b_hi + ks * 32), bl = smem_desc<Cfg::BK>(b_lo + ks * 32);
+              const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
+              if constexpr (CG == 2) {
+                tc_mma_pair(d, ah, bh, p.idesc, acc);
+                tc_mma_pair(d, ah, bl, p.idesc, 1u);
+                tc_mma_pair(d, al, bh, p.idesc, 1u);
+              } else {
+                tc_mma(d, ah, bh, p.idesc, acc);
+                tc_mma(d, ah, bl, p.idesc, 1u);
+                tc_mma(d, al, bh, p.idesc, 1u);
+              }
+            }
+            if constexpr (CG == 2) {
+              tc_commit_pair(empty_bar(s));
+              if (kc == p.kc_iters - 1) tc_commit_pair(acc_full(buf));
+            } else {
+              tc_commit(empty_bar(s));
+              if (kc == p.kc_iters - 1) tc_commit(acc_full(buf));
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ================================ epilogue (warps 2..9, every CTA) ================================
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;        // which 128 accumulator columns
+    const uint32_t ae_leader = CG == 2 ? mapa(acc_empty(0), 0) : acc_empty(0);
+    int iw = 0;
+    for (int tile = pair; tile < p.total_tiles; tile += npairs, ++iw) {
+      int b, tm, tn;
+      decode(tile, b, tm, tn);
+      const int buf = iw & 1;
+      const int m = tm * 128 * CG + (int)rank * 128 + q * 32 + lane;
+      const int nb0 = tn * Cfg::BN + half * 128;
+      mbar_wait(acc_full(buf), ((uint32_t)(iw >> 1)) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * Cfg::BN + half * 128);
+      float* crow = p.c + (long long)b * p.c_batch_stride + (long long)m * p.ldc;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tc_ld32(taddr + c0, v);
+        const int nb = nb0 + c0;
+        if (m < p.M && nb < p.N) {
+          float* c = crow + nb;
+          if (nb + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(c + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            for (int j = 0; j < 32 && nb + j < p.N; ++j) c[j] = __uint_as_float(v[j]);
+          }
+        }
+      }
+      // all TMEM reads of this warp are complete: hand the buffer back to the (leader's) MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(ae_leader + 8u * buf);
+        else mbar_arrive(acc_empty(buf));
+      }
+    }
+  }
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    if constexpr (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major
+static inline uint32_t instr_desc_mn(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int CG>
+static int launch_gemm_tc2(const void* A, long long a_plane, const void* B, long long b_plane, float* C, int M, int N, int K,
+                           long long ldc, long long c_batch_stride, int batch, cudaStream_t st) {
+  using Cfg = G2Cfg<CG>;
+  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+  const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(A);
+  const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(B);
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)M, (cuuint64_t)batch};
+    cuuint64_t str[2] = {(cuuint64_t)K * 2, (cuuint64_t)M * K * 2};
+    cuuint32_t box[3] = {(cuuint32_t)Cfg::BK, 128, 1};
+    int rc = make_map(&mA_hi, a, 3, dims, str, box, Cfg::BK);
+    if (rc) return rc;
+    rc = make_map(&mA_lo, a + a_plane, 3, dims, str, box, Cfg::BK);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)batch};
+    cuuint64_t str[2] = {(cuuint64_t)K * 2, (cuuint64_t)N * K * 2};
+    cuuint32_t box[3] = {(cuuint32_t)Cfg::BK, (cuuint32_t)Cfg::B_ROWS, 1};
+    int rc = make_map(&mB_hi, b, 3, dims, str, box, Cfg::BK);
+    if (rc) return rc;
+    rc = make_map(&mB_lo, b + b_plane, 3, dims, str, box, Cfg::BK);
+    if (rc) return rc;
+  }
+  G2Params p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.batch = batch;
+  p.tiles_m = (M + 128 * CG - 1) / (128 * CG);
+  p.tiles_n = (N + Cfg::BN - 1) / Cfg::BN;
+  p.total_tiles = p.tiles_m * p.tiles_n * batch;
+  p.kc_iters = K / Cfg::BK;
+  p.c = C; p.ldc = ldc; p.c_batch_stride = c_batch_stride;
+  p.idesc = instr_desc_mn(128 * CG, Cfg::BN);
+  auto kern = gemm_tc2_kernel<CG>;
+  TCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  int dev = 0, sms = 0;
+  TCV_CUDA(cudaGetDevice(&dev));
+  TCV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int npairs = sms / CG;
+  if (npairs > p.total_tiles) npairs = p.total_tiles;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(npairs * CG), 1, 1);
+  cfg.blockDim = dim3(320, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TCV_CUDA(cudaLaunchKernelEx(&cfg, kern, mA_hi, mA_lo, mB_hi, mB_lo, p));
+  return launched("gemm_tc2_kernel");
+}
+
+// mode: 2 = CTA pair (256 x 256 tiles), 1 = single CTA (128 x 256 tiles)
+int gemm_tc2(const void* A, long long a_plane, const void* B, long long b_plane, float* C, int M, int N, int K, long long ldc,
+             long long c_batch_stride, int batch, int mode, cudaStream_t st) {
+  if (mode == 2) return launch_gemm_tc2<2>(A, a_plane, B, b_plane, C, M, N, K, ldc, c_batch_stride, batch, st);
+  return launch_gemm_tc2<1>(A, a_plane, B, b_plane, C, M, N, K, ldc, c_batch_stride, batch, st);
+}
+
+}  // namespace tcv

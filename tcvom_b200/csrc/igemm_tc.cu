@@ -22,6 +22,10 @@
 
 namespace tcv {
 
+extern std::atomic<int> g_debug_flags;
+int gemm_tc2(const void* A, long long a_plane, const void* B, long long b_plane, float* C, int M, int N, int K, long long ldc,
+             long long c_batch_stride, int batch, int mode, cudaStream_t st);
+
 enum { EPI_CONV = 0, EPI_F32 = 1, EPI_BF16 = 2 };
 
 struct TcParams {
@@ -433,6 +437,14 @@ extern "C" int tcv_gemm_tn_tc(const void* A, long long a_plane, const void* B, l
   TCV_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0,
               "gemm_tn_tc: pointers must be 16-byte aligned");
   TCV_REQUIRE(out_bf16 || ldc % 4 == 0, "gemm_tn_tc: ldc must be a multiple of 4 for fp32 output");
+  {
+    // large fp32-output bf16x3 products (the GCA scores / aggregation GEMMs): persistent 256-wide tiles, by default on
+    // CTA pairs (gemm_tc2.cu).  tcv_set_debug_flags: 1024 = single-CTA 128 x 256 tiles, 2048 = the per-tile kernel below.
+    const int flags = g_debug_flags.load();
+    if (nsplit == 3 && !out_bf16 && !in_fp16 && M >= 512 && N >= 256 && !(flags & 2048))
+      return gemm_tc2(A, a_plane, B, b_plane, reinterpret_cast<float*>(C), M, N, K, ldc, c_batch_stride, batch,
+                      (flags & 1024) ? 1 : 2, S(stream));
+  }
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.gh = 1; p.gw = M; p.TH = 1; p.TW = 128;
