@@ -587,7 +587,7 @@ def run_native(args, rank, world, local_rank):
             total = sum(k["ms"] for k in kinds.values())
             top_name, top = max(kinds.items(), key=lambda kv: kv[1]["ms"])
             pk = peaks()
-            tensor_kinds = ("gca_scores_gemm", "gca_pv_gemm", "conv_tc", "conv_tc2", "conv_tc3", "gca_scores_gemm_tc", "gca_pv_gemm_tc")
+            tensor_kinds = ("gca_scores_gemm", "gca_pv_gemm", "conv_tc", "conv_tc2", "conv_tc2p", "conv_tc3", "gca_scores_gemm_tc", "gca_pv_gemm_tc")
             if top_name in tensor_kinds:
                 ach = top["flops"] / (top["ms"] * 1e-3) / 1e12
                 roof = dict(bound="tensor", achieved=ach, peak=pk["tf_sustained"], unit="TFLOP/s",

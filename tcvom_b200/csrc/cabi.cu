@@ -29,6 +29,8 @@ int conv2d_tc_supported(const tcv_conv_desc& d);
 int conv2d_tc(const tcv_conv_desc& d, cudaStream_t st);
 int conv2d_tc2_supported(const tcv_conv_desc& d);
 int conv2d_tc2(const tcv_conv_desc& d, cudaStream_t st);
+int conv2d_tc2p_supported(const tcv_conv_desc& d);
+int conv2d_tc2p(const tcv_conv_desc& d, cudaStream_t st);
 int conv2d_tc3_supported(const tcv_conv_desc& d);
 int conv2d_tc3(const tcv_conv_desc& d, cudaStream_t st);
 std::atomic<int> g_conv_tc_version{3};
@@ -50,6 +52,7 @@ int tcv_conv2d_path(const tcv_conv_desc* dp) {
   if (d.x_plane == 0) d.x_plane = (long long)d.n * d.ih * d.iw * d.cin;
   if (d.x_img_stride == 0) d.x_img_stride = (long long)d.ih * d.iw * d.cin;
   if (g_conv_tc_version.load() >= 3 && conv2d_tc3_supported(d)) return 3;
+  if (g_conv_tc_version.load() >= 2 && !(g_debug_flags.load() & 4096) && conv2d_tc2p_supported(d)) return 4;
   if (g_conv_tc_version.load() >= 2 && conv2d_tc2_supported(d)) return 2;
   return conv2d_tc_supported(d) ? 1 : 0;
 }
@@ -90,6 +93,9 @@ int tcv_conv2d(const tcv_conv_desc* dp, tcv_stream_t stream) {
     d.res1_plane = (long long)d.n * (d.oh >> d.res1_shift) * (d.ow >> d.res1_shift) * d.cout;
   if (d.res2 && d.res2_plane == 0) d.res2_plane = (long long)d.n * d.oh * d.ow * d.cout;
   if (g_conv_tc_version.load() >= 3 && conv2d_tc3_supported(d)) return conv2d_tc3(d, S(stream));
+  // wide layers (Cout >= 128) on CTA pairs (conv_tc2p.cu); tcv_set_debug_flags bit 4096 falls back to the single-CTA kernel
+  if (g_conv_tc_version.load() >= 2 && !(g_debug_flags.load() & 4096) && conv2d_tc2p_supported(d))
+    return conv2d_tc2p(d, S(stream));
   if (g_conv_tc_version.load() >= 2 && conv2d_tc2_supported(d)) return conv2d_tc2(d, S(stream));
   if (conv2d_tc_supported(d)) return conv2d_tc(d, S(stream));
   return conv2d_direct(d, S(stream));

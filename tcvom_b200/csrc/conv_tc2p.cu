@@ -1,0 +1,412 @@
+// CTA-pair version of the persistent tcgen05 convolution kernel (conv_tc2.cu) for the wide layers (Cout >= 128).
+//
+// Why: with both operands in shared memory an M=128,N=128,K=16 MMA reads 8 KB per 64 cycles -- exactly the 128 B/clk a
+// SM's shared memory delivers -- so in conv_tc2 the MMA stream and the TMA writes of the next stage (37 B/clk) serialise
+// (measured: MMA alone 14.5 us, TMA alone 11.7 us, together 27 us per work item of a 128->128 layer).  A CTA pair
+// (cluster of 2, tcgen05.mma.cta_group::2, M = 256) halves the B-operand traffic per SM:
+//   * the pair owns the same 2*TH x TW pixel super-tile as one conv_tc2 CTA, but CTA rank r stages only ITS half
+//     (TH + halo rows) of the activation box and HALF (BN/2 rows) of every weight tile;
+//   * one MMA of M=256, N=BN (up to 256) covers both pixel tiles: per SM it reads 4 KB of A + BN*16 B of B per
+//     BN/2 cycles (N=256: 64 B/clk), TMA writes ~30 B/clk;
+//   * each CTA holds ONE accumulator [128 px x BN ch], double-buffered in TMEM (2 x BN columns); its 8 epilogue warps
+//     split the columns in two halves (4 warps = 4 TMEM lane quarters each) and run the same fused epilogue
+//     (tc_epilogue.cuh) with the TMA-store staging of conv_tc2.
+// Barrier protocol as in gemm_tc2.cu: fullA/fullB live in the leader (its producer expects both CTAs' bytes, both CTAs'
+// TMA loads complete_tx there), emptyA/emptyB/accFull per CTA (multicast commit), accEmpty in the leader (16 arrivals).
+#include "tc_epilogue.cuh"
+
+namespace tcv {
+
+extern std::atomic<int> g_debug_flags;
+
+constexpr int VP_BK = 32;
+constexpr int VP_MAXG = 3;
+constexpr int VP_MAXDY = 3;
+constexpr int VP_A_SLOT_BYTES = 2 * 12288;   // hi + lo planes of one (TH + halo) x TW x 32-channel box: up to 192 rows x 64 B
+
+struct VPParams {
+  int gh, gw, TH, TW, tiles_x, tiles_y, n_tiles_n, total_work;
+  int kc_iters;
+  int ngroups, group_dx[VP_MAXG], ndy[VP_MAXG], dy[VP_MAXG][VP_MAXDY], wtap[VP_MAXG][VP_MAXDY];
+  int dy_min, box_rows;
+  int tma_store;
+  uint32_t idesc;
+  EpiParams epi;
+};
+
+template <int BN>
+struct VPCfg {
+  static constexpr int B_ROWS = BN / 2;                         // rows of a weight tile this CTA stages
+  static constexpr int B_SLOT_BYTES = 2 * B_ROWS * VP_BK * 2;   // hi + lo
+  static constexpr int A_SLOTS = 3;
+  static constexpr int A_BYTES = A_SLOTS * VP_A_SLOT_BYTES;     // 72 KB
+  static constexpr int STAGE_BYTES = 2 * 2 * 128 * 64;          // TMA-store staging: 2 column groups x hi/lo x 128 rows x 64 B
+  static constexpr int B_SLOTS = (200 * 1024 - A_BYTES - STAGE_BYTES) / B_SLOT_BYTES > 8
+                                     ? 8 : (200 * 1024 - A_BYTES - STAGE_BYTES) / B_SLOT_BYTES;
+  static constexpr int SMEM = A_BYTES + B_SLOTS * B_SLOT_BYTES + STAGE_BYTES + 1024 + 512;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // 2 buffers x one accumulator
+};
+
+__device__ __forceinline__ uint32_t vp_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void vp_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t vp_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void vp_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void vp_tma_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2,
+                                          int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void vp_tma_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void vp_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void vp_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(320, 1) conv_tc2p_kernel(const __grid_constant__ CUtensorMap mapA_hi,
+                                                           const __grid_constant__ CUtensorMap mapA_lo,
+                                                           const __grid_constant__ CUtensorMap mapB_hi,
+                                                           const __grid_constant__ CUtensorMap mapB_lo,
+                                                           const __grid_constant__ CUtensorMap mapY_hi,
+                                                           const __grid_constant__ CUtensorMap mapY_lo,
+                                                           const __grid_constant__ VPParams p) {
+  using Cfg = VPCfg<BN>;
+  constexpr int SA = Cfg::A_SLOTS, SB = Cfg::B_SLOTS;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_base = smem_base + Cfg::A_BYTES;
+  const uint32_t stage_base = b_base + SB * Cfg::B_SLOT_BYTES;
+  const uint32_t bar_base = stage_base + Cfg::STAGE_BYTES;
+  auto fullA = [&](int s) { return bar_base + 8u * s; };
+  auto emptyA = [&](int s) { return bar_base + 8u * (SA + s); };
+  auto fullB = [&](int s) { return bar_base + 8u * (2 * SA + s); };
+  auto emptyB = [&](int s) { return bar_base + 8u * (2 * SA + SB + s); };
+  auto accFull = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SB + a); };
+  auto accEmpty = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SB + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * SA + 2 * SB + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = vp_cluster_rank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < SA; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(accFull(a), 1); mbar_init(accEmpty(a), 16); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB_lo) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  vp_cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int a_plane_bytes = p.box_rows * p.TW * (VP_BK * 2);   // one plane of this CTA's A box
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  // work item -> (image, origin of the pair's 2*TH x TW super-tile, first output channel)
+  auto decode = [&](int work, int& img, int& h0, int& w0, int& n0) {
+    const int nt = work % p.n_tiles_n;
+    int r = work / p.n_tiles_n;
+    const int t = r % tiles_per_img;
+    img = r / tiles_per_img;
+    const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+    h0 = ty * 2 * p.TH;
+    w0 = tx * p.TW;
+    n0 = nt * BN;
+  };
+
+  if (warp == 0) {
+    // ================================ TMA producer (every CTA) ================================
+    int ia = 0, ib = 0;
+    for (int work = pair; work < p.total_work; work += npairs) {
+      int img, h0, w0, n0;
+      decode(work, img, h0, w0, n0);
+      const int hr = h0 + (int)rank * p.TH + p.dy_min;      // first box row of this CTA's pixel tile
+      const int nb = n0 + (int)rank * Cfg::B_ROWS;          // this CTA's half of the weight tile
+      for (int kc = 0; kc < p.kc_iters; ++kc) {
+        for (int g = 0; g < p.ngroups; ++g, ++ia) {
+          const int sa = ia % SA;
+          mbar_wait(emptyA(sa), ((uint32_t)(ia / SA) & 1u) ^ 1u);
+          const uint32_t adst = smem_base + sa * VP_A_SLOT_BYTES;
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(fullA(sa), 4u * a_plane_bytes);
+            const uint32_t fb = vp_mapa(fullA(sa), 0);
+            vp_tma_4d(adst, &mapA_hi, fb, kc * VP_BK, w0 + p.group_dx[g], hr, img);
+            vp_tma_4d(adst + a_plane_bytes, &mapA_lo, fb, kc * VP_BK, w0 + p.group_dx[g], hr, img);
+          }
+          __syncwarp();
+          for (int j = 0; j < p.ndy[g]; ++j, ++ib) {
+            const int sb = ib % SB;
+            mbar_wait(emptyB(sb), ((uint32_t)(ib / SB) & 1u) ^ 1u);
+            const uint32_t bdst = b_base + sb * Cfg::B_SLOT_BYTES;
+            if (elect_one()) {
+              if (leader) mbar_expect_tx(fullB(sb), 2u * Cfg::B_SLOT_BYTES);
+              const uint32_t fb = vp_mapa(fullB(sb), 0);
+              vp_tma_3d(bdst, &mapB_hi, fb, kc * VP_BK, nb, p.wtap[g][j]);
+              vp_tma_3d(bdst + Cfg::B_SLOT_BYTES / 2, &mapB_lo, fb, kc * VP_BK, nb, p.wtap[g][j]);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader CTA only) ================================
+    if (leader) {
+      int ia = 0, ib = 0, iw = 0;
+      for (int work = pair; work < p.total_work; work += npairs, ++iw) {
+        const int buf = iw & 1;
+        mbar_wait(accEmpty(buf), ((uint32_t)(iw >> 1) & 1u) ^ 1u);   // both CTAs' epilogues have drained this buffer
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(buf * BN);
+        bool first = true;
+        for (int kc = 0; kc < p.kc_iters; ++kc) {
+          for (int g = 0; g < p.ngroups; ++g, ++ia) {
+            const int sa = ia % SA;
+            mbar_wait(fullA(sa), (uint32_t)(ia / SA) & 1u);
+            tc_fence_after();
+            const uint32_t a_hi = smem_base + sa * VP_A_SLOT_BYTES, a_lo = a_hi + a_plane_bytes;
+            for (int j = 0; j < p.ndy[g]; ++j, ++ib) {
+              const int sb = ib % SB;
+              mbar_wait(fullB(sb), (uint32_t)(ib / SB) & 1u);
+              tc_fence_after();
+              const uint32_t b_hi = b_base + sb * Cfg::B_SLOT_BYTES, b_lo = b_hi + Cfg::B_SLOT_BYTES / 2;
+              if (elect_one()) {
+                // rows of the accumulator for vertical tap dy start (dy - dy_min) image rows into the box (same offset in
+                // the peer's shared memory, whose box starts TH image rows lower)
+                const uint32_t roff = (uint32_t)((p.dy[g][j] - p.dy_min) * p.TW) * (VP_BK * 2);
+#pragma unroll
+                for (int ks = 0; ks < VP_BK / 16; ++ks) {
+                  const uint64_t ah = smem_desc<VP_BK>(a_hi + roff + ks * 32), al = smem_desc<VP_BK>(a_lo + roff + ks * 32);
+                  const uint64_t bh = smem_desc<VP_BK>(b_hi + ks * 32), bl = smem_desc<VP_BK>(b_lo + ks * 32);
+                  vp_mma(d, ah, bh, p.idesc, (first && ks == 0) ? 0u : 1u);
+                  vp_mma(d, ah, bl, p.idesc, 1u);
+                  vp_mma(d, al, bh, p.idesc, 1u);
+                }
+                vp_commit(emptyB(sb));
+                if (j == p.ndy[g] - 1) {
+                  vp_commit(emptyA(sa));
+                  if (kc == p.kc_iters - 1 && g == p.ngroups - 1) vp_commit(accFull(buf));
+                }
+              }
+              __syncwarp();
+              first = false;
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ================================ epilogue (warps 2..9, every CTA) ================================
+    constexpr int HN = BN / 2;           // columns per 4-warp group
+    const int e = warp - 2;              // 0..7
+    const int grp = e >> 2;              // column half of this CTA's accumulator
+    const int q = warp & 3;              // TMEM lane quarter accessible to this warp
+    const int r = q * 32 + lane;         // accumulator row = pixel of this CTA's TH x TW tile
+    StoreCtx stc;
+    if (p.tma_store) {
+      stc.stage_hi = stage_base + (uint32_t)grp * (2u * 128u * 64u);
+      stc.stage_lo = stc.stage_hi + 128u * 64u;
+      stc.row = r;
+      stc.bar = 1 + grp;
+      stc.issuer = (e & 3) == 0 && lane == 0;
+      stc.map_hi = &mapY_hi;
+      stc.map_lo = &mapY_lo;
+    }
+    const uint32_t ae_leader = vp_mapa(accEmpty(0), 0);
+    int iw = 0;
+    for (int work = pair; work < p.total_work; work += npairs, ++iw) {
+      int img, h0, w0, n0;
+      decode(work, img, h0, w0, n0);
+      const int buf = iw & 1;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + grp * HN);
+      const int ty = r / p.TW, tx = r - ty * p.TW;
+      const int gy = h0 + (int)rank * p.TH + ty, gx = w0 + tx;
+      stc.cx = w0;
+      stc.cy = h0 + (int)rank * p.TH;
+      conv_epilogue<HN>(p.epi, taddr, gy < p.gh && gx < p.gw, img, gy, gx, n0 + grp * HN, accFull(buf),
+                        (uint32_t)(iw >> 1) & 1u, ae_leader + 8u * buf, lane, stc, false, /*remote_empty=*/true);
+    }
+    if (stc.issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  vp_cluster_sync();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+static bool vp_build_groups(const tcv_conv_desc& d, VPParams& p) {
+  p.ngroups = 0;
+  int dymin = 1 << 30, dymax = -(1 << 30);
+  for (int t = 0; t < d.ntaps; ++t) {
+    int g = -1;
+    for (int k = 0; k < p.ngroups; ++k)
+      if (p.group_dx[k] == d.dx[t]) g = k;
+    if (g < 0) {
+      if (p.ngroups == VP_MAXG) return false;
+      g = p.ngroups++;
+      p.group_dx[g] = d.dx[t];
+      p.ndy[g] = 0;
+    }
+    if (p.ndy[g] == VP_MAXDY) return false;
+    p.dy[g][p.ndy[g]] = d.dy[t];
+    p.wtap[g][p.ndy[g]] = d.wtap[t];
+    p.ndy[g]++;
+    dymin = d.dy[t] < dymin ? d.dy[t] : dymin;
+    dymax = d.dy[t] > dymax ? d.dy[t] : dymax;
+  }
+  p.dy_min = dymin;
+  p.box_rows = dymax - dymin;   // halo rows; TH added once the tile is chosen
+  return true;
+}
+
+static void vp_pick_tile(int gh, int gw, int halo, int* TH, int* TW) {
+  long long best = -1;
+  const int cand[3][2] = {{8, 16}, {4, 32}, {16, 8}};
+  for (auto& c : cand) {
+    const int th = c[0], tw = c[1];
+    if ((th + halo) * tw * VP_BK * 2 > VP_A_SLOT_BYTES / 2) continue;
+    // cost model: pixels covered by the pair tiles, plus the halo rows each CTA fetches on top of its TH rows
+    const long long tiles = (long long)((gh + 2 * th - 1) / (2 * th)) * ((gw + tw - 1) / tw);
+    const long long cost = tiles * 2 * (th + halo) * tw;
+    if (best < 0 || cost < best) { best = cost; *TH = th; *TW = tw; }
+  }
+}
+
+int conv2d_tc2p_supported(const tcv_conv_desc& d) {
+  if (!d.w_tc) return 0;
+  if (d.stride != 1 || d.pad_mode != TCV_PAD_ZERO) return 0;
+  if (d.cin % 32 != 0 || d.cout % 64 != 0) return 0;
+  if (d.cout % 128 != 0 && !(g_debug_flags.load() & 8192)) return 0;   // 64-channel layers: opt-in (A/B switch)
+  if (d.x_img_stride != (long long)d.ih * d.iw * d.cin) return 0;
+  if (!d.y || d.y_f32) return 0;                       // TMA-store epilogue only
+  VPParams p;
+  return vp_build_groups(d, p) ? 1 : 0;
+}
+
+template <int BN>
+static int conv_tc2p_bn(const tcv_conv_desc& d, cudaStream_t st) {
+  using Cfg = VPCfg<BN>;
+  VPParams p;
+  memset(&p, 0, sizeof(p));
+  if (!vp_build_groups(d, p)) return fail(TCV_ERR_UNSUPPORTED, "conv_tc2p: tap pattern not supported");
+  const int halo = p.box_rows;
+  vp_pick_tile(d.gh, d.gw, halo, &p.TH, &p.TW);
+  p.box_rows = p.TH + halo;
+  p.gh = d.gh; p.gw = d.gw;
+  p.tiles_x = (d.gw + p.TW - 1) / p.TW;
+  p.tiles_y = (d.gh + 2 * p.TH - 1) / (2 * p.TH);
+  p.n_tiles_n = d.cout / BN;
+  p.total_work = p.tiles_x * p.tiles_y * p.n_tiles_n * d.n;
+  p.kc_iters = d.cin / VP_BK;
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  fill_epi(p.epi, d, 0);
+  p.tma_store = 1;
+
+  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo, mY_hi, mY_lo;
+  const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(d.x);
+  const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(d.w_tc);
+  {
+    const __nv_bfloat16* y = reinterpret_cast<const __nv_bfloat16*>(d.y) + ((long long)d.oy_off * d.ow + d.ox_off) * d.cout;
+    cuuint64_t dims[4] = {(cuuint64_t)d.cout, (cuuint64_t)d.gw, (cuuint64_t)d.gh, (cuuint64_t)d.n};
+    cuuint64_t str[3] = {(cuuint64_t)d.ox_mul * d.cout * 2, (cuuint64_t)d.oy_mul * d.ow * d.cout * 2,
+                         (cuuint64_t)d.oh * d.ow * d.cout * 2};
+    cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+    int rc = make_map(&mY_hi, y, 4, dims, str, box, 32);
+    if (rc) return rc;
+    rc = make_map(&mY_lo, y + (long long)d.n * d.oh * d.ow * d.cout, 4, dims, str, box, 32);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)d.iw, (cuuint64_t)d.ih, (cuuint64_t)d.n};
+    cuuint64_t str[3] = {(cuuint64_t)d.cin * 2, (cuuint64_t)d.iw * d.cin * 2, (cuuint64_t)d.x_img_stride * 2};
+    cuuint32_t box[4] = {(cuuint32_t)VP_BK, (cuuint32_t)p.TW, (cuuint32_t)p.box_rows, 1};
+    int rc = make_map(&mA_hi, a, 4, dims, str, box, VP_BK);
+    if (rc) return rc;
+    rc = make_map(&mA_lo, a + d.x_plane, 4, dims, str, box, VP_BK);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)d.cin, (cuuint64_t)d.cout, (cuuint64_t)d.w_tc_taps};
+    cuuint64_t str[2] = {(cuuint64_t)d.cin * 2, (cuuint64_t)d.cout * d.cin * 2};
+    cuuint32_t box[3] = {(cuuint32_t)VP_BK, (cuuint32_t)Cfg::B_ROWS, 1};
+    int rc = make_map(&mB_hi, b, 3, dims, str, box, VP_BK);
+    if (rc) return rc;
+    rc = make_map(&mB_lo, b + (long long)d.w_tc_taps * d.cout * d.cin, 3, dims, str, box, VP_BK);
+    if (rc) return rc;
+  }
+  auto kern = conv_tc2p_kernel<BN>;
+  TCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  int dev = 0, sms = 0;
+  TCV_CUDA(cudaGetDevice(&dev));
+  TCV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int npairs = sms / 2;
+  if (npairs > p.total_work) npairs = p.total_work;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(2 * npairs), 1, 1);
+  cfg.blockDim = dim3(320, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TCV_CUDA(cudaLaunchKernelEx(&cfg, kern, mA_hi, mA_lo, mB_hi, mB_lo, mY_hi, mY_lo, p));
+  return launched("conv_tc2p_kernel");
+}
+
+int conv2d_tc2p(const tcv_conv_desc& d, cudaStream_t st) {
+  if (d.cout % 256 == 0) return conv_tc2p_bn<256>(d, st);
+  if (d.cout % 128 == 0) return conv_tc2p_bn<128>(d, st);
+  return conv_tc2p_bn<64>(d, st);
+}
+
+}  // namespace tcv

@@ -49,7 +49,8 @@ struct StoreCtx {
 template <int BN>
 __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr, bool in_grid, int img, int gy, int gx,
                                               int n0, uint32_t acc_full, uint32_t full_parity, uint32_t acc_empty,
-                                              int lane, const StoreCtx& st = StoreCtx(), bool split_halves = false) {
+                                              int lane, const StoreCtx& st = StoreCtx(), bool split_halves = false,
+                                              bool remote_empty = false) {
   const bool valid = in_grid && !(p.dbg & 2);
   const int oy = gy * p.oy_mul + p.oy_off, ox = gx * p.ox_mul + p.ox_off;
   const long long oplane = (long long)p.n_imgs * p.oh * p.ow * p.cout;
@@ -106,7 +107,13 @@ __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr
       // all TMEM reads of this warp are complete: hand the buffer back to the MMA warp early
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty);
+      if (lane == 0) {
+        // remote_empty: `acc_empty` is a shared::cluster address (the leader CTA's barrier of a CTA pair)
+        if (remote_empty)
+          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(acc_empty) : "memory");
+        else
+          mbar_arrive(acc_empty);
+      }
     } else {
       fetch(c0 + 32, slot ^ 1);
     }

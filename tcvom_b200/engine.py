@@ -454,7 +454,7 @@ class GcaVmnEngine:
             nbytes += 4 * (px >> (2 * d.res1_shift)) * d.cout
         if d.res2:
             nbytes += 4 * px * d.cout
-        path = {0: "direct", 1: "tc", 2: "tc2", 3: "tc3"}[_cabi.lib().tcv_conv2d_path(C.byref(d))]
+        path = {0: "direct", 1: "tc", 2: "tc2", 3: "tc3", 4: "tc2p"}[_cabi.lib().tcv_conv2d_path(C.byref(d))]
         return dict(kind=f"conv_{path}", layer=wkey, flops=flops, bytes=nbytes,
                     shape=f"{d.cin}->{d.cout} k{k} s{stride} @{d.gh}x{d.gw} n{d.n}")
 

@@ -42,6 +42,19 @@ def test_conv_tc_matches_cuda_core_conv(cin, cout, h, w, n, kind):
     _tc().case_conv(cin, cout, h, w, n, kind)
 
 
+@pytest.mark.parametrize("cin,cout,h,w,n,kind", [
+    (128, 128, 136, 240, 3, "3x3"),     # N = 128 pair tiles, 3 rounds of work items
+    (256, 256, 68, 120, 3, "3x3"),      # N = 256
+    (512, 512, 34, 60, 3, "3x3"),       # two N tiles, K = 4608
+    (256, 128, 10, 12, 3, "3x3"),       # image smaller than a pair tile (the lower CTA's tile is mostly outside)
+    (128, 256, 18, 22, 2, "1x1"),       # no halo
+    (256, 256, 9, 14, 2, "deconv"),     # transposed-conv phase: strided TMA-store view
+])
+def test_conv_cta_pair_kernel(cin, cout, h, w, n, kind):
+    """Wide layers on CTA pairs (conv_tc2p.cu, tcgen05.mma.cta_group::2) against fp64 torch and the CUDA-core kernel."""
+    _tc().case_conv(cin, cout, h, w, n, kind, False, 4)
+
+
 def test_conv_kernel_generation_switch():
     """tcv_set_conv_tc_version selects the kernel generation; all generations agree."""
     from tcvom_b200 import _cabi

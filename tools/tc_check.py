@@ -56,7 +56,30 @@ def case_gemm(nsplit, M, N, K, batch, out_bf16=0):
     assert rel < tol and pad_ok
 
 
-def case_conv(cin, cout, h, w, n, kind):
+def conv_ref_fp64(x, wf, taps, wt, stride, gh, gw, oh, ow, mul, offs, s1, b1, res1, s2, b2, res2):
+    """fp64 torch restatement of what tcv_conv2d computes (include/tcvom_b200.h): zero-padded taps, BatchNorm affine,
+    nearest-upsampled residual, LeakyReLU(0.2), second affine, second residual, strided placement."""
+    import torch
+    n, h, w, cin = x.shape
+    P = 4
+    xp = torch.nn.functional.pad(x.double(), (0, 0, P, P + 2, P, P + 2))
+    acc = torch.zeros((n, gh, gw, wf.shape[2]), dtype=torch.float64, device=x.device)
+    for (dy, dx), k in zip(taps, wt):
+        sl = xp[:, P + dy: P + dy + (gh - 1) * stride + 1: stride, P + dx: P + dx + (gw - 1) * stride + 1: stride, :]
+        acc += torch.einsum("nhwc,cd->nhwd", sl, wf[k].double())
+    t = acc * s1.double() + b1.double()
+    oy = torch.arange(gh, device=x.device) * mul + offs[0]
+    ox = torch.arange(gw, device=x.device) * mul + offs[1]
+    t = t + res1.double()[:, (oy // 2)][:, :, (ox // 2)]
+    t = torch.where(t > 0, t, 0.2 * t)
+    t = t * s2.double() + b2.double()
+    t = t + res2.double()[:, oy][:, :, ox]
+    out = torch.zeros((n, oh, ow, wf.shape[2]), dtype=torch.float64, device=x.device)
+    out[:, oy[:, None], ox[None, :]] = t
+    return out, (oy, ox)
+
+
+def case_conv(cin, cout, h, w, n, kind, f32_side=True, expect_path=None):
     import torch
     from tcvom_b200 import _cabi
     from tcvom_b200._cabi import ConvDesc
@@ -107,8 +130,8 @@ def case_conv(cin, cout, h, w, n, kind):
             d.dy[i], d.dx[i], d.wtap[i] = dy, dx, wt[i]
         d.stride, d.pad_mode = (2 if kind == "3x3s2" else 1), 0
         d.y = y.data_ptr()
-        if cout != 32:
-            d.y_f32 = yf.data_ptr()   # (the narrow-layer kernel has no fp32 side output)
+        if cout != 32 and f32_side:
+            d.y_f32 = yf.data_ptr()   # (the narrow-layer and the CTA-pair kernels have no fp32 side output)
         d.oh, d.ow, d.cout, d.gh, d.gw = oh, ow, cout, gh, gw
         d.oy_mul, d.oy_off, d.ox_mul, d.ox_off = mul, offs[0], mul, offs[1]
         d.s1, d.b1 = s1.data_ptr(), b1.data_ptr()
@@ -118,15 +141,32 @@ def case_conv(cin, cout, h, w, n, kind):
         d.res2 = res2.data_ptr()
         path = L.tcv_conv2d_path(C.byref(d))
         assert (path > 0) == bool(use_tc), "dispatch did not pick the expected path"
+        if use_tc and expect_path is not None:
+            assert path == expect_path, f"expected kernel path {expect_path}, dispatch chose {path}"
         _cabi.check(L.tcv_conv2d(C.byref(d), st), "conv2d")
         torch.cuda.synchronize()
         ys = y[0].float() + y[1].float()
-        outs.append((ys, yf.clone() if cout != 32 else ys))
+        outs.append((ys, yf.clone() if (cout != 32 and f32_side) else ys))
     err = (outs[0][1] - outs[1][1]).abs().max().item()
     errs = (outs[0][0] - outs[1][0]).abs().max().item()
     mag = outs[0][1].abs().max().item()
-    print(f"conv {kind} {cin}->{cout} {h}x{w} n={n} path={path}: tc vs direct max abs err f32 {err:.3e} split {errs:.3e} (max |y| {mag:.2f})")
+    # independent reference: fp64 torch on the same (split-bf16 exact) operands
+    xs = x[0].float().double() + x[1].float().double()
+    r1 = res1[0].float().double() + res1[1].float().double()
+    r2 = res2[0].float().double() + res2[1].float().double()
+    ref, (oy, ox) = conv_ref_fp64(xs, wf, taps, wt, 2 if kind == "3x3s2" else 1, gh, gw, oh, ow, mul, offs, s1, b1, r1, s2, b2, r2)
+    sel = lambda t: t.double()[:, oy[:, None], ox[None, :]]
+    e_tc = (sel(outs[1][0]) - sel(ref)).abs().max().item()
+    e_dir = (sel(outs[0][0]) - sel(ref)).abs().max().item()
+    untouched = True
+    if mul == 2:      # a transposed-conv phase must leave the other three phases alone
+        mask = torch.ones((oh, ow), dtype=torch.bool, device=dev)
+        mask[oy[:, None], ox[None, :]] = False
+        untouched = bool((outs[1][0][:, mask] == 0).all())
+    print(f"conv {kind} {cin}->{cout} {h}x{w} n={n} path={path}: tc vs direct max abs err f32 {err:.3e} split {errs:.3e}; "
+          f"vs fp64 torch: tc {e_tc:.3e} direct {e_dir:.3e} (max |y| {mag:.2f})")
     assert err < 2e-4 * max(1.0, mag) and errs < 2e-4 * max(1.0, mag)
+    assert e_tc < 1e-4 * max(1.0, mag) and e_dir < 1e-4 * max(1.0, mag) and untouched
 
 
 CASES = {
@@ -142,6 +182,12 @@ CASES = {
     "conv3x3_128_128_big": lambda: case_conv(128, 128, 136, 240, 3, "3x3"),
     "conv3x3_32_32_big": lambda: case_conv(32, 32, 272, 480, 2, "3x3"),
     "conv3x3_512_512": lambda: case_conv(512, 512, 34, 60, 3, "3x3"),
+    "pair_3x3_128_128_big": lambda: case_conv(128, 128, 136, 240, 3, "3x3", False, 4),
+    "pair_3x3_256_256": lambda: case_conv(256, 256, 68, 120, 3, "3x3", False, 4),
+    "pair_3x3_512_512": lambda: case_conv(512, 512, 34, 60, 3, "3x3", False, 4),
+    "pair_3x3_256_128_ragged": lambda: case_conv(256, 128, 10, 12, 3, "3x3", False, 4),
+    "pair_1x1_128_256": lambda: case_conv(128, 256, 18, 22, 2, "1x1", False, 4),
+    "pair_deconv_256_256": lambda: case_conv(256, 256, 9, 14, 2, "deconv", False, 4),
     "conv3x3s2_64_128": lambda: case_conv(64, 128, 40, 56, 2, "3x3s2"),
     "conv3x3s2_32_64": lambda: case_conv(32, 64, 36, 52, 1, "3x3s2"),
     "conv3x3_8_32_fold": lambda: case_conv(8, 32, 40, 56, 2, "3x3"),
