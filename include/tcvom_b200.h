@@ -289,6 +289,13 @@ int tcv_pad_reflect1_bwd(const void* dy, int n, int h, int w, int c, void* dx, t
 /* gradient of (tanh(z)+1)/2 given the output: dz8[i][0] = dpred[i]*2*pred[i]*(1-pred[i]), channels 1..7 = 0
  * (split-bf16 [pixels][8], the 8-channel padding the conv kernels need) */
 int tcv_tanh01_bwd(const float* pred, const float* dpred, long long pixels, void* dz8, tcv_stream_t stream);
+/* alpha head of the decoder (resnet_dec.py:80 conv2 = Conv2d(32, 1, 3, padding=1, bias) ; VMN_GCA.py:46-47 (tanh+1)/2) in one
+ * HBM-bound pass: x split-bf16 NHWC [n,h,w,32] (lo plane x_plane elements later; 0 = contiguous), wt fp32 [9][32] (tap-major,
+ * tap = ky*3+kx), bias fp32 [1] or NULL -> pred fp32 [n,h,w].  Inference path; training keeps the padded 32-channel
+ * tensor-core form (tcv_conv2d + tcv_head_tanh01) whose gradients run on the conv kernels. */
+int tcv_head_conv_tanh01(const void* x, long long x_plane, int n, int h, int w, const float* wt, const float* bias,
+                         float* pred, tcv_stream_t stream);
+
 /* Alpha head on the tensor-core conv path: decoder.conv2 (32 -> 1, VMN_GCA.py:46) is run as a 32 -> 32 conv whose
  * output channels 1..31 have zero weights; pred[i] = (tanh(x[i][0]) + 1) / 2 (VMN_GCA.py:47) and the gradient
  * dz[i][0] = dpred[i]*2*pred[i]*(1-pred[i]), dz[i][1..c-1] = 0.  x / dz split-bf16 [pixels][c]. */

@@ -321,7 +321,7 @@ int conv2d_tc2p_supported(const tcv_conv_desc& d) {
   if (!d.w_tc) return 0;
   if (d.stride != 1 || d.pad_mode != TCV_PAD_ZERO) return 0;
   if (d.cin % 32 != 0 || d.cout % 64 != 0) return 0;
-  if (d.cout % 128 != 0 && !(g_debug_flags.load() & 8192)) return 0;   // 64-channel layers: opt-in (A/B switch)
+  if (d.cout % 128 != 0 && (g_debug_flags.load() & 8192)) return 0;    // A/B switch: 64-channel layers on conv_tc2 instead
   if (d.x_img_stride != (long long)d.ih * d.iw * d.cin) return 0;
   if (!d.y || d.y_f32) return 0;                       // TMA-store epilogue only
   VPParams p;

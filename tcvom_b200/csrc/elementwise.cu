@@ -398,3 +398,4 @@ int tcv_split_to_nchw(const void* x, int n, int c, int h, int w, int c_pad, long
 }
 
 }  // extern "C"
+

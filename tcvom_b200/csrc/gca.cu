@@ -533,6 +533,7 @@ __global__ void __launch_bounds__(256) gca_shift_add_kernel(const float* __restr
   }
   const long long plane = (long long)n * Pk * ld;
   __nv_bfloat16* out = A2 + ((long long)img * Pk + m) * ld;
+#pragma unroll 4
   for (int j = threadIdx.x * 2; j < ld; j += 512) {
     float v0 = 0.f, v1 = 0.f;
 #pragma unroll
@@ -548,64 +549,59 @@ __global__ void __launch_bounds__(256) gca_shift_add_kernel(const float* __restr
   }
 }
 
-// A2[img][m][j] = sum_a softmax(S)[m - a][j - shift_a], split-bf16 planes [2][n][Pk][ld].
-// CTA = (column chunk of CW, row m, image): the <= 4 source rows are exponentiated once into shared memory (chunk + halo of
-// ww+2 columns on the left), then summed at the four shifts.
-constexpr int A2_CW = 2048;
+// A2[img][m][j] = sum_a softmax(S)[m - a][j - shift_a], split-bf16 planes [2][n][Pk][ld], straight from the logits and the
+// row statistics (no normalised copy of S in HBM).  Same streaming structure as gca_shift_add_kernel -- one CTA per
+// (row m, image), threads stride over the columns, the <= 4 source rows are read as long contiguous streams (L2: a row is
+// re-read by its 4 consumers within 2 key-grid rows) -- plus the exponential of every operand.
 __global__ void __launch_bounds__(256) gca_softmax_shift_kernel(const float* __restrict__ S, const float2* __restrict__ stats,
                                                                 const float* __restrict__ mm, int n, int hh, int ww, int ld,
-                                                                int halo, __nv_bfloat16* __restrict__ A2) {
-  extern __shared__ float sm[];     // 4 rows of (halo + A2_CW) floats
-  const int P = hh * ww, ww1 = ww + 1, Pk = (hh + 1) * ww1;
-  const int j0 = blockIdx.x * A2_CW, m = blockIdx.y, img = blockIdx.z;
+                                                                __nv_bfloat16* __restrict__ A2) {
+  const int P = hh * ww, ww1 = ww + 1, Pk = (hh + 1) * ww1, Pv = hh * ww1;
+  const int m = blockIdx.x, img = blockIdx.y;
   const int my = m / ww1, mx = m - my * ww1;
-  const KeyGrid kg{ww1, hh * ww1};
-  const int rw = halo + A2_CW;
+  const float* rows[4];
+  float mxv[4], inv[4], dg[4];
+  int sh[4], qj[4];
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     const int qy = my - (a >> 1), qx = mx - (a & 1);
-    float* dst = sm + a * rw;
-    if (qy < 0 || qy >= hh || qx < 0 || qx >= ww) {
-      for (int i = threadIdx.x * 4; i < rw; i += 1024) *reinterpret_cast<float4*>(dst + i) = make_float4(0, 0, 0, 0);
-      continue;
-    }
-    const int q = qy * ww + qx, qj = qy * ww1 + qx;
-    const float* row = S + ((long long)img * P + q) * ld;
-    const float2 st = stats[(long long)img * P + q];
-    const float diag = -1e4f * mm[(long long)img * P + q];
-    for (int i = threadIdx.x * 4; i < rw; i += 1024) {
-      const int j4 = j0 - halo + i;
-      float e[4] = {0.f, 0.f, 0.f, 0.f};
-      if (j4 >= 0 && j4 < ld) {
-        const float4 v = *reinterpret_cast<const float4*>(row + j4);
-        const float s[4] = {v.x, v.y, v.z, v.w};
-        int col = j4 % ww1;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int j = j4 + k;
-          const float t = s[k] + (j == qj ? diag : 0.f);
-          e[k] = (j < kg.Pv && col != ww) ? expf(t - st.x) * st.y : 0.f;
-          if (++col == ww1) col = 0;
-        }
-      }
-      *reinterpret_cast<float4*>(dst + i) = make_float4(e[0], e[1], e[2], e[3]);
+    const bool ok = qy >= 0 && qy < hh && qx >= 0 && qx < ww;
+    sh[a] = (a >> 1) * ww1 + (a & 1);
+    rows[a] = nullptr;
+    mxv[a] = inv[a] = dg[a] = 0.f;
+    qj[a] = -1;
+    if (ok) {
+      const long long q = (long long)img * P + qy * ww + qx;
+      rows[a] = S + q * ld - sh[a];
+      const float2 st = __ldg(stats + q);
+      mxv[a] = st.x;
+      inv[a] = st.y;
+      dg[a] = -1e4f * __ldg(mm + q);
+      qj[a] = qy * ww1 + qx + sh[a];          // output column whose operand from row a is the self-masked logit
     }
   }
-  __syncthreads();
   const long long plane = (long long)n * Pk * ld;
-  __nv_bfloat16* out = A2 + ((long long)img * Pk + m) * ld + j0;
-  const int s1 = 1, s2 = ww1, s3 = ww1 + 1;
-  const float* r0 = sm + halo;
-  const float* r1 = sm + rw + halo - s1;
-  const float* r2 = sm + 2 * rw + halo - s2;
-  const float* r3 = sm + 3 * rw + halo - s3;
-  for (int i = threadIdx.x * 2; i < A2_CW && j0 + i < ld; i += 512) {
-    const float v0 = (r0[i] + r1[i]) + (r2[i] + r3[i]);
-    const float v1 = (r0[i + 1] + r1[i + 1]) + (r2[i + 1] + r3[i + 1]);
+  __nv_bfloat16* out = A2 + ((long long)img * Pk + m) * ld;
+#pragma unroll 4
+  for (int j = threadIdx.x * 2; j < ld; j += 512) {
+    float v0 = 0.f, v1 = 0.f;
+    // column validity of the operand at output column c shifted by sh: c - sh is a real key
+    const int c0 = j % ww1;                 // (j - sh[a]) % ww1 takes the values c0, c0 - 1 (mod ww1) only
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      if (rows[a] == nullptr) continue;
+      const int s0 = j - sh[a], s1 = s0 + 1;
+      const int col0 = (a & 1) ? (c0 == 0 ? ww : c0 - 1) : c0;
+      const int col1 = col0 == ww ? 0 : col0 + 1;
+      if (s0 >= 0 && s0 < Pv && col0 != ww)
+        v0 += __expf(__ldg(rows[a] + j) + (j == qj[a] ? dg[a] : 0.f) - mxv[a]) * inv[a];
+      if (s1 >= 0 && s1 < Pv && col1 != ww)
+        v1 += __expf(__ldg(rows[a] + j + 1) + (j + 1 == qj[a] ? dg[a] : 0.f) - mxv[a]) * inv[a];
+    }
     uint32_t hi, lo;
     split2_bf16(v0, v1, hi, lo);
-    *reinterpret_cast<uint32_t*>(out + i) = hi;
-    *reinterpret_cast<uint32_t*>(out + plane + i) = lo;
+    *reinterpret_cast<uint32_t*>(out + j) = hi;
+    *reinterpret_cast<uint32_t*>(out + plane + j) = lo;
   }
 }
 
@@ -691,13 +687,9 @@ int tcv_gca_softmax_shift(const float* Sm, const float* stats, const float* mm, 
                           tcv_stream_t stream) {
   TCV_REQUIRE(Sm && stats && mm && A2, "gca_softmax_shift: null pointer");
   const int hh = h / 2, ww = w / 2, Pk = (hh + 1) * (ww + 1);
-  TCV_REQUIRE(n > 0 && hh > 0 && ww > 0 && ld % 4 == 0 && ld >= Pk, "gca_softmax_shift: bad geometry");
-  const int halo = (ww + 2 + 3) / 4 * 4;
-  const size_t smem = (size_t)4 * (halo + A2_CW) * sizeof(float);
-  TCV_REQUIRE(smem <= 200 * 1024, "gca_softmax_shift: halo of %d columns does not fit shared memory", halo);
-  TCV_CUDA(cudaFuncSetAttribute(gca_softmax_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gca_softmax_shift_kernel<<<dim3((ld + A2_CW - 1) / A2_CW, Pk, n), 256, smem, S(stream)>>>(
-      Sm, reinterpret_cast<const float2*>(stats), mm, n, hh, ww, ld, halo, reinterpret_cast<__nv_bfloat16*>(A2));
+  TCV_REQUIRE(n > 0 && hh > 0 && ww > 0 && ld % 64 == 0 && ld >= Pk, "gca_softmax_shift: bad geometry (ld %% 64)");
+  gca_softmax_shift_kernel<<<dim3(Pk, n), 256, 0, S(stream)>>>(Sm, reinterpret_cast<const float2*>(stats), mm, n, hh, ww, ld,
+                                                               reinterpret_cast<__nv_bfloat16*>(A2));
   return launched("gca_softmax_shift_kernel");
 }
 

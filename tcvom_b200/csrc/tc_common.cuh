@@ -133,7 +133,8 @@ static inline EncodeTiledFn get_encode() {
   return fn;
 }
 
-// bf16 tensor map, dims innermost-first; strides[i] = byte stride of dim i+1
+// bf16 tensor map, dims innermost-first; strides[i] = byte stride of dim i+1; bk: 64 -> SWIZZLE_128B, 0 -> no swizzle,
+// anything else -> SWIZZLE_64B
 static inline int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
                     const cuuint32_t* box, int bk, bool fp16 = false, int trav = 1) {
   EncodeTiledFn enc = get_encode();
@@ -141,7 +142,8 @@ static inline int make_map(CUtensorMap* m, const void* base, int rank, const cuu
   // traversal stride on the two spatial dims (W, H) of a 4-D activation map: every `trav`-th pixel
   cuuint32_t estr[5] = {1, (cuuint32_t)trav, (cuuint32_t)trav, 1, 1};
   CUresult r = enc(m, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_64B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(TCV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return TCV_OK;

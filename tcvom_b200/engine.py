@@ -137,6 +137,8 @@ class GcaVmnEngine:
         # 3.8x the FLOPs, kept as the cross-check)
         # windowed forward: shortcut branches 0..2 only for the centre frames that consume them (see per_frame)
         self.centre_shortcuts = os.environ.get("TCV_CENTRE_SHORTCUTS", "1") == "1"
+        # softmax folded into the shift-add kernel (one pass over S, 4 exponentials per output) instead of normalise-in-place
+        # + shift-add: measured slower on B200 (0.77 + 0.25 vs 0.34 + 0.50 ms per launch), kept as the cross-check
         self.gca_softmax_in_consumer = os.environ.get("TCV_GCA_SOFTMAX_IN_CONSUMER", "0") == "1"
         self.gca_shift_sum = os.environ.get("TCV_GCA_SHIFT_SUM", "1") == "1" and self.pv_mode == "bf16x3"
         # opt-in (default off, to be A/B-measured on a GPU): the three stride-2 layers with 8 / 16 input channels
@@ -710,7 +712,15 @@ class GcaVmnEngine:
         t = self._dec_layer(t, "decoder.layer4", DEC_LAYERS[3][2], fea[1])
         t = self.deconv4x4s2(t, "decoder.conv1", bn="decoder.bn1", act=ACT_LEAKY02, res2=fea[0])
         hk = "decoder.conv2" + self.HEAD32
-        if self.use_tc_conv and hk in self.w and os.environ.get("TCV_HEAD32", "1") == "1":
+        hw_ = self.w["decoder.conv2"]
+        if hw_["cin"] == 32 and hw_["cout"] == 1 and hw_["k"] == 3 and os.environ.get("TCV_HEAD_DIRECT", "1") == "1":
+            # one HBM-bound pass: 3x3 conv to the single alpha channel + (tanh+1)/2 (the padded 32-channel tensor-core form
+            # below writes and re-reads a 32-channel full-resolution tensor for one real channel)
+            self._call("tcv_head_conv_tanh01", t.ptr, t.plane, t.n, t.h, t.w, hw_["w"].data_ptr(),
+                       self.bias["decoder.conv2"].data_ptr(), pred_ptr,
+                       meta=dict(kind="tcv_head_conv_tanh01", bytes=t.n * t.h * t.w * (4 * 32 + 4),
+                                 flops=2 * t.n * t.h * t.w * 9 * 32))
+        elif self.use_tc_conv and hk in self.w and os.environ.get("TCV_HEAD32", "1") == "1":
             z = self.conv(t, hk, bias=True)
             self._call("tcv_head_tanh01", z.ptr, z.plane, z.n * z.h * z.w, z.c, pred_ptr,
                        meta=dict(kind="tcv_head_tanh01", bytes=z.n * z.h * z.w * (2 * 32 + 4)))

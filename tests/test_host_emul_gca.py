@@ -182,13 +182,15 @@ def test_shift_sum_aggregation_equals_fold_program(emu, case):
     for ss in (False, True, "consumer"):
         eng = make_gca_engine()
         eng.gca_shift_sum = bool(ss)
-        eng.gca_softmax_in_consumer = ss == "consumer"      # exponentials in the shift kernel instead of a normalise pass
+        eng.gca_softmax_in_consumer = ss == "consumer"      # exponentials in the shift kernel / a normalise pass (default)
         eng.refresh_weights(_net())
         plan, io = record_eval(eng, B, S, H, W, int(g["dilate"]), True)
         io["imgs"].copy_(imgs); io["tris"].copy_(tris)
         plan.replay(0)
         res[ss] = io["alphas"].clone()
         kinds = [m["kind"] for m in plan.meta]
+        eng_default = make_gca_engine()
+        assert eng_default.gca_shift_sum and not eng_default.gca_softmax_in_consumer  # what ships (measured faster)
         assert ("tcv_gca_shift_add" in kinds) == (ss is True) and ("tcv_gca_softmax_shift" in kinds) == (ss == "consumer")
         assert ("tcv_gca_fold" in kinds) == (not ss)
     assert np.abs(res[True].numpy() - g["alphas"]).max() < 1e-3
