@@ -488,8 +488,10 @@ __global__ void __launch_bounds__(256) gca_rowstats_kernel(const float* __restri
   mx = bcast;
   float sum = 0.f;
   for (int j4 = threadIdx.x * 4; j4 < ld; j4 += 1024) {
-    const float4 v = *reinterpret_cast<const float4*>(srow + j4);
-    sum += (expf(v.x - mx) + expf(v.y - mx)) + (expf(v.z - mx) + expf(v.w - mx));
+    float4 v = *reinterpret_cast<const float4*>(srow + j4);
+    v.x = expf(v.x - mx); v.y = expf(v.y - mx); v.z = expf(v.z - mx); v.w = expf(v.w - mx);   // exp(-inf) = 0 at the pads
+    sum += (v.x + v.y) + (v.z + v.w);
+    if (NORMALISE) *reinterpret_cast<float4*>(srow + j4) = v;     // each thread re-reads only what it wrote itself
   }
   sum = warp_sum(sum);
   __syncthreads();
@@ -508,9 +510,8 @@ __global__ void __launch_bounds__(256) gca_rowstats_kernel(const float* __restri
   const float inv = bcast;
   float* out = const_cast<float*>(row);
   for (int j4 = threadIdx.x * 4; j4 < ld; j4 += 1024) {
-    const float4 v = *reinterpret_cast<const float4*>(srow + j4);   // exp(-inf) = 0 at the pad columns
-    *reinterpret_cast<float4*>(out + j4) =
-        make_float4(expf(v.x - mx) * inv, expf(v.y - mx) * inv, expf(v.z - mx) * inv, expf(v.w - mx) * inv);
+    const float4 v = *reinterpret_cast<const float4*>(srow + j4);
+    *reinterpret_cast<float4*>(out + j4) = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
   }
 }
 
@@ -533,19 +534,40 @@ __global__ void __launch_bounds__(256) gca_shift_add_kernel(const float* __restr
   }
   const long long plane = (long long)n * Pk * ld;
   __nv_bfloat16* out = A2 + ((long long)img * Pk + m) * ld;
-#pragma unroll 4
-  for (int j = threadIdx.x * 2; j < ld; j += 512) {
-    float v0 = 0.f, v1 = 0.f;
+  // four consecutive outputs per thread; a source row shifted by sh is read with the widest loads its alignment allows
+  // (sh % 4 == 0: one 16-byte load; == 2: two 8-byte loads; odd: 4 + 8 + 4 bytes)
+#pragma unroll 2
+  for (int j = threadIdx.x * 4; j < ld; j += 1024) {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
       if (rows[a] == nullptr) continue;
-      if (j >= sh[a]) v0 += __ldg(rows[a] + j);
-      if (j + 1 >= sh[a]) v1 += __ldg(rows[a] + j + 1);
+      const float* src = rows[a] + j;               // element for output column j (source column j - sh)
+      if (j >= sh[a]) {
+        const int al = sh[a] & 3;
+        if (al == 0) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+          v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+        } else if (al == 2) {
+          const float2 t0 = __ldg(reinterpret_cast<const float2*>(src)), t1 = __ldg(reinterpret_cast<const float2*>(src + 2));
+          v[0] += t0.x; v[1] += t0.y; v[2] += t1.x; v[3] += t1.y;
+        } else {
+          const float t0 = __ldg(src);
+          const float2 t1 = __ldg(reinterpret_cast<const float2*>(src + 1));
+          const float t3 = __ldg(src + 3);
+          v[0] += t0; v[1] += t1.x; v[2] += t1.y; v[3] += t3;
+        }
+      } else {                                      // the first columns of the row: part of the window is left of the row
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (j + e >= sh[a]) v[e] += __ldg(src + e);
+      }
     }
-    uint32_t hi, lo;
-    split2_bf16(v0, v1, hi, lo);
-    *reinterpret_cast<uint32_t*>(out + j) = hi;
-    *reinterpret_cast<uint32_t*>(out + plane + j) = lo;
+    uint32_t h0, l0, h1, l1;
+    split2_bf16(v[0], v[1], h0, l0);
+    split2_bf16(v[2], v[3], h1, l1);
+    *reinterpret_cast<uint2*>(out + j) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(out + plane + j) = make_uint2(l0, l1);
   }
 }
 
@@ -678,7 +700,7 @@ int tcv_gca_rowstats(float* Sm, const float* mm, int n, int h, int w, int ld, fl
 int tcv_gca_shift_add(const float* A, int n, int h, int w, int ld, void* A2, tcv_stream_t stream) {
   TCV_REQUIRE(A && A2, "gca_shift_add: null pointer");
   const int hh = h / 2, ww = w / 2, Pk = (hh + 1) * (ww + 1);
-  TCV_REQUIRE(n > 0 && hh > 0 && ww > 0 && ld % 2 == 0 && ld >= Pk, "gca_shift_add: bad geometry");
+  TCV_REQUIRE(n > 0 && hh > 0 && ww > 0 && ld % 4 == 0 && ld >= Pk, "gca_shift_add: bad geometry (ld %% 4)");
   gca_shift_add_kernel<<<dim3(Pk, n), 256, 0, S(stream)>>>(A, n, hh, ww, ld, reinterpret_cast<__nv_bfloat16*>(A2));
   return launched("gca_shift_add_kernel");
 }

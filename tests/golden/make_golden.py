@@ -181,13 +181,30 @@ def grad_sample(g):
     return f if f.numel() <= 8192 else f[::GRAD_STRIDE]
 
 
-def train_step_golden(B=2, S=5, H=64, W=64):
+DAMP = 0.04      # residual-branch BatchNorm gains of the well-conditioned fixture = DAMP x the standard fixture's
+
+
+def damp_state(sd, damp=DAMP):
+    """The standard fixture with every residual-branch BatchNorm gain (``*.bn2.weight``, ``gca.W.1.weight``) scaled by
+    `damp`: the network stays the same program, but a perturbation is no longer amplified ~1000x through the 29 residual
+    blocks, so a whole-step gradient comparison resolves 1e-3 instead of sitting at the 1e-2 noise floor of the standard
+    fixture (measured on the CPU oracle, fp32 against fp64: median gradient rel-L2 2.5e-5 instead of 2.7e-3)."""
+    out = {k: v.clone() for k, v in sd.items()}
+    for k in out:
+        if k.endswith(".bn2.weight") or k.endswith("W.1.weight"):
+            out[k] = out[k] * damp
+    return out
+
+
+def train_step_golden(B=2, S=5, H=64, W=64, damp=None):
     """One reference training step (train_ddp.py:52-65 without the optimizer): FullModel_VMD in .train() mode,
     loss = L_alpha + L_comp + L_grad + 0.5 L_dt + 0.25 L_att, backward.  Stores the losses, every gradient's
     L2 norm / sum and a strided sample, and the state the forward mutates (spectral-norm u/v, BatchNorm
     running statistics).  dilate_kernel is fixed so that no host RNG is involved."""
     from helpers_golden import load_full
     full = load_full()
+    if damp is not None:
+        full = damp_state(full, damp)
     tm = FullModel_VMD(model="vmn_gca", agg_window=7, dilate_kernel=3)
     tm.NET.load_state_dict(full, strict=True)
     tm.train()
@@ -213,12 +230,14 @@ def train_step_golden(B=2, S=5, H=64, W=64):
     for k, v in tm.NET.state_dict().items():
         if k.endswith(("weight_u", "weight_v", "running_mean", "running_var", "num_batches_tracked")):
             res["st:" + k] = v.numpy().copy()
-    np.savez_compressed(os.path.join(HERE, "train_step_s5.npz"), **res)
-    print("train step losses", res["losses"], "params", len(names))
+    np.savez_compressed(os.path.join(HERE, "train_step_s5.npz" if damp is None else "train_step_s5_damped.npz"), **res)
+    print("train step losses", res["losses"], "params", len(names), "damp", damp)
 
 
 if __name__ == "__main__":
-    if "--train-step" in sys.argv:
+    if "--train-step-damped" in sys.argv:
+        train_step_golden(damp=DAMP)
+    elif "--train-step" in sys.argv:
         train_step_golden()
     else:
         main(only_train="--only-train" in sys.argv)

@@ -313,5 +313,5 @@ def test_eval_forward_1080p_matches_oracle():
     ea, p9999 = float(d.max()), float(d.flatten()[::7].quantile(0.9999))
     eF, eB = float((Fs.cpu() - rF).abs().max()), float((Bs.cpu() - rB).abs().max())
     print(f"1088x1920 alpha max abs err {ea:.2e} (p99.99 {p9999:.2e}), F {eF:.2e}, B {eB:.2e}")
-    assert ea < 1.2e-3 and p9999 < 5e-4
+    assert ea < 1e-3 and p9999 < 5e-4        # north_star: 1e-3 max abs on the alpha matte
     assert eF < 3e-4 and eB < 3e-4

@@ -58,9 +58,15 @@ def from_act(a):
     return y
 
 
-def make_net():
+DAMP = 0.04      # tests/golden/make_golden.py: residual-branch BatchNorm gains of the well-conditioned fixture
+
+
+def make_net(damp=None):
     model = tcvom_b200.FullModel_VMD(model="vmn_gca", agg_window=7, dilate_kernel=3)
-    model.NET.load_state_dict(fixture_sd(), strict=True)
+    sd = fixture_sd()
+    if damp is not None:
+        sd = {k: (v * damp if (k.endswith(".bn2.weight") or k.endswith("W.1.weight")) else v) for k, v in sd.items()}
+    model.NET.load_state_dict(sd, strict=True)
     return model.to(DEV).train()
 
 
@@ -265,7 +271,7 @@ LOSS_WEIGHTS = (1.0, 1.0, 1.0, 0.5, 0.25)
 GRAD_STRIDE = 257
 
 
-def check_full_step(verbose=True, bound=1e-1):
+def check_full_step(verbose=True, bound=1e-1, damped=False):
     """One native training step against one training step of the unmodified reference
     (tests/golden/train_step_s5.npz): losses, alphas, every gradient, spectral-norm u/v, BN running statistics.
 
@@ -277,8 +283,8 @@ def check_full_step(verbose=True, bound=1e-1):
     comparison therefore sits AT its noise floor (1.4e-2 .. 2.1e-2 median measured); worst-case bound 1e-1, median
     bounded by the caller.  The per-operator checks above (3e-6 .. 2e-5) are the precise evidence."""
     from helpers import golden, key_table
-    g = golden("train_step_s5.npz")
-    model = make_net()
+    g = golden("train_step_s5_damped.npz" if damped else "train_step_s5.npz")
+    model = make_net(DAMP if damped else None)
     a, fg, bg = (torch.from_numpy(g[k]).float().to(DEV) for k in ("a", "fg", "bg"))
     n0 = _cabi.launch_count()
     out = model(a, fg, bg)
@@ -303,6 +309,12 @@ def check_full_step(verbose=True, bound=1e-1):
     rows.sort(reverse=True)
     errs["grad_worst"] = rows[0][0]
     errs["grad_median"] = rows[len(rows) // 2][0]
+    errs["grad_p90"] = rows[len(rows) // 10][0]
+    # all gradients as ONE vector (every stored sample, each tensor weighted by its own size): insensitive to the few
+    # tiny-norm tensors whose relative error is dominated by absolute noise
+    num = sum((r[0] * r[2]) ** 2 for r in rows) ** 0.5
+    den = sum(r[2] ** 2 for r in rows) ** 0.5
+    errs["grad_global"] = num / max(den, 1e-30)
     st_err = 0.0
     sd = model.NET.state_dict()
     worst_st = None
