@@ -685,6 +685,12 @@ def main():
     ap.add_argument("--no-fba", action="store_true", help="skip the secondary FBA+TAM forward measurement (configs[4])")
     ap.add_argument("--dump-calls", default=None, help="write the per-launch timing table (JSON lines) here")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: everything else -- Python prints of the reference modules AND C-level writes to
+    # fd 1 (NCCL prints its version banner there) -- is redirected to stderr
+    global JSON_OUT
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     sys.stdout = sys.stderr
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
