@@ -543,6 +543,16 @@ int tcv_postprocess_eval_fba(const float* pred, const void* imgs, const void* tr
                              int batch, int frames, int h, int w, float* alphas, float* Fs, float* Bs,
                              tcv_stream_t stream);
 
+/* ---- SyncBatchNorm statistic exchange over NVLink peer memory (train_ddp.py:273 nn.SyncBatchNorm; csrc/peer_reduce.cu).
+ * In-place sum of `count` doubles over `world` ranks of one node in ONE kernel on the caller's stream.  `peers_dev`: device
+ * array of `world` pointers, entry r = rank r's symmetric buffer (tcv_peer_buffer_bytes(slot_doubles) bytes, zero-filled
+ * before the first call, mapped into this process: torch.distributed._symmetric_memory or CUDA IPC provide that).
+ * `epoch`: 1, 2, 3, ... -- the same on every rank for the same call.  The sum runs in rank order: all ranks get identical
+ * bits.  A peer that never arrives makes the kernel trap after ~2 s instead of hanging. */
+int tcv_peer_allreduce_f64(double* data, int count, void* const* peers_dev, int rank, int world,
+                           unsigned long long epoch, long long slot_doubles, tcv_stream_t stream);
+int tcv_peer_buffer_bytes(long long slot_doubles, long long* bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,8 @@ class TrainEngine(GcaVmnEngine):
         self.dbias: Dict[str, torch.Tensor] = {}
         self.dbn: Dict[str, tuple] = {}
         self.sync_bn = False
+        self._peer = None
+        self._peer_tried = False
         self.process_group = None
         self.world = 1
         # weight gradients of the stride-1 convs / deconv phases on the tensor cores (split-K tcgen05 GEMM over
@@ -381,6 +383,18 @@ class TrainEngine(GcaVmnEngine):
         self.tape.append(backward)
         return z
 
+    def _allreduce_sums(self, t: torch.Tensor) -> None:
+        """Cross-rank sum of one BatchNorm statistic block (nn.SyncBatchNorm, train_ddp.py:273): the peer-memory kernel on
+        the compute stream when the node's GPUs can map each other (tcvom_b200/peer.py), else NCCL."""
+        if self._peer is None and not self._peer_tried:
+            self._peer_tried = True
+            from .peer import make_peer_reducer
+            self._peer = make_peer_reducer(self.process_group, self.device)
+        if self._peer is not None:
+            self._peer.allreduce_(t, self._stream_ptr())
+        else:
+            torch.distributed.all_reduce(t, group=self.process_group)
+
     # ------------------------------------------------------------------ train-mode BatchNorm (+ 1/sigma, act, residuals)
     def bn_op(self, z: TAct, bnkey: str, *, mode=1, act=ACT_NONE, snkey: Optional[str] = None,
               res1: Optional[TAct] = None, res1_shift=0, res2: Optional[TAct] = None, unbias_mul=1) -> TAct:
@@ -412,7 +426,7 @@ class TrainEngine(GcaVmnEngine):
         self._call("tcv_bn_stats", C.byref(d), sums.data_ptr(), meta=tag)
         count = float((za.n // groups) * za.h * za.w)
         if self.sync_bn:
-            torch.distributed.all_reduce(sums, group=self.process_group)
+            self._allreduce_sums(sums)
             count *= self.world
         self._call("tcv_bn_finalize", sums.data_ptr(), count, count * unbias_mul, groups, c, BN_EPS, BN_MOMENTUM,
                    mean.data_ptr(), invstd.data_ptr(), self.named[bnkey + ".running_mean"].data_ptr(),
@@ -444,7 +458,7 @@ class TrainEngine(GcaVmnEngine):
                 self.dbn[bnkey] = (dg, db)
             self._call("tcv_bn_param_grads", bsums.data_ptr(), groups, c, dg.data_ptr(), db.data_ptr())
             if self.sync_bn:
-                torch.distributed.all_reduce(bsums, group=self.process_group)
+                self._allreduce_sums(bsums)
             dz = self._act(za.n, za.h, za.w, c)
             self._call("tcv_bn_bwd_apply", C.byref(d), e.ptr, e.plane, bsums.data_ptr(), count, dz.ptr, dz.plane,
                        sn["zdot"].data_ptr() if sn is not None else None, meta=tag)

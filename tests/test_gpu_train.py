@@ -113,6 +113,23 @@ def test_ddp_syncbn_two_ranks():
     assert res["ok"], res
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_syncbn_statistics_over_peer_memory_match_nccl():
+    """tcv_peer_allreduce_f64 (one kernel over NVLink peer memory, rank-ordered sum) == the NCCL all-reduce it replaces for
+    the SyncBatchNorm statistics, bit-identical on all ranks: tools/peer_check.py."""
+    import json
+    import subprocess
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29519", os.path.join(ROOT, "tools", "peer_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert line, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.loads(line[-1])
+    print(res)
+    assert res["available"], "peer memory unavailable on this box: the step fell back to NCCL (still correct, not faster)"
+    assert res["ok"], res
+
+
 def test_vmn_seam_train_mode_matches_wrapper(tc):
     """The plugin seam in train mode (reference FullModel_VMD on top of tcvom_b200.VMN): torch losses on the native
     VMN outputs give the same losses and gradients as the fully native wrapper."""
