@@ -141,10 +141,14 @@ class GcaVmnEngine:
         # + shift-add: measured slower on B200 (0.77 + 0.25 vs 0.34 + 0.50 ms per launch), kept as the cross-check
         self.gca_softmax_in_consumer = os.environ.get("TCV_GCA_SOFTMAX_IN_CONSUMER", "0") == "1"
         self.gca_shift_sum = os.environ.get("TCV_GCA_SHIFT_SUM", "1") == "1" and self.pv_mode == "bf16x3"
-        # opt-in (default off, to be A/B-measured on a GPU): the three stride-2 layers with 8 / 16 input channels
-        # (encoder.conv1, guidance_head.1 / .5), which run on the CUDA-core kernel, as stride-1 2x2-tap convolutions over
-        # the 2x2 space-to-depth image on the tcgen05 kernels (same rewrite as the FBA stem, tcv_s2d_pack)
-        self.s2d_stride2 = os.environ.get("TCV_S2D_STRIDE2", "0") == "1"
+        # the stride-2 layers with 8 / 16 input channels (encoder.conv1, guidance_head.1 / .5) either on the CUDA-core kernel
+        # or as stride-1 2x2-tap convolutions over the 2x2 space-to-depth image on the tcgen05 kernels (same rewrite as the
+        # FBA stem, tcv_s2d_pack): TCV_S2D_STRIDE2 = "conv1" (default), "1" (all three), "0" (none)
+        # Measured on B200 (round 2, 1088x1920 x 3): encoder.conv1 309 us on the CUDA cores -> 71 (space-to-depth copy) + 107 us;
+        # guidance_head.1 / .5 170 / 163 us -> 240 / 256 us (reflect border + copy + conv).  Default: conv1 only.
+        mode = os.environ.get("TCV_S2D_STRIDE2", "conv1")
+        self.s2d_stride2 = mode in ("1", "conv1")
+        self.s2d_guidance = mode == "1"
 
     # ------------------------------------------------------------------ weights
     def _named(self) -> Dict[str, torch.Tensor]:
@@ -660,7 +664,7 @@ class GcaVmnEngine:
         c3 = self.conv(x1, e + ".conv3", stride=2, bn=e + ".bn3", act=ACT_RELU)
         g = x8
         for ci, bi in ((1, 3), (5, 7), (9, 11)):                                # guidance head (res_gca_enc.py:20-33)
-            if s2d and ci in (1, 5):
+            if s2d and self.s2d_guidance and ci in (1, 5):
                 # reflect border materialised once, then the space-to-depth form (output channels of .1 padded 16 -> 32
                 # with zero weights / affine, which .5 reads through zero weight rows)
                 g = self.conv_s2d(self.pad_reflect1(g), f"{e}.guidance_head.{ci}", act=ACT_RELU,

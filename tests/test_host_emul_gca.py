@@ -159,7 +159,7 @@ def test_space_to_depth_stride2_program(emu, case):
     res = {}
     for s2d in (False, True):
         eng = make_gca_engine()
-        eng.s2d_stride2 = s2d
+        eng.s2d_stride2 = eng.s2d_guidance = s2d            # all three layers (the default program converts conv1 only)
         eng.refresh_weights(_net())
         plan, io = record_eval(eng, B, S, H, W, int(g["dilate"]), True)
         io["imgs"].copy_(imgs); io["tris"].copy_(tris)
