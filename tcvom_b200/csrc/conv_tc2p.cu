@@ -30,21 +30,33 @@ struct VPParams {
   int ngroups, group_dx[VP_MAXG], ndy[VP_MAXG], dy[VP_MAXG][VP_MAXDY], wtap[VP_MAXG][VP_MAXDY];
   int dy_min, box_rows;
   int tma_store;
+  int b_resident;    // all weight tiles of a work item fit the B ring: staged by the first work item only
   uint32_t idesc;
+  uint32_t idesc2;   // STACK: the N = 2*BN descriptor of the stacked MMA (idesc stays N = BN)
   EpiParams epi;
 };
 
-template <int BN>
+// STACK (BN = 64 only): the hi.hi and hi.lo products of a K step come from ONE MMA of N = 2*BN over the stacked operand
+// [B_hi ; B_lo] (columns BN..2BN-1 of the accumulator are added in the epilogue), then A_lo.B_hi with N = BN: two reads of
+// the 4 KB activation tile per K step instead of three -- a 64-channel layer is bound by exactly those reads (160 B/clk per
+// SM with three MMAs of N = 64; 117 B/clk stacked).  In cta_group::2 the N rows of an operand are split between the CTAs, so
+// the leader stages B_hi (all BN rows) and the peer B_lo at slot offset 0; the N = BN operand of the second MMA sits at
+// slot offset 2*BN*64 B: rows 0..BN/2-1 of B_hi in the leader, rows BN/2..BN-1 in the peer.
+template <int BN, bool STACK = false>
 struct VPCfg {
   static constexpr int B_ROWS = BN / 2;                         // rows of a weight tile this CTA stages
-  static constexpr int B_SLOT_BYTES = 2 * B_ROWS * VP_BK * 2;   // hi + lo
+  static constexpr int B_SLOT_BYTES = STACK ? 3 * B_ROWS * VP_BK * 2 : 2 * B_ROWS * VP_BK * 2;   // hi + lo (STACK: 2 + 1 blocks)
+  static constexpr int ACC_COLS = STACK ? 2 * BN : BN;
   static constexpr int A_SLOTS = 3;
   static constexpr int A_BYTES = A_SLOTS * VP_A_SLOT_BYTES;     // 72 KB
   static constexpr int STAGE_BYTES = 2 * 2 * 128 * 64;          // TMA-store staging: 2 column groups x hi/lo x 128 rows x 64 B
-  static constexpr int B_SLOTS = (200 * 1024 - A_BYTES - STAGE_BYTES) / B_SLOT_BYTES > 8
-                                     ? 8 : (200 * 1024 - A_BYTES - STAGE_BYTES) / B_SLOT_BYTES;
+  // BN = 64: enough slots to keep all 9 taps x 2 K blocks of a 64 -> 64 layer resident (loaded once per CTA, never recycled:
+  // the weight tiles were 47 % of the TMA traffic of those HBM-bound layers)
+  static constexpr int B_CAP = BN <= 64 ? 18 : 8;
+  static constexpr int B_SLOTS = (200 * 1024 - A_BYTES - STAGE_BYTES) / B_SLOT_BYTES > B_CAP
+                                     ? B_CAP : (200 * 1024 - A_BYTES - STAGE_BYTES) / B_SLOT_BYTES;
   static constexpr int SMEM = A_BYTES + B_SLOTS * B_SLOT_BYTES + STAGE_BYTES + 1024 + 512;
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // 2 buffers x one accumulator
+  static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;   // 2 buffers x one accumulator
 };
 
 __device__ __forceinline__ uint32_t vp_cluster_rank() {
@@ -91,7 +103,7 @@ __device__ __forceinline__ void vp_commit(uint32_t bar) {
                : "memory");
 }
 
-template <int BN>
+template <int BN, bool STACK>
 __global__ void __launch_bounds__(320, 1) conv_tc2p_kernel(const __grid_constant__ CUtensorMap mapA_hi,
                                                            const __grid_constant__ CUtensorMap mapA_lo,
                                                            const __grid_constant__ CUtensorMap mapB_hi,
@@ -99,8 +111,9 @@ __global__ void __launch_bounds__(320, 1) conv_tc2p_kernel(const __grid_constant
                                                            const __grid_constant__ CUtensorMap mapY_hi,
                                                            const __grid_constant__ CUtensorMap mapY_lo,
                                                            const __grid_constant__ VPParams p) {
-  using Cfg = VPCfg<BN>;
+  using Cfg = VPCfg<BN, STACK>;
   constexpr int SA = Cfg::A_SLOTS, SB = Cfg::B_SLOTS;
+  constexpr uint32_t BLK = Cfg::B_ROWS * VP_BK * 2;     // one plane of B_ROWS weight rows
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_base = smem_base + Cfg::A_BYTES;
@@ -164,6 +177,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc2p_kernel(const __grid_constant
       decode(work, img, h0, w0, n0);
       const int hr = h0 + (int)rank * p.TH + p.dy_min;      // first box row of this CTA's pixel tile
       const int nb = n0 + (int)rank * Cfg::B_ROWS;          // this CTA's half of the weight tile
+      const bool load_b = !p.b_resident || work == pair;    // resident weights: first work item only
       for (int kc = 0; kc < p.kc_iters; ++kc) {
         for (int g = 0; g < p.ngroups; ++g, ++ia) {
           const int sa = ia % SA;
@@ -176,15 +190,25 @@ __global__ void __launch_bounds__(320, 1) conv_tc2p_kernel(const __grid_constant
             vp_tma_4d(adst + a_plane_bytes, &mapA_lo, fb, kc * VP_BK, w0 + p.group_dx[g], hr, img);
           }
           __syncwarp();
+          if (!load_b) continue;
           for (int j = 0; j < p.ndy[g]; ++j, ++ib) {
-            const int sb = ib % SB;
+            const int sb = ib % SB;          // resident mode: ib < SB, slot == stage index within the work item
             mbar_wait(emptyB(sb), ((uint32_t)(ib / SB) & 1u) ^ 1u);
             const uint32_t bdst = b_base + sb * Cfg::B_SLOT_BYTES;
             if (elect_one()) {
               if (leader) mbar_expect_tx(fullB(sb), 2u * Cfg::B_SLOT_BYTES);
               const uint32_t fb = vp_mapa(fullB(sb), 0);
-              vp_tma_3d(bdst, &mapB_hi, fb, kc * VP_BK, nb, p.wtap[g][j]);
-              vp_tma_3d(bdst + Cfg::B_SLOT_BYTES / 2, &mapB_lo, fb, kc * VP_BK, nb, p.wtap[g][j]);
+              if constexpr (STACK) {
+                // leader: B_hi rows 0..BN-1 (stacked operand, its N rows 0..BN-1) + B_hi rows 0..BN/2-1 again;
+                // peer:   B_lo rows 0..BN-1 (N rows BN..2BN-1)                  + B_hi rows BN/2..BN-1
+                const CUtensorMap* m0 = leader ? &mapB_hi : &mapB_lo;
+                vp_tma_3d(bdst, m0, fb, kc * VP_BK, n0, p.wtap[g][j]);
+                vp_tma_3d(bdst + BLK, m0, fb, kc * VP_BK, n0 + Cfg::B_ROWS, p.wtap[g][j]);
+                vp_tma_3d(bdst + 2 * BLK, &mapB_hi, fb, kc * VP_BK, nb, p.wtap[g][j]);
+              } else {
+                vp_tma_3d(bdst, &mapB_hi, fb, kc * VP_BK, nb, p.wtap[g][j]);
+                vp_tma_3d(bdst + Cfg::B_SLOT_BYTES / 2, &mapB_lo, fb, kc * VP_BK, nb, p.wtap[g][j]);
+              }
             }
             __syncwarp();
           }
@@ -199,18 +223,21 @@ __global__ void __launch_bounds__(320, 1) conv_tc2p_kernel(const __grid_constant
         const int buf = iw & 1;
         mbar_wait(accEmpty(buf), ((uint32_t)(iw >> 1) & 1u) ^ 1u);   // both CTAs' epilogues have drained this buffer
         tc_fence_after();
-        const uint32_t d = tmem_base + (uint32_t)(buf * BN);
+        const uint32_t d = tmem_base + (uint32_t)(buf * Cfg::ACC_COLS);
         bool first = true;
+        int il = 0;   // weight stage index within this work item
         for (int kc = 0; kc < p.kc_iters; ++kc) {
           for (int g = 0; g < p.ngroups; ++g, ++ia) {
             const int sa = ia % SA;
             mbar_wait(fullA(sa), (uint32_t)(ia / SA) & 1u);
             tc_fence_after();
             const uint32_t a_hi = smem_base + sa * VP_A_SLOT_BYTES, a_lo = a_hi + a_plane_bytes;
-            for (int j = 0; j < p.ndy[g]; ++j, ++ib) {
-              const int sb = ib % SB;
-              mbar_wait(fullB(sb), (uint32_t)(ib / SB) & 1u);
-              tc_fence_after();
+            for (int j = 0; j < p.ndy[g]; ++j, ++ib, ++il) {
+              const int sb = p.b_resident ? il : ib % SB;
+              if (!p.b_resident || iw == 0) {   // resident weights: only the first work item has to wait for them
+                mbar_wait(fullB(sb), p.b_resident ? 0u : ((uint32_t)(ib / SB) & 1u));
+                tc_fence_after();
+              }
               const uint32_t b_hi = b_base + sb * Cfg::B_SLOT_BYTES, b_lo = b_hi + Cfg::B_SLOT_BYTES / 2;
               if (elect_one()) {
                 // rows of the accumulator for vertical tap dy start (dy - dy_min) image rows into the box (same offset in
@@ -219,12 +246,18 @@ __global__ void __launch_bounds__(320, 1) conv_tc2p_kernel(const __grid_constant
 #pragma unroll
                 for (int ks = 0; ks < VP_BK / 16; ++ks) {
                   const uint64_t ah = smem_desc<VP_BK>(a_hi + roff + ks * 32), al = smem_desc<VP_BK>(a_lo + roff + ks * 32);
-                  const uint64_t bh = smem_desc<VP_BK>(b_hi + ks * 32), bl = smem_desc<VP_BK>(b_lo + ks * 32);
-                  vp_mma(d, ah, bh, p.idesc, (first && ks == 0) ? 0u : 1u);
-                  vp_mma(d, ah, bl, p.idesc, 1u);
-                  vp_mma(d, al, bh, p.idesc, 1u);
+                  if constexpr (STACK) {
+                    const uint64_t bs = smem_desc<VP_BK>(b_hi + ks * 32), bh2 = smem_desc<VP_BK>(b_hi + 2 * BLK + ks * 32);
+                    vp_mma(d, ah, bs, p.idesc2, (first && ks == 0) ? 0u : 1u);     // cols [0,BN): hi.hi ; [BN,2BN): hi.lo
+                    vp_mma(d, al, bh2, p.idesc, 1u);                               // cols [0,BN) += lo.hi
+                  } else {
+                    const uint64_t bh = smem_desc<VP_BK>(b_hi + ks * 32), bl = smem_desc<VP_BK>(b_lo + ks * 32);
+                    vp_mma(d, ah, bh, p.idesc, (first && ks == 0) ? 0u : 1u);
+                    vp_mma(d, ah, bl, p.idesc, 1u);
+                    vp_mma(d, al, bh, p.idesc, 1u);
+                  }
                 }
-                vp_commit(emptyB(sb));
+                if (!p.b_resident) vp_commit(emptyB(sb));
                 if (j == p.ndy[g] - 1) {
                   vp_commit(emptyA(sa));
                   if (kc == p.kc_iters - 1 && g == p.ngroups - 1) vp_commit(accFull(buf));
@@ -260,13 +293,14 @@ __global__ void __launch_bounds__(320, 1) conv_tc2p_kernel(const __grid_constant
       int img, h0, w0, n0;
       decode(work, img, h0, w0, n0);
       const int buf = iw & 1;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + grp * HN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * Cfg::ACC_COLS + grp * HN);
       const int ty = r / p.TW, tx = r - ty * p.TW;
       const int gy = h0 + (int)rank * p.TH + ty, gx = w0 + tx;
       stc.cx = w0;
       stc.cy = h0 + (int)rank * p.TH;
-      conv_epilogue<HN>(p.epi, taddr, gy < p.gh && gx < p.gw, img, gy, gx, n0 + grp * HN, accFull(buf),
-                        (uint32_t)(iw >> 1) & 1u, ae_leader + 8u * buf, lane, stc, false, /*remote_empty=*/true);
+      conv_epilogue<HN, BN>(p.epi, taddr, gy < p.gh && gx < p.gw, img, gy, gx, n0 + grp * HN, accFull(buf),
+                            (uint32_t)(iw >> 1) & 1u, ae_leader + 8u * buf, lane, stc, /*split_halves=*/STACK,
+                            /*remote_empty=*/true);
     }
     if (stc.issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -328,9 +362,9 @@ int conv2d_tc2p_supported(const tcv_conv_desc& d) {
   return vp_build_groups(d, p) ? 1 : 0;
 }
 
-template <int BN>
+template <int BN, bool STACK = false>
 static int conv_tc2p_bn(const tcv_conv_desc& d, cudaStream_t st) {
-  using Cfg = VPCfg<BN>;
+  using Cfg = VPCfg<BN, STACK>;
   VPParams p;
   memset(&p, 0, sizeof(p));
   if (!vp_build_groups(d, p)) return fail(TCV_ERR_UNSUPPORTED, "conv_tc2p: tap pattern not supported");
@@ -343,7 +377,9 @@ static int conv_tc2p_bn(const tcv_conv_desc& d, cudaStream_t st) {
   p.n_tiles_n = d.cout / BN;
   p.total_work = p.tiles_x * p.tiles_y * p.n_tiles_n * d.n;
   p.kc_iters = d.cin / VP_BK;
+  p.b_resident = (p.n_tiles_n == 1 && d.ntaps * p.kc_iters <= Cfg::B_SLOTS && !(g_debug_flags.load() & 32768)) ? 1 : 0;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  p.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
   fill_epi(p.epi, d, 0);
   p.tma_store = 1;
 
@@ -379,7 +415,7 @@ static int conv_tc2p_bn(const tcv_conv_desc& d, cudaStream_t st) {
     rc = make_map(&mB_lo, b + (long long)d.w_tc_taps * d.cout * d.cin, 3, dims, str, box, VP_BK);
     if (rc) return rc;
   }
-  auto kern = conv_tc2p_kernel<BN>;
+  auto kern = conv_tc2p_kernel<BN, STACK>;
   TCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
   int dev = 0, sms = 0;
   TCV_CUDA(cudaGetDevice(&dev));
@@ -406,7 +442,8 @@ static int conv_tc2p_bn(const tcv_conv_desc& d, cudaStream_t st) {
 int conv2d_tc2p(const tcv_conv_desc& d, cudaStream_t st) {
   if (d.cout % 256 == 0) return conv_tc2p_bn<256>(d, st);
   if (d.cout % 128 == 0) return conv_tc2p_bn<128>(d, st);
-  return conv_tc2p_bn<64>(d, st);
+  if (g_debug_flags.load() & 16384) return conv_tc2p_bn<64, false>(d, st);   // A/B switch: three N = 64 MMAs per K step
+  return conv_tc2p_bn<64, true>(d, st);
 }
 
 }  // namespace tcv

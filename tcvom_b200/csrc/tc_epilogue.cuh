@@ -45,8 +45,8 @@ struct StoreCtx {
 // gy/gx: position of this thread's pixel in the compute grid; in_grid: inside it.  The warp waits on
 // `acc_full` (parity given), drains its 32 TMEM lanes starting at `taddr`, and arrives on `acc_empty` as soon
 // as its last tcgen05.ld has completed.
-// split_halves: the accumulator is 2*BN columns wide and the two halves are summed first.
-template <int BN>
+// split_halves: the accumulator holds a second partial product SPLIT_OFF columns further right; the two are summed first.
+template <int BN, int SPLIT_OFF = BN>
 __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr, bool in_grid, int img, int gy, int gx,
                                               int n0, uint32_t acc_full, uint32_t full_parity, uint32_t acc_empty,
                                               int lane, const StoreCtx& st = StoreCtx(), bool split_halves = false,
@@ -99,7 +99,7 @@ __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr
     tc_ld32(taddr + c0, v);
     if (split_halves) {   // BN == 32: columns [32,64) hold the A_hi.B_lo partial product
       uint32_t v2[32];
-      tc_ld32(taddr + BN + c0, v2);
+      tc_ld32(taddr + SPLIT_OFF + c0, v2);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
     }

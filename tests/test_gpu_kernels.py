@@ -49,6 +49,9 @@ def test_conv_tc_matches_cuda_core_conv(cin, cout, h, w, n, kind):
     (256, 128, 10, 12, 3, "3x3"),       # image smaller than a pair tile (the lower CTA's tile is mostly outside)
     (128, 256, 18, 22, 2, "1x1"),       # no halo
     (256, 256, 9, 14, 2, "deconv"),     # transposed-conv phase: strided TMA-store view
+    (64, 64, 40, 56, 2, "3x3"),         # N = 64: stacked [B_hi ; B_lo] operand, two MMAs per K step
+    (128, 64, 272, 480, 1, "3x3"),      # the same at a full-size layer shape
+    (64, 64, 9, 14, 2, "deconv"),
 ])
 def test_conv_cta_pair_kernel(cin, cout, h, w, n, kind):
     """Wide layers on CTA pairs (conv_tc2p.cu, tcgen05.mma.cta_group::2) against fp64 torch and the CUDA-core kernel."""

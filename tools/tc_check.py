@@ -187,6 +187,9 @@ CASES = {
     "pair_3x3_512_512": lambda: case_conv(512, 512, 34, 60, 3, "3x3", False, 4),
     "pair_3x3_256_128_ragged": lambda: case_conv(256, 128, 10, 12, 3, "3x3", False, 4),
     "pair_1x1_128_256": lambda: case_conv(128, 256, 18, 22, 2, "1x1", False, 4),
+    "pair_3x3_64_64_stacked": lambda: case_conv(64, 64, 40, 56, 2, "3x3", False, 4),
+    "pair_3x3_128_64_stacked": lambda: case_conv(128, 64, 272, 480, 1, "3x3", False, 4),
+    "pair_deconv_64_64_stacked": lambda: case_conv(64, 64, 9, 14, 2, "deconv", False, 4),
     "pair_deconv_256_256": lambda: case_conv(256, 256, 9, 14, 2, "deconv", False, 4),
     "conv3x3s2_64_128": lambda: case_conv(64, 128, 40, 56, 2, "3x3s2"),
     "conv3x3s2_32_64": lambda: case_conv(32, 64, 36, 52, 1, "3x3s2"),
