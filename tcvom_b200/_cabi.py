@@ -11,7 +11,8 @@ import ctypes as C
 import os
 import threading
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtcvom_b200.so")
+# TCV_LIB: kernel A/B experiments only (a second build of the same sources with other tile constants)
+LIB_PATH = os.environ.get("TCV_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtcvom_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_TANH01, ACT_LEAKY001 = 0, 1, 2, 3, 4
 PAD_ZERO, PAD_REFLECT = 0, 1

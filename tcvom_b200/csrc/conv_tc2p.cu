@@ -47,14 +47,24 @@ struct VPCfg {
   static constexpr int B_ROWS = BN / 2;                         // rows of a weight tile this CTA stages
   static constexpr int B_SLOT_BYTES = STACK ? 3 * B_ROWS * VP_BK * 2 : 2 * B_ROWS * VP_BK * 2;   // hi + lo (STACK: 2 + 1 blocks)
   static constexpr int ACC_COLS = STACK ? 2 * BN : BN;
-  static constexpr int A_SLOTS = 3;
+  // activation ring depth: one box feeds only ndy x 2 (x 3) MMAs, i.e. 0.3 us of tensor work for a 64-channel layer against
+  // ~1 us of TMA latency -- ncu shows those layers neither DRAM- (9 %), L2- (20 %) nor tensor-bound (23 %).
+  // Measured (round 2): SIX / FOUR slots made every layer slower (64 -> 64: 149 -> 171 us, 128 -> 128: 93 -> 104 us), and so
+  // did a 220 KB instead of a 200 KB shared-memory budget (256 -> 256 with one more weight slot: 91 -> 147 us): the
+  // epilogue's residual / affine loads live in what the carve-out leaves to L1.  Three slots, <= VP_SMEM_BUDGET.
+#ifndef VP_A_SLOTS
+#define VP_A_SLOTS 3
+#endif
+#ifndef VP_SMEM_BUDGET
+#define VP_SMEM_BUDGET (200 * 1024)
+#endif
+  static constexpr int A_SLOTS = VP_A_SLOTS;
   static constexpr int A_BYTES = A_SLOTS * VP_A_SLOT_BYTES;     // 72 KB
   static constexpr int STAGE_BYTES = 2 * 2 * 128 * 64;          // TMA-store staging: 2 column groups x hi/lo x 128 rows x 64 B
-  // BN = 64: enough slots to keep all 9 taps x 2 K blocks of a 64 -> 64 layer resident (loaded once per CTA, never recycled:
-  // the weight tiles were 47 % of the TMA traffic of those HBM-bound layers)
-  static constexpr int B_CAP = BN <= 64 ? 18 : 8;
-  static constexpr int B_SLOTS = (200 * 1024 - A_BYTES - STAGE_BYTES) / B_SLOT_BYTES > B_CAP
-                                     ? B_CAP : (200 * 1024 - A_BYTES - STAGE_BYTES) / B_SLOT_BYTES;
+  // (weights that fit the ring stay resident -- b_resident; measured: no gain for the 64-channel layers, so the ring is small)
+  static constexpr int B_CAP = 8;
+  static constexpr int B_SLOTS = (VP_SMEM_BUDGET - A_BYTES - STAGE_BYTES) / B_SLOT_BYTES > B_CAP
+                                     ? B_CAP : (VP_SMEM_BUDGET - A_BYTES - STAGE_BYTES) / B_SLOT_BYTES;
   static constexpr int SMEM = A_BYTES + B_SLOTS * B_SLOT_BYTES + STAGE_BYTES + 1024 + 512;
   static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;   // 2 buffers x one accumulator
 };
