@@ -19,10 +19,9 @@ namespace tcv {
 
 extern std::atomic<int> g_debug_flags;
 
-constexpr int VP_BK = 32;
 constexpr int VP_MAXG = 3;
 constexpr int VP_MAXDY = 3;
-constexpr int VP_A_SLOT_BYTES = 2 * 12288;   // hi + lo planes of one (TH + halo) x TW x 32-channel box: up to 192 rows x 64 B
+constexpr int VP_A_ROWS = 192;   // rows (pixels) of the largest (TH + halo) x TW activation box
 
 struct VPParams {
   int gh, gw, TH, TW, tiles_x, tiles_y, n_tiles_n, total_work;
@@ -30,6 +29,7 @@ struct VPParams {
   int ngroups, group_dx[VP_MAXG], ndy[VP_MAXG], dy[VP_MAXG][VP_MAXDY], wtap[VP_MAXG][VP_MAXDY];
   int dy_min, box_rows;
   int tma_store;
+  int dbg;           // measurement switches (tcv_set_debug_flags): 1 no MMA, 4 activations loaded once, 8 weights loaded once
   int b_resident;    // all weight tiles of a work item fit the B ring: staged by the first work item only
   uint32_t idesc;
   uint32_t idesc2;   // STACK: the N = 2*BN descriptor of the stacked MMA (idesc stays N = BN)
@@ -42,11 +42,20 @@ struct VPParams {
 // SM with three MMAs of N = 64; 117 B/clk stacked).  In cta_group::2 the N rows of an operand are split between the CTAs, so
 // the leader stages B_hi (all BN rows) and the peer B_lo at slot offset 0; the N = BN operand of the second MMA sits at
 // slot offset 2*BN*64 B: rows 0..BN/2-1 of B_hi in the leader, rows BN/2..BN-1 in the peer.
-template <int BN, bool STACK = false>
+// BK: K elements (channels) per stage = bytes per shared-memory row / 2: 32 -> SWIZZLE_64B, 64 -> SWIZZLE_128B.  BK = 64 halves
+// the number of stages per work item: the per-stage cost of the issuing thread (barrier wait, descriptors, commits: ~0.26 us,
+// measured with the MMAs switched off) exceeds the 0.2 us of tensor work of a BK = 32 stage of the <= 128-channel layers.
+template <int BN, bool STACK = false, int BK_ = 32>
 struct VPCfg {
+  static constexpr int BK = BK_;
+  static constexpr int A_SLOT_BYTES = 2 * VP_A_ROWS * BK * 2;   // hi + lo planes
   static constexpr int B_ROWS = BN / 2;                         // rows of a weight tile this CTA stages
-  static constexpr int B_SLOT_BYTES = STACK ? 3 * B_ROWS * VP_BK * 2 : 2 * B_ROWS * VP_BK * 2;   // hi + lo (STACK: 2 + 1 blocks)
+  static constexpr int B_SLOT_BYTES = STACK ? 3 * B_ROWS * BK * 2 : 2 * B_ROWS * BK * 2;   // hi + lo (STACK: 2 + 1 blocks)
   static constexpr int ACC_COLS = STACK ? 2 * BN : BN;
+  // narrow layers: all (<= 3) vertical taps of a horizontal-offset group share ONE weight stage (one full/empty barrier round
+  // trip per 3 taps): a 64-channel stage is only 4 MMAs = 0.1 us of tensor work, the per-stage hand-shake cost more
+  static constexpr int TPS = BN <= 64 ? VP_MAXDY : 1;
+  static constexpr int B_TAP_BYTES = B_SLOT_BYTES;
   // activation ring depth: one box feeds only ndy x 2 (x 3) MMAs, i.e. 0.3 us of tensor work for a 64-channel layer against
   // ~1 us of TMA latency -- ncu shows those layers neither DRAM- (9 %), L2- (20 %) nor tensor-bound (23 %).
   // Measured (round 2): SIX / FOUR slots made every layer slower (64 -> 64: 149 -> 171 us, 128 -> 128: 93 -> 104 us), and so
@@ -58,14 +67,15 @@ struct VPCfg {
 #ifndef VP_SMEM_BUDGET
 #define VP_SMEM_BUDGET (200 * 1024)
 #endif
-  static constexpr int A_SLOTS = VP_A_SLOTS;
-  static constexpr int A_BYTES = A_SLOTS * VP_A_SLOT_BYTES;     // 72 KB
+  static constexpr int A_SLOTS = BK == 64 ? 2 : VP_A_SLOTS;     // (a BK = 64 slot carries twice the K)
+  static constexpr int A_BYTES = A_SLOTS * A_SLOT_BYTES;        // 72 / 96 KB
   static constexpr int STAGE_BYTES = 2 * 2 * 128 * 64;          // TMA-store staging: 2 column groups x hi/lo x 128 rows x 64 B
   // (weights that fit the ring stay resident -- b_resident; measured: no gain for the 64-channel layers, so the ring is small)
+  static constexpr int B_STAGE_BYTES = TPS * B_TAP_BYTES;
   static constexpr int B_CAP = 8;
-  static constexpr int B_SLOTS = (VP_SMEM_BUDGET - A_BYTES - STAGE_BYTES) / B_SLOT_BYTES > B_CAP
-                                     ? B_CAP : (VP_SMEM_BUDGET - A_BYTES - STAGE_BYTES) / B_SLOT_BYTES;
-  static constexpr int SMEM = A_BYTES + B_SLOTS * B_SLOT_BYTES + STAGE_BYTES + 1024 + 512;
+  static constexpr int B_SLOTS = (VP_SMEM_BUDGET - A_BYTES - STAGE_BYTES) / B_STAGE_BYTES > B_CAP
+                                     ? B_CAP : (VP_SMEM_BUDGET - A_BYTES - STAGE_BYTES) / B_STAGE_BYTES;
+  static constexpr int SMEM = A_BYTES + B_SLOTS * B_STAGE_BYTES + STAGE_BYTES + 1024 + 512;
   static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;   // 2 buffers x one accumulator
 };
 
@@ -113,7 +123,7 @@ __device__ __forceinline__ void vp_commit(uint32_t bar) {
                : "memory");
 }
 
-template <int BN, bool STACK>
+template <int BN, bool STACK, int BK>
 __global__ void __launch_bounds__(320, 1) conv_tc2p_kernel(const __grid_constant__ CUtensorMap mapA_hi,
                                                            const __grid_constant__ CUtensorMap mapA_lo,
                                                            const __grid_constant__ CUtensorMap mapB_hi,
@@ -121,13 +131,16 @@ __global__ void __launch_bounds__(320, 1) conv_tc2p_kernel(const __grid_constant
                                                            const __grid_constant__ CUtensorMap mapY_hi,
                                                            const __grid_constant__ CUtensorMap mapY_lo,
                                                            const __grid_constant__ VPParams p) {
-  using Cfg = VPCfg<BN, STACK>;
+  using Cfg = VPCfg<BN, STACK, BK>;
   constexpr int SA = Cfg::A_SLOTS, SB = Cfg::B_SLOTS;
+  constexpr int VP_BK = BK;
+  constexpr int VP_A_SLOT_BYTES = Cfg::A_SLOT_BYTES;
   constexpr uint32_t BLK = Cfg::B_ROWS * VP_BK * 2;     // one plane of B_ROWS weight rows
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_base = smem_base + Cfg::A_BYTES;
-  const uint32_t stage_base = b_base + SB * Cfg::B_SLOT_BYTES;
+  const uint32_t stage_base = b_base + SB * Cfg::B_STAGE_BYTES;
+  constexpr int TPS = Cfg::TPS;
   const uint32_t bar_base = stage_base + Cfg::STAGE_BYTES;
   auto fullA = [&](int s) { return bar_base + 8u * s; };
   auto emptyA = [&](int s) { return bar_base + 8u * (SA + s); };
@@ -194,30 +207,42 @@ __global__ void __launch_bounds__(320, 1) conv_tc2p_kernel(const __grid_constant
           mbar_wait(emptyA(sa), ((uint32_t)(ia / SA) & 1u) ^ 1u);
           const uint32_t adst = smem_base + sa * VP_A_SLOT_BYTES;
           if (elect_one()) {
-            if (leader) mbar_expect_tx(fullA(sa), 4u * a_plane_bytes);
-            const uint32_t fb = vp_mapa(fullA(sa), 0);
-            vp_tma_4d(adst, &mapA_hi, fb, kc * VP_BK, w0 + p.group_dx[g], hr, img);
-            vp_tma_4d(adst + a_plane_bytes, &mapA_lo, fb, kc * VP_BK, w0 + p.group_dx[g], hr, img);
+            if ((p.dbg & 4) && ia >= SA) {          // measurement switch: activations loaded once (results are garbage)
+              if (leader) mbar_arrive(fullA(sa));
+            } else {
+              if (leader) mbar_expect_tx(fullA(sa), 4u * a_plane_bytes);
+              const uint32_t fb = vp_mapa(fullA(sa), 0);
+              vp_tma_4d(adst, &mapA_hi, fb, kc * VP_BK, w0 + p.group_dx[g], hr, img);
+              vp_tma_4d(adst + a_plane_bytes, &mapA_lo, fb, kc * VP_BK, w0 + p.group_dx[g], hr, img);
+            }
           }
           __syncwarp();
           if (!load_b) continue;
-          for (int j = 0; j < p.ndy[g]; ++j, ++ib) {
+          for (int j0 = 0; j0 < p.ndy[g]; j0 += TPS, ++ib) {
             const int sb = ib % SB;          // resident mode: ib < SB, slot == stage index within the work item
+            const int nt = p.ndy[g] - j0 < TPS ? p.ndy[g] - j0 : TPS;     // taps in this weight stage
+            int nt0 = 1;
             mbar_wait(emptyB(sb), ((uint32_t)(ib / SB) & 1u) ^ 1u);
-            const uint32_t bdst = b_base + sb * Cfg::B_SLOT_BYTES;
             if (elect_one()) {
-              if (leader) mbar_expect_tx(fullB(sb), 2u * Cfg::B_SLOT_BYTES);
+              if ((p.dbg & 8) && ib >= SB) {        // measurement switch: weights loaded once
+                if (leader) mbar_arrive(fullB(sb));
+                nt0 = 0;
+              } else if (leader) mbar_expect_tx(fullB(sb), 2u * (uint32_t)nt * Cfg::B_TAP_BYTES);
               const uint32_t fb = vp_mapa(fullB(sb), 0);
-              if constexpr (STACK) {
-                // leader: B_hi rows 0..BN-1 (stacked operand, its N rows 0..BN-1) + B_hi rows 0..BN/2-1 again;
-                // peer:   B_lo rows 0..BN-1 (N rows BN..2BN-1)                  + B_hi rows BN/2..BN-1
-                const CUtensorMap* m0 = leader ? &mapB_hi : &mapB_lo;
-                vp_tma_3d(bdst, m0, fb, kc * VP_BK, n0, p.wtap[g][j]);
-                vp_tma_3d(bdst + BLK, m0, fb, kc * VP_BK, n0 + Cfg::B_ROWS, p.wtap[g][j]);
-                vp_tma_3d(bdst + 2 * BLK, &mapB_hi, fb, kc * VP_BK, nb, p.wtap[g][j]);
-              } else {
-                vp_tma_3d(bdst, &mapB_hi, fb, kc * VP_BK, nb, p.wtap[g][j]);
-                vp_tma_3d(bdst + Cfg::B_SLOT_BYTES / 2, &mapB_lo, fb, kc * VP_BK, nb, p.wtap[g][j]);
+              for (int jj = 0; jj < (nt0 ? nt : 0); ++jj) {
+                const int j = j0 + jj;
+                const uint32_t bdst = b_base + sb * Cfg::B_STAGE_BYTES + jj * Cfg::B_TAP_BYTES;
+                if constexpr (STACK) {
+                  // leader: B_hi rows 0..BN-1 (stacked operand, its N rows 0..BN-1) + B_hi rows 0..BN/2-1 again;
+                  // peer:   B_lo rows 0..BN-1 (N rows BN..2BN-1)                  + B_hi rows BN/2..BN-1
+                  const CUtensorMap* m0 = leader ? &mapB_hi : &mapB_lo;
+                  vp_tma_3d(bdst, m0, fb, kc * VP_BK, n0, p.wtap[g][j]);
+                  vp_tma_3d(bdst + BLK, m0, fb, kc * VP_BK, n0 + Cfg::B_ROWS, p.wtap[g][j]);
+                  vp_tma_3d(bdst + 2 * BLK, &mapB_hi, fb, kc * VP_BK, nb, p.wtap[g][j]);
+                } else {
+                  vp_tma_3d(bdst, &mapB_hi, fb, kc * VP_BK, nb, p.wtap[g][j]);
+                  vp_tma_3d(bdst + Cfg::B_TAP_BYTES / 2, &mapB_lo, fb, kc * VP_BK, nb, p.wtap[g][j]);
+                }
               }
             }
             __syncwarp();
@@ -227,54 +252,63 @@ __global__ void __launch_bounds__(320, 1) conv_tc2p_kernel(const __grid_constant
     }
   } else if (warp == 1) {
     // ================================ MMA issuer (leader CTA only) ================================
+    // The issue path is latency-critical (measured: a handful of extra instructions per stage cost the 128-channel layers
+    // 10 %): every operand descriptor of a stage is formed from precomputed low words BEFORE the stage's barrier is awaited,
+    // so that the MMAs go out back to back the moment the data has landed.
     if (leader) {
       int ia = 0, ib = 0, iw = 0;
+      const uint32_t plane16 = (uint32_t)a_plane_bytes >> 4;
+      const uint32_t row16 = (uint32_t)(p.TW * (VP_BK * 2)) >> 4;          // one image row of the box, in 16-byte units
       for (int work = pair; work < p.total_work; work += npairs, ++iw) {
         const int buf = iw & 1;
         mbar_wait(accEmpty(buf), ((uint32_t)(iw >> 1) & 1u) ^ 1u);   // both CTAs' epilogues have drained this buffer
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)(buf * Cfg::ACC_COLS);
-        bool first = true;
+        uint32_t acc_first = 0u;
         int il = 0;   // weight stage index within this work item
         for (int kc = 0; kc < p.kc_iters; ++kc) {
           for (int g = 0; g < p.ngroups; ++g, ++ia) {
             const int sa = ia % SA;
+            const uint32_t a_lo32 = smem_desc_lo(smem_base + sa * VP_A_SLOT_BYTES);
+            const int ndy = p.ndy[g];
+            const bool last_group = kc == p.kc_iters - 1 && g == p.ngroups - 1;
             mbar_wait(fullA(sa), (uint32_t)(ia / SA) & 1u);
-            tc_fence_after();
-            const uint32_t a_hi = smem_base + sa * VP_A_SLOT_BYTES, a_lo = a_hi + a_plane_bytes;
-            for (int j = 0; j < p.ndy[g]; ++j, ++ib, ++il) {
+            for (int j = 0; j < ndy; ++j) {
+              const bool stage_first = (j % TPS) == 0, stage_last = ((j + 1) % TPS) == 0 || j == ndy - 1;
               const int sb = p.b_resident ? il : ib % SB;
-              if (!p.b_resident || iw == 0) {   // resident weights: only the first work item has to wait for them
+              // rows of the accumulator for vertical tap dy start (dy - dy_min) image rows into the box (same offset in
+              // the peer's shared memory, whose box starts TH image rows lower)
+              const uint32_t ah32 = a_lo32 + (uint32_t)(p.dy[g][j] - p.dy_min) * row16, al32 = ah32 + plane16;
+              const uint32_t bh32 = smem_desc_lo(b_base + sb * Cfg::B_STAGE_BYTES + (j % TPS) * Cfg::B_TAP_BYTES);
+              if (stage_first && (!p.b_resident || iw == 0))   // resident weights: only the first work item waits for them
                 mbar_wait(fullB(sb), p.b_resident ? 0u : ((uint32_t)(ib / SB) & 1u));
-                tc_fence_after();
-              }
-              const uint32_t b_hi = b_base + sb * Cfg::B_SLOT_BYTES, b_lo = b_hi + Cfg::B_SLOT_BYTES / 2;
+              tc_fence_after();
               if (elect_one()) {
-                // rows of the accumulator for vertical tap dy start (dy - dy_min) image rows into the box (same offset in
-                // the peer's shared memory, whose box starts TH image rows lower)
-                const uint32_t roff = (uint32_t)((p.dy[g][j] - p.dy_min) * p.TW) * (VP_BK * 2);
 #pragma unroll
-                for (int ks = 0; ks < VP_BK / 16; ++ks) {
-                  const uint64_t ah = smem_desc<VP_BK>(a_hi + roff + ks * 32), al = smem_desc<VP_BK>(a_lo + roff + ks * 32);
+                for (int ks = 0; ks < ((p.dbg & 1) ? 0 : VP_BK / 16); ++ks) {
+                  const uint64_t ah = smem_desc_join<VP_BK>(ah32 + 2 * ks), al = smem_desc_join<VP_BK>(al32 + 2 * ks);
                   if constexpr (STACK) {
-                    const uint64_t bs = smem_desc<VP_BK>(b_hi + ks * 32), bh2 = smem_desc<VP_BK>(b_hi + 2 * BLK + ks * 32);
-                    vp_mma(d, ah, bs, p.idesc2, (first && ks == 0) ? 0u : 1u);     // cols [0,BN): hi.hi ; [BN,2BN): hi.lo
-                    vp_mma(d, al, bh2, p.idesc, 1u);                               // cols [0,BN) += lo.hi
+                    const uint64_t bs = smem_desc_join<VP_BK>(bh32 + 2 * ks);
+                    const uint64_t bh2 = smem_desc_join<VP_BK>(bh32 + ((2 * BLK) >> 4) + 2 * ks);
+                    vp_mma(d, ah, bs, p.idesc2, acc_first | (uint32_t)ks);        // cols [0,BN): hi.hi ; [BN,2BN): hi.lo
+                    vp_mma(d, al, bh2, p.idesc, 1u);                              // cols [0,BN) += lo.hi
                   } else {
-                    const uint64_t bh = smem_desc<VP_BK>(b_hi + ks * 32), bl = smem_desc<VP_BK>(b_lo + ks * 32);
-                    vp_mma(d, ah, bh, p.idesc, (first && ks == 0) ? 0u : 1u);
+                    const uint64_t bh = smem_desc_join<VP_BK>(bh32 + 2 * ks);
+                    const uint64_t bl = smem_desc_join<VP_BK>(bh32 + (Cfg::B_TAP_BYTES >> 5) + 2 * ks);
+                    vp_mma(d, ah, bh, p.idesc, acc_first | (uint32_t)ks);
                     vp_mma(d, ah, bl, p.idesc, 1u);
                     vp_mma(d, al, bh, p.idesc, 1u);
                   }
                 }
-                if (!p.b_resident) vp_commit(emptyB(sb));
-                if (j == p.ndy[g] - 1) {
+                if (!p.b_resident && stage_last) vp_commit(emptyB(sb));
+                if (j == ndy - 1) {
                   vp_commit(emptyA(sa));
-                  if (kc == p.kc_iters - 1 && g == p.ngroups - 1) vp_commit(accFull(buf));
+                  if (last_group) vp_commit(accFull(buf));
                 }
               }
               __syncwarp();
-              first = false;
+              acc_first = 1u;
+              if (stage_last) { ++ib; ++il; }
             }
           }
         }
@@ -348,7 +382,7 @@ static bool vp_build_groups(const tcv_conv_desc& d, VPParams& p) {
   return true;
 }
 
-static void vp_pick_tile(int gh, int gw, int halo, int* TH, int* TW) {
+static void vp_pick_tile(int gh, int gw, int halo, int VP_BK, int VP_A_SLOT_BYTES, int* TH, int* TW) {
   long long best = -1;
   const int cand[3][2] = {{8, 16}, {4, 32}, {16, 8}};
   for (auto& c : cand) {
@@ -372,14 +406,15 @@ int conv2d_tc2p_supported(const tcv_conv_desc& d) {
   return vp_build_groups(d, p) ? 1 : 0;
 }
 
-template <int BN, bool STACK = false>
+template <int BN, bool STACK = false, int BK = 32>
 static int conv_tc2p_bn(const tcv_conv_desc& d, cudaStream_t st) {
-  using Cfg = VPCfg<BN, STACK>;
+  using Cfg = VPCfg<BN, STACK, BK>;
+  constexpr int VP_BK = BK;
   VPParams p;
   memset(&p, 0, sizeof(p));
   if (!vp_build_groups(d, p)) return fail(TCV_ERR_UNSUPPORTED, "conv_tc2p: tap pattern not supported");
   const int halo = p.box_rows;
-  vp_pick_tile(d.gh, d.gw, halo, &p.TH, &p.TW);
+  vp_pick_tile(d.gh, d.gw, halo, BK, Cfg::A_SLOT_BYTES, &p.TH, &p.TW);
   p.box_rows = p.TH + halo;
   p.gh = d.gh; p.gw = d.gw;
   p.tiles_x = (d.gw + p.TW - 1) / p.TW;
@@ -387,10 +422,16 @@ static int conv_tc2p_bn(const tcv_conv_desc& d, cudaStream_t st) {
   p.n_tiles_n = d.cout / BN;
   p.total_work = p.tiles_x * p.tiles_y * p.n_tiles_n * d.n;
   p.kc_iters = d.cin / VP_BK;
-  p.b_resident = (p.n_tiles_n == 1 && d.ntaps * p.kc_iters <= Cfg::B_SLOTS && !(g_debug_flags.load() & 32768)) ? 1 : 0;
+  {
+    int stages = 0;      // weight stages per work item
+    for (int g = 0; g < p.ngroups; ++g) stages += (p.ndy[g] + Cfg::TPS - 1) / Cfg::TPS;
+    stages *= p.kc_iters;
+    p.b_resident = (p.n_tiles_n == 1 && stages <= Cfg::B_SLOTS && !(g_debug_flags.load() & 32768)) ? 1 : 0;
+  }
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
   p.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-  fill_epi(p.epi, d, 0);
+  p.dbg = g_debug_flags.load() & (1 | 4 | 8);
+  fill_epi(p.epi, d, g_debug_flags.load() & (2 | 32 | 128));
   p.tma_store = 1;
 
   CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo, mY_hi, mY_lo;
@@ -425,7 +466,7 @@ static int conv_tc2p_bn(const tcv_conv_desc& d, cudaStream_t st) {
     rc = make_map(&mB_lo, b + (long long)d.w_tc_taps * d.cout * d.cin, 3, dims, str, box, VP_BK);
     if (rc) return rc;
   }
-  auto kern = conv_tc2p_kernel<BN, STACK>;
+  auto kern = conv_tc2p_kernel<BN, STACK, BK>;
   TCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
   int dev = 0, sms = 0;
   TCV_CUDA(cudaGetDevice(&dev));
@@ -450,10 +491,12 @@ static int conv_tc2p_bn(const tcv_conv_desc& d, cudaStream_t st) {
 }
 
 int conv2d_tc2p(const tcv_conv_desc& d, cudaStream_t st) {
-  if (d.cout % 256 == 0) return conv_tc2p_bn<256>(d, st);
-  if (d.cout % 128 == 0) return conv_tc2p_bn<128>(d, st);
+  const bool bk64 = d.cin % 64 == 0 && !(g_debug_flags.load() & 65536);       // A/B switch 65536: BK = 32 everywhere
+  if (d.cout % 256 == 0)
+    return (bk64 && (g_debug_flags.load() & 131072)) ? conv_tc2p_bn<256, false, 64>(d, st) : conv_tc2p_bn<256>(d, st);
+  if (d.cout % 128 == 0) return bk64 ? conv_tc2p_bn<128, false, 64>(d, st) : conv_tc2p_bn<128>(d, st);
   if (g_debug_flags.load() & 16384) return conv_tc2p_bn<64, false>(d, st);   // A/B switch: three N = 64 MMAs per K step
-  return conv_tc2p_bn<64, true>(d, st);
+  return bk64 ? conv_tc2p_bn<64, true, 64>(d, st) : conv_tc2p_bn<64, true>(d, st);
 }
 
 }  // namespace tcv

@@ -91,6 +91,19 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
   return (uint64_t)((addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 
+// The same descriptor in two halves, for issue loops that must stay short: the high word is a compile-time constant and
+// the low word is (address >> 4) | LBO, so an operand `off` bytes further on is `lo + (off >> 4)` (shared-memory addresses
+// are < 2^18, the sum never carries into the LBO field).
+template <int BK>
+__device__ __forceinline__ constexpr uint32_t smem_desc_hi() {
+  return (uint32_t)((8u * BK * 2u) >> 4) | (1u << 14) | ((BK * 2 == 128 ? 2u : 4u) << 29);
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); }
+template <int BK>
+__device__ __forceinline__ uint64_t smem_desc_join(uint32_t lo) {
+  return ((uint64_t)smem_desc_hi<BK>() << 32) | lo;
+}
+
 // kind::f16 instruction descriptor: D=f32, A=B=bf16 (format 1) or fp16 (format 0), both K-major, M=128, N=bn
 static inline uint32_t instr_desc(int bn, bool fp16) {
   const uint32_t fmt = fp16 ? 0u : 1u;

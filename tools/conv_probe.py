@@ -49,7 +49,7 @@ def run(cin, cout, h, w, n, res=True, sweep=None):
                 _cabi.check(L.tcv_conv2d(C.byref(d), st), "conv")
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 10
-            print(f"{cin}->{cout} {h}x{w} n{n} v{ver} flags={flags:2d}: {ms*1e3:8.1f} us  {flops/ms/1e9:7.1f} TF/s(alg)", flush=True)
+            print(f"{cin}->{cout} {h}x{w} n{n} v{ver} flags={flags:3d}: {ms*1e3:8.1f} us  {flops/ms/1e9:7.1f} TF/s(alg)", flush=True)
     L.tcv_set_debug_flags(0); L.tcv_set_conv_tc_version(2)
 
 
