@@ -493,6 +493,7 @@ static int conv_tc2p_bn(const tcv_conv_desc& d, cudaStream_t st) {
 int conv2d_tc2p(const tcv_conv_desc& d, cudaStream_t st) {
   const bool bk64 = d.cin % 64 == 0 && !(g_debug_flags.load() & 65536);       // A/B switch 65536: BK = 32 everywhere
   if (d.cout % 256 == 0)
+    // N = 256: BK = 32 (a stage is already 0.4 us of tensor work; BK = 64 leaves only two weight slots: measured 2-5 % slower)
     return (bk64 && (g_debug_flags.load() & 131072)) ? conv_tc2p_bn<256, false, 64>(d, st) : conv_tc2p_bn<256>(d, st);
   if (d.cout % 128 == 0) return bk64 ? conv_tc2p_bn<128, false, 64>(d, st) : conv_tc2p_bn<128>(d, st);
   if (g_debug_flags.load() & 16384) return conv_tc2p_bn<64, false>(d, st);   // A/B switch: three N = 64 MMAs per K step

@@ -36,15 +36,15 @@ struct G2Params {
   uint32_t idesc;
 };
 
-template <int CG>
+template <int CG, int BK_ = 64>
 struct G2Cfg {
-  static constexpr int BK = 32;
+  static constexpr int BK = BK_;      // 64 (SWIZZLE_128B): half as many stages = barrier round trips of the issuing thread
   static constexpr int BN = 256;
   static constexpr int A_PLANE = 128 * BK * 2;        // 8 KB: this CTA's 128 rows of A
   static constexpr int B_ROWS = BN / CG;              // rows of the B tile this CTA stages
   static constexpr int B_PLANE = B_ROWS * BK * 2;
   static constexpr int STAGE = 2 * (A_PLANE + B_PLANE);   // hi + lo planes: 32 KB (pair) / 48 KB (single)
-  static constexpr int STAGES = CG == 2 ? 6 : 4;          // 192 KB
+  static constexpr int STAGES = (192 * 1024) / STAGE;     // 192 KB
   static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
 };
 
@@ -87,13 +87,13 @@ __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
                : "memory");
 }
 
-template <int CG>
+template <int CG, int BK>
 __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi,
                                                           const __grid_constant__ CUtensorMap mapA_lo,
                                                           const __grid_constant__ CUtensorMap mapB_hi,
                                                           const __grid_constant__ CUtensorMap mapB_lo,
                                                           const __grid_constant__ G2Params p) {
-  using Cfg = G2Cfg<CG>;
+  using Cfg = G2Cfg<CG, BK>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -190,16 +190,16 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
         const uint32_t d = tmem_base + (uint32_t)(buf * Cfg::BN);
         for (int kc = 0; kc < p.kc_iters; ++kc, ++it) {
           const int s = it % STAGES;
+          // operand descriptors of this stage (low words; see smem_desc_lo) before the barrier is awaited
+          const uint32_t a32 = smem_desc_lo(smem_base + s * Cfg::STAGE);
+          const uint32_t al32 = a32 + (Cfg::A_PLANE >> 4), b32 = a32 + ((2 * Cfg::A_PLANE) >> 4), bl32 = b32 + (Cfg::B_PLANE >> 4);
           mbar_wait(full_bar(s), ((uint32_t)(it / STAGES)) & 1u);
           tc_fence_after();
-          const uint32_t st = smem_base + s * Cfg::STAGE;
-          const uint32_t a_hi = st, a_lo = st + Cfg::A_PLANE;
-          const uint32_t b_hi = st + 2 * Cfg::A_PLANE, b_lo = b_hi + Cfg::B_PLANE;
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < Cfg::BK / 16; ++ks) {
-              const uint64_t ah = smem_desc<Cfg::BK>(a_hi + ks * 32), al = smem_desc<Cfg::BK>(a_lo + ks * 32);
-              const uint64_t bh = smem_desc<Cfg::BK>(b_hi + ks * 32), bl = smem_desc<Cfg::BK>(b_lo + ks * 32);
+              const uint64_t ah = smem_desc_join<Cfg::BK>(a32 + 2 * ks), al = smem_desc_join<Cfg::BK>(al32 + 2 * ks);
+              const uint64_t bh = smem_desc_join<Cfg::BK>(b32 + 2 * ks), bl = smem_desc_join<Cfg::BK>(bl32 + 2 * ks);
               const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
               if constexpr (CG == 2) {
                 tc_mma_pair(d, ah, bh, p.idesc, acc);
@@ -278,10 +278,10 @@ static inline uint32_t instr_desc_mn(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <int CG>
+template <int CG, int BK>
 static int launch_gemm_tc2(const void* A, long long a_plane, const void* B, long long b_plane, float* C, int M, int N, int K,
                            long long ldc, long long c_batch_stride, int batch, cudaStream_t st) {
-  using Cfg = G2Cfg<CG>;
+  using Cfg = G2Cfg<CG, BK>;
   CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
   const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(A);
   const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(B);
@@ -312,7 +312,7 @@ static int launch_gemm_tc2(const void* A, long long a_plane, const void* B, long
   p.kc_iters = K / Cfg::BK;
   p.c = C; p.ldc = ldc; p.c_batch_stride = c_batch_stride;
   p.idesc = instr_desc_mn(128 * CG, Cfg::BN);
-  auto kern = gemm_tc2_kernel<CG>;
+  auto kern = gemm_tc2_kernel<CG, BK>;
   TCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
   int dev = 0, sms = 0;
   TCV_CUDA(cudaGetDevice(&dev));
@@ -339,8 +339,11 @@ static int launch_gemm_tc2(const void* A, long long a_plane, const void* B, long
 // mode: 2 = CTA pair (256 x 256 tiles), 1 = single CTA (128 x 256 tiles)
 int gemm_tc2(const void* A, long long a_plane, const void* B, long long b_plane, float* C, int M, int N, int K, long long ldc,
              long long c_batch_stride, int batch, int mode, cudaStream_t st) {
-  if (mode == 2) return launch_gemm_tc2<2>(A, a_plane, B, b_plane, C, M, N, K, ldc, c_batch_stride, batch, st);
-  return launch_gemm_tc2<1>(A, a_plane, B, b_plane, C, M, N, K, ldc, c_batch_stride, batch, st);
+  const bool bk32 = (g_debug_flags.load() & 262144) != 0;      // A/B switch: BK = 32 stages
+  if (mode == 2)
+    return bk32 ? launch_gemm_tc2<2, 32>(A, a_plane, B, b_plane, C, M, N, K, ldc, c_batch_stride, batch, st)
+                : launch_gemm_tc2<2, 64>(A, a_plane, B, b_plane, C, M, N, K, ldc, c_batch_stride, batch, st);
+  return launch_gemm_tc2<1, 32>(A, a_plane, B, b_plane, C, M, N, K, ldc, c_batch_stride, batch, st);
 }
 
 }  // namespace tcv

@@ -49,11 +49,15 @@ def run(cin, cout, h, w, n, res=True, sweep=None):
                 _cabi.check(L.tcv_conv2d(C.byref(d), st), "conv")
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 10
-            print(f"{cin}->{cout} {h}x{w} n{n} v{ver} flags={flags:3d}: {ms*1e3:8.1f} us  {flops/ms/1e9:7.1f} TF/s(alg)", flush=True)
+            print(f"{cin}->{cout} {h}x{w} n{n} v{ver} flags={flags:6d}: {ms*1e3:8.1f} us  {flops/ms/1e9:7.1f} TF/s(alg)", flush=True)
     L.tcv_set_debug_flags(0); L.tcv_set_conv_tc_version(2)
 
 
-if len(sys.argv) >= 6:      # python tools/conv_probe.py cin cout h w n : conv_tc2 under its measurement switches
+if len(sys.argv) >= 7:      # python tools/conv_probe.py cin cout h w n flagA,flagB,... : A/B of tcv_set_debug_flags values
+    cin, cout, h, w, n = map(int, sys.argv[1:6])
+    for rep in range(2):
+        run(cin, cout, h, w, n, sweep=tuple(int(v) for v in sys.argv[6].split(",")))
+elif len(sys.argv) >= 6:      # python tools/conv_probe.py cin cout h w n : conv_tc2 under its measurement switches
     cin, cout, h, w, n = map(int, sys.argv[1:6])
     # 1 no MMA, 2 no epilogue memory ops, 4 activations loaded once, 8 weights loaded once
     run(cin, cout, h, w, n, sweep=(0, 1, 2, 3, 4, 8, 12, 15))

@@ -10,7 +10,7 @@ from tcvom_b200 import _cabi
 
 L = _cabi.lib()
 dev = torch.device("cuda:0")
-KERNELS = (("pair 256x256", 0), ("single 128x256", 1024), ("per-tile 128x128", 2048))
+KERNELS = (("pair 256x256 BK64", 0), ("pair 256x256 BK32", 262144), ("single 128x256", 1024), ("per-tile 128x128", 2048))
 
 
 def planes(x):
