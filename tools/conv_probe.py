@@ -37,7 +37,7 @@ def run(cin, cout, h, w, n, res=True, sweep=None):
         d.res1 = res1.data_ptr()
     d.act = 1
     flops = 2 * n * h * w * 9 * cin * cout
-    for ver in ((2,) if sweep else (3, 2)):
+    for ver in ((int(os.environ.get("TCV_PROBE_VER", "2")),) if sweep else (3, 2)):
         L.tcv_set_conv_tc_version(ver)
         for flags in (sweep if sweep else ((0, 64, 1) if ver == 3 else (0,))):
             L.tcv_set_debug_flags(flags)
