@@ -44,7 +44,8 @@ struct V3Cfg {
   static constexpr int MAX_B_SLOTS = 18;                      // 9 taps x up to 2 K blocks stay resident (72 KB)
   static constexpr int A_SLOT_BYTES = 45056;                  // hi + lo of one 10x34-pixel x 32-channel box
   static constexpr int MAX_A_SLOTS = 3;
-  static constexpr int STAGE_BYTES = 2 * 2 * 128 * BN * 2;    // output staging: 2 accumulators x hi/lo x 128 px x BN ch
+  static constexpr int STAGE_HALF = 2 * 2 * 128 * BN * 2;     // output staging: 2 accumulators x hi/lo x 128 px x BN ch
+  static constexpr int STAGE_BYTES = 2 * STAGE_HALF;          // double-buffered (the epilogue bounds these layers)
   static constexpr int BAR_BYTES = 512;
   static constexpr int TMEM_COLS = 8 * BN;                    // 2 buffers x 2 accumulators x (hi.hi | hi.lo) halves
   static int smem_bytes(int a_slots, int b_slots) {
@@ -162,6 +163,15 @@ __global__ void __launch_bounds__(320, 1) conv_tc3_kernel(const __grid_constant_
     int ia = 0, ib = 0, iw = 0;
     const uint32_t row_bytes = (uint32_t)p.box_w * 16u;                       // SBO: next image row of the box
     const uint32_t lbo = p.fold ? 16u : chunk_bytes;                          // K-adjacent core matrix
+    // Resident weights (every layer shape of the network): ONE issue block per K block -- all taps back to back, operand
+    // descriptors formed from low words (address >> 4) with constant high words.  The per-tap version below needed an
+    // elect / descriptor round of ~0.3 us for 0.1 us of tensor work per tap (measured: 165 us with the epilogue's memory
+    // operations switched off, 100 us with the MMAs off as well, for 32 -> 32 @ 544 x 960 x 3).
+    const bool fast = p.b_resident && !(p.epi.dbg & (64 | 256));
+    const uint32_t a_lo16 = a_lo_off >> 4, th16 = (uint32_t)(V3_TH * p.box_w);      // (pixel = 16 bytes)
+    const uint32_t kstep16 = p.fold ? 2u : (2u * chunk_bytes) >> 4;
+    const uint32_t ns_hi = ((row_bytes >> 4) & 0x3FFFu) | (1u << 14);
+    const uint32_t ns_lbo = ((lbo >> 4) & 0x3FFFu) << 16;
     for (int work = blockIdx.x; work < p.total_work; work += gridDim.x, ++iw) {
       const int buf = iw & 1;
       mbar_wait(accEmpty(buf), ((uint32_t)(iw >> 1) & 1u) ^ 1u);
@@ -169,6 +179,40 @@ __global__ void __launch_bounds__(320, 1) conv_tc3_kernel(const __grid_constant_
       const uint32_t d0 = tmem_base + (uint32_t)(buf * 4 * BN), d1 = d0 + (uint32_t)(2 * BN);
       bool first = true;
       int il = 0;
+      if (fast) {
+        if (iw == 0) {                       // the weights arrive once
+          for (int s = 0; s < p.ntaps * p.kc_iters; ++s) mbar_wait(fullB(s), 0u);
+        }
+        for (int kc = 0; kc < p.kc_iters; ++kc, ++ia) {
+          const int sa = ia % SA;
+          const uint32_t a32 = (((smem_base + sa * Cfg::A_SLOT_BYTES) & 0x3FFFFu) >> 4) | ns_lbo;
+          const uint32_t b32 = smem_desc_lo(b_base + (uint32_t)(kc * p.ntaps) * Cfg::B_SLOT_BYTES);
+          mbar_wait(fullA(sa), (uint32_t)(ia / SA) & 1u);
+          tc_fence_after();
+          if (elect_one()) {
+            for (int t = 0; t < p.ntaps; ++t) {
+              const uint32_t px0 = (uint32_t)((p.dy[t] - p.dy_min) * p.box_w + (p.fold ? 0 : p.dx[t] - p.dx_min));
+              const uint32_t ah32 = a32 + px0, bt32 = b32 + (uint32_t)t * (Cfg::B_SLOT_BYTES >> 4);
+#pragma unroll
+              for (int ks = 0; ks < ((p.epi.dbg & 1) ? 0 : 2); ++ks) {
+                const uint32_t a0 = ah32 + ks * kstep16;
+                const uint64_t ah0 = ((uint64_t)ns_hi << 32) | a0, ah1 = ((uint64_t)ns_hi << 32) | (a0 + th16);
+                const uint64_t al0 = ((uint64_t)ns_hi << 32) | (a0 + a_lo16), al1 = ((uint64_t)ns_hi << 32) | (a0 + a_lo16 + th16);
+                const uint64_t bh = smem_desc_join<32>(bt32 + 2 * ks);
+                const uint32_t acc = (kc == 0 && t == 0 && ks == 0) ? 0u : 1u;
+                tc_mma(d0, ah0, bh, p.idesc2, acc);
+                tc_mma(d1, ah1, bh, p.idesc2, acc);
+                tc_mma(d0, al0, bh, p.idesc, 1u);
+                tc_mma(d1, al1, bh, p.idesc, 1u);
+              }
+            }
+            tc_commit(emptyA(sa));
+            if (kc == p.kc_iters - 1) tc_commit(accFull(buf));
+          }
+          __syncwarp();
+        }
+        continue;
+      }
       for (int kc = 0; kc < p.kc_iters; ++kc, ++ia) {
         const int sa = ia % SA;
         mbar_wait(fullA(sa), (uint32_t)(ia / SA) & 1u);
@@ -234,6 +278,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc3_kernel(const __grid_constant_
     stc.issuer = (e & 3) == 0 && lane == 0;
     stc.map_hi = &mapY_hi;
     stc.map_lo = &mapY_lo;
+    stc.alt_bytes = Cfg::STAGE_HALF;
     const bool issuer = stc.issuer;
     int iw = 0;
     for (int work = blockIdx.x; work < p.total_work; work += gridDim.x, ++iw) {

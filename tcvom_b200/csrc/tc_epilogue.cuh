@@ -40,6 +40,10 @@ struct StoreCtx {
   const CUtensorMap* map_hi = nullptr;   // output views {cout, gw, gh, n} of the hi / lo plane
   const CUtensorMap* map_lo = nullptr;
   int cx = 0, cy = 0;                    // tile origin in the compute grid
+  // double-buffered staging (alt_bytes != 0): chunk k stages at stage_* + (k & 1) * alt_bytes, so that the bulk store of the
+  // previous chunk may still be reading its tile while this one is being written (wait_group.read 1 instead of 0)
+  uint32_t alt_bytes = 0;
+  uint32_t chunk = 0;                    // running chunk counter of this warp group (kept across work items)
 };
 
 // gy/gx: position of this thread's pixel in the compute grid; in_grid: inside it.  The warp waits on
@@ -49,7 +53,7 @@ struct StoreCtx {
 template <int BN, int SPLIT_OFF = BN>
 __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr, bool in_grid, int img, int gy, int gx,
                                               int n0, uint32_t acc_full, uint32_t full_parity, uint32_t acc_empty,
-                                              int lane, const StoreCtx& st = StoreCtx(), bool split_halves = false,
+                                              int lane, StoreCtx& st, bool split_halves = false,
                                               bool remote_empty = false) {
   const bool valid = in_grid && !(p.dbg & 2);
   const int oy = gy * p.oy_mul + p.oy_off, ox = gx * p.ox_mul + p.ox_off;
@@ -163,8 +167,14 @@ __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr
       if (has2) add_res(rb[slot], f);
     }
     if (st.stage_hi) {
-      // the previous bulk store of this group must have finished READING the staging tile
-      if (st.issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      // the previous bulk store into THIS staging tile must have finished READING it
+      const uint32_t alt = (st.chunk & 1u) * st.alt_bytes;
+      const uint32_t stage_hi = st.stage_hi + alt, stage_lo = st.stage_lo + alt;
+      ++st.chunk;
+      if (st.issuer) {
+        if (st.alt_bytes) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
       asm volatile("bar.sync %0, 128;" ::"r"(st.bar) : "memory");
       if (valid) {
         const uint32_t sw = (uint32_t)((st.row >> 1) & 3);
@@ -174,17 +184,17 @@ __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr
 #pragma unroll
           for (int m = 0; m < 4; ++m) split2_bf16(f[8 * k + 2 * m], f[8 * k + 2 * m + 1], h[m], l[m]);
           const uint32_t off = (uint32_t)st.row * 64u + (((uint32_t)k ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st.stage_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st.stage_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync %0, 128;" ::"r"(st.bar + 2) : "memory");
       if (st.issuer && !(p.dbg & 2)) {
         asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                     ::"l"(st.map_hi), "r"(st.stage_hi), "r"(n0 + c0), "r"(st.cx), "r"(st.cy), "r"(img) : "memory");
+                     ::"l"(st.map_hi), "r"(stage_hi), "r"(n0 + c0), "r"(st.cx), "r"(st.cy), "r"(img) : "memory");
         asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                     ::"l"(st.map_lo), "r"(st.stage_lo), "r"(n0 + c0), "r"(st.cx), "r"(st.cy), "r"(img) : "memory");
+                     ::"l"(st.map_lo), "r"(stage_lo), "r"(n0 + c0), "r"(st.cx), "r"(st.cy), "r"(img) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       continue;
