@@ -431,7 +431,7 @@ static int conv_tc2p_bn(const tcv_conv_desc& d, cudaStream_t st) {
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
   p.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
   p.dbg = g_debug_flags.load() & (1 | 4 | 8);
-  fill_epi(p.epi, d, g_debug_flags.load() & (2 | 32 | 128));
+  fill_epi(p.epi, d, g_debug_flags.load() & (2 | 32 | 128 | 512));
   p.tma_store = 1;
 
   CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo, mY_hi, mY_lo;

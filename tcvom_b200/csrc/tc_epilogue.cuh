@@ -6,6 +6,15 @@
 
 namespace tcv {
 
+// 32 bytes per lane in one request (LDG.E.256, sm_100): the residual operand of a 32-channel chunk is 64 B per pixel and plane
+// at a pixel pitch of cout * 2 B, so a warp-wide 16-byte load touches 32 sectors and uses half of each; measured with the
+// MMAs switched off, those loads were 17 of the 27 us the epilogue adds to a 128 -> 128 layer.
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+
 struct EpiParams {
   int n_imgs, oh, ow, cout, oy_mul, oy_off, ox_mul, ox_off;
   __nv_bfloat16* y;
@@ -68,16 +77,16 @@ __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr
   uint4 ra[2][8], rb[2][8];   // [double buffer][4 x hi, 4 x lo] for res1 / res2
   auto fetch = [&](int c0, int slot) {
     if (has1) {
-      const uint4* h = reinterpret_cast<const uint4*>(p.res1 + r1base + c0);
-      const uint4* l = reinterpret_cast<const uint4*>(p.res1 + r1base + c0 + p.res1_plane);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { ra[slot][k] = __ldg(h + k); ra[slot][4 + k] = __ldg(l + k); }
+      const __nv_bfloat16* h = p.res1 + r1base + c0;
+      const __nv_bfloat16* l = h + p.res1_plane;
+      ldg256(h, ra[slot][0], ra[slot][1]); ldg256(h + 16, ra[slot][2], ra[slot][3]);
+      ldg256(l, ra[slot][4], ra[slot][5]); ldg256(l + 16, ra[slot][6], ra[slot][7]);
     }
     if (has2) {
-      const uint4* h = reinterpret_cast<const uint4*>(p.res2 + obase + c0);
-      const uint4* l = reinterpret_cast<const uint4*>(p.res2 + obase + c0 + p.res2_plane);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { rb[slot][k] = __ldg(h + k); rb[slot][4 + k] = __ldg(l + k); }
+      const __nv_bfloat16* h = p.res2 + obase + c0;
+      const __nv_bfloat16* l = h + p.res2_plane;
+      ldg256(h, rb[slot][0], rb[slot][1]); ldg256(h + 16, rb[slot][2], rb[slot][3]);
+      ldg256(l, rb[slot][4], rb[slot][5]); ldg256(l + 16, rb[slot][6], rb[slot][7]);
     }
   };
   auto add_res = [&](const uint4* rr, float* f) {
@@ -93,6 +102,7 @@ __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr
     }
   };
   fetch(0, 0);
+  if (BN / 32 == 2) fetch(32, 1);     // two chunks: both residual operands are in flight while the MMAs still run
   mbar_wait(acc_full, full_parity);
   tc_fence_after();
 #pragma unroll
@@ -118,7 +128,7 @@ __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr
         else
           mbar_arrive(acc_empty);
       }
-    } else {
+    } else if (BN / 32 != 2) {
       fetch(c0 + 32, slot ^ 1);
     }
     float f[32];
@@ -190,7 +200,7 @@ __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync %0, 128;" ::"r"(st.bar + 2) : "memory");
-      if (st.issuer && !(p.dbg & 2)) {
+      if (st.issuer && !(p.dbg & (2 | 512))) {      // (512: measurement switch, staging written but never stored)
         asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                      ::"l"(st.map_hi), "r"(stage_hi), "r"(n0 + c0), "r"(st.cx), "r"(st.cy), "r"(img) : "memory");
         asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
