@@ -17,8 +17,6 @@
 
 namespace tcv {
 
-extern std::atomic<int> g_debug_flags;
-
 constexpr int VP_MAXG = 3;
 constexpr int VP_MAXDY = 3;
 constexpr int VP_A_ROWS = 192;   // rows (pixels) of the largest (TH + halo) x TW activation box
@@ -152,6 +150,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc2p_kernel(const __grid_constant
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   const uint32_t rank = vp_cluster_rank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
@@ -176,6 +175,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc2p_kernel(const __grid_constant
   vp_cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();        // everything above overlapped the previous kernel's tail; from here on its results are read
 
   const int a_plane_bytes = p.box_rows * p.TW * (VP_BK * 2);   // one plane of this CTA's A box
   const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -479,13 +479,9 @@ static int conv_tc2p_bn(const tcv_conv_desc& d, cudaStream_t st) {
   cfg.blockDim = dim3(320, 1, 1);
   cfg.dynamicSmemBytes = Cfg::SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = tc_launch_attrs(attr, 2);
   TCV_CUDA(cudaLaunchKernelEx(&cfg, kern, mA_hi, mA_lo, mB_hi, mB_lo, mY_hi, mY_lo, p));
   return launched("conv_tc2p_kernel");
 }

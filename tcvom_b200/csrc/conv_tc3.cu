@@ -19,8 +19,6 @@
 
 namespace tcv {
 
-extern std::atomic<int> g_debug_flags;
-
 constexpr int V3_TH = 16, V3_TW = 8;
 constexpr int V3_MAXT = 9;
 
@@ -84,6 +82,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc3_kernel(const __grid_constant_
   const uint32_t tmem_slot = bar_base + 8u * (2 * SA + 2 * SB + 4);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < SA; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
@@ -103,6 +102,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc3_kernel(const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();
 
   const int box_px = p.box_w * p.box_rows;                  // pixels per chunk plane
   const uint32_t chunk_bytes = (uint32_t)box_px * 16u;      // one 8-channel chunk plane of the box
@@ -409,7 +409,16 @@ static int conv_tc3_bn(const tcv_conv_desc& d, cudaStream_t st) {
   TCV_CUDA(cudaGetDevice(&dev));
   TCV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.total_work < sms ? p.total_work : sms;
-  kern<<<grid, 320, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, mY_hi, mY_lo, p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(320, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  cfg.attrs = attr;
+  cfg.numAttrs = tc_launch_attrs(attr, 1);
+  TCV_CUDA(cudaLaunchKernelEx(&cfg, kern, mA_hi, mA_lo, mB_hi, mB_lo, mY_hi, mY_lo, p));
   return launched("conv_tc3_kernel");
 }
 

@@ -25,8 +25,6 @@
 
 namespace tcv {
 
-extern std::atomic<int> g_debug_flags;
-
 struct G2Params {
   int M, N, batch;
   int tiles_m, tiles_n, total_tiles;
@@ -106,6 +104,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   const uint32_t rank = CG == 2 ? cluster_rank() : 0u;
   const bool leader = rank == 0;
   const int pair = blockIdx.x / CG, npairs = gridDim.x / CG;
@@ -138,6 +137,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();
 
   const int tiles_per_batch = p.tiles_m * p.tiles_n;
   auto decode = [&](int tile, int& b, int& tm, int& tn) {
@@ -325,13 +325,9 @@ static int launch_gemm_tc2(const void* A, long long a_plane, const void* B, long
   cfg.blockDim = dim3(320, 1, 1);
   cfg.dynamicSmemBytes = Cfg::SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = tc_launch_attrs(attr, CG);
   TCV_CUDA(cudaLaunchKernelEx(&cfg, kern, mA_hi, mA_lo, mB_hi, mB_lo, p));
   return launched("gemm_tc2_kernel");
 }

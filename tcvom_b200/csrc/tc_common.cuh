@@ -111,6 +111,15 @@ static inline uint32_t instr_desc(int bn, bool fp16) {
 }
 
 
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream is still draining.  pdl_launch_dependents() at the top of a kernel lets the NEXT kernel's
+// CTAs be scheduled as soon as SMs free up; pdl_wait() blocks until the PREVIOUS kernel has completed and flushed -- it must
+// precede the first access to memory the predecessor may have written.  Between the two sits the prologue (barrier init, TMEM
+// allocation, tensor-map prefetch, cluster sync), which thereby overlaps the predecessor's tail.  Both are no-ops for a
+// kernel launched without the attribute.  Opt-in through tcv_set_debug_flags bit 524288 (measured: no gain inside a CUDA graph).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // One lane of a fully converged warp.  Issuing TMA / tcgen05 instructions under this predicate (with
 // all loop control kept warp-uniform) lets ptxas emit them directly; under a plain `lane == 0` branch
 // it wraps every UTCHMMA / UTMALDG in a vote-and-elect serialisation loop (measured: ~16 extra
@@ -127,6 +136,25 @@ __device__ __forceinline__ bool elect_one() {
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+extern std::atomic<int> g_debug_flags;
+// launch attributes of the persistent tensor-core kernels: optional cluster of two CTAs, programmatic dependent launch
+static inline int tc_launch_attrs(cudaLaunchAttribute* attr, int cluster) {
+  int n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (g_debug_flags.load() & 524288) {      // opt-in: measured on B200 (CUDA-graph replay of the window): no gain
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  return n;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
