@@ -543,6 +543,19 @@ int tcv_postprocess_eval_fba(const float* pred, const void* imgs, const void* tr
                              int batch, int frames, int h, int w, float* alphas, float* Fs, float* Bs,
                              tcv_stream_t stream);
 
+/* ---- training side of the shift-sum aggregation (csrc/gca_train2.cu; autograd of GCA/ops.py:112-118,204):
+ *  shift_add_u:        A fp32 [n][P][lda] (softmax on the unpadded key grid) -> A2 split-bf16 planes [2][n][Pk][ld]
+ *  shift_gather:       dA2 fp32 [n][Pk][ld] -> dA fp32 [n][P][lda],  dA[q][p] = sum_a dA2[q+a][p+a]
+ *  unfold_parity_bwd:  dY split-bf16 [n,h,w,128] -> dO2 planes [2][n][Pk][512] = gradient of tcv_gca_unfold_parity (x 1/4)
+ *  values_parity_bwd:  dF fp32 [n][Pk][512] -> dfeat split-bf16 [n,h,w,128] = gradient of tcv_gca_values_parity (the reflect
+ *                      border makes rows / columns 1 and h-2 / w-2 receive two contributions)
+ *  rowdot_f32:         out[r] = sum_{c < cols} A[r][c] * B[r][c]   (delta of the softmax backward) */
+int tcv_gca_shift_add_u(const float* A, int n, int h, int w, int lda, int ld, void* A2, tcv_stream_t stream);
+int tcv_gca_shift_gather(const float* dA2, int n, int h, int w, int ld, int lda, float* dA, tcv_stream_t stream);
+int tcv_gca_unfold_parity_bwd(const void* dY, int n, int h, int w, void* dO2, tcv_stream_t stream);
+int tcv_gca_values_parity_bwd(const float* dF, int n, int h, int w, void* dfeat, tcv_stream_t stream);
+int tcv_rowdot_f32(const float* A, const float* B, long long rows, int cols, long long ld, float* out, tcv_stream_t stream);
+
 /* ---- SyncBatchNorm statistic exchange over NVLink peer memory (train_ddp.py:273 nn.SyncBatchNorm; csrc/peer_reduce.cu).
  * In-place sum of `count` doubles over `world` ranks of one node in ONE kernel on the caller's stream.  `peers_dev`: device
  * array of `world` pointers, entry r = rank r's symmetric buffer (tcv_peer_buffer_bytes(slot_doubles) bytes, zero-filled

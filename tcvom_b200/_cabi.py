@@ -123,6 +123,11 @@ SIGNATURES = {
     "tcv_pad_reflect1_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_tanh01_bwd": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_void_p]),
     "tcv_head_tanh01": (c_int, [c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p]),
+    "tcv_gca_shift_add_u": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_gca_shift_gather": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_gca_unfold_parity_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_gca_values_parity_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_rowdot_f32": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_ll, c_void_p, c_void_p]),
     "tcv_peer_allreduce_f64": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, C.c_ulonglong, c_ll, c_void_p]),
     "tcv_peer_buffer_bytes": (c_int, [c_ll, C.POINTER(c_ll)]),
     "tcv_head_conv_tanh01": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -1,0 +1,188 @@
+// Training side of the shift-sum aggregation of guided contextual attention (forward: csrc/gca.cu, "Shift-sum form";
+// reference: GCA/ops.py:112-118,204 and its autograd).  With m = q + a, p' = p + a on the (hh+1) x (ww+1) grid:
+//     Y  = unfold_parity( A2 . F ) / 4           A2[m][p'] = sum_a A[m-a][p'-a]        F_r[p'] = feat_reflect[2p'+r-1]
+//     dO2 = unfold_parity^T(dY) / 4              dA2 = dO2 . F^T      dF = A2^T . dO2
+//     dA[q][p] = sum_a dA2[q+a][p+a]             dfeat = values_parity^T(dF)
+// i.e. the two backward GEMMs shrink from [P x 2048 x P] to [Pk x 512 x Pk] like the forward one (3.8x fewer FLOPs each).
+// The scores side (Q, Kn, softmax, dS, dQ, dKn) keeps the unpadded key grid [P x P_pad] of the round-1 backward, so only
+// the element-wise kernels below are new:
+//   shift_add_u   A fp32 [n][P][lda] (unpadded columns)  -> A2 split-bf16 planes [2][n][Pk][ld]
+//   shift_gather  dA2 fp32 [n][Pk][ld]                    -> dA fp32 [n][P][lda]
+//   unfold_parity_bwd  dY split-bf16 [n,h,w,128]          -> dO2 planes [2][n][Pk][512] (x 1/4)
+//   values_parity_bwd  dF fp32 [n][Pk][512]               -> dfeat split-bf16 [n,h,w,128]
+//   rowdot        delta[r] = sum_c A[r][c] * B[r][c]
+#include "common.cuh"
+
+namespace tcv {
+constexpr int T2_FC = 128;
+
+__global__ void __launch_bounds__(256) gca_shift_add_u_kernel(const float* __restrict__ A, int n, int hh, int ww, int lda,
+                                                              int ld, __nv_bfloat16* __restrict__ A2) {
+  const int P = hh * ww, ww1 = ww + 1, Pk = (hh + 1) * ww1;
+  const int m = blockIdx.x, img = blockIdx.y;
+  const int my = m / ww1, mx = m - my * ww1;
+  const float* rows[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int qy = my - (a >> 1), qx = mx - (a & 1);
+    rows[a] = (qy >= 0 && qy < hh && qx >= 0 && qx < ww) ? A + ((long long)img * P + qy * ww + qx) * lda : nullptr;
+  }
+  const long long plane = (long long)n * Pk * ld;
+  __nv_bfloat16* out = A2 + ((long long)img * Pk + m) * ld;
+  for (int j = threadIdx.x * 2; j < ld; j += 512) {
+    float v[2] = {0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int jj = j + e;
+      if (jj >= Pk) continue;
+      const int ky = jj / ww1, kx = jj - ky * ww1;          // padded key-grid position p'
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int py = ky - (a >> 1), px = kx - (a & 1);
+        if (rows[a] != nullptr && py >= 0 && py < hh && px >= 0 && px < ww) v[e] += __ldg(rows[a] + py * ww + px);
+      }
+    }
+    uint32_t hi, lo;
+    split2_bf16(v[0], v[1], hi, lo);
+    *reinterpret_cast<uint32_t*>(out + j) = hi;
+    *reinterpret_cast<uint32_t*>(out + plane + j) = lo;
+  }
+}
+
+__global__ void __launch_bounds__(256) gca_shift_gather_kernel(const float* __restrict__ dA2, int hh, int ww, int ld, int lda,
+                                                               float* __restrict__ dA) {
+  const int P = hh * ww, ww1 = ww + 1, Pk = (hh + 1) * ww1;
+  const int q = blockIdx.x, img = blockIdx.y;
+  const int qy = q / ww, qx = q - qy * ww;
+  const float* base = dA2 + (long long)img * Pk * ld;
+  float* out = dA + ((long long)img * P + q) * lda;
+  for (int p = threadIdx.x; p < lda; p += 256) {
+    float v = 0.f;
+    if (p < P) {
+      const int py = p / ww, px = p - py * ww;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int ay = a >> 1, ax = a & 1;
+        v += __ldg(base + (long long)((qy + ay) * ww1 + qx + ax) * ld + (py + ay) * ww1 + px + ax);
+      }
+    }
+    out[p] = v;
+  }
+}
+
+// work item = 8 channels of one (image, m, parity)
+__global__ void gca_unfold_parity_bwd_kernel(const __nv_bfloat16* __restrict__ dY, int n, int h, int w,
+                                             __nv_bfloat16* __restrict__ dO2) {
+  const int ww1 = w / 2 + 1, Pk = (h / 2 + 1) * ww1;
+  const long long total = (long long)n * Pk * 4 * (T2_FC / 8);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % (T2_FC / 8)) * 8;
+  long long t = i / (T2_FC / 8);
+  const int r = (int)(t % 4);
+  t /= 4;
+  const int m = (int)(t % Pk);
+  const int img = (int)(t / Pk);
+  const int my = m / ww1, mx = m - my * ww1;
+  const int y = 2 * my + (r >> 1) - 1, x = 2 * mx + (r & 1) - 1;
+  float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (y >= 0 && y < h && x >= 0 && x < w) {
+    load8(dY + (((long long)img * h + y) * w + x) * T2_FC + c, (long long)n * h * w * T2_FC, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] *= 0.25f;
+  }
+  store8(dO2 + ((long long)img * Pk + m) * (4 * T2_FC) + r * T2_FC + c, (long long)n * Pk * 4 * T2_FC, f);
+}
+
+// work item = 4 channels of one feature pixel: the (<= 2 x 2) positions of the reflect-padded parity grid that read it
+__global__ void gca_values_parity_bwd_kernel(const float* __restrict__ dF, int n, int h, int w, __nv_bfloat16* __restrict__ dfeat) {
+  const int ww1 = w / 2 + 1, Pk = (h / 2 + 1) * ww1;
+  const long long total = (long long)n * h * w * (T2_FC / 4);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % (T2_FC / 4)) * 4;
+  long long t = i / (T2_FC / 4);
+  const int x = (int)(t % w);
+  t /= w;
+  const int y = (int)(t % h);
+  const int img = (int)(t / h);
+  int us[2], vs[2], nu = 1, nv = 1;      // unreflected coordinates u in [-1, h], v in [-1, w] that reflect onto (y, x)
+  us[0] = y; vs[0] = x;
+  if (y == 1) us[nu++] = -1;
+  if (y == h - 2) us[nu++] = h;
+  if (x == 1) vs[nv++] = -1;
+  if (x == w - 2) vs[nv++] = w;
+  // (h, w >= 4: y == 1 and y == h-2 never coincide with a third source)
+  float acc[4] = {0, 0, 0, 0};
+  for (int a = 0; a < nu && a < 2; ++a)
+    for (int b = 0; b < nv && b < 2; ++b) {
+      const int u = us[a], v = vs[b];
+      const int ry = (u + 1) & 1, rx = (v + 1) & 1;
+      const int py = (u + 1 - ry) >> 1, px = (v + 1 - rx) >> 1;
+      const float4 g = *reinterpret_cast<const float4*>(dF + ((long long)img * Pk + py * ww1 + px) * (4 * T2_FC) +
+                                                        (ry * 2 + rx) * T2_FC + c);
+      acc[0] += g.x; acc[1] += g.y; acc[2] += g.z; acc[3] += g.w;
+    }
+  store4(dfeat + (((long long)img * h + y) * w + x) * T2_FC + c, (long long)n * h * w * T2_FC, acc);
+}
+
+// one warp per row
+__global__ void rowdot_kernel(const float* __restrict__ A, const float* __restrict__ B, long long rows, int cols, long long ld,
+                              float* __restrict__ out) {
+  const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* a = A + r * ld;
+  const float* b = B + r * ld;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s = fmaf(a[c], b[c], s);
+  s = warp_sum(s);
+  if (lane == 0) out[r] = s;
+}
+}  // namespace tcv
+
+using namespace tcv;
+
+extern "C" {
+
+int tcv_gca_shift_add_u(const float* A, int n, int h, int w, int lda, int ld, void* A2, tcv_stream_t stream) {
+  TCV_REQUIRE(A && A2, "gca_shift_add_u: null pointer");
+  const int hh = h / 2, ww = w / 2, Pk = (hh + 1) * (ww + 1);
+  TCV_REQUIRE(n > 0 && hh > 0 && ww > 0 && ld % 2 == 0 && ld >= Pk && lda >= hh * ww, "gca_shift_add_u: bad geometry");
+  gca_shift_add_u_kernel<<<dim3(Pk, n), 256, 0, S(stream)>>>(A, n, hh, ww, lda, ld, reinterpret_cast<__nv_bfloat16*>(A2));
+  return launched("gca_shift_add_u_kernel");
+}
+
+int tcv_gca_shift_gather(const float* dA2, int n, int h, int w, int ld, int lda, float* dA, tcv_stream_t stream) {
+  TCV_REQUIRE(dA2 && dA, "gca_shift_gather: null pointer");
+  const int hh = h / 2, ww = w / 2;
+  TCV_REQUIRE(n > 0 && hh > 0 && ww > 0 && ld >= (hh + 1) * (ww + 1) && lda >= hh * ww, "gca_shift_gather: bad geometry");
+  gca_shift_gather_kernel<<<dim3(hh * ww, n), 256, 0, S(stream)>>>(dA2, hh, ww, ld, lda, dA);
+  return launched("gca_shift_gather_kernel");
+}
+
+int tcv_gca_unfold_parity_bwd(const void* dY, int n, int h, int w, void* dO2, tcv_stream_t stream) {
+  TCV_REQUIRE(dY && dO2, "gca_unfold_parity_bwd: null pointer");
+  TCV_REQUIRE(n > 0 && h % 2 == 0 && w % 2 == 0 && h >= 4 && w >= 4, "gca_unfold_parity_bwd: h,w must be even and >= 4");
+  const long long total = (long long)n * (h / 2 + 1) * (w / 2 + 1) * 4 * (T2_FC / 8);
+  gca_unfold_parity_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dY), n, h, w, reinterpret_cast<__nv_bfloat16*>(dO2));
+  return launched("gca_unfold_parity_bwd_kernel");
+}
+
+int tcv_gca_values_parity_bwd(const float* dF, int n, int h, int w, void* dfeat, tcv_stream_t stream) {
+  TCV_REQUIRE(dF && dfeat, "gca_values_parity_bwd: null pointer");
+  TCV_REQUIRE(n > 0 && h % 2 == 0 && w % 2 == 0 && h >= 4 && w >= 4, "gca_values_parity_bwd: h,w must be even and >= 4");
+  const long long total = (long long)n * h * w * (T2_FC / 4);
+  gca_values_parity_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(dF, n, h, w,
+                                                                                      reinterpret_cast<__nv_bfloat16*>(dfeat));
+  return launched("gca_values_parity_bwd_kernel");
+}
+
+int tcv_rowdot_f32(const float* A, const float* B, long long rows, int cols, long long ld, float* out, tcv_stream_t stream) {
+  TCV_REQUIRE(A && B && out && rows > 0 && cols > 0 && ld >= cols, "rowdot_f32: bad arguments");
+  rowdot_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, S(stream)>>>(A, B, rows, cols, ld, out);
+  return launched("rowdot_kernel");
+}
+
+}  // extern "C"
