@@ -61,6 +61,24 @@ def test_gca_forward_backward(tc, model):
     assert tc.check_gca(model)
 
 
+@pytest.mark.parametrize("form", ["shift_sum", "fold"])
+def test_gca_forward_backward_both_forms(tc, model, form, monkeypatch):
+    """The training GCA in the shift-sum form (csrc/gca_train2.cu; [Pk x 512 x Pk] value GEMMs, on the CTA-pair GEMM at
+    this size) and in the round-1 fold form against the oracle's autograd, at a size with a ragged key grid."""
+    from tcvom_b200 import train_engine
+    orig = train_engine.TrainEngine.__init__
+
+    def init(self, window):
+        orig(self, window)
+        self.gca_shift_sum_train = form == "shift_sum"
+    monkeypatch.setattr(train_engine.TrainEngine, "__init__", init)
+    getattr(model.NET, "_train_engines", {}).clear()
+    try:
+        assert tc.check_gca(model, hw=(40, 58))
+    finally:
+        getattr(model.NET, "_train_engines", {}).clear()
+
+
 def test_tam_forward_backward(tc, model):
     assert tc.check_tam(model)
 

@@ -197,14 +197,14 @@ def check_sn(model):
     return report("sn_power_iter", errs, 1e-4)
 
 
-def check_gca(model, bound=3e-3):
+def check_gca(model, bound=3e-3, hw=(8, 12)):
     net = model.NET
     eng = _train_engine_for(net, 7)
     eng.tape = []
     eng.dw.clear(); eng.dbias.clear(); eng.dbn.clear(); eng._arena_begin(); eng._nbt = []
     eng.spectral_norm_step(2, 2)
     p = "decoder.gca"
-    n, h, w = 2, 8, 12
+    n, (h, w) = 2, hw
     f = rnd((n, 128, h, w), 11)
     al = rnd((n, 128, h, w), 12)
     unk = (rnd((n, 1, h, w), 13) > 0.3).float()
