@@ -554,6 +554,12 @@ int tcv_gca_shift_add_u(const float* A, int n, int h, int w, int lda, int ld, vo
 int tcv_gca_shift_gather(const float* dA2, int n, int h, int w, int ld, int lda, float* dA, tcv_stream_t stream);
 int tcv_gca_unfold_parity_bwd(const void* dY, int n, int h, int w, void* dO2, tcv_stream_t stream);
 int tcv_gca_values_parity_bwd(const float* dF, int n, int h, int w, void* dfeat, tcv_stream_t stream);
+/* fused backward of tcv_gca_rowstats(normalise) + tcv_gca_shift_add on the padded key grid: A fp32 [n][P][ld] (probabilities,
+ * zeros at the pad keys), dA2 fp32 [n][Pk][ld] -> dS split-bf16 planes [2][n][P][ld] = A * (gather(dA2) - <A, gather(dA2)>) */
+int tcv_gca_softmax_bwd_grid(const float* A, const float* dA2, int n, int h, int w, int ld, void* dS, tcv_stream_t stream);
+/* tcv_gca_prep_bwd with the key gradient on the padded grid of tcv_gca_prep_grid: dKn_grid fp32 [n][Pk][576] */
+int tcv_gca_prep_bwd_grid(float* dQ, const float* dKn_grid, const float* Q, const float* mm, const float* scales, int n,
+                          int h, int w, void* dg, tcv_stream_t stream);
 int tcv_rowdot_f32(const float* A, const float* B, long long rows, int cols, long long ld, float* out, tcv_stream_t stream);
 
 /* ---- SyncBatchNorm statistic exchange over NVLink peer memory (train_ddp.py:273 nn.SyncBatchNorm; csrc/peer_reduce.cu).

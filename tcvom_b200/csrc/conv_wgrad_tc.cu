@@ -11,6 +11,8 @@
 //
 // One CTA = one (filter tap, 128x{64,128} tile of the (ci, co) plane, slice of the pixel tiles); 192 threads:
 // warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue (TMEM -> fp32 atomics into dw).
+#include <algorithm>
+
 #include "tc_common.cuh"
 
 namespace tcv {
@@ -35,6 +37,13 @@ struct WgParams {
   // MMA of N = tpg * cblk columns serves tpg taps.  An MN-major MMA costs ~100 cycles per K = 16 step almost
   // independently of N (measured), so the narrow layers want few, wide MMAs.
   int swap, tpg, ngroups;
+  // rows mode (3x3 unit-spaced taps, stride 1, both sides <= 32 channels): ONE MMA per K step serves all nine taps.
+  // A = dz of the three output rows that meet x row y (blocks b = 0..2: row y - (dy0 + b); the MMA's 4th block aliases
+  // the next buffer, its accumulator rows are never read), B = x row y at the three horizontal shifts (blocks c = 0..2:
+  // column + dx0 + c).  Per 64 pixels that is 6 boxes and 12 MMAs instead of 11 boxes and 24 MMAs in the two CTAs of the
+  // stacked-tap mode.  fold: an 8-channel x (the network input) is read through an overlapping tensor map whose
+  // "channels" are 3 neighbouring pixels x 8 channels, so one box holds all three horizontal shifts (nbx = 1).
+  int rows, fold, nbx, dy0, dx0, y_first, wtap3[9];
   uint32_t idesc;
   float* dw;
 };
@@ -57,7 +66,7 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
   const int WG_STAGES = p.stages;
   const int cblk = p.row_bytes / 2;                      // channels per block
   // wide: A = x (a_nblk blocks), B = dz (nblk blocks); stacked: A = dz (1 block), B = x boxes of tpg taps
-  const int nb_a = p.swap ? 1 : p.a_nblk, nb_b = p.swap ? p.tpg : p.nblk;
+  const int nb_a = p.rows ? 3 : (p.swap ? 1 : p.a_nblk), nb_b = p.rows ? p.nbx : (p.swap ? p.tpg : p.nblk);
   const int stage_bytes = 2 * (nb_a + nb_b) * WG_BLK;
   const uint32_t bar_base = smem_base + WG_STAGES * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -76,7 +85,7 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
   const int tile_begin = slice * p.tiles_per_slice;
   const int tile_end = min(tile_begin + p.tiles_per_slice, p.total_tiles);
   const int iters = tile_end - tile_begin;
-  const uint32_t ncols_used = (uint32_t)(cblk * (p.swap ? p.tpg : p.nblk));
+  const uint32_t ncols_used = (uint32_t)(cblk * nb_b);
   uint32_t ncols = 32;                                     // TMEM allocation: power of two >= columns used
   while (ncols < ncols_used) ncols <<= 1;
 
@@ -115,7 +124,18 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
         if (elect_one()) {
           const int zx = x0 * p.mul + p.ox, zy = y0 * p.mul + p.oy;   // dz (sub-sampled by mul for the deconv phases)
           const uint32_t bst = st + 2 * nb_a * WG_BLK;
-          if (p.swap) {
+          if (p.rows) {
+            mbar_expect_tx(full_bar(s), (uint32_t)stage_bytes);
+            const int xy = p.y_first + y0;                   // x row of this tile (tiles run over the rows of x)
+            for (int b = 0; b < 3; ++b) {
+              tma_load_4d(st + b * WG_BLK, &mapZ_hi, full_bar(s), 0, x0, xy - (p.dy0 + b), img);
+              tma_load_4d(st + (3 + b) * WG_BLK, &mapZ_lo, full_bar(s), 0, x0, xy - (p.dy0 + b), img);
+            }
+            for (int c = 0; c < nb_b; ++c) {
+              tma_load_4d(bst + c * WG_BLK, &mapX_hi, full_bar(s), 0, x0 + p.dx0 + c, xy, img);
+              tma_load_4d(bst + (nb_b + c) * WG_BLK, &mapX_lo, full_bar(s), 0, x0 + p.dx0 + c, xy, img);
+            }
+          } else if (p.swap) {
             mbar_expect_tx(full_bar(s), (uint32_t)(2 * (1 + nt_here) * WG_BLK));
             tma_load_4d(st, &mapZ_hi, full_bar(s), 0, zx, zy, img);
             tma_load_4d(st + WG_BLK, &mapZ_lo, full_bar(s), 0, zx, zy, img);
@@ -175,7 +195,24 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
       mbar_wait(accum_bar, 0);
       tc_fence_after();
       const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
-      if (p.swap) {
+      if (p.rows) {
+        // accumulator rows = (output row block b = this warp, output channel), columns = (horizontal shift, input channel)
+        if (q < 3) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < (int)ncols_used; c0 += 32) {
+            uint32_t v[32];
+            tc_ld32(taddr + c0, v);
+            if (lane >= p.dz_c) continue;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int c = p.fold ? (i >> 3) : (c0 >> 5), ci = p.fold ? (i & 7) : i;
+              const float f = __uint_as_float(v[i]);
+              if (c < 3 && ci < p.cin && f != 0.f)
+                atomicAdd(p.dw + ((long long)p.wtap3[q * 3 + c] * p.cin + ci) * p.dz_c + lane, f);
+            }
+          }
+        }
+      } else if (p.swap) {
         // rows = output channels (duplicates beyond the block are skipped), columns = (tap of the group, input channel)
         const bool row_ok = r < cblk && r < p.dz_c;
 #pragma unroll 1
@@ -215,10 +252,14 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
   }
 }
 
+// c_mem / w_mem: the channels and width of the tensor in memory when they differ from the extents (c, w) the map exposes
+// (fold mode: a pixel of the map is 3 neighbouring 8-channel pixels, pixel stride still 8 channels)
 static int make_nhwc_map(CUtensorMap* m, const __nv_bfloat16* base, int c, int w, int h, int n, int tw, int th, int trav,
-                         int cblk) {
+                         int cblk, int c_mem = 0, int w_mem = 0) {
+  if (c_mem == 0) c_mem = c;
+  if (w_mem == 0) w_mem = w;
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-  cuuint64_t str[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint64_t str[3] = {(cuuint64_t)c_mem * 2, (cuuint64_t)w_mem * c_mem * 2, (cuuint64_t)h * w_mem * c_mem * 2};
   cuuint32_t box[4] = {(cuuint32_t)cblk, (cuuint32_t)(tw * trav), (cuuint32_t)(th * trav), 1};
   return make_map(m, base, 4, dims, str, box, /*bk: 64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B*/ cblk, false, trav);
 }
@@ -272,7 +313,36 @@ int conv2d_wgrad_tc(const tcv_conv_desc& d, const __nv_bfloat16* dz, long long d
     mn = 1;
     p.idesc = (p.idesc & ~(0x3Fu << 17)) | ((uint32_t)((p.tpg * cblk) >> 3) << 17);
   }
+  // rows mode: nine unit-spaced taps of a stride-1 narrow layer in one MMA (see WgParams)
+  int x_w = d.iw, x_c = d.cin;                 // geometry of the x tensor map (fold: overlapping 24-"channel" pixels)
+  if (narrow && d.stride == 1 && p.mul == 1 && p.oy == 0 && p.ox == 0 && d.ntaps == 9 && !(g_debug_flags.load() & (1 << 20))) {
+    int dy0 = d.dy[0], dx0 = d.dx[0];
+    for (int t = 1; t < 9; ++t) { dy0 = std::min(dy0, d.dy[t]); dx0 = std::min(dx0, d.dx[t]); }
+    bool grid3 = true;
+    int seen = 0;
+    for (int t = 0; t < 9; ++t) {
+      const int b = d.dy[t] - dy0, c = d.dx[t] - dx0;
+      if (b < 0 || b > 2 || c < 0 || c > 2) { grid3 = false; break; }
+      seen |= 1 << (b * 3 + c);
+      p.wtap3[b * 3 + c] = d.wtap[t];
+    }
+    if (grid3 && seen == 0x1FF) {
+      p.rows = 1; p.swap = 0;
+      p.dy0 = dy0; p.dx0 = dx0;
+      p.y_first = std::max(0, dy0);
+      const int y_count = std::min(d.ih, d.gh + dy0 + 2) - p.y_first;
+      p.tiles_y = (y_count + p.TH - 1) / p.TH;
+      p.total_tiles = d.n * p.tiles_x * p.tiles_y;
+      p.fold = (d.cin == 8 && dx0 >= 0) ? 1 : 0;
+      p.nbx = p.fold ? 1 : 3;
+      if (p.fold) { x_w = d.iw - 2; x_c = 24; }
+      p.idesc = (p.idesc & ~(0x3Fu << 17)) | ((uint32_t)((p.nbx * cblk) >> 3) << 17);
+      grid_x = 1;
+      mn = 1;
+    }
+  }
   int slices = (4 * 148 + grid_x * mn - 1) / (grid_x * mn);
+  if (p.rows) slices = 148;                    // 48 KB stages: one resident CTA per SM
   const int max_slices = (p.total_tiles + 3) / 4;          // at least 4 pixel tiles (256 pixels) per CTA
   if (slices > max_slices) slices = max_slices;
   if (slices < 1) slices = 1;
@@ -281,12 +351,12 @@ int conv2d_wgrad_tc(const tcv_conv_desc& d, const __nv_bfloat16* dz, long long d
 
   CUtensorMap mX_hi, mX_lo, mZ_hi, mZ_lo;
   const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(d.x);
-  int rc = make_nhwc_map(&mX_hi, x, d.cin, d.iw, d.ih, d.n, p.TW, p.TH, d.stride, cblk);
+  int rc = make_nhwc_map(&mX_hi, x, x_c, x_w, d.ih, d.n, p.TW, p.TH, d.stride, cblk, d.cin, d.iw);
   if (rc) return rc;
-  if ((rc = make_nhwc_map(&mX_lo, x + d.x_plane, d.cin, d.iw, d.ih, d.n, p.TW, p.TH, d.stride, cblk))) return rc;
+  if ((rc = make_nhwc_map(&mX_lo, x + d.x_plane, x_c, x_w, d.ih, d.n, p.TW, p.TH, d.stride, cblk, d.cin, d.iw))) return rc;
   if ((rc = make_nhwc_map(&mZ_hi, dz, dz_c, d.ow, d.oh, d.n, p.TW, p.TH, p.mul, cblk))) return rc;
   if ((rc = make_nhwc_map(&mZ_lo, dz + dz_plane, dz_c, d.ow, d.oh, d.n, p.TW, p.TH, p.mul, cblk))) return rc;
-  const int stage_bytes = 2 * (p.swap ? 1 + p.tpg : p.a_nblk + p.nblk) * WG_KT * p.row_bytes;
+  const int stage_bytes = 2 * (p.rows ? 3 + p.nbx : (p.swap ? 1 + p.tpg : p.a_nblk + p.nblk)) * WG_KT * p.row_bytes;
   p.stages = WG_SMEM_BUDGET / stage_bytes;
   if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
   const int smem = p.stages * stage_bytes + 1024 + 256;

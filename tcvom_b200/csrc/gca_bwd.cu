@@ -187,13 +187,16 @@ __global__ void gca_values_bwd_kernel(const float* __restrict__ dV, int n, int h
 
 // dQ[p] += d(Kn)/d(Q) applied to dKn[p]; one warp per patch (576 = 18 per lane)
 __global__ void gca_qgrad_kernel(float* __restrict__ dQ, const float* __restrict__ dKn, const float* __restrict__ Q,
-                                 const float* __restrict__ mm, const float* __restrict__ scales, int P, long long rows) {
+                                 const float* __restrict__ mm, const float* __restrict__ scales, int P, long long rows,
+                                 int ww, int Pk) {
   const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
   const int img = (int)(r / P);
   const float* q = Q + r * QD;
-  const float* dk = dKn + r * QD;
+  // ww > 0: dKn lives on the padded (hh+1) x (ww+1) key grid of the shift-sum form (rows py*(ww+1) + px, Pk per image)
+  const int pl = (int)(r - (long long)img * P);
+  const float* dk = dKn + (ww > 0 ? (long long)img * Pk + (pl / ww) * (ww + 1) + pl % ww : r) * QD;
   float qv[18], dv[18], ss = 0.f, qd = 0.f;
 #pragma unroll
   for (int j = 0; j < 18; ++j) {
@@ -313,19 +316,30 @@ int tcv_gca_values_bwd(const float* dV, int n, int h, int w, void* dfeat, tcv_st
   return launched("gca_values_bwd_kernel");
 }
 
-int tcv_gca_prep_bwd(float* dQ, const float* dKn, const float* Q, const float* mm, const float* scales, int n,
-                     int h, int w, void* dg, tcv_stream_t stream) {
+static int gca_prep_bwd_impl(float* dQ, const float* dKn, const float* Q, const float* mm, const float* scales, int n,
+                             int h, int w, void* dg, int key_grid, tcv_stream_t stream) {
   TCV_REQUIRE(dQ && dKn && Q && mm && scales && dg, "gca_prep_bwd: null pointer");
   TCV_REQUIRE(h % 2 == 0 && w % 2 == 0 && h >= 8 && w >= 8, "gca_prep_bwd: h,w must be even and >= 8");
   const int hh = h / 2, ww = w / 2, P = hh * ww;
   const long long rows = (long long)n * P;
-  gca_qgrad_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, S(stream)>>>(dQ, dKn, Q, mm, scales, P, rows);
+  gca_qgrad_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, S(stream)>>>(dQ, dKn, Q, mm, scales, P, rows,
+                                                                              key_grid ? ww : 0, (hh + 1) * (ww + 1));
   int rc = launched("gca_qgrad_kernel");
   if (rc) return rc;
   const long long total = rows * (GC / 4);
   gca_patch_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(dQ, n, hh, ww,
                                                                               reinterpret_cast<__nv_bfloat16*>(dg));
   return launched("gca_patch_bwd_kernel");
+}
+
+int tcv_gca_prep_bwd(float* dQ, const float* dKn, const float* Q, const float* mm, const float* scales, int n,
+                     int h, int w, void* dg, tcv_stream_t stream) {
+  return gca_prep_bwd_impl(dQ, dKn, Q, mm, scales, n, h, w, dg, 0, stream);
+}
+
+int tcv_gca_prep_bwd_grid(float* dQ, const float* dKn_grid, const float* Q, const float* mm, const float* scales, int n,
+                          int h, int w, void* dg, tcv_stream_t stream) {
+  return gca_prep_bwd_impl(dQ, dKn_grid, Q, mm, scales, n, h, w, dg, 1, stream);
 }
 
 }  // extern "C"

@@ -554,12 +554,12 @@ class TrainEngine(GcaVmnEngine):
         mm = torch.empty((n, P), dtype=f32, device=dev)
         scales = torch.empty((n, 2), dtype=f32, device=dev)
         O = torch.empty((n, P, 2048), dtype=f32, device=dev)
+        if self.use_tc_attn and self.gca_shift_sum_train:
+            return self._gca_shift_sum(p, feat, g, unknown, mm, scales)
         Q = torch.empty((2, n, P, 576), dtype=torch.bfloat16, device=dev)
         Kn = torch.empty_like(Q)
         self._call("tcv_gca_prep", ga.ptr, unknown.data_ptr(), n, h, w, Q.data_ptr(), Kn.data_ptr(), mm.data_ptr(),
                    scales.data_ptr(), 2)
-        if self.use_tc_attn and self.gca_shift_sum_train:
-            return self._gca_shift_sum(p, feat, g, unknown, Q, Kn, mm, scales)
         Vt = torch.empty((2, n, 2048, P_pad), dtype=torch.bfloat16, device=dev)
         self._call("tcv_gca_values", fa.ptr, n, h, w, Vt.data_ptr(), 2)
         Sm = torch.empty((n, P, P_pad), dtype=f32, device=dev)
@@ -660,13 +660,14 @@ class TrainEngine(GcaVmnEngine):
         self.last_gca_scales = scales
         return self.conv_bn(Y, _k(p, "W.0"), _k(p, "W.1"), res1=feat)
 
-    def _gca_shift_sum(self, p: str, feat: TAct, g: TAct, unknown: torch.Tensor, Q: torch.Tensor, Kn: torch.Tensor,
-                       mm: torch.Tensor, scales: torch.Tensor) -> TAct:
-        """Aggregation and its backward in the shift-sum form (csrc/gca_train2.cu): with A2[m][p'] = sum_a A[m-a][p'-a] on
-        the (hh+1) x (ww+1) key grid, fold(A.V)/4 = unfold_parity(A2.F), so the value GEMM and its two backward GEMMs are
-        [Pk x 512 x Pk] instead of [P x 2048 x P].  The scores side (Q.Kn^T, softmax, dS, dQ, dKn) keeps the unpadded grid.
-        Reference: GCA/ops.py:112-118,204 (the conv_transpose2d aggregation) and its autograd."""
-        fa = feat.a
+    def _gca_shift_sum(self, p: str, feat: TAct, g: TAct, unknown: torch.Tensor, mm: torch.Tensor,
+                       scales: torch.Tensor) -> TAct:
+        """Attention and its backward in the shift-sum form on the padded (hh+1) x (ww+1) key grid -- the same forward
+        kernels as the inference engine (engine.py:_gca_shift_sum) plus csrc/gca_train2.cu: with
+        A2[m][p'] = sum_a A[m-a][p'-a], fold(A.V)/4 = unfold_parity(A2.F), so the value GEMM and its two backward GEMMs are
+        [Pk x 512 x Pk] instead of [P x 2048 x P], and shift-add / gather are linear column offsets on the grid.
+        Reference: GCA/ops.py:106-229 (scores, masked softmax, conv_transpose2d aggregation) and its autograd."""
+        fa, ga = feat.a, g.a
         n, h, w = fa.n, fa.h, fa.w
         hh, ww = h // 2, w // 2
         P = hh * ww
@@ -685,18 +686,23 @@ class TrainEngine(GcaVmnEngine):
             self._call("tcv_gemm_tn_tc", A_.data_ptr(), n * a_rows * K_, B_.data_ptr(), n * b_rows * K_, C_.data_ptr(),
                        a_rows, b_rows, K_, ldc, a_rows * ldc, n, 3, 0, 0)
 
-        A = torch.empty((n, P, P_pad), dtype=f32, device=dev)                 # logits, then probabilities (kept for backward)
-        gemm_tc(Q, P, Kn, P, 576, A, P_pad)
-        self._call("tcv_gca_softmax", A.data_ptr(), mm.data_ptr(), n, P, P_pad, None, 0)
+        Q = torch.empty((2, n, P, 576), dtype=bf16, device=dev)
+        Kn = torch.empty((2, n, Pk, 576), dtype=bf16, device=dev)       # zero rows at the pad keys
+        self._call("tcv_gca_prep_grid", ga.ptr, unknown.data_ptr(), n, h, w, Q.data_ptr(), Kn.data_ptr(), mm.data_ptr(),
+                   scales.data_ptr())
+        A = torch.empty((n, P, ld), dtype=f32, device=dev)              # logits, then probabilities (kept for backward)
+        gemm_tc(Q, P, Kn, Pk, 576, A, ld)
+        stats = torch.empty((n, P, 2), dtype=f32, device=dev)
+        self._call("tcv_gca_rowstats", A.data_ptr(), mm.data_ptr(), n, h, w, ld, stats.data_ptr(), 1)
         A2 = torch.empty((2, n, Pk, ld), dtype=bf16, device=dev)
-        self._call("tcv_gca_shift_add_u", A.data_ptr(), n, h, w, P_pad, ld, A2.data_ptr())
+        self._call("tcv_gca_shift_add", A.data_ptr(), n, h, w, ld, A2.data_ptr())
         Ft = torch.empty((2, n, 512, ld), dtype=bf16, device=dev)
         self._call("tcv_gca_values_parity", fa.ptr, n, h, w, ld, Ft.data_ptr())
         O2 = torch.empty((n, Pk, 512), dtype=f32, device=dev)
         gemm_tc(A2, Pk, Ft, 512, ld, O2, 512)
         Ya = self._act(n, h, w, 128)
         self._call("tcv_gca_unfold_parity", O2.data_ptr(), n, h, w, Ya.ptr)
-        del O2
+        del O2, stats
         Y = TAct(Ya, feat.groups)
 
         def backward():
@@ -708,14 +714,10 @@ class TrainEngine(GcaVmnEngine):
             # dA2[m,p'] = sum_d dO2[m,d] F[p',d]
             dA2 = torch.empty((n, Pk, ld), dtype=f32, device=dev)
             gemm_tc(dO2, Pk, transpose(Ft, 512, Pk, ld, 512), Pk, 512, dA2, ld)
-            dA = torch.empty((n, P, P_pad), dtype=f32, device=dev)
-            self._call("tcv_gca_shift_gather", dA2.data_ptr(), n, h, w, ld, P_pad, dA.data_ptr())
+            # dS = A * (gather(dA2) - <A, gather(dA2)>): gather, row dot and softmax backward in one kernel
+            dS_s = torch.empty((2, n, P, ld), dtype=bf16, device=dev)
+            self._call("tcv_gca_softmax_bwd_grid", A.data_ptr(), dA2.data_ptr(), n, h, w, ld, dS_s.data_ptr())
             del dA2
-            delta = torch.empty((n, P), dtype=f32, device=dev)
-            self._call("tcv_rowdot_f32", A.data_ptr(), dA.data_ptr(), n * P, P, P_pad, delta.data_ptr())
-            dS_s = torch.empty((2, n, P, P_pad), dtype=bf16, device=dev)
-            self._call("tcv_gca_softmax_bwd", A.data_ptr(), dA.data_ptr(), delta.data_ptr(), n, P, P_pad, dS_s.data_ptr())
-            del dA
             if feat.needs_grad:
                 # dF[p',d] = sum_m A2[m,p'] dO2[m,d]
                 dF = torch.empty((n, Pk, 512), dtype=f32, device=dev)
@@ -726,11 +728,12 @@ class TrainEngine(GcaVmnEngine):
             Q32 = torch.empty((n, P, 576), dtype=f32, device=dev)
             self._call("tcv_split_to_f32", Q.data_ptr(), n * P * 576, n * P * 576, Q32.data_ptr())
             dQ = torch.empty((n, P, 576), dtype=f32, device=dev)
-            dKn = torch.empty((n, P, 576), dtype=f32, device=dev)
-            gemm_tc(dS_s, P, transpose(Kn, P, 576, 576, P_pad), 576, P_pad, dQ, 576)
-            gemm_tc(transpose(dS_s, P, P, P_pad, P_pad), P, transpose(Q, P, 576, 576, P_pad), 576, P_pad, dKn, 576)
+            dKn = torch.empty((n, Pk, 576), dtype=f32, device=dev)
+            # dQ[q,c] = sum_p' dS[q,p'] Kn[p',c] ; dKn[p',c] = sum_q dS[q,p'] Q[q,c]
+            gemm_tc(dS_s, P, transpose(Kn, Pk, 576, 576, ld), 576, ld, dQ, 576)
+            gemm_tc(transpose(dS_s, P, Pk, ld, P_pad), Pk, transpose(Q, P, 576, 576, P_pad), 576, P_pad, dKn, 576)
             dg = self._act(n, h // 2, w // 2, 64)
-            self._call("tcv_gca_prep_bwd", dQ.data_ptr(), dKn.data_ptr(), Q32.data_ptr(), mm.data_ptr(),
+            self._call("tcv_gca_prep_bwd_grid", dQ.data_ptr(), dKn.data_ptr(), Q32.data_ptr(), mm.data_ptr(),
                        scales.data_ptr(), n, h, w, dg.ptr)
             self._acc(g, dg, True)
             Y.g = None

@@ -58,6 +58,22 @@ def test_conv_cta_pair_kernel(cin, cout, h, w, n, kind):
     _tc().case_conv(cin, cout, h, w, n, kind, False, 4)
 
 
+@pytest.mark.parametrize("cin,cout,h,w,n,prepad,flags,perm", [
+    (32, 32, 40, 72, 2, False, 0, False),        # rows mode (one MMA = nine taps), ragged 64-pixel tiles
+    (32, 32, 40, 72, 2, True, 0, False),         # pre-padded x (reflect layers): taps 0..2
+    (8, 32, 24, 136, 2, True, 0, False),         # fold: 3 pixels x 8 channels per box row
+    (8, 32, 24, 136, 2, False, 0, True),         # 8 channels, zero padding: rows mode without the fold, shuffled taps
+    (32, 8, 18, 40, 3, False, 0, True),          # 8 output channels, 32 x 2 tiles
+    (16, 32, 20, 24, 1, True, 0, False),         # 16 x 4 tiles
+    (32, 32, 40, 72, 2, False, 1 << 20, False),  # the stacked-tap mode the rows mode replaces
+    (64, 64, 20, 72, 2, False, 0, False),        # stacked taps, 64 channels
+    (128, 256, 12, 40, 2, False, 0, False),      # wide layers: one CTA per tap and 128 x 128 tile
+])
+def test_wgrad_nhwc_tc(cin, cout, h, w, n, prepad, flags, perm):
+    """Weight gradient straight from the NHWC activations (conv_wgrad_tc.cu) against torch fp64 autograd."""
+    _tc().case_wgrad(cin, cout, h, w, n, prepad, flags, perm)
+
+
 def test_conv_kernel_generation_switch():
     """tcv_set_conv_tc_version selects the kernel generation; all generations agree."""
     from tcvom_b200 import _cabi

@@ -79,6 +79,58 @@ def conv_ref_fp64(x, wf, taps, wt, stride, gh, gw, oh, ow, mul, offs, s1, b1, re
     return out, (oy, ox)
 
 
+def case_wgrad(cin, cout, h, w, n, prepad=False, flags=0, perm=False):
+    """tcv_conv2d_wgrad_nhwc_tc (3x3, stride 1) against torch fp64 autograd.  prepad: x carries its own 1-pixel border and
+    the taps are (0..2, 0..2) (the reflect-padded layers); perm: the nine taps in a shuffled order / shuffled weight slots."""
+    import torch
+    import torch.nn.functional as F
+    from tcvom_b200 import _cabi
+    from tcvom_b200._cabi import ConvDesc
+    L = _cabi.lib()
+    torch.manual_seed(3)
+    dev = "cuda"
+    st = torch.cuda.current_stream().cuda_stream
+    ih, iw = (h + 2, w + 2) if prepad else (h, w)
+    x = split(torch.randn(n, ih, iw, cin, device=dev))
+    dz = split(torch.randn(n, h, w, cout, device=dev))
+    off = 0 if prepad else -1
+    taps = [(ky + off, kx + off) for ky in range(3) for kx in range(3)]
+    order = list(range(9))
+    slots = list(range(9))
+    if perm:
+        order = [4, 0, 8, 2, 6, 1, 3, 5, 7]
+        slots = [8, 7, 6, 5, 4, 3, 2, 1, 0]
+    d = ConvDesc()
+    d.x, d.x_plane, d.x_img_stride = x.data_ptr(), x[0].numel(), ih * iw * cin
+    d.n, d.ih, d.iw, d.cin = n, ih, iw, cin
+    d.ntaps = 9
+    for i, t in enumerate(order):
+        d.dy[i], d.dx[i], d.wtap[i] = taps[t][0], taps[t][1], slots[t]
+    d.stride, d.pad_mode = 1, 0
+    d.oh, d.ow, d.cout, d.gh, d.gw = h, w, cout, h, w
+    d.oy_mul, d.oy_off, d.ox_mul, d.ox_off = 1, 0, 1, 0
+    dw = torch.zeros((9, cin, cout), device=dev)
+    L.tcv_set_debug_flags(flags)
+    try:
+        _cabi.check(L.tcv_conv2d_wgrad_nhwc_tc(C.byref(d), dz.data_ptr(), dz[0].numel(), cout, dw.data_ptr(), st), "wgrad_nhwc")
+        torch.cuda.synchronize()
+    finally:
+        L.tcv_set_debug_flags(0)
+    x64 = (x[0].double() + x[1].double()).permute(0, 3, 1, 2)
+    z64 = (dz[0].double() + dz[1].double()).permute(0, 3, 1, 2)
+    wz = torch.zeros((cout, cin, 3, 3), device=dev, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(x64, wz, None, 1, 0 if prepad else 1)
+    (gw,) = torch.autograd.grad(y, wz, z64)
+    ref = gw.permute(2, 3, 1, 0).reshape(9, cin, cout)          # [tap][ci][co]
+    got = torch.empty_like(ref)
+    for t in range(9):
+        got[t] = dw[slots[t]].double()
+    err = float((got - ref).abs().max() / ref.abs().max())
+    print(f"wgrad cin={cin} cout={cout} {h}x{w} n={n} prepad={prepad} flags={flags} perm={perm}: rel err {err:.2e}")
+    assert err < 1e-4, err
+    return err
+
+
 def case_conv(cin, cout, h, w, n, kind, f32_side=True, expect_path=None):
     import torch
     from tcvom_b200 import _cabi
