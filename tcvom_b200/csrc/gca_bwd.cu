@@ -116,33 +116,53 @@ __global__ void gca_softmax_bwd_kernel(const float* __restrict__ A, float* __res
   if (dS_split) store1(dS_split + i, rows * P_pad, v);
 }
 
-// out[b][c][r] = in[b][r][c] for both planes of a split-bf16 matrix (raw 16-bit moves), r >= rows zero-filled up to ld_out
+// out[b][c][r] = in[b][r][c] for both planes of a split-bf16 matrix (raw 16-bit moves), r >= rows zero-filled up to ld_out.
+// 64 x 64 tiles, 8-byte global accesses on both sides (rows of 128 B); blockIdx.z = batch * 2 + plane.
 __global__ void __launch_bounds__(256) transpose_planes_kernel(const uint16_t* __restrict__ in, long long in_plane,
                                                                int rows, int cols, long long ld_in, long long bs_in,
                                                                uint16_t* __restrict__ out, long long out_plane,
                                                                long long ld_out, long long bs_out) {
-  __shared__ uint16_t tile[2][32][34];
-  const int b = blockIdx.z;
-  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int rr = ty; rr < 32; rr += 8) {
-    const int r = r0 + rr, c = c0 + tx;
-    uint16_t a = 0, l = 0;
-    if (r < rows && c < cols) {
-      const long long src = (long long)b * bs_in + (long long)r * ld_in + c;
-      a = in[src];
-      l = in[src + in_plane];
+  __shared__ uint16_t tile[64][66];       // pitch 33 words: a column read of the 64 rows is two-way bank-conflicted at worst
+  const int b = blockIdx.z >> 1, pl = blockIdx.z & 1;
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const uint16_t* src = in + (long long)pl * in_plane + (long long)b * bs_in;
+  uint16_t* dst = out + (long long)pl * out_plane + (long long)b * bs_out;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;       // 16 threads x 4 elements per 64-element row
+  const bool vec_in = (ld_in & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 7) == 0);
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const int rr = pass * 16 + ty, r = r0 + rr, c = c0 + tx * 4;
+    uint16_t v[4] = {0, 0, 0, 0};
+    if (r < rows) {
+      const uint16_t* p = src + (long long)r * ld_in + c;
+      if (vec_in && c + 3 < cols) {
+        const uint2 t = *reinterpret_cast<const uint2*>(p);
+        v[0] = (uint16_t)(t.x & 0xFFFF); v[1] = (uint16_t)(t.x >> 16); v[2] = (uint16_t)(t.y & 0xFFFF); v[3] = (uint16_t)(t.y >> 16);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (c + e < cols) v[e] = p[e];
+      }
     }
-    tile[0][rr][tx] = a;
-    tile[1][rr][tx] = l;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) tile[rr][tx * 4 + e] = v[e];
   }
   __syncthreads();
-  for (int cc = ty; cc < 32; cc += 8) {
-    const int c = c0 + cc, r = r0 + tx;
-    if (c < cols && r < ld_out) {
-      const long long dst = (long long)b * bs_out + (long long)c * ld_out + r;
-      out[dst] = tile[0][tx][cc];
-      out[dst + out_plane] = tile[1][tx][cc];
+  const bool vec_out = (ld_out & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0);
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const int cc = pass * 16 + ty, c = c0 + cc, r = r0 + tx * 4;
+    if (c >= cols || r >= ld_out) continue;
+    uint16_t v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = tile[tx * 4 + e][cc];
+    uint16_t* p = dst + (long long)c * ld_out + r;
+    if (vec_out && r + 3 < ld_out) {
+      *reinterpret_cast<uint2*>(p) = make_uint2((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (r + e < ld_out) p[e] = v[e];
     }
   }
 }
@@ -281,7 +301,7 @@ int tcv_transpose_planes(const void* in, long long in_plane, int rows, int cols,
                          tcv_stream_t stream) {
   TCV_REQUIRE(in && out && rows > 0 && cols > 0 && ld_in >= cols && ld_out >= rows && batch > 0,
               "transpose_planes: bad arguments");
-  dim3 grid((cols + 31) / 32, (unsigned)((ld_out + 31) / 32), batch);
+  dim3 grid((cols + 63) / 64, (unsigned)((ld_out + 63) / 64), batch * 2);
   transpose_planes_kernel<<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const uint16_t*>(in), in_plane, rows, cols, ld_in,
                                                       bs_in, reinterpret_cast<uint16_t*>(out), out_plane, ld_out, bs_out);
   return launched("transpose_planes_kernel");

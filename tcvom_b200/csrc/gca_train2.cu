@@ -134,10 +134,9 @@ __global__ void gca_values_parity_bwd_kernel(const float* __restrict__ dF, int n
 __global__ void __launch_bounds__(256) gca_softmax_bwd_grid_kernel(const float* __restrict__ A, const float* __restrict__ dA2,
                                                                    int n, int hh, int ww, int ld,
                                                                    __nv_bfloat16* __restrict__ dS) {
-  extern __shared__ float t2_smem[];   // g[ld], a[ld]
+  extern __shared__ float t2_smem[];   // g[ld]
   __shared__ float red[8];
   float* gs = t2_smem;
-  float* as = t2_smem + ld;
   const int P = hh * ww, ww1 = ww + 1, Pk = (hh + 1) * ww1;
   const int q = blockIdx.x, img = blockIdx.y;
   const int qy = q / ww, qx = q - qy * ww;
@@ -150,42 +149,41 @@ __global__ void __launch_bounds__(256) gca_softmax_bwd_grid_kernel(const float* 
   }
   const float* arow = A + ((long long)img * P + q) * ld;
   float dot = 0.f;
+  // the loads of an iteration do not depend on each other (a zero probability masks its column afterwards)
+#pragma unroll 2
   for (int j = threadIdx.x * 4; j < ld; j += 1024) {
-    const float4 av = *reinterpret_cast<const float4*>(arow + j);
+    const float4 av = __ldg(reinterpret_cast<const float4*>(arow + j));
     float g[4] = {0.f, 0.f, 0.f, 0.f};
-    if (av.x != 0.f || av.y != 0.f || av.z != 0.f || av.w != 0.f) {
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const float* src = rows[a] + j;
-        if (j + 4 + sh[a] <= ld) {
-          const int al = sh[a] & 3;
-          if (al == 0) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(src));
-            g[0] += t.x; g[1] += t.y; g[2] += t.z; g[3] += t.w;
-          } else if (al == 2) {
-            const float2 t0 = __ldg(reinterpret_cast<const float2*>(src)), t1 = __ldg(reinterpret_cast<const float2*>(src + 2));
-            g[0] += t0.x; g[1] += t0.y; g[2] += t1.x; g[3] += t1.y;
-          } else {
-            const float t0 = __ldg(src);
-            const float2 t1 = __ldg(reinterpret_cast<const float2*>(src + 1));
-            const float t3 = __ldg(src + 3);
-            g[0] += t0; g[1] += t1.x; g[2] += t1.y; g[3] += t3;
-          }
+    for (int a = 0; a < 4; ++a) {
+      const float* src = rows[a] + j;
+      if (j + 4 + sh[a] <= ld) {
+        const int al = sh[a] & 3;
+        if (al == 0) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+          g[0] += t.x; g[1] += t.y; g[2] += t.z; g[3] += t.w;
+        } else if (al == 2) {
+          const float2 t0 = __ldg(reinterpret_cast<const float2*>(src)), t1 = __ldg(reinterpret_cast<const float2*>(src + 2));
+          g[0] += t0.x; g[1] += t0.y; g[2] += t1.x; g[3] += t1.y;
         } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (j + e + sh[a] < ld) g[e] += __ldg(src + e);
+          const float t0 = __ldg(src);
+          const float2 t1 = __ldg(reinterpret_cast<const float2*>(src + 1));
+          const float t3 = __ldg(src + 3);
+          g[0] += t0; g[1] += t1.x; g[2] += t1.y; g[3] += t3;
         }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (j + e + sh[a] < ld) g[e] += __ldg(src + e);
       }
     }
     const float a4[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      if (a4[e] == 0.f) g[e] = 0.f;            // never propagate an unwritten dA2 column
+      if (a4[e] == 0.f) g[e] = 0.f;            // pad keys and columns >= Pk: dA2 there is unwritten memory
       dot = fmaf(a4[e], g[e], dot);
     }
     *reinterpret_cast<float4*>(gs + j) = make_float4(g[0], g[1], g[2], g[3]);
-    *reinterpret_cast<float4*>(as + j) = av;
   }
   dot = warp_sum(dot);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
@@ -195,9 +193,10 @@ __global__ void __launch_bounds__(256) gca_softmax_bwd_grid_kernel(const float* 
   for (int k = 0; k < 8; ++k) delta += red[k];
   const long long plane = (long long)n * P * ld;
   __nv_bfloat16* out = dS + ((long long)img * P + q) * ld;
-  for (int j = threadIdx.x * 4; j < ld; j += 1024) {   // each thread re-reads only what it wrote itself
+#pragma unroll 2
+  for (int j = threadIdx.x * 4; j < ld; j += 1024) {   // each thread re-reads only what it wrote itself; A from L1/L2
     const float4 g = *reinterpret_cast<const float4*>(gs + j);
-    const float4 a = *reinterpret_cast<const float4*>(as + j);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(arow + j));
     uint32_t h0, l0, h1, l1;
     split2_bf16(a.x * (g.x - delta), a.y * (g.y - delta), h0, l0);
     split2_bf16(a.z * (g.z - delta), a.w * (g.w - delta), h1, l1);
@@ -263,7 +262,7 @@ int tcv_gca_softmax_bwd_grid(const float* A, const float* dA2, int n, int h, int
   TCV_REQUIRE(A && dA2 && dS, "gca_softmax_bwd_grid: null pointer");
   const int hh = h / 2, ww = w / 2;
   TCV_REQUIRE(n > 0 && hh > 0 && ww > 0 && ld % 4 == 0 && ld >= (hh + 1) * (ww + 1), "gca_softmax_bwd_grid: bad geometry");
-  const size_t smem = (size_t)ld * 2 * sizeof(float);
+  const size_t smem = (size_t)ld * sizeof(float);
   TCV_REQUIRE(smem <= 200 * 1024, "gca_softmax_bwd_grid: row of %d keys does not fit shared memory", ld);
   TCV_CUDA(cudaFuncSetAttribute(gca_softmax_bwd_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   gca_softmax_bwd_grid_kernel<<<dim3(hh * ww, n), 256, smem, S(stream)>>>(A, dA2, n, hh, ww, ld,
