@@ -46,6 +46,7 @@ typedef void* tcv_stream_t; /* cudaStream_t */
 #define TCV_ACT_LEAKY02 2
 #define TCV_ACT_TANH01 3 /* (tanh(x)+1)/2 -- VMN_GCA.py:47 */
 #define TCV_ACT_LEAKY001 4 /* nn.LeakyReLU() default slope 0.01 -- FBA/models.py:266-300 */
+#define TCV_ACT_CLAMP01 5  /* .clamp(0, 1) -- VMN_DIM.py:135 */
 
 #define TCV_PAD_ZERO 0
 #define TCV_PAD_REFLECT 1
@@ -542,6 +543,21 @@ int tcv_fba_fusion(const void* o8, const void* x16, long long x16_plane, long lo
 int tcv_postprocess_eval_fba(const float* pred, const void* imgs, const void* tris, int is_u8, const float* trimask,
                              int batch, int frames, int h, int w, float* alphas, float* Fs, float* Bs,
                              tcv_stream_t stream);
+
+/* =====================================================================================================
+ * DIM base network behind the TAM operator (models/VMN/VMN_DIM.py).  Convolutions
+ * (3x3 / 5x5 / 7x7 as chains of <= 3x3 tap groups of tcv_conv2d), eval BatchNorm, the TAM and the eval pre/post-
+ * processing reuse the entry points above; what DIM adds:
+ *   tcv_maxpool2_idx     VMN_DIM.py:14,20,28,36,44   nn.MaxPool2d((2,2), stride=2, return_indices=True): split-bf16 NHWC
+ *                        [n,h,w,c] -> pooled [n,h/2,w/2,c] + idx uint8 [n,h/2,w/2,c] = position of the FIRST maximum in
+ *                        the window in row-major order (ky*2 + kx), torch's tie rule
+ *   tcv_maxunpool2       VMN_DIM.py:82-96,113-131    nn.MaxUnpool2d((2,2), stride=2): [n,h/2,w/2,c] + idx -> [n,h,w,c], zeros
+ *                        everywhere but the recorded position
+ *   tcv_dim_fix_inputs   models/model.py:366-368,392 (TRIMAP_CHANNEL == 1): channel 3 of the 8-channel input tensor written
+ *                        by tcv_preprocess_eval := tri / 255, channels 4..7 := 0  (tris fp32 or uint8 [F,1,H,W]) */
+int tcv_maxpool2_idx(const void* x, int n, int h, int w, int c, void* y, uint8_t* idx, tcv_stream_t stream);
+int tcv_maxunpool2(const void* x, const uint8_t* idx, int n, int h, int w, int c, void* y, tcv_stream_t stream);
+int tcv_dim_fix_inputs(const void* tris, int is_u8, int frames, int h, int w, void* x8, tcv_stream_t stream);
 
 /* ---- training side of the shift-sum aggregation (csrc/gca_train2.cu; autograd of GCA/ops.py:112-118,204):
  *  shift_add_u:        A fp32 [n][P][lda] (softmax on the unpadded key grid) -> A2 split-bf16 planes [2][n][Pk][ld]

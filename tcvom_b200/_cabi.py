@@ -14,7 +14,7 @@ import threading
 # TCV_LIB: kernel A/B experiments only (a second build of the same sources with other tile constants)
 LIB_PATH = os.environ.get("TCV_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtcvom_b200.so")
 
-ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_TANH01, ACT_LEAKY001 = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_TANH01, ACT_LEAKY001, ACT_CLAMP01 = 0, 1, 2, 3, 4, 5
 PAD_ZERO, PAD_REFLECT = 0, 1
 MAX_TAPS = 16
 
@@ -123,6 +123,9 @@ SIGNATURES = {
     "tcv_pad_reflect1_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_tanh01_bwd": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_void_p]),
     "tcv_head_tanh01": (c_int, [c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p]),
+    "tcv_maxpool2_idx": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "tcv_maxunpool2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tcv_dim_fix_inputs": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_gca_shift_add_u": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_gca_shift_gather": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_gca_unfold_parity_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

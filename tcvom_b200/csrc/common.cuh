@@ -90,6 +90,9 @@ __device__ __forceinline__ void apply_act_n(float* f, int act) {
   } else if (act == TCV_ACT_LEAKY001) {
 #pragma unroll
     for (int j = 0; j < N; ++j) f[j] = f[j] > 0.f ? f[j] : 0.01f * f[j];
+  } else if (act == TCV_ACT_CLAMP01) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) f[j] = fminf(fmaxf(f[j], 0.f), 1.f);
   }
 }
 
@@ -133,6 +136,7 @@ __device__ __forceinline__ float apply_act(float t, int act) {
     case TCV_ACT_LEAKY02: return t > 0.f ? t : 0.2f * t;
     case TCV_ACT_TANH01: return (tanhf(t) + 1.0f) * 0.5f;
     case TCV_ACT_LEAKY001: return t > 0.f ? t : 0.01f * t;
+    case TCV_ACT_CLAMP01: return fminf(fmaxf(t, 0.f), 1.f);
     default: return t;
   }
 }

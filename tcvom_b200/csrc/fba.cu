@@ -236,7 +236,7 @@ int tcv_gn_apply(const void* x, long long x_plane, int n, long long pixels, int 
   TCV_REQUIRE(x && scale && shift && y, "gn_apply: null pointer");
   TCV_REQUIRE(n > 0 && pixels > 0 && c % 8 == 0 && y_c % 8 == 0 && y_off % 8 == 0 && y_off + c <= y_c,
               "gn_apply: bad dims");
-  TCV_REQUIRE(act >= TCV_ACT_NONE && act <= TCV_ACT_LEAKY001, "gn_apply: unknown activation");
+  TCV_REQUIRE(act >= TCV_ACT_NONE && act <= TCV_ACT_CLAMP01, "gn_apply: unknown activation");
   if (x_plane == 0) x_plane = (long long)n * pixels * c;
   if (res && res_plane == 0) res_plane = (long long)n * pixels * c;
   if (y_plane == 0) y_plane = (long long)n * pixels * y_c;
@@ -363,6 +363,24 @@ int tcv_fba_fusion(const void* o8, const void* x16, long long x16_plane, long lo
   if (x16_img_stride == 0) x16_img_stride = (long long)h * w * 16;
   FusionP p{CU16(o8), CU16(x16), x16_plane, x16_img_stride, n, h, w, pred};
   return launch_body<FusionP, fba_fusion_body>(p, (ll)n * h * w, S(stream), "fba_fusion_kernel");
+}
+
+int tcv_maxpool2_idx(const void* x, int n, int h, int w, int c, void* y, uint8_t* idx, tcv_stream_t stream) {
+  TCV_REQUIRE(x && y && idx && n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0 && c % 8 == 0, "maxpool2_idx: bad arguments");
+  Pool2P p{CU16(x), n, h, w, c, U16(y), idx};
+  return launch_body<Pool2P, maxpool2_idx_body>(p, (ll)n * (h / 2) * (w / 2) * (c / 8), S(stream), "maxpool2_idx_kernel");
+}
+
+int tcv_maxunpool2(const void* x, const uint8_t* idx, int n, int h, int w, int c, void* y, tcv_stream_t stream) {
+  TCV_REQUIRE(x && y && idx && n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0 && c % 8 == 0, "maxunpool2: bad arguments");
+  Unpool2P p{CU16(x), idx, n, h, w, c, U16(y)};
+  return launch_body<Unpool2P, maxunpool2_body>(p, (ll)n * h * w * (c / 8), S(stream), "maxunpool2_kernel");
+}
+
+int tcv_dim_fix_inputs(const void* tris, int is_u8, int frames, int h, int w, void* x8, tcv_stream_t stream) {
+  TCV_REQUIRE(tris && x8 && frames > 0 && h > 0 && w > 0, "dim_fix_inputs: bad arguments");
+  DimFixP p{tris, is_u8, (ll)frames * h * w, U16(x8)};
+  return launch_body<DimFixP, dim_fix_inputs_body>(p, p.pixels, S(stream), "dim_fix_inputs_kernel");
 }
 
 int tcv_space_to_depth2(const void* x, long long x_plane, int n, int h, int w, int c, void* y, tcv_stream_t stream) {

@@ -80,6 +80,7 @@ TCV_HD float act_fn(float t, int act) {
     case 2: return t > 0.f ? t : 0.2f * t;                 // TCV_ACT_LEAKY02
     case 3: return (tanhf(t) + 1.0f) * 0.5f;               // TCV_ACT_TANH01
     case 4: return t > 0.f ? t : 0.01f * t;                // TCV_ACT_LEAKY001
+    case 5: return t < 0.f ? 0.f : (t > 1.f ? 1.f : t);    // TCV_ACT_CLAMP01
     default: return t;
   }
 }
@@ -541,6 +542,91 @@ TCV_HD void s2d_pack_body(ll i, const S2dPackGenP& p) {
   if (ky >= 0 && ky < p.k && kx >= 0 && kx < p.k && c < p.cin_src && co < p.cout_src)
     v = p.src[((ll)(ky * p.k + kx) * p.cin_src + c) * p.cout_src + co];
   p.out[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------ DIM (VMN_DIM.py)
+struct Pool2P {
+  const uint16_t* x;  // dense [n, h, w, c]
+  int n, h, w, c;
+  uint16_t* y;        // dense [n, h/2, w/2, c]
+  uint8_t* idx;       // [n, h/2, w/2, c]: ky*2 + kx of the first maximum (torch scans the window row-major, keeps on ties)
+};
+// work item = 8 channels of one pooled pixel; total = n*(h/2)*(w/2)*c/8
+TCV_HD void maxpool2_idx_body(ll i, const Pool2P& p) {
+  const int cv = p.c / 8;
+  const int ch = (int)(i % cv) * 8;
+  ll t = i / cv;
+  const int oh = p.h / 2, ow = p.w / 2;
+  const int x = (int)(t % ow);
+  t /= ow;
+  const int y = (int)(t % oh);
+  const int img = (int)(t / oh);
+  const ll xplane = (ll)p.n * p.h * p.w * p.c, yplane = (ll)p.n * oh * ow * p.c;
+  float best[8];
+  int bi[8];
+  for (int k = 0; k < 4; ++k) {
+    const uint16_t* s = p.x + (((ll)img * p.h + 2 * y + (k >> 1)) * p.w + 2 * x + (k & 1)) * p.c + ch;
+    float f[8];
+    ld8(s, xplane, f);
+    for (int j = 0; j < 8; ++j)
+      if (k == 0 || f[j] > best[j] || (f[j] != f[j] && best[j] == best[j])) {   // torch: (val > max) || isnan(val)
+        best[j] = f[j];
+        bi[j] = k;
+      }
+  }
+  const ll o = (((ll)img * oh + y) * ow + x) * p.c + ch;
+  // the maximum is one of the stored values: copy its two planes instead of re-splitting (bit-exact pooling)
+  for (int j = 0; j < 8; ++j) {
+    const uint16_t* s = p.x + (((ll)img * p.h + 2 * y + (bi[j] >> 1)) * p.w + 2 * x + (bi[j] & 1)) * p.c + ch + j;
+    p.y[o + j] = s[0];
+    p.y[o + j + yplane] = s[xplane];
+    p.idx[o + j] = (uint8_t)bi[j];
+  }
+}
+
+struct Unpool2P {
+  const uint16_t* x;   // dense [n, h/2, w/2, c]
+  const uint8_t* idx;  // [n, h/2, w/2, c]
+  int n, h, w, c;      // OUTPUT size
+  uint16_t* y;         // dense [n, h, w, c]
+};
+// work item = 8 channels of one OUTPUT pixel; total = n*h*w*c/8
+TCV_HD void maxunpool2_body(ll i, const Unpool2P& p) {
+  const int cv = p.c / 8;
+  const int ch = (int)(i % cv) * 8;
+  ll t = i / cv;
+  const int x = (int)(t % p.w);
+  t /= p.w;
+  const int y = (int)(t % p.h);
+  const int img = (int)(t / p.h);
+  const int ih = p.h / 2, iw = p.w / 2;
+  const ll xplane = (ll)p.n * ih * iw * p.c, yplane = (ll)p.n * p.h * p.w * p.c;
+  const ll s = (((ll)img * ih + (y >> 1)) * iw + (x >> 1)) * p.c + ch;
+  const ll o = (((ll)img * p.h + y) * p.w + x) * p.c + ch;
+  const int me = (y & 1) * 2 + (x & 1);
+  for (int j = 0; j < 8; ++j) {
+    const bool hit = p.idx[s + j] == me;
+    p.y[o + j] = hit ? p.x[s + j] : (uint16_t)0;
+    p.y[o + j + yplane] = hit ? p.x[s + j + xplane] : (uint16_t)0;
+  }
+}
+
+struct DimFixP {
+  const void* tris;   // [F,1,H,W] fp32 or uint8
+  int is_u8;
+  ll pixels;          // F*H*W
+  uint16_t* x8;       // dense [F,H,W,8]
+};
+// work item = one pixel: channel 3 := tri/255 (models/model.py:368: tri.float() * IMG_SCALE), channels 4..7 := 0
+TCV_HD void dim_fix_inputs_body(ll i, const DimFixP& p) {
+  const float tv = p.is_u8 ? (float)((const uint8_t*)p.tris)[i] : ((const float*)p.tris)[i];
+  const ll plane = p.pixels * 8;
+  uint16_t* d = p.x8 + i * 8;
+  st1(d + 3, plane, tv * (1.0f / 255));
+  for (int k = 4; k < 8; ++k) {
+    d[k] = 0;
+    d[k + plane] = 0;
+  }
 }
 
 }  // namespace tcv_fba

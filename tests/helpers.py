@@ -49,3 +49,11 @@ def fixture_sd_fba():
         shapes = {k: tuple(s) for k, s in key_table_fba()["state_dict"]}
         _SD["fba"] = synthetic.fixture_state_dict_fba(shapes, 0)
     return _SD["fba"]
+
+
+def fixture_sd_dim():
+    """The seeded ``vmn_dim`` fixture checkpoint (113 keys / 134 M parameters, CPU fp32; regenerated, never committed)."""
+    if "dim" not in _SD:
+        from oracle.vmn_dim_oracle import fixture_sd_dim as make
+        _SD["dim"] = make()
+    return _SD["dim"]

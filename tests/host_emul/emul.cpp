@@ -808,6 +808,23 @@ int tcv_fba_fusion(const void* o8, const void* x16, long long x16_plane, long lo
   return run_body<FusionP, fba_fusion_body>(p, (ll)n * h * w);
 }
 
+int tcv_maxpool2_idx(const void* x, int n, int h, int w, int c, void* y, uint8_t* idx, tcv_stream_t) {
+  REQ(h % 2 == 0 && w % 2 == 0 && c % 8 == 0, "maxpool2_idx: dims");
+  Pool2P p{(const uint16_t*)x, n, h, w, c, (uint16_t*)y, idx};
+  return run_body<Pool2P, maxpool2_idx_body>(p, (ll)n * (h / 2) * (w / 2) * (c / 8));
+}
+
+int tcv_maxunpool2(const void* x, const uint8_t* idx, int n, int h, int w, int c, void* y, tcv_stream_t) {
+  REQ(h % 2 == 0 && w % 2 == 0 && c % 8 == 0, "maxunpool2: dims");
+  Unpool2P p{(const uint16_t*)x, idx, n, h, w, c, (uint16_t*)y};
+  return run_body<Unpool2P, maxunpool2_body>(p, (ll)n * h * w * (c / 8));
+}
+
+int tcv_dim_fix_inputs(const void* tris, int is_u8, int frames, int h, int w, void* x8, tcv_stream_t) {
+  DimFixP p{tris, is_u8, (ll)frames * h * w, (uint16_t*)x8};
+  return run_body<DimFixP, dim_fix_inputs_body>(p, p.pixels);
+}
+
 int tcv_space_to_depth2(const void* x, long long x_plane, int n, int h, int w, int c, void* y, tcv_stream_t) {
   REQ(h % 2 == 0 && w % 2 == 0 && c % 8 == 0, "space_to_depth2: dims");
   if (x_plane == 0) x_plane = (ll)n * h * w * c;

@@ -48,7 +48,7 @@ def test_get_vmn_models_error_behaviour():
     with pytest.raises(ValueError):
         tcvom_b200.get_VMN_models("nope", agg_window=7)   # VMN/__init__.py:26-27
     with pytest.raises(NotImplementedError):
-        tcvom_b200.get_VMN_models("vmn_dim", agg_window=7)
+        tcvom_b200.get_VMN_models("vmn_index", agg_window=7)
 
 
 def test_fba_state_dict_contract_matches_reference_layout():
