@@ -608,6 +608,7 @@ class EvalModel(nn.Module):
             plan.io["feat"] = out["feat"].buf
             if self.method == 'dim':
                 plan.io["pool_idx"] = out["pf"]["idxs"]          # max-pooling routing (tests follow it, see oracle/vmn_dim_oracle.py)
+                plan.io["x8"] = x8.buf
         finally:
             eng._rec = None
         eng.put_plan(key, plan)

@@ -100,12 +100,16 @@ def test_vmn_seam_equals_eval_model(model):
     model(imgs.cuda(), tris.cuda())
     plan = model._plan(1, 3, 64, 96, torch.device("cuda:0"), True)
     want = plan.io["pred"][:, 0].clone()
-    x4, trimask = O.eval_preprocess(imgs.float(), tris.float())
-    images = [x4[:, i:i + 1].cuda() for i in range(3)]
+    _, trimask = O.eval_preprocess(imgs.float(), tris.float())
+    # the network input exactly as EvalModel's plan holds it (a 1e-6 difference in the normalised image can re-route a
+    # near-tie of the max-pooling and move the matte by 1e-2 around it: this test is about the seam, not about rounding)
+    x8 = (plan.io["x8"][0].float() + plan.io["x8"][1].float())[..., :4].permute(0, 3, 1, 2).contiguous()   # [S,4,H,W]
+    assert float((x8.cpu() - O.eval_preprocess(imgs.float(), tris.float())[0][0]).abs().max()) < 3e-5
+    images = [x8[i][None, None].clone() for i in range(3)]
     masks = [trimask[:, i:i + 1].cuda() for i in range(3)]
     preds, attb, attf, small = model.NET(images, masks)
     assert len(preds) == 3 and float(preds[0].abs().max()) == 0 and float(preds[2].abs().max()) == 0
-    assert float((preds[1] - want).abs().max()) < 1e-5
+    assert float((preds[1] - want).abs().max()) < 1e-6
     assert attb[0] is None and attb[1].shape == (1, 49, 8 * 12) and small[1].dtype == torch.bool
 
 
