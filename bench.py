@@ -348,6 +348,10 @@ def run_fba_section(args, rank, world, dev, max_over_ranks):
                         breakdown_ms={k: round(v, 3) for k, v in sorted(kinds.items(), key=lambda kv: -kv[1])})
         model.NET.engine().plans.clear()
         del plan, model
+        import gc
+        from tcvom_b200.engine import release_idle_pools
+        gc.collect()
+        release_idle_pools()
         torch.cuda.empty_cache()
     except Exception as e:                                     # noqa: BLE001 - reported in the JSON line
         err = f"{type(e).__name__}: {e}"
@@ -617,8 +621,12 @@ def run_native(args, rank, world, local_rank):
 
     train = train_1080 = None
     if not args.no_train:
-        model.NET.engine().plans.clear()           # release the forward plan's 10 GB of activations
+        model.NET.engine().plans.clear()           # release the forward plan's activations
         del plan
+        import gc
+        from tcvom_b200.engine import release_idle_pools
+        gc.collect()
+        release_idle_pools()
         torch.cuda.empty_cache()
         train = run_train_section(args, rank, world, dev, barrier, max_over_ranks)
         try:
@@ -631,7 +639,11 @@ def run_native(args, rank, world, local_rank):
 
     fba = None
     if not args.no_fba:
+        import gc
+        from tcvom_b200.engine import release_idle_pools
         model.NET.engine().plans.clear()
+        gc.collect()
+        release_idle_pools()
         torch.cuda.empty_cache()
         fba = run_fba_section(args, rank, world, dev, max_over_ranks)
 

@@ -10,6 +10,7 @@ Program restated from (reference checkout):
 from __future__ import annotations
 
 import collections
+import contextlib
 import ctypes as C
 import os
 from typing import Dict, List, Optional, Tuple
@@ -58,6 +59,20 @@ class Plan:
         self.io: Dict[str, torch.Tensor] = {}
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.n_launch = 0
+        # private memory pool the plan was recorded in (GcaVmnEngine.recording): dead intermediates are reused by later
+        # allocations of the same recording, and the pool keeps the address ranges reserved for the replays
+        self.pool = None
+        self.pool_device = None
+
+    def __del__(self):
+        # The pool goes back to a free list instead of being destroyed here: a MemPool destructor empties its cache, which
+        # the caching allocator refuses (abort) while ANOTHER recording is routing allocations to a pool -- and the garbage
+        # collector may run this finaliser at exactly such a moment.  The next recording on the device reuses the pool (and
+        # its cached blocks); release_idle_pools() frees them.
+        pool = self.__dict__.get("pool")
+        if pool is not None:
+            _IDLE_POOLS.setdefault(self.pool_device, []).append(pool)
+            self.pool = None
 
     def replay(self, stream_ptr: int) -> None:
         for fn, args, what in self.calls:
@@ -80,6 +95,24 @@ class Plan:
             evs.append((e0, e1))
         st.synchronize()
         return [a.elapsed_time(b) for a, b in evs]
+
+
+_IDLE_POOLS: Dict[Optional[int], list] = {}
+_RECORDING = [0]
+
+
+def release_idle_pools() -> int:
+    """Destroys the memory pools of plans that no longer exist (their device memory returns to the driver).  Returns the
+    number of pools released; a no-op while a plan is being recorded."""
+    if _RECORDING[0]:
+        return 0
+    n = 0
+    for dev, pools in list(_IDLE_POOLS.items()):
+        n += len(pools)
+        pools.clear()
+    if n and torch.cuda.is_available():
+        torch.cuda.empty_cache()
+    return n
 
 
 def named_tensors(net: torch.nn.Module) -> Dict[str, torch.Tensor]:
@@ -122,6 +155,7 @@ class GcaVmnEngine:
         self.max_plans = int(os.environ.get("TCV_MAX_PLANS", "2"))
         self._rec: Optional[Plan] = None
         self.use_graphs = os.environ.get("TCV_GRAPHS", "1") == "1"
+        self.plan_pool = os.environ.get("TCV_PLAN_POOL", "1") == "1"
         # tcgen05 paths (default on); the CUDA-core fp32 paths stay available as the exact cross-check
         self.use_tc_conv = os.environ.get("TCV_TC_CONV", "1") == "1"
         self.use_tc_attn = os.environ.get("TCV_TC_ATTN", "1") == "1"
@@ -384,7 +418,34 @@ class GcaVmnEngine:
 
     def _keep(self, *objs):
         if self._rec is not None:
+            if self._rec.pool is not None:
+                # pooled recording: device tensors live exactly as long as the program references them (their memory is
+                # then reused by later buffers of the same plan); only host-side objects (descriptors) are pinned
+                objs = [o for o in objs if not isinstance(o, torch.Tensor)]
             self._rec.keep.extend(objs)
+
+    @contextlib.contextmanager
+    def recording(self, plan: "Plan"):
+        """Records the C-ABI calls issued inside the block into `plan`.  On a CUDA device the block allocates from a private
+        ``torch.cuda.MemPool`` owned by the plan (TCV_PLAN_POOL=0: every buffer is kept for the plan's lifetime, the round-1
+        behaviour): an intermediate whose last consumer has been issued is freed by Python's reference counting and its
+        memory serves a later buffer of the same plan -- all kernels of a plan run in issue order on one stream, so the
+        aliasing is safe, and replays see the same addresses.  A 1088x1920 GCA window needs its true peak liveness instead
+        of the sum of all its buffers (10.5 GB)."""
+        self._rec = plan
+        cm = contextlib.nullcontext()
+        if self.plan_pool and self.device is not None and self.device.type == "cuda":
+            idle = _IDLE_POOLS.get(self.device.index)
+            plan.pool = idle.pop() if idle else torch.cuda.MemPool()
+            plan.pool_device = self.device.index
+            cm = torch.cuda.use_mem_pool(plan.pool, device=self.device)
+        _RECORDING[0] += 1
+        try:
+            with cm:
+                yield plan
+        finally:
+            _RECORDING[0] -= 1
+            self._rec = None
 
     def _empty(self, shape, dtype=torch.float32):
         t = torch.empty(shape, dtype=dtype, device=self.device)

@@ -562,13 +562,10 @@ class EvalModel(nn.Module):
         if plan is not None:
             return plan
         plan = Plan()
-        eng._rec = plan
-        try:
+        with eng.recording(plan):
             n0 = _cabi.launch_count()
             plan.io = eng.eval_program(B, S, H, W, dil, u8)
             plan.n_launch = _cabi.launch_count() - n0
-        finally:
-            eng._rec = None
         eng.put_plan(key, plan)
         return plan
 
@@ -581,8 +578,7 @@ class EvalModel(nn.Module):
         if plan is not None:
             return plan
         plan = Plan()
-        eng._rec = plan
-        try:
+        with eng.recording(plan):
             in_dt = torch.uint8 if u8 else torch.float32
             sfx = "_u8" if u8 else ""
             imgs = eng._empty((B, S, 3, H, W), in_dt)
@@ -609,8 +605,6 @@ class EvalModel(nn.Module):
             if self.method == 'dim':
                 plan.io["pool_idx"] = out["pf"]["idxs"]          # max-pooling routing (tests follow it, see oracle/vmn_dim_oracle.py)
                 plan.io["x8"] = x8.buf
-        finally:
-            eng._rec = None
         eng.put_plan(key, plan)
         return plan
 
@@ -703,8 +697,7 @@ class FullModel_VMD(nn.Module):
         if plan is not None:
             return plan
         plan = Plan()
-        eng._rec = plan
-        try:
+        with eng.recording(plan):
             a = eng._empty((B, S, 1, H, W)); fg = eng._empty((B, S, 3, H, W)); bg = eng._empty((B, S, 3, H, W))
             radii = eng._empty((B,), torch.int32)
             a.zero_(); fg.zero_(); bg.zero_(); radii.zero_()
@@ -730,8 +723,6 @@ class FullModel_VMD(nn.Module):
             plan.io = dict(a=a, fg=fg, bg=bg, radii=radii, losses=losses, imgs=imgs, tris_vis=tris_vis, alphas=alphas,
                            comps=comps, gts=gts, fgs=fgs, bgs=bgs, trimask=trimask,
                            **{k: out[k] for k in ("pred", "attb", "attf", "small_mask")})
-        finally:
-            eng._rec = None
         eng.put_plan(key, plan)
         return plan
 
