@@ -379,6 +379,65 @@ def run_fba_section(args, rank, world, dev, max_over_ranks):
                 algorithmic_tflops=FBA_GFLOP_PER_WINDOW / ms, cpu_baseline=cpu, **info)
 
 
+DIM_GFLOP_PER_WINDOW = 7103.1       # convolution FLOPs of EvalModel('vmn_dim') at 1088x1920: 3 x 2028.9 (per frame) + 1016.3 (tail)
+
+
+def run_dim_section(args, rank, world, dev, max_over_ranks):
+    """Secondary measurement: EvalModel('vmn_dim') forward on one 1088x1920 3-frame window per GPU (SURVEY.md section 8 row
+    f4, the third base network behind the plugin seam).  Inputs resident in HBM, CUDA-graph replay."""
+    import gc
+    import torch
+    import tcvom_b200
+    from tcvom_b200 import synthetic
+    from tcvom_b200.engine import release_idle_pools
+    from helpers import fixture_sd_dim
+    ms_local, info, err = -1.0, {}, None
+    try:
+        torch.cuda.reset_peak_memory_stats(dev)
+        model = tcvom_b200.EvalModel(model="vmn_dim", agg_window=7, dilate_kernel=None)
+        model.NET.load_state_dict(fixture_sd_dim(), strict=True)
+        model = model.to(dev).eval()
+        imgs_np, tris_np = synthetic.make_window(H, W, seed=7 + rank)
+        imgs, tris = torch.from_numpy(imgs_np).to(dev), torch.from_numpy(tris_np).to(dev)
+        steps = 5
+        with torch.no_grad():
+            out = model(imgs, tris)
+            plan = list(model.NET.engine().plans.values())[0]
+            for _ in range(3):
+                model.run_plan(plan)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                model.run_plan(plan)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms_local = e0.elapsed_time(e1) / steps
+            kinds = {}
+            if rank == 0:
+                plan.replay_timed(dev)
+                for m, t in zip(plan.meta, plan.replay_timed(dev)):
+                    kinds[m["kind"]] = kinds.get(m["kind"], 0.0) + t
+            info = dict(gpu_launches_per_window=plan.n_launch, steps=steps, warmup=3,
+                        peak_mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+                        finite=bool(torch.isfinite(out).all()),
+                        breakdown_ms={k: round(v, 3) for k, v in sorted(kinds.items(), key=lambda kv: -kv[1])})
+        model.NET.engine().plans.clear()
+        del plan, model
+        gc.collect()
+        release_idle_pools()
+        torch.cuda.empty_cache()
+    except Exception as e:                                     # noqa: BLE001 - reported in the JSON line
+        err = f"{type(e).__name__}: {e}"
+    ms = max_over_ranks(ms_local)
+    any_failed = max_over_ranks(1.0 if (err is not None or ms_local < 0) else 0.0) > 0
+    if any_failed:
+        return dict(workload="DIM+TAM forward 1080p", error=err or "failed on another rank")
+    return dict(workload="DIM+TAM forward-only 1080p 3-frame window, batch 1 per GPU (vmn_dim, SURVEY 8 f4; "
+                         f"{DIM_GFLOP_PER_WINDOW:.1f} GFLOP/window, convolutions only)",
+                ms_per_window=ms, windows_per_s=world * 1e3 / ms, algorithmic_tflops=DIM_GFLOP_PER_WINDOW / ms, **info)
+
+
 # ------------------------------------------------------------------------------------- reference on the same GPU
 def run_gpu_eager_section(dev):
     """What the hot path costs TODAY on this GPU without this repo: the reference's PyTorch modules (eager, cuDNN / cuBLAS,
@@ -646,6 +705,9 @@ def run_native(args, rank, world, local_rank):
         release_idle_pools()
         torch.cuda.empty_cache()
         fba = run_fba_section(args, rank, world, dev, max_over_ranks)
+    dim = None
+    if not args.no_dim:
+        dim = run_dim_section(args, rank, world, dev, max_over_ranks)
 
     if rank != 0:
         if world > 1:
@@ -678,7 +740,7 @@ def run_native(args, rank, world, local_rank):
                          h2d_bytes_per_step=imgs_u8.numel() + tris_u8.numel(), input_dtype="uint8",
                          d2h_bytes_per_step=out_h.numel() * 4),
                 gpu_launches=launches, roofline=roof, cpu_baseline=cpu, gpu_eager_baseline=eager, train_step=train,
-                train_step_1080p=train_1080, fba_forward=fba)
+                train_step_1080p=train_1080, fba_forward=fba, dim_forward=dim)
     print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -695,6 +757,7 @@ def main():
                     help="skip the reference-on-this-GPU measurement (PyTorch eager, N=1 only)")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
     ap.add_argument("--no-fba", action="store_true", help="skip the secondary FBA+TAM forward measurement (configs[4])")
+    ap.add_argument("--no-dim", action="store_true", help="skip the secondary DIM+TAM forward measurement (SURVEY 8 f4)")
     ap.add_argument("--dump-calls", default=None, help="write the per-launch timing table (JSON lines) here")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: everything else -- Python prints of the reference modules AND C-level writes to

@@ -558,6 +558,11 @@ int tcv_postprocess_eval_fba(const float* pred, const void* imgs, const void* tr
 int tcv_maxpool2_idx(const void* x, int n, int h, int w, int c, void* y, uint8_t* idx, tcv_stream_t stream);
 int tcv_maxunpool2(const void* x, const uint8_t* idx, int n, int h, int w, int c, void* y, tcv_stream_t stream);
 int tcv_dim_fix_inputs(const void* tris, int is_u8, int frames, int h, int w, void* x8, tcv_stream_t stream);
+/* alpha head of the DIM decoder (VMN_DIM.py:97,135: alpha_pred = Conv2d(64, 1, 5, padding=2) then .clamp(0, 1)) in one HBM-
+ * bound pass: x split-bf16 NHWC [n,h,w,64], wt fp32 [25][64] (tap-major, tap = ky*5+kx), bias fp32 [1] or NULL ->
+ * pred fp32 [n,h,w] */
+int tcv_head_conv5_clamp01(const void* x, long long x_plane, int n, int h, int w, const float* wt, const float* bias,
+                           float* pred, tcv_stream_t stream);
 
 /* ---- training side of the shift-sum aggregation (csrc/gca_train2.cu; autograd of GCA/ops.py:112-118,204):
  *  shift_add_u:        A fp32 [n][P][lda] (softmax on the unpadded key grid) -> A2 split-bf16 planes [2][n][Pk][ld]

@@ -575,13 +575,25 @@ TCV_HD void maxpool2_idx_body(ll i, const Pool2P& p) {
       }
   }
   const ll o = (((ll)img * oh + y) * ow + x) * p.c + ch;
-  // the maximum is one of the stored values: copy its two planes instead of re-splitting (bit-exact pooling)
+#ifdef __CUDA_ARCH__
+  // hi + lo is exact in fp32, so re-splitting stores the same VALUE (the pair itself can differ in a rounding tie)
+  st8(p.y + o, yplane, best);
+  uint32_t lo4 = 0, hi4 = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    lo4 |= (uint32_t)bi[j] << (8 * j);
+    hi4 |= (uint32_t)bi[j + 4] << (8 * j);
+  }
+  *reinterpret_cast<uint2*>(p.idx + o) = make_uint2(lo4, hi4);
+#else
+  // the maximum is one of the stored values: copy its two planes
   for (int j = 0; j < 8; ++j) {
     const uint16_t* s = p.x + (((ll)img * p.h + 2 * y + (bi[j] >> 1)) * p.w + 2 * x + (bi[j] & 1)) * p.c + ch + j;
     p.y[o + j] = s[0];
     p.y[o + j + yplane] = s[xplane];
     p.idx[o + j] = (uint8_t)bi[j];
   }
+#endif
 }
 
 struct Unpool2P {
@@ -604,11 +616,28 @@ TCV_HD void maxunpool2_body(ll i, const Unpool2P& p) {
   const ll s = (((ll)img * ih + (y >> 1)) * iw + (x >> 1)) * p.c + ch;
   const ll o = (((ll)img * p.h + y) * p.w + x) * p.c + ch;
   const int me = (y & 1) * 2 + (x & 1);
+#ifdef __CUDA_ARCH__
+  const uint2 id = *reinterpret_cast<const uint2*>(p.idx + s);
+  const uint4 a = *reinterpret_cast<const uint4*>(p.x + s), b = *reinterpret_cast<const uint4*>(p.x + s + xplane);
+  uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t k = ((j < 4 ? id.x : id.y) >> (8 * (j & 3))) & 0xffu;
+    if ((int)k != me) {
+      const uint32_t keep = (j & 1) ? 0x0000ffffu : 0xffff0000u;
+      aw[j >> 1] &= keep;
+      bw[j >> 1] &= keep;
+    }
+  }
+  *reinterpret_cast<uint4*>(p.y + o) = make_uint4(aw[0], aw[1], aw[2], aw[3]);
+  *reinterpret_cast<uint4*>(p.y + o + yplane) = make_uint4(bw[0], bw[1], bw[2], bw[3]);
+#else
   for (int j = 0; j < 8; ++j) {
     const bool hit = p.idx[s + j] == me;
     p.y[o + j] = hit ? p.x[s + j] : (uint16_t)0;
     p.y[o + j + yplane] = hit ? p.x[s + j + xplane] : (uint16_t)0;
   }
+#endif
 }
 
 struct DimFixP {

@@ -25,6 +25,7 @@ from .dim_modules import ENC_STAGES
 from .engine import Act, GcaVmnEngine
 
 FOLDED = "#b"          # BatchNorm affine with the convolution bias folded in
+C11 = "encoder.conv11#c32"
 HEAD = "decoder.alpha_pred"
 
 
@@ -34,6 +35,12 @@ class DimVmnEngine(GcaVmnEngine):
     def __init__(self, window: int):
         super().__init__(window)
         self.s2d_stride2 = False          # no stride-2 convolutions in this network
+        import os
+        # alpha head as one HBM-bound kernel (default) or as the zero-padded 32-output-channel tensor-core conv chain
+        self.head_direct = os.environ.get("TCV_HEAD_DIRECT", "1") == "1"
+        # conv11 (4 -> 64) reads a 32-channel zero-padded copy of the input so that it runs on the CTA-pair tcgen05 kernel
+        # instead of the CUDA-core one (3.1 -> ~0.5 ms per 1088x1920 window); "0": 8-channel input on the CUDA cores
+        self.conv11_pad32 = os.environ.get("TCV_DIM_CONV11_PAD32", "1") == "1"
 
     # ------------------------------------------------------------------ weights
     def refresh_weights(self, net: torch.nn.Module, force=False) -> None:
@@ -58,7 +65,18 @@ class DimVmnEngine(GcaVmnEngine):
                     own[0].copy_(s)
                     torch.addcmul(b, named[f"encoder.{cname}.bias"], s, out=own[1])
         w, b = named[HEAD + ".weight"], named[HEAD + ".bias"]
-        self._pack_head32(_cabi.lib(), self._stream_ptr(), HEAD, w, b)
+        L, st = _cabi.lib(), self._stream_ptr()
+        self._pack_head32(L, st, HEAD, w, b)
+        # conv11 with its input channels zero-padded to 32 (weights [9][32][64] + the tensor-core copy), updated in place
+        w11 = named["encoder.conv11.weight"]
+        ent = self.w.get(C11)
+        if ent is None or ent["w"].device != dev:
+            ent = self.w[C11] = dict(w=torch.empty((9, 32, 64), dtype=torch.float32, device=dev),
+                                     w_tc=torch.empty((2, 9, 64, 32), dtype=torch.bfloat16, device=dev),
+                                     cout=64, cin=32, cin_real=w11.shape[1], k=3, transposed=False)
+        _cabi.check(L.tcv_sn_fold_pack(w11.data_ptr(), None, None, 64, w11.shape[1], 3, 3, 0, 32, ent["w"].data_ptr(), None,
+                                       st), "sn_fold_pack")
+        _cabi.check(L.tcv_pack_weight_tc(ent["w"].data_ptr(), 9, 32, 64, ent["w_tc"].data_ptr(), st), "pack_weight_tc")
 
     # ------------------------------------------------------------------ operators
     def maxpool2(self, x: Act) -> Tuple[Act, torch.Tensor]:
@@ -109,6 +127,14 @@ class DimVmnEngine(GcaVmnEngine):
         idxs: List[torch.Tensor] = []
         for _, convs in ENC_STAGES:
             for cname, bname, _, _ in convs:
+                if cname == "conv11" and self.conv11_pad32 and self.use_tc_conv:
+                    x32 = self._act(x8.n, x8.h, x8.w, 32)
+                    x32.buf.zero_()              # channels 8..31 stay zero: written once, no recorded call touches them
+                    self._hold.append(x32.buf)   # (a pooled plan must not hand this block to a later buffer)
+                    self._call("tcv_copy_channels", x8.ptr, x8.plane, 8, 0, x32.ptr, x32.plane, 32, 0, 8,
+                               x8.n * x8.h * x8.w, meta=dict(kind="tcv_copy_channels", bytes=x8.n * x8.h * x8.w * 64))
+                    x = self.conv(x32, C11, bn=f"{e}.{bname}{FOLDED}", act=ACT_RELU)
+                    continue
                 x = self.conv(x, f"{e}.{cname}", bn=f"{e}.{bname}{FOLDED}", act=ACT_RELU)
             x, idx = self.maxpool2(x)
             idxs.append(idx)
@@ -135,6 +161,15 @@ class DimVmnEngine(GcaVmnEngine):
         t = self.conv_k(self.unpool2(t, idx_ptr(2)), d + ".dconv3", act=ACT_RELU)                # OS4
         t = self.conv_k(self.unpool2(t, idx_ptr(1)), d + ".dconv2", act=ACT_RELU)                # OS2
         t = self.conv_k(self.unpool2(t, idx_ptr(0)), d + ".dconv1", act=ACT_RELU)                # OS1
+        hw_ = self.w[HEAD]
+        if self.head_direct and hw_["cin"] == 64 and hw_["cout"] == 1 and hw_["k"] == 5:
+            # one HBM-bound pass: 5x5 conv to the single alpha channel + clamp (the padded tensor-core form below writes and
+            # re-reads 32-channel full-resolution partial sums four times for one real channel)
+            self._call("tcv_head_conv5_clamp01", t.ptr, t.plane, t.n, t.h, t.w, hw_["w"].data_ptr(),
+                       self.bias[HEAD].data_ptr(), pred_ptr,
+                       meta=dict(kind="tcv_head_conv5_clamp01", bytes=t.n * t.h * t.w * (4 * 64 + 4),
+                                 flops=2 * t.n * t.h * t.w * 25 * 64))
+            return
         z = self.conv_k(t, HEAD + self.HEAD32, act=ACT_CLAMP01)      # 64 -> 1 as 64 -> 32 (zero weights), channel 0 = alpha
         self._call("tcv_split_to_nchw", z.ptr, z.n, 1, z.h, z.w, z.c, z.plane, pred_ptr,
                    meta=dict(kind="tcv_split_to_nchw", bytes=z.n * z.h * z.w * 8))
@@ -148,7 +183,9 @@ class DimVmnEngine(GcaVmnEngine):
         attb = self._empty((B, ncen, w2, N8))
         attf = self._empty((B, ncen, w2, N8))
         sm = self._empty((B, ncen, 1, H // 8, W // 8), torch.uint8)
+        self._hold = []
         pf = self.per_frame(x8)
+        pf["hold"] = self._hold
         for b in range(B):
             n0 = b * S
             self.tail(pf, n0, ncen, trimask.data_ptr() + 4 * (n0 + 1) * H * W, H * W, H, W,

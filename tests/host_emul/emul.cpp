@@ -579,6 +579,25 @@ int tcv_gca_unfold_parity(const float* O2, int n, int h, int w, void* Y, tcv_str
   return 0;
 }
 
+int tcv_head_conv5_clamp01(const void* x, long long x_plane, int n, int h, int w, const float* wt, const float* bias,
+                           float* pred, tcv_stream_t) {
+  if (x_plane == 0) x_plane = (ll)n * h * w * 64;
+  for (int img = 0; img < n; ++img)
+    for (int y = 0; y < h; ++y)
+      for (int xx = 0; xx < w; ++xx) {
+        float acc = bias ? bias[0] : 0.f;
+        for (int t = 0; t < 25; ++t) {
+          const int yy = y + t / 5 - 2, xc = xx + t % 5 - 2;
+          if (yy < 0 || yy >= h || xc < 0 || xc >= w) continue;
+          for (int c = 0; c < 64; ++c)
+            acc += ld1((const uint16_t*)x + (((ll)img * h + yy) * w + xc) * 64 + c, x_plane) * wt[t * 64 + c];
+        }
+        pred[((ll)img * h + y) * w + xx] = acc < 0.f ? 0.f : (acc > 1.f ? 1.f : acc);
+      }
+  ++g_launches;
+  return 0;
+}
+
 int tcv_head_conv_tanh01(const void* x, long long x_plane, int n, int h, int w, const float* wt, const float* bias, float* pred,
                          tcv_stream_t) {
   if (x_plane == 0) x_plane = (ll)n * h * w * 32;
