@@ -96,9 +96,18 @@ typedef struct {
   const float* b2;
   const void* res2;   /* split-bf16 NHWC [n, oh, ow, cout]                                   */
   long long res2_plane; /* elements between hi and lo plane of res2 (0: contiguous default)  */
+  /* optional per-channel statistics of the OUTPUT (the value written to y), accumulated by the epilogue of the CTA-pair
+   * tcgen05 kernel (tcv_conv2d_path(d) == 4 with stats == NULL; any other shape rejects a non-null `stats`):
+   *   stats[(img % stats_groups) * cout + co][0..1] += sum, sum of squares over the pixels of image img
+   * (fp64, caller-zeroed: tcv_zero_bytes).  GroupNorm (layers_WS.py:26-27, stats_groups = n) and train-mode BatchNorm
+   * (stats_groups = frames per call) read their sums from here instead of a separate pass over y. */
+  double* stats;
+  int stats_groups;
 } tcv_conv_desc;
 
 int tcv_conv2d(const tcv_conv_desc* d, tcv_stream_t stream);
+/* cudaMemsetAsync(p, 0, bytes) on the stream (a recorded plan zeroes its accumulators with it) */
+int tcv_zero_bytes(void* p, long long bytes, tcv_stream_t stream);
 /* which kernel tcv_conv2d dispatches this descriptor to: 3 = narrow-layer tcgen05 conv (un-swizzled
  * halo tile), 2 = persistent shared-halo tcgen05 conv,
  * 1 = tcgen05 implicit GEMM (one tap per K block), 0 = CUDA-core gather conv (no launch) */

@@ -92,6 +92,11 @@ int tcv_conv2d(const tcv_conv_desc* dp, tcv_stream_t stream) {
   if (d.res1 && d.res1_plane == 0)
     d.res1_plane = (long long)d.n * (d.oh >> d.res1_shift) * (d.ow >> d.res1_shift) * d.cout;
   if (d.res2 && d.res2_plane == 0) d.res2_plane = (long long)d.n * d.oh * d.ow * d.cout;
+  if (d.stats) {
+    TCV_REQUIRE(g_conv_tc_version.load() >= 2 && !(g_debug_flags.load() & 4096) && conv2d_tc2p_supported(d),
+                "conv2d: output statistics need the CTA-pair tcgen05 kernel (tcv_conv2d_path 4)");
+    return conv2d_tc2p(d, S(stream));
+  }
   if (g_conv_tc_version.load() >= 3 && conv2d_tc3_supported(d)) return conv2d_tc3(d, S(stream));
   // wide layers (Cout >= 128) on CTA pairs (conv_tc2p.cu); tcv_set_debug_flags bit 4096 falls back to the single-CTA kernel
   if (g_conv_tc_version.load() >= 2 && !(g_debug_flags.load() & 4096) && conv2d_tc2p_supported(d))
@@ -99,6 +104,12 @@ int tcv_conv2d(const tcv_conv_desc* dp, tcv_stream_t stream) {
   if (g_conv_tc_version.load() >= 2 && conv2d_tc2_supported(d)) return conv2d_tc2(d, S(stream));
   if (conv2d_tc_supported(d)) return conv2d_tc(d, S(stream));
   return conv2d_direct(d, S(stream));
+}
+
+int tcv_zero_bytes(void* p, long long bytes, tcv_stream_t stream) {
+  TCV_REQUIRE(p && bytes > 0, "zero_bytes: bad arguments");
+  TCV_CUDA(cudaMemsetAsync(p, 0, (size_t)bytes, S(stream)));
+  return launched("zero_bytes");
 }
 
 }  // extern "C"

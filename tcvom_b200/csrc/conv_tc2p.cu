@@ -121,7 +121,7 @@ __device__ __forceinline__ void vp_commit(uint32_t bar) {
                : "memory");
 }
 
-template <int BN, bool STACK, int BK>
+template <int BN, bool STACK, int BK, bool STATS>
 __global__ void __launch_bounds__(320, 1) conv_tc2p_kernel(const __grid_constant__ CUtensorMap mapA_hi,
                                                            const __grid_constant__ CUtensorMap mapA_lo,
                                                            const __grid_constant__ CUtensorMap mapB_hi,
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc2p_kernel(const __grid_constant
       const int gy = h0 + (int)rank * p.TH + ty, gx = w0 + tx;
       stc.cx = w0;
       stc.cy = h0 + (int)rank * p.TH;
-      conv_epilogue<HN, BN>(p.epi, taddr, gy < p.gh && gx < p.gw, img, gy, gx, n0 + grp * HN, accFull(buf),
+      conv_epilogue<HN, BN, STATS>(p.epi, taddr, gy < p.gh && gx < p.gw, img, gy, gx, n0 + grp * HN, accFull(buf),
                             (uint32_t)(iw >> 1) & 1u, ae_leader + 8u * buf, lane, stc, /*split_halves=*/STACK,
                             /*remote_empty=*/true);
     }
@@ -406,7 +406,7 @@ int conv2d_tc2p_supported(const tcv_conv_desc& d) {
   return vp_build_groups(d, p) ? 1 : 0;
 }
 
-template <int BN, bool STACK = false, int BK = 32>
+template <int BN, bool STACK = false, int BK = 32, bool STATS = false>
 static int conv_tc2p_bn(const tcv_conv_desc& d, cudaStream_t st) {
   using Cfg = VPCfg<BN, STACK, BK>;
   constexpr int VP_BK = BK;
@@ -466,7 +466,7 @@ static int conv_tc2p_bn(const tcv_conv_desc& d, cudaStream_t st) {
     rc = make_map(&mB_lo, b + (long long)d.w_tc_taps * d.cout * d.cin, 3, dims, str, box, VP_BK);
     if (rc) return rc;
   }
-  auto kern = conv_tc2p_kernel<BN, STACK, BK>;
+  auto kern = conv_tc2p_kernel<BN, STACK, BK, STATS>;
   TCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
   int dev = 0, sms = 0;
   TCV_CUDA(cudaGetDevice(&dev));
@@ -488,6 +488,12 @@ static int conv_tc2p_bn(const tcv_conv_desc& d, cudaStream_t st) {
 
 int conv2d_tc2p(const tcv_conv_desc& d, cudaStream_t st) {
   const bool bk64 = d.cin % 64 == 0 && !(g_debug_flags.load() & 65536);       // A/B switch 65536: BK = 32 everywhere
+  if (d.stats) {
+    // epilogue with per-channel output statistics (tcv_conv_desc.stats): separate instantiations, default tile shapes
+    if (d.cout % 256 == 0) return conv_tc2p_bn<256, false, 32, true>(d, st);
+    if (d.cout % 128 == 0) return bk64 ? conv_tc2p_bn<128, false, 64, true>(d, st) : conv_tc2p_bn<128, false, 32, true>(d, st);
+    return bk64 ? conv_tc2p_bn<64, true, 64, true>(d, st) : conv_tc2p_bn<64, true, 32, true>(d, st);
+  }
   if (d.cout % 256 == 0)
     // N = 256: BK = 32 (a stage is already 0.4 us of tensor work; BK = 64 leaves only two weight slots: measured 2-5 % slower)
     return (bk64 && (g_debug_flags.load() & 131072)) ? conv_tc2p_bn<256, false, 64>(d, st) : conv_tc2p_bn<256>(d, st);

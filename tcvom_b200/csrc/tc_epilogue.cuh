@@ -24,7 +24,31 @@ struct EpiParams {
   long long res1_plane, res2_plane;
   int res1_shift, act;
   int dbg;
+  double* stats;      // optional per-(image group, channel) sum / sum of squares of the output (tcv_conv_desc.stats)
+  int stats_groups;
 };
+
+// Sum over the 32 lanes of a warp of 32 per-lane values: afterwards lane j holds the total of element j.  Recursive halving:
+// 16 + 8 + 4 + 2 + 1 = 31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float warp_transpose_sum32(const float* f, int lane) {
+  float t[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const bool up = lane & 16;
+    const float mine = up ? f[16 + i] : f[i], give = up ? f[i] : f[16 + i];
+    t[i] = mine + __shfl_xor_sync(0xffffffffu, give, 16);
+  }
+#pragma unroll
+  for (int w = 8; w >= 1; w >>= 1) {
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const bool up = lane & w;
+      const float mine = up ? t[w + i] : t[i], give = up ? t[i] : t[w + i];
+      t[i] = mine + __shfl_xor_sync(0xffffffffu, give, w);
+    }
+  }
+  return t[0];
+}
 
 static inline void fill_epi(EpiParams& e, const tcv_conv_desc& d, int dbg) {
   e.n_imgs = d.n; e.oh = d.oh; e.ow = d.ow; e.cout = d.cout;
@@ -36,6 +60,19 @@ static inline void fill_epi(EpiParams& e, const tcv_conv_desc& d, int dbg) {
   e.res2 = reinterpret_cast<const __nv_bfloat16*>(d.res2);
   e.res1_plane = d.res1_plane; e.res2_plane = d.res2_plane; e.res1_shift = d.res1_shift; e.act = d.act;
   e.dbg = dbg;
+  e.stats = d.stats;
+  e.stats_groups = d.stats_groups > 0 ? d.stats_groups : 1;
+}
+
+// per-channel sum / sum of squares of the 32 pixels of this warp (rows outside the image were zeroed by the caller);
+// lane j ends up with channel j of the chunk and adds it to its fp64 accumulator pair
+static __device__ __noinline__ void epi_stats(float* g, int lane, double* acc) {
+  const float s = warp_transpose_sum32(g, lane);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) g[j] *= g[j];
+  const float q = warp_transpose_sum32(g, lane);
+  atomicAdd(acc, (double)s);
+  atomicAdd(acc + 1, (double)q);
 }
 
 // TMA-store path: the 4 warps that drain one accumulator stage each 32-channel chunk in a 64B-swizzled
@@ -59,7 +96,7 @@ struct StoreCtx {
 // `acc_full` (parity given), drains its 32 TMEM lanes starting at `taddr`, and arrives on `acc_empty` as soon
 // as its last tcgen05.ld has completed.
 // split_halves: the accumulator holds a second partial product SPLIT_OFF columns further right; the two are summed first.
-template <int BN, int SPLIT_OFF = BN>
+template <int BN, int SPLIT_OFF = BN, bool STATS = false>
 __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr, bool in_grid, int img, int gy, int gx,
                                               int n0, uint32_t acc_full, uint32_t full_parity, uint32_t acc_empty,
                                               int lane, StoreCtx& st, bool split_halves = false,
@@ -175,6 +212,13 @@ __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr
         }
       }
       if (has2) add_res(rb[slot], f);
+    }
+    if constexpr (STATS) {
+      // (compiled only into the STATS instantiations of the kernels: the common path pays nothing for it)
+      float g[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) g[j] = valid ? f[j] : 0.f;
+      epi_stats(g, lane, p.stats + ((long long)(img % p.stats_groups) * p.cout + n0 + c0 + lane) * 2);
     }
     if (st.stage_hi) {
       // the previous bulk store into THIS staging tile must have finished READING it

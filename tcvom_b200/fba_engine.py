@@ -47,6 +47,12 @@ class FbaVmnEngine(GcaVmnEngine):
     def __init__(self, window: int):
         super().__init__(window)
         self.gn_params: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
+        # GroupNorm statistics accumulated by the epilogue of the producing convolution (tcv_conv_desc.stats) instead of a
+        # separate pass over its output; TCV_FBA_GN_FUSED=0: tcv_gn_stats everywhere (the cross-check)
+        self.fuse_gn_stats = os.environ.get("TCV_FBA_GN_FUSED", "1") == "1"
+        self._pending_stats: Dict[int, torch.Tensor] = {}
+
+    STATS_PATH = 4       # tcv_conv2d_path value of the kernel whose epilogue can accumulate statistics (conv_tc2p)
 
     # ------------------------------------------------------------------ weights
     def refresh_weights(self, net: torch.nn.Module, force=False) -> None:
@@ -151,6 +157,14 @@ class FbaVmnEngine(GcaVmnEngine):
             y = self._act(x.n, oh, ow, cout)
             d = self._desc(x, ent["w"].data_ptr(), taps, stride, PAD_ZERO, y, oh, ow, cout, oh, ow, 1, 0, 1, 0, wkey,
                            None, bias and last, act if last else ACT_NONE, prev, 0, None, None, 0, wtap=wtap)
+            if last and act == ACT_NONE and self.fuse_gn_stats and cout % 32 == 0 and \
+                    _cabi.lib().tcv_conv2d_path(C.byref(d)) == self.STATS_PATH:
+                # per-(image, channel) sum / sum of squares of the output from the conv epilogue: the GroupNorm that
+                # follows (gn) skips its own pass over the tensor
+                sums = self._empty((x.n, cout, 2), torch.float64)
+                self._call("tcv_zero_bytes", sums.data_ptr(), sums.numel() * 8)
+                d.stats, d.stats_groups = sums.data_ptr(), x.n
+                self._pending_stats[y.ptr] = sums
             self._call("tcv_conv2d", C.byref(d), meta=self._conv_meta(d, wkey, x, k, stride))
             prev = y
         return prev
@@ -199,12 +213,14 @@ class FbaVmnEngine(GcaVmnEngine):
         gamma, beta = self.gn_params[p]
         n, pixels, c = z.n, z.h * z.w, z.c
         assert gamma.numel() == c, (p, gamma.numel(), c)
-        sums = self._empty((n, c, 2), torch.float64)
         scale = self._empty((n, c))
         shift = self._empty((n, c))
         nbytes = 4 * n * pixels * c
-        self._call("tcv_gn_stats", z.ptr, z.plane, n, pixels, c, sums.data_ptr(),
-                   meta=dict(kind="tcv_gn_stats", bytes=nbytes, layer=p))
+        sums = self._pending_stats.pop(z.ptr, None)          # written by the epilogue of the convolution that made z
+        if sums is None:
+            sums = self._empty((n, c, 2), torch.float64)
+            self._call("tcv_gn_stats", z.ptr, z.plane, n, pixels, c, sums.data_ptr(),
+                       meta=dict(kind="tcv_gn_stats", bytes=nbytes, layer=p))
         self._call("tcv_gn_finalize", sums.data_ptr(), n, pixels, c, GN_GROUPS, gamma.data_ptr(), beta.data_ptr(),
                    GN_EPS, scale.data_ptr(), shift.data_ptr())
         y = out if out is not None else self._act(n, z.h, z.w, c)

@@ -74,6 +74,17 @@ def test_wgrad_nhwc_tc(cin, cout, h, w, n, prepad, flags, perm):
     _tc().case_wgrad(cin, cout, h, w, n, prepad, flags, perm)
 
 
+@pytest.mark.parametrize("cin,cout,h,w,n,groups,dil", [
+    (64, 64, 40, 56, 3, 3, 1),          # N = 64 stacked operand, ragged tiles
+    (128, 128, 34, 60, 3, 3, 2),        # dilation 2 (FBA layer3)
+    (256, 256, 18, 30, 4, 2, 1),        # N = 256; two images per statistics group (train-mode BatchNorm layout)
+    (512, 512, 10, 12, 2, 2, 4),        # two N tiles, image smaller than a pair tile
+])
+def test_conv_epilogue_statistics(cin, cout, h, w, n, groups, dil):
+    """Per-channel output statistics from the conv epilogue (tcv_conv_desc.stats) against sums over the stored output."""
+    _tc().case_conv_stats(cin, cout, h, w, n, groups, dil)
+
+
 def test_conv_kernel_generation_switch():
     """tcv_set_conv_tc_version selects the kernel generation; all generations agree."""
     from tcvom_b200 import _cabi

@@ -131,6 +131,53 @@ def case_wgrad(cin, cout, h, w, n, prepad=False, flags=0, perm=False):
     return err
 
 
+def case_conv_stats(cin, cout, h, w, n, groups, dil=1):
+    """tcv_conv_desc.stats: per-(image group, channel) sum / sum of squares of the conv output accumulated by the epilogue
+    of the CTA-pair kernel, against the same sums taken from the stored output tensor."""
+    import torch
+    from tcvom_b200 import _cabi
+    from tcvom_b200._cabi import ConvDesc
+    L = _cabi.lib()
+    torch.manual_seed(2)
+    dev = "cuda"
+    st = torch.cuda.current_stream().cuda_stream
+    x = split(torch.randn(n, h, w, cin, device=dev))
+    taps = [((ky - 1) * dil, (kx - 1) * dil) for ky in range(3) for kx in range(3)]
+    wf = (torch.randn(9, cin, cout, device=dev) / (cin * 9) ** 0.5).contiguous()
+    wtc = torch.empty((2, 9, cout, cin), dtype=torch.bfloat16, device=dev)
+    _cabi.check(L.tcv_pack_weight_tc(wf.data_ptr(), 9, cin, cout, wtc.data_ptr(), st), "pack")
+    bias = torch.randn(cout, device=dev)
+    outs = []
+    for with_stats in (False, True):
+        y = torch.zeros((2, n, h, w, cout), dtype=torch.bfloat16, device=dev)
+        d = ConvDesc()
+        d.x = x.data_ptr(); d.n, d.ih, d.iw, d.cin = n, h, w, cin
+        d.w = wf.data_ptr(); d.w_tc = wtc.data_ptr(); d.w_tc_taps = 9; d.ntaps = 9
+        for i, (dy, dx) in enumerate(taps):
+            d.dy[i], d.dx[i], d.wtap[i] = dy, dx, i
+        d.stride, d.pad_mode = 1, 0
+        d.y = y.data_ptr()
+        d.oh, d.ow, d.cout, d.gh, d.gw = h, w, cout, h, w
+        d.oy_mul, d.oy_off, d.ox_mul, d.ox_off = 1, 0, 1, 0
+        d.b1 = bias.data_ptr()
+        assert L.tcv_conv2d_path(C.byref(d)) == 4
+        sums = torch.full((groups, cout, 2), 7.0, dtype=torch.float64, device=dev)
+        if with_stats:
+            _cabi.check(L.tcv_zero_bytes(sums.data_ptr(), sums.numel() * 8, st), "zero_bytes")
+            d.stats, d.stats_groups = sums.data_ptr(), groups
+        _cabi.check(L.tcv_conv2d(C.byref(d), st), "conv2d")
+        torch.cuda.synchronize()
+        outs.append((y, sums))
+    (y0, _), (y1, sums) = outs
+    assert torch.equal(y0, y1)                                  # the statistics do not change the output
+    v = (y1[0].double() + y1[1].double()).reshape(n // groups, groups, h * w, cout)
+    ref = torch.stack([v.sum(dim=(0, 2)), (v * v).sum(dim=(0, 2))], dim=-1)
+    err = float(((sums - ref).abs() / ref.abs().clamp(min=1.0)).max())
+    print(f"conv stats cin={cin} cout={cout} {h}x{w} n={n} groups={groups} dil={dil}: rel err {err:.2e}")
+    assert err < 2e-4, err                                      # fp32 accumulator vs the split-bf16 value it is stored as
+    return err
+
+
 def case_conv(cin, cout, h, w, n, kind, f32_side=True, expect_path=None):
     import torch
     from tcvom_b200 import _cabi
