@@ -98,11 +98,14 @@ typedef struct {
   long long res2_plane; /* elements between hi and lo plane of res2 (0: contiguous default)  */
   /* optional per-channel statistics of the OUTPUT (the value written to y), accumulated by the epilogue of the CTA-pair
    * tcgen05 kernel (tcv_conv2d_path(d) == 4 with stats == NULL; any other shape rejects a non-null `stats`):
-   *   stats[(img % stats_groups) * cout + co][0..1] += sum, sum of squares over the pixels of image img
-   * (fp64, caller-zeroed: tcv_zero_bytes).  GroupNorm (layers_WS.py:26-27, stats_groups = n) and train-mode BatchNorm
-   * (stats_groups = frames per call) read their sums from here instead of a separate pass over y. */
+   *   stats[copy][(img % stats_groups) * cout + co][0..1] += sum, sum of squares over the pixels of image img
+   * (fp64, caller-zeroed).  `stats_copies` (>= 1) accumulator copies [copies][stats_groups][cout][2] spread the atomics of
+   * the ~10^3 tiles of a layer over distinct addresses (same-address fp64 atomics serialise in L2: with one copy they cost
+   * more than the pass they replace); the consumer sums the copies (tcv_gn_finalize_acc).  GroupNorm (layers_WS.py:26-27,
+   * stats_groups = n) reads its sums from here instead of a separate pass over y. */
   double* stats;
   int stats_groups;
+  int stats_copies;
 } tcv_conv_desc;
 
 int tcv_conv2d(const tcv_conv_desc* d, tcv_stream_t stream);
@@ -489,6 +492,10 @@ int tcv_ws_pack(const float* w, int cout, int cin, int kh, int kw, int standardi
 int tcv_gn_stats(const void* x, long long x_plane, int n, long long pixels, int c, double* sums, tcv_stream_t stream);
 int tcv_gn_finalize(const double* sums, int n, long long pixels, int c, int groups, const float* gamma,
                     const float* beta, float eps, float* scale, float* shift, tcv_stream_t stream);
+/* tcv_gn_finalize over `copies` accumulator copies sums[copies][n][c][2] (tcv_conv_desc.stats); clear != 0: the copies
+ * are zeroed after they have been read, so a recorded plan needs no memset before its next replay */
+int tcv_gn_finalize_acc(double* sums, int copies, int clear, int n, long long pixels, int c, int groups, const float* gamma,
+                        const float* beta, float eps, float* scale, float* shift, tcv_stream_t stream);
 int tcv_gn_apply(const void* x, long long x_plane, int n, long long pixels, int c, const float* scale,
                  const float* shift, const void* res, long long res_plane, int act, void* y, long long y_plane,
                  int y_c, int y_off, tcv_stream_t stream);

@@ -36,7 +36,7 @@ class ConvDesc(C.Structure):
         ("s1", c_void_p), ("b1", c_void_p), ("res1", c_void_p), ("res1_plane", c_ll),
         ("res1_shift", c_int), ("act", c_int),
         ("s2", c_void_p), ("b2", c_void_p), ("res2", c_void_p), ("res2_plane", c_ll),
-        ("stats", c_void_p), ("stats_groups", c_int),
+        ("stats", c_void_p), ("stats_groups", c_int), ("stats_copies", c_int),
     ]
 
 
@@ -124,6 +124,8 @@ SIGNATURES = {
     "tcv_pad_reflect1_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_tanh01_bwd": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_void_p]),
     "tcv_head_tanh01": (c_int, [c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p]),
+    "tcv_gn_finalize_acc": (c_int, [c_void_p, c_int, c_int, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p,
+                                    c_void_p, c_void_p]),
     "tcv_zero_bytes": (c_int, [c_void_p, c_ll, c_void_p]),
     "tcv_maxpool2_idx": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "tcv_maxunpool2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

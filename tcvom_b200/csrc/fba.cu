@@ -177,11 +177,13 @@ __global__ void __launch_bounds__(256) gn_finalize_warp_kernel(GnFinalizeP p) {
   const int img = (int)(warp / p.groups), g = (int)(warp % p.groups);
   const int cpg = p.c / p.groups;
   double s = 0.0, ss = 0.0;
-  for (int k = lane; k < cpg; k += 32) {
-    const double* q = p.sums + ((ll)img * p.c + g * cpg + k) * 2;
-    s += q[0];
-    ss += q[1];
-  }
+  for (int cp = 0; cp < p.copies; ++cp)
+    for (int k = lane; k < cpg; k += 32) {
+      double* q = const_cast<double*>(p.sums) + (((ll)cp * p.n + img) * p.c + g * cpg + k) * 2;
+      s += q[0];
+      ss += q[1];
+      if (p.clear) q[0] = q[1] = 0.0;
+    }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -222,9 +224,19 @@ int tcv_gn_finalize(const double* sums, int n, long long pixels, int c, int grou
                     const float* beta, float eps, float* scale, float* shift, tcv_stream_t stream) {
   TCV_REQUIRE(sums && gamma && beta && scale && shift, "gn_finalize: null pointer");
   TCV_REQUIRE(n > 0 && pixels > 0 && groups > 0 && c % groups == 0, "gn_finalize: bad dims");
-  GnFinalizeP p{sums, n, c, groups, pixels, gamma, beta, eps, scale, shift};
+  GnFinalizeP p{sums, n, c, groups, pixels, gamma, beta, eps, scale, shift, 1, 0};
   // one WARP per (image, group): lanes stride the group's channels (the per-work-item body needs 2 x 64 dependent fp64
   // additions in one thread: 15 us per launch, 0.77 ms per window)
+  const ll warps = (ll)n * groups;
+  gn_finalize_warp_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, S(stream)>>>(p);
+  return launched("gn_finalize_kernel");
+}
+
+int tcv_gn_finalize_acc(double* sums, int copies, int clear, int n, long long pixels, int c, int groups, const float* gamma,
+                        const float* beta, float eps, float* scale, float* shift, tcv_stream_t stream) {
+  TCV_REQUIRE(sums && gamma && beta && scale && shift, "gn_finalize_acc: null pointer");
+  TCV_REQUIRE(copies > 0 && n > 0 && pixels > 0 && groups > 0 && c % groups == 0, "gn_finalize_acc: bad dims");
+  GnFinalizeP p{sums, n, c, groups, pixels, gamma, beta, eps, scale, shift, copies, clear};
   const ll warps = (ll)n * groups;
   gn_finalize_warp_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, S(stream)>>>(p);
   return launched("gn_finalize_kernel");

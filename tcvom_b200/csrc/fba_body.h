@@ -87,7 +87,7 @@ TCV_HD float act_fn(float t, int act) {
 
 // ------------------------------------------------------------------------------------------ GroupNorm
 struct GnFinalizeP {
-  const double* sums;  // [n][c][2]
+  const double* sums;  // [copies][n][c][2]
   int n, c, groups;
   ll pixels;
   const float* gamma;
@@ -95,17 +95,20 @@ struct GnFinalizeP {
   float eps;
   float* scale;  // [n][c]
   float* shift;
+  int copies, clear;   // accumulator copies to sum (>= 1); clear: zero them after reading
 };
 // work item = (image, group); total = n * groups
 TCV_HD void gn_finalize_body(ll i, const GnFinalizeP& p) {
   const int img = (int)(i / p.groups), g = (int)(i % p.groups);
   const int cpg = p.c / p.groups;
   double s = 0.0, ss = 0.0;
-  for (int k = 0; k < cpg; ++k) {
-    const double* q = p.sums + ((ll)img * p.c + g * cpg + k) * 2;
-    s += q[0];
-    ss += q[1];
-  }
+  for (int cp = 0; cp < p.copies; ++cp)
+    for (int k = 0; k < cpg; ++k) {
+      double* q = const_cast<double*>(p.sums) + (((ll)cp * p.n + img) * p.c + g * cpg + k) * 2;
+      s += q[0];
+      ss += q[1];
+      if (p.clear) q[0] = q[1] = 0.0;
+    }
   const double cnt = (double)cpg * (double)p.pixels;
   const double mean = s / cnt;
   double var = ss / cnt - mean * mean;  // biased, as nn.GroupNorm

@@ -25,7 +25,7 @@ struct EpiParams {
   int res1_shift, act;
   int dbg;
   double* stats;      // optional per-(image group, channel) sum / sum of squares of the output (tcv_conv_desc.stats)
-  int stats_groups;
+  int stats_groups, stats_copies;
 };
 
 // Sum over the 32 lanes of a warp of 32 per-lane values: afterwards lane j holds the total of element j.  Recursive halving:
@@ -62,6 +62,7 @@ static inline void fill_epi(EpiParams& e, const tcv_conv_desc& d, int dbg) {
   e.dbg = dbg;
   e.stats = d.stats;
   e.stats_groups = d.stats_groups > 0 ? d.stats_groups : 1;
+  e.stats_copies = d.stats_copies > 0 ? d.stats_copies : 1;
 }
 
 // per-channel sum / sum of squares of the 32 pixels of this warp (rows outside the image were zeroed by the caller);
@@ -218,7 +219,8 @@ __device__ __forceinline__ void conv_epilogue(const EpiParams& p, uint32_t taddr
       float g[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) g[j] = valid ? f[j] : 0.f;
-      epi_stats(g, lane, p.stats + ((long long)(img % p.stats_groups) * p.cout + n0 + c0 + lane) * 2);
+      const int copy = (int)((blockIdx.x * 8u + (threadIdx.x >> 5)) % (unsigned)p.stats_copies);
+      epi_stats(g, lane, p.stats + (((long long)copy * p.stats_groups + img % p.stats_groups) * p.cout + n0 + c0 + lane) * 2);
     }
     if (st.stage_hi) {
       // the previous bulk store into THIS staging tile must have finished READING it

@@ -53,6 +53,7 @@ class FbaVmnEngine(GcaVmnEngine):
         self._pending_stats: Dict[int, torch.Tensor] = {}
 
     STATS_PATH = 4       # tcv_conv2d_path value of the kernel whose epilogue can accumulate statistics (conv_tc2p)
+    STATS_COPIES = 32
 
     # ------------------------------------------------------------------ weights
     def refresh_weights(self, net: torch.nn.Module, force=False) -> None:
@@ -161,9 +162,13 @@ class FbaVmnEngine(GcaVmnEngine):
                     _cabi.lib().tcv_conv2d_path(C.byref(d)) == self.STATS_PATH:
                 # per-(image, channel) sum / sum of squares of the output from the conv epilogue: the GroupNorm that
                 # follows (gn) skips its own pass over the tensor
-                sums = self._empty((x.n, cout, 2), torch.float64)
-                self._call("tcv_zero_bytes", sums.data_ptr(), sums.numel() * 8)
-                d.stats, d.stats_groups = sums.data_ptr(), x.n
+                # (STATS_COPIES accumulator copies: same-address fp64 atomics serialise in L2.  Zeroed once here; the
+                # finalize kernel clears them after reading, so replays need no memset -- which is why the buffer is pinned
+                # for the life of the plan instead of going back to the plan's memory pool.)
+                sums = torch.zeros((self.STATS_COPIES, x.n, cout, 2), dtype=torch.float64, device=self.device)
+                if self._rec is not None:
+                    self._rec.keep.append(sums)
+                d.stats, d.stats_groups, d.stats_copies = sums.data_ptr(), x.n, self.STATS_COPIES
                 self._pending_stats[y.ptr] = sums
             self._call("tcv_conv2d", C.byref(d), meta=self._conv_meta(d, wkey, x, k, stride))
             prev = y
@@ -221,8 +226,11 @@ class FbaVmnEngine(GcaVmnEngine):
             sums = self._empty((n, c, 2), torch.float64)
             self._call("tcv_gn_stats", z.ptr, z.plane, n, pixels, c, sums.data_ptr(),
                        meta=dict(kind="tcv_gn_stats", bytes=nbytes, layer=p))
-        self._call("tcv_gn_finalize", sums.data_ptr(), n, pixels, c, GN_GROUPS, gamma.data_ptr(), beta.data_ptr(),
-                   GN_EPS, scale.data_ptr(), shift.data_ptr())
+            self._call("tcv_gn_finalize", sums.data_ptr(), n, pixels, c, GN_GROUPS, gamma.data_ptr(), beta.data_ptr(),
+                       GN_EPS, scale.data_ptr(), shift.data_ptr())
+        else:
+            self._call("tcv_gn_finalize_acc", sums.data_ptr(), self.STATS_COPIES, 1, n, pixels, c, GN_GROUPS,
+                       gamma.data_ptr(), beta.data_ptr(), GN_EPS, scale.data_ptr(), shift.data_ptr())
         y = out if out is not None else self._act(n, z.h, z.w, c)
         assert (y.n, y.h, y.w) == (n, z.h, z.w) and out_off + c <= y.c
         if res is not None:

@@ -752,7 +752,13 @@ int tcv_gn_stats(const void* x, long long x_plane, int n, long long pixels, int 
 
 int tcv_gn_finalize(const double* sums, int n, long long pixels, int c, int groups, const float* gamma,
                     const float* beta, float eps, float* scale, float* shift, tcv_stream_t) {
-  GnFinalizeP p{sums, n, c, groups, pixels, gamma, beta, eps, scale, shift};
+  GnFinalizeP p{sums, n, c, groups, pixels, gamma, beta, eps, scale, shift, 1, 0};
+  return run_body<GnFinalizeP, gn_finalize_body>(p, (ll)n * groups);
+}
+
+int tcv_gn_finalize_acc(double* sums, int copies, int clear, int n, long long pixels, int c, int groups, const float* gamma,
+                        const float* beta, float eps, float* scale, float* shift, tcv_stream_t) {
+  GnFinalizeP p{sums, n, c, groups, pixels, gamma, beta, eps, scale, shift, copies, clear};
   return run_body<GnFinalizeP, gn_finalize_body>(p, (ll)n * groups);
 }
 

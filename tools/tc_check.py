@@ -161,14 +161,17 @@ def case_conv_stats(cin, cout, h, w, n, groups, dil=1):
         d.oy_mul, d.oy_off, d.ox_mul, d.ox_off = 1, 0, 1, 0
         d.b1 = bias.data_ptr()
         assert L.tcv_conv2d_path(C.byref(d)) == 4
-        sums = torch.full((groups, cout, 2), 7.0, dtype=torch.float64, device=dev)
+        copies = 5
+        sums = torch.full((copies, groups, cout, 2), 7.0, dtype=torch.float64, device=dev)
         if with_stats:
             _cabi.check(L.tcv_zero_bytes(sums.data_ptr(), sums.numel() * 8, st), "zero_bytes")
-            d.stats, d.stats_groups = sums.data_ptr(), groups
+            d.stats, d.stats_groups, d.stats_copies = sums.data_ptr(), groups, copies
         _cabi.check(L.tcv_conv2d(C.byref(d), st), "conv2d")
         torch.cuda.synchronize()
         outs.append((y, sums))
     (y0, _), (y1, sums) = outs
+    assert all(float(sums[k].abs().sum()) > 0 for k in range(sums.shape[0]))     # every accumulator copy was used
+    sums = sums.sum(dim=0)
     assert torch.equal(y0, y1)                                  # the statistics do not change the output
     v = (y1[0].double() + y1[1].double()).reshape(n // groups, groups, h * w, cout)
     ref = torch.stack([v.sum(dim=(0, 2)), (v * v).sum(dim=(0, 2))], dim=-1)
