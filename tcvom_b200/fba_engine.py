@@ -47,16 +47,12 @@ class FbaVmnEngine(GcaVmnEngine):
     def __init__(self, window: int):
         super().__init__(window)
         self.gn_params: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
-        # TCV_FBA_GN_FUSED=1: GroupNorm statistics accumulated by the epilogue of the producing convolution
-        # (tcv_conv_desc.stats) instead of a separate pass over its output.  Measured on B200 (1088x1920 window): the pass
-        # it removes costs 4.1 ms, but the convolutions get 4.6 ms slower and the 32-copy finalize 1.2 ms -- these layers
-        # (1x1 bottleneck convs, 5-6 tiles per CTA pair) are epilogue-bound, so the 62 shuffles + 2 atomics per 32-channel
-        # chunk are not hidden behind the MMAs.  Off by default; kept as a tested option of the C ABI.
-        self.fuse_gn_stats = os.environ.get("TCV_FBA_GN_FUSED", "0") == "1"
-        self._pending_stats: Dict[int, torch.Tensor] = {}
-
-    STATS_PATH = 4       # tcv_conv2d_path value of the kernel whose epilogue can accumulate statistics (conv_tc2p)
-    STATS_COPIES = 32
+        # GroupNorm statistics from the epilogue of the producing convolution (tcv_conv_desc.stats) were built and measured
+        # on B200 (1088x1920 window): the pass they remove costs 4.1 ms, the convolutions got 7.7 ms slower with one
+        # accumulator copy (same-address fp64 atomics) and 4.6 ms with 32 copies + 1.2 ms for the wider finalize -- these
+        # layers (1x1 bottleneck convs, 5-6 tiles per CTA pair) are epilogue-bound, the 62 shuffles + 2 atomics per
+        # 32-channel chunk are not hidden behind the MMAs.  The engine therefore keeps the separate tcv_gn_stats pass; the
+        # C-ABI option stays (tests/test_gpu_kernels.py::test_conv_epilogue_statistics).
 
     # ------------------------------------------------------------------ weights
     def refresh_weights(self, net: torch.nn.Module, force=False) -> None:
@@ -140,8 +136,7 @@ class FbaVmnEngine(GcaVmnEngine):
                         "pack_weight_tc")
 
     # ------------------------------------------------------------------ operators
-    def convf(self, x: Act, wkey: str, *, stride=1, dilation=1, bias=False, act=ACT_NONE, split_rows=False,
-              want_stats=False) -> Act:
+    def convf(self, x: Act, wkey: str, *, stride=1, dilation=1, bias=False, act=ACT_NONE, split_rows=False) -> Act:
         """k x k convolution (k in {1, 3}), padding = dilation * (k // 2), optional bias / activation epilogue.
 
         split_rows: one launch per filter row, chained through the residual input of the epilogue.  The tensor cores
@@ -162,18 +157,6 @@ class FbaVmnEngine(GcaVmnEngine):
             y = self._act(x.n, oh, ow, cout)
             d = self._desc(x, ent["w"].data_ptr(), taps, stride, PAD_ZERO, y, oh, ow, cout, oh, ow, 1, 0, 1, 0, wkey,
                            None, bias and last, act if last else ACT_NONE, prev, 0, None, None, 0, wtap=wtap)
-            if last and want_stats and act == ACT_NONE and self.fuse_gn_stats and cout % 32 == 0 and \
-                    _cabi.lib().tcv_conv2d_path(C.byref(d)) == self.STATS_PATH:
-                # per-(image, channel) sum / sum of squares of the output from the conv epilogue: the GroupNorm that
-                # follows (gn) skips its own pass over the tensor
-                # (STATS_COPIES accumulator copies: same-address fp64 atomics serialise in L2.  Zeroed once here; the
-                # finalize kernel clears them after reading, so replays need no memset -- which is why the buffer is pinned
-                # for the life of the plan instead of going back to the plan's memory pool.)
-                sums = torch.zeros((self.STATS_COPIES, x.n, cout, 2), dtype=torch.float64, device=self.device)
-                if self._rec is not None:
-                    self._rec.keep.append(sums)
-                d.stats, d.stats_groups, d.stats_copies = sums.data_ptr(), x.n, self.STATS_COPIES
-                self._pending_stats[y.ptr] = sums
             self._call("tcv_conv2d", C.byref(d), meta=self._conv_meta(d, wkey, x, k, stride))
             prev = y
         return prev
@@ -225,16 +208,11 @@ class FbaVmnEngine(GcaVmnEngine):
         scale = self._empty((n, c))
         shift = self._empty((n, c))
         nbytes = 4 * n * pixels * c
-        sums = self._pending_stats.pop(z.ptr, None)          # written by the epilogue of the convolution that made z
-        if sums is None:
-            sums = self._empty((n, c, 2), torch.float64)
-            self._call("tcv_gn_stats", z.ptr, z.plane, n, pixels, c, sums.data_ptr(),
-                       meta=dict(kind="tcv_gn_stats", bytes=nbytes, layer=p))
-            self._call("tcv_gn_finalize", sums.data_ptr(), n, pixels, c, GN_GROUPS, gamma.data_ptr(), beta.data_ptr(),
-                       GN_EPS, scale.data_ptr(), shift.data_ptr())
-        else:
-            self._call("tcv_gn_finalize_acc", sums.data_ptr(), self.STATS_COPIES, 1, n, pixels, c, GN_GROUPS,
-                       gamma.data_ptr(), beta.data_ptr(), GN_EPS, scale.data_ptr(), shift.data_ptr())
+        sums = self._empty((n, c, 2), torch.float64)
+        self._call("tcv_gn_stats", z.ptr, z.plane, n, pixels, c, sums.data_ptr(),
+                   meta=dict(kind="tcv_gn_stats", bytes=nbytes, layer=p))
+        self._call("tcv_gn_finalize", sums.data_ptr(), n, pixels, c, GN_GROUPS, gamma.data_ptr(), beta.data_ptr(),
+                   GN_EPS, scale.data_ptr(), shift.data_ptr())
         y = out if out is not None else self._act(n, z.h, z.w, c)
         assert (y.n, y.h, y.w) == (n, z.h, z.w) and out_off + c <= y.c
         if res is not None:
@@ -265,12 +243,12 @@ class FbaVmnEngine(GcaVmnEngine):
     def _bottleneck(self, x: Act, p: str, stride: int, dil: int, has_down: bool, dstride: int,
                     out: Optional[Act] = None) -> Act:
         """Bottleneck.forward (resnet_GN_WS.py:69-91)."""
-        o = self.gn(self.convf(x, p + ".conv1", want_stats=True), p + ".bn1", ACT_RELU)
-        o = self.gn(self.convf(o, p + ".conv2", stride=stride, dilation=dil, want_stats=True), p + ".bn2", ACT_RELU)
+        o = self.gn(self.convf(x, p + ".conv1"), p + ".bn1", ACT_RELU)
+        o = self.gn(self.convf(o, p + ".conv2", stride=stride, dilation=dil), p + ".bn2", ACT_RELU)
         z = self.convf(o, p + ".conv3")
         idt = x
         if has_down:
-            idt = self.gn(self.convf(x, p + ".downsample.0", stride=dstride, want_stats=True), p + ".downsample.1", ACT_NONE)
+            idt = self.gn(self.convf(x, p + ".downsample.0", stride=dstride), p + ".downsample.1", ACT_NONE)
         return self.gn(z, p + ".bn3", ACT_RELU, res=idt, out=out)
 
     def per_frame(self, x16: Act) -> dict:
@@ -296,11 +274,11 @@ class FbaVmnEngine(GcaVmnEngine):
             pooled = self._act(cat.n, s, s, 2048)
             self._call("tcv_adaptive_avgpool", cat.ptr, cat.plane, cat.n, h8, w8, 2048, cat.c, 0, s, pooled.ptr,
                        meta=dict(kind="tcv_adaptive_avgpool", bytes=4 * cat.n * h8 * w8 * 2048))
-            t = self.gn(self.convf(pooled, f"{d}.ppm.{i}.1", bias=True, want_stats=True), f"{d}.ppm.{i}.2", ACT_LEAKY001)
+            t = self.gn(self.convf(pooled, f"{d}.ppm.{i}.1", bias=True), f"{d}.ppm.{i}.2", ACT_LEAKY001)
             self.bilinear(t, h8, w8, cat, 2048 + 256 * i)
         split = os.environ.get("TCV_FBA_SPLIT_K", "1") == "1"
-        x = self.gn(self.convf(cat, d + ".conv_up1.0", bias=True, split_rows=split, want_stats=True), d + ".conv_up1.1", ACT_LEAKY001)
-        feat = self.gn(self.convf(x, d + ".conv_up1.3", bias=True, want_stats=True), d + ".conv_up1.4", ACT_LEAKY001)
+        x = self.gn(self.convf(cat, d + ".conv_up1.0", bias=True, split_rows=split), d + ".conv_up1.1", ACT_LEAKY001)
+        feat = self.gn(self.convf(x, d + ".conv_up1.3", bias=True), d + ".conv_up1.4", ACT_LEAKY001)
         return dict(feat=feat, l1=l1, c1=c1, x16=x16)
 
     def tail(self, pf: dict, n0: int, ncen: int, mask_ptr: int, mask_stride: int, H: int, W: int, pred_ptr: int,
@@ -315,11 +293,11 @@ class FbaVmnEngine(GcaVmnEngine):
         cat2 = self._act(ncen, l1.h, l1.w, 512)
         self.bilinear(t, l1.h, l1.w, cat2, 0)
         self.copy_channels(l1, 0, 256, cat2, 256)
-        x = self.gn(self.convf(cat2, d + ".conv_up2.0", bias=True, want_stats=True), d + ".conv_up2.1", ACT_LEAKY001)
+        x = self.gn(self.convf(cat2, d + ".conv_up2.0", bias=True), d + ".conv_up2.1", ACT_LEAKY001)
         cat3 = self._act(ncen, c1.h, c1.w, 320)
         self.bilinear(x, c1.h, c1.w, cat3, 0)
         self.copy_channels(c1, 0, 64, cat3, 256)
-        x = self.gn(self.convf(cat3, d + ".conv_up3.0", bias=True, want_stats=True), d + ".conv_up3.1", ACT_LEAKY001)
+        x = self.gn(self.convf(cat3, d + ".conv_up3.0", bias=True), d + ".conv_up3.1", ACT_LEAKY001)
         cat4 = self._act(ncen, H, W, 96)                       # 64 + 3 + 3 + 2 = 72 channels, zero-padded to 96
         self.bilinear(x, H, W, cat4, 0)
         self._call("tcv_fba_cat_inputs", x16.ptr, x16.plane, ncen * H * W, cat4.ptr, cat4.plane, cat4.c, 64,

@@ -243,27 +243,6 @@ def test_eval_forward_matches_reference_golden(case):
     assert float(alphas[:, 0].abs().max()) == 0 and float(alphas[:, -1].abs().max()) == 0
 
 
-def test_groupnorm_statistics_from_the_conv_epilogue():
-    """TCV_FBA_GN_FUSED=1 (off by default: measured slower, fba_engine.py): GroupNorm sums accumulated by the epilogue of the
-    producing convolution (tcv_conv_desc.stats, 32 accumulator copies, self-clearing finalize) give the same matte, also on
-    the second and third replay of the recorded plan."""
-    g = golden("fba_ring96x128.npz")
-    imgs, tris = torch.from_numpy(g["imgs"]).to(DEV), torch.from_numpy(g["tris"]).to(DEV)
-    outs = {}
-    for fused in (False, True):
-        m = _model(None)
-        m.NET.engine().fuse_gn_stats = fused
-        with torch.no_grad():
-            a = [m(imgs, tris)[0].clone() for _ in range(3)]
-        assert torch.equal(a[0], a[1]) or float((a[0] - a[1]).abs().max()) < 1e-5       # atomics: summation order
-        assert float((a[0] - a[2]).abs().max()) < 1e-5
-        kinds = [mm["kind"] for mm in list(m.NET.engine().plans.values())[0].meta]
-        assert ("tcv_gn_finalize_acc" in kinds) == fused
-        outs[fused] = a[0]
-    assert float(np.abs(outs[True].cpu().numpy() - g["alphas"]).max()) < ALPHA_TOL
-    assert float((outs[True] - outs[False]).abs().max()) < 2e-4
-
-
 def test_eval_forward_float_ingest_and_graph_replay():
     g = golden("fba_ring64.npz")
     m = _model()
