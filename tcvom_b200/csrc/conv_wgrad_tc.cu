@@ -85,7 +85,9 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
   const int tile_begin = slice * p.tiles_per_slice;
   const int tile_end = min(tile_begin + p.tiles_per_slice, p.total_tiles);
   const int iters = tile_end - tile_begin;
-  const uint32_t ncols_used = (uint32_t)(cblk * nb_b);
+  // (rows == 2: two accumulators side by side)
+  const uint32_t acc_cols = (uint32_t)(cblk * nb_b);
+  const uint32_t ncols_used = p.rows == 2 ? 2 * acc_cols : acc_cols;
   uint32_t ncols = 32;                                     // TMEM allocation: power of two >= columns used
   while (ncols < ncols_used) ncols <<= 1;
 
@@ -182,6 +184,15 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
             tc_mma(tmem_d, ah, bh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
             tc_mma(tmem_d, ah, bl, idesc, 1u);
             tc_mma(tmem_d, al, bh, idesc, 1u);
+            if (p.rows == 2) {
+              // 64-channel blocks: M = 128 holds two of the three dz row blocks; the third one (its upper half aliases
+              // the next buffer, never read) accumulates into a second accumulator
+              const uint64_t ah2 = smem_desc_mn(a_hi + 2 * WG_BLK + koff, a_lbo, rb);
+              const uint64_t al2 = smem_desc_mn(a_lo + 2 * WG_BLK + koff, a_lbo, rb);
+              tc_mma(tmem_d + acc_cols, ah2, bh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+              tc_mma(tmem_d + acc_cols, ah2, bl, idesc, 1u);
+              tc_mma(tmem_d + acc_cols, al2, bh, idesc, 1u);
+            }
           }
           tc_commit(empty_bar(s));
           if (it == iters - 1) tc_commit(accum_bar);
@@ -195,7 +206,29 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
       mbar_wait(accum_bar, 0);
       tc_fence_after();
       const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
-      if (p.rows) {
+      if (p.rows == 2) {
+        // 64-channel blocks.  accumulator 0: rows 0..63 = dz row block 0, 64..127 = block 1; accumulator 1: rows 0..63 =
+        // block 2.  columns = (horizontal shift c, input channel): c0 = c * 64 + ci
+        const int co = (q & 1) * 32 + lane;
+#pragma unroll 1
+        for (int acc = 0; acc < 2; ++acc) {
+          const int blk = acc * 2 + (q >> 1);
+          if (blk > 2) continue;
+#pragma unroll 1
+          for (int c0 = 0; c0 < (int)acc_cols; c0 += 32) {
+            uint32_t v[32];
+            tc_ld32(taddr + acc * acc_cols + c0, v);
+            if (co >= p.dz_c) continue;
+            const int c = c0 >> 6, ci0 = c0 & 63;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float f = __uint_as_float(v[i]);
+              if (ci0 + i < p.cin && f != 0.f)
+                atomicAdd(p.dw + ((long long)p.wtap3[blk * 3 + c] * p.cin + ci0 + i) * p.dz_c + co, f);
+            }
+          }
+        }
+      } else if (p.rows) {
         // accumulator rows = (output row block b = this warp, output channel), columns = (horizontal shift, input channel)
         if (q < 3) {
 #pragma unroll 1
@@ -315,7 +348,9 @@ int conv2d_wgrad_tc(const tcv_conv_desc& d, const __nv_bfloat16* dz, long long d
   }
   // rows mode: nine unit-spaced taps of a stride-1 narrow layer in one MMA (see WgParams)
   int x_w = d.iw, x_c = d.cin;                 // geometry of the x tensor map (fold: overlapping 24-"channel" pixels)
-  if (narrow && d.stride == 1 && p.mul == 1 && p.oy == 0 && p.ox == 0 && d.ntaps == 9 && !(g_debug_flags.load() & (1 << 20))) {
+  const bool mid = !narrow && d.cin <= 64 && dz_c <= 64;       // 64-channel blocks: rows mode with two accumulators
+  if ((narrow || (mid && !(g_debug_flags.load() & (1 << 21)))) && d.stride == 1 && p.mul == 1 && p.oy == 0 && p.ox == 0 &&
+      d.ntaps == 9 && !(g_debug_flags.load() & (1 << 20))) {
     int dy0 = d.dy[0], dx0 = d.dx[0];
     for (int t = 1; t < 9; ++t) { dy0 = std::min(dy0, d.dy[t]); dx0 = std::min(dx0, d.dx[t]); }
     bool grid3 = true;
@@ -327,13 +362,13 @@ int conv2d_wgrad_tc(const tcv_conv_desc& d, const __nv_bfloat16* dz, long long d
       p.wtap3[b * 3 + c] = d.wtap[t];
     }
     if (grid3 && seen == 0x1FF) {
-      p.rows = 1; p.swap = 0;
+      p.rows = mid ? 2 : 1; p.swap = 0;
       p.dy0 = dy0; p.dx0 = dx0;
       p.y_first = std::max(0, dy0);
       const int y_count = std::min(d.ih, d.gh + dy0 + 2) - p.y_first;
       p.tiles_y = (y_count + p.TH - 1) / p.TH;
       p.total_tiles = d.n * p.tiles_x * p.tiles_y;
-      p.fold = (d.cin == 8 && dx0 >= 0) ? 1 : 0;
+      p.fold = (!mid && d.cin == 8 && dx0 >= 0) ? 1 : 0;
       p.nbx = p.fold ? 1 : 3;
       if (p.fold) { x_w = d.iw - 2; x_c = 24; }
       p.idesc = (p.idesc & ~(0x3Fu << 17)) | ((uint32_t)((p.nbx * cblk) >> 3) << 17);

@@ -66,7 +66,10 @@ def test_conv_cta_pair_kernel(cin, cout, h, w, n, kind):
     (32, 8, 18, 40, 3, False, 0, True),          # 8 output channels, 32 x 2 tiles
     (16, 32, 20, 24, 1, True, 0, False),         # 16 x 4 tiles
     (32, 32, 40, 72, 2, False, 1 << 20, False),  # the stacked-tap mode the rows mode replaces
-    (64, 64, 20, 72, 2, False, 0, False),        # stacked taps, 64 channels
+    (64, 64, 20, 72, 2, False, 0, False),        # rows mode with 64-channel blocks: two accumulators
+    (32, 64, 24, 136, 2, True, 0, True),         # ... 32 input channels in a 64-channel box, pre-padded, shuffled taps
+    (64, 32, 18, 40, 3, False, 0, False),        # ... 32 output channels, 32 x 2 tiles
+    (64, 64, 20, 72, 2, False, 1 << 21, False),  # the stacked-tap mode it replaces (64 channels)
     (128, 256, 12, 40, 2, False, 0, False),      # wide layers: one CTA per tap and 128 x 128 tile
 ])
 def test_wgrad_nhwc_tc(cin, cout, h, w, n, prepad, flags, perm):
