@@ -367,14 +367,17 @@ int tcv_bn_finalize(const double* sums, double count, double unbiased_count, int
                     tcv_stream_t stream);
 int tcv_bn_apply(const tcv_bn_desc* d, tcv_stream_t stream);
 /* e = dL/d(BN output): mode 1 dy * act'(BN(t0)+res1) (written to e; it is also the gradient of res1 before
- * down-pooling), mode 2 dy itself (e may be NULL).  sums[g][c] = (sum e, sum e*xhat), zeroed here. */
+ * down-pooling), mode 2 dy itself (e may be NULL).  sums[g][c] = (sum e, sum e*xhat), zeroed here.
+ * Mode 1 WITHOUT res1 may pass e == NULL as well: nothing but tcv_bn_bwd_apply reads e then, and it can recompute it from dy
+ * (e_is_dy) -- one full-tensor write less per such layer. */
 int tcv_bn_bwd_reduce(const tcv_bn_desc* d, const void* dy, long long dy_plane, void* e, long long e_plane,
                       double* sums, tcv_stream_t stream);
 /* dgamma[c] += sum_g sums[g][c][1], dbeta[c] += sum_g sums[g][c][0] (local sums, before any all-reduce) */
 int tcv_bn_param_grads(const double* sums, int groups, int c, float* dgamma, float* dbeta, tcv_stream_t stream);
-/* dz = dL/dz from e and the (all-reduced) sums; zdot[g] += sum z*dz (NULL to skip; feeds the sigma gradient) */
+/* dz = dL/dz from e and the (all-reduced) sums; zdot[g] += sum z*dz (NULL to skip; feeds the sigma gradient).
+ * e_is_dy != 0 (mode 1 without res1): `e` holds dy and e = dy * act'(BN(t0)) is recomputed here */
 int tcv_bn_bwd_apply(const tcv_bn_desc* d, const void* e, long long e_plane, const double* sums, double count,
-                     void* dz, long long dz_plane, double* zdot, tcv_stream_t stream);
+                     void* dz, long long dz_plane, double* zdot, int e_is_dy, tcv_stream_t stream);
 /* zdot[g] += sum over images of group g of z*dz  (layers whose spectral-norm conv is not followed by BatchNorm) */
 int tcv_group_dot(const void* z, long long z_plane, const void* dz, long long dz_plane, int n, long long img_elems,
                   int groups, double* zdot, tcv_stream_t stream);

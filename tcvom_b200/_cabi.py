@@ -154,7 +154,7 @@ SIGNATURES = {
     "tcv_bn_bwd_reduce": (c_int, [C.POINTER(BnDesc), c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p]),
     "tcv_bn_param_grads": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "tcv_bn_bwd_apply": (c_int, [C.POINTER(BnDesc), c_void_p, c_ll, c_void_p, c_double, c_void_p, c_ll, c_void_p,
-                                 c_void_p]),
+                                 c_int, c_void_p]),
     "tcv_group_dot": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_ll, c_int, c_void_p, c_void_p]),
     "tcv_conv2d_wgrad": (c_int, [C.POINTER(ConvDesc), c_void_p, c_ll, c_int, c_void_p, c_void_p]),
     "tcv_transpose_pad": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const tcv_bn_desc d,
         const float tpre = xh[k] * ga[k] + be[k] + r[k];
         gy[k] *= act_grad(tpre, d.act);
       }
-      store8(e + pix * d.c + ch, e_plane, gy);
+      if (e) store8(e + pix * d.c + ch, e_plane, gy);
     } else {
 #pragma unroll
       for (int k = 0; k < 8; ++k) xh[k] = (apply_act(f[k] * is, d.act) - mu[k]) * iv[k];
@@ -212,17 +212,20 @@ __global__ void bn_param_grads_kernel(const double* __restrict__ sums, int group
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const tcv_bn_desc d, const __nv_bfloat16* __restrict__ e,
                                                            long long e_plane, const double* __restrict__ sums,
                                                            double count, __nv_bfloat16* __restrict__ dz,
-                                                           long long dz_plane, double* __restrict__ zdot, int pix) {
+                                                           long long dz_plane, double* __restrict__ zdot, int pix,
+                                                           int e_is_dy) {
   __shared__ double dred[8];
   const BnGeom q = bn_geom(d, pix);
   const long long ibase = (long long)q.img * d.h * d.w;
   const int ch = q.cg * 8;
   const float is = d.inv_sigma ? d.inv_sigma[q.g] : 1.f;
-  float mu[8], iv[8], m1[8], m2[8], gi[8];
+  float mu[8], iv[8], m1[8], m2[8], gi[8], ga[8], be[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     mu[k] = d.mean[q.g * d.c + ch + k];
     iv[k] = d.invstd[q.g * d.c + ch + k];
+    ga[k] = d.gamma[ch + k];
+    be[k] = d.beta[ch + k];
     gi[k] = d.gamma[ch + k] * iv[k];
     m1[k] = (float)(sums[((long long)q.g * d.c + ch + k) * 2] / count);
     m2[k] = (float)(sums[((long long)q.g * d.c + ch + k) * 2 + 1] / count);
@@ -238,6 +241,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const tcv_bn_desc d, 
       const float t0 = f[k] * is;
       if (d.mode == 1) {
         const float xh = (t0 - mu[k]) * iv[k];
+        if (e_is_dy) ge[k] *= act_grad(xh * ga[k] + be[k], d.act);     // same expression as bn_bwd_reduce (no res1)
         o[k] = gi[k] * (ge[k] - m1[k] - xh * m2[k]) * is;
       } else {
         const float xh = (apply_act(t0, d.act) - mu[k]) * iv[k];
@@ -365,7 +369,7 @@ int tcv_bn_bwd_reduce(const tcv_bn_desc* dp, const void* dy, long long dy_plane,
   const tcv_bn_desc d = with_defaults(dp);
   int rc = check_desc(d, "bn_bwd_reduce");
   if (rc) return rc;
-  TCV_REQUIRE(d.mode == 2 || e, "bn_bwd_reduce: mode 1 needs the e output");
+  TCV_REQUIRE(d.mode == 2 || e || !d.res1, "bn_bwd_reduce: mode 1 with a residual input needs the e output");
   const long long full = (long long)d.n * d.h * d.w * d.c;
   TCV_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * d.groups * d.c, S(stream)));
   const int pix = bn_pix(d);
@@ -383,17 +387,18 @@ int tcv_bn_param_grads(const double* sums, int groups, int c, float* dgamma, flo
 }
 
 int tcv_bn_bwd_apply(const tcv_bn_desc* dp, const void* e, long long e_plane, const double* sums, double count,
-                     void* dz, long long dz_plane, double* zdot, tcv_stream_t stream) {
+                     void* dz, long long dz_plane, double* zdot, int e_is_dy, tcv_stream_t stream) {
   TCV_REQUIRE(dp && e && sums && dz && count > 0, "bn_bwd_apply: null pointer");
   const tcv_bn_desc d = with_defaults(dp);
   int rc = check_desc(d, "bn_bwd_apply");
   if (rc) return rc;
+  TCV_REQUIRE(!e_is_dy || (d.mode == 1 && !d.res1), "bn_bwd_apply: e_is_dy is for mode 1 without a residual input");
   const long long full = (long long)d.n * d.h * d.w * d.c;
   const int pix = bn_pix(d);
   bn_bwd_apply_kernel<<<bn_grid(d, pix), 256, 0, S(stream)>>>(d, reinterpret_cast<const __nv_bfloat16*>(e),
                                                              e_plane ? e_plane : full, sums, count,
                                                              reinterpret_cast<__nv_bfloat16*>(dz),
-                                                             dz_plane ? dz_plane : full, zdot, pix);
+                                                             dz_plane ? dz_plane : full, zdot, pix, e_is_dy);
   return launched("bn_bwd_apply_kernel");
 }
 

@@ -448,11 +448,15 @@ class TrainEngine(GcaVmnEngine):
                 return
             _ = keep
             bsums = torch.empty((groups, c, 2), dtype=torch.float64, device=dev)
-            if mode == 1:
+            e_is_dy = 0
+            if mode == 1 and res1 is not None:
                 e = self._act(za.n, za.h, za.w, c)
                 self._call("tcv_bn_bwd_reduce", C.byref(d), dy.ptr, dy.plane, e.ptr, e.plane, bsums.data_ptr(), meta=tag)
             else:
+                # mode 2, or mode 1 without a residual input: nothing but tcv_bn_bwd_apply needs e = dy * act'(...), which it
+                # recomputes from dy (one full-tensor write less)
                 e = dy
+                e_is_dy = 1 if mode == 1 else 0
                 self._call("tcv_bn_bwd_reduce", C.byref(d), dy.ptr, dy.plane, None, 0, bsums.data_ptr(), meta=tag)
             dg, db = self.dbn.get(bnkey, (None, None))
             if dg is None:
@@ -463,7 +467,7 @@ class TrainEngine(GcaVmnEngine):
                 self._allreduce_sums(bsums)
             dz = self._act(za.n, za.h, za.w, c)
             self._call("tcv_bn_bwd_apply", C.byref(d), e.ptr, e.plane, bsums.data_ptr(), count, dz.ptr, dz.plane,
-                       sn["zdot"].data_ptr() if sn is not None else None, meta=tag)
+                       sn["zdot"].data_ptr() if sn is not None else None, e_is_dy, meta=tag)
             self._acc(z, dz, True)
             if res1 is not None and res1.needs_grad:
                 if res1_shift:
