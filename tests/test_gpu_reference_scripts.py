@@ -84,6 +84,30 @@ def test_pred_test_script_runs_on_the_native_package(tmp_path):
     assert unknown > 0.05 and any(len(np.unique(o)) > 8 for o in outs["native"]), "vacuous clip"
 
 
+def test_pred_test_script_runs_vmn_dim_on_the_native_package(tmp_path):
+    """The same script with --model vmn_dim: install() routes EvalModel('vmn_dim') to the native DIM+TAM
+    path.  Max-unpooling makes the matte discontinuous in the arg-max routing, and the reference's own GPU run
+    computes its convolutions in TF32, so the two PNG sets are compared statistically; the rigorous parity test is
+    tests/test_gpu_dim.py."""
+    import cv2
+    from helpers import fixture_sd_dim
+    H, W, T = 96, 128, 4
+    data = tmp_path / "data"
+    _write_clip(str(data / "clip0"), H, W, T)
+    ckpt = str(tmp_path / "fixture_dim.pth")
+    torch.save(fixture_sd_dim(), ckpt)
+    outs = {}
+    for arm, flags in (("native", ["--native"]), ("reference", [])):
+        save = str(tmp_path / f"out_{arm}")
+        _run(flags + ["pred_test.py", "--model", "vmn_dim", "--load", ckpt, "--data", str(data), "--save", save, "--gpu", "0"])
+        outs[arm] = [cv2.imread(os.path.join(save, "clip0", f"{t:04d}_alpha.png"), cv2.IMREAD_GRAYSCALE) for t in range(T)]
+        assert all(o is not None and o.shape == (H, W) for o in outs[arm]), arm
+    for t in range(T):
+        d = np.abs(outs["native"][t].astype(np.int32) - outs["reference"][t].astype(np.int32))
+        assert np.median(d) <= 1 and (d <= 3).mean() > 0.95 and d.max() <= 40, (t, float(np.median(d)), float((d <= 3).mean()), int(d.max()))
+    assert any(len(np.unique(o)) > 8 for o in outs["native"]), "vacuous clip"
+
+
 def _train_cfg(tmp_path, ckpt):
     cfg = tmp_path / "gca_tiny.yaml"
     cfg.write_text(
