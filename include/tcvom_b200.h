@@ -583,6 +583,15 @@ int tcv_dim_fix_inputs(const void* tris, int is_u8, int frames, int h, int w, vo
 int tcv_head_conv5_clamp01(const void* x, long long x_plane, int n, int h, int w, const float* wt, const float* bias,
                            float* pred, tcv_stream_t stream);
 
+/* C[b] = A[b] . B[b]^T (bf16x3, fp32 out) on the CTA-pair kernel (gemm_tc2.cu) with either operand
+ *   K-major  (x_mn == 0): split-bf16 [batch][rows][ld], the reduction index contiguous (K <= ld), or
+ *   MN-major (x_mn != 0): split-bf16 [batch][K][ld], the ROW index contiguous (rows <= ld); any K (TMA zero-fills the tail):
+ * the operand of a "transposed" product is read as its producer left it -- the attention backward (dF = A2^T.dO2,
+ * dKn = dS^T.Q, dA2 = dO2.F^T, dQ = dS.Kn) needs no transposed copies.  M >= 512, N >= 256; planes / strides in elements. */
+int tcv_gemm_tc_ex(const void* A, long long a_plane, long long a_ld, long long a_batch_stride, int a_mn, const void* B,
+                   long long b_plane, long long b_ld, long long b_batch_stride, int b_mn, float* C, int M, int N, int K,
+                   long long ldc, long long c_batch_stride, int batch, tcv_stream_t stream);
+
 /* ---- training side of the shift-sum aggregation (csrc/gca_train2.cu; autograd of GCA/ops.py:112-118,204):
  *  shift_add_u:        A fp32 [n][P][lda] (softmax on the unpadded key grid) -> A2 split-bf16 planes [2][n][Pk][ld]
  *  shift_gather:       dA2 fp32 [n][Pk][ld] -> dA fp32 [n][P][lda],  dA[q][p] = sum_a dA2[q+a][p+a]

@@ -126,6 +126,8 @@ SIGNATURES = {
     "tcv_head_tanh01": (c_int, [c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p]),
     "tcv_gn_finalize_acc": (c_int, [c_void_p, c_int, c_int, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p,
                                     c_void_p, c_void_p]),
+    "tcv_gemm_tc_ex": (c_int, [c_void_p, c_ll, c_ll, c_ll, c_int, c_void_p, c_ll, c_ll, c_ll, c_int, c_void_p, c_int, c_int,
+                               c_int, c_ll, c_ll, c_int, c_void_p]),
     "tcv_zero_bytes": (c_int, [c_void_p, c_ll, c_void_p]),
     "tcv_maxpool2_idx": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "tcv_maxunpool2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -85,7 +85,17 @@ __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
                : "memory");
 }
 
-template <int CG, int BK>
+// MN-major operand descriptor (operand stored [K][MN], MN contiguous: a TMA box {64 MN elements, BK rows of K} is the canonical
+// SWIZZLE_128B MN-major layout, see conv_wgrad_tc.cu): LBO = bytes between 64-element MN blocks, SBO = 8 K rows
+__device__ __forceinline__ uint64_t g2_desc_mn(uint32_t addr, uint32_t lbo_bytes) {
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)((8 * 128) >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+
+// AMN / BMN: the A / B operand is given MN-major ([batch][K][ld], rows = reduction index) instead of K-major ([batch][rows][K]):
+// the backward GEMMs of the attention (dF = A2^T.dO2, dKn = dS^T.Q, dA2 = dO2.F^T, dQ = dS.Kn) read their operands as the
+// forward left them, without transposed copies.  BK = 64 only; K need not be a multiple of BK (TMA zero-fills the tail rows).
+template <int CG, int BK, bool AMN = false, bool BMN = false>
 __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi,
                                                           const __grid_constant__ CUtensorMap mapA_lo,
                                                           const __grid_constant__ CUtensorMap mapB_hi,
@@ -164,10 +174,26 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
           if constexpr (CG == 2) {
             if (leader) mbar_expect_tx(full_bar(s), 2u * Cfg::STAGE);
             const uint32_t fb = mapa(full_bar(s), 0);
-            tma_load_3d_pair(st, &mapA_hi, fb, k0, m0, b);
-            tma_load_3d_pair(st + Cfg::A_PLANE, &mapA_lo, fb, k0, m0, b);
-            tma_load_3d_pair(st + 2 * Cfg::A_PLANE, &mapB_hi, fb, k0, n0, b);
-            tma_load_3d_pair(st + 2 * Cfg::A_PLANE + Cfg::B_PLANE, &mapB_lo, fb, k0, n0, b);
+            if constexpr (AMN) {      // two boxes {64 rows of M, BK rows of K} per plane
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                tma_load_3d_pair(st + j * (Cfg::A_PLANE / 2), &mapA_hi, fb, m0 + 64 * j, k0, b);
+                tma_load_3d_pair(st + Cfg::A_PLANE + j * (Cfg::A_PLANE / 2), &mapA_lo, fb, m0 + 64 * j, k0, b);
+              }
+            } else {
+              tma_load_3d_pair(st, &mapA_hi, fb, k0, m0, b);
+              tma_load_3d_pair(st + Cfg::A_PLANE, &mapA_lo, fb, k0, m0, b);
+            }
+            if constexpr (BMN) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                tma_load_3d_pair(st + 2 * Cfg::A_PLANE + j * (Cfg::B_PLANE / 2), &mapB_hi, fb, n0 + 64 * j, k0, b);
+                tma_load_3d_pair(st + 2 * Cfg::A_PLANE + Cfg::B_PLANE + j * (Cfg::B_PLANE / 2), &mapB_lo, fb, n0 + 64 * j, k0, b);
+              }
+            } else {
+              tma_load_3d_pair(st + 2 * Cfg::A_PLANE, &mapB_hi, fb, k0, n0, b);
+              tma_load_3d_pair(st + 2 * Cfg::A_PLANE + Cfg::B_PLANE, &mapB_lo, fb, k0, n0, b);
+            }
           } else {
             mbar_expect_tx(full_bar(s), (uint32_t)Cfg::STAGE);
             tma_load_3d(st, &mapA_hi, full_bar(s), k0, m0, b);
@@ -198,8 +224,23 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < Cfg::BK / 16; ++ks) {
-              const uint64_t ah = smem_desc_join<Cfg::BK>(a32 + 2 * ks), al = smem_desc_join<Cfg::BK>(al32 + 2 * ks);
-              const uint64_t bh = smem_desc_join<Cfg::BK>(b32 + 2 * ks), bl = smem_desc_join<Cfg::BK>(bl32 + 2 * ks);
+              uint64_t ah, al, bh, bl;
+              if constexpr (AMN) {     // 16 K rows of 128 B further per K step; 64-row M blocks A_PLANE / 2 apart
+                const uint32_t a0 = smem_base + s * Cfg::STAGE + ks * 2048;
+                ah = g2_desc_mn(a0, Cfg::A_PLANE / 2);
+                al = g2_desc_mn(a0 + Cfg::A_PLANE, Cfg::A_PLANE / 2);
+              } else {
+                ah = smem_desc_join<Cfg::BK>(a32 + 2 * ks);
+                al = smem_desc_join<Cfg::BK>(al32 + 2 * ks);
+              }
+              if constexpr (BMN) {
+                const uint32_t b0 = smem_base + s * Cfg::STAGE + 2 * Cfg::A_PLANE + ks * 2048;
+                bh = g2_desc_mn(b0, Cfg::B_PLANE / 2);
+                bl = g2_desc_mn(b0 + Cfg::B_PLANE, Cfg::B_PLANE / 2);
+              } else {
+                bh = smem_desc_join<Cfg::BK>(b32 + 2 * ks);
+                bl = smem_desc_join<Cfg::BK>(bl32 + 2 * ks);
+              }
               const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
               if constexpr (CG == 2) {
                 tc_mma_pair(d, ah, bh, p.idesc, acc);
@@ -278,41 +319,54 @@ static inline uint32_t instr_desc_mn(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// One operand of the GEMM.  K-major: [batch][rows][ld], ld >= K elements per row (zero beyond K when ld > K is read: K is a
+// multiple of BK there).  MN-major: [batch][K][ld], ld >= rows.
+struct G2Operand {
+  const void* p;
+  long long plane;          // elements between the hi and lo plane
+  long long ld;             // row pitch in elements
+  long long batch_stride;   // elements between batches
+  int mn_major;
+};
+
 template <int CG, int BK>
-static int launch_gemm_tc2(const void* A, long long a_plane, const void* B, long long b_plane, float* C, int M, int N, int K,
+static int g2_make_maps(CUtensorMap* hi, CUtensorMap* lo, const G2Operand& o, int rows, int K, int batch, int box_rows) {
+  const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(o.p);
+  if (o.mn_major) {
+    cuuint64_t dims[3] = {(cuuint64_t)rows, (cuuint64_t)K, (cuuint64_t)batch};
+    cuuint64_t str[2] = {(cuuint64_t)o.ld * 2, (cuuint64_t)o.batch_stride * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)BK, 1};
+    int rc = make_map(hi, a, 3, dims, str, box, 64);
+    if (rc) return rc;
+    return make_map(lo, a + o.plane, 3, dims, str, box, 64);
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t str[2] = {(cuuint64_t)o.ld * 2, (cuuint64_t)o.batch_stride * 2};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  int rc = make_map(hi, a, 3, dims, str, box, BK);
+  if (rc) return rc;
+  return make_map(lo, a + o.plane, 3, dims, str, box, BK);
+}
+
+template <int CG, int BK, bool AMN = false, bool BMN = false>
+static int launch_gemm_tc2(const G2Operand& A, const G2Operand& B, float* C, int M, int N, int K,
                            long long ldc, long long c_batch_stride, int batch, cudaStream_t st) {
   using Cfg = G2Cfg<CG, BK>;
   CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
-  const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(A);
-  const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(B);
-  {
-    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)M, (cuuint64_t)batch};
-    cuuint64_t str[2] = {(cuuint64_t)K * 2, (cuuint64_t)M * K * 2};
-    cuuint32_t box[3] = {(cuuint32_t)Cfg::BK, 128, 1};
-    int rc = make_map(&mA_hi, a, 3, dims, str, box, Cfg::BK);
-    if (rc) return rc;
-    rc = make_map(&mA_lo, a + a_plane, 3, dims, str, box, Cfg::BK);
-    if (rc) return rc;
-  }
-  {
-    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)batch};
-    cuuint64_t str[2] = {(cuuint64_t)K * 2, (cuuint64_t)N * K * 2};
-    cuuint32_t box[3] = {(cuuint32_t)Cfg::BK, (cuuint32_t)Cfg::B_ROWS, 1};
-    int rc = make_map(&mB_hi, b, 3, dims, str, box, Cfg::BK);
-    if (rc) return rc;
-    rc = make_map(&mB_lo, b + b_plane, 3, dims, str, box, Cfg::BK);
-    if (rc) return rc;
-  }
+  int rc = g2_make_maps<CG, BK>(&mA_hi, &mA_lo, A, M, K, batch, 128);
+  if (rc) return rc;
+  rc = g2_make_maps<CG, BK>(&mB_hi, &mB_lo, B, N, K, batch, Cfg::B_ROWS);
+  if (rc) return rc;
   G2Params p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.batch = batch;
   p.tiles_m = (M + 128 * CG - 1) / (128 * CG);
   p.tiles_n = (N + Cfg::BN - 1) / Cfg::BN;
   p.total_tiles = p.tiles_m * p.tiles_n * batch;
-  p.kc_iters = K / Cfg::BK;
+  p.kc_iters = (K + Cfg::BK - 1) / Cfg::BK;
   p.c = C; p.ldc = ldc; p.c_batch_stride = c_batch_stride;
-  p.idesc = instr_desc_mn(128 * CG, Cfg::BN);
-  auto kern = gemm_tc2_kernel<CG, BK>;
+  p.idesc = instr_desc_mn(128 * CG, Cfg::BN) | (AMN ? (1u << 15) : 0u) | (BMN ? (1u << 16) : 0u);
+  auto kern = gemm_tc2_kernel<CG, BK, AMN, BMN>;
   TCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
   int dev = 0, sms = 0;
   TCV_CUDA(cudaGetDevice(&dev));
@@ -336,10 +390,37 @@ static int launch_gemm_tc2(const void* A, long long a_plane, const void* B, long
 int gemm_tc2(const void* A, long long a_plane, const void* B, long long b_plane, float* C, int M, int N, int K, long long ldc,
              long long c_batch_stride, int batch, int mode, cudaStream_t st) {
   const bool bk32 = (g_debug_flags.load() & 262144) != 0;      // A/B switch: BK = 32 stages
+  const G2Operand a{A, a_plane, K, (long long)M * K, 0}, b{B, b_plane, K, (long long)N * K, 0};
   if (mode == 2)
-    return bk32 ? launch_gemm_tc2<2, 32>(A, a_plane, B, b_plane, C, M, N, K, ldc, c_batch_stride, batch, st)
-                : launch_gemm_tc2<2, 64>(A, a_plane, B, b_plane, C, M, N, K, ldc, c_batch_stride, batch, st);
-  return launch_gemm_tc2<1, 32>(A, a_plane, B, b_plane, C, M, N, K, ldc, c_batch_stride, batch, st);
+    return bk32 ? launch_gemm_tc2<2, 32>(a, b, C, M, N, K, ldc, c_batch_stride, batch, st)
+                : launch_gemm_tc2<2, 64>(a, b, C, M, N, K, ldc, c_batch_stride, batch, st);
+  return launch_gemm_tc2<1, 32>(a, b, C, M, N, K, ldc, c_batch_stride, batch, st);
+}
+
+// general operand layouts on the CTA-pair kernel (tcv_gemm_tc_ex)
+int gemm_tc2_ex(const G2Operand& a, const G2Operand& b, float* C, int M, int N, int K, long long ldc, long long c_batch_stride,
+                int batch, cudaStream_t st) {
+  if (a.mn_major && b.mn_major) return launch_gemm_tc2<2, 64, true, true>(a, b, C, M, N, K, ldc, c_batch_stride, batch, st);
+  if (a.mn_major) return launch_gemm_tc2<2, 64, true, false>(a, b, C, M, N, K, ldc, c_batch_stride, batch, st);
+  if (b.mn_major) return launch_gemm_tc2<2, 64, false, true>(a, b, C, M, N, K, ldc, c_batch_stride, batch, st);
+  return launch_gemm_tc2<2, 64>(a, b, C, M, N, K, ldc, c_batch_stride, batch, st);
 }
 
 }  // namespace tcv
+
+// C[b] = A[b] . B[b]^T (bf16x3, fp32 out) on the CTA-pair kernel with either operand K-major ([batch][rows][ld], K contiguous)
+// or MN-major ([batch][K][ld], rows contiguous).  Any K: TMA zero-fills what lies beyond the K extent of either operand.
+extern "C" int tcv_gemm_tc_ex(const void* A, long long a_plane, long long a_ld, long long a_batch_stride, int a_mn,
+                              const void* B, long long b_plane, long long b_ld, long long b_batch_stride, int b_mn, float* C,
+                              int M, int N, int K, long long ldc, long long c_batch_stride, int batch, tcv_stream_t stream) {
+  using namespace tcv;
+  TCV_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && batch > 0, "gemm_tc_ex: bad arguments");
+  TCV_REQUIRE(M >= 512 && N >= 256, "gemm_tc_ex: the CTA-pair kernel needs M >= 512 and N >= 256");
+  TCV_REQUIRE(a_ld % 8 == 0 && b_ld % 8 == 0 && ldc % 4 == 0 && a_batch_stride % 8 == 0 && b_batch_stride % 8 == 0,
+              "gemm_tc_ex: pitches must keep 16-byte alignment");
+  TCV_REQUIRE(a_ld >= (a_mn ? M : K) && b_ld >= (b_mn ? N : K), "gemm_tc_ex: pitch smaller than the row");
+  TCV_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0 && a_plane % 8 == 0 &&
+              b_plane % 8 == 0, "gemm_tc_ex: pointers must be 16-byte aligned");
+  const G2Operand a{A, a_plane, a_ld, a_batch_stride, a_mn}, b{B, b_plane, b_ld, b_batch_stride, b_mn};
+  return gemm_tc2_ex(a, b, C, M, N, K, ldc, c_batch_stride, batch, S(stream));
+}

@@ -66,6 +66,8 @@ class TrainEngine(GcaVmnEngine):
         self.use_head32 = os.environ.get("TCV_HEAD32", "1") == "1"
         # training GCA in the shift-sum form (value GEMM and its two backward GEMMs 3.8x smaller); "0": round-1 fold form
         self.gca_shift_sum_train = os.environ.get("TCV_GCA_SHIFT_SUM_TRAIN", "1") != "0"
+        # attention-backward GEMMs with MN-major operands (tcv_gemm_tc_ex) instead of transposed copies; "0": transposes
+        self.gca_mn_gemm = os.environ.get("TCV_GCA_MN_GEMM", "1") != "0"
         self.use_tc_wgrad = os.environ.get("TCV_TC_WGRAD", "1") != "0"
         # "2": the NHWC-direct kernel (MN-major operands, no channel-major copies); "1": the split-K GEMM over copies
         self.wgrad_nhwc = os.environ.get("TCV_TC_WGRAD", "2") == "2"
@@ -690,6 +692,17 @@ class TrainEngine(GcaVmnEngine):
             self._call("tcv_gemm_tn_tc", A_.data_ptr(), n * a_rows * K_, B_.data_ptr(), n * b_rows * K_, C_.data_ptr(),
                        a_rows, b_rows, K_, ldc, a_rows * ldc, n, 3, 0, 0)
 
+        def gemm_ex(A_, a_mn, B_, b_mn, M_, N_, K_, C_, ldc):
+            """C[M x N] = A . B^T on the CTA-pair kernel; an operand [2][n][r][ld] is K-major (r = its rows, K_ <= ld) or
+            MN-major (r = K_ rows of the reduction index, its rows <= ld): no transposed copies (tcv_gemm_tc_ex)."""
+            ra, la = A_.shape[2], A_.shape[3]
+            rb, lb = B_.shape[2], B_.shape[3]
+            self._call("tcv_gemm_tc_ex", A_.data_ptr(), n * ra * la, la, ra * la, int(a_mn), B_.data_ptr(), n * rb * lb, lb,
+                       rb * lb, int(b_mn), C_.data_ptr(), M_, N_, K_, ldc, M_ * ldc, n)
+
+        # the backward GEMMs read their operands as the forward left them when the CTA-pair kernel applies
+        mn_ok = self.gca_mn_gemm and P >= 512
+
         Q = torch.empty((2, n, P, 576), dtype=bf16, device=dev)
         Kn = torch.empty((2, n, Pk, 576), dtype=bf16, device=dev)       # zero rows at the pad keys
         self._call("tcv_gca_prep_grid", ga.ptr, unknown.data_ptr(), n, h, w, Q.data_ptr(), Kn.data_ptr(), mm.data_ptr(),
@@ -717,7 +730,10 @@ class TrainEngine(GcaVmnEngine):
             self._call("tcv_gca_unfold_parity_bwd", dY.ptr, n, h, w, dO2.data_ptr())
             # dA2[m,p'] = sum_d dO2[m,d] F[p',d]
             dA2 = torch.empty((n, Pk, ld), dtype=f32, device=dev)
-            gemm_tc(dO2, Pk, transpose(Ft, 512, Pk, ld, 512), Pk, 512, dA2, ld)
+            if mn_ok:
+                gemm_ex(dO2, False, Ft, True, Pk, Pk, 512, dA2, ld)           # F^T: Ft [512][ld] is F MN-major
+            else:
+                gemm_tc(dO2, Pk, transpose(Ft, 512, Pk, ld, 512), Pk, 512, dA2, ld)
             # dS = A * (gather(dA2) - <A, gather(dA2)>): gather, row dot and softmax backward in one kernel
             dS_s = torch.empty((2, n, P, ld), dtype=bf16, device=dev)
             self._call("tcv_gca_softmax_bwd_grid", A.data_ptr(), dA2.data_ptr(), n, h, w, ld, dS_s.data_ptr())
@@ -725,7 +741,10 @@ class TrainEngine(GcaVmnEngine):
             if feat.needs_grad:
                 # dF[p',d] = sum_m A2[m,p'] dO2[m,d]
                 dF = torch.empty((n, Pk, 512), dtype=f32, device=dev)
-                gemm_tc(transpose(A2, Pk, Pk, ld, ld), Pk, transpose(dO2, Pk, 512, 512, ld), 512, ld, dF, 512)
+                if mn_ok:
+                    gemm_ex(A2, True, dO2, True, Pk, 512, Pk, dF, 512)
+                else:
+                    gemm_tc(transpose(A2, Pk, Pk, ld, ld), Pk, transpose(dO2, Pk, 512, 512, ld), 512, ld, dF, 512)
                 dfeat = self._act(n, h, w, 128)
                 self._call("tcv_gca_values_parity_bwd", dF.data_ptr(), n, h, w, dfeat.ptr)
                 self._acc(feat, dfeat, True)
@@ -734,8 +753,12 @@ class TrainEngine(GcaVmnEngine):
             dQ = torch.empty((n, P, 576), dtype=f32, device=dev)
             dKn = torch.empty((n, Pk, 576), dtype=f32, device=dev)
             # dQ[q,c] = sum_p' dS[q,p'] Kn[p',c] ; dKn[p',c] = sum_q dS[q,p'] Q[q,c]
-            gemm_tc(dS_s, P, transpose(Kn, Pk, 576, 576, ld), 576, ld, dQ, 576)
-            gemm_tc(transpose(dS_s, P, Pk, ld, P_pad), Pk, transpose(Q, P, 576, 576, P_pad), 576, P_pad, dKn, 576)
+            if mn_ok:
+                gemm_ex(dS_s, False, Kn, True, P, 576, Pk, dQ, 576)
+                gemm_ex(dS_s, True, Q, True, Pk, 576, P, dKn, 576)
+            else:
+                gemm_tc(dS_s, P, transpose(Kn, Pk, 576, 576, ld), 576, ld, dQ, 576)
+                gemm_tc(transpose(dS_s, P, Pk, ld, P_pad), Pk, transpose(Q, P, 576, 576, P_pad), 576, P_pad, dKn, 576)
             dg = self._act(n, h // 2, w // 2, 64)
             self._call("tcv_gca_prep_bwd_grid", dQ.data_ptr(), dKn.data_ptr(), Q32.data_ptr(), mm.data_ptr(),
                        scales.data_ptr(), n, h, w, dg.ptr)

@@ -77,6 +77,16 @@ def test_wgrad_nhwc_tc(cin, cout, h, w, n, prepad, flags, perm):
     _tc().case_wgrad(cin, cout, h, w, n, prepad, flags, perm)
 
 
+@pytest.mark.parametrize("M,N,K,batch,a_mn,b_mn", [
+    (1000, 520, 576, 2, False, False),     # K-major operands with padded pitches
+    (1000, 520, 600, 2, False, True),      # dQ = dS . Kn : B as its producer left it; K not a multiple of 64
+    (1035, 512, 1035, 2, True, True),      # dF = A2^T . dO2 : both operands MN-major, ragged M / K
+    (640, 300, 520, 1, True, False),
+])
+def test_gemm_tc_ex_operand_layouts(M, N, K, batch, a_mn, b_mn):
+    _tc().case_gemm_ex(M, N, K, batch, a_mn, b_mn)
+
+
 @pytest.mark.parametrize("cin,cout,h,w,n,groups,dil", [
     (64, 64, 40, 56, 3, 3, 1),          # N = 64 stacked operand, ragged tiles
     (128, 128, 34, 60, 3, 3, 2),        # dilation 2 (FBA layer3)

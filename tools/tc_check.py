@@ -131,6 +131,48 @@ def case_wgrad(cin, cout, h, w, n, prepad=False, flags=0, perm=False):
     return err
 
 
+def case_gemm_ex(M, N, K, batch, a_mn, b_mn):
+    """tcv_gemm_tc_ex: C = A . B^T on the CTA-pair kernel with K-major / MN-major operands (padded pitches, ragged K)."""
+    import torch
+    from tcvom_b200 import _cabi
+    L = _cabi.lib()
+    torch.manual_seed(4)
+    dev = "cuda"
+    st = torch.cuda.current_stream().cuda_stream
+    A = torch.randn(batch, M, K, device=dev, dtype=torch.float64)
+    B = torch.randn(batch, N, K, device=dev, dtype=torch.float64)
+
+    def operand(X, mn):      # -> split planes with a padded pitch, filled with NaN outside the matrix
+        rows = X.shape[1]
+        if mn:
+            ld = (rows + 63) // 64 * 64 + 64
+            buf = torch.full((batch, K, ld), float("nan"), device=dev)
+            buf[:, :, :rows] = X.transpose(1, 2).float()
+        else:
+            ld = (K + 7) // 8 * 8 + 8
+            buf = torch.full((batch, rows, ld), float("nan"), device=dev)
+            buf[:, :, :K] = X.float()
+        planes = split(buf)
+        return planes, ld, buf.shape[1] * ld
+
+    a, a_ld, a_bs = operand(A, a_mn)
+    b, b_ld, b_bs = operand(B, b_mn)
+    ldc = (N + 3) // 4 * 4
+    C_ = torch.zeros((batch, M, ldc), device=dev)
+    _cabi.check(L.tcv_gemm_tc_ex(a.data_ptr(), a[0].numel(), a_ld, a_bs, int(a_mn), b.data_ptr(), b[0].numel(), b_ld, b_bs,
+                                 int(b_mn), C_.data_ptr(), M, N, K, ldc, M * ldc, batch, st), "gemm_tc_ex")
+    torch.cuda.synchronize()
+    a64 = (a[0].double() + a[1].double())
+    b64 = (b[0].double() + b[1].double())
+    A64 = a64[:, :, :M].transpose(1, 2) if a_mn else a64[:, :, :K]
+    B64 = b64[:, :, :N].transpose(1, 2) if b_mn else b64[:, :, :K]
+    ref = A64 @ B64.transpose(1, 2)
+    err = float((C_[:, :, :N].double() - ref).abs().max() / ref.abs().max())
+    print(f"gemm_ex M={M} N={N} K={K} batch={batch} a_mn={a_mn} b_mn={b_mn}: rel err {err:.2e}")
+    assert err < 3e-5, err
+    return err
+
+
 def case_conv_stats(cin, cout, h, w, n, groups, dil=1):
     """tcv_conv_desc.stats: per-(image group, channel) sum / sum of squares of the conv output accumulated by the epilogue
     of the CTA-pair kernel, against the same sums taken from the stored output tensor."""
