@@ -154,6 +154,7 @@ class GcaVmnEngine:
         # recently used shapes so that a folder of differently sized clips cannot exhaust HBM
         self.max_plans = int(os.environ.get("TCV_MAX_PLANS", "2"))
         self._rec: Optional[Plan] = None
+        self._stream_cache: Optional[int] = None
         self.use_graphs = os.environ.get("TCV_GRAPHS", "1") == "1"
         self.plan_pool = os.environ.get("TCV_PLAN_POOL", "1") == "1"
         # tcgen05 paths (default on); the CUDA-core fp32 paths stay available as the exact cross-check
@@ -383,9 +384,29 @@ class GcaVmnEngine:
             raise RuntimeError("tcvom_b200: the module must live on a CUDA device (no CPU fallback)")
 
     def _stream_ptr(self) -> int:
+        st = self._stream_cache
+        if st is not None:
+            return st
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    @contextlib.contextmanager
+    def stream_scope(self):
+        """Pins the stream handle for the calls issued inside the block (one torch.cuda.current_stream() lookup instead of one
+        per C-ABI call).  The caller must not switch streams inside."""
+        prev = self._stream_cache
+        self._stream_cache = torch.cuda.current_stream(self.device).cuda_stream
+        try:
+            yield
+        finally:
+            self._stream_cache = prev
+
     def _call(self, fn_name: str, *args, meta: Optional[dict] = None):
+        # (the device context manager costs ~5 us per call and a training step makes 1 200 of them: enter it only when the
+        # module's device is not the current one)
+        dev = self.device
+        if dev is None or dev.type != "cuda" or torch.cuda.current_device() == dev.index:
+            self._call_on_device(fn_name, *args, meta=meta)
+            return
         with self._device_guard():
             self._call_on_device(fn_name, *args, meta=meta)
 

@@ -257,7 +257,7 @@ class TrainEngine(GcaVmnEngine):
     def _ctag(self, d: ConvDesc, what: str) -> dict:
         if getattr(self, "_prof", None) is None:
             return {}
-        path = {0: "direct", 1: "tc", 2: "tc2", 3: "tc3"}[_cabi.lib().tcv_conv2d_path(C.byref(d))]
+        path = {0: "direct", 1: "tc", 2: "tc2", 3: "tc3", 4: "tc2p"}[_cabi.lib().tcv_conv2d_path(C.byref(d))]
         return dict(tag=f"{what} {path} {d.cin}->{d.cout} t{d.ntaps} s{d.stride} px{d.n * d.gh * d.gw}")
 
     # ------------------------------------------------------------------ convolution (raw, no BatchNorm)
@@ -426,7 +426,9 @@ class TrainEngine(GcaVmnEngine):
             assert res2.a.c == c and res2.a.n == za.n and res2.a.h == za.h and res2.a.w == za.w, bnkey
             d.res2, d.res2_plane = res2.a.ptr, res2.a.plane
         d.y, d.y_plane = y.ptr, y.plane
-        tag = dict(tag=f"c{c} px{za.n * za.h * za.w} m{mode}{'r1' if res1 is not None else ''}{'r2' if res2 is not None else ''}")
+        tag = None
+        if getattr(self, "_prof", None) is not None:
+            tag = dict(tag=f"c{c} px{za.n * za.h * za.w} m{mode}{'r1' if res1 is not None else ''}{'r2' if res2 is not None else ''}")
         self._call("tcv_bn_stats", C.byref(d), sums.data_ptr(), meta=tag)
         count = float((za.n // groups) * za.h * za.w)
         if self.sync_bn:
@@ -862,6 +864,10 @@ class TrainEngine(GcaVmnEngine):
 
     def train_forward(self, x8a: Act, trimask: torch.Tensor, B: int, S: int, H: int, W: int) -> dict:
         """VMN.forward in train mode on preprocessed input; records the tape.  trimask fp32 [B,S,1,H,W]."""
+        with self.stream_scope():
+            return self._train_forward(x8a, trimask, B, S, H, W)
+
+    def _train_forward(self, x8a: Act, trimask: torch.Tensor, B: int, S: int, H: int, W: int) -> dict:
         self.tape = []
         self.step_id = getattr(self, "step_id", 0) + 1       # stamps the autograd node (model._TrainStepFn / _VMNTrainFn)
         self.dw.clear(); self.dbias.clear(); self.dbn.clear()
@@ -906,6 +912,10 @@ class TrainEngine(GcaVmnEngine):
 
     def train_backward(self, dpred: torch.Tensor, dattb: Optional[torch.Tensor], dattf: Optional[torch.Tensor]) -> None:
         """Runs the tape in reverse from dL/dpred (fp32 [B,ncen,1,H,W]) and the TAM-logit gradients of L_af."""
+        with self.stream_scope():
+            self._train_backward(dpred, dattb, dattf)
+
+    def _train_backward(self, dpred: torch.Tensor, dattb: Optional[torch.Tensor], dattf: Optional[torch.Tensor]) -> None:
         n = dpred.numel()
         hin = self.head_in.a
         if self.head.a is not None:              # padded 32-channel head

@@ -36,6 +36,21 @@ def main():
     ap.add_argument("--breakdown", type=int, default=1)
     args = ap.parse_args()
     dev = "cuda:0"
+    if os.environ.get("TCV_PRE_FORWARD") == "1":
+        # what bench.py does before its training sections: one recorded 1088x1920 forward window, then everything released
+        import gc
+        from tcvom_b200.engine import release_idle_pools
+        m = tcvom_b200.EvalModel(model="vmn_gca", agg_window=7, dilate_kernel=None)
+        m.NET.load_state_dict(fixture_sd(), strict=True)
+        m = m.to(dev).eval()
+        imgs, tris = synthetic.make_window(1088, 1920, seed=7)
+        with torch.no_grad():
+            for _ in range(3):
+                m(torch.from_numpy(imgs).to(dev), torch.from_numpy(tris).to(dev))
+        torch.cuda.synchronize()
+        m.NET.engine().plans.clear()
+        del m
+        gc.collect(); release_idle_pools(); torch.cuda.empty_cache()
     model = tcvom_b200.FullModel_VMD(model="vmn_gca", agg_window=7, dilate_kernel=None)
     model.NET.load_state_dict(fixture_sd(), strict=True)
     model = model.to(dev).train()
@@ -58,15 +73,22 @@ def main():
     torch.cuda.reset_peak_memory_stats()
     n0 = _cabi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import gc
+    import time
+    g0 = [g["collections"] for g in gc.get_stats()]
     e0.record()
+    t0 = time.perf_counter()
     for _ in range(args.steps):
         loss = step()
+    cpu_ms = (time.perf_counter() - t0) * 1e3 / args.steps       # time to ISSUE a step (no synchronisation inside)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
+    g1 = [g["collections"] for g in gc.get_stats()]
     launches = (_cabi.launch_count() - n0) // args.steps
     res = dict(workload=f"GCA+TAM train step (L_im+L_tc+L_af, fwd+bwd+Adam) {H}x{W} crop, batch {B}, S={S}",
                ms_per_step=ms, samples_per_s=B / (ms / 1e3), centre_windows_per_s=B * (S - 2) / (ms / 1e3),
+               cpu_issue_ms_per_step=cpu_ms, gc_collections=[b - a for a, b in zip(g0, g1)], gc_objects=len(gc.get_objects()),
                launches_per_step=launches, peak_mem_gb=torch.cuda.max_memory_allocated() / 2**30, loss=float(loss))
     if args.breakdown:
         eng = model.NET.__dict__["_train_engines"][0]
