@@ -593,14 +593,9 @@ int tcv_gemm_tc_ex(const void* A, long long a_plane, long long a_ld, long long a
                    long long ldc, long long c_batch_stride, int batch, tcv_stream_t stream);
 
 /* ---- training side of the shift-sum aggregation (csrc/gca_train2.cu; autograd of GCA/ops.py:112-118,204):
- *  shift_add_u:        A fp32 [n][P][lda] (softmax on the unpadded key grid) -> A2 split-bf16 planes [2][n][Pk][ld]
- *  shift_gather:       dA2 fp32 [n][Pk][ld] -> dA fp32 [n][P][lda],  dA[q][p] = sum_a dA2[q+a][p+a]
  *  unfold_parity_bwd:  dY split-bf16 [n,h,w,128] -> dO2 planes [2][n][Pk][512] = gradient of tcv_gca_unfold_parity (x 1/4)
  *  values_parity_bwd:  dF fp32 [n][Pk][512] -> dfeat split-bf16 [n,h,w,128] = gradient of tcv_gca_values_parity (the reflect
- *                      border makes rows / columns 1 and h-2 / w-2 receive two contributions)
- *  rowdot_f32:         out[r] = sum_{c < cols} A[r][c] * B[r][c]   (delta of the softmax backward) */
-int tcv_gca_shift_add_u(const float* A, int n, int h, int w, int lda, int ld, void* A2, tcv_stream_t stream);
-int tcv_gca_shift_gather(const float* dA2, int n, int h, int w, int ld, int lda, float* dA, tcv_stream_t stream);
+ *                      border makes rows / columns 1 and h-2 / w-2 receive two contributions) */
 int tcv_gca_unfold_parity_bwd(const void* dY, int n, int h, int w, void* dO2, tcv_stream_t stream);
 int tcv_gca_values_parity_bwd(const float* dF, int n, int h, int w, void* dfeat, tcv_stream_t stream);
 /* fused backward of tcv_gca_rowstats(normalise) + tcv_gca_shift_add on the padded key grid: A fp32 [n][P][ld] (probabilities,
@@ -609,7 +604,6 @@ int tcv_gca_softmax_bwd_grid(const float* A, const float* dA2, int n, int h, int
 /* tcv_gca_prep_bwd with the key gradient on the padded grid of tcv_gca_prep_grid: dKn_grid fp32 [n][Pk][576] */
 int tcv_gca_prep_bwd_grid(float* dQ, const float* dKn_grid, const float* Q, const float* mm, const float* scales, int n,
                           int h, int w, void* dg, tcv_stream_t stream);
-int tcv_rowdot_f32(const float* A, const float* B, long long rows, int cols, long long ld, float* out, tcv_stream_t stream);
 
 /* ---- SyncBatchNorm statistic exchange over NVLink peer memory (train_ddp.py:273 nn.SyncBatchNorm; csrc/peer_reduce.cu).
  * In-place sum of `count` doubles over `world` ranks of one node in ONE kernel on the caller's stream.  `peers_dev`: device

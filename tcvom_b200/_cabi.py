@@ -133,14 +133,11 @@ SIGNATURES = {
     "tcv_maxunpool2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_head_conv5_clamp01": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tcv_dim_fix_inputs": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "tcv_gca_shift_add_u": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "tcv_gca_shift_gather": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_gca_unfold_parity_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_gca_values_parity_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_gca_softmax_bwd_grid": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_gca_prep_bwd_grid": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                       c_void_p]),
-    "tcv_rowdot_f32": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_ll, c_void_p, c_void_p]),
     "tcv_peer_allreduce_f64": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, C.c_ulonglong, c_ll, c_void_p]),
     "tcv_peer_buffer_bytes": (c_int, [c_ll, C.POINTER(c_ll)]),
     "tcv_head_conv_tanh01": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

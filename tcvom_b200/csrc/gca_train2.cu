@@ -2,73 +2,16 @@
 // reference: GCA/ops.py:112-118,204 and its autograd).  With m = q + a, p' = p + a on the (hh+1) x (ww+1) grid:
 //     Y  = unfold_parity( A2 . F ) / 4           A2[m][p'] = sum_a A[m-a][p'-a]        F_r[p'] = feat_reflect[2p'+r-1]
 //     dO2 = unfold_parity^T(dY) / 4              dA2 = dO2 . F^T      dF = A2^T . dO2
-//     dA[q][p] = sum_a dA2[q+a][p+a]             dfeat = values_parity^T(dF)
+//     dA[q][p'] = sum_a dA2[q+a][p'+sh_a]        dfeat = values_parity^T(dF)
 // i.e. the two backward GEMMs shrink from [P x 2048 x P] to [Pk x 512 x Pk] like the forward one (3.8x fewer FLOPs each).
-// The scores side (Q, Kn, softmax, dS, dQ, dKn) keeps the unpadded key grid [P x P_pad] of the round-1 backward, so only
-// the element-wise kernels below are new:
-//   shift_add_u   A fp32 [n][P][lda] (unpadded columns)  -> A2 split-bf16 planes [2][n][Pk][ld]
-//   shift_gather  dA2 fp32 [n][Pk][ld]                    -> dA fp32 [n][P][lda]
-//   unfold_parity_bwd  dY split-bf16 [n,h,w,128]          -> dO2 planes [2][n][Pk][512] (x 1/4)
-//   values_parity_bwd  dF fp32 [n][Pk][512]               -> dfeat split-bf16 [n,h,w,128]
-//   rowdot        delta[r] = sum_c A[r][c] * B[r][c]
+// Scores, softmax and shift-add run on the padded key grid with the inference kernels (gca.cu); what is new here:
+//   unfold_parity_bwd   dY split-bf16 [n,h,w,128]          -> dO2 planes [2][n][Pk][512] (x 1/4)
+//   softmax_bwd_grid    A fp32 [n][P][ld], dA2 [n][Pk][ld] -> dS split-bf16 [2][n][P][ld]   (gather + row dot + softmax backward)
+//   values_parity_bwd   dF fp32 [n][Pk][512]               -> dfeat split-bf16 [n,h,w,128]
 #include "common.cuh"
 
 namespace tcv {
 constexpr int T2_FC = 128;
-
-__global__ void __launch_bounds__(256) gca_shift_add_u_kernel(const float* __restrict__ A, int n, int hh, int ww, int lda,
-                                                              int ld, __nv_bfloat16* __restrict__ A2) {
-  const int P = hh * ww, ww1 = ww + 1, Pk = (hh + 1) * ww1;
-  const int m = blockIdx.x, img = blockIdx.y;
-  const int my = m / ww1, mx = m - my * ww1;
-  const float* rows[4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int qy = my - (a >> 1), qx = mx - (a & 1);
-    rows[a] = (qy >= 0 && qy < hh && qx >= 0 && qx < ww) ? A + ((long long)img * P + qy * ww + qx) * lda : nullptr;
-  }
-  const long long plane = (long long)n * Pk * ld;
-  __nv_bfloat16* out = A2 + ((long long)img * Pk + m) * ld;
-  for (int j = threadIdx.x * 2; j < ld; j += 512) {
-    float v[2] = {0.f, 0.f};
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int jj = j + e;
-      if (jj >= Pk) continue;
-      const int ky = jj / ww1, kx = jj - ky * ww1;          // padded key-grid position p'
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int py = ky - (a >> 1), px = kx - (a & 1);
-        if (rows[a] != nullptr && py >= 0 && py < hh && px >= 0 && px < ww) v[e] += __ldg(rows[a] + py * ww + px);
-      }
-    }
-    uint32_t hi, lo;
-    split2_bf16(v[0], v[1], hi, lo);
-    *reinterpret_cast<uint32_t*>(out + j) = hi;
-    *reinterpret_cast<uint32_t*>(out + plane + j) = lo;
-  }
-}
-
-__global__ void __launch_bounds__(256) gca_shift_gather_kernel(const float* __restrict__ dA2, int hh, int ww, int ld, int lda,
-                                                               float* __restrict__ dA) {
-  const int P = hh * ww, ww1 = ww + 1, Pk = (hh + 1) * ww1;
-  const int q = blockIdx.x, img = blockIdx.y;
-  const int qy = q / ww, qx = q - qy * ww;
-  const float* base = dA2 + (long long)img * Pk * ld;
-  float* out = dA + ((long long)img * P + q) * lda;
-  for (int p = threadIdx.x; p < lda; p += 256) {
-    float v = 0.f;
-    if (p < P) {
-      const int py = p / ww, px = p - py * ww;
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int ay = a >> 1, ax = a & 1;
-        v += __ldg(base + (long long)((qy + ay) * ww1 + qx + ax) * ld + (py + ay) * ww1 + px + ax);
-      }
-    }
-    out[p] = v;
-  }
-}
 
 // work item = 8 channels of one (image, m, parity)
 __global__ void gca_unfold_parity_bwd_kernel(const __nv_bfloat16* __restrict__ dY, int n, int h, int w,
@@ -205,40 +148,11 @@ __global__ void __launch_bounds__(256) gca_softmax_bwd_grid_kernel(const float* 
   }
 }
 
-// one warp per row
-__global__ void rowdot_kernel(const float* __restrict__ A, const float* __restrict__ B, long long rows, int cols, long long ld,
-                              float* __restrict__ out) {
-  const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (r >= rows) return;
-  const float* a = A + r * ld;
-  const float* b = B + r * ld;
-  float s = 0.f;
-  for (int c = lane; c < cols; c += 32) s = fmaf(a[c], b[c], s);
-  s = warp_sum(s);
-  if (lane == 0) out[r] = s;
-}
 }  // namespace tcv
 
 using namespace tcv;
 
 extern "C" {
-
-int tcv_gca_shift_add_u(const float* A, int n, int h, int w, int lda, int ld, void* A2, tcv_stream_t stream) {
-  TCV_REQUIRE(A && A2, "gca_shift_add_u: null pointer");
-  const int hh = h / 2, ww = w / 2, Pk = (hh + 1) * (ww + 1);
-  TCV_REQUIRE(n > 0 && hh > 0 && ww > 0 && ld % 2 == 0 && ld >= Pk && lda >= hh * ww, "gca_shift_add_u: bad geometry");
-  gca_shift_add_u_kernel<<<dim3(Pk, n), 256, 0, S(stream)>>>(A, n, hh, ww, lda, ld, reinterpret_cast<__nv_bfloat16*>(A2));
-  return launched("gca_shift_add_u_kernel");
-}
-
-int tcv_gca_shift_gather(const float* dA2, int n, int h, int w, int ld, int lda, float* dA, tcv_stream_t stream) {
-  TCV_REQUIRE(dA2 && dA, "gca_shift_gather: null pointer");
-  const int hh = h / 2, ww = w / 2;
-  TCV_REQUIRE(n > 0 && hh > 0 && ww > 0 && ld >= (hh + 1) * (ww + 1) && lda >= hh * ww, "gca_shift_gather: bad geometry");
-  gca_shift_gather_kernel<<<dim3(hh * ww, n), 256, 0, S(stream)>>>(dA2, hh, ww, ld, lda, dA);
-  return launched("gca_shift_gather_kernel");
-}
 
 int tcv_gca_unfold_parity_bwd(const void* dY, int n, int h, int w, void* dO2, tcv_stream_t stream) {
   TCV_REQUIRE(dY && dO2, "gca_unfold_parity_bwd: null pointer");
@@ -268,12 +182,6 @@ int tcv_gca_softmax_bwd_grid(const float* A, const float* dA2, int n, int h, int
   gca_softmax_bwd_grid_kernel<<<dim3(hh * ww, n), 256, smem, S(stream)>>>(A, dA2, n, hh, ww, ld,
                                                                          reinterpret_cast<__nv_bfloat16*>(dS));
   return launched("gca_softmax_bwd_grid_kernel");
-}
-
-int tcv_rowdot_f32(const float* A, const float* B, long long rows, int cols, long long ld, float* out, tcv_stream_t stream) {
-  TCV_REQUIRE(A && B && out && rows > 0 && cols > 0 && ld >= cols, "rowdot_f32: bad arguments");
-  rowdot_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, S(stream)>>>(A, B, rows, cols, ld, out);
-  return launched("rowdot_kernel");
 }
 
 }  // extern "C"
