@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256) tam_attend_kernel(
   if (lane == 0) small_mask[(long long)b * N + pix] = m ? 1 : 0;
 
   float o[CPL];
-  if (CPL == 4) load4(v + base, plane, o); else load8(v + base, plane, o);
+  if (CPL == 1) o[0] = load1(v + base, plane); else if (CPL == 4) load4(v + base, plane, o); else load8(v + base, plane, o);
 
   if (!m) {
     for (int j = lane; j < w2; j += 32) {
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) tam_attend_kernel(
     }
   } else {
     float qv[CPL];
-    if (CPL == 4) load4(q + base, plane, qv); else load8(q + base, plane, qv);
+    if (CPL == 1) qv[0] = load1(q + base, plane); else if (CPL == 4) load4(q + base, plane, qv); else load8(q + base, plane, qv);
     const float inv_sqrt_c = 1.0f / sqrtf((float)C);
 #pragma unroll 1
     for (int nb = 0; nb < 2; ++nb) {
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) tam_attend_kernel(
         if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
           float kv[CPL];
           const __nv_bfloat16* kp = k + ((long long)b * N + (long long)yy * w + xx) * C + lane * CPL;
-          if (CPL == 4) load4(kp, plane, kv); else load8(kp, plane, kv);
+          if (CPL == 1) kv[0] = load1(kp, plane); else if (CPL == 4) load4(kp, plane, kv); else load8(kp, plane, kv);
 #pragma unroll
           for (int c = 0; c < CPL; ++c) d = fmaf(qv[c], kv[c], d);
           d = warp_sum(d);
@@ -77,14 +77,14 @@ __global__ void __launch_bounds__(256) tam_attend_kernel(
         if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
           float kv[CPL];
           const __nv_bfloat16* kp = k + ((long long)b * N + (long long)yy * w + xx) * C + lane * CPL;
-          if (CPL == 4) load4(kp, plane, kv); else load8(kp, plane, kv);
+          if (CPL == 1) kv[0] = load1(kp, plane); else if (CPL == 4) load4(kp, plane, kv); else load8(kp, plane, kv);
 #pragma unroll
           for (int c = 0; c < CPL; ++c) o[c] = fmaf(a, kv[c], o[c]);
         }
       }
     }
   }
-  if (CPL == 4) store4(out + base, plane, o); else store8(out + base, plane, o);
+  if (CPL == 1) store1(out + base, plane, o[0]); else if (CPL == 4) store4(out + base, plane, o); else store8(out + base, plane, o);
 }
 
 }  // namespace tcv
@@ -96,7 +96,7 @@ extern "C" int tcv_tam_attend(const void* q, const void* v, const void* kb, cons
                               void* out, float* attb, float* attf, uint8_t* small_mask, tcv_stream_t stream) {
   TCV_REQUIRE(q && v && kb && kf && mask && out && attb && attf && small_mask, "tam_attend: null pointer");
   TCV_REQUIRE(window >= 1 && window % 2 == 1 && window * window <= 64, "tam_attend: window must be odd and <= 7");
-  TCV_REQUIRE(c == 128 || c == 256, "tam_attend: channels must be 128 or 256");
+  TCV_REQUIRE(c == 32 || c == 128 || c == 256, "tam_attend: channels must be 32, 128 or 256 (the TAM widths of the reference's four base networks)");
   const long long warps = (long long)batch * h * w;
   const unsigned grid = (unsigned)((warps * 32 + 255) / 256);
   auto Q = reinterpret_cast<const __nv_bfloat16*>(q);
@@ -104,7 +104,10 @@ extern "C" int tcv_tam_attend(const void* q, const void* v, const void* kb, cons
   auto KB = reinterpret_cast<const __nv_bfloat16*>(kb);
   auto KF = reinterpret_cast<const __nv_bfloat16*>(kf);
   auto O = reinterpret_cast<__nv_bfloat16*>(out);
-  if (c == 128)
+  if (c == 32)
+    tam_attend_kernel<1><<<grid, 256, 0, S(stream)>>>(Q, V, KB, KF, mask, mask_stride, mh, mw, batch, h, w,
+                                                      window, O, attb, attf, small_mask);
+  else if (c == 128)
     tam_attend_kernel<4><<<grid, 256, 0, S(stream)>>>(Q, V, KB, KF, mask, mask_stride, mh, mw, batch, h, w,
                                                       window, O, attb, attf, small_mask);
   else

@@ -103,6 +103,27 @@ def test_tam_operator_matches_reference_golden():
         assert np.abs(mine.cpu().numpy() - ref).max() <= 1e-3 * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("chn", [32, 256])
+def test_tam_operator_other_widths_match_oracle(chn):
+    """FeatureAggregationModule(32 / 256, ...) -- the TAM widths of the IndexNet and the DIM / FBA base networks
+    (VMN_Index.py:10, VMN_DIM.py:99, VMN_FBA.py:9) -- against the oracle's dense-then-mask restatement."""
+    import tcvom_b200
+    from oracle import vmn_gca_oracle as O
+    torch.manual_seed(chn)
+    fam = tcvom_b200.FeatureAggregationModule(chn, 1, 7)
+    sd = {k: torch.randn_like(v) * (0.3 / (chn * 9) ** 0.5 if k.endswith("weight") else 0.1) for k, v in fam.state_dict().items()}
+    fam.load_state_dict(sd, strict=True)
+    fam = fam.cuda().eval()
+    x, b, f = (torch.randn(2, chn, 10, 14) for _ in range(3))
+    mask = (torch.rand(2, 1, 80, 112) > 0.4).float()
+    with torch.no_grad():
+        feat, attb, attf, sm = fam(x.cuda(), b.cuda(), f.cuda(), mask.cuda())
+        rfeat, rb, rf, rm = O.tam({"fam." + k: v for k, v in sd.items()}, "fam", x, b, f, mask, 7)
+    assert torch.equal(sm.cpu(), rm)
+    for mine, ref in ((feat, rfeat), (attb, rb), (attf, rf)):
+        assert float((mine.cpu() - ref).abs().max()) <= 1e-3 * max(1.0, float(ref.abs().max()))
+
+
 def test_gca_operator_matches_reference_golden():
     import tcvom_b200
     g = golden("op_gca.npz")
