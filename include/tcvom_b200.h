@@ -47,6 +47,7 @@ typedef void* tcv_stream_t; /* cudaStream_t */
 #define TCV_ACT_TANH01 3 /* (tanh(x)+1)/2 -- VMN_GCA.py:47 */
 #define TCV_ACT_LEAKY001 4 /* nn.LeakyReLU() default slope 0.01 -- FBA/models.py:266-300 */
 #define TCV_ACT_CLAMP01 5  /* .clamp(0, 1) -- VMN_DIM.py:135 */
+#define TCV_ACT_RELU6 6    /* nn.ReLU6 -- models/Index/hlconv.py:39, net.py:47 */
 
 #define TCV_PAD_ZERO 0
 #define TCV_PAD_REFLECT 1
@@ -582,6 +583,32 @@ int tcv_dim_fix_inputs(const void* tris, int is_u8, int frames, int h, int w, vo
  * pred fp32 [n,h,w] */
 int tcv_head_conv5_clamp01(const void* x, long long x_plane, int n, int h, int w, const float* wt, const float* bias,
                            float* pred, tcv_stream_t stream);
+
+/* =====================================================================================================
+ * IndexNet base network behind the TAM operator (models/Index, models/VMN/VMN_Index.py).
+ * Dense convolutions (1x1, 3x3, 4x4 / stride 2, 5x5 as tap-group chains), eval BatchNorm + ReLU6 (TCV_ACT_RELU6), the
+ * ASPP pooling branch (tcv_adaptive_avgpool, tcv_bilinear, tcv_copy_channels), the TAM and the eval pre/post-processing
+ * reuse the entry points above; what IndexNet adds (split-bf16 NHWC, channel counts multiples of 8):
+ *   tcv_dwconv3x3     net.py:42-44,52-54, hlaspp.py:40  depthwise 3x3 (dilation = padding = dil) + BatchNorm affine +
+ *                     activation.  wt fp32 [9][c]; border fp32 [c] or NULL = value an out-of-image tap reads: the
+ *                     reference's InvertedResidual pads the block input and runs its 1x1 expansion + BN + ReLU6 over the
+ *                     padded tensor (net.py:62-83), so the depthwise conv sees relu6(BN shift) there, not zero
+ *   tcv_index_finish  hlindex.py:155-166  four branch outputs [n,h2,w2,c] -> idx_en = softmax over the branches of
+ *                     sigmoid(branch), idx_de = sigmoid(branch), both [n,2*h2,2*w2,c] (pixel shuffle: branch k lands
+ *                     on sub-pixel (k / 2, k % 2))
+ *   tcv_index_pool    net.py:193-194 etc.  masked = idx_en * x [n,h,w,c], pooled = 4 * avg_pool2(masked) [n,h/2,w/2,c]
+ *   tcv_index_upcat   hldecoder.py:121-127  cat [n,h,w,cat_c] = [ idx * nearest_up(dec)[:dec_real] | low[:low_real] | 0 ];
+ *                     idx == NULL: dec is taken as is (up must be 0); idx_plane / low_plane: elements between the hi and lo
+ *                     plane (0: dense; idx / low may be image slices of a larger tensor) */
+int tcv_dwconv3x3(const void* x, int n, int h, int w, int c, int dil, const float* wt, const float* scale, const float* shift,
+                  const float* border, int act, void* y, tcv_stream_t stream);
+int tcv_index_finish(const void* b0, const void* b1, const void* b2, const void* b3, int n, int h2, int w2, int c,
+                     void* idx_en, void* idx_de, tcv_stream_t stream);
+int tcv_index_pool(const void* x, const void* idx_en, int n, int h, int w, int c, void* masked, void* pooled,
+                   tcv_stream_t stream);
+int tcv_index_upcat(const void* dec, int dec_c, int dec_real, int up, const void* idx, int idx_c, long long idx_plane,
+                    const void* low, int low_c, long long low_plane, int low_real, int n, int h, int w, int cat_c, void* cat,
+                    tcv_stream_t stream);
 
 /* C[b] = A[b] . B[b]^T (bf16x3, fp32 out) on the CTA-pair kernel (gemm_tc2.cu) with either operand
  *   K-major  (x_mn == 0): split-bf16 [batch][rows][ld], the reduction index contiguous (K <= ld), or

@@ -16,10 +16,10 @@ def install(native_wrapper: bool = True, fba_seam: bool = False):
     * ``models.VMN.get_VMN_models('vmn_gca', ...)`` -> :func:`tcvom_b200.get_VMN_models`
       (the plugin seam ``models/model.py:39-44`` calls at construction time); other archs are
       forwarded to the reference untouched.  ``fba_seam=True`` also routes the inference-only native networks
-      (``'vmn_fba'``, ``'vmn_dim'``) through the seam -- leave it off when the reference's own training wrappers
-      (``FullModel_VMD('vmn_fba')`` / ``('vmn_dim')``) are to keep working; ``'vmn_index'`` always stays on the reference;
+      (``'vmn_fba'``, ``'vmn_dim'``, ``'vmn_index'``) through the seam -- leave it off when the reference's own training
+      wrappers (``FullModel_VMD('vmn_fba')`` etc.) are to keep working;
     * with ``native_wrapper`` also ``models.model.EvalModel`` -> :class:`tcvom_b200.EvalModel`
-      when it is built for ``vmn_gca`` / ``vmn_fba`` / ``vmn_dim`` (fused preprocess / postprocess kernels, CUDA-graph
+      when it is built for ``vmn_gca`` / ``vmn_fba`` / ``vmn_dim`` / ``vmn_index`` (fused preprocess / postprocess kernels, CUDA-graph
       replay; for ``vmn_fba`` also the trimap distance transforms on the GPU instead of ``cv2``).
 
     Call it before the reference script imports ``models.model``."""
@@ -38,7 +38,7 @@ def install(native_wrapper: bool = True, fba_seam: bool = False):
     orig_factory = ref_vmn.get_VMN_models
 
     def factory(arch, *args, **kwargs):
-        if arch == "vmn_gca" or (arch in ("vmn_fba", "vmn_dim") and fba_seam):
+        if arch == "vmn_gca" or (arch in ("vmn_fba", "vmn_dim", "vmn_index") and fba_seam):
             return get_VMN_models(arch, *args, **kwargs)
         return orig_factory(arch, *args, **kwargs)
 
@@ -52,7 +52,7 @@ def install(native_wrapper: bool = True, fba_seam: bool = False):
             """EvalModel('vmn_gca', ...) -> native wrapper; anything else -> reference class."""
 
             def __new__(cls, model, *args, **kwargs):
-                if model in ("vmn_gca", "vmn_fba", "vmn_dim"):
+                if model in ("vmn_gca", "vmn_fba", "vmn_dim", "vmn_index"):
                     return EvalModel(model, *args, **kwargs)
                 return orig_eval(model, *args, **kwargs)
 

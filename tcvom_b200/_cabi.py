@@ -14,7 +14,7 @@ import threading
 # TCV_LIB: kernel A/B experiments only (a second build of the same sources with other tile constants)
 LIB_PATH = os.environ.get("TCV_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtcvom_b200.so")
 
-ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_TANH01, ACT_LEAKY001, ACT_CLAMP01 = 0, 1, 2, 3, 4, 5
+ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_TANH01, ACT_LEAKY001, ACT_CLAMP01, ACT_RELU6 = 0, 1, 2, 3, 4, 5, 6
 PAD_ZERO, PAD_REFLECT = 0, 1
 MAX_TAPS = 16
 
@@ -129,6 +129,13 @@ SIGNATURES = {
     "tcv_gemm_tc_ex": (c_int, [c_void_p, c_ll, c_ll, c_ll, c_int, c_void_p, c_ll, c_ll, c_ll, c_int, c_void_p, c_int, c_int,
                                c_int, c_ll, c_ll, c_int, c_void_p]),
     "tcv_zero_bytes": (c_int, [c_void_p, c_ll, c_void_p]),
+    "tcv_dwconv3x3": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                              c_void_p, c_void_p]),
+    "tcv_index_finish": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                 c_void_p]),
+    "tcv_index_pool": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "tcv_index_upcat": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_ll, c_void_p, c_int, c_ll, c_int, c_int,
+                                c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_maxpool2_idx": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "tcv_maxunpool2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tcv_head_conv5_clamp01": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

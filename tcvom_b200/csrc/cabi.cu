@@ -75,7 +75,7 @@ int tcv_conv2d(const tcv_conv_desc* dp, tcv_stream_t stream) {
   TCV_REQUIRE(d.cout >= 1, "conv2d: bad cout");
   TCV_REQUIRE(d.ntaps >= 1 && d.ntaps <= TCV_MAX_TAPS, "conv2d: ntaps=%d out of range", d.ntaps);
   TCV_REQUIRE(d.stride == 1 || d.stride == 2, "conv2d: stride must be 1 or 2");
-  TCV_REQUIRE(d.act >= TCV_ACT_NONE && d.act <= TCV_ACT_CLAMP01, "conv2d: unknown activation %d", d.act);
+  TCV_REQUIRE(d.act >= TCV_ACT_NONE && d.act <= TCV_ACT_RELU6, "conv2d: unknown activation %d", d.act);
   TCV_REQUIRE((d.s2 == nullptr) == (d.b2 == nullptr), "conv2d: s2 and b2 go together");
   TCV_REQUIRE((d.gh - 1) * d.oy_mul + d.oy_off < d.oh && (d.gw - 1) * d.ox_mul + d.ox_off < d.ow,
               "conv2d: compute grid does not fit the output tensor");

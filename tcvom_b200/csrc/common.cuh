@@ -93,6 +93,9 @@ __device__ __forceinline__ void apply_act_n(float* f, int act) {
   } else if (act == TCV_ACT_CLAMP01) {
 #pragma unroll
     for (int j = 0; j < N; ++j) f[j] = fminf(fmaxf(f[j], 0.f), 1.f);
+  } else if (act == TCV_ACT_RELU6) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) f[j] = fminf(fmaxf(f[j], 0.f), 6.f);
   }
 }
 
@@ -137,6 +140,7 @@ __device__ __forceinline__ float apply_act(float t, int act) {
     case TCV_ACT_TANH01: return (tanhf(t) + 1.0f) * 0.5f;
     case TCV_ACT_LEAKY001: return t > 0.f ? t : 0.01f * t;
     case TCV_ACT_CLAMP01: return fminf(fmaxf(t, 0.f), 1.f);
+    case TCV_ACT_RELU6: return fminf(fmaxf(t, 0.f), 6.f);
     default: return t;
   }
 }

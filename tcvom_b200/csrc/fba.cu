@@ -248,7 +248,7 @@ int tcv_gn_apply(const void* x, long long x_plane, int n, long long pixels, int 
   TCV_REQUIRE(x && scale && shift && y, "gn_apply: null pointer");
   TCV_REQUIRE(n > 0 && pixels > 0 && c % 8 == 0 && y_c % 8 == 0 && y_off % 8 == 0 && y_off + c <= y_c,
               "gn_apply: bad dims");
-  TCV_REQUIRE(act >= TCV_ACT_NONE && act <= TCV_ACT_CLAMP01, "gn_apply: unknown activation");
+  TCV_REQUIRE(act >= TCV_ACT_NONE && act <= TCV_ACT_RELU6, "gn_apply: unknown activation");
   if (x_plane == 0) x_plane = (long long)n * pixels * c;
   if (res && res_plane == 0) res_plane = (long long)n * pixels * c;
   if (y_plane == 0) y_plane = (long long)n * pixels * y_c;
@@ -375,6 +375,43 @@ int tcv_fba_fusion(const void* o8, const void* x16, long long x16_plane, long lo
   if (x16_img_stride == 0) x16_img_stride = (long long)h * w * 16;
   FusionP p{CU16(o8), CU16(x16), x16_plane, x16_img_stride, n, h, w, pred};
   return launch_body<FusionP, fba_fusion_body>(p, (ll)n * h * w, S(stream), "fba_fusion_kernel");
+}
+
+int tcv_dwconv3x3(const void* x, int n, int h, int w, int c, int dil, const float* wt, const float* scale, const float* shift,
+                  const float* border, int act, void* y, tcv_stream_t stream) {
+  TCV_REQUIRE(x && wt && scale && shift && y && n > 0 && h > 0 && w > 0 && c % 8 == 0 && dil >= 1, "dwconv3x3: bad arguments");
+  TCV_REQUIRE(act >= TCV_ACT_NONE && act <= TCV_ACT_RELU6, "dwconv3x3: unknown activation");
+  DwConvP p{CU16(x), n, h, w, c, dil, wt, scale, shift, border, act, U16(y)};
+  return launch_body<DwConvP, dwconv3x3_body>(p, (ll)n * h * w * (c / 8), S(stream), "dwconv3x3_kernel");
+}
+
+int tcv_index_finish(const void* b0, const void* b1, const void* b2, const void* b3, int n, int h2, int w2, int c,
+                     void* idx_en, void* idx_de, tcv_stream_t stream) {
+  TCV_REQUIRE(b0 && b1 && b2 && b3 && idx_en && idx_de && n > 0 && h2 > 0 && w2 > 0 && c % 8 == 0, "index_finish: bad arguments");
+  IndexFinishP p{{CU16(b0), CU16(b1), CU16(b2), CU16(b3)}, n, h2, w2, c, U16(idx_en), U16(idx_de)};
+  return launch_body<IndexFinishP, index_finish_body>(p, (ll)n * h2 * w2 * (c / 8), S(stream), "index_finish_kernel");
+}
+
+int tcv_index_pool(const void* x, const void* idx_en, int n, int h, int w, int c, void* masked, void* pooled,
+                   tcv_stream_t stream) {
+  TCV_REQUIRE(x && idx_en && masked && pooled && n > 0 && h % 2 == 0 && w % 2 == 0 && c % 8 == 0, "index_pool: bad arguments");
+  IndexPoolP p{CU16(x), CU16(idx_en), n, h, w, c, U16(masked), U16(pooled)};
+  return launch_body<IndexPoolP, index_pool_body>(p, (ll)n * (h / 2) * (w / 2) * (c / 8), S(stream), "index_pool_kernel");
+}
+
+int tcv_index_upcat(const void* dec, int dec_c, int dec_real, int up, const void* idx, int idx_c, long long idx_plane,
+                    const void* low, int low_c, long long low_plane, int low_real, int n, int h, int w, int cat_c, void* cat,
+                    tcv_stream_t stream) {
+  TCV_REQUIRE(dec && low && cat && n > 0 && h > 0 && w > 0, "index_upcat: bad arguments");
+  TCV_REQUIRE(dec_c % 8 == 0 && dec_real % 8 == 0 && low_c % 8 == 0 && low_real % 8 == 0 && cat_c % 8 == 0 &&
+              dec_real <= dec_c && low_real <= low_c && dec_real + low_real <= cat_c, "index_upcat: bad channel counts");
+  TCV_REQUIRE((up == 0 || up == 1) && (up == 0 || (h % 2 == 0 && w % 2 == 0)) && (!idx || (idx_c % 8 == 0 && idx_c >= dec_real)),
+              "index_upcat: bad geometry");
+  if (idx_plane == 0) idx_plane = (ll)n * h * w * idx_c;
+  if (low_plane == 0) low_plane = (ll)n * h * w * low_c;
+  IndexUpcatP p{CU16(dec), CU16(idx), CU16(low), n, h, w, up, dec_c, dec_real, idx_c, low_c, low_real, cat_c, U16(cat),
+                idx_plane, low_plane};
+  return launch_body<IndexUpcatP, index_upcat_body>(p, (ll)n * h * w * (cat_c / 8), S(stream), "index_upcat_kernel");
 }
 
 int tcv_maxpool2_idx(const void* x, int n, int h, int w, int c, void* y, uint8_t* idx, tcv_stream_t stream) {

@@ -81,6 +81,7 @@ TCV_HD float act_fn(float t, int act) {
     case 3: return (tanhf(t) + 1.0f) * 0.5f;               // TCV_ACT_TANH01
     case 4: return t > 0.f ? t : 0.01f * t;                // TCV_ACT_LEAKY001
     case 5: return t < 0.f ? 0.f : (t > 1.f ? 1.f : t);    // TCV_ACT_CLAMP01
+    case 6: return t < 0.f ? 0.f : (t > 6.f ? 6.f : t);    // TCV_ACT_RELU6
     default: return t;
   }
 }
@@ -659,6 +660,149 @@ TCV_HD void dim_fix_inputs_body(ll i, const DimFixP& p) {
     d[k] = 0;
     d[k + plane] = 0;
   }
+}
+
+// ------------------------------------------------------------------------------------------ IndexNet (models/Index)
+struct DwConvP {
+  const uint16_t* x;   // dense [n, h, w, c]
+  int n, h, w, c, dil;
+  const float* wt;     // [9][c] (tap-major, tap = ky*3+kx)
+  const float* scale;  // [c] BatchNorm scale / shift (eval fold)
+  const float* shift;
+  const float* border; // [c] value of an out-of-image tap (NULL: zero padding).  MobileNetV2 blocks of the reference pad
+                       // the block INPUT and run the 1x1 expansion + BN + ReLU6 over the padded tensor (net.py:79-83), so
+                       // the depthwise conv sees relu6(BN shift) -- not zero -- in its one-pixel border.
+  int act;
+  uint16_t* y;         // dense [n, h, w, c]
+};
+// work item = 8 channels of one output pixel: depthwise 3x3 (dilation dil, padding dil) + affine + activation
+TCV_HD void dwconv3x3_body(ll i, const DwConvP& p) {
+  const int cv = p.c / 8;
+  const int ch = (int)(i % cv) * 8;
+  ll t = i / cv;
+  const int x = (int)(t % p.w);
+  t /= p.w;
+  const int y = (int)(t % p.h);
+  const int img = (int)(t / p.h);
+  const ll plane = (ll)p.n * p.h * p.w * p.c;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = 0; k < 9; ++k) {
+    const int yy = y + (k / 3 - 1) * p.dil, xx = x + (k % 3 - 1) * p.dil;
+    float f[8];
+    if (yy >= 0 && yy < p.h && xx >= 0 && xx < p.w) {
+      ld8(p.x + (((ll)img * p.h + yy) * p.w + xx) * p.c + ch, plane, f);
+    } else {
+      for (int j = 0; j < 8; ++j) f[j] = p.border ? p.border[ch + j] : 0.f;
+    }
+    const float* wv = p.wt + (ll)k * p.c + ch;
+    for (int j = 0; j < 8; ++j) acc[j] += f[j] * wv[j];
+  }
+  for (int j = 0; j < 8; ++j) acc[j] = act_fn(acc[j] * p.scale[ch + j] + p.shift[ch + j], p.act);
+  st8(p.y + (((ll)img * p.h + y) * p.w + x) * p.c + ch, plane, acc);
+}
+
+struct IndexFinishP {
+  const uint16_t* b[4];  // the four branch outputs, dense [n, h2, w2, c] each
+  int n, h2, w2, c;
+  uint16_t* idx_en;      // dense [n, 2*h2, 2*w2, c]: softmax over the branches of sigmoid(branch)   (hlindex.py:155-166)
+  uint16_t* idx_de;      //                           sigmoid(branch); branch k lands on sub-pixel (k / 2, k % 2)
+};
+// work item = 8 channels of one LOW-resolution pixel
+TCV_HD void index_finish_body(ll i, const IndexFinishP& p) {
+  const int cv = p.c / 8;
+  const int ch = (int)(i % cv) * 8;
+  ll t = i / cv;
+  const int x = (int)(t % p.w2);
+  t /= p.w2;
+  const int y = (int)(t % p.h2);
+  const int img = (int)(t / p.h2);
+  const ll iplane = (ll)p.n * p.h2 * p.w2 * p.c, oplane = iplane * 4;
+  const ll src = (((ll)img * p.h2 + y) * p.w2 + x) * p.c + ch;
+  float s[4][8], e[4][8], sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = 0; k < 4; ++k) {
+    ld8(p.b[k] + src, iplane, s[k]);
+    for (int j = 0; j < 8; ++j) {
+      s[k][j] = 1.0f / (1.0f + expf(-s[k][j]));
+      e[k][j] = expf(s[k][j]);
+      sum[j] += e[k][j];
+    }
+  }
+  for (int k = 0; k < 4; ++k) {
+    const ll dst = (((ll)img * 2 * p.h2 + 2 * y + (k >> 1)) * (2 * p.w2) + 2 * x + (k & 1)) * p.c + ch;
+    float z[8];
+    for (int j = 0; j < 8; ++j) z[j] = e[k][j] / sum[j];
+    st8(p.idx_en + dst, oplane, z);
+    st8(p.idx_de + dst, oplane, s[k]);
+  }
+}
+
+struct IndexPoolP {
+  const uint16_t* x;       // dense [n, h, w, c]
+  const uint16_t* idx_en;  // dense [n, h, w, c]
+  int n, h, w, c;
+  uint16_t* masked;        // dense [n, h, w, c] = idx_en * x                         (net.py:193,201,...)
+  uint16_t* pooled;        // dense [n, h/2, w/2, c] = 4 * avg_pool2(idx_en * x) = sum over the 2x2 window
+};
+// work item = 8 channels of one POOLED pixel
+TCV_HD void index_pool_body(ll i, const IndexPoolP& p) {
+  const int cv = p.c / 8;
+  const int ch = (int)(i % cv) * 8;
+  ll t = i / cv;
+  const int oh = p.h / 2, ow = p.w / 2;
+  const int x = (int)(t % ow);
+  t /= ow;
+  const int y = (int)(t % oh);
+  const int img = (int)(t / oh);
+  const ll plane = (ll)p.n * p.h * p.w * p.c, pplane = (ll)p.n * oh * ow * p.c;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = 0; k < 4; ++k) {
+    const ll o = (((ll)img * p.h + 2 * y + (k >> 1)) * p.w + 2 * x + (k & 1)) * p.c + ch;
+    float a[8], b[8];
+    ld8(p.x + o, plane, a);
+    ld8(p.idx_en + o, plane, b);
+    for (int j = 0; j < 8; ++j) {
+      a[j] *= b[j];
+      acc[j] += a[j];
+    }
+    st8(p.masked + o, plane, a);
+  }
+  // the reference pools the STORED product (4 * avg_pool2d of l = idx_en * l); summing the fp32 products differs from that
+  // only by the rounding of the stored tensor
+  st8(p.pooled + (((ll)img * oh + y) * ow + x) * p.c + ch, pplane, acc);
+}
+
+struct IndexUpcatP {
+  const uint16_t* dec;   // dense [n, h >> up, w >> up, dec_c]: decoder feature, first dec_real channels are used
+  const uint16_t* idx;   // dense [n, h, w, idx_c] decoder indices (NULL: no index guidance)
+  const uint16_t* low;   // dense [n, h, w, low_c]: encoder feature, first low_real channels are used
+  int n, h, w, up;       // up = 1: nearest x2 upsampling of dec (only together with idx), 0: same resolution
+  int dec_c, dec_real, idx_c, low_c, low_real, cat_c;
+  uint16_t* cat;         // dense [n, h, w, cat_c] = [ idx * up(dec) | low | 0 ]     (hldecoder.py:121-127)
+  ll idx_plane, low_plane;   // elements between the hi and lo plane of idx / low (they may be image slices of a larger tensor)
+};
+// work item = 8 channels of one output pixel
+TCV_HD void index_upcat_body(ll i, const IndexUpcatP& p) {
+  const int cv = p.cat_c / 8;
+  const int ch = (int)(i % cv) * 8;
+  ll t = i / cv;
+  const int x = (int)(t % p.w);
+  t /= p.w;
+  const int y = (int)(t % p.h);
+  const int img = (int)(t / p.h);
+  const ll px = ((ll)img * p.h + y) * p.w + x;
+  float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (ch < p.dec_real) {
+    const int dh = p.h >> p.up, dw = p.w >> p.up;
+    ld8(p.dec + (((ll)img * dh + (y >> p.up)) * dw + (x >> p.up)) * p.dec_c + ch, (ll)p.n * dh * dw * p.dec_c, f);
+    if (p.idx) {
+      float g[8];
+      ld8(p.idx + px * p.idx_c + ch, p.idx_plane, g);
+      for (int j = 0; j < 8; ++j) f[j] *= g[j];
+    }
+  } else if (ch < p.dec_real + p.low_real) {
+    ld8(p.low + px * p.low_c + (ch - p.dec_real), p.low_plane, f);
+  }
+  st8(p.cat + px * p.cat_c + ch, (ll)p.n * p.h * p.w * p.cat_c, f);
 }
 
 }  // namespace tcv_fba

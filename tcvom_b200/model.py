@@ -25,6 +25,8 @@ from .engine import Act, GcaVmnEngine, Plan, named_tensors
 from .dim_engine import DimVmnEngine
 from .dim_modules import DIMDecoderParams, DIMEncoderParams
 from .fba_engine import FbaVmnEngine
+from .index_engine import IndexVmnEngine
+from .index_modules import IndexDecoderParams, IndexEncoderParams
 from .fba_modules import FBADecoderParams, FBAEncoderParams
 from .train_engine import TrainEngine
 from .modules import GCADecoderParams, GCAEncoderParams, GuidedCxtAttenParams, TAMParams
@@ -420,6 +422,64 @@ class _DIMDecoder(DIMDecoderParams):
         return self
 
 
+class _FourChannelVMN(VMN):
+    """Shared inference forward of the base networks that read normalised RGB + the one-channel trimap (TRIMAP_CHANNEL == 1,
+    models/model.py:22-27: 'dim', 'index')."""
+    ENGINE = None
+    NAME = ""
+
+    def engine(self):
+        return _engine_for(self, self.decoder.fam.window, self.ENGINE)
+
+    def forward(self, images: List[torch.Tensor], masks: Sequence[torch.Tensor], extras=None):
+        if self.training:
+            raise NotImplementedError(f"tcvom_b200: {self.NAME} is built for inference; call .eval()")
+        if extras is not None:
+            raise NotImplementedError("tcvom_b200: `extras` is only used by the FBA base network")
+        S = len(images)
+        for i in range(S):
+            images[i] = images[i].squeeze(1)                        # VMN_model.py:94 (in-place list update)
+        x0 = images[0]
+        _require_cuda(x0, "images")
+        B, Cin, H, W = x0.shape
+        assert Cin == 4, f"{self.NAME} takes 3 image channels + the one-channel trimap"
+        if H % 32 or W % 32:
+            raise ValueError("tcvom_b200: H and W must be multiples of 32 (pred_test.py pads to 32)")
+        eng = self.engine()
+        L = _cabi.lib()
+        st = _stream(x0.device)
+        x8 = Act.empty(B * S, H, W, 8, x0.device)
+        trimask = torch.empty((B * S, H, W), dtype=torch.float32, device=x0.device)
+        for i in range(S):
+            xi = images[i].contiguous().float()
+            mi = masks[i].reshape(B, H, W).float()
+            for b in range(B):
+                n = b * S + i
+                _cabi.check(L.tcv_nchw_to_split(xi[b].data_ptr(), 1, 4, H, W, 8, x8.slice(n, n + 1).ptr, x8.plane, st),
+                            "nchw_to_split")
+                trimask[n].copy_(mi[b])
+        out = eng.window_program(x8, trimask, B, S, H, W)
+        preds: List[Optional[torch.Tensor]] = [None] * S
+        attb: List[Optional[torch.Tensor]] = [None] * S
+        attf: List[Optional[torch.Tensor]] = [None] * S
+        small: List[Optional[torch.Tensor]] = [None] * S
+        for i in range(1, S - 1):
+            preds[i] = out["pred"][:, i - 1]
+            attb[i] = out["attb"][:, i - 1]
+            attf[i] = out["attf"][:, i - 1]
+            small[i] = out["small_mask"][:, i - 1].bool()
+        preds[0] = torch.zeros_like(preds[1])
+        preds[-1] = torch.zeros_like(preds[-2])
+        return preds, attb, attf, small
+
+
+class VMN_Index(_FourChannelVMN):
+    """Video matting network (VMN_model.py:70-113) with the IndexNet base net (models/VMN/__init__.py:22-24, VMN_Index.py,
+    models/Index/net.py), native inference forward."""
+    ENGINE = IndexVmnEngine
+    NAME = "vmn_index"
+
+
 class VMN_DIM(VMN):
     """Video matting network (VMN_model.py:70-113) with the Deep-Image-Matting base net (models/VMN/__init__.py:15-17,
     VMN_DIM.py), native inference forward.  images: S tensors [B,1,4,H,W] (normalised RGB + trimap / 255,
@@ -504,10 +564,7 @@ def trimap_transform(trimap: torch.Tensor) -> torch.Tensor:
 
 def get_VMN_models(arch, agg_window, agg_reduction=1, freeze_backbone=False, **kwargs):
     """Plugin seam of the reference (models/VMN/__init__.py:11-29)."""
-    if arch not in ('vmn_gca', 'vmn_fba', 'vmn_dim'):
-        if arch == 'vmn_index':
-            raise NotImplementedError("tcvom_b200: base network 'vmn_index' (IndexNet / MobileNetV2) is outside the built "
-                                      "hot path (vmn_gca, vmn_fba, vmn_dim)")
+    if arch not in ('vmn_gca', 'vmn_fba', 'vmn_dim', 'vmn_index'):
         raise ValueError
     if agg_reduction != 1:
         raise NotImplementedError("tcvom_b200: agg_reduction != 1 is not supported")
@@ -516,6 +573,11 @@ def get_VMN_models(arch, agg_window, agg_reduction=1, freeze_backbone=False, **k
         d = _FBADecoder(agg_reduction, int(agg_window), freeze_backbone=freeze_backbone)
         d.fam = FeatureAggregationModule(256, agg_reduction, int(agg_window))
         return VMN_FBA(encoder=e, decoder=d, freeze_backbone=freeze_backbone)
+    if arch == 'vmn_index':
+        e = IndexEncoderParams()
+        d = IndexDecoderParams(agg_reduction, int(agg_window), freeze_backbone=freeze_backbone)
+        d.fam = FeatureAggregationModule(32, agg_reduction, int(agg_window))
+        return VMN_Index(encoder=e, decoder=d, freeze_backbone=freeze_backbone)
     if arch == 'vmn_dim':
         e = DIMEncoderParams(4)
         d = _DIMDecoder(agg_reduction, int(agg_window), freeze_backbone=freeze_backbone)
@@ -548,7 +610,7 @@ class EvalModel(nn.Module):
         self.NET = get_VMN_models(arch=model, **kwargs)
         self.window = kwargs['agg_window']
         self.method = model[model.rfind('_') + 1:]
-        self.TRIMAP_CHANNEL = {'fba': 8, 'dim': 1}.get(self.method, 3)      # models/model.py:22-27
+        self.TRIMAP_CHANNEL = {'fba': 8, 'dim': 1, 'index': 1}.get(self.method, 3)      # models/model.py:22-27
 
     # -- plan handling ---------------------------------------------------------------
     def _plan_fba(self, B, S, H, W, u8=False) -> Plan:
@@ -592,7 +654,7 @@ class EvalModel(nn.Module):
             n0 = _cabi.launch_count()
             eng._call("tcv_preprocess_eval" + sfx, imgs.data_ptr(), tris.data_ptr(), B * S, H, W, dil, x8.ptr,
                       trimask.data_ptr(), tmp.data_ptr())
-            if self.method == 'dim':
+            if self.method in ('dim', 'index'):
                 # TRIMAP_CHANNEL == 1 (models/model.py:368,392): the network reads the raw trimap / 255 as its 4th channel
                 eng._call("tcv_dim_fix_inputs", tris.data_ptr(), 1 if u8 else 0, B * S, H, W, x8.ptr)
             out = eng.window_program(x8, trimask, B, S, H, W)

@@ -57,3 +57,16 @@ def fixture_sd_dim():
         from oracle.vmn_dim_oracle import fixture_sd_dim as make
         _SD["dim"] = make()
     return _SD["dim"]
+
+
+def key_table_index():
+    with open(os.path.join(GOLDEN, "vmn_index_keys.json")) as f:
+        return json.load(f)
+
+
+def fixture_sd_index():
+    """The seeded ``vmn_index`` fixture checkpoint (555 keys, CPU fp32)."""
+    if "index" not in _SD:
+        from oracle.vmn_index_oracle import fixture_sd_index as make
+        _SD["index"] = make({k: tuple(s) for k, s in key_table_index()["state_dict"]})
+    return _SD["index"]

@@ -850,6 +850,35 @@ int tcv_fba_fusion(const void* o8, const void* x16, long long x16_plane, long lo
   return run_body<FusionP, fba_fusion_body>(p, (ll)n * h * w);
 }
 
+int tcv_dwconv3x3(const void* x, int n, int h, int w, int c, int dil, const float* wt, const float* scale, const float* shift,
+                  const float* border, int act, void* y, tcv_stream_t) {
+  REQ(c % 8 == 0 && dil >= 1, "dwconv3x3: dims");
+  DwConvP p{(const uint16_t*)x, n, h, w, c, dil, wt, scale, shift, border, act, (uint16_t*)y};
+  return run_body<DwConvP, dwconv3x3_body>(p, (ll)n * h * w * (c / 8));
+}
+
+int tcv_index_finish(const void* b0, const void* b1, const void* b2, const void* b3, int n, int h2, int w2, int c,
+                     void* idx_en, void* idx_de, tcv_stream_t) {
+  IndexFinishP p{{(const uint16_t*)b0, (const uint16_t*)b1, (const uint16_t*)b2, (const uint16_t*)b3}, n, h2, w2, c,
+                 (uint16_t*)idx_en, (uint16_t*)idx_de};
+  return run_body<IndexFinishP, index_finish_body>(p, (ll)n * h2 * w2 * (c / 8));
+}
+
+int tcv_index_pool(const void* x, const void* idx_en, int n, int h, int w, int c, void* masked, void* pooled, tcv_stream_t) {
+  IndexPoolP p{(const uint16_t*)x, (const uint16_t*)idx_en, n, h, w, c, (uint16_t*)masked, (uint16_t*)pooled};
+  return run_body<IndexPoolP, index_pool_body>(p, (ll)n * (h / 2) * (w / 2) * (c / 8));
+}
+
+int tcv_index_upcat(const void* dec, int dec_c, int dec_real, int up, const void* idx, int idx_c, long long idx_plane,
+                    const void* low, int low_c, long long low_plane, int low_real, int n, int h, int w, int cat_c, void* cat,
+                    tcv_stream_t) {
+  if (idx_plane == 0) idx_plane = (ll)n * h * w * idx_c;
+  if (low_plane == 0) low_plane = (ll)n * h * w * low_c;
+  IndexUpcatP p{(const uint16_t*)dec, (const uint16_t*)idx, (const uint16_t*)low, n, h, w, up, dec_c, dec_real, idx_c, low_c,
+                low_real, cat_c, (uint16_t*)cat, idx_plane, low_plane};
+  return run_body<IndexUpcatP, index_upcat_body>(p, (ll)n * h * w * (cat_c / 8));
+}
+
 int tcv_maxpool2_idx(const void* x, int n, int h, int w, int c, void* y, uint8_t* idx, tcv_stream_t) {
   REQ(h % 2 == 0 && w % 2 == 0 && c % 8 == 0, "maxpool2_idx: dims");
   Pool2P p{(const uint16_t*)x, n, h, w, c, (uint16_t*)y, idx};

@@ -47,8 +47,8 @@ def test_get_vmn_models_error_behaviour():
     import tcvom_b200
     with pytest.raises(ValueError):
         tcvom_b200.get_VMN_models("nope", agg_window=7)   # VMN/__init__.py:26-27
-    with pytest.raises(NotImplementedError):
-        tcvom_b200.get_VMN_models("vmn_index", agg_window=7)
+    for arch in ("vmn_gca", "vmn_fba", "vmn_dim", "vmn_index"):          # the four base networks of models/VMN/__init__.py
+        assert tcvom_b200.get_VMN_models(arch, agg_window=7) is not None
 
 
 def test_fba_state_dict_contract_matches_reference_layout():

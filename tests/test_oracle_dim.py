@@ -52,5 +52,3 @@ def test_native_module_has_the_reference_state_dict_layout():
     got = [(k, tuple(v.shape)) for k, v in net.state_dict().items()]
     assert got == want
     net.load_state_dict(fixture_sd_dim(), strict=True)
-    with pytest.raises(NotImplementedError):
-        tcvom_b200.get_VMN_models("vmn_index", agg_window=7)
