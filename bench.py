@@ -390,20 +390,25 @@ def run_fba_section(args, rank, world, dev, max_over_ranks):
 DIM_GFLOP_PER_WINDOW = 7103.1       # convolution FLOPs of EvalModel('vmn_dim') at 1088x1920: 3 x 2028.9 (per frame) + 1016.3 (tail)
 
 
-def run_dim_section(args, rank, world, dev, max_over_ranks):
-    """Secondary measurement: EvalModel('vmn_dim') forward on one 1088x1920 3-frame window per GPU (SURVEY.md section 8 row
-    f4, the third base network behind the plugin seam).  Inputs resident in HBM, CUDA-graph replay."""
+INDEX_GFLOP_PER_WINDOW = 874.0      # torch FlopCounterMode over the oracle's EvalModel('vmn_index') forward, scaled to 1088x1920
+
+
+def run_dim_section(args, rank, world, dev, max_over_ranks, arch="vmn_dim"):
+    """Secondary measurement: EvalModel('vmn_dim' | 'vmn_index') forward on one 1088x1920 3-frame window per GPU (SURVEY.md
+    section 8 row f4, the third and fourth base network behind the plugin seam).  Inputs resident in HBM, CUDA-graph replay."""
     import gc
     import torch
     import tcvom_b200
     from tcvom_b200 import synthetic
     from tcvom_b200.engine import release_idle_pools
-    from helpers import fixture_sd_dim
+    from helpers import fixture_sd_dim, fixture_sd_index
+    label, gflop, fixture = (("DIM+TAM", DIM_GFLOP_PER_WINDOW, fixture_sd_dim) if arch == "vmn_dim" else
+                             ("IndexNet+TAM", INDEX_GFLOP_PER_WINDOW, fixture_sd_index))
     ms_local, info, err = -1.0, {}, None
     try:
         torch.cuda.reset_peak_memory_stats(dev)
-        model = tcvom_b200.EvalModel(model="vmn_dim", agg_window=7, dilate_kernel=None)
-        model.NET.load_state_dict(fixture_sd_dim(), strict=True)
+        model = tcvom_b200.EvalModel(model=arch, agg_window=7, dilate_kernel=None)
+        model.NET.load_state_dict(fixture(), strict=True)
         model = model.to(dev).eval()
         imgs_np, tris_np = synthetic.make_window(H, W, seed=7 + rank)
         imgs, tris = torch.from_numpy(imgs_np).to(dev), torch.from_numpy(tris_np).to(dev)
@@ -440,10 +445,10 @@ def run_dim_section(args, rank, world, dev, max_over_ranks):
     ms = max_over_ranks(ms_local)
     any_failed = max_over_ranks(1.0 if (err is not None or ms_local < 0) else 0.0) > 0
     if any_failed:
-        return dict(workload="DIM+TAM forward 1080p", error=err or "failed on another rank")
-    return dict(workload="DIM+TAM forward-only 1080p 3-frame window, batch 1 per GPU (vmn_dim, SURVEY 8 f4; "
-                         f"{DIM_GFLOP_PER_WINDOW:.1f} GFLOP/window, convolutions only)",
-                ms_per_window=ms, windows_per_s=world * 1e3 / ms, algorithmic_tflops=DIM_GFLOP_PER_WINDOW / ms, **info)
+        return dict(workload=f"{label} forward 1080p", error=err or "failed on another rank")
+    return dict(workload=f"{label} forward-only 1080p 3-frame window, batch 1 per GPU ({arch}, SURVEY 8 f4; "
+                         f"{gflop:.1f} GFLOP/window, convolutions only)",
+                ms_per_window=ms, windows_per_s=world * 1e3 / ms, algorithmic_tflops=gflop / ms, **info)
 
 
 # ------------------------------------------------------------------------------------- reference on the same GPU
@@ -713,9 +718,10 @@ def run_native(args, rank, world, local_rank):
         release_idle_pools()
         torch.cuda.empty_cache()
         fba = run_fba_section(args, rank, world, dev, max_over_ranks)
-    dim = None
+    dim = index = None
     if not args.no_dim:
         dim = run_dim_section(args, rank, world, dev, max_over_ranks)
+        index = run_dim_section(args, rank, world, dev, max_over_ranks, arch="vmn_index")
 
     if rank != 0:
         if world > 1:
@@ -748,7 +754,7 @@ def run_native(args, rank, world, local_rank):
                          h2d_bytes_per_step=imgs_u8.numel() + tris_u8.numel(), input_dtype="uint8",
                          d2h_bytes_per_step=out_h.numel() * 4),
                 gpu_launches=launches, roofline=roof, cpu_baseline=cpu, gpu_eager_baseline=eager, train_step=train,
-                train_step_1080p=train_1080, fba_forward=fba, dim_forward=dim)
+                train_step_1080p=train_1080, fba_forward=fba, dim_forward=dim, index_forward=index)
     print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -765,7 +771,7 @@ def main():
                     help="skip the reference-on-this-GPU measurement (PyTorch eager, N=1 only)")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
     ap.add_argument("--no-fba", action="store_true", help="skip the secondary FBA+TAM forward measurement (configs[4])")
-    ap.add_argument("--no-dim", action="store_true", help="skip the secondary DIM+TAM forward measurement (SURVEY 8 f4)")
+    ap.add_argument("--no-dim", action="store_true", help="skip the secondary DIM+TAM / IndexNet+TAM forward measurements (SURVEY 8 f4)")
     ap.add_argument("--dump-calls", default=None, help="write the per-launch timing table (JSON lines) here")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: everything else -- Python prints of the reference modules AND C-level writes to
