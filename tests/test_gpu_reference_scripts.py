@@ -109,6 +109,38 @@ def test_pred_test_script_runs_vmn_dim_on_the_native_package(tmp_path):
     assert any(len(np.unique(o)) > 8 for o in outs["native"]), "vacuous clip"
 
 
+def test_pred_test_script_runs_vmn_index_on_the_native_package(tmp_path):
+    """The same script with --model vmn_index: install() routes EvalModel('vmn_index') to the native IndexNet+TAM path; its
+    PNGs against the reference's own GPU run (TF32 convolutions there) and against the CPU oracle."""
+    import cv2
+    import torch.nn.functional as F
+    from helpers import fixture_sd_index
+    from oracle import vmn_index_oracle as O
+    H, W, T = 90, 120, 4                        # not a multiple of 32: exercises TestFolder.possible_pad (reflect)
+    data = tmp_path / "data"
+    imgs, tris = _write_clip(str(data / "clip0"), H, W, T)
+    ckpt = str(tmp_path / "fixture_index.pth")
+    sd = fixture_sd_index()
+    torch.save(sd, ckpt)
+    outs = {}
+    for arm, flags in (("native", ["--native"]), ("reference", [])):
+        save = str(tmp_path / f"out_{arm}")
+        _run(flags + ["pred_test.py", "--model", "vmn_index", "--load", ckpt, "--data", str(data), "--save", save, "--gpu", "0"])
+        outs[arm] = [cv2.imread(os.path.join(save, "clip0", f"{t:04d}_alpha.png"), cv2.IMREAD_GRAYSCALE) for t in range(T)]
+        assert all(o is not None and o.shape == (H, W) for o in outs[arm]), arm
+    ti = F.pad(torch.from_numpy(imgs[0]).float(), (0, 128 - W, 0, 96 - H), mode="reflect")
+    tt = F.pad(torch.from_numpy(tris[0]).float(), (0, 128 - W, 0, 96 - H), mode="reflect")
+    for c in range(T):
+        p = c + 1 if c == 0 else c - 1
+        n = c - 1 if c == T - 1 else c + 1
+        ref = O.eval_forward(sd, ti[[p, c, n]][None], tt[[p, c, n]][None])[0, 1, 0, :H, :W].numpy()
+        want = np.uint8(np.clip(ref, 0, 1) * 255)
+        d = np.abs(outs["native"][c].astype(np.int32) - want.astype(np.int32)).max()
+        assert d <= 1, (c, d)                  # 1e-3 on alpha = at most one grey level after the uint8 truncation
+        assert np.abs(outs["native"][c].astype(np.int32) - outs["reference"][c].astype(np.int32)).max() <= 4
+    assert any(len(np.unique(o)) > 8 for o in outs["native"]), "vacuous clip"
+
+
 def _train_cfg(tmp_path, ckpt):
     cfg = tmp_path / "gca_tiny.yaml"
     cfg.write_text(
