@@ -694,7 +694,16 @@ TCV_HD void dwconv3x3_body(ll i, const DwConvP& p) {
     } else {
       for (int j = 0; j < 8; ++j) f[j] = p.border ? p.border[ch + j] : 0.f;
     }
-    const float* wv = p.wt + (ll)k * p.c + ch;
+    float wv[8];
+#ifdef __CUDA_ARCH__
+    {   // (ch and c are multiples of 8: two aligned 16-byte loads instead of eight scalar ones)
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.wt + (ll)k * p.c + ch));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.wt + (ll)k * p.c + ch + 4));
+      wv[0] = w0.x; wv[1] = w0.y; wv[2] = w0.z; wv[3] = w0.w; wv[4] = w1.x; wv[5] = w1.y; wv[6] = w1.z; wv[7] = w1.w;
+    }
+#else
+    for (int j = 0; j < 8; ++j) wv[j] = p.wt[(ll)k * p.c + ch + j];
+#endif
     for (int j = 0; j < 8; ++j) acc[j] += f[j] * wv[j];
   }
   for (int j = 0; j < 8; ++j) acc[j] = act_fn(acc[j] * p.scale[ch + j] + p.shift[ch + j], p.act);
