@@ -35,6 +35,7 @@ class DimVmnEngine(GcaVmnEngine):
     def __init__(self, window: int):
         super().__init__(window)
         self.s2d_stride2 = False          # no stride-2 convolutions in this network
+        self._hold: list = []
         import os
         # alpha head as one HBM-bound kernel (default) or as the zero-padded 32-output-channel tensor-core conv chain
         self.head_direct = os.environ.get("TCV_HEAD_DIRECT", "1") == "1"

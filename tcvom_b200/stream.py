@@ -14,7 +14,7 @@ times; it is an additional entry point:
         out = stream.push(img, tri)                          # None for the first two frames, then the result for the
                                                              # PREVIOUS frame: alpha [1,H,W] (vmn_fba: alpha, F, B)
 
-Works for both base networks (the engines share the ``per_frame`` / ``tail`` split).  All compute goes through the same
+Works for all four base networks (the engines share the ``per_frame`` / ``tail`` split).  All compute goes through the same
 recorded plans / C-ABI calls as ``EvalModel.forward``; torch only moves the cached tensors between the static
 per-frame buffers and the three-frame window buffers.
 """
@@ -41,13 +41,25 @@ def _flat_acts(pf: dict) -> Dict[str, Act]:
     return out
 
 
-def _unflatten(flat: Dict[str, Act], like: dict) -> dict:
+def _flat_tensors(pf: dict) -> Dict[str, torch.Tensor]:
+    """name -> plain tensor with a leading image dimension (vmn_dim: the uint8 max-pooling indices the tail unpools with)."""
+    out: Dict[str, torch.Tensor] = {}
+    for k, v in pf.items():
+        if isinstance(v, (list, tuple)):
+            for i, a in enumerate(v):
+                if isinstance(a, torch.Tensor):
+                    out[f"{k}.{i}"] = a
+    return out
+
+
+def _unflatten(flat: Dict[str, Act], like: dict, tensors: Optional[Dict[str, torch.Tensor]] = None) -> dict:
     out = {}
     for k, v in like.items():
         if isinstance(v, Act):
             out[k] = flat[k]
         elif isinstance(v, (list, tuple)):
-            out[k] = [flat.get(f"{k}.{i}") for i in range(len(v))]
+            out[k] = [flat.get(f"{k}.{i}") if not isinstance(a, torch.Tensor) else tensors[f"{k}.{i}"]
+                      for i, a in enumerate(v)]
     return out
 
 
@@ -88,17 +100,21 @@ class FrameStream:
                 eng.encode_inputs(self.f_img, self.f_tri, 1, H, W, x16)
                 pf = eng.per_frame(x16)
             else:
+                if model.method in ('dim', 'index'):      # TRIMAP_CHANNEL == 1: the raw trimap / 255 is the 4th channel
+                    eng._call("tcv_dim_fix_inputs", self.f_tri.data_ptr(), 1 if u8 else 0, 1, H, W, x8.ptr)
                 pf = eng.per_frame(x8)
             self.frame_plan.n_launch = _cabi.launch_count() - n0
         finally:
             eng._rec = None
         self.f_acts = _flat_acts(pf)
+        self.f_tensors = _flat_tensors(pf)
 
         # ---- three-frame window buffers (previous, centre, next) for everything the tail may read
         dev = eng.device
         self.w_acts = {k: Act.empty(3, a.h, a.w, a.c, dev) for k, a in self.f_acts.items()}
         for a in self.w_acts.values():
             a.buf.zero_()
+        self.w_tensors = {k: torch.zeros((3,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev) for k, t in self.f_tensors.items()}
         self.w_img = torch.zeros((1, 3, 3, H, W), dtype=in_dt, device=dev)
         self.w_tri = torch.zeros((1, 3, 1, H, W), dtype=in_dt, device=dev)
         self.w_trimask = torch.zeros((3, H, W), dtype=torch.float32, device=dev)
@@ -115,7 +131,7 @@ class FrameStream:
             self.small_mask = eng._empty((1, 1, 1, H // 8, W // 8), torch.uint8)
             self.alphas = eng._empty((1, 3, 1, H, W))
             n0 = _cabi.launch_count()
-            eng.tail(_unflatten(self.w_acts, pf), 0, 1, self.w_trimask.data_ptr() + 4 * H * W, H * W, H, W,
+            eng.tail(_unflatten(self.w_acts, pf, self.w_tensors), 0, 1, self.w_trimask.data_ptr() + 4 * H * W, H * W, H, W,
                      self.pred.data_ptr(), self.attb.data_ptr(), self.attf.data_ptr(), self.small_mask.data_ptr())
             if self.fba:
                 self.Fs = eng._empty((1, 3, 3, H, W))
@@ -162,6 +178,8 @@ class FrameStream:
         self._run(self.frame_plan)
         for k, w in self.w_acts.items():
             self._shift(w.buf, 1, self.f_acts[k].buf[:, 0])          # buf: [2 planes, images, h, w, c]
+        for k, w in self.w_tensors.items():
+            self._shift(w, 0, self.f_tensors[k][0])
         self._shift(self.w_img, 1, self.f_img[0, 0])
         self._shift(self.w_tri, 1, self.f_tri[0, 0])
         self._shift(self.w_trimask, 0, self.f_trimask[0])

@@ -7,7 +7,7 @@ scale / shift can land on the neighbouring float -- hence a 5e-5 bound there ins
 import pytest
 import torch
 
-from helpers import fixture_sd, fixture_sd_fba
+from helpers import fixture_sd, fixture_sd_dim, fixture_sd_fba, fixture_sd_index
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -19,11 +19,13 @@ def _clip(H, W, frames, seed):
     return torch.from_numpy(imgs).to(DEV), torch.from_numpy(tris).to(DEV)
 
 
-@pytest.mark.parametrize("arch,dilate", [("vmn_gca", None), ("vmn_gca", 3), ("vmn_fba", None)])
+@pytest.mark.parametrize("arch,dilate", [("vmn_gca", None), ("vmn_gca", 3), ("vmn_fba", None), ("vmn_dim", 2),
+                                         ("vmn_index", None)])
 def test_stream_equals_windowed_forward(arch, dilate):
     import tcvom_b200
     m = tcvom_b200.EvalModel(model=arch, agg_window=7, dilate_kernel=dilate)
-    m.NET.load_state_dict(fixture_sd() if arch == "vmn_gca" else fixture_sd_fba(), strict=True)
+    sd = {"vmn_gca": fixture_sd, "vmn_fba": fixture_sd_fba, "vmn_dim": fixture_sd_dim, "vmn_index": fixture_sd_index}[arch]()
+    m.NET.load_state_dict(sd, strict=True)
     m = m.to(DEV).eval()
     H, W, T = 64, 96, 6
     imgs, tris = _clip(H, W, T, seed=15)

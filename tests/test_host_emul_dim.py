@@ -125,3 +125,51 @@ def test_eval_program_matches_reference_golden(emu, name):
     alphas.zero_()
     plan.replay(0)
     assert torch.equal(alphas, first)
+
+
+def test_frame_stream_equals_windowed_program(emu):
+    """tcvom_b200.FrameStream (per-frame feature reuse across sliding windows) against the windowed program on
+    every window of a 5-frame clip: same kernels on the same values."""
+    import tcvom_b200
+    from tcvom_b200 import synthetic
+    from tcvom_b200.engine import Plan
+    from tcvom_b200.stream import FrameStream
+    net = tcvom_b200.get_VMN_models("vmn_dim", agg_window=7)
+    net.load_state_dict(fixture_sd_dim(), strict=True)
+    m = tcvom_b200.EvalModel(model="vmn_dim", agg_window=7, dilate_kernel=2)
+    m.NET = net
+    m.eval()
+    eng = make_engine()
+    eng.refresh_weights(net)
+    H, W = 32, 64
+    imgs, tris = synthetic.make_window(H, W, seed=4, frames=5)
+    imgs, tris = torch.from_numpy(imgs), torch.from_numpy(tris)
+
+    class HostStream(FrameStream):
+        def _run(self, plan):
+            plan.replay(0)
+
+        @staticmethod
+        def _check_input(img):
+            pass
+
+    stream = HostStream(m, H, W, u8=True, engine=eng)
+    outs = [stream.push(imgs[0, t], tris[0, t]) for t in range(5)]
+    assert outs[0] is None and outs[1] is None
+    plan = Plan()
+    eng._rec = plan
+    x8 = eng._act(3, H, W, 8)
+    trimask = eng._empty((3, H, W))
+    tmp = eng._empty((2 * 3 * H * W,), torch.uint8)
+    alphas = eng._empty((1, 3, 1, H, W))
+    im, tr = imgs[:, :3].clone(), tris[:, :3].clone()
+    eng._call("tcv_preprocess_eval_u8", im.data_ptr(), tr.data_ptr(), 3, H, W, 2, x8.ptr, trimask.data_ptr(), tmp.data_ptr())
+    eng._call("tcv_dim_fix_inputs", tr.data_ptr(), 1, 3, H, W, x8.ptr)
+    out = eng.window_program(x8, trimask, 1, 3, H, W)
+    eng._call("tcv_postprocess_eval_u8", out["pred"].data_ptr(), tr.data_ptr(), trimask.data_ptr(), 1, 3, H, W,
+              alphas.data_ptr())
+    eng._rec = None
+    for t in range(1, 4):
+        im.copy_(imgs[:, t - 1:t + 2]); tr.copy_(tris[:, t - 1:t + 2])
+        plan.replay(0)
+        assert float((outs[t + 1] - alphas[0, 1]).abs().max()) < 1e-6
