@@ -610,6 +610,16 @@ int tcv_index_upcat(const void* dec, int dec_c, int dec_real, int up, const void
                     const void* low, int low_c, long long low_plane, int low_real, int n, int h, int w, int cat_c, void* cat,
                     tcv_stream_t stream);
 
+/* Evaluation metrics of one frame (calc_metric.py:22-46,74-98) in one pass over the unknown
+ * region 0 < tri < 255.  alpha / gt / tri (and the NEXT frame's next_alpha / next_gt, or NULL) uint8 [h, w] as read from
+ * the PNGs, flow fp32 [h, w, 2] current -> next in pixels with NaN = invalid (NULL: no warped metric).
+ * out double[7] = (pixel_count, sum |a-g|, sum (a-g)^2, sum ((a-ha)-(g-hg))^2, sum |(a-g)-(pa-pg)|, sum |(a-g)^2-(pa-pg)^2|,
+ * flow_pixel_count) with a = alpha / 255 etc. and pa / pg the next frame sampled bilinearly at x + flow (zero padding):
+ * mSAD = out[1]/out[0], MSE = out[2]/out[0], SSDA = sqrt(out[2]), dtSSD = sqrt(out[3]), MESSDdt_fix = out[4],
+ * MESSDdt = out[5]. */
+int tcv_frame_metrics(const uint8_t* alpha, const uint8_t* gt, const uint8_t* tri, const uint8_t* next_alpha,
+                      const uint8_t* next_gt, const float* flow, int h, int w, double* out, tcv_stream_t stream);
+
 /* C[b] = A[b] . B[b]^T (bf16x3, fp32 out) on the CTA-pair kernel (gemm_tc2.cu) with either operand
  *   K-major  (x_mn == 0): split-bf16 [batch][rows][ld], the reduction index contiguous (K <= ld), or
  *   MN-major (x_mn != 0): split-bf16 [batch][K][ld], the ROW index contiguous (rows <= ld); any K (TMA zero-fills the tail):

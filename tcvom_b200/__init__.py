@@ -6,6 +6,7 @@ Public surface mirrors the reference's operator/plugin interface for this path:
 from .model import (EvalModel, FeatureAggregationModule, FullModel, FullModel_VMD, GuidedCxtAtten, VMN,  # noqa: F401
                     VMN_FBA, get_VMN_models, trimap_transform)
 from .stream import FrameStream  # noqa: F401
+from . import metrics  # noqa: F401  (calc_metric.py's metrics on the GPU)
 
 __version__ = "0.1.0"
 

@@ -129,6 +129,8 @@ SIGNATURES = {
     "tcv_gemm_tc_ex": (c_int, [c_void_p, c_ll, c_ll, c_ll, c_int, c_void_p, c_ll, c_ll, c_ll, c_int, c_void_p, c_int, c_int,
                                c_int, c_ll, c_ll, c_int, c_void_p]),
     "tcv_zero_bytes": (c_int, [c_void_p, c_ll, c_void_p]),
+    "tcv_frame_metrics": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                                  c_void_p]),
     "tcv_dwconv3x3": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                               c_void_p, c_void_p]),
     "tcv_index_finish": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

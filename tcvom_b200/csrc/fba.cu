@@ -377,6 +377,58 @@ int tcv_fba_fusion(const void* o8, const void* x16, long long x16_plane, long lo
   return launch_body<FusionP, fba_fusion_body>(p, (ll)n * h * w, S(stream), "fba_fusion_kernel");
 }
 
+// One thread per four consecutive pixels: the trimap quad is tested first (most of a frame is known foreground / background
+// and costs one 4-byte load), the per-pixel body then reads its bytes from lines the warp already pulled into L1.  Sums are
+// kept in double per thread, reduced over the warp and the CTA, and leave as one atomic per CTA and slot.
+__global__ void __launch_bounds__(256) frame_metrics_kernel(MetricP p, double* __restrict__ out, int vec) {
+  __shared__ float lut[256];
+  lut[threadIdx.x] = metric_u8((uint8_t)threadIdx.x);
+  __syncthreads();
+  p.lut = lut;
+  double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  const int total = p.h * p.w, quads = (total + 3) >> 2;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += gridDim.x * blockDim.x) {
+    const int i0 = q << 2;
+    if (vec && i0 + 3 < total) {
+      const uchar4 t = __ldg(reinterpret_cast<const uchar4*>(p.tri) + q);
+      const unsigned char tk[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (tk[k] > 0 && tk[k] < 255) metric_body(i0 + k, p, acc);
+    } else {
+      for (int k = 0; k < 4 && i0 + k < total; ++k) metric_body(i0 + k, p, acc);
+    }
+  }
+  __shared__ double red[8][7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 7) {
+    double v = 0.0;
+#pragma unroll
+    for (int wp = 0; wp < 8; ++wp) v += red[wp][threadIdx.x];
+    if (v != 0.0) atomicAdd(out + threadIdx.x, v);
+  }
+}
+
+int tcv_frame_metrics(const uint8_t* alpha, const uint8_t* gt, const uint8_t* tri, const uint8_t* next_alpha,
+                      const uint8_t* next_gt, const float* flow, int h, int w, double* out, tcv_stream_t stream) {
+  TCV_REQUIRE(alpha && gt && tri && out && h > 1 && w > 1, "frame_metrics: bad arguments");
+  TCV_REQUIRE((next_alpha == nullptr) == (next_gt == nullptr) && (!flow || next_alpha), "frame_metrics: the next frame needs both images");
+  TCV_CUDA(cudaMemsetAsync(out, 0, 7 * sizeof(double), S(stream)));
+  MetricP p{alpha, gt, tri, next_alpha, next_gt, flow, h, w, nullptr};
+  TCV_REQUIRE((ll)h * w < (1ll << 31) - 4, "frame_metrics: frame too large");
+  const int quads = (h * w + 3) / 4;
+  const int blocks = std::min((quads + 255) / 256, 8 * 148);
+  frame_metrics_kernel<<<blocks, 256, 0, S(stream)>>>(p, out, (reinterpret_cast<uintptr_t>(tri) & 3) == 0);
+  return launched("frame_metrics_kernel");
+}
+
 int tcv_dwconv3x3(const void* x, int n, int h, int w, int c, int dil, const float* wt, const float* scale, const float* shift,
                   const float* border, int act, void* y, tcv_stream_t stream) {
   TCV_REQUIRE(x && wt && scale && shift && y && n > 0 && h > 0 && w > 0 && c % 8 == 0 && dil >= 1, "dwconv3x3: bad arguments");

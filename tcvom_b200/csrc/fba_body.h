@@ -814,4 +814,59 @@ TCV_HD void index_upcat_body(ll i, const IndexUpcatP& p) {
   st8(p.cat + px * p.cat_c + ch, (ll)p.n * p.h * p.w * p.cat_c, f);
 }
 
+// ------------------------------------------------------------------------------------------ calc_metric.py
+struct MetricP {
+  const uint8_t* a;    // predicted alpha, uint8 [h, w]            (calc_metric.py:49-62: PNGs, value / 255.0 -> float32)
+  const uint8_t* g;    // ground-truth alpha
+  const uint8_t* tri;  // trimap; the metrics run over 0 < tri < 255
+  const uint8_t* ha;   // the NEXT frame's prediction / ground truth (NULL: single-frame metrics only)
+  const uint8_t* hg;
+  const float* flow;   // [h, w, 2] optical flow current -> next in pixels, NaN = invalid (NULL: no warped metric)
+  int h, w;
+  const float* lut;    // lut[v] = metric_u8(v), 256 entries (shared memory on the device): no fp64 divide per load
+};
+TCV_HD float metric_u8(uint8_t v) { return (float)((double)v / 255.0); }
+// bilinear sample with zero padding at pixel coordinates (F.grid_sample(align_corners=True) through utils.grid_sampler,
+// utils/utils.py:76-90: the coordinates make the round trip through the normalised grid in fp32)
+TCV_HD float metric_sample(const uint8_t* img, const float* lut, int h, int w, float px, float py) {
+  const float gx = 2.0f * px / (float)(w - 1) - 1.0f, gy = 2.0f * py / (float)(h - 1) - 1.0f;
+  const float ix = (gx + 1.0f) * 0.5f * (float)(w - 1), iy = (gy + 1.0f) * 0.5f * (float)(h - 1);
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  const int x0 = (int)x0f, y0 = (int)y0f;
+  const float wx[2] = {x0f + 1.0f - ix, ix - x0f}, wy[2] = {y0f + 1.0f - iy, iy - y0f};
+  float acc = 0.f;
+  for (int dy = 0; dy < 2; ++dy)
+    for (int dx = 0; dx < 2; ++dx) {
+      const int xx = x0 + dx, yy = y0 + dy;
+      if (xx < 0 || xx >= w || yy < 0 || yy >= h) continue;
+      acc += lut[img[(ll)yy * w + xx]] * (wx[dx] * wy[dy]);
+    }
+  return acc;
+}
+// contributions of pixel i to out[7] = (pixel count, sum |a-g|, sum (a-g)^2, sum ((a-ha)-(g-hg))^2,
+//                                       sum |(a-g)-(pa-pg)|, sum |(a-g)^2-(pa-pg)^2|, flow pixel count)
+TCV_HD void metric_body(ll i, const MetricP& p, double* out) {
+  const uint8_t t = p.tri[i];
+  if (!(t > 0 && t < 255)) return;
+  const float a = p.lut[p.a[i]], g = p.lut[p.g[i]];
+  const float d = a - g;
+  out[0] += 1.0;
+  out[1] += (double)fabsf(d);
+  out[2] += (double)(d * d);
+  if (!p.ha) return;
+  const float dd = (a - p.lut[p.ha[i]]) - (g - p.lut[p.hg[i]]);
+  out[3] += (double)(dd * dd);
+  if (!p.flow) return;
+  const float fx = p.flow[2 * i];
+  float fy = p.flow[2 * i + 1];
+  if (fx != fx) return;                                   // NaN: no flow for this pixel (calc_metric.py:64-70); the
+  if (fy != fy) fy = 0.f;                                 // validity mask is the x channel's (utils/utils.py:109-113)
+  const int y = (int)((unsigned)i / (unsigned)p.w), x = (int)i - y * p.w;   // h * w < 2^31 (checked by the entry point)
+  const float e = metric_sample(p.ha, p.lut, p.h, p.w, (float)x + fx, (float)y + fy) -
+                  metric_sample(p.hg, p.lut, p.h, p.w, (float)x + fx, (float)y + fy);
+  out[4] += (double)fabsf(d - e);
+  out[5] += (double)fabsf(d * d - e * e);
+  out[6] += 1.0;
+}
+
 }  // namespace tcv_fba

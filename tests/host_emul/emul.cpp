@@ -850,6 +850,17 @@ int tcv_fba_fusion(const void* o8, const void* x16, long long x16_plane, long lo
   return run_body<FusionP, fba_fusion_body>(p, (ll)n * h * w);
 }
 
+int tcv_frame_metrics(const uint8_t* alpha, const uint8_t* gt, const uint8_t* tri, const uint8_t* next_alpha,
+                      const uint8_t* next_gt, const float* flow, int h, int w, double* out, tcv_stream_t) {
+  float lut[256];
+  for (int v = 0; v < 256; ++v) lut[v] = metric_u8((uint8_t)v);
+  MetricP p{alpha, gt, tri, next_alpha, next_gt, flow, h, w, lut};
+  for (int k = 0; k < 7; ++k) out[k] = 0.0;
+  for (ll i = 0; i < (ll)h * w; ++i) metric_body(i, p, out);
+  ++g_launches;
+  return 0;
+}
+
 int tcv_dwconv3x3(const void* x, int n, int h, int w, int c, int dil, const float* wt, const float* scale, const float* shift,
                   const float* border, int act, void* y, tcv_stream_t) {
   REQ(c % 8 == 0 && dil >= 1, "dwconv3x3: dims");

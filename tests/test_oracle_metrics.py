@@ -1,0 +1,70 @@
+"""The metrics oracle against the golden vectors of the unmodified reference (tests/golden/make_golden_metrics.py), and the
+metric kernel's body on the host test double against both.  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden
+from test_host_emul_fba import emu  # noqa: F401
+
+from oracle import metrics_oracle as mo
+
+CASES = ["blob96x128", "bigflow64x80", "noflow48x64"]
+KEYS = ("mSAD", "MSE", "SSDA", "dtSSD", "MESSDdt_fix", "MESSDdt", "pixel_count", "flow_pixel_count")
+
+
+def close(got, want, tol=2e-5):
+    for k, w in zip(KEYS, want):
+        g = got[k]
+        if k.endswith("count"):
+            assert int(g) == int(w), k
+        else:
+            assert abs(g - w) <= tol * max(1.0, abs(w)), (k, g, w)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_golden(name):
+    g = golden(f"metrics_{name}.npz")
+    close(mo.frame_metrics(g["a0"], g["g0"], g["t0"], g["a1"], g["g1"], g["flow"]), g["pair"], 1e-6)
+    close(mo.frame_metrics(g["a1"], g["g1"], g["t1"]), g["single"], 1e-6)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_kernel_body_matches_reference_golden(emu, name):
+    from tcvom_b200 import metrics
+    g = golden(f"metrics_{name}.npz")
+    t = lambda k: torch.from_numpy(g[k])
+    out = torch.empty(7, dtype=torch.float64)
+    s = metrics.frame_sums(t("a0"), t("g0"), t("t0"), t("a1"), t("g1"), t("flow"), out=out, _stream_ptr=0)
+    close(metrics.finish(s.tolist(), True), g["pair"])
+    s = metrics.frame_sums(t("a1"), t("g1"), t("t1"), out=out, _stream_ptr=0)
+    close(metrics.finish(s.tolist(), False), g["single"])
+
+
+def test_y_flow_nan_alone_counts_as_zero(emu):
+    """utils/utils.py:109-113: the validity mask is the x channel's; a NaN in y alone becomes a zero displacement."""
+    from tcvom_b200 import metrics
+    rng = np.random.default_rng(5)
+    h, w = 24, 40
+    a, g, ha, hg = (rng.integers(0, 256, (h, w), dtype=np.uint8) for _ in range(4))
+    tri = rng.choice(np.array([0, 128, 255], np.uint8), (h, w))
+    flow = rng.normal(0, 2, (h, w, 2)).astype(np.float32)
+    flow[3:9, 5:20, 1] = np.nan
+    flow[12:15, :, 0] = np.nan
+    want = mo.frame_metrics(a, g, tri, ha, hg, flow)
+    out = torch.empty(7, dtype=torch.float64)
+    s = metrics.frame_sums(*(torch.from_numpy(v) for v in (a, g, tri, ha, hg, flow)), out=out, _stream_ptr=0)
+    close(metrics.finish(s.tolist(), True), [want[k] for k in KEYS])
+
+
+def test_argument_checks():
+    from tcvom_b200 import metrics
+    u = torch.zeros(4, 4, dtype=torch.uint8)
+    with pytest.raises(TypeError):
+        metrics.frame_sums(u.float(), u, u)
+    with pytest.raises(ValueError):
+        metrics.frame_sums(u, u, u, next_alpha=u)
+    with pytest.raises(ValueError):
+        metrics.frame_sums(u, u, u, flow=torch.zeros(4, 4, 2))
+    with pytest.raises(RuntimeError):
+        metrics.frame_sums(u, u, u)            # host tensors: there is no CPU path
