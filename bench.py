@@ -256,7 +256,9 @@ def run_train_section(args, rank, world, dev, barrier, max_over_ranks, shape=Non
     # shape = (batch per GPU, frames, H, W, timed steps, reference GFLOP per sample-step, label)
     TRAIN_B, TRAIN_S, TH_, TW_, steps, gflop, label = shape or (4, 5, 512, 512, 5, TRAIN_GFLOP_PER_SAMPLE, "configs[2]")
     torch.cuda.reset_peak_memory_stats(dev)
-    model = tcvom_b200.FullModel_VMD(model="vmn_gca", agg_window=7, dilate_kernel=None)
+    # TCV_FREEZE_BACKBONE=1 (tools/train_time.py only): the TAM pre-training mode, train_single_ddp.py:184-185
+    freeze = dict(freeze_backbone=True) if os.environ.get("TCV_FREEZE_BACKBONE") == "1" else {}
+    model = tcvom_b200.FullModel_VMD(model="vmn_gca", agg_window=7, dilate_kernel=None, **freeze)
     model.NET.load_state_dict(fixture_sd(), strict=True)
     if world > 1:
         model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model).to(dev)

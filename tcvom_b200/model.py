@@ -28,7 +28,7 @@ from .fba_engine import FbaVmnEngine
 from .index_engine import IndexVmnEngine
 from .index_modules import IndexDecoderParams, IndexEncoderParams
 from .fba_modules import FBADecoderParams, FBAEncoderParams
-from .train_engine import TrainEngine
+from .train_engine import FROZEN_PREFIXES, FrozenBackboneEngine, TrainEngine
 from .modules import GCADecoderParams, GCAEncoderParams, GuidedCxtAttenParams, TAMParams
 
 
@@ -74,11 +74,25 @@ def _train_engine_for(module: nn.Module, window: int) -> TrainEngine:
         if eng is None:
             eng = table[dev.index] = TrainEngine(window)
     eng.refresh_weights(module)
+    eng.freeze_backbone = bool(getattr(module, "freeze_backbone", False))
+    if eng.freeze_backbone:
+        if eng.backbone is None:
+            eng.backbone = FrozenBackboneEngine(window)
+        eng.backbone.refresh_weights(module)
     sync = any(isinstance(m, nn.SyncBatchNorm) for m in module.modules())
     dist = torch.distributed
     eng.sync_bn = bool(sync and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
     eng.world = dist.get_world_size() if eng.sync_bn else 1
     return eng
+
+
+def _trainable_names(net: nn.Module, named) -> List[str]:
+    """Parameters the native step returns gradients for.  With ``freeze_backbone`` the frozen part runs under no_grad in the
+    reference, so its parameters keep ``grad is None`` (an optimizer with weight decay must not touch them)."""
+    names = [n for n, t in named.items() if isinstance(t, nn.Parameter) and t.requires_grad]
+    if getattr(net, "freeze_backbone", False):
+        names = [n for n in names if not n.startswith(FROZEN_PREFIXES)]
+    return names
 
 
 class _TrainStepFn(torch.autograd.Function):
@@ -265,8 +279,6 @@ class VMN(nn.Module):
 
     def _forward_train(self, images, masks):
         """Train-mode VMN.forward (VMN_model.py:83-113) on the native training engine, autograd-connected."""
-        if self.freeze_backbone:
-            raise NotImplementedError("tcvom_b200: freeze_backbone training (pretrain_ddp.py) is not built")
         S = len(images)
         for i in range(S):
             images[i] = images[i].squeeze(1)
@@ -288,7 +300,7 @@ class VMN(nn.Module):
                             "nchw_to_split")
             trimask[:, i] = masks[i].reshape(B, 1, H, W).float()
         named = named_tensors(self)
-        names = [n for n, t in named.items() if isinstance(t, nn.Parameter) and t.requires_grad]
+        names = _trainable_names(self, named)
         self.__dict__["_train_param_names"] = names
         params = [named[n] for n in names]
         if torch.is_grad_enabled():
@@ -796,8 +808,6 @@ class FullModel_VMD(nn.Module):
         power iteration), losses.  Returns the tensors the backward needs plus the visualisation outputs."""
         if self.method != 'gca':
             raise NotImplementedError("tcvom_b200: training is built for vmn_gca only")
-        if getattr(self.NET, "freeze_backbone", False):
-            raise NotImplementedError("tcvom_b200: freeze_backbone training (pretrain_ddp.py) is not built")
         B, S = a.shape[:2]
         H, W = a.shape[-2:]
         dev = a.device
@@ -848,7 +858,7 @@ class FullModel_VMD(nn.Module):
 
     def _train_step(self, a, fg, bg):
         named = named_tensors(self.NET)
-        names = [n for n, t in named.items() if isinstance(t, nn.Parameter) and t.requires_grad]
+        names = _trainable_names(self.NET, named)
         self.__dict__["_train_param_names"] = names
         params = [named[n] for n in names]
         if torch.is_grad_enabled() and not names:

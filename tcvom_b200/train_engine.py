@@ -39,6 +39,19 @@ class TAct:
         self.a, self.g, self.g_owned, self.needs_grad, self.groups = a, None, False, needs_grad, groups
 
 
+# the part of vmn_gca that ``freeze_backbone=True`` keeps in eval mode under no_grad: the whole encoder (VMN_model.py:77-81,
+# 99-103) and the decoder's feature-extraction half (VMN_GCA.py:18-24,26-34)
+FROZEN_PREFIXES = ("encoder.", "decoder.layer1.", "decoder.layer2.", "decoder.gca.")
+
+
+class FrozenBackboneEngine(GcaVmnEngine):
+    """Inference engine over the frozen part only: its folded / packed weights are re-derived when a BACKBONE tensor changes,
+    not on every optimizer step of the trainable tail."""
+
+    def _named(self) -> Dict[str, torch.Tensor]:
+        return {k: v for k, v in super()._named().items() if k.startswith(FROZEN_PREFIXES)}
+
+
 class TrainEngine(GcaVmnEngine):
     """Owns the derived device state of one training step for one ``VMN`` module on one device."""
 
@@ -50,6 +63,10 @@ class TrainEngine(GcaVmnEngine):
         self.dbias: Dict[str, torch.Tensor] = {}
         self.dbn: Dict[str, tuple] = {}
         self.sync_bn = False
+        # TAM pre-training (get_VMN_models(freeze_backbone=True)): per-frame features from `backbone` (eval-mode program,
+        # running-statistics BatchNorm, stored spectral-norm u / v), tape and gradients for the decoder tail only
+        self.freeze_backbone = False
+        self.backbone: Optional[FrozenBackboneEngine] = None
         self._peer = None
         self._peer_tried = False
         self.process_group = None
@@ -141,6 +158,8 @@ class TrainEngine(GcaVmnEngine):
         one launch; u, v of the module are updated in place like the reference's ``u.data = ...``."""
         L = _cabi.lib()
         keys = [p for p, e in self.w.items() if e.get("sn")]
+        if self.freeze_backbone:          # eval-mode layers keep u / v (ops.py:38-45,76-80)
+            keys = [p for p in keys if not (p + ".").startswith(FROZEN_PREFIXES)]
         descs = (SnDesc * len(keys))()
         for i, p in enumerate(keys):
             wbar = self.named[p + ".module.weight_bar"]
@@ -878,13 +897,25 @@ class TrainEngine(GcaVmnEngine):
         N8 = (H // 8) * (W // 8)
         w2 = self.window * self.window
         dev = self.device
-        x8 = TAct(x8a, S, needs_grad=False)
-        pf = self.per_frame_t(x8)
-        feat = pf["feat"]
+        if self.freeze_backbone:
+            # VMN_model.py:99-101: feature extraction under no_grad, in eval mode; no tape entries, no statistics updates
+            if self.backbone is None:
+                raise RuntimeError("tcvom_b200: freeze_backbone step without a backbone engine")
+            # shortcut branches 0..2 feed the tail of CENTRE frames only (VMN_GCA.py:38-44): evaluated for those frames
+            # (the reference computes them for the end frames as well and drops the result); 3 and 4 end in the head
+            pfi = self.backbone.per_frame(x8a, shortcuts="head")
+            feat = TAct(pfi["feat"], S, needs_grad=False)
+            fea = []
+            for i in range(3):
+                src = self.gather_op(TAct(pfi["shortcut_src"][i], S, needs_grad=False), B, S, ncen, 1)
+                fea.append(TAct(self.backbone._shortcut(src.a, f"encoder.shortcut.{i}"), ncen, needs_grad=False))
+        else:
+            pf = self.per_frame_t(TAct(x8a, S, needs_grad=False))
+            feat = pf["feat"]
+            fea = [self.gather_op(f, B, S, ncen, 1) for f in pf["fea"][:3]]
         x = self.gather_op(feat, B, S, ncen, 1)
         xb = self.gather_op(feat, B, S, ncen, 0)
         xf = self.gather_op(feat, B, S, ncen, 2)
-        fea = [self.gather_op(f, B, S, ncen, 1) for f in pf["fea"]]
         mask = trimask.reshape(B, S, H, W)[:, 1:S - 1].contiguous()            # centre-frame unknown masks
         pred = torch.empty((B, ncen, 1, H, W), dtype=torch.float32, device=dev)
         attb = torch.empty((B, ncen, w2, N8), dtype=torch.float32, device=dev)

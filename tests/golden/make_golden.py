@@ -196,7 +196,7 @@ def damp_state(sd, damp=DAMP):
     return out
 
 
-def train_step_golden(B=2, S=5, H=64, W=64, damp=None):
+def train_step_golden(B=2, S=5, H=64, W=64, damp=None, freeze=False):
     """One reference training step (train_ddp.py:52-65 without the optimizer): FullModel_VMD in .train() mode,
     loss = L_alpha + L_comp + L_grad + 0.5 L_dt + 0.25 L_att, backward.  Stores the losses, every gradient's
     L2 norm / sum and a strided sample, and the state the forward mutates (spectral-norm u/v, BatchNorm
@@ -205,7 +205,9 @@ def train_step_golden(B=2, S=5, H=64, W=64, damp=None):
     full = load_full()
     if damp is not None:
         full = damp_state(full, damp)
-    tm = FullModel_VMD(model="vmn_gca", agg_window=7, dilate_kernel=3)
+    # freeze=True: the TAM pre-training mode (train_single_ddp.py:184-185, VMN_model.py:77-81,99-103, VMN_GCA.py:18-24):
+    # encoder + decoder.layer1 / layer2 / gca in eval mode under no_grad, the rest of the decoder trains
+    tm = FullModel_VMD(model="vmn_gca", agg_window=7, dilate_kernel=3, **(dict(freeze_backbone=True) if freeze else {}))
     tm.NET.load_state_dict(full, strict=True)
     tm.train()
     aa, ff, bb = [], [], []
@@ -220,6 +222,7 @@ def train_step_golden(B=2, S=5, H=64, W=64, damp=None):
     res = dict(a=a, fg=fg, bg=bg, losses=np.array([float(o) for o in out[:5]], np.float64),
                alphas=out[7].detach().numpy())
     names = []
+    res["nograd"] = np.array([n for n, p in tm.NET.named_parameters() if p.requires_grad and p.grad is None])
     for n, p in tm.NET.named_parameters():
         if not p.requires_grad:
             continue
@@ -230,12 +233,15 @@ def train_step_golden(B=2, S=5, H=64, W=64, damp=None):
     for k, v in tm.NET.state_dict().items():
         if k.endswith(("weight_u", "weight_v", "running_mean", "running_var", "num_batches_tracked")):
             res["st:" + k] = v.numpy().copy()
-    np.savez_compressed(os.path.join(HERE, "train_step_s5.npz" if damp is None else "train_step_s5_damped.npz"), **res)
+    fname = "train_step_s5_freeze.npz" if freeze else ("train_step_s5.npz" if damp is None else "train_step_s5_damped.npz")
+    np.savez_compressed(os.path.join(HERE, fname), **res)
     print("train step losses", res["losses"], "params", len(names), "damp", damp)
 
 
 if __name__ == "__main__":
-    if "--train-step-damped" in sys.argv:
+    if "--train-step-freeze" in sys.argv:
+        train_step_golden(damp=DAMP, freeze=True)
+    elif "--train-step-damped" in sys.argv:
         train_step_golden(damp=DAMP)
     elif "--train-step" in sys.argv:
         train_step_golden()

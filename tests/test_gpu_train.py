@@ -113,6 +113,50 @@ def test_full_training_step_matches_reference_on_the_well_conditioned_fixture(tc
     assert errs["grad_global"] < 1.5e-2 and errs["grad_median"] < 1e-2 and errs["grad_p90"] < 4e-2, errs
 
 
+def test_freeze_backbone_step_matches_reference(tc):
+    """TAM pre-training mode, get_VMN_models(freeze_backbone=True) (VMN_model.py:77-81,99-103, VMN_GCA.py:18-24): encoder and
+    decoder.layer1 / layer2 / gca in eval mode under no_grad, gradients and statistics updates for the decoder tail only.
+    Against one step of the unmodified reference in that mode (tests/golden/train_step_s5_freeze.npz): losses, alphas, the
+    tail's gradients, `grad is None` for exactly the parameters the reference leaves without a gradient, and the state
+    tensors (frozen layers: spectral-norm u / v and running statistics unchanged; tail: updated)."""
+    for attempt in range(2):
+        ok, rows, errs = tc.check_full_step(verbose=attempt == 0, bound=1.0, freeze=True)
+        print("freeze_backbone:", {k: float("%.3e" % v) for k, v in errs.items()})
+        if errs["grad_global"] < 1.5e-2 and errs["grad_p90"] < 4e-2:
+            break
+    assert errs["nograd_mismatch"] == 0, errs
+    assert errs["losses"] < 1e-4 and errs["alphas"] < 3e-4 and errs["state"] < 1e-4, errs
+    assert errs["grad_global"] < 1.5e-2 and errs["grad_median"] < 1e-2 and errs["grad_p90"] < 4e-2, errs
+
+
+def test_freeze_backbone_at_the_plugin_seam(tc):
+    """VMN.forward in train mode with freeze_backbone through autograd: only tail parameters receive gradients."""
+    import tcvom_b200
+    from helpers import fixture_sd
+    from tcvom_b200.train_engine import FROZEN_PREFIXES
+    net = tcvom_b200.get_VMN_models("vmn_gca", agg_window=7, freeze_backbone=True)
+    net.load_state_dict(fixture_sd(), strict=True)
+    net = net.cuda().train()
+    assert not net.encoder.training and not net.decoder.layer1.training and net.decoder.layer3.training
+    before = {k: v.clone() for k, v in net.state_dict().items()}
+    torch.manual_seed(0)
+    S, H, W = 3, 64, 64
+    frames = [torch.randn(1, 1, 6, H, W, device="cuda") for _ in range(S)]
+    masks = [(torch.rand(1, 1, 1, H, W, device="cuda") > 0.5).float() for _ in range(S)]
+    preds, attb, attf, small = net(frames, masks)
+    (preds[1].mean() + attb[1].mean()).backward()
+    after = net.state_dict()
+    for n, p in net.named_parameters():
+        if n.startswith(FROZEN_PREFIXES):
+            assert p.grad is None, n
+    assert any(p.grad is not None and float(p.grad.abs().sum()) > 0 for n, p in net.named_parameters()
+               if n.startswith("decoder.fam"))
+    for k, v in before.items():
+        if k.startswith(FROZEN_PREFIXES):
+            assert torch.equal(v, after[k]), k                       # no statistics / u / v update in the frozen part
+    assert any(not torch.equal(before[k], after[k]) for k in before if k.startswith("decoder.layer3") and "running_mean" in k)
+
+
 def test_train_mode_without_grad_runs_forward_only(model):
     import numpy as np
     from helpers import golden

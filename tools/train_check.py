@@ -61,8 +61,9 @@ def from_act(a):
 DAMP = 0.04      # tests/golden/make_golden.py: residual-branch BatchNorm gains of the well-conditioned fixture
 
 
-def make_net(damp=None):
-    model = tcvom_b200.FullModel_VMD(model="vmn_gca", agg_window=7, dilate_kernel=3)
+def make_net(damp=None, freeze=False):
+    model = tcvom_b200.FullModel_VMD(model="vmn_gca", agg_window=7, dilate_kernel=3,
+                                     **(dict(freeze_backbone=True) if freeze else {}))
     sd = fixture_sd()
     if damp is not None:
         sd = {k: (v * damp if (k.endswith(".bn2.weight") or k.endswith("W.1.weight")) else v) for k, v in sd.items()}
@@ -271,7 +272,7 @@ LOSS_WEIGHTS = (1.0, 1.0, 1.0, 0.5, 0.25)
 GRAD_STRIDE = 257
 
 
-def check_full_step(verbose=True, bound=1e-1, damped=False):
+def check_full_step(verbose=True, bound=1e-1, damped=False, freeze=False):
     """One native training step against one training step of the unmodified reference
     (tests/golden/train_step_s5.npz): losses, alphas, every gradient, spectral-norm u/v, BN running statistics.
 
@@ -283,8 +284,9 @@ def check_full_step(verbose=True, bound=1e-1, damped=False):
     comparison therefore sits AT its noise floor (1.4e-2 .. 2.1e-2 median measured); worst-case bound 1e-1, median
     bounded by the caller.  The per-operator checks above (3e-6 .. 2e-5) are the precise evidence."""
     from helpers import golden, key_table
-    g = golden("train_step_s5_damped.npz" if damped else "train_step_s5.npz")
-    model = make_net(DAMP if damped else None)
+    # freeze: get_VMN_models(freeze_backbone=True) on the damped fixture (tests/golden/make_golden.py --train-step-freeze)
+    g = golden("train_step_s5_freeze.npz" if freeze else ("train_step_s5_damped.npz" if damped else "train_step_s5.npz"))
+    model = make_net(DAMP if (damped or freeze) else None, freeze=freeze)
     a, fg, bg = (torch.from_numpy(g[k]).float().to(DEV) for k in ("a", "fg", "bg"))
     n0 = _cabi.launch_count()
     out = model(a, fg, bg)
@@ -298,7 +300,11 @@ def check_full_step(verbose=True, bound=1e-1, damped=False):
                 alphas=float((out[7].detach().cpu() - torch.from_numpy(g["alphas"])).abs().max()))
     named = dict(model.NET.named_parameters())
     rows = []
+    nograd = set(str(x) for x in g["nograd"]) if "nograd" in g.files else set()
+    errs["nograd_mismatch"] = float(sum((named[n].grad is None) != (n in nograd) for n in key_table()["trainable"])) if freeze else 0.0
     for n in key_table()["trainable"]:
+        if n in nograd:
+            continue
         grad = named[n].grad
         grad = grad if grad is not None else torch.zeros_like(named[n])
         f = grad.detach().flatten().cpu()
