@@ -11,7 +11,7 @@ from . import metrics  # noqa: F401  (calc_metric.py's metrics on the GPU)
 __version__ = "0.1.0"
 
 
-def install(native_wrapper: bool = True, fba_seam: bool = False):
+def install(native_wrapper: bool = True, fba_seam: bool = False, native_tam: bool = False):
     """Hooks this package into an importable reference checkout (``models`` on ``sys.path``).
 
     * ``models.VMN.get_VMN_models('vmn_gca', ...)`` -> :func:`tcvom_b200.get_VMN_models`
@@ -22,6 +22,11 @@ def install(native_wrapper: bool = True, fba_seam: bool = False):
     * with ``native_wrapper`` also ``models.model.EvalModel`` -> :class:`tcvom_b200.EvalModel`
       when it is built for ``vmn_gca`` / ``vmn_fba`` / ``vmn_dim`` / ``vmn_index`` (fused preprocess / postprocess kernels, CUDA-graph
       replay; for ``vmn_fba`` also the trimap distance transforms on the GPU instead of ``cv2``).
+
+    * ``native_tam=True`` also replaces the reference's ``FeatureAggregationModule`` class (VMN_model.py:9-68, bound by
+      name in VMN_DIM.py:4, VMN_Index.py:5, VMN_FBA.py:3, VMN_GCA.py:6) by :class:`tcvom_b200.FeatureAggregationModule`:
+      the reference's OWN ``vmn_dim`` / ``vmn_index`` / ``vmn_fba`` networks then run -- and TRAIN, through autograd --
+      with the native TAM operator (same parameter names, so checkpoints load unchanged).
 
     Call it before the reference script imports ``models.model``."""
     import importlib
@@ -34,6 +39,15 @@ def install(native_wrapper: bool = True, fba_seam: bool = False):
             sys.modules.setdefault(m, types.ModuleType(m))
     ref_vmn = importlib.import_module("models.VMN")
     ref_model = importlib.import_module("models.model")
+    if native_tam:
+        from .model import FeatureAggregationModule as _NativeTAM
+        for name in ("VMN_model", "VMN_DIM", "VMN_Index", "VMN_FBA", "VMN_GCA"):
+            mod = importlib.import_module("models.VMN." + name)
+            cur = getattr(mod, "FeatureAggregationModule", None)
+            if cur is not None and cur is not _NativeTAM:
+                if not hasattr(_NativeTAM, "_reference"):
+                    _NativeTAM._reference = cur
+                mod.FeatureAggregationModule = _NativeTAM
     if getattr(ref_vmn.get_VMN_models, "_tcvom_b200", False):
         return
     orig_factory = ref_vmn.get_VMN_models

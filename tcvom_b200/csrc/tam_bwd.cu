@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(256) tam_attend_bwd_kernel(
   for (int c = 0; c < CPL; ++c) dqv[c] = 0.f;
   if (m) {
     float qv[CPL], go[CPL];
-    if (CPL == 4) { load4(q + base, plane, qv); load4(dout + base, plane, go); }
+    if (CPL == 1) { qv[0] = load1(q + base, plane); go[0] = load1(dout + base, plane); }
+    else if (CPL == 4) { load4(q + base, plane, qv); load4(dout + base, plane, go); }
     else { load8(q + base, plane, qv); load8(dout + base, plane, go); }
     const float inv_sqrt_c = 1.0f / sqrtf((float)C);
 #pragma unroll 1
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(256) tam_attend_bwd_kernel(
         if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
           float kv[CPL];
           const __nv_bfloat16* kp = k + ((long long)b * N + (long long)yy * w + xx) * C + lane * CPL;
-          if (CPL == 4) load4(kp, plane, kv); else load8(kp, plane, kv);
+          if (CPL == 1) kv[0] = load1(kp, plane); else if (CPL == 4) load4(kp, plane, kv); else load8(kp, plane, kv);
 #pragma unroll
           for (int c = 0; c < CPL; ++c) { d = fmaf(qv[c], kv[c], d); g = fmaf(go[c], kv[c], g); }
           d = warp_sum(d);
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(256) tam_attend_bwd_kernel(
         if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
           float kv[CPL];
           const long long ko = ((long long)b * N + (long long)yy * w + xx) * C + lane * CPL;
-          if (CPL == 4) load4(k + ko, plane, kv); else load8(k + ko, plane, kv);
+          if (CPL == 1) kv[0] = load1(k + ko, plane); else if (CPL == 4) load4(k + ko, plane, kv); else load8(k + ko, plane, kv);
 #pragma unroll
           for (int c = 0; c < CPL; ++c) {
             dqv[c] = fmaf(dl, kv[c], dqv[c]);
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(256) tam_attend_bwd_kernel(
       }
     }
   }
-  if (CPL == 4) store4(dq + base, plane, dqv); else store8(dq + base, plane, dqv);
+  if (CPL == 1) store1(dq + base, plane, dqv[0]); else if (CPL == 4) store4(dq + base, plane, dqv); else store8(dq + base, plane, dqv);
 }
 
 }  // namespace tcv
@@ -104,7 +105,7 @@ extern "C" int tcv_tam_attend_bwd(const void* q, const void* kb, const void* kf,
                                   float* dkf, tcv_stream_t stream) {
   TCV_REQUIRE(q && kb && kf && mask && dout && dq && dkb && dkf, "tam_attend_bwd: null pointer");
   TCV_REQUIRE(window >= 1 && window % 2 == 1 && window * window <= 64, "tam_attend_bwd: window must be odd and <= 7");
-  TCV_REQUIRE(c == 128 || c == 256, "tam_attend_bwd: channels must be 128 or 256");
+  TCV_REQUIRE(c == 32 || c == 128 || c == 256, "tam_attend_bwd: channels must be 32, 128 or 256");
   const long long elems = (long long)batch * h * w * c;
   TCV_CUDA(cudaMemsetAsync(dkb, 0, sizeof(float) * elems, S(stream)));
   TCV_CUDA(cudaMemsetAsync(dkf, 0, sizeof(float) * elems, S(stream)));
@@ -115,7 +116,10 @@ extern "C" int tcv_tam_attend_bwd(const void* q, const void* kb, const void* kf,
   auto KF = reinterpret_cast<const __nv_bfloat16*>(kf);
   auto DO = reinterpret_cast<const __nv_bfloat16*>(dout);
   auto DQ = reinterpret_cast<__nv_bfloat16*>(dq);
-  if (c == 128)
+  if (c == 32)
+    tam_attend_bwd_kernel<1><<<grid, 256, 0, S(stream)>>>(Q, KB, KF, mask, mask_stride, mh, mw, batch, h, w, window,
+                                                          DO, dattb, dattf, DQ, dkb, dkf);
+  else if (c == 128)
     tam_attend_bwd_kernel<4><<<grid, 256, 0, S(stream)>>>(Q, KB, KF, mask, mask_stride, mh, mw, batch, h, w, window,
                                                           DO, dattb, dattf, DQ, dkb, dkf);
   else

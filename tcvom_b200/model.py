@@ -28,7 +28,7 @@ from .fba_engine import FbaVmnEngine
 from .index_engine import IndexVmnEngine
 from .index_modules import IndexDecoderParams, IndexEncoderParams
 from .fba_modules import FBADecoderParams, FBAEncoderParams
-from .train_engine import FROZEN_PREFIXES, FrozenBackboneEngine, TrainEngine
+from .train_engine import FROZEN_PREFIXES, FrozenBackboneEngine, TAct, TrainEngine
 from .modules import GCADecoderParams, GCAEncoderParams, GuidedCxtAttenParams, TAMParams
 
 
@@ -153,6 +153,118 @@ class _VMNTrainFn(torch.autograd.Function):
         return (None,) * 7 + tuple(eng.collect_grads(ctx.names))
 
 
+def _nchw_to_act(t: torch.Tensor) -> Act:
+    n, c, h, w = t.shape
+    a = Act.empty(n, h, w, c, t.device)
+    _cabi.check(_cabi.lib().tcv_nchw_to_split(t.detach().contiguous().float().data_ptr(), n, c, h, w, c, a.ptr, 0,
+                                              _stream(t.device)), "nchw_to_split")
+    return a
+
+
+def _act_to_nchw(a: Optional[Act], like: torch.Tensor) -> torch.Tensor:
+    if a is None:
+        return torch.zeros_like(like, dtype=torch.float32)
+    y = torch.empty((a.n, a.c, a.h, a.w), dtype=torch.float32, device=like.device)
+    _cabi.check(_cabi.lib().tcv_split_to_nchw(a.ptr, a.n, a.c, a.h, a.w, a.c, 0, y.data_ptr(), _stream(like.device)),
+                "split_to_nchw")
+    return y
+
+
+def _op_param_names(mod: nn.Module) -> List[str]:
+    return [n for n, t in named_tensors(mod).items() if isinstance(t, nn.Parameter) and t.requires_grad]
+
+
+def _check_op_tape(ctx):
+    eng = ctx.eng
+    if eng is None or not eng.tape or eng.step_id != ctx.step_id:
+        raise RuntimeError("tcvom_b200: this operator call was already back-propagated, or the same module ran another "
+                           "train-mode forward before backward() (one tape per module: forward, backward, forward, ...)")
+    return eng
+
+
+class _NoCtx:
+    """Stand-in for the autograd context when an operator's train-mode forward runs under no_grad."""
+
+    def mark_non_differentiable(self, *a):
+        pass
+
+
+class _TamTrainFn(torch.autograd.Function):
+    """FeatureAggregationModule.forward in train mode (VMN_model.py:18-68) on the training engine's TAM operator: the
+    three 3x3 convolutions and the windowed attention forward, their data / weight / bias gradients and the gradient of
+    the returned attention logits backward."""
+
+    @staticmethod
+    def forward(ctx, mod, x, b, f, mask, *params):
+        eng = _train_engine_for(mod, int(mod.window))
+        B, Cc, H, W = x.shape
+        w2 = int(mod.window) ** 2
+        with eng.stream_scope():
+            eng.begin_operator_step()
+            ts = [TAct(_nchw_to_act(t), 1) for t in (x, b, f)]
+            m = mask.detach().contiguous().float()
+            mh, mw = m.shape[-2:]
+            attb = torch.empty((B, w2, H * W), dtype=torch.float32, device=x.device)
+            attf = torch.empty_like(attb)
+            sm = torch.empty((B, 1, H, W), dtype=torch.uint8, device=x.device)
+            ctx.datt = {}
+            out = eng.tam_op("", ts[0], ts[1], ts[2], m, mh, mw, attb, attf, sm, ctx.datt)
+            y = _act_to_nchw(out.a, x)
+        ctx.eng, ctx.ts, ctx.out, ctx.mask = eng, ts, out, m
+        ctx.step_id, ctx.names, ctx.like = eng.step_id, _op_param_names(mod), (x, b, f)
+        smb = sm.bool()
+        ctx.mark_non_differentiable(smb)
+        return y, attb, attf, smb
+
+    @staticmethod
+    def backward(ctx, dy, dattb, dattf, _):
+        eng = _check_op_tape(ctx)
+        with eng.stream_scope():
+            ctx.out.g = _nchw_to_act(dy if dy is not None else torch.zeros_like(ctx.like[0]))
+            ctx.out.g_owned = True
+            ctx.datt["b"] = dattb.contiguous().float() if dattb is not None else None
+            ctx.datt["f"] = dattf.contiguous().float() if dattf is not None else None
+            eng.run_tape()
+            gin = [_act_to_nchw(t.g, like) for t, like in zip(ctx.ts, ctx.like)]
+            pg = eng.collect_grads(ctx.names)
+        ctx.eng = None
+        return (None, gin[0], gin[1], gin[2], None) + tuple(pg)
+
+
+class _GcaTrainFn(torch.autograd.Function):
+    """GuidedCxtAtten.forward in train mode (GCA/ops.py:106-229): guidance 1x1 conv, guided attention, W = 1x1 conv +
+    batch-statistics BatchNorm (running statistics updated), residual; gradients for both inputs and all parameters."""
+
+    @staticmethod
+    def forward(ctx, mod, f, alpha, unknown, *params):
+        eng = _train_engine_for(mod, 1)
+        B, Cc, H, W = alpha.shape
+        with eng.stream_scope():
+            eng.begin_operator_step()
+            tf, ta = TAct(_nchw_to_act(f), 1), TAct(_nchw_to_act(alpha), 1)
+            unk = unknown.detach().contiguous().float().reshape(B, H, W)
+            out = eng.gca_op("", tf, ta, unk)
+            eng.end_operator_forward()
+            y = _act_to_nchw(out.a, alpha)
+            scales = eng.last_gca_scales.clone()
+        ctx.eng, ctx.ts, ctx.out, ctx.unk = eng, (tf, ta), out, unk
+        ctx.step_id, ctx.names, ctx.like = eng.step_id, _op_param_names(mod), (f, alpha)
+        ctx.mark_non_differentiable(scales)
+        return y, scales
+
+    @staticmethod
+    def backward(ctx, dy, _):
+        eng = _check_op_tape(ctx)
+        with eng.stream_scope():
+            ctx.out.g = _nchw_to_act(dy if dy is not None else torch.zeros_like(ctx.like[1]))
+            ctx.out.g_owned = True
+            eng.run_tape()
+            gin = [_act_to_nchw(t.g, like) for t, like in zip(ctx.ts, ctx.like)]
+            pg = eng.collect_grads(ctx.names)
+        ctx.eng = None
+        return (None, gin[0], gin[1], None) + tuple(pg)
+
+
 class _OpEngineMixin:
     """Gives a standalone operator module (TAM / GCA) its own small engine over its parameters."""
 
@@ -168,8 +280,12 @@ class FeatureAggregationModule(TAMParams, _OpEngineMixin):
             _require_cuda(t, nme)
         B, Cc, H, W = x.shape
         assert b.shape == x.shape and f.shape == x.shape          # VMN_model.py:26
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("tcvom_b200: TAM backward kernels are not built yet (inference only)")
+        if torch.is_grad_enabled() and (any(t.requires_grad for t in (x, b, f)) or
+                                        any(p.requires_grad for p in self.parameters())):
+            # autograd-connected call (the module has no train/eval difference, VMN_model.py:18-68): the training
+            # engine's TAM operator -- lets the reference's own VMN_DIM / VMN_Index / VMN_FBA train with the native TAM
+            named = named_tensors(self)
+            return _TamTrainFn.apply(self, x, b, f, mask, *[named[n] for n in _op_param_names(self)])
         eng = self._op_engine(self.window)
         L = _cabi.lib()
         st = _stream(x.device)
@@ -200,10 +316,20 @@ class GuidedCxtAtten(GuidedCxtAttenParams, _OpEngineMixin):
         _require_cuda(f, "f"); _require_cuda(alpha, "alpha")
         if unknown is None:
             raise NotImplementedError("tcvom_b200: GuidedCxtAtten without an unknown map is not on the VMN path")
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("tcvom_b200: GCA backward kernels are not built yet (inference only)")
         B, Cc, H, W = alpha.shape
         assert unknown.shape[2] == H and unknown.shape[3] == W, "mask should have same size as f at dim 2,3"
+        if self.training:
+            # batch-statistics BatchNorm in W (ops.py:97-101): the training engine's GCA operator, with or without autograd
+            named = named_tensors(self)
+            if torch.is_grad_enabled():
+                y, scales = _GcaTrainFn.apply(self, f, alpha, unknown, *[named[n] for n in _op_param_names(self)])
+            else:
+                y, scales = _GcaTrainFn.forward(_NoCtx(), self, f, alpha, unknown)
+                _train_engine_for(self, 1).tape = []
+            return y, (None, scales)
+        if torch.is_grad_enabled() and (f.requires_grad or alpha.requires_grad):
+            raise NotImplementedError("tcvom_b200: gradients through the eval-mode GCA operator (running-statistics "
+                                      "BatchNorm) are not built; call .train() or wrap the call in torch.no_grad()")
         eng = self._op_engine()
         L = _cabi.lib()
         st = _stream(f.device)

@@ -881,6 +881,25 @@ class TrainEngine(GcaVmnEngine):
         feat = self.gca_op("decoder.gca", im_fea, d, unknown)
         return dict(fea=fea, feat=feat)
 
+    def begin_operator_step(self) -> None:
+        """Fresh tape and gradient accumulators for ONE standalone operator call (the TAM / GCA drop-in modules in train
+        mode, model._TamTrainFn / _GcaTrainFn); the whole-network step does the same at the top of `_train_forward`."""
+        self.tape = []
+        self.step_id = getattr(self, "step_id", 0) + 1
+        self.dw.clear(); self.dbias.clear(); self.dbn.clear()
+        self._arena_begin()
+        self._nbt = []
+
+    def end_operator_forward(self) -> None:
+        if self._nbt:
+            torch._foreach_add_([t_ for t_, _ in self._nbt], [int(g_) for _, g_ in self._nbt])
+            self._nbt = []
+
+    def run_tape(self) -> None:
+        for fn in reversed(self.tape):
+            fn()
+        self.tape = []
+
     def train_forward(self, x8a: Act, trimask: torch.Tensor, B: int, S: int, H: int, W: int) -> dict:
         """VMN.forward in train mode on preprocessed input; records the tape.  trimask fp32 [B,S,1,H,W]."""
         with self.stream_scope():

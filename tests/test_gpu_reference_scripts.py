@@ -184,3 +184,24 @@ def test_train_ddp_script_runs_on_the_native_package(tmp_path, world):
     assert list(saved.keys()) == list(sd.keys())
     moved = max(float((saved[k].float() - sd[k].float()).abs().max()) for k in sd if k.endswith("weight_bar"))
     assert 0 < moved < 1e-2 and all(torch.isfinite(v.float()).all() for v in saved.values())
+
+
+@pytest.mark.parametrize("arch", ["vmn_dim", "vmn_index"])
+def test_reference_networks_train_with_the_native_tam_operator(arch):
+    """install(native_tam=True): the reference's OWN vmn_dim / vmn_index network (unmodified modules from baseline/_ref)
+    instantiates tcvom_b200.FeatureAggregationModule and trains through it (tools/ref_tam_train_check.py: one train-mode
+    forward + backward with the reference TAM and with the native one, same weights / inputs / dropout seed).  The TAM
+    logits agree to 1e-5; predictions and gradients are compared against the noise floor the same script measures (the
+    reference TAM with its activations rounded to the 16 mantissa bits the native operator stores: a random-weight
+    network with batch-statistics BatchNorm amplifies that rounding by orders of magnitude)."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_tam_train_check.py"), arch], cwd=ROOT,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    print(out)
+    assert out["small_equal"] and out["attb"] < 1e-4, out
+    assert out["pred"] <= max(1e-4, 3 * out["floor"]["pred"]), out
+    assert out["grad_global"] <= max(1e-3, 3 * out["floor"]["grad_global"]), out
+    for n in ("decoder.fam.query_conv.weight", "decoder.fam.key_conv.weight"):
+        assert out["tam_grads"][n] < 1e-2, out
