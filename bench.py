@@ -244,7 +244,7 @@ LOSS_WEIGHTS = (1.0, 1.0, 1.0, 0.5, 0.25)   # train_ddp.py:61
 TRAIN_1080_GFLOP_PER_SAMPLE = 20000.0   # 1088x1920, S=5, fwd 6 661 GFLOP, fwd+bwd ~3x
 
 
-def run_train_section(args, rank, world, dev, barrier, max_over_ranks, shape=None):
+def run_train_section(args, rank, world, dev, barrier, max_over_ranks, shape=None, freeze=False):
     """Secondary measurement: the native training step (FullModel_VMD fwd + losses + bwd + Adam, train_ddp.py:52-65)
     at BASELINE.json configs[2]'s shape, batch 4 per GPU; with N > 1 under SyncBatchNorm + DistributedDataParallel
     over NCCL exactly like train_ddp.py:270-280 (configs[3]'s recipe).  Reported next to, not instead of, the
@@ -257,8 +257,9 @@ def run_train_section(args, rank, world, dev, barrier, max_over_ranks, shape=Non
     TRAIN_B, TRAIN_S, TH_, TW_, steps, gflop, label = shape or (4, 5, 512, 512, 5, TRAIN_GFLOP_PER_SAMPLE, "configs[2]")
     torch.cuda.reset_peak_memory_stats(dev)
     # TCV_FREEZE_BACKBONE=1 (tools/train_time.py only): the TAM pre-training mode, train_single_ddp.py:184-185
-    freeze = dict(freeze_backbone=True) if os.environ.get("TCV_FREEZE_BACKBONE") == "1" else {}
-    model = tcvom_b200.FullModel_VMD(model="vmn_gca", agg_window=7, dilate_kernel=None, **freeze)
+    freeze = freeze or os.environ.get("TCV_FREEZE_BACKBONE") == "1"
+    model = tcvom_b200.FullModel_VMD(model="vmn_gca", agg_window=7, dilate_kernel=None,
+                                     **(dict(freeze_backbone=True) if freeze else {}))
     model.NET.load_state_dict(fixture_sd(), strict=True)
     if world > 1:
         model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model).to(dev)
@@ -301,11 +302,14 @@ def run_train_section(args, rank, world, dev, barrier, max_over_ranks, shape=Non
     ms = max_over_ranks(e0.elapsed_time(e1)) / steps
     samples = world * TRAIN_B
     n_params = sum(p.numel() for p in model.parameters() if p.requires_grad)
-    out = dict(workload=f"GCA+TAM train step (L_im+L_tc+L_af fwd+bwd+Adam) {TH_}x{TW_}, batch {TRAIN_B}/GPU, "
+    what = ("GCA+TAM pre-training step, freeze_backbone=True (train_single_ddp.py:184-185: frozen encoder + decoder head "
+            "in eval mode, TAM + decoder tail fwd+bwd+Adam)" if freeze else
+            "GCA+TAM train step (L_im+L_tc+L_af fwd+bwd+Adam)")
+    out = dict(workload=f"{what} {TH_}x{TW_}, batch {TRAIN_B}/GPU, "
                          f"S={TRAIN_S} ({label}; N>1: SyncBatchNorm + DDP over NCCL, train_ddp.py:270-280)",
                 ms_per_step=ms, samples_per_s=samples / (ms / 1e3),
                 centre_windows_per_s=samples * (TRAIN_S - 2) / (ms / 1e3),
-                algorithmic_tflops=samples * gflop / (ms / 1e3) / 1e3, steps=steps, warmup=2,
+                algorithmic_tflops=(samples * gflop / (ms / 1e3) / 1e3) if gflop else None, steps=steps, warmup=2,
                 gpu_launches_per_step=(_cabi.launch_count() - n0) // steps, loss=float(loss.detach()),
                 grad_allreduce_mb=(4 * n_params / 1e6) if world > 1 else 0.0, sync_batchnorm=world > 1,
                 peak_mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30)
@@ -693,7 +697,7 @@ def run_native(args, rank, world, local_rank):
                     roof["traffic"] = t["dram_bytes_per_launch"]       # ncu dram__bytes_read+write, per launch
                     roof["algorithmic_bytes_per_launch"] = top["bytes"] / top["n"]
 
-    train = train_1080 = None
+    train = train_1080 = pretrain_1080 = None
     if not args.no_train:
         model.NET.engine().plans.clear()           # release the forward plan's activations
         del plan
@@ -710,6 +714,12 @@ def run_native(args, rank, world, local_rank):
             if world > 1:
                 raise                                          # a rank that fails alone would dead-lock the others
             train_1080 = dict(error=f"{type(e).__name__}: {e}")
+        if world == 1:
+            try:
+                pretrain_1080 = run_train_section(args, rank, world, dev, barrier, max_over_ranks, freeze=True,
+                                                  shape=(1, 5, H, W, 3, None, "configs[3] shape"))
+            except Exception as e:                             # noqa: BLE001 - reported in the JSON line
+                pretrain_1080 = dict(error=f"{type(e).__name__}: {e}")
 
     fba = None
     if not args.no_fba:
@@ -756,7 +766,7 @@ def run_native(args, rank, world, local_rank):
                          h2d_bytes_per_step=imgs_u8.numel() + tris_u8.numel(), input_dtype="uint8",
                          d2h_bytes_per_step=out_h.numel() * 4),
                 gpu_launches=launches, roofline=roof, cpu_baseline=cpu, gpu_eager_baseline=eager, train_step=train,
-                train_step_1080p=train_1080, fba_forward=fba, dim_forward=dim, index_forward=index)
+                train_step_1080p=train_1080, pretrain_step_1080p=pretrain_1080, fba_forward=fba, dim_forward=dim, index_forward=index)
     print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
