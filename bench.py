@@ -644,6 +644,7 @@ def run_native(args, rank, world, local_rank):
         # the read-back of its matte are inside the timed region (step 0's upload is ordered after e0).
         main = torch.cuda.current_stream(dev)
         up = torch.cuda.Stream(dev)
+        down = torch.cuda.Stream(dev)
 
         def upload():
             with torch.cuda.stream(up):
@@ -659,10 +660,16 @@ def run_native(args, rank, world, local_rank):
                 (im_d, tr_d), ev = nxt
                 main.wait_event(ev)
                 im_d.record_stream(main); tr_d.record_stream(main)
-                a = model(im_d, tr_d)
+                a = model(im_d, tr_d)                # a fresh tensor per call (the plan's output is cloned)
                 if i + 1 < n:
                     nxt = upload()
-                out_h.copy_(a[:, S // 2:S // 2 + 1], non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(main)
+                with torch.cuda.stream(down):        # matte read-back behind the next window's compute
+                    down.wait_event(done)
+                    out_h.copy_(a[:, S // 2:S // 2 + 1], non_blocking=True)
+                    a.record_stream(down)
+            main.wait_stream(down)                   # the last read-back ends before e1
 
         e2e_loop(3)
         barrier()
@@ -784,8 +791,8 @@ def run_native(args, rank, world, local_rank):
                 clocks=clocks,
                 e2e=dict(value=e2e_value, unit=UNIT, ms_per_step=ms_e2e / args.steps,
                          h2d_bytes_per_step=imgs_u8.numel() + tris_u8.numel(), input_dtype="uint8",
-                         upload="next window's frames copied on a side stream while the current one computes; every copy "
-                                "inside the timed region",
+                         upload="next window's frames copied on a side stream while the current one computes, the matte read "
+                                "back on another; every copy inside the timed region",
                          d2h_bytes_per_step=out_h.numel() * 4),
                 gpu_launches=launches, roofline=roof, cpu_baseline=cpu, gpu_eager_baseline=eager, train_step=train,
                 train_step_1080p=train_1080, pretrain_step_1080p=pretrain_1080, fba_forward=fba, dim_forward=dim, index_forward=index)

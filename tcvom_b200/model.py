@@ -860,9 +860,9 @@ class FullModel_VMD(nn.Module):
     forward(a [B,S,1,H,W] 0..255, fg, bg [B,S,3,H,W] BGR 0..255) -> the reference's 12-list
     [L_alpha, L_comp, L_grad, L_dt, L_att, scaled_imgs, tris_vis, alphas, comps, scaled_gts, Fs, Bs].
 
-    Built for the inference use of the wrapper (pred_vmn.py:107-116: ``net.eval()`` + ``no_grad``): the loss
-    values are computed by fused forward kernels; there is no backward yet, so a grad-enabled / train-mode
-    call raises instead of falling back to PyTorch."""
+    Eval mode (pred_vmn.py:107-116: ``net.eval()`` + ``no_grad``): one recorded plan, loss values from fused forward
+    kernels.  Train mode (train_ddp.py:52-65): the native training step behind ONE autograd node (`_TrainStepFn`), for
+    ``vmn_gca`` with or without ``freeze_backbone``; other base networks raise instead of falling back to PyTorch."""
     TAM_OS = 8
     FBA_L_ATT_MULTIPLIER = 1
     ARCH_DICT = {'gca': None, 'dim': None, 'fba': None, 'index': None}     # pred_vmn.py:29 lists the keys
