@@ -137,6 +137,48 @@ def _synthetic_dataset_module():
     return m
 
 
+def _synthetic_dim_dataset_module():
+    import torch
+    from torch.utils import data
+    from tcvom_b200 import synthetic
+
+    def item(H, W, idx):
+        a, fg, bg = synthetic.make_train_batch(1, 3, H, W, seed=51 + 7 * idx)
+        f = lambda t: torch.from_numpy(t[0]).float()
+        return f(a), f(fg), f(bg)
+
+    class DIMPretrainDataset(data.Dataset):
+        """Synthetic stand-in with the constructor and item layout of dataset/DIM.py (pretrain_ddp.py:190-196,52-53):
+        3-frame samples (a [3,1,H,W], fg, bg [3,3,H,W])."""
+
+        def __init__(self, data_root, image_shape, min_shape=None, isTrain=True, plus1=False, **kw):
+            self.image_shape = tuple(image_shape)
+            self.n = int(os.environ.get("TCVOM_STUB_DATASET_LEN", "4"))
+
+        def __len__(self):
+            return self.n
+
+        def __getitem__(self, idx):
+            return item(*self.image_shape, idx)
+
+    class DIMEvalDataset(data.Dataset):
+        """pretrain_ddp.py:207-213,112: items are 5-tuples (a, fg, bg, name, size)."""
+
+        def __init__(self, data_root, min_shape=None, plus1=False, val_mode="origin", **kw):
+            self.n = int(os.environ.get("TCVOM_STUB_EVAL_LEN", "1"))
+
+        def __len__(self):
+            return self.n
+
+        def __getitem__(self, idx):
+            a, fg, bg = item(64, 64, 100 + idx)
+            return a, fg, bg, f"synthetic/{idx:04d}", torch.tensor([64, 64])
+
+    m = types.ModuleType("dataset.DIM")
+    m.DIMPretrainDataset, m.DIMEvalDataset = DIMPretrainDataset, DIMEvalDataset
+    return m
+
+
 import contextlib
 
 
@@ -182,6 +224,7 @@ def activate(cpu: bool = False, synthetic_dataset: bool = False) -> str:
         pkg.__path__ = []
         sys.modules["dataset"] = pkg
         sys.modules["dataset.VMD"] = pkg.VMD = _synthetic_dataset_module()
+        sys.modules["dataset.DIM"] = pkg.DIM = _synthetic_dim_dataset_module()
     if cpu:
         import torch
         torch.cuda.current_device = lambda: torch.device("cpu")

@@ -205,3 +205,42 @@ def test_reference_networks_train_with_the_native_tam_operator(arch):
     assert out["grad_global"] <= max(1e-3, 3 * out["floor"]["grad_global"]), out
     for n in ("decoder.fam.query_conv.weight", "decoder.fam.key_conv.weight"):
         assert out["tam_grads"][n] < 1e-2, out
+
+
+def test_pretrain_ddp_script_runs_on_the_native_package(tmp_path):
+    """pretrain_ddp.py (the TAM pre-training script: FullModel(..., freeze_backbone=True), cfgs/pretrain_vmn_gca.yaml),
+    unmodified, one process under its --local_rank launcher: the checkpoint it loads has no TAM keys, so the script puts
+    exactly the missing (TAM) parameters into the optimizer (pretrain_ddp.py:246-249); the native VMN runs the frozen
+    backbone on the inference kernels and trains the tail.  After one epoch: finite losses, a checkpoint with every key,
+    backbone tensors bit-identical to the loaded ones (no gradient, no statistics update)."""
+    sd = fixture_sd()
+    backbone_only = {k: v for k, v in sd.items() if not k.startswith("decoder.fam.")}
+    ckpt = str(tmp_path / "backbone.pth")
+    torch.save(backbone_only, ckpt)
+    cfg = tmp_path / "pretrain_tiny.yaml"
+    cfg.write_text(
+        "MODEL: 'vmn_gca'\nAGG_WINDOW: 7\n"
+        "SYSTEM:\n  NUM_WORKERS: 0\n  RANDOM_SEED: 777\n  OUTDIR: '%s'\n"
+        "DATASET:\n  PATH: ''\n"
+        "TRAIN:\n  LOAD_CKPT: '%s'\n  FREEZE_BACKBONE: True\n  BATCH_SIZE_PER_GPU: 2\n  VAL_BATCH_SIZE_PER_GPU: 1\n"
+        "  BASE_LR: 1e-3\n  LR_STRATEGY: 'poly'\n  TRAIN_INPUT_SIZE: (64, 64)\n  TOTAL_STEPS: 1\n"
+        "  PRINT_FREQ: 1\n  IMAGE_FREQ: 500\n" % (tmp_path / "train_log", ckpt))
+    e = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29671", RANK="0", WORLD_SIZE="1", LOCAL_RANK="0",
+             TCVOM_STUB_DATASET_LEN="4")
+    r = subprocess.run([sys.executable, RUNNER, "--native", "--synthetic-dataset", "pretrain_ddp.py", "--cfg", str(cfg),
+                        "--local_rank", "0"], cwd=ROOT, env=e, capture_output=True, text=True, timeout=900)
+    log = r.stdout + r.stderr
+    assert r.returncode == 0, log[-4000:]
+    lines = [l for l in log.splitlines() if "Iter:[" in l]
+    assert len(lines) == 2, log[-3000:]
+    losses = [float(l.split("Current: Loss: ")[1].split(",")[0]) for l in lines]
+    assert all(np.isfinite(losses)) and all(l > 0 for l in losses), lines
+    optimised = [l.split("=> ")[1].split(",")[0] for l in log.splitlines() if "\t=> " in l and "size:" in l]
+    assert optimised and all(k.startswith("module.NET.decoder.fam.") for k in optimised), optimised
+    saved = torch.load(str(tmp_path / "train_log" / "pretrain_tiny" / "checkpoint_1.pth.tar"), map_location="cpu")
+    assert set(saved.keys()) == set(sd.keys())
+    from tcvom_b200.train_engine import FROZEN_PREFIXES
+    for k, v in saved.items():
+        if k.startswith(FROZEN_PREFIXES):
+            assert torch.equal(v, sd[k]), k
+    assert all(torch.isfinite(v.float()).all() for v in saved.values())
