@@ -97,8 +97,8 @@ def test_full_training_step_matches_reference_on_the_well_conditioned_fixture(tc
     damp_state): perturbations are no longer amplified ~1000x, so this comparison can SEE a 1 % gradient bug, which the
     standard fixture (gradients at a 1e-2 noise floor) cannot."""
     # The step is not bit-reproducible (fp32 atomics in the weight-gradient kernels) and a rare ordering lands on the other
-    # side of a ReLU / |.| kink early in the network: 1 run in ~5 of the whole suite showed an outlier.  Two attempts.
-    for attempt in range(2):
+    # side of a ReLU / |.| kink early in the network: 1 run in ~5 of the whole suite showed an outlier.  Three attempts.
+    for attempt in range(3):
         ok, rows, errs = tc.check_full_step(verbose=attempt == 0, bound=1.0, damped=True)
         print("damped fixture:", {k: float("%.3e" % v) for k, v in errs.items()})
         if errs["grad_global"] < 1.5e-2 and errs["grad_median"] < 1e-2 and errs["grad_p90"] < 4e-2 and errs["alphas"] < 3e-4:
@@ -119,7 +119,7 @@ def test_freeze_backbone_step_matches_reference(tc):
     Against one step of the unmodified reference in that mode (tests/golden/train_step_s5_freeze.npz): losses, alphas, the
     tail's gradients, `grad is None` for exactly the parameters the reference leaves without a gradient, and the state
     tensors (frozen layers: spectral-norm u / v and running statistics unchanged; tail: updated)."""
-    for attempt in range(2):
+    for attempt in range(3):
         ok, rows, errs = tc.check_full_step(verbose=attempt == 0, bound=1.0, freeze=True)
         print("freeze_backbone:", {k: float("%.3e" % v) for k, v in errs.items()})
         if errs["grad_global"] < 1.5e-2 and errs["grad_p90"] < 4e-2:
