@@ -244,3 +244,57 @@ def test_pretrain_ddp_script_runs_on_the_native_package(tmp_path):
         if k.startswith(FROZEN_PREFIXES):
             assert torch.equal(v, sd[k]), k
     assert all(torch.isfinite(v.float()).all() for v in saved.values())
+
+
+def test_calc_metric_script_with_the_gpu_metric_operator(tmp_path):
+    """calc_metric.py's own main() (folder walk, per-video / overall averages, metric.json) with its per-frame function bound
+    to tcvom_b200.metrics.calc_metric (tools/run_calc_metric.py), against the untouched script on the same synthetic
+    dataset folder: three videos x three frames, 16-bit flow PNGs with invalid pixels.  (The reference's video scan appends
+    a video when the NEXT one starts, calc_metric.py:140-153, so the last video of a dataset is never evaluated: both arms
+    report the first two.)"""
+    import json
+    import cv2
+    rng = np.random.default_rng(3)
+    H, W = 96, 128
+    pred, data = tmp_path / "pred", tmp_path / "data"
+    names = []
+    for v in ("vidA", "vidB", "vidC"):
+        for d in (pred / v, data / "FG_done" / v, data / "flow_png" / v):
+            os.makedirs(d)
+        ys, xs = np.mgrid[0:H, 0:W]
+        for t in range(3):
+            r = np.hypot((xs - W * (0.45 + 0.03 * t)) / (0.3 * W), (ys - H * 0.5) / (0.35 * H))
+            g = np.clip((1.15 - r) * 4.0, 0, 1)
+            a = np.clip(g + rng.normal(0, 0.06, g.shape) * ((g > 0) & (g < 1)), 0, 1)
+            g8, a8 = np.uint8(np.round(g * 255)), np.uint8(np.round(a * 255))
+            tri = np.where(g8 == 0, 0, np.where(g8 == 255, 255, 128)).astype(np.uint8)
+            fg = np.zeros((H, W, 4), np.uint8)
+            fg[..., 3] = g8
+            cv2.imwrite(str(pred / v / f"{t:05d}_pred.png"), a8)
+            cv2.imwrite(str(pred / v / f"{t:05d}_tri.png"), tri)
+            cv2.imwrite(str(data / "FG_done" / v / f"{t:05d}.png"), fg)
+            names.append(f"{v}/{t:05d}.png")
+            if t < 2:
+                fl = np.int16(np.round((rng.normal(0, 1.5, (H, W, 2)) + [0.03 * W, 0]) * 100))
+                png = np.zeros((H, W, 3), np.uint16)
+                png[..., :2] = fl.view(np.uint16)
+                png[..., 2] = rng.random((H, W)) > 0.15
+                cv2.imwrite(str(data / "flow_png" / v / f"flow_{t:05d}_{t + 1:05d}.png"), png)
+    (data / "frame_corr.json").write_text(json.dumps({n: {} for n in names}))
+    tool = os.path.join(ROOT, "tools", "run_calc_metric.py")
+    out = {}
+    for arm, flags in (("reference", ["--reference"]), ("native", [])):
+        o = str(tmp_path / f"{arm}.json")
+        r = subprocess.run([sys.executable, tool] + flags + ["--pred", str(pred), "--data", str(data), "--output", o], cwd=ROOT,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
+        out[arm] = json.load(open(o))
+    nat, ref = out["native"], out["reference"]
+    assert set(nat["all"]) == set(ref["all"]) == {"vidA", "vidB"}        # vidC: see the docstring
+    for k, v in ref["avg"].items():
+        assert abs(nat["avg"][k] - v) <= 2e-5 * max(1.0, abs(v)), (k, nat["avg"][k], v)
+    for vid in ref["all"]:
+        for fn, fr in ref["all"][vid]["all"].items():
+            for k, v in fr.items():
+                got = nat["all"][vid]["all"][fn][k]
+                assert abs(got - v) <= 2e-5 * max(1.0, abs(v)), (vid, fn, k, got, v)
