@@ -269,14 +269,29 @@ def decoder_tail(mid, sd: SD, x, xb, xf, mask, window=7, p="decoder"):
     return (torch.tanh(x) + 1.0) / 2.0, attb, attf, sm
 
 
-def vmn_forward(sd: SD, frames: Sequence[torch.Tensor], masks: Sequence[torch.Tensor], window=7):
-    """VMN.forward -- VMN/VMN_model.py:83-113.  frames[i]: [B,6,H,W]; masks[i]: [B,1,H,W]."""
+def vmn_forward(sd: SD, frames: Sequence[torch.Tensor], masks: Sequence[torch.Tensor], window=7, freeze_backbone=False):
+    """VMN.forward -- VMN/VMN_model.py:83-113.  frames[i]: [B,6,H,W]; masks[i]: [B,1,H,W].
+
+    ``freeze_backbone`` (VMN_model.py:77-81,99-103, VMN_GCA.py:18-24): the encoder and the decoder's feature-extraction half
+    (layer1, layer2, gca) run in eval mode (running-statistics BatchNorm, spectral norm without a power iteration) under
+    no_grad, whatever mode the rest of the network is in."""
     S = len(frames)
     mids, feats = [], []
+    was_train = TrainMode.active
     for i in range(S):
-        emb, mid = encoder(frames[i], sd)
+        if freeze_backbone:
+            TrainMode.active = False
+            try:
+                with torch.no_grad():
+                    emb, mid = encoder(frames[i], sd)
+                    feat = decoder_head(emb, mid, sd)
+            finally:
+                TrainMode.active = was_train
+        else:
+            emb, mid = encoder(frames[i], sd)
+            feat = decoder_head(emb, mid, sd)
         mids.append(mid)
-        feats.append(decoder_head(emb, mid, sd))
+        feats.append(feat)
     preds: List[Optional[torch.Tensor]] = [None] * S
     attb: List[Optional[torch.Tensor]] = [None] * S
     attf: List[Optional[torch.Tensor]] = [None] * S
@@ -421,7 +436,7 @@ def vmd_losses(pp, preds, attb, attf, small, window=7, att_thres=0.3, label_smoo
 
 
 def full_vmd_forward(sd: SD, a, fg, bg, radii, window=7, att_thres=0.3, label_smooth=0.2, eps=0.0, train=False,
-                     rank_rows=None):
+                     rank_rows=None, freeze_backbone=False):
     """FullModel_VMD.forward for vmn_gca -- models/model.py:258-357 (single_image_loss :94-127, L_att :285-323,
     _dtSSD :326-345).  Returns the reference's 12-list.  ``train=False``: network in eval mode under no_grad
     (pred_vmn.py:107-116); ``train=True``: ``.train()`` semantics with autograd enabled (train_ddp.py:52-65) --
@@ -439,7 +454,7 @@ def full_vmd_forward(sd: SD, a, fg, bg, radii, window=7, att_thres=0.3, label_sm
         S = a.shape[1]
         frames = [pp["x6"][:, i] for i in range(S)]
         masks = [pp["trimask"][:, i] for i in range(S)]
-        preds, attb, attf, small, _ = vmn_forward(sd, frames, masks, window)
+        preds, attb, attf, small, _ = vmn_forward(sd, frames, masks, window, freeze_backbone=freeze_backbone and train)
         gts, trimask = pp["gts"], pp["trimask"]
         tris_vis = torch.where(trimask.bool(), torch.ones_like(gts) * 128 * (1.0 / 255), gts)
         if rank_rows is not None:

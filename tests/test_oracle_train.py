@@ -74,3 +74,31 @@ def test_rank_rows_emulation_is_consistent_with_the_whole_batch():
     two = O.full_vmd_forward(sd, a, fg, bg, [3] * B, train=True, rank_rows=[slice(r, r + 1) for r in range(B)])
     assert len(two[0]) == B
     assert float((two[7].detach() - whole[7].detach()).abs().max()) < 1e-6
+
+
+def test_oracle_freeze_backbone_step_matches_reference():
+    """TAM pre-training mode (freeze_backbone=True) on the well-conditioned fixture against one step of the unmodified
+    reference in that mode (tests/golden/train_step_s5_freeze.npz, make_golden.py --train-step-freeze)."""
+    g = golden("train_step_s5_freeze.npz")
+    damp = 0.04                                       # tests/golden/make_golden.py DAMP
+    sd = {k: (v * damp if (k.endswith(".bn2.weight") or k.endswith("W.1.weight")) else v).clone()
+          for k, v in fixture_sd().items()}
+    trainable = key_table()["trainable"]
+    for n in trainable:
+        sd[n].requires_grad_(True)
+    a, fg, bg = (torch.from_numpy(g[k]).float() for k in ("a", "fg", "bg"))
+    out = O.full_vmd_forward(sd, a, fg, bg, [3] * a.shape[0], train=True, freeze_backbone=True)
+    sum(w * o.mean() for w, o in zip(LOSS_WEIGHTS, out[:5])).backward()
+    np.testing.assert_allclose(np.array([float(o) for o in out[:5]]), g["losses"], rtol=1e-4, atol=1e-6)
+    assert float((out[7].detach() - torch.from_numpy(g["alphas"])).abs().max()) < 1e-4
+    nograd = set(str(x) for x in g["nograd"])
+    assert nograd and all(n.startswith(("encoder.", "decoder.layer1.", "decoder.layer2.", "decoder.gca.")) for n in nograd)
+    for n in trainable:
+        assert (sd[n].grad is None) == (n in nograd), n
+        if n not in nograd:
+            assert grad_sample_error(sd[n].grad, g["gs:" + n]) < 2e-3, n
+    for k in g.files:                                 # frozen u / v / running statistics untouched, the tail's updated
+        if k.startswith("st:"):
+            ref = torch.from_numpy(g[k])
+            got = sd[k[3:]].detach()
+            assert float((got.float() - ref.float()).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max())), k
