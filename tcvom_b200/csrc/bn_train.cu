@@ -109,7 +109,7 @@ __device__ __forceinline__ void load_res1(const tcv_bn_desc& d, int img, int y, 
   load8(p, d.res1_plane, r);
 }
 
-__global__ void __launch_bounds__(256) bn_apply_kernel(const tcv_bn_desc d) {
+__global__ void __launch_bounds__(256) bn_apply_kernel(const tcv_bn_desc d, const bool vec) {
   const int c8 = d.c / 8;
   const long long total = (long long)d.n * d.h * d.w * c8;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -123,11 +123,26 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const tcv_bn_desc d) {
   const float is = d.inv_sigma ? d.inv_sigma[g] : 1.f;
   float f[8];
   load8(reinterpret_cast<const __nv_bfloat16*>(d.z) + pix * d.c + ch, d.z_plane, f);
-  const float* mu = d.mean + g * d.c + ch;
-  const float* iv = d.invstd + g * d.c + ch;
+  // per-channel parameters as 16-byte loads: 32 scalar loads per thread (lanes 32 bytes apart -> 32 sectors per request)
+  // made the L1, not DRAM, the limit of this kernel
+  float mu[8], iv[8], ga[8], be[8];
+  if (vec) {
+    ldf8(d.mean + g * d.c + ch, mu);
+    ldf8(d.invstd + g * d.c + ch, iv);
+    ldf8(d.gamma + ch, ga);
+    ldf8(d.beta + ch, be);
+  } else {          // a parameter tensor that is not 16-byte aligned (a view into a flat buffer)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      mu[k] = d.mean[g * d.c + ch + k];
+      iv[k] = d.invstd[g * d.c + ch + k];
+      ga[k] = d.gamma[ch + k];
+      be[k] = d.beta[ch + k];
+    }
+  }
   if (d.mode == 1) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = (f[k] * is - mu[k]) * iv[k] * d.gamma[ch + k] + d.beta[ch + k];
+    for (int k = 0; k < 8; ++k) f[k] = (f[k] * is - mu[k]) * iv[k] * ga[k] + be[k];
     if (d.res1) {
       float r[8];
       load_res1(d, img, y, x, ch, r);
@@ -146,7 +161,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const tcv_bn_desc d) {
     for (int k = 0; k < 8; ++k) f[k] *= is;
     apply_act_n<8>(f, d.act);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = (f[k] - mu[k]) * iv[k] * d.gamma[ch + k] + d.beta[ch + k];
+    for (int k = 0; k < 8; ++k) f[k] = (f[k] - mu[k]) * iv[k] * ga[k] + be[k];
   }
   store8(reinterpret_cast<__nv_bfloat16*>(d.y) + pix * d.c + ch, d.y_plane, f);
 }
@@ -359,7 +374,9 @@ int tcv_bn_apply(const tcv_bn_desc* dp, tcv_stream_t stream) {
   if (rc) return rc;
   TCV_REQUIRE(d.y, "bn_apply: null output");
   const long long total = (long long)d.n * d.h * d.w * (d.c / 8);
-  bn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(d);
+  const bool vec = ((reinterpret_cast<uintptr_t>(d.mean) | reinterpret_cast<uintptr_t>(d.invstd) |
+                     reinterpret_cast<uintptr_t>(d.gamma) | reinterpret_cast<uintptr_t>(d.beta)) & 15) == 0;
+  bn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(d, vec);
   return launched("bn_apply_kernel");
 }
 

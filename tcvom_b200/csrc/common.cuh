@@ -62,6 +62,13 @@ __device__ __forceinline__ void load4(const __nv_bfloat16* hi, long long plane, 
   f[3] = __uint_as_float(a.y & 0xffff0000u) + __uint_as_float(b.y & 0xffff0000u);
 }
 
+// eight consecutive fp32 per-channel parameters (32-byte aligned) as two 16-byte loads instead of eight scalar ones
+__device__ __forceinline__ void ldf8(const float* p, float* f) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
 __device__ __forceinline__ float load1(const __nv_bfloat16* hi, long long plane) {
   return __bfloat162float(hi[0]) + __bfloat162float(hi[plane]);
 }

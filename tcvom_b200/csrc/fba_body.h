@@ -57,6 +57,19 @@ TCV_HD void ld8(const uint16_t* p, ll plane, float* f) {
   for (int i = 0; i < 8; ++i) f[i] = ld1(p + i, plane);
 #endif
 }
+// eight consecutive fp32 parameters (per-channel scale / shift, 32-byte aligned: channel offsets are multiples of 8) as two
+// 16-byte loads.  Eight scalar loads cost a warp 8 requests x 32 sectors (the lanes are 32 bytes apart): on a 64-byte-per-
+// thread streaming kernel that L1 traffic, not DRAM, set the speed (ncu: 30 sectors per load request in gn_apply).
+TCV_HD void ldf8(const float* p, float* f) {
+#ifdef __CUDA_ARCH__
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+#else
+  for (int i = 0; i < 8; ++i) f[i] = p[i];
+#endif
+}
+
 TCV_HD void st8(uint16_t* p, ll plane, const float* f) {
 #ifdef __CUDA_ARCH__
   uint32_t h[4], l[4];
@@ -140,13 +153,25 @@ struct GnApplyP {
 // work item = 8 channels of one pixel; total = n * pixels * c / 8
 TCV_HD void gn_apply_body(ll i, const GnApplyP& p) {
   const int cv = p.c / 8;
-  const ll pix = i / cv;
-  const int ch = (int)(i % cv) * 8;
-  const int img = (int)(pix / p.pixels);
+  ll pix;
+  int ch, img;
+  if ((ll)p.n * p.pixels * cv < (1ll << 32)) {
+    // 32-bit index arithmetic: three 64-bit divisions (~100 instructions each on the GPU) made this 64-byte-per-thread
+    // streaming kernel instruction-bound at 55 % of the copy bandwidth
+    const unsigned iu = (unsigned)i, pu = iu / (unsigned)cv;
+    ch = (int)(iu - pu * (unsigned)cv) * 8;
+    img = (int)(pu / (unsigned)p.pixels);
+    pix = pu;
+  } else {
+    pix = i / cv;
+    ch = (int)(i % cv) * 8;
+    img = (int)(pix / p.pixels);
+  }
   float f[8];
   ld8(p.x + pix * p.c + ch, p.x_plane, f);
-  const float* sc = p.scale + (ll)img * p.c + ch;
-  const float* sh = p.shift + (ll)img * p.c + ch;
+  float sc[8], sh[8];
+  ldf8(p.scale + (ll)img * p.c + ch, sc);
+  ldf8(p.shift + (ll)img * p.c + ch, sh);
   for (int k = 0; k < 8; ++k) f[k] = f[k] * sc[k] + sh[k];
   if (p.res) {
     float r[8];
@@ -692,7 +717,9 @@ TCV_HD void dwconv3x3_body(ll i, const DwConvP& p) {
     if (yy >= 0 && yy < p.h && xx >= 0 && xx < p.w) {
       ld8(p.x + (((ll)img * p.h + yy) * p.w + xx) * p.c + ch, plane, f);
     } else {
-      for (int j = 0; j < 8; ++j) f[j] = p.border ? p.border[ch + j] : 0.f;
+      if (p.border) ldf8(p.border + ch, f);
+      else
+        for (int j = 0; j < 8; ++j) f[j] = 0.f;
     }
     float wv[8];
 #ifdef __CUDA_ARCH__
@@ -706,7 +733,10 @@ TCV_HD void dwconv3x3_body(ll i, const DwConvP& p) {
 #endif
     for (int j = 0; j < 8; ++j) acc[j] += f[j] * wv[j];
   }
-  for (int j = 0; j < 8; ++j) acc[j] = act_fn(acc[j] * p.scale[ch + j] + p.shift[ch + j], p.act);
+  float sc[8], sh[8];
+  ldf8(p.scale + ch, sc);
+  ldf8(p.shift + ch, sh);
+  for (int j = 0; j < 8; ++j) acc[j] = act_fn(acc[j] * sc[j] + sh[j], p.act);
   st8(p.y + (((ll)img * p.h + y) * p.w + x) * p.c + ch, plane, acc);
 }
 
