@@ -117,15 +117,18 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const uint16_t* __restric
 }
 
 // ---------------------------------------------------------------------------------- adaptive average pooling
-// grid (s*s, images, c/64); 256 threads = 32 pixel lanes x 8 channel vectors
+// grid (s*s, images, c/cw); 256 threads = (256 / (cw/8)) pixel lanes x cw/8 channel vectors.  cw = 64 channels per CTA, or 16
+// when the grid would otherwise leave most SMs idle (the 1x1 and 2x2 bins of the pyramid pooling: 96 / 384 CTAs, each walking
+// 8 / 2 MB alone -- they took most of the 1.2 ms the four pooling launches of an FBA window cost)
 __global__ void __launch_bounds__(256) adaptive_avgpool_kernel(const uint16_t* __restrict__ x, ll x_plane, int n, int h,
-                                                               int w, int c, int x_c, int x_off, int s,
+                                                               int w, int c, int x_c, int x_off, int s, int cw,
                                                                uint16_t* __restrict__ y) {
   __shared__ float red[256][9];
   const int bi = blockIdx.x / s, bj = blockIdx.x % s;
   const int img = blockIdx.y;
-  const int vec = threadIdx.x & 7, lane = threadIdx.x >> 3;
-  const int ch = blockIdx.z * 64 + vec * 8;
+  const int vecs = cw >> 3, lanes = 256 / vecs;
+  const int vec = threadIdx.x % vecs, lane = threadIdx.x / vecs;
+  const int ch = blockIdx.z * cw + vec * 8;
   const int y0 = bin_start(bi, h, s), y1 = bin_end(bi, h, s);
   const int x0 = bin_start(bj, w, s), x1 = bin_end(bj, w, s);
   const int rw = x1 - x0, cnt = (y1 - y0) * rw;
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(256) adaptive_avgpool_kernel(const uint16_t* _
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
 #pragma unroll 4
-  for (int i = lane; i < cnt; i += 32) {
+  for (int i = lane; i < cnt; i += lanes) {
     const int yy = y0 + i / rw, xx = x0 + i % rw;
     float f[8];
     ld8(x + (((ll)img * h + yy) * w + xx) * x_c + x_off + ch, x_plane, f);
@@ -143,12 +146,12 @@ __global__ void __launch_bounds__(256) adaptive_avgpool_kernel(const uint16_t* _
 #pragma unroll
   for (int k = 0; k < 8; ++k) red[threadIdx.x][k] = acc[k];
   __syncthreads();
-  if (threadIdx.x < 64) {
+  if (threadIdx.x < cw) {
     const int v = threadIdx.x >> 3, k = threadIdx.x & 7;
     float a = 0.f;
-    for (int l = 0; l < 32; ++l) a += red[l * 8 + v][k];
+    for (int l = 0; l < lanes; ++l) a += red[l * vecs + v][k];
     const ll yplane = (ll)n * s * s * c;
-    st1(y + (((ll)img * s + bi) * s + bj) * c + blockIdx.z * 64 + v * 8 + k, yplane, a / (float)cnt);
+    st1(y + (((ll)img * s + bi) * s + bj) * c + blockIdx.z * cw + v * 8 + k, yplane, a / (float)cnt);
   }
 }
 
@@ -267,8 +270,9 @@ int tcv_adaptive_avgpool(const void* x, long long x_plane, int n, int h, int w, 
   TCV_REQUIRE(x && y && n > 0 && h > 0 && w > 0 && s > 0, "adaptive_avgpool: bad arguments");
   TCV_REQUIRE(c % 64 == 0 && x_c % 8 == 0 && x_off % 8 == 0 && x_off + c <= x_c, "adaptive_avgpool: bad channels");
   if (x_plane == 0) x_plane = (long long)n * h * w * x_c;
-  dim3 grid(s * s, n, c / 64);
-  adaptive_avgpool_kernel<<<grid, 256, 0, S(stream)>>>(CU16(x), x_plane, n, h, w, c, x_c, x_off, s, U16(y));
+  const int cw = ((ll)s * s * n * (c / 64) >= 8 * 148) ? 64 : 16;
+  dim3 grid(s * s, n, c / cw);
+  adaptive_avgpool_kernel<<<grid, 256, 0, S(stream)>>>(CU16(x), x_plane, n, h, w, c, x_c, x_off, s, cw, U16(y));
   return launched("adaptive_avgpool_kernel");
 }
 
