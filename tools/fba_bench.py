@@ -11,6 +11,8 @@ from helpers import fixture_sd_fba
 H, W = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (1088, 1920)
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 GFLOP_256 = 223.1                               # SURVEY.md section 8d config 5 (reference FlopCounterMode, conv only)
+from tcvom_b200 import _cabi
+_cabi.lib().tcv_set_debug_flags(int(os.environ.get("TCV_DEBUG_FLAGS", "0")))   # measurement switches
 m = tcvom_b200.EvalModel(model="vmn_fba", agg_window=7)
 m.NET.load_state_dict(fixture_sd_fba(), strict=True)
 m = m.cuda().eval()
