@@ -7,7 +7,8 @@ lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "tcvom_b200", "li
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 PAT = collections.OrderedDict([("UTC*MMA", r"\bUTC[A-Z]*MMA"), ("UTC*MMA.2CTA", r"\bUTC[A-Z]*MMA\.2CTA"), ("LDTM", r"\bLDTM"),
                                ("UTMALDG", r"\bUTMALDG"), ("UTMALDG.2CTA", r"\bUTMALDG[.0-9A-Z]*\.2CTA"),
-                               ("UTMASTG", r"\bUTMASTG"), ("UTCBAR", r"\bUTCBAR"), ("HMMA", r"\bHMMA"), ("LDGSTS", r"\bLDGSTS")])
+                               ("UTMASTG", r"\bUTMASTG"), ("UTCBAR", r"\bUTCBAR"), ("HMMA", r"\bHMMA"), ("LDGSTS", r"\bLDGSTS"),
+                               ("LDG.256", r"\bLDG\.[.A-Z0-9]*256"), ("STG.256", r"\bSTG\.[.A-Z0-9]*256")])
 rows, cur, cnt = [], None, None
 for line in sass.splitlines():
     m = re.search(r"Function : (\S+)", line)
