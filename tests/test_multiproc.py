@@ -84,3 +84,39 @@ def test_install_hooks_reference_when_available():
         sys.path.remove(ref)
         for k in [k for k in sys.modules if k == "models" or k.startswith("models.") or k == "utils" or k.startswith("utils.")]:
             del sys.modules[k]
+
+
+def test_install_native_tam_rebinds_the_reference_decoders():
+    """install(native_tam=True): the FeatureAggregationModule name the reference decoders instantiate (VMN_DIM.py:4,99,
+    VMN_Index.py:5,10, VMN_FBA.py:3,9, VMN_GCA.py:6,15) resolves to the native operator module; the networks the reference's
+    own factory then builds carry it and still take the reference's state_dict."""
+    import sys
+    ref = os.environ.get("TCVOM_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "models")):
+        pytest.skip("reference checkout not present (GPU box)")
+    sys.path.insert(0, ref)
+    try:
+        import tcvom_b200
+        import models.VMN as V
+        from models.VMN.VMN_model import FeatureAggregationModule as RefTAM
+        factory = getattr(V.get_VMN_models, "_reference", V.get_VMN_models)
+        ref_net = factory("vmn_index", 7)
+        assert type(ref_net.decoder.fam) is RefTAM
+        tcvom_b200.install(native_tam=True)
+        for name in ("VMN_model", "VMN_DIM", "VMN_Index", "VMN_FBA", "VMN_GCA"):
+            mod = sys.modules["models.VMN." + name]
+            assert mod.FeatureAggregationModule is tcvom_b200.FeatureAggregationModule, name
+        assert tcvom_b200.FeatureAggregationModule._reference is RefTAM
+        factory = V.get_VMN_models._reference
+        for arch, chn in (("vmn_index", 32), ("vmn_dim", 256)):
+            net = factory(arch, 7)
+            assert type(net.decoder.fam) is tcvom_b200.FeatureAggregationModule
+            assert net.decoder.fam.key_conv.weight.shape == (chn, chn, 3, 3)
+            if arch == "vmn_index":
+                net.load_state_dict(ref_net.state_dict(), strict=True)
+    finally:
+        sys.path.remove(ref)
+        if hasattr(tcvom_b200.FeatureAggregationModule, "_reference"):
+            del tcvom_b200.FeatureAggregationModule._reference
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.") or k == "utils" or k.startswith("utils.")]:
+            del sys.modules[k]
