@@ -492,7 +492,8 @@ int tcv_ws_pack(const float* w, int cout, int cin, int kh, int kw, int standardi
  *  finalize: per (image, group of c/groups channels) mean / biased variance -> per (image, channel)
  *            scale = gamma*invstd, shift = beta - mean*scale  (fp32 [n][c] each)
  *  apply:    y[n][pixel][y_off + ch] (row stride y_c elements, hi/lo planes y_plane apart; 0: n*pixels*y_c)
- *            = act( x*scale + shift + res ), res split-bf16 [n][pixels][c] or NULL */
+ *            = act( x*scale + shift + res ), res split-bf16 [n][pixels][c] or NULL; scale / shift are read with 16-byte
+ *            loads: 16-byte aligned pointers (any cudaMalloc / torch allocation; c is a multiple of 8) */
 int tcv_gn_stats(const void* x, long long x_plane, int n, long long pixels, int c, double* sums, tcv_stream_t stream);
 int tcv_gn_finalize(const double* sums, int n, long long pixels, int c, int groups, const float* gamma,
                     const float* beta, float eps, float* scale, float* shift, tcv_stream_t stream);
@@ -592,7 +593,8 @@ int tcv_head_conv5_clamp01(const void* x, long long x_plane, int n, int h, int w
  *   tcv_dwconv3x3     net.py:42-44,52-54, hlaspp.py:40  depthwise 3x3 (dilation = padding = dil) + BatchNorm affine +
  *                     activation.  wt fp32 [9][c]; border fp32 [c] or NULL = value an out-of-image tap reads: the
  *                     reference's InvertedResidual pads the block input and runs its 1x1 expansion + BN + ReLU6 over the
- *                     padded tensor (net.py:62-83), so the depthwise conv sees relu6(BN shift) there, not zero
+ *                     padded tensor (net.py:62-83), so the depthwise conv sees relu6(BN shift) there, not zero.  wt / scale /
+ *                     shift / border are read with 16-byte loads (16-byte aligned pointers)
  *   tcv_index_finish  hlindex.py:155-166  four branch outputs [n,h2,w2,c] -> idx_en = softmax over the branches of
  *                     sigmoid(branch), idx_de = sigmoid(branch), both [n,2*h2,2*w2,c] (pixel shuffle: branch k lands
  *                     on sub-pixel (k / 2, k % 2))
