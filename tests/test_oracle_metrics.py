@@ -68,3 +68,31 @@ def test_argument_checks():
         metrics.frame_sums(u, u, u, flow=torch.zeros(4, 4, 2))
     with pytest.raises(RuntimeError):
         metrics.frame_sums(u, u, u)            # host tensors: there is no CPU path
+
+
+def test_oracle_matches_the_reference_functions_directly():
+    """Build container only (skipped where /root/reference is absent): the restatement against calc_metric.py's own SAD / MSE /
+    SSDA / dtSSD / MESSDdt on a fresh random case, beyond the three committed goldens."""
+    import os
+    import sys
+    ref = os.environ.get("TCVOM_REFERENCE", "/root/reference")
+    if not os.path.isfile(os.path.join(ref, "calc_metric.py")):
+        pytest.skip("reference checkout not present (GPU box)")
+    sys.path.insert(0, ref)
+    try:
+        import calc_metric as cm
+        rng = np.random.default_rng(17)
+        h, w = 120, 200
+        a8, g8, ha8, hg8 = (rng.integers(0, 256, (h, w), dtype=np.uint8) for _ in range(4))
+        tri = rng.choice(np.array([0, 128, 255], np.uint8), (h, w), p=[0.3, 0.4, 0.3])
+        flow = rng.normal(0, 6, (h, w, 2)).astype(np.float32)
+        flow[rng.random((h, w)) < 0.2] = np.nan
+        a, g, m = mo.preprocess(a8, g8, tri)
+        ha, hg, _ = mo.preprocess(ha8, hg8, tri)
+        fix, org, valid = cm.MESSDdt(a, g, m, ha, hg, torch.from_numpy(flow.copy()))
+        want = [cm.SAD(a, g, m), cm.MSE(a, g, m), cm.SSDA(a, g, m), cm.dtSSD(a, g, m, ha, hg), fix, org, int(m.sum()), valid]
+        close(mo.frame_metrics(a8, g8, tri, ha8, hg8, flow), want, 1e-6)
+    finally:
+        sys.path.remove(ref)
+        for k in [k for k in sys.modules if k in ("calc_metric", "utils") or k.startswith("utils.")]:
+            del sys.modules[k]
